@@ -1,0 +1,390 @@
+#!/usr/bin/env python3
+"""Benchmark of the batched MNA-solve hot path (BASELINE.json metric: solves/s).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload cfg2|cfg3|cfg4|cfg5]
+    python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N ...
+    python bench.py --impl reference ...     # the reference algorithm's CPU port on all host cores
+
+A "step" is one pass of the hot path over one batch: for cfg2 (default, the configuration the
+metric is quoted on) one full 1,000,001-point AC sweep of the 64-node RC ladder (Nvar = 65).
+  value      whole-job solves/s with inputs resident in HBM, CUDA-event timed, max over ranks
+  e2e        the same through the host-buffer C-ABI call (pinned host buffers, H2D + D2H inside)
+  roofline   dominant kernel vs the FP64 (AC) or HBM-write (TRAN) roofline, SURVEY.md §8(d) figures
+  cpu_baseline  oracle/oracle.c (C restatement of the reference algorithm) on a bounded sample
+Multi-GPU: every rank runs the same per-GPU workload on its own device (weak scaling, no
+collective on the data path); timing is barrier + synchronize on both sides, max over ranks.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+from spicey_b200 import workloads as W  # noqa: E402
+from spicey_b200.parsing import compute_effective_time_step, parse_netlist  # noqa: E402
+
+
+def fma_count(n):
+    return (n - 1) * n * (2 * n - 1) // 6 + n * (n - 1)
+
+
+def f_cplx(n):  # complex FMA = 8 flop, complex divide = 11
+    return 8 * fma_count(n) + 11 * (n * (n + 1) // 2)
+
+
+def read_peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as fh:
+            return json.load(fh), "measured (MEASURED_PEAKS.json)"
+    except Exception:
+        return {"hbm_gbs": 6650.0}, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
+                 "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm = [float(r[0]) for r in self.rows if len(r) >= 6 and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) >= 6 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(len(r) >= 6 and r[2 + i] == "Active" for r in self.rows)]
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(sm)}
+
+
+def dist_env():
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    return rank, local, world
+
+
+# ---- workloads --------------------------------------------------------------------------
+
+def load_workload(name, points=None, instances=None):
+    import spicey_b200 as sp
+    from spicey_b200.packing import make_sweep, pack_circuit, sample_sources, initial_state
+    wl = {"name": name}
+    if name in ("cfg2", "cfg4", "cfg1"):
+        text = {"cfg2": W.rc_ladder(64), "cfg4": W.rc_mesh(16), "cfg1": W.README_RC}[name]
+        ck = parse_netlist(text)
+        freqs = np.array(sp.analysis.ac_frequencies(ck), dtype=np.float64)
+        if points:
+            freqs = freqs[:: max(1, freqs.shape[0] // points)][:points]
+        table = pack_circuit(ck)
+        wl.update(kind="ac", ckt=ck, table=table, freqs=freqs, units=int(freqs.shape[0]), sweep=None,
+                  label={"cfg2": "cfg2: 64-node RC ladder .ac dec 200000 1 100k (1,000,001 points, Nvar=65, c128 LU)",
+                         "cfg4": "cfg4: 16x16 RC mesh .ac (Nvar=257)", "cfg1": "cfg1: README RC low-pass"}[name],
+                  flops_per_unit=f_cplx(table.nvar),
+                  bytes_per_unit=8 + 16 * table.nvar + 16 * table.n_ac_elem)
+    else:
+        text, ovf, n_full = {"cfg3": (W.RLC_TANK, W.rlc_tank_overrides, 65536),
+                             "cfg5": (W.RECTIFIER, W.rectifier_overrides, 100000)}[name]
+        n = instances or n_full
+        ck = parse_netlist(text)
+        ov = {k: v[:n] for k, v in ovf(n_full).items()}
+        dt, steps = compute_effective_time_step(ck.analyses.tran.dt, ck.analyses.tran.tstop)
+        table = pack_circuit(ck)
+        vsrc, mask = sample_sources(ck, dt, steps)
+        wl.update(kind="tran", ckt=ck, table=table, dt=dt, steps=steps, vsrc=vsrc, mask=mask, overrides=ov,
+                  sweep=make_sweep(table, n, ov), n_inst=n, units=n * (steps + 1),
+                  state0=initial_state(ck, table, n),
+                  label="%s: %s, %d instances x %d recorded steps (Nvar=%d, f64)" % (
+                      name, "RLC tank .tran 1u 1m Monte-Carlo" if name == "cfg3" else "diode half-wave rectifier .tran 1u 3m sweep",
+                      n, steps + 1, table.nvar),
+                  flops_per_unit=55, bytes_per_unit=8 * (table.n_nodes + table.n_elem))
+    return wl
+
+
+# ---- reference arm: the reference algorithm's CPU port on all host cores ------------------
+
+def cpu_rate(wl, target_s=12.0, threads=None):
+    """solves/s of oracle/oracle.c on a bounded sample of the workload (about target_s of CPU work)."""
+    from oracle import c_oracle as co
+    threads = threads or os.cpu_count() or 1
+    if wl["kind"] == "ac":
+        freqs = wl["freqs"]
+        probe = freqs[:: max(1, len(freqs) // (64 * threads))][: 64 * threads]
+        t0 = time.perf_counter()
+        co.ac_solve(wl["ckt"], probe, nthreads=threads)
+        rate = len(probe) / max(1e-9, time.perf_counter() - t0)
+        n = int(min(len(freqs), max(len(probe), rate * target_s)))
+        stride = max(1, len(freqs) // n)
+        sample = freqs[::stride][:n]
+        t0 = time.perf_counter()
+        co.ac_solve(wl["ckt"], sample, nthreads=threads)
+        dt = time.perf_counter() - t0
+        return len(sample) / dt, threads, "every %d-th of %d frequencies (%d points, %.1f s)" % (
+            stride, len(freqs), len(sample), dt)
+    n = min(wl["n_inst"], 8 * threads)
+    ov = {k: v[:n] for k, v in wl["overrides"].items()}
+    t0 = time.perf_counter()
+    co.tran_solve(wl["ckt"], wl["dt"], wl["steps"], n_inst=n, overrides=ov, nthreads=threads)
+    rate = n / max(1e-9, time.perf_counter() - t0)
+    n2 = int(min(wl["n_inst"], max(n, rate * target_s)))
+    ov = {k: v[:n2] for k, v in wl["overrides"].items()}
+    t0 = time.perf_counter()
+    _, _, iters, _, _ = co.tran_solve(wl["ckt"], wl["dt"], wl["steps"], n_inst=n2, overrides=ov, nthreads=threads)
+    dt = time.perf_counter() - t0
+    return n2 * (wl["steps"] + 1) / dt, threads, "first %d of %d instances (%d recorded steps, %.1f s)" % (
+        n2, wl["n_inst"], n2 * (wl["steps"] + 1), dt)
+
+
+def run_reference(args):
+    rank, local, world = dist_env()
+    if rank != 0:
+        return
+    wl = load_workload(args.workload, args.points, args.instances)
+    for _ in range(max(0, min(args.warmup, 1))):
+        cpu_rate(wl, target_s=0.5)
+    rates, sample = [], ""
+    per_step = max(2.0, min(15.0, 120.0 / max(1, args.steps)))
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        r, threads, sample = cpu_rate(wl, target_s=per_step)
+        rates.append(r)
+    value = float(np.mean(rates))
+    line = {
+        "impl": "reference", "metric": "batched MNA solves/sec", "value": value, "unit": "solves/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": 1e3 * (time.perf_counter() - t0) / max(1, args.steps), "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "c128" if wl["kind"] == "ac" else "f64",
+        "data": "synthetic", "config": {"workload": wl["label"]},
+        "cpu_baseline": {"value": value, "unit": "solves/s", "cores": threads, "kind": "port", "sample": sample,
+                         "note": "C restatement of the reference algorithm (oracle/oracle.c); the reference itself "
+                                 "is TypeScript and no JS runtime exists in this image"},
+        "e2e": {"value": value, "unit": "solves/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line))
+
+
+# ---- native arm -------------------------------------------------------------------------
+
+def run_native(args):
+    import torch
+    import torch.distributed as dist
+    import spicey_b200 as sp
+    from spicey_b200 import native
+
+    rank, local, world = dist_env()
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device — the product has no CPU path (use --impl reference for the CPU port)")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    dev = torch.device("cuda", local)
+    eng = native.Engine([local])
+    wl = load_workload(args.workload, args.points, args.instances)
+    table = wl["table"]
+    stream = torch.cuda.current_stream()
+    peaks, peak_src = read_peaks()
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    launches = 0
+    if wl["kind"] == "ac":
+        P = wl["units"]
+        d_freqs = torch.from_numpy(wl["freqs"]).to(dev)
+        d_x = torch.empty((P, table.nvar), dtype=torch.complex128, device=dev)
+        d_i = torch.empty((P, table.n_ac_elem), dtype=torch.complex128, device=dev)
+        d_s = torch.empty(P, dtype=torch.int32, device=dev)
+
+        def step_resident():
+            eng.ac_solve_device(table, d_freqs.data_ptr(), P, d_x.data_ptr(), d_i.data_ptr(), d_s.data_ptr(),
+                                stream=stream.cuda_stream)
+
+        h_freqs, p0 = native.pinned_empty(eng.lib, (P,), np.float64)
+        h_freqs[:] = wl["freqs"]
+        h_x, p1 = native.pinned_empty(eng.lib, (P, table.nvar), np.complex128)
+        h_i, p2 = native.pinned_empty(eng.lib, (P, table.n_ac_elem), np.complex128)
+        h_s, p3 = native.pinned_empty(eng.lib, (P,), np.int32)
+        pins = [p0, p1, p2, p3]
+
+        def step_e2e():
+            eng.ac_solve(table, h_freqs, out=(h_x, h_i, h_s))
+            return int(h_s.max())
+
+        def check():
+            assert int(d_s.max().item()) == 0, "non-zero status in bench run"
+        working_set = P * wl["bytes_per_unit"]
+    else:
+        n, S1 = wl["n_inst"], wl["steps"] + 1
+        sweep = wl["sweep"]
+        d_var = torch.from_numpy(sweep.var_values).to(dev)
+        d_vsrc = torch.from_numpy(wl["vsrc"]).to(dev)
+        d_st0 = torch.from_numpy(wl["state0"]).to(dev)
+        d_v = torch.empty((S1, table.n_nodes, n), dtype=torch.float64, device=dev)
+        d_i = torch.empty((S1, table.n_elem, n), dtype=torch.float64, device=dev)
+        d_s = torch.empty(n, dtype=torch.int32, device=dev)
+
+        def step_resident():
+            eng.tran_solve_device(table, wl["dt"], wl["steps"], d_vsrc.data_ptr(), wl["mask"], d_st0.data_ptr(),
+                                  d_v.data_ptr(), d_i.data_ptr(), None, None, d_s.data_ptr(), sweep=sweep,
+                                  d_var_values=d_var.data_ptr(), stream=stream.cuda_stream)
+
+        h_v, p1 = native.pinned_empty(eng.lib, (S1, table.n_nodes, n), np.float64)
+        h_i, p2 = native.pinned_empty(eng.lib, (S1, table.n_elem, n), np.float64)
+        pins = [p1, p2]
+
+        def step_e2e():
+            r = eng.tran_solve(table, wl["dt"], wl["steps"], vsrc=wl["vsrc"], vsrc_mask=wl["mask"], sweep=sweep,
+                               state0=wl["state0"], out=(h_v, h_i))
+            return int(r["status"].max())
+
+        def check():
+            assert int(d_s.max().item()) == 0, "non-zero status in bench run"
+        working_set = wl["units"] * wl["bytes_per_unit"]
+
+    # ---- device-resident timing (value) ----
+    for _ in range(args.warmup):
+        step_resident()
+    barrier()
+    check()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record(stream)
+    for k in range(args.steps):
+        ev[k][0].record(stream)
+        step_resident()
+        ev[k][1].record(stream)
+        launches += eng.stats()["kernel_launches"]
+    e1.record(stream)
+    barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    total_ms = e0.elapsed_time(e1)
+    kern_ms = float(np.mean([a.elapsed_time(b) for a, b in ev]))
+    tier = eng.stats()["tier"]
+    check()
+    t = torch.tensor([total_ms, kern_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    total_ms, kern_ms = float(t[0]), float(t[1])
+
+    # ---- end-to-end through the host-buffer C ABI ----
+    e2e_steps = max(1, min(args.steps, 3))
+    step_e2e()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        st = step_e2e()
+        assert st == 0
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    es = eng.stats()
+    t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.barrier()
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_s = float(t[0])
+    fp64_peak = eng.fp64_peak_gflops() / 1e3  # TFLOP/s, own DFMA-loop microbenchmark
+
+    if rank == 0:
+        units = wl["units"]
+        value = world * units * args.steps / (total_ms * 1e-3)
+        if wl["kind"] == "ac":
+            ach = units * wl["flops_per_unit"] / (kern_ms * 1e-3) / 1e12
+            roof = {"bound": "fp64", "achieved": ach, "peak": fp64_peak, "unit": "TFLOP/s", "frac": ach / fp64_peak,
+                    "traffic": None,
+                    "peak_source": "own DFMA-loop microbenchmark in this run (MEASURED_PEAKS.json has no FP64 figure)",
+                    "flops_per_solve_dense": wl["flops_per_unit"],
+                    "note": "achieved counts the DENSE algorithmic flops of SURVEY.md 8(d) per solve; the kernel "
+                            "skips structurally zero multipliers/columns as the reference's |f|<EPS shortcut does, "
+                            "so executed DFMA is lower (profiles/)"}
+        else:
+            ach = units * wl["bytes_per_unit"] / (kern_ms * 1e-3) / 1e9
+            peak = float(peaks.get("hbm_gbs", 6650.0))
+            roof = {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+                    "traffic": None, "peak_source": peak_src}
+        tr = os.path.join(ROOT, "profiles", "traffic_%s.json" % wl["name"])
+        if os.path.exists(tr):
+            try:
+                roof["traffic"] = json.load(open(tr)).get("dram_bytes_per_launch")
+            except Exception:
+                pass
+        cpu_v, cores, sample = cpu_rate(wl, target_s=12.0)
+        line = {
+            "metric": "batched MNA solves/sec", "value": value, "unit": "solves/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": total_ms / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "c128" if wl["kind"] == "ac" else "f64", "data": "synthetic",
+            "config": {"workload": wl["label"], "per_gpu_units_per_step": units, "tier": tier,
+                       "l2": "no flush: each step writes %.2f GB of results, larger than the 126 MB L2" % (
+                           working_set / 1e9),
+                       "parallelism": "replicated sweep per GPU, contiguous ranges, no collective"},
+            "kernel_ms_per_step": kern_ms,
+            "roofline": roof,
+            "cpu_baseline": {"value": cpu_v, "unit": "solves/s", "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": world * units * e2e_steps / e2e_s, "unit": "solves/s",
+                    "h2d_bytes_per_step": int(es["h2d_bytes"]), "d2h_bytes_per_step": int(es["d2h_bytes"]),
+                    "steps": e2e_steps, "kernel_ms_per_step": es["kernel_ms"]},
+            "gpu_launches": int(launches),
+            "clocks": clocks,
+        }
+        print(json.dumps(line))
+    for p in pins:
+        eng.lib.spicey_host_free(p)
+    eng.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="native", choices=["native", "reference"])
+    ap.add_argument("--workload", default="cfg2", choices=["cfg1", "cfg2", "cfg3", "cfg4", "cfg5"])
+    ap.add_argument("--points", type=int, default=None, help="AC: subsample to this many frequency points")
+    ap.add_argument("--instances", type=int, default=None, help="TRAN: number of instances")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_native(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,206 @@
+/*
+ * spicey_native.h — C ABI of the B200-native batched MNA solve engine.
+ *
+ * This is the drop-in boundary for the reference's hot path (SURVEY.md §8 b).  The
+ * reference (tscircuit/spicey, TypeScript) has no FFI of its own; the seam is its
+ * exported functions, so each entry point below names the reference code it replaces:
+ *
+ *   spicey_ac_solve    replaces the body of the per-frequency loop of simulateAC
+ *                      (lib/analysis/simulateAC.ts:80-127): buildLinearSystemForAC
+ *                      (:24-60, lib/stamping/stamp*Complex.ts), solveComplex
+ *                      (lib/math/solveComplex.ts:4-73, lib/math/Complex.ts) and the
+ *                      node-voltage / element-current unpack (:85-126).
+ *   spicey_tran_solve  replaces the time-step loop of simulateTRAN
+ *                      (lib/analysis/simulateTRAN.ts:146-238): stampAllElementsAtTime
+ *                      (:25-102, lib/stamping/stamp*Real.ts), solveReal
+ *                      (lib/math/solveReal.ts:3-73), updateSwitchStatesFromSolution
+ *                      (:108-128), the recording (:164-219) and state update (:221-237).
+ *
+ * The host side (netlist parsing, frequency list, step count, waveform sampling, result
+ * objects) stays in the caller's language; lib/native binds this header with bun:ffi
+ * (INTEGRATION.md), spicey_b200/native.py binds it with ctypes.
+ *
+ * Conventions
+ *  - Plain pointers and sizes only.  The caller owns every buffer; the library never
+ *    keeps a host pointer after a call returns and never returns memory to be freed
+ *    (except spicey_host_alloc / spicey_host_free, an optional pinned-buffer helper).
+ *  - All floating point is IEEE binary64.  Complex numbers are interleaved (re, im).
+ *  - Call-level failures return a non-zero code; text via spicey_last_error().
+ *    Per-instance numerical failures (the reference's synchronous throws) are reported
+ *    in status[] with SPICEY_ST_*; the wrapper re-throws the reference's message for
+ *    the first failing index.  One bad instance never poisons a batch.
+ *  - A handle is safe for one caller at a time.  There is NO CPU fallback: every
+ *    solve entry point fails with SPICEY_ERR_NO_DEVICE when no CUDA device is usable.
+ */
+#ifndef SPICEY_NATIVE_H
+#define SPICEY_NATIVE_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SPICEY_NATIVE_ABI_VERSION 1
+
+/* Element kinds of the flat element table (ParsedCircuit, lib/parsing/parseNetlist.ts:12-105). */
+enum {
+  SPICEY_ELEM_R = 0, /* values: R                         (ParsedResistor  :12)   */
+  SPICEY_ELEM_C = 1, /* values: C            state: vPrev (ParsedCapacitor :13-19) */
+  SPICEY_ELEM_L = 2, /* values: L            state: iPrev (ParsedInductor  :20-26) */
+  SPICEY_ELEM_V = 3, /* values: dc, acMag, acPhaseDeg     (ParsedVoltageSource :34-43) */
+  SPICEY_ELEM_S = 4, /* values: Ron, Roff, Von, Voff  state: isOn (ParsedSwitch :62-71) */
+  SPICEY_ELEM_D = 5  /* values: Is, N        state: vdPrev (ParsedDiode :53-60)   */
+};
+
+/* Per-instance status, mapped by the wrapper to the reference's error messages. */
+enum {
+  SPICEY_ST_OK = 0,
+  SPICEY_ST_SINGULAR = 1,   /* "Singular matrix (complex|real)"  solveComplex.ts:29 / solveReal.ts:28 */
+  SPICEY_ST_CDIV = 2,       /* "Complex divide by ~0"            Complex.ts:42 */
+  SPICEY_ST_R_NONPOS = 3    /* "R <name> must be > 0"            simulateAC.ts:37 (AC only) */
+};
+
+/* Call-level return codes. */
+enum {
+  SPICEY_SUCCESS = 0,
+  SPICEY_ERR_INVALID = 1,    /* bad argument / malformed table */
+  SPICEY_ERR_NO_DEVICE = 2,  /* no usable CUDA device: there is no CPU path */
+  SPICEY_ERR_CUDA = 3,       /* CUDA runtime error (text in spicey_last_error) */
+  SPICEY_ERR_UNSUPPORTED = 4 /* system larger than the largest kernel tier */
+};
+
+/*
+ * Flat element table (struct of arrays).  Elements are grouped by kind in the order
+ * R, C, L, V, S, D and keep netlist order inside a kind — the order in which the
+ * reference pushes element currents (simulateAC.ts:94-126, simulateTRAN.ts:173-219).
+ * Node ids are the reference's: 0 is ground, the matrix row of node id is id-1
+ * (NodeIndex.ts:28-31); the k-th V element owns branch row n_nodes + k
+ * (parseNetlist.ts:455-460).
+ */
+typedef struct spicey_elem_table {
+  int32_t n_nodes;          /* non-ground nodes (nn) */
+  int32_t n_elem;
+  int32_t n_values;         /* length of values[] */
+  int32_t reserved;
+  const int32_t* type;      /* [n_elem] SPICEY_ELEM_* (grouped, see above) */
+  const int32_t* n1;        /* [n_elem] first node  (n1 / nPlus) */
+  const int32_t* n2;        /* [n_elem] second node (n2 / nMinus) */
+  const int32_t* nc1;       /* [n_elem] switch control + (ncPos), else 0 */
+  const int32_t* nc2;       /* [n_elem] switch control - (ncNeg), else 0 */
+  const int32_t* value_idx; /* [n_elem] first slot of the element in values[] */
+  const double* values;     /* [n_values] nominal values, slots per kind as listed above */
+} spicey_elem_table;
+
+/*
+ * Sweep / Monte-Carlo batch: n_inst instances of the same topology whose value slots
+ * var_slot[v] take per-instance values var_values[v*n_inst + inst].  NULL or n_inst==1
+ * with n_var==0 means one nominal instance.
+ */
+typedef struct spicey_sweep {
+  int64_t n_inst;
+  int32_t n_var;
+  int32_t reserved;
+  const int32_t* var_slot;   /* [n_var] indices into values[] */
+  const double* var_values;  /* [n_var][n_inst] */
+} spicey_sweep;
+
+/* Counters of the most recent solve call on a handle (all devices of the handle). */
+typedef struct spicey_stats {
+  double kernel_ms;          /* CUDA-event time of the solve kernels, max over devices */
+  double total_ms;           /* host wall time of the call */
+  int64_t kernel_launches;   /* kernels of this library launched by the call */
+  int64_t h2d_bytes;
+  int64_t d2h_bytes;
+  int64_t solves;            /* AC points, or TRAN matrix solves (sum of re-solve iterations) */
+  int32_t tier;              /* kernel tier used (SPICEY_TIER_*) */
+  int32_t n_devices;
+} spicey_stats;
+
+enum {
+  SPICEY_TIER_THREAD = 1,    /* one thread per system (Nvar <= 16) */
+  SPICEY_TIER_CTA_SMEM = 2,  /* one CTA per system, matrix resident in shared memory */
+  SPICEY_TIER_CTA_GMEM = 3   /* one CTA per system, matrix in an L2-resident global scratch */
+};
+
+typedef struct spicey_handle spicey_handle;
+
+int32_t spicey_native_abi_version(void);
+/* Number of usable CUDA devices (0 when none). */
+int32_t spicey_device_count(void);
+/* Text of the last call-level error on this thread ("" when none). */
+const char* spicey_last_error(void);
+
+/* devices == NULL or n_devices <= 0 selects device 0. Work is sharded across the
+ * handle's devices in contiguous index ranges (SURVEY.md §8 e); no collective. */
+int32_t spicey_create(const int32_t* devices, int32_t n_devices, spicey_handle** out);
+void spicey_destroy(spicey_handle* h);
+int32_t spicey_get_stats(const spicey_handle* h, spicey_stats* out);
+
+/* Optional page-locked host buffers for the caller's inputs/outputs (faster copies). */
+void* spicey_host_alloc(int64_t bytes);
+void spicey_host_free(void* p);
+
+/*
+ * AC small-signal batch.  Point p = inst*n_freq + k solves the complex MNA system of
+ * instance inst at freqs[k].  Nvar = n_nodes + nV.  S and D elements are ignored, as in
+ * the reference (simulateAC.ts:36-57).
+ *   x      [n_inst*n_freq][Nvar][2]    solution: node voltages then V branch currents
+ *   ielem  [n_inst*n_freq][nAc][2]     currents of the R, C, L, V elements in table order
+ *                                      (nAc = their count); may be NULL
+ *   status [n_inst*n_freq]             SPICEY_ST_*; rows of a failed point are NaN
+ * Host pointers.  flags: SPICEY_FLAG_*.
+ */
+int32_t spicey_ac_solve(spicey_handle* h, const spicey_elem_table* table, const spicey_sweep* sweep,
+                        const double* freqs, int64_t n_freq, double* x, double* ielem,
+                        int32_t* status, uint32_t flags);
+
+/* Same, on ONE device with device pointers (freqs, sweep->var_values, x, ielem, status
+ * live on device devices[dev_index]); the table arrays stay on the host.  Launches on
+ * `stream` (a cudaStream_t, NULL = default stream) and does not synchronise. */
+int32_t spicey_ac_solve_device(spicey_handle* h, int32_t dev_index, const spicey_elem_table* table,
+                               const spicey_sweep* sweep, const double* d_freqs, int64_t n_freq,
+                               double* d_x, double* d_ielem, int32_t* d_status, uint32_t flags,
+                               void* stream);
+
+/*
+ * Transient batch: fixed-step backward Euler from state0, steps+1 recorded samples
+ * (t_k = k*dt, k = 0..steps; dt and steps come from computeEffectiveTimeStep on the
+ * host, simulateTRAN.ts:14-19 — hazard H2).  The re-solve policy is the reference's:
+ * another iteration only while a switch toggled, at most 20 (simulateTRAN.ts:151-162).
+ *   vsrc      [nV][steps+1] pre-sampled waveform(t_k) per V element (NULL if none)
+ *   vsrc_mask [nV] non-zero: use vsrc row; zero: use the element's dc value
+ *   state0    [nState][n_inst] initial vPrev/iPrev/isOn/vdPrev of the C, L, S, D
+ *             elements in table order; NULL = all zero / off
+ *   v         [steps+1][n_nodes][n_inst]   node voltages
+ *   ielem     [steps+1][n_elem][n_inst]    element currents, table order; may be NULL
+ *   state_out [nState][n_inst]             final state (the reference mutates ckt); may be NULL
+ *   iters     [steps+1][n_inst]            solves done per step; may be NULL
+ *   status    [n_inst]
+ */
+int32_t spicey_tran_solve(spicey_handle* h, const spicey_elem_table* table, const spicey_sweep* sweep,
+                          double dt, int64_t steps, const double* vsrc, const int32_t* vsrc_mask,
+                          const double* state0, double* v, double* ielem, double* state_out,
+                          int32_t* iters, int32_t* status, uint32_t flags);
+
+int32_t spicey_tran_solve_device(spicey_handle* h, int32_t dev_index, const spicey_elem_table* table,
+                                 const spicey_sweep* sweep, double dt, int64_t steps,
+                                 const double* d_vsrc, const int32_t* vsrc_mask /* host */,
+                                 const double* d_state0, double* d_v, double* d_ielem,
+                                 double* d_state_out, int32_t* d_iters, int32_t* d_status,
+                                 uint32_t flags, void* stream);
+
+enum {
+  SPICEY_FLAG_STRICT = 1u,      /* reference-order, unfused arithmetic (slow; parity testing) */
+  SPICEY_FLAG_FORCE_GMEM = 2u,  /* testing: force the global-scratch tier */
+  SPICEY_FLAG_FORCE_CTA = 4u    /* testing: force a CTA tier even for tiny systems */
+};
+
+/* Measures this GPU's FP64 FMA peak with a register-only DFMA loop (GFLOP/s), the
+ * denominator the FP64-bound roofline is reported against. */
+int32_t spicey_measure_fp64_peak(spicey_handle* h, int32_t dev_index, double* gflops_out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SPICEY_NATIVE_H */

@@ -1,0 +1,774 @@
+// C ABI of the B200-native batched MNA engine (include/spicey_native.h).
+//
+// Host side of the hot path: validates the flat element table, builds the per-topology
+// plan (gather-form stamping lists + structural row masks), uploads it, picks the kernel
+// tier, shards the batch axis over the handle's devices in contiguous ranges and, for the
+// host-buffer entry points, pipelines kernel chunks against device->host copies on a
+// second stream.  No CPU compute path exists here: without a CUDA device every solve
+// entry point fails with SPICEY_ERR_NO_DEVICE.
+#include "../../include/spicey_native.h"
+
+#include <algorithm>
+#include <chrono>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "ac_kernels.cuh"
+#include "tran_kernels.cuh"
+
+using namespace spicey;
+
+namespace {
+
+thread_local std::string g_err;
+
+int fail(int code, const std::string& msg) {
+  g_err = msg;
+  return code;
+}
+
+#define CUDA_TRY(expr)                                                                  \
+  do {                                                                                  \
+    cudaError_t _e = (expr);                                                            \
+    if (_e != cudaSuccess)                                                              \
+      return fail(SPICEY_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(_e)); \
+  } while (0)
+
+// ---------------------------------------------------------------------------------
+// Host plan
+struct HostGather {
+  std::vector<int> row_ptr, ent_col, ent_ptr, contrib;
+  std::vector<unsigned> rowmask;
+};
+
+struct HostPlan {
+  int nn = 0, nV = 0, nvar = 0, n_elem = 0, n_values = 0, n_ac_elem = 0, n_state = 0, MW = 0;
+  int off[7] = {0, 0, 0, 0, 0, 0, 0};
+  std::vector<int4> ends;
+  std::vector<int2> meta;
+  std::vector<int> state_idx;
+  std::vector<double> values;
+  std::vector<int> var_of_slot;
+  HostGather ac, tran;
+};
+
+const int kValueSlots[6] = {1, 1, 1, 3, 4, 2};
+
+struct GatherBuilder {
+  int nvar;
+  std::map<std::pair<int, int>, std::vector<int>> ent;  // (row, col) -> ordered contributions
+  explicit GatherBuilder(int n) : nvar(n) {}
+  void add(int row, int col, int idx, int src, bool neg) {
+    ent[std::make_pair(row, col)].push_back((idx << 3) | (src << 1) | (neg ? 1 : 0));
+  }
+  // stampAdmittance{Real,Complex}.ts: +Y (i1,i1), +Y (i2,i2), -Y (i1,i2), -Y (i2,i1); ground skipped.
+  void admittance(int e, int n1, int n2) {
+    int i1 = n1 - 1, i2 = n2 - 1;
+    if (i1 >= 0) add(i1, i1, e, SRC_Y, false);
+    if (i2 >= 0) add(i2, i2, e, SRC_Y, false);
+    if (i1 >= 0 && i2 >= 0) { add(i1, i2, e, SRC_Y, true); add(i2, i1, e, SRC_Y, true); }
+  }
+  // stampCurrentReal.ts: b[n+] -= I, b[n-] += I.
+  void current(int e, int np, int nm) {
+    int ip = np - 1, im = nm - 1;
+    if (ip >= 0) add(ip, nvar, e, SRC_J, true);
+    if (im >= 0) add(im, nvar, e, SRC_J, false);
+  }
+  // stampVoltageSource{Real,Complex}.ts: +-1 in column/row j, b[j] += V.
+  void vsource(int e, int n1, int n2, int j) {
+    int i1 = n1 - 1, i2 = n2 - 1;
+    if (i1 >= 0) add(i1, j, 0, SRC_ONE, false);
+    if (i2 >= 0) add(i2, j, 0, SRC_ONE, true);
+    if (i1 >= 0) add(j, i1, 0, SRC_ONE, false);
+    if (i2 >= 0) add(j, i2, 0, SRC_ONE, true);
+    add(j, nvar, e, SRC_J, false);
+  }
+  void finish(HostGather& g, int MW) const {
+    g.row_ptr.assign(nvar + 1, 0);
+    g.rowmask.assign((size_t)nvar * MW, 0u);
+    g.ent_ptr.push_back(0);
+    int row = 0;
+    for (const auto& kv : ent) {
+      int r = kv.first.first, c = kv.first.second;
+      while (row < r) g.row_ptr[++row] = (int)g.ent_col.size();
+      g.ent_col.push_back(c);
+      for (int w : kv.second) g.contrib.push_back(w);
+      g.ent_ptr.push_back((int)g.contrib.size());
+      g.rowmask[(size_t)r * MW + (c >> 5)] |= 1u << (c & 31);
+    }
+    while (row < nvar) g.row_ptr[++row] = (int)g.ent_col.size();
+  }
+};
+
+int build_plan(const spicey_elem_table* tb, const spicey_sweep* sw, HostPlan& hp) {
+  if (!tb) return fail(SPICEY_ERR_INVALID, "element table is NULL");
+  if (tb->n_nodes < 0 || tb->n_elem < 0 || tb->n_values < 0)
+    return fail(SPICEY_ERR_INVALID, "negative size in element table");
+  if (tb->n_elem > 0 && (!tb->type || !tb->n1 || !tb->n2 || !tb->value_idx || !tb->values))
+    return fail(SPICEY_ERR_INVALID, "element table array is NULL");
+  hp.nn = tb->n_nodes;
+  hp.n_elem = tb->n_elem;
+  hp.n_values = tb->n_values;
+  hp.ends.resize(hp.n_elem);
+  hp.meta.resize(hp.n_elem);
+  hp.state_idx.assign(hp.n_elem, -1);
+  int prev = 0, ns = 0;
+  int count[6] = {0, 0, 0, 0, 0, 0};
+  for (int e = 0; e < hp.n_elem; ++e) {
+    int ty = tb->type[e];
+    if (ty < 0 || ty > 5) return fail(SPICEY_ERR_INVALID, "unknown element type");
+    if (ty < prev) return fail(SPICEY_ERR_INVALID, "elements must be grouped in the order R,C,L,V,S,D");
+    prev = ty;
+    count[ty]++;
+    int n1 = tb->n1[e], n2 = tb->n2[e];
+    int c1 = (ty == ELEM_S && tb->nc1) ? tb->nc1[e] : 0, c2 = (ty == ELEM_S && tb->nc2) ? tb->nc2[e] : 0;
+    if (n1 < 0 || n1 > hp.nn || n2 < 0 || n2 > hp.nn || c1 < 0 || c1 > hp.nn || c2 < 0 || c2 > hp.nn)
+      return fail(SPICEY_ERR_INVALID, "node id out of range");
+    int vi = tb->value_idx[e];
+    if (vi < 0 || vi + kValueSlots[ty] > hp.n_values) return fail(SPICEY_ERR_INVALID, "value_idx out of range");
+    hp.ends[e] = make_int4(n1, n2, c1, c2);
+    hp.meta[e] = make_int2(ty, vi);
+    if (ty == ELEM_C || ty == ELEM_L || ty == ELEM_S || ty == ELEM_D) hp.state_idx[e] = ns++;
+  }
+  hp.n_state = ns;
+  hp.off[0] = 0;
+  for (int k = 0; k < 6; ++k) hp.off[k + 1] = hp.off[k] + count[k];
+  hp.nV = count[ELEM_V];
+  hp.nvar = hp.nn + hp.nV;
+  hp.n_ac_elem = hp.off[ELEM_V + 1];
+  hp.MW = (hp.nvar + 1 + 31) / 32;
+  hp.values.assign(tb->values, tb->values + hp.n_values);
+  hp.var_of_slot.assign(hp.n_values, -1);
+  if (sw) {
+    if (sw->n_inst < 1 || sw->n_var < 0) return fail(SPICEY_ERR_INVALID, "bad sweep sizes");
+    if (sw->n_var > 0 && (!sw->var_slot || !sw->var_values)) return fail(SPICEY_ERR_INVALID, "sweep array is NULL");
+    for (int v = 0; v < sw->n_var; ++v) {
+      int s = sw->var_slot[v];
+      if (s < 0 || s >= hp.n_values) return fail(SPICEY_ERR_INVALID, "sweep slot out of range");
+      hp.var_of_slot[s] = v;
+    }
+  }
+  if (hp.nvar < 1) return fail(SPICEY_ERR_INVALID, "circuit has no unknowns");
+  if (hp.nvar > 1024) return fail(SPICEY_ERR_UNSUPPORTED, "Nvar > 1024 exceeds the largest kernel tier");
+
+  GatherBuilder ac(hp.nvar), tr(hp.nvar);
+  // AC stamping order R, C, L, V (simulateAC.ts:36-57); S and D are not stamped.
+  for (int e = 0; e < hp.n_ac_elem; ++e) {
+    int ty = hp.meta[e].x;
+    if (ty == ELEM_V) ac.vsource(e, hp.ends[e].x, hp.ends[e].y, hp.nn + (e - hp.off[ELEM_V]));
+    else ac.admittance(e, hp.ends[e].x, hp.ends[e].y);
+  }
+  // TRAN stamping order R, C, L, S, V, D (simulateTRAN.ts:35-101).
+  const int order[6] = {ELEM_R, ELEM_C, ELEM_L, ELEM_S, ELEM_V, ELEM_D};
+  for (int oi = 0; oi < 6; ++oi) {
+    int ty = order[oi];
+    for (int e = hp.off[ty]; e < hp.off[ty + 1]; ++e) {
+      int n1 = hp.ends[e].x, n2 = hp.ends[e].y;
+      if (ty == ELEM_V) { tr.vsource(e, n1, n2, hp.nn + (e - hp.off[ELEM_V])); continue; }
+      tr.admittance(e, n1, n2);
+      if (ty == ELEM_C || ty == ELEM_L || ty == ELEM_D) tr.current(e, n1, n2);
+    }
+  }
+  ac.finish(hp.ac, hp.MW);
+  tr.finish(hp.tran, hp.MW);
+  return SPICEY_SUCCESS;
+}
+
+// ---------------------------------------------------------------------------------
+// Device context
+struct Buffer {
+  void* p = nullptr;
+  size_t cap = 0;
+  int ensure(size_t bytes) {
+    if (bytes <= cap) return SPICEY_SUCCESS;
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+    size_t want = bytes + bytes / 8 + 256;
+    CUDA_TRY(cudaMalloc(&p, want));
+    cap = want;
+    return SPICEY_SUCCESS;
+  }
+  void release() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+  }
+};
+
+struct DeviceCtx {
+  int dev = 0;
+  int sm_count = 0;
+  size_t smem_optin = 0;
+  cudaStream_t compute = nullptr, copy = nullptr;
+  Buffer plan, scratch, in0, in1, in2, out_x[2], out_i[2], out_s[2], aux0, aux1;
+  std::vector<cudaEvent_t> events;
+  cudaEvent_t get_event(size_t i) {
+    while (events.size() <= i) {
+      cudaEvent_t e;
+      cudaEventCreate(&e);
+      events.push_back(e);
+    }
+    return events[i];
+  }
+};
+
+template <typename T> size_t push_blob(std::vector<unsigned char>& blob, const std::vector<T>& v) {
+  size_t off = (blob.size() + 15) & ~(size_t)15;
+  blob.resize(off + sizeof(T) * v.size());
+  if (!v.empty()) memcpy(blob.data() + off, v.data(), sizeof(T) * v.size());
+  return off;
+}
+
+// Uploads the plan into ctx.plan on `stream` and fills the device-pointer view.
+int upload_plan(DeviceCtx& ctx, const HostPlan& hp, cudaStream_t stream, DevPlan& dp,
+                std::vector<unsigned char>& blob) {
+  blob.clear();
+  size_t o_ends = push_blob(blob, hp.ends), o_meta = push_blob(blob, hp.meta);
+  size_t o_sidx = push_blob(blob, hp.state_idx), o_val = push_blob(blob, hp.values);
+  size_t o_vos = push_blob(blob, hp.var_of_slot);
+  size_t o[2][5];
+  const HostGather* gs[2] = {&hp.ac, &hp.tran};
+  for (int k = 0; k < 2; ++k) {
+    o[k][0] = push_blob(blob, gs[k]->row_ptr);
+    o[k][1] = push_blob(blob, gs[k]->ent_col);
+    o[k][2] = push_blob(blob, gs[k]->ent_ptr);
+    o[k][3] = push_blob(blob, gs[k]->contrib);
+    o[k][4] = push_blob(blob, gs[k]->rowmask);
+  }
+  int rc = ctx.plan.ensure(blob.size());
+  if (rc) return rc;
+  CUDA_TRY(cudaMemcpyAsync(ctx.plan.p, blob.data(), blob.size(), cudaMemcpyHostToDevice, stream));
+  unsigned char* b = (unsigned char*)ctx.plan.p;
+  memset(&dp, 0, sizeof(dp));
+  dp.nn = hp.nn; dp.nV = hp.nV; dp.nvar = hp.nvar; dp.n_elem = hp.n_elem; dp.n_values = hp.n_values;
+  dp.n_ac_elem = hp.n_ac_elem; dp.n_state = hp.n_state; dp.MW = hp.MW;
+  for (int k = 0; k < 7; ++k) dp.off[k] = hp.off[k];
+  dp.ends = (const int4*)(b + o_ends);
+  dp.meta = (const int2*)(b + o_meta);
+  dp.state_idx = (const int*)(b + o_sidx);
+  dp.values = (const double*)(b + o_val);
+  dp.var_of_slot = (const int*)(b + o_vos);
+  GatherPlan* gp[2] = {&dp.ac, &dp.tran};
+  for (int k = 0; k < 2; ++k) {
+    gp[k]->row_ptr = (const int*)(b + o[k][0]);
+    gp[k]->ent_col = (const int*)(b + o[k][1]);
+    gp[k]->ent_ptr = (const int*)(b + o[k][2]);
+    gp[k]->contrib = (const int*)(b + o[k][3]);
+    gp[k]->rowmask = (const unsigned*)(b + o[k][4]);
+  }
+  return SPICEY_SUCCESS;
+}
+
+int round32(int n) { return std::max(32, (n + 31) / 32 * 32); }
+
+}  // namespace
+
+struct spicey_handle {
+  std::vector<DeviceCtx> devs;
+  spicey_stats stats;
+  std::vector<unsigned char> blob;  // plan staging (kept alive until the stream has consumed it)
+};
+
+namespace {
+
+// ---------------------------------------------------------------------------------
+// AC launch on one device (device pointers), asynchronous on `stream`.
+int launch_ac(DeviceCtx& ctx, const HostPlan& hp, const DevPlan& dp, const AcArgs& args, uint32_t flags,
+              cudaStream_t stream, int* tier_out, int64_t* launches) {
+  if (args.p_count <= 0) return SPICEY_SUCCESS;
+  const bool strict = flags & SPICEY_FLAG_STRICT;
+  const int NT = round32(hp.nvar);
+  const int nwarps = NT / 32;
+  AcSmem sm(hp.nvar, hp.n_elem, hp.MW, nwarps, false);
+  bool gmem = (flags & SPICEY_FLAG_FORCE_GMEM) || sm.total > ctx.smem_optin;
+  AcSmem L(hp.nvar, hp.n_elem, hp.MW, nwarps, gmem);
+  if (L.total > ctx.smem_optin) return fail(SPICEY_ERR_UNSUPPORTED, "element table too large for shared memory");
+  void (*kern)(DevPlan, AcArgs) =
+      gmem ? (strict ? ac_cta_kernel<true, true> : ac_cta_kernel<false, true>)
+           : (strict ? ac_cta_kernel<true, false> : ac_cta_kernel<false, false>);
+  CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total));
+  int occ = 0;
+  CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, NT, L.total));
+  if (occ < 1) return fail(SPICEY_ERR_UNSUPPORTED, "AC kernel does not fit on an SM");
+  long long grid = std::min<long long>(args.p_count, (long long)occ * ctx.sm_count);
+  AcArgs a = args;
+  if (gmem) {
+    size_t per = sizeof(double2) * (size_t)hp.nvar * (hp.nvar + 1);
+    int rc = ctx.scratch.ensure(per * grid);
+    if (rc) return rc;
+    a.scratch = (double2*)ctx.scratch.p;
+  }
+  kern<<<(unsigned)grid, NT, L.total, stream>>>(dp, a);
+  CUDA_TRY(cudaGetLastError());
+  if (tier_out) *tier_out = gmem ? SPICEY_TIER_CTA_GMEM : SPICEY_TIER_CTA_SMEM;
+  if (launches) ++*launches;
+  return SPICEY_SUCCESS;
+}
+
+int launch_tran(DeviceCtx& ctx, const HostPlan& hp, const DevPlan& dp, const TranArgs& args, uint32_t flags,
+                cudaStream_t stream, int* tier_out, int64_t* launches) {
+  if (args.n_local <= 0) return SPICEY_SUCCESS;
+  const bool strict = flags & SPICEY_FLAG_STRICT;
+  const int n_ent = (int)hp.tran.ent_col.size(), n_con = (int)hp.tran.contrib.size();
+  // Thread tier when the per-thread footprint leaves room for >= 32 threads per CTA.
+  if (!(flags & (SPICEY_FLAG_FORCE_CTA | SPICEY_FLAG_FORCE_GMEM)) && hp.nvar <= 16) {
+    for (int nt = 128; nt >= 32; nt >>= 1) {
+      TranThreadSmem L(hp.nvar, hp.n_elem, hp.n_state, n_ent, n_con, nt);
+      if (L.total > std::min<size_t>(ctx.smem_optin, nt == 32 ? ctx.smem_optin : 110 * 1024)) continue;
+      void (*kern)(DevPlan, TranArgs, int, int) = strict ? tran_thread_kernel<true> : tran_thread_kernel<false>;
+      CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total));
+      long long grid = (args.n_local + nt - 1) / nt;
+      kern<<<(unsigned)grid, nt, L.total, stream>>>(dp, args, n_ent, n_con);
+      CUDA_TRY(cudaGetLastError());
+      if (tier_out) *tier_out = SPICEY_TIER_THREAD;
+      if (launches) ++*launches;
+      return SPICEY_SUCCESS;
+    }
+  }
+  const int NT = round32(hp.nvar);
+  const int nwarps = NT / 32;
+  TranCtaSmem sm(hp.nvar, hp.n_elem, hp.n_state, hp.MW, nwarps, false);
+  bool gmem = (flags & SPICEY_FLAG_FORCE_GMEM) || sm.total > ctx.smem_optin;
+  TranCtaSmem L(hp.nvar, hp.n_elem, hp.n_state, hp.MW, nwarps, gmem);
+  if (L.total > ctx.smem_optin) return fail(SPICEY_ERR_UNSUPPORTED, "element table too large for shared memory");
+  void (*kern)(DevPlan, TranArgs, double*) =
+      gmem ? (strict ? tran_cta_kernel<true, true> : tran_cta_kernel<false, true>)
+           : (strict ? tran_cta_kernel<true, false> : tran_cta_kernel<false, false>);
+  CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total));
+  int occ = 0;
+  CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, NT, L.total));
+  if (occ < 1) return fail(SPICEY_ERR_UNSUPPORTED, "TRAN kernel does not fit on an SM");
+  long long grid = std::min<long long>(args.n_local, (long long)occ * ctx.sm_count);
+  double* scratch = nullptr;
+  if (gmem) {
+    int rc = ctx.scratch.ensure(sizeof(double) * (size_t)hp.nvar * (hp.nvar + 1) * grid);
+    if (rc) return rc;
+    scratch = (double*)ctx.scratch.p;
+  }
+  kern<<<(unsigned)grid, NT, L.total, stream>>>(dp, args, scratch);
+  CUDA_TRY(cudaGetLastError());
+  if (tier_out) *tier_out = gmem ? SPICEY_TIER_CTA_GMEM : SPICEY_TIER_CTA_SMEM;
+  if (launches) ++*launches;
+  return SPICEY_SUCCESS;
+}
+
+double now_ms() {
+  using namespace std::chrono;
+  return duration<double, std::milli>(steady_clock::now().time_since_epoch()).count();
+}
+
+__global__ void dfma_peak_kernel(double* out, int iters) {
+  double a0 = threadIdx.x * 1e-9, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6,
+         a7 = a0 + 7;
+  const double m = 1.0000001, c = 1e-9;
+  for (int i = 0; i < iters; ++i) {
+    a0 = fma(a0, m, c); a1 = fma(a1, m, c); a2 = fma(a2, m, c); a3 = fma(a3, m, c);
+    a4 = fma(a4, m, c); a5 = fma(a5, m, c); a6 = fma(a6, m, c); a7 = fma(a7, m, c);
+  }
+  if (a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7 == 123.456) out[0] = a0;
+}
+
+}  // namespace
+
+// ---------------------------------------------------------------------------------
+extern "C" {
+
+int32_t spicey_native_abi_version(void) { return SPICEY_NATIVE_ABI_VERSION; }
+
+int32_t spicey_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) {
+    cudaGetLastError();
+    return 0;
+  }
+  return n;
+}
+
+const char* spicey_last_error(void) { return g_err.c_str(); }
+
+int32_t spicey_create(const int32_t* devices, int32_t n_devices, spicey_handle** out) {
+  if (!out) return fail(SPICEY_ERR_INVALID, "out is NULL");
+  *out = nullptr;
+  int avail = spicey_device_count();
+  if (avail <= 0) return fail(SPICEY_ERR_NO_DEVICE, "no CUDA device available (this library has no CPU path)");
+  std::vector<int> ids;
+  if (!devices || n_devices <= 0) ids.push_back(0);
+  else ids.assign(devices, devices + n_devices);
+  spicey_handle* h = new spicey_handle();
+  memset(&h->stats, 0, sizeof(h->stats));
+  for (int id : ids) {
+    if (id < 0 || id >= avail) {
+      delete h;
+      return fail(SPICEY_ERR_INVALID, "device id out of range");
+    }
+    DeviceCtx c;
+    c.dev = id;
+    cudaDeviceProp prop;
+    if (cudaSetDevice(id) != cudaSuccess || cudaGetDeviceProperties(&prop, id) != cudaSuccess) {
+      delete h;
+      return fail(SPICEY_ERR_CUDA, "cannot query device");
+    }
+    c.sm_count = prop.multiProcessorCount;
+    c.smem_optin = prop.sharedMemPerBlockOptin;
+    cudaStreamCreateWithFlags(&c.compute, cudaStreamNonBlocking);
+    cudaStreamCreateWithFlags(&c.copy, cudaStreamNonBlocking);
+    h->devs.push_back(c);
+  }
+  h->stats.n_devices = (int)h->devs.size();
+  *out = h;
+  return SPICEY_SUCCESS;
+}
+
+void spicey_destroy(spicey_handle* h) {
+  if (!h) return;
+  for (auto& c : h->devs) {
+    cudaSetDevice(c.dev);
+    cudaDeviceSynchronize();
+    Buffer* bufs[] = {&c.plan, &c.scratch, &c.in0, &c.in1, &c.in2, &c.out_x[0], &c.out_x[1], &c.out_i[0],
+                      &c.out_i[1], &c.out_s[0], &c.out_s[1], &c.aux0, &c.aux1};
+    for (Buffer* b : bufs) b->release();
+    for (auto e : c.events) cudaEventDestroy(e);
+    cudaStreamDestroy(c.compute);
+    cudaStreamDestroy(c.copy);
+  }
+  delete h;
+}
+
+int32_t spicey_get_stats(const spicey_handle* h, spicey_stats* out) {
+  if (!h || !out) return fail(SPICEY_ERR_INVALID, "NULL argument");
+  *out = h->stats;
+  return SPICEY_SUCCESS;
+}
+
+void* spicey_host_alloc(int64_t bytes) {
+  void* p = nullptr;
+  if (bytes <= 0 || cudaMallocHost(&p, (size_t)bytes) != cudaSuccess) {
+    cudaGetLastError();
+    return nullptr;
+  }
+  return p;
+}
+
+void spicey_host_free(void* p) {
+  if (p) cudaFreeHost(p);
+}
+
+int32_t spicey_ac_solve_device(spicey_handle* h, int32_t dev_index, const spicey_elem_table* table,
+                               const spicey_sweep* sweep, const double* d_freqs, int64_t n_freq, double* d_x,
+                               double* d_ielem, int32_t* d_status, uint32_t flags, void* stream) {
+  if (!h) return fail(SPICEY_ERR_INVALID, "handle is NULL");
+  if (dev_index < 0 || dev_index >= (int)h->devs.size()) return fail(SPICEY_ERR_INVALID, "dev_index out of range");
+  if (!d_freqs || n_freq < 1 || !d_x || !d_status) return fail(SPICEY_ERR_INVALID, "NULL buffer or empty sweep");
+  DeviceCtx& ctx = h->devs[dev_index];
+  HostPlan hp;
+  int rc = build_plan(table, sweep, hp);
+  if (rc) return rc;
+  CUDA_TRY(cudaSetDevice(ctx.dev));
+  cudaStream_t st = (cudaStream_t)stream;
+  DevPlan dp;
+  rc = upload_plan(ctx, hp, st, dp, h->blob);
+  if (rc) return rc;
+  dp.n_inst = sweep ? sweep->n_inst : 1;
+  dp.n_var = sweep ? sweep->n_var : 0;
+  dp.var_values = sweep ? sweep->var_values : nullptr;
+  AcArgs a;
+  a.freqs = d_freqs; a.n_freq = n_freq; a.p_begin = 0; a.p_count = dp.n_inst * n_freq;
+  a.x = (double2*)d_x; a.ielem = (double2*)d_ielem; a.status = d_status; a.scratch = nullptr;
+  int tier = 0;
+  int64_t launches = 0;
+  rc = launch_ac(ctx, hp, dp, a, flags, st, &tier, &launches);
+  if (rc) return rc;
+  h->stats.kernel_launches = launches;
+  h->stats.tier = tier;
+  h->stats.solves = a.p_count;
+  h->stats.h2d_bytes = (int64_t)h->blob.size();
+  h->stats.d2h_bytes = 0;
+  return SPICEY_SUCCESS;
+}
+
+int32_t spicey_ac_solve(spicey_handle* h, const spicey_elem_table* table, const spicey_sweep* sweep,
+                        const double* freqs, int64_t n_freq, double* x, double* ielem, int32_t* status,
+                        uint32_t flags) {
+  if (!h) return fail(SPICEY_ERR_INVALID, "handle is NULL");
+  if (!freqs || n_freq < 1 || !x || !status) return fail(SPICEY_ERR_INVALID, "NULL buffer or empty sweep");
+  const double t0 = now_ms();
+  HostPlan hp;
+  int rc = build_plan(table, sweep, hp);
+  if (rc) return rc;
+  const long long n_inst = sweep ? sweep->n_inst : 1;
+  const int n_var = sweep ? sweep->n_var : 0;
+  const long long P = n_inst * n_freq;
+  const int D = (int)h->devs.size();
+  const size_t xrow = sizeof(double2) * hp.nvar, irow = sizeof(double2) * hp.n_ac_elem;
+  // Chunk size: ~96 MiB of results per chunk so that copies overlap the next chunk's kernel.
+  long long chunk = std::max<long long>(1024, (long long)((96ull << 20) / (xrow + (ielem ? irow : 0) + 4)));
+  int64_t launches = 0, h2d = 0, d2h = 0;
+  int tier = 0;
+  struct Shard { long long lo, hi; size_t ev0; int nchunks; };
+  std::vector<Shard> shards(D);
+  for (int d = 0; d < D; ++d) {
+    DeviceCtx& ctx = h->devs[d];
+    Shard& s = shards[d];
+    s.lo = P * d / D; s.hi = P * (d + 1) / D; s.nchunks = 0; s.ev0 = 0;
+    if (s.hi <= s.lo) continue;
+    CUDA_TRY(cudaSetDevice(ctx.dev));
+    DevPlan dp;
+    rc = upload_plan(ctx, hp, ctx.compute, dp, h->blob);
+    if (rc) return rc;
+    CUDA_TRY(cudaStreamSynchronize(ctx.compute));  // h->blob is reused by the next device
+    h2d += (int64_t)h->blob.size();
+    dp.n_inst = n_inst; dp.n_var = n_var;
+    rc = ctx.in0.ensure(sizeof(double) * n_freq);
+    if (rc) return rc;
+    CUDA_TRY(cudaMemcpyAsync(ctx.in0.p, freqs, sizeof(double) * n_freq, cudaMemcpyHostToDevice, ctx.compute));
+    h2d += sizeof(double) * n_freq;
+    if (n_var > 0) {
+      size_t vb = sizeof(double) * (size_t)n_var * n_inst;
+      rc = ctx.in1.ensure(vb);
+      if (rc) return rc;
+      CUDA_TRY(cudaMemcpyAsync(ctx.in1.p, sweep->var_values, vb, cudaMemcpyHostToDevice, ctx.compute));
+      h2d += vb;
+      dp.var_values = (const double*)ctx.in1.p;
+    }
+    const long long cnt = s.hi - s.lo;
+    const long long csz = std::min(chunk, cnt);
+    for (int b = 0; b < 2; ++b) {
+      if ((rc = ctx.out_x[b].ensure(xrow * csz))) return rc;
+      if (ielem && (rc = ctx.out_i[b].ensure(irow * csz))) return rc;
+      if ((rc = ctx.out_s[b].ensure(sizeof(int) * csz))) return rc;
+    }
+    int ci = 0;
+    for (long long lo = s.lo; lo < s.hi; lo += csz, ++ci) {
+      const long long n = std::min(csz, s.hi - lo);
+      const int b = ci & 1;
+      // events per chunk: [4*ci] kernel start, [4*ci+1] kernel end, [4*ci+2] copy done
+      cudaEvent_t ks = ctx.get_event(4 * ci), ke = ctx.get_event(4 * ci + 1), cd = ctx.get_event(4 * ci + 2);
+      if (ci >= 2) CUDA_TRY(cudaStreamWaitEvent(ctx.compute, ctx.get_event(4 * (ci - 2) + 2), 0));
+      AcArgs a;
+      a.freqs = (const double*)ctx.in0.p; a.n_freq = n_freq; a.p_begin = lo; a.p_count = n;
+      a.x = (double2*)ctx.out_x[b].p; a.ielem = ielem ? (double2*)ctx.out_i[b].p : nullptr;
+      a.status = (int*)ctx.out_s[b].p; a.scratch = nullptr;
+      CUDA_TRY(cudaEventRecord(ks, ctx.compute));
+      rc = launch_ac(ctx, hp, dp, a, flags, ctx.compute, &tier, &launches);
+      if (rc) return rc;
+      CUDA_TRY(cudaEventRecord(ke, ctx.compute));
+      CUDA_TRY(cudaStreamWaitEvent(ctx.copy, ke, 0));
+      CUDA_TRY(cudaMemcpyAsync((char*)x + xrow * lo, a.x, xrow * n, cudaMemcpyDeviceToHost, ctx.copy));
+      if (ielem)
+        CUDA_TRY(cudaMemcpyAsync((char*)ielem + irow * lo, a.ielem, irow * n, cudaMemcpyDeviceToHost, ctx.copy));
+      CUDA_TRY(cudaMemcpyAsync(status + lo, a.status, sizeof(int) * n, cudaMemcpyDeviceToHost, ctx.copy));
+      CUDA_TRY(cudaEventRecord(cd, ctx.copy));
+      d2h += (int64_t)((xrow + (ielem ? irow : 0) + 4) * n);
+    }
+    s.nchunks = ci;
+  }
+  double kmax = 0;
+  for (int d = 0; d < D; ++d) {
+    DeviceCtx& ctx = h->devs[d];
+    if (shards[d].hi <= shards[d].lo) continue;
+    CUDA_TRY(cudaSetDevice(ctx.dev));
+    CUDA_TRY(cudaStreamSynchronize(ctx.copy));
+    CUDA_TRY(cudaStreamSynchronize(ctx.compute));
+    double k = 0;
+    for (int ci = 0; ci < shards[d].nchunks; ++ci) {
+      float ms = 0;
+      cudaEventElapsedTime(&ms, ctx.get_event(4 * ci), ctx.get_event(4 * ci + 1));
+      k += ms;
+    }
+    kmax = std::max(kmax, k);
+  }
+  h->stats.kernel_ms = kmax;
+  h->stats.total_ms = now_ms() - t0;
+  h->stats.kernel_launches = launches;
+  h->stats.h2d_bytes = h2d;
+  h->stats.d2h_bytes = d2h;
+  h->stats.solves = P;
+  h->stats.tier = tier;
+  return SPICEY_SUCCESS;
+}
+
+int32_t spicey_tran_solve_device(spicey_handle* h, int32_t dev_index, const spicey_elem_table* table,
+                                 const spicey_sweep* sweep, double dt, int64_t steps, const double* d_vsrc,
+                                 const int32_t* vsrc_mask, const double* d_state0, double* d_v, double* d_ielem,
+                                 double* d_state_out, int32_t* d_iters, int32_t* d_status, uint32_t flags,
+                                 void* stream) {
+  if (!h) return fail(SPICEY_ERR_INVALID, "handle is NULL");
+  if (dev_index < 0 || dev_index >= (int)h->devs.size()) return fail(SPICEY_ERR_INVALID, "dev_index out of range");
+  if (steps < 1 || !d_v || !d_status) return fail(SPICEY_ERR_INVALID, "NULL buffer or steps < 1");
+  DeviceCtx& ctx = h->devs[dev_index];
+  HostPlan hp;
+  int rc = build_plan(table, sweep, hp);
+  if (rc) return rc;
+  CUDA_TRY(cudaSetDevice(ctx.dev));
+  cudaStream_t st = (cudaStream_t)stream;
+  std::vector<int> mask(std::max(1, hp.nV), 0);
+  for (int k = 0; k < hp.nV; ++k) {
+    mask[k] = vsrc_mask ? (vsrc_mask[k] != 0) : 0;
+    if (mask[k] && !d_vsrc) return fail(SPICEY_ERR_INVALID, "vsrc_mask set but vsrc is NULL");
+  }
+  DevPlan dp;
+  rc = upload_plan(ctx, hp, st, dp, h->blob);
+  if (rc) return rc;
+  if ((rc = ctx.aux0.ensure(sizeof(int) * mask.size()))) return rc;
+  CUDA_TRY(cudaMemcpyAsync(ctx.aux0.p, mask.data(), sizeof(int) * mask.size(), cudaMemcpyHostToDevice, st));
+  CUDA_TRY(cudaStreamSynchronize(st));  // mask is a stack-lifetime staging buffer
+  dp.n_inst = sweep ? sweep->n_inst : 1;
+  dp.n_var = sweep ? sweep->n_var : 0;
+  dp.var_values = sweep ? sweep->var_values : nullptr;
+  TranArgs a;
+  a.dt = dt; a.steps = steps; a.vsrc = d_vsrc; a.vsrc_mask = (const int*)ctx.aux0.p; a.state0 = d_state0;
+  a.inst0 = 0; a.n_local = dp.n_inst; a.v = d_v; a.ielem = d_ielem; a.state_out = d_state_out;
+  a.iters = d_iters; a.status = d_status;
+  int tier = 0;
+  int64_t launches = 0;
+  rc = launch_tran(ctx, hp, dp, a, flags, st, &tier, &launches);
+  if (rc) return rc;
+  h->stats.kernel_launches = launches;
+  h->stats.tier = tier;
+  h->stats.solves = dp.n_inst * (steps + 1);
+  return SPICEY_SUCCESS;
+}
+
+int32_t spicey_tran_solve(spicey_handle* h, const spicey_elem_table* table, const spicey_sweep* sweep, double dt,
+                          int64_t steps, const double* vsrc, const int32_t* vsrc_mask, const double* state0,
+                          double* v, double* ielem, double* state_out, int32_t* iters, int32_t* status,
+                          uint32_t flags) {
+  if (!h) return fail(SPICEY_ERR_INVALID, "handle is NULL");
+  if (steps < 1 || !v || !status) return fail(SPICEY_ERR_INVALID, "NULL buffer or steps < 1");
+  const double t0 = now_ms();
+  HostPlan hp;
+  int rc = build_plan(table, sweep, hp);
+  if (rc) return rc;
+  const long long n_inst = sweep ? sweep->n_inst : 1;
+  const int n_var = sweep ? sweep->n_var : 0;
+  const long long S1 = steps + 1;
+  const int D = (int)h->devs.size();
+  std::vector<int> mask(std::max(1, hp.nV), 0);
+  bool any_wave = false;
+  for (int k = 0; k < hp.nV; ++k) {
+    mask[k] = vsrc_mask ? (vsrc_mask[k] != 0) : 0;
+    any_wave |= mask[k] != 0;
+  }
+  if (any_wave && !vsrc) return fail(SPICEY_ERR_INVALID, "vsrc_mask set but vsrc is NULL");
+  int64_t launches = 0, h2d = 0, d2h = 0;
+  int tier = 0;
+  std::vector<std::pair<long long, long long>> shards(D);
+  for (int d = 0; d < D; ++d) {
+    DeviceCtx& ctx = h->devs[d];
+    const long long lo = n_inst * d / D, hi = n_inst * (d + 1) / D, nl = hi - lo;
+    shards[d] = std::make_pair(lo, hi);
+    if (nl <= 0) continue;
+    CUDA_TRY(cudaSetDevice(ctx.dev));
+    DevPlan dp;
+    rc = upload_plan(ctx, hp, ctx.compute, dp, h->blob);
+    if (rc) return rc;
+    if ((rc = ctx.aux0.ensure(sizeof(int) * mask.size()))) return rc;
+    CUDA_TRY(cudaMemcpyAsync(ctx.aux0.p, mask.data(), sizeof(int) * mask.size(), cudaMemcpyHostToDevice, ctx.compute));
+    CUDA_TRY(cudaStreamSynchronize(ctx.compute));
+    h2d += (int64_t)h->blob.size();
+    dp.n_inst = n_inst; dp.n_var = n_var;
+    TranArgs a;
+    a.dt = dt; a.steps = steps; a.vsrc = nullptr; a.vsrc_mask = (const int*)ctx.aux0.p; a.state0 = nullptr;
+    if (any_wave) {
+      size_t b = sizeof(double) * (size_t)hp.nV * S1;
+      if ((rc = ctx.in0.ensure(b))) return rc;
+      CUDA_TRY(cudaMemcpyAsync(ctx.in0.p, vsrc, b, cudaMemcpyHostToDevice, ctx.compute));
+      h2d += b;
+      a.vsrc = (const double*)ctx.in0.p;
+    }
+    if (n_var > 0) {
+      size_t b = sizeof(double) * (size_t)n_var * n_inst;
+      if ((rc = ctx.in1.ensure(b))) return rc;
+      CUDA_TRY(cudaMemcpyAsync(ctx.in1.p, sweep->var_values, b, cudaMemcpyHostToDevice, ctx.compute));
+      h2d += b;
+      dp.var_values = (const double*)ctx.in1.p;
+    }
+    if (state0 && hp.n_state > 0) {
+      size_t b = sizeof(double) * (size_t)hp.n_state * n_inst;
+      if ((rc = ctx.in2.ensure(b))) return rc;
+      CUDA_TRY(cudaMemcpyAsync(ctx.in2.p, state0, b, cudaMemcpyHostToDevice, ctx.compute));
+      h2d += b;
+      a.state0 = (const double*)ctx.in2.p;
+    }
+    if ((rc = ctx.out_x[0].ensure(sizeof(double) * S1 * hp.nn * nl))) return rc;
+    if (ielem && (rc = ctx.out_i[0].ensure(sizeof(double) * S1 * hp.n_elem * nl))) return rc;
+    if ((rc = ctx.out_s[0].ensure(sizeof(int) * nl))) return rc;
+    if (state_out && (rc = ctx.aux1.ensure(sizeof(double) * std::max(1, hp.n_state) * nl))) return rc;
+    if (iters && (rc = ctx.out_s[1].ensure(sizeof(int) * S1 * nl))) return rc;
+    a.inst0 = lo; a.n_local = nl;
+    a.v = (double*)ctx.out_x[0].p;
+    a.ielem = ielem ? (double*)ctx.out_i[0].p : nullptr;
+    a.state_out = state_out ? (double*)ctx.aux1.p : nullptr;
+    a.iters = iters ? (int*)ctx.out_s[1].p : nullptr;
+    a.status = (int*)ctx.out_s[0].p;
+    CUDA_TRY(cudaEventRecord(ctx.get_event(0), ctx.compute));
+    rc = launch_tran(ctx, hp, dp, a, flags, ctx.compute, &tier, &launches);
+    if (rc) return rc;
+    CUDA_TRY(cudaEventRecord(ctx.get_event(1), ctx.compute));
+    // [rows][n_local] device slabs -> [rows][n_inst] host arrays at column offset lo
+    const size_t dp_ = sizeof(double) * n_inst, sp_ = sizeof(double) * nl;
+    CUDA_TRY(cudaMemcpy2DAsync((char*)v + sizeof(double) * lo, dp_, a.v, sp_, sp_, S1 * hp.nn,
+                               cudaMemcpyDeviceToHost, ctx.compute));
+    d2h += (int64_t)(sp_ * S1 * hp.nn);
+    if (ielem && hp.n_elem > 0) {
+      CUDA_TRY(cudaMemcpy2DAsync((char*)ielem + sizeof(double) * lo, dp_, a.ielem, sp_, sp_, S1 * hp.n_elem,
+                                 cudaMemcpyDeviceToHost, ctx.compute));
+      d2h += (int64_t)(sp_ * S1 * hp.n_elem);
+    }
+    if (state_out && hp.n_state > 0)
+      CUDA_TRY(cudaMemcpy2DAsync((char*)state_out + sizeof(double) * lo, dp_, a.state_out, sp_, sp_, hp.n_state,
+                                 cudaMemcpyDeviceToHost, ctx.compute));
+    if (iters)
+      CUDA_TRY(cudaMemcpy2DAsync((char*)iters + sizeof(int) * lo, sizeof(int) * n_inst, a.iters, sizeof(int) * nl,
+                                 sizeof(int) * nl, S1, cudaMemcpyDeviceToHost, ctx.compute));
+    CUDA_TRY(cudaMemcpyAsync(status + lo, a.status, sizeof(int) * nl, cudaMemcpyDeviceToHost, ctx.compute));
+  }
+  double kmax = 0;
+  for (int d = 0; d < D; ++d) {
+    DeviceCtx& ctx = h->devs[d];
+    if (shards[d].second <= shards[d].first) continue;
+    CUDA_TRY(cudaSetDevice(ctx.dev));
+    CUDA_TRY(cudaStreamSynchronize(ctx.compute));
+    float ms = 0;
+    cudaEventElapsedTime(&ms, ctx.get_event(0), ctx.get_event(1));
+    kmax = std::max(kmax, (double)ms);
+  }
+  h->stats.kernel_ms = kmax;
+  h->stats.total_ms = now_ms() - t0;
+  h->stats.kernel_launches = launches;
+  h->stats.h2d_bytes = h2d;
+  h->stats.d2h_bytes = d2h;
+  h->stats.solves = n_inst * S1;
+  h->stats.tier = tier;
+  return SPICEY_SUCCESS;
+}
+
+int32_t spicey_measure_fp64_peak(spicey_handle* h, int32_t dev_index, double* gflops_out) {
+  if (!h || !gflops_out) return fail(SPICEY_ERR_INVALID, "NULL argument");
+  if (dev_index < 0 || dev_index >= (int)h->devs.size()) return fail(SPICEY_ERR_INVALID, "dev_index out of range");
+  DeviceCtx& ctx = h->devs[dev_index];
+  CUDA_TRY(cudaSetDevice(ctx.dev));
+  int rc = ctx.aux1.ensure(64);
+  if (rc) return rc;
+  const int iters = 1 << 16, threads = 256, blocks = ctx.sm_count * 8;
+  cudaEvent_t e0 = ctx.get_event(0), e1 = ctx.get_event(1);
+  double best = 0;
+  for (int rep = 0; rep < 5; ++rep) {
+    CUDA_TRY(cudaEventRecord(e0, ctx.compute));
+    dfma_peak_kernel<<<blocks, threads, 0, ctx.compute>>>((double*)ctx.aux1.p, iters);
+    CUDA_TRY(cudaEventRecord(e1, ctx.compute));
+    CUDA_TRY(cudaStreamSynchronize(ctx.compute));
+    float ms = 0;
+    cudaEventElapsedTime(&ms, e0, e1);
+    double flops = 2.0 * 8 * (double)iters * threads * blocks;
+    if (rep > 0) best = std::max(best, flops / (ms * 1e-3) / 1e9);
+  }
+  *gflops_out = best;
+  return SPICEY_SUCCESS;
+}
+
+}  // extern "C"

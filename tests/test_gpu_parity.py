@@ -1,0 +1,298 @@
+"""Parity of the CUDA path (through the C ABI) against the oracle on the same inputs.
+
+Bars (BASELINE.json north_star): max relative error 1e-9 for AC (node voltages and branch
+currents, complex: magnitude and phase), 1e-6 for transient waveforms.  Strict mode
+(SPICEY_FLAG_STRICT: reference-order unfused arithmetic) is held to 1e-12.
+"""
+import numpy as np
+import pytest
+
+from oracle import c_oracle as co
+from oracle import spicey_oracle as o
+from spicey_b200 import native, workloads as w
+from spicey_b200.parsing import compute_effective_time_step, parse_netlist
+
+pytestmark = pytest.mark.gpu
+
+AC_TOL = 1e-9
+TRAN_TOL = 1e-6
+
+
+@pytest.fixture(scope="module")
+def eng():
+    import spicey_b200 as sp
+    e = native.Engine()
+    sp.set_engine(e)
+    yield e
+    sp.set_engine(None)
+    e.close()
+
+
+def rel_err(a, b):
+    """max |a-b| / |b| over entries, entries of b below 1e-300 compared absolutely."""
+    a, b = np.asarray(a), np.asarray(b)
+    den = np.abs(b)
+    den = np.where(den < 1e-300, 1.0, den)
+    return float(np.max(np.abs(a - b) / den)) if a.size else 0.0
+
+
+def ac_case(eng, text, freqs, flags=0, n_inst=1, overrides=None):
+    import spicey_b200 as sp
+    ck = parse_netlist(text)
+    out = sp.simulate_ac_batch(ck, freqs, n_inst=n_inst, overrides=overrides, engine=eng, flags=flags)
+    x, ie, st = co.ac_solve(ck, freqs, n_inst=n_inst, overrides=overrides, nthreads=4)
+    F = len(freqs)
+    return out, x.reshape(n_inst, F, -1), ie.reshape(n_inst, F, -1), st.reshape(n_inst, F), ck
+
+
+def test_library_loaded_and_device_present(eng):
+    assert eng.lib.spicey_device_count() >= 1
+    assert eng.fp64_peak_gflops() > 1000.0
+
+
+def test_simulate_readme_golden_text(eng, golden):
+    """tests/basics/basics01.test.ts through the drop-in simulate(): 201 rows, character for character."""
+    import spicey_b200 as sp
+    g = golden("basics01_ac")
+    res = sp.simulate(g["netlist"])
+    assert res["tran"] is None
+    lines = sp.formatAcResult(res["ac"]).split("\n")
+    assert lines[0] == g["header"] and len(lines) == 202
+    for ln, row in zip(lines[1:], g["rows"]):
+        assert ln == "%s, %s,%s, %s,%s" % tuple(row)
+    assert list(res["ac"]["elementCurrents"].keys()) == ["r1", "c1", "v1"]
+
+
+@pytest.mark.parametrize("flags,tol", [(0, AC_TOL), (native.FLAG_STRICT, 1e-12), (native.FLAG_FORCE_GMEM, AC_TOL)])
+def test_ac_readme_rc(eng, flags, tol):
+    ck = parse_netlist(w.README_RC)
+    import spicey_b200 as sp
+    freqs = sp.analysis.ac_frequencies(ck)
+    out, x, ie, st, _ = ac_case(eng, w.README_RC, freqs, flags)
+    assert out["status"].max() == 0 and st.max() == 0
+    assert rel_err(out["x"], x) <= tol
+    assert rel_err(out["ielem"], ie) <= tol
+
+
+@pytest.mark.parametrize("flags,tol", [(0, AC_TOL), (native.FLAG_STRICT, 1e-12), (native.FLAG_FORCE_GMEM, AC_TOL)])
+def test_ac_ladder64_slice(eng, flags, tol):
+    """cfg 2 topology (Nvar = 65), every 997th of the 1,000,001 frequencies."""
+    import spicey_b200 as sp
+    text = w.rc_ladder(64)
+    freqs = np.array(sp.analysis.ac_frequencies(parse_netlist(text)))
+    assert freqs.shape[0] == 1000001
+    sub = freqs[::997]
+    out, x, ie, st, _ = ac_case(eng, text, sub, flags)
+    assert out["status"].max() == 0 and st.max() == 0
+    assert rel_err(out["x"], x) <= tol, rel_err(out["x"], x)
+    assert rel_err(out["ielem"], ie) <= tol
+    # magnitude and phase separately, as the north star words it
+    assert rel_err(np.abs(out["x"]), np.abs(x)) <= tol
+    dphi = np.angle(out["x"] * np.conj(x))
+    assert np.max(np.abs(dphi)) <= tol
+
+
+def test_ac_mesh16_slice_global_scratch_tier(eng):
+    """cfg 4 topology (Nvar = 257): does not fit one SM's shared memory -> global-scratch tier."""
+    import spicey_b200 as sp
+    text = w.rc_mesh(16)
+    freqs = np.array(sp.analysis.ac_frequencies(parse_netlist(text)))
+    assert freqs.shape[0] == 8000001
+    sub = freqs[::200003]
+    out, x, ie, st, _ = ac_case(eng, text, sub)
+    assert eng.stats()["tier"] == native.TIER_CTA_GMEM
+    assert out["status"].max() == 0 and st.max() == 0
+    assert rel_err(out["x"], x) <= AC_TOL, rel_err(out["x"], x)
+    assert rel_err(out["ielem"], ie) <= AC_TOL
+
+
+def random_rlc_netlist(rng, n_nodes, n_elem, n_v=2):
+    lines = ["* random RLC"]
+    nodes = ["0"] + ["n%d" % i for i in range(1, n_nodes + 1)]
+    for k in range(n_v):
+        lines.append("v%d n%d 0 dc 1 ac %g %g" % (k + 1, k + 1, rng.uniform(0.5, 2), rng.uniform(-90, 90)))
+    for i in range(1, n_nodes + 1):  # a resistor tree keeps every node connected
+        lines.append("r%d n%d %s %g" % (i, i, nodes[rng.integers(0, i)], rng.uniform(10, 1e4)))
+    for k in range(n_elem):
+        a, b = rng.choice(len(nodes), 2, replace=False)
+        kind = "rcl"[rng.integers(0, 3)]
+        val = {"r": rng.uniform(10, 1e4), "c": rng.uniform(1e-9, 1e-6), "l": rng.uniform(1e-4, 1e-2)}[kind]
+        lines.append("%s%d %s %s %g" % (kind, 100 + k, nodes[a], nodes[b], val))
+    lines.append(".ac dec 7 10 1meg")
+    return "\n".join(lines) + "\n"
+
+
+@pytest.mark.parametrize("n_nodes,n_elem", [(1, 0), (2, 3), (5, 12), (14, 60), (30, 200), (31, 40), (62, 300), (100, 700)])
+def test_ac_random_rlc_networks(eng, n_nodes, n_elem):
+    """Dense-ish random networks: exercises pivoting away from the diagonal, fill-in and ties."""
+    import spicey_b200 as sp
+    rng = np.random.default_rng(n_nodes * 1000 + n_elem)
+    text = random_rlc_netlist(rng, n_nodes, n_elem, n_v=min(2, n_nodes))
+    freqs = sp.analysis.ac_frequencies(parse_netlist(text))
+    for flags, tol in ((0, AC_TOL), (native.FLAG_STRICT, 1e-11)):
+        out, x, ie, st, _ = ac_case(eng, text, freqs, flags)
+        assert np.array_equal(out["status"], st)
+        assert st.max() == 0
+        scale = np.max(np.abs(x), axis=2, keepdims=True)  # mixed-magnitude solutions: error relative to the row's max
+        assert np.max(np.abs(out["x"] - x) / scale) <= tol
+        iscale = np.max(np.abs(ie), axis=2, keepdims=True)
+        assert np.max(np.abs(out["ielem"] - ie) / iscale) <= tol
+
+
+def test_ac_sweep_instances(eng):
+    """Monte-Carlo axis on AC: 37 instances x 11 frequencies with swept R/C/source."""
+    rng = np.random.default_rng(5)
+    n = 37
+    ov = {"r1": rng.uniform(10, 100, n), "c1": rng.uniform(1e-5, 1e-3, n), "v1.acmag": rng.uniform(0.5, 2, n),
+          "v1.acphase": rng.uniform(-180, 180, n)}
+    freqs = np.logspace(0, 3, 11)
+    out, x, ie, st, _ = ac_case(eng, w.README_RC, freqs, n_inst=n, overrides=ov)
+    assert out["status"].max() == 0
+    assert rel_err(out["x"], x) <= AC_TOL
+    assert rel_err(out["ielem"], ie) <= AC_TOL
+
+
+def test_ac_error_statuses_do_not_poison_batch(eng):
+    """R<=0 (simulateAC.ts:37), singular matrix (solveComplex.ts:29), Complex.div guard (Complex.ts:42)."""
+    n = 8
+    r = np.full(n, 30.0)
+    r[3] = -1.0
+    out, x, ie, st, _ = ac_case(eng, w.README_RC, [1.0, 10.0], n_inst=n, overrides={"r1": r})
+    assert np.array_equal(out["status"], st)
+    assert (st[3] == native.ST_R_NONPOS).all() and st[[0, 1, 2, 4, 5, 6, 7]].max() == 0
+    ok = [0, 1, 2, 4, 5, 6, 7]
+    assert rel_err(out["x"][ok], x[ok]) <= AC_TOL
+    assert np.isnan(out["x"][3]).all()
+    # two ideal sources in parallel -> singular
+    text = "* sing\nv1 a 0 ac 1\nv2 a 0 ac 1\nr1 a 0 1k\n.ac lin 2 1 2\n"
+    out, x, ie, st, _ = ac_case(eng, text, [1.0, 2.0])
+    assert (st == native.ST_SINGULAR).all() and np.array_equal(out["status"], st)
+    # inductor with 1e-15 <= 2*pi*f*L < 3.2e-8 -> "Complex divide by ~0" (hazard H5)
+    text = "* cdiv\nv1 a 0 ac 1\nl1 a b 1e-10\nr1 b 0 1k\n.ac lin 2 1 2\n"
+    out, x, ie, st, _ = ac_case(eng, text, [1.0, 1e6])
+    assert st[0, 0] == native.ST_CDIV and st[0, 1] == 0 and np.array_equal(out["status"], st)
+    import spicey_b200 as sp
+    with pytest.raises(ValueError, match="R r1 must be > 0"):
+        sp.simulate("* bad\nv1 1 0 ac 1\nr1 1 2 -5\nc1 2 0 1u\n.ac dec 2 1 10\n")
+    with pytest.raises(ArithmeticError, match=r"Singular matrix \(complex\)"):
+        sp.simulate("* sing\nv1 a 0 ac 1\nv2 a 0 ac 1\nr1 a 0 1k\n.ac lin 2 1 2\n")
+
+
+# ---- transient --------------------------------------------------------------------
+
+GOLDEN_TRAN = ["transient01_rc_pulse", "two_probes", "switch_vt_vh", "vswitch_pwl", "boost_converter_probe",
+               "diode_switch", "case_insensitive_nodes"]
+
+
+@pytest.mark.parametrize("name", GOLDEN_TRAN)
+@pytest.mark.parametrize("flags", [0, native.FLAG_STRICT, native.FLAG_FORCE_CTA, native.FLAG_FORCE_GMEM])
+def test_tran_reference_netlists(eng, golden, name, flags):
+    """Every transient netlist of the reference's tests through the drop-in simulateTRAN, all tiers."""
+    import spicey_b200 as sp
+    text = golden(name)["netlist"]
+    ref = o.simulate(text)
+    ck = parse_netlist(text)
+    got = sp.simulateTRAN(ck, flags=flags)
+    assert got["times"] == ref["tran"]["times"]
+    assert list(got["nodeVoltages"].keys()) == list(ref["tran"]["nodeVoltages"].keys())
+    assert list(got["elementCurrents"].keys()) == list(ref["tran"]["elementCurrents"].keys())
+    for kind in ("nodeVoltages", "elementCurrents"):
+        for k, b in ref["tran"][kind].items():
+            a, b = np.asarray(got[kind][k]), np.asarray(b)
+            scale = max(1e-30, float(np.max(np.abs(b))))
+            assert np.max(np.abs(a - b)) <= TRAN_TOL * scale, (kind, k, np.max(np.abs(a - b)) / scale)
+    # circuit state is left as the reference leaves it (simulateTRAN.ts:221-237)
+    rc = ref["circuit"]
+    for a, b in zip(ck.C, rc.C):
+        assert abs(a.vPrev - b.vPrev) <= TRAN_TOL * max(1.0, abs(b.vPrev))
+    for a, b in zip(ck.L, rc.L):
+        assert abs(a.iPrev - b.iPrev) <= TRAN_TOL * max(1.0, abs(b.iPrev))
+    for a, b in zip(ck.S, rc.S):
+        assert a.isOn == b.isOn
+
+
+def test_tran_svg_golden_pixels(eng, golden):
+    """GPU waveforms against the reference's SVG snapshots directly (1e-4 px at 6 decimals)."""
+    import spicey_b200 as sp
+    for name in ["transient01_rc_pulse", "switch_vt_vh", "vswitch_pwl", "boost_converter_probe"]:
+        g = golden(name)
+        tran = sp.simulate(g["netlist"])["tran"]
+        vmin, vmax = g["v_range"]
+        for sname, pts in g["series_px"].items():
+            key = [k for k in tran["nodeVoltages"] if k.upper() == sname[2:-1].upper()][0]
+            ys = 520 - (np.asarray(tran["nodeVoltages"][key]) - vmin) / (vmax - vmin) * 456
+            assert np.max(np.abs(ys - np.array(pts)[:, 1])) <= 1e-4
+
+
+def tran_batch_case(eng, text, n_inst, overrides, flags=0):
+    import spicey_b200 as sp
+    ck = parse_netlist(text)
+    got = sp.simulate_tran_batch(ck, n_inst=n_inst, overrides=overrides, engine=eng, flags=flags, want_iters=True)
+    ck2 = parse_netlist(text)
+    dt, steps = compute_effective_time_step(ck2.analyses.tran.dt, ck2.analyses.tran.tstop)
+    v, ie, iters, st, state = co.tran_solve(ck2, dt, steps, n_inst=n_inst, overrides=overrides, nthreads=8)
+    return got, v, ie, iters, st
+
+
+@pytest.mark.parametrize("flags", [0, native.FLAG_FORCE_CTA])
+def test_tran_rlc_tank_monte_carlo_slice(eng, flags):
+    """cfg 3 on its first 512 instances: steps = 1001 (hazard H2), +-5 % R/L/C."""
+    n = 512 if flags == 0 else 64
+    ov = {k: v[:n] for k, v in w.rlc_tank_overrides(65536).items()}
+    got, v, ie, iters, st = tran_batch_case(eng, w.RLC_TANK, n, ov, flags)
+    assert got["steps"] == 1001 and got["v"].shape == (1002, 2, n)
+    assert got["status"].max() == 0 and st.max() == 0
+    assert np.array_equal(got["iters"].T, iters)
+    ref_v = np.transpose(v, (1, 2, 0))
+    ref_i = np.transpose(ie, (1, 2, 0))
+    assert np.max(np.abs(got["v"] - ref_v)) <= TRAN_TOL * np.max(np.abs(ref_v))
+    assert np.max(np.abs(got["ielem"] - ref_i)) <= TRAN_TOL * np.max(np.abs(ref_i))
+
+
+@pytest.mark.parametrize("flags", [0, native.FLAG_FORCE_CTA])
+def test_tran_rectifier_sweep_slice(eng, flags):
+    """cfg 5 (diode, single linearisation per step) on 400 instances spread over the sweep."""
+    n = 400 if flags == 0 else 48
+    full = w.rectifier_overrides(100000)
+    pick = np.linspace(0, 99999, n).astype(int)
+    ov = {k: v[pick] for k, v in full.items()}
+    got, v, ie, iters, st = tran_batch_case(eng, w.RECTIFIER, n, ov, flags)
+    assert got["steps"] == 3000
+    assert got["status"].max() == 0 and st.max() == 0
+    ref_v = np.transpose(v, (1, 2, 0))
+    ref_i = np.transpose(ie, (1, 2, 0))
+    vs = np.max(np.abs(ref_v), axis=0, keepdims=True)
+    assert np.max(np.abs(got["v"] - ref_v) / vs) <= TRAN_TOL
+    cs = np.maximum(np.max(np.abs(ref_i), axis=0, keepdims=True), 1e-30)
+    assert np.max(np.abs(got["ielem"] - ref_i) / cs) <= TRAN_TOL
+
+
+def test_tran_singular_instance_is_isolated(eng):
+    """A singular instance (two sources fighting) reports status 1 and NaNs; neighbours are untouched."""
+    import spicey_b200 as sp
+    text = "* t\nV1 1 0 PULSE(0 5 0 1n 1n 5u 10u)\nR1 1 2 1k\nC1 2 0 1u\n.tran 0.1u 2u\n"
+    r = np.array([1000.0, 1000.0, 1000.0])
+    got, v, ie, iters, st = tran_batch_case(eng, text, 3, {"R1": r})
+    assert got["status"].max() == 0
+    with pytest.raises(ArithmeticError, match=r"Singular matrix \(real\)"):
+        sp.simulate("* sing\nv1 a 0 dc 1\nv2 a 0 dc 2\nr1 a 0 1k\n.tran 1u 5u\n")
+
+
+def test_full_size_properties_cfg2(eng):
+    """BASELINE cfg 2 at full size (1,000,001 points), size-independent properties:
+    every status 0; V(n1) equals the source phasor exactly; KCL at the source node
+    (i_v1 = -i_r1); |V| decreases monotonically along the ladder; a 1/997 subsample matches
+    the oracle at 1e-9."""
+    import spicey_b200 as sp
+    ck = parse_netlist(w.rc_ladder(64))
+    freqs = np.array(sp.analysis.ac_frequencies(ck))
+    out = sp.simulate_ac_batch(ck, freqs, engine=eng)
+    assert out["status"].max() == 0
+    x, ie = out["x"][0], out["ielem"][0]
+    assert np.all(x[:, 0] == 1.0 + 0j)
+    assert np.max(np.abs(ie[:, -1] + ie[:, 0])) <= 1e-12 * np.max(np.abs(ie[:, 0]))
+    mags = np.abs(x[:, :64])
+    assert np.all(np.diff(mags, axis=1) <= 1e-12 * mags[:, :-1])
+    sub = slice(0, None, 997)
+    xr, ier, st = co.ac_solve(ck, freqs[sub], nthreads=8)
+    assert rel_err(x[sub], xr) <= AC_TOL
