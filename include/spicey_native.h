@@ -115,12 +115,16 @@ typedef struct spicey_stats {
   int64_t solves;            /* AC points, or TRAN matrix solves (sum of re-solve iterations) */
   int32_t tier;              /* kernel tier used (SPICEY_TIER_*) */
   int32_t n_devices;
+  int64_t fallback_solves;   /* sparse tier: systems re-solved by the dense kernel (pivot differed) */
+  int64_t program_cfma;      /* sparse tier: complex FMAs executed per system */
 } spicey_stats;
 
 enum {
   SPICEY_TIER_THREAD = 1,    /* one thread per system (Nvar <= 16) */
   SPICEY_TIER_CTA_SMEM = 2,  /* one CTA per system, matrix resident in shared memory */
-  SPICEY_TIER_CTA_GMEM = 3   /* one CTA per system, matrix in an L2-resident global scratch */
+  SPICEY_TIER_CTA_GMEM = 3,  /* one CTA per system, matrix in an L2-resident global scratch */
+  SPICEY_TIER_SPARSE = 4     /* one thread per system, static-pivot sparse LU program verified per
+                                system, dense pivoting kernel as fallback (single-instance sweeps) */
 };
 
 typedef struct spicey_handle spicey_handle;
@@ -193,7 +197,9 @@ int32_t spicey_tran_solve_device(spicey_handle* h, int32_t dev_index, const spic
 enum {
   SPICEY_FLAG_STRICT = 1u,      /* reference-order, unfused arithmetic (slow; parity testing) */
   SPICEY_FLAG_FORCE_GMEM = 2u,  /* testing: force the global-scratch tier */
-  SPICEY_FLAG_FORCE_CTA = 4u    /* testing: force a CTA tier even for tiny systems */
+  SPICEY_FLAG_FORCE_CTA = 4u,   /* testing: force a CTA tier even for tiny systems */
+  SPICEY_FLAG_DENSE = 8u,       /* never use the sparse program path */
+  SPICEY_FLAG_SPARSE = 16u      /* use the sparse program path even for small batches */
 };
 
 /* Measures this GPU's FP64 FMA peak with a register-only DFMA loop (GFLOP/s), the

@@ -23,16 +23,19 @@ struct AcArgs {
   double2* ielem;       // [p_count][n_ac_elem] or null
   int* status;          // [p_count]
   double2* scratch;     // global-scratch tier: gridDim.x * nvar*(nvar+1)
+  const long long* plist;  // optional: launch-local point indices to solve (fallback of the sparse path)
+  const int* pcount;       // optional: number of entries of plist (device-resident)
+  unsigned long long* fb_total;  // optional: running total of fallback solves (statistics)
 };
 
 // Shared-memory carve-up, identical on host (sizing) and device.
 struct AcSmem {
   size_t a_off, y_off, j_off, xs_off, mask_off, red_off, ends_off, meta_off, total;
-  __host__ __device__ AcSmem(int nvar, int n_elem, int MW, int nwarps, bool gmem) {
+  __host__ __device__ AcSmem(int nvar, int n_elem, int nV, int MW, int nwarps, bool gmem) {
     size_t o = 0;
     a_off = o; o += gmem ? 0 : sizeof(double2) * (size_t)nvar * (nvar + 1);
     y_off = o; o += sizeof(double2) * n_elem;
-    j_off = o; o += sizeof(double2) * n_elem;
+    j_off = o; o += sizeof(double2) * (nV > 0 ? nV : 1);
     xs_off = o; o += sizeof(double2) * nvar;
     red_off = o; o += sizeof(PivotPartial) * 2 * nwarps;
     ends_off = o; o += sizeof(int4) * n_elem;
@@ -79,7 +82,7 @@ __global__ void ac_cta_kernel(DevPlan P, AcArgs a) {
   const int t = threadIdx.x;
   const int nvar = P.nvar, ne = P.n_elem, MW = P.MW;
   const int nwarps = (blockDim.x + 31) >> 5;
-  const AcSmem L(nvar, ne, MW, nwarps, GMEM);
+  const AcSmem L(nvar, ne, P.nV, MW, nwarps, GMEM);
   cplx* A = GMEM ? (a.scratch + (size_t)blockIdx.x * nvar * (nvar + 1)) : (cplx*)(smem + L.a_off);
   cplx* Yv = (cplx*)(smem + L.y_off);
   cplx* Jv = (cplx*)(smem + L.j_off);
@@ -95,7 +98,10 @@ __global__ void ac_cta_kernel(DevPlan P, AcArgs a) {
   const int ldr = nvar;
   const GatherPlan& G = P.ac;
 
-  for (long long q = blockIdx.x; q < a.p_count; q += gridDim.x) {
+  const long long work = a.plist ? (long long)*a.pcount : a.p_count;
+  if (a.fb_total && blockIdx.x == 0 && t == 0 && work > 0) atomicAdd(a.fb_total, (unsigned long long)work);
+  for (long long qi = blockIdx.x; qi < work; qi += gridDim.x) {
+    const long long q = a.plist ? a.plist[qi] : qi;
     const long long p = a.p_begin + q;
     const long long inst = p / a.n_freq;
     const double f = a.freqs[p - inst * a.n_freq];
@@ -107,7 +113,7 @@ __global__ void ac_cta_kernel(DevPlan P, AcArgs a) {
       cplx Y, J;
       int st = ac_element_values<STRICT>(P, meta[e].x, meta[e].y, inst, f, Y, J);
       Yv[e] = Y;
-      Jv[e] = J;
+      if (meta[e].x == ELEM_V) Jv[e - P.off[ELEM_V]] = J;
       if (st != ST_OK) atomicMax(&s_status, st);  // R<=0 (3) outranks the L divide guard (2): R loop runs first
     }
     // Phase 2a: clear my row and reset its structural mask.
@@ -125,7 +131,7 @@ __global__ void ac_cta_kernel(DevPlan P, AcArgs a) {
           for (int c = G.ent_ptr[en]; c < G.ent_ptr[en + 1]; ++c) {
             int w = G.contrib[c];
             int src = (w >> 1) & 3, idx = w >> 3;
-            cplx v = src == SRC_Y ? Yv[idx] : (src == SRC_J ? Jv[idx] : make_double2(1.0, 0.0));
+            cplx v = src == SRC_Y ? Yv[idx] : (src == SRC_J ? Jv[idx - P.off[ELEM_V]] : make_double2(1.0, 0.0));
             if (w & 1) { acc.x -= v.x; acc.y -= v.y; } else { acc.x += v.x; acc.y += v.y; }
           }
           A[(size_t)G.ent_col[en] * ldr + t] = acc;

@@ -17,6 +17,7 @@
 #include <vector>
 
 #include "ac_kernels.cuh"
+#include "ac_sparse.cuh"
 #include "tran_kernels.cuh"
 
 using namespace spicey;
@@ -205,6 +206,12 @@ struct DeviceCtx {
   size_t smem_optin = 0;
   cudaStream_t compute = nullptr, copy = nullptr;
   Buffer plan, scratch, in0, in1, in2, out_x[2], out_i[2], out_s[2], aux0, aux1;
+  // sparse AC path: cached program (keyed by the element table), workspace, fallback list
+  Buffer sp_blob, sp_work, sp_fb;
+  SparseProgram sp;
+  SparseArgs sp_args;
+  uint64_t sp_key = 0;
+  bool sp_valid = false;
   std::vector<cudaEvent_t> events;
   cudaEvent_t get_event(size_t i) {
     while (events.size() <= i) {
@@ -275,17 +282,150 @@ struct spicey_handle {
 
 namespace {
 
+
+uint64_t fnv1a(uint64_t h, const void* data, size_t n) {
+  const unsigned char* p = (const unsigned char*)data;
+  for (size_t i = 0; i < n; ++i) { h ^= p[i]; h *= 1099511628211ull; }
+  return h;
+}
+
+uint64_t plan_key(const HostPlan& hp) {
+  uint64_t h = 1469598103934665603ull;
+  h = fnv1a(h, &hp.nn, sizeof(int));
+  h = fnv1a(h, hp.ends.data(), sizeof(int4) * hp.ends.size());
+  h = fnv1a(h, hp.meta.data(), sizeof(int2) * hp.meta.size());
+  h = fnv1a(h, hp.values.data(), sizeof(double) * hp.values.size());
+  return h ? h : 1;
+}
+
+// Builds (or reuses) the sparse program of this topology on ctx.  pilot_f: a representative frequency.
+// Returns SPICEY_SUCCESS with ctx.sp_valid=false when the sparse path does not apply.
+int prepare_sparse(DeviceCtx& ctx, const HostPlan& hp, double pilot_f, cudaStream_t stream) {
+  const uint64_t key = plan_key(hp);
+  if (ctx.sp_key == key) return SPICEY_SUCCESS;  // cached (valid or known not to apply)
+  ctx.sp_key = key;
+  ctx.sp_valid = false;
+  SparseProgram& sp = ctx.sp;
+  sp = SparseProgram();
+  const HostGather& G = hp.ac;
+  const int n_ent = (int)G.ent_col.size();
+  sp.ent_alpha.assign(n_ent, 0.0); sp.ent_beta.assign(n_ent, 0.0); sp.ent_gamma.assign(n_ent, 0.0);
+  sp.ent_jre.assign(n_ent, 0.0); sp.ent_jim.assign(n_ent, 0.0);
+  std::vector<int> rhs_slot;
+  std::vector<double> rhs_re, rhs_im;
+  for (int e = 0; e < hp.n_ac_elem; ++e)
+    if (hp.meta[e].x == ELEM_R && !(hp.values[hp.meta[e].y] > 0)) return SPICEY_SUCCESS;  // R<=0: dense kernel reports it
+  for (int en = 0; en < n_ent; ++en) {
+    bool has_j = false;
+    for (int c = G.ent_ptr[en]; c < G.ent_ptr[en + 1]; ++c) {
+      const int w = G.contrib[c], src = (w >> 1) & 3, idx = w >> 3;
+      const double sgn = (w & 1) ? -1.0 : 1.0;
+      if (src == SRC_ONE) { sp.ent_alpha[en] += sgn; continue; }
+      const int ty = hp.meta[idx].x;
+      const double* v = &hp.values[hp.meta[idx].y];
+      if (src == SRC_J) {  // source phasor, Complex.fromPolar (Complex.ts:16-19)
+        const double ph = (v[2] * kPi) / 180;
+        sp.ent_jre[en] += sgn * (v[1] * cos(ph));
+        sp.ent_jim[en] += sgn * (v[1] * sin(ph));
+        has_j = true;
+      } else if (ty == ELEM_R) sp.ent_alpha[en] += sgn * (1 / v[0]);
+      else if (ty == ELEM_C) sp.ent_beta[en] += sgn * v[0];
+      else if (ty == ELEM_L) sp.ent_gamma[en] += sgn * (1 / v[0]);
+    }
+    if (has_j) { rhs_slot.push_back(en); rhs_re.push_back(sp.ent_jre[en]); rhs_im.push_back(sp.ent_jim[en]); }
+  }
+  sp.el_a.assign(hp.n_ac_elem, 0.0); sp.el_b.assign(hp.n_ac_elem, 0.0); sp.el_g.assign(hp.n_ac_elem, 0.0);
+  for (int e = 0; e < hp.n_ac_elem; ++e) {
+    const int ty = hp.meta[e].x;
+    const double v = hp.values[hp.meta[e].y];
+    if (ty == ELEM_R) sp.el_a[e] = 1 / v;
+    else if (ty == ELEM_C) sp.el_b[e] = v;
+    else if (ty == ELEM_L) { sp.el_g[e] = 1 / v; sp.ind_L.push_back(v); }
+  }
+  PilotInput pin;
+  pin.n = hp.nvar;
+  pin.row_ptr = &G.row_ptr;
+  pin.ent_col = &G.ent_col;
+  const double w = (2 * kPi) * pilot_f;
+  pin.ent_val.resize(n_ent);
+  for (int en = 0; en < n_ent; ++en)
+    pin.ent_val[en] = std::complex<double>(sp.ent_alpha[en] + sp.ent_jre[en],
+                                           w * sp.ent_beta[en] - sp.ent_gamma[en] / w + sp.ent_jim[en]);
+  build_sparse_program(pin, sp);
+  if (!sp.ok) return SPICEY_SUCCESS;
+  // upload
+  std::vector<unsigned char> blob;
+  size_t o_code = push_blob(blob, sp.code), o_a = push_blob(blob, sp.ent_alpha), o_b = push_blob(blob, sp.ent_beta);
+  size_t o_g = push_blob(blob, sp.ent_gamma), o_rs = push_blob(blob, rhs_slot), o_rr = push_blob(blob, rhs_re);
+  size_t o_ri = push_blob(blob, rhs_im), o_ea = push_blob(blob, sp.el_a), o_eb = push_blob(blob, sp.el_b);
+  size_t o_eg = push_blob(blob, sp.el_g), o_l = push_blob(blob, sp.ind_L), o_ends = push_blob(blob, hp.ends);
+  size_t o_meta = push_blob(blob, hp.meta);
+  int rc = ctx.sp_blob.ensure(blob.size() + 16);
+  if (rc) return rc;
+  CUDA_TRY(cudaMemcpyAsync(ctx.sp_blob.p, blob.data(), blob.size(), cudaMemcpyHostToDevice, stream));
+  CUDA_TRY(cudaStreamSynchronize(stream));
+  unsigned char* b = (unsigned char*)ctx.sp_blob.p;
+  SparseArgs& a = ctx.sp_args;
+  memset(&a, 0, sizeof(a));
+  a.code = (const int*)(b + o_code);
+  a.n = hp.nvar; a.n_stamp = sp.n_stamp; a.n_slots = sp.n_slots; a.n_rhs_src = (int)rhs_slot.size();
+  a.ent_alpha = (const double*)(b + o_a); a.ent_beta = (const double*)(b + o_b); a.ent_gamma = (const double*)(b + o_g);
+  a.rhs_slot = (const int*)(b + o_rs); a.rhs_re = (const double*)(b + o_rr); a.rhs_im = (const double*)(b + o_ri);
+  a.el_a = (const double*)(b + o_ea); a.el_b = (const double*)(b + o_eb); a.el_g = (const double*)(b + o_eg);
+  a.ind_L = (const double*)(b + o_l); a.n_ind = (int)sp.ind_L.size();
+  a.ends = (const int4*)(b + o_ends); a.meta = (const int2*)(b + o_meta);
+  a.n_ac_elem = hp.n_ac_elem; a.nn = hp.nn; a.v_first = hp.off[ELEM_V];
+  ctx.sp_valid = true;
+  return SPICEY_SUCCESS;
+}
+
+// Sparse launch + dense fallback over the diverged list.  args.p_begin must be the start of a
+// single-instance frequency range (point index == frequency index).
+int launch_ac_dense(DeviceCtx& ctx, const HostPlan& hp, const DevPlan& dp, const AcArgs& args, uint32_t flags,
+                    cudaStream_t stream, int* tier_out, int64_t* launches);
+
+int launch_ac_sparse(DeviceCtx& ctx, const HostPlan& hp, const DevPlan& dp, const AcArgs& args, uint32_t flags,
+                     cudaStream_t stream, int* tier_out, int64_t* launches) {
+  const int block = 128;
+  long long T = std::min<long long>((args.p_count + block - 1) / block, (long long)ctx.sm_count * 8) * block;
+  size_t wbytes = sizeof(double2) * (size_t)(ctx.sp.n_slots + hp.nvar) * T;
+  int rc = ctx.sp_work.ensure(wbytes);
+  if (rc) return rc;
+  if ((rc = ctx.sp_fb.ensure(sizeof(long long) * args.p_count + 64))) return rc;
+  int* fb_count = (int*)ctx.sp_fb.p;
+  long long* fb_list = (long long*)((char*)ctx.sp_fb.p + 64);
+  CUDA_TRY(cudaMemsetAsync(fb_count, 0, sizeof(int), stream));
+  SparseArgs a = ctx.sp_args;
+  a.freqs = args.freqs + args.p_begin;
+  a.p_count = args.p_count;
+  a.W = (double2*)ctx.sp_work.p;
+  a.T = T;
+  a.x = args.x; a.ielem = args.ielem; a.status = args.status;
+  a.fb_list = fb_list; a.fb_count = fb_count;
+  ac_sparse_kernel<<<(unsigned)(T / block), block, 0, stream>>>(a);
+  CUDA_TRY(cudaGetLastError());
+  if (launches) ++*launches;
+  AcArgs d = args;
+  d.plist = fb_list;
+  d.pcount = fb_count;
+  d.fb_total = (unsigned long long*)((char*)ctx.sp_fb.p + 32);
+  rc = launch_ac_dense(ctx, hp, dp, d, flags, stream, nullptr, launches);
+  if (rc) return rc;
+  if (tier_out) *tier_out = SPICEY_TIER_SPARSE;
+  return SPICEY_SUCCESS;
+}
+
 // ---------------------------------------------------------------------------------
 // AC launch on one device (device pointers), asynchronous on `stream`.
-int launch_ac(DeviceCtx& ctx, const HostPlan& hp, const DevPlan& dp, const AcArgs& args, uint32_t flags,
+int launch_ac_dense(DeviceCtx& ctx, const HostPlan& hp, const DevPlan& dp, const AcArgs& args, uint32_t flags,
               cudaStream_t stream, int* tier_out, int64_t* launches) {
   if (args.p_count <= 0) return SPICEY_SUCCESS;
   const bool strict = flags & SPICEY_FLAG_STRICT;
   const int NT = round32(hp.nvar);
   const int nwarps = NT / 32;
-  AcSmem sm(hp.nvar, hp.n_elem, hp.MW, nwarps, false);
+  AcSmem sm(hp.nvar, hp.n_elem, hp.nV, hp.MW, nwarps, false);
   bool gmem = (flags & SPICEY_FLAG_FORCE_GMEM) || sm.total > ctx.smem_optin;
-  AcSmem L(hp.nvar, hp.n_elem, hp.MW, nwarps, gmem);
+  AcSmem L(hp.nvar, hp.n_elem, hp.nV, hp.MW, nwarps, gmem);
   if (L.total > ctx.smem_optin) return fail(SPICEY_ERR_UNSUPPORTED, "element table too large for shared memory");
   void (*kern)(DevPlan, AcArgs) =
       gmem ? (strict ? ac_cta_kernel<true, true> : ac_cta_kernel<false, true>)
@@ -307,6 +447,28 @@ int launch_ac(DeviceCtx& ctx, const HostPlan& hp, const DevPlan& dp, const AcArg
   if (tier_out) *tier_out = gmem ? SPICEY_TIER_CTA_GMEM : SPICEY_TIER_CTA_SMEM;
   if (launches) ++*launches;
   return SPICEY_SUCCESS;
+}
+
+
+// Dispatcher: sparse program path for a large single-instance sweep, dense pivoting kernel otherwise.
+int launch_ac(DeviceCtx& ctx, const HostPlan& hp, const DevPlan& dp, const AcArgs& args, uint32_t flags,
+              cudaStream_t stream, int* tier_out, int64_t* launches, double pilot_f, bool pilot_known) {
+  const bool want_sparse = !(flags & (SPICEY_FLAG_STRICT | SPICEY_FLAG_FORCE_GMEM | SPICEY_FLAG_DENSE)) &&
+                           dp.n_inst == 1 && dp.n_var == 0 &&
+                           (args.p_count >= 2048 || (flags & SPICEY_FLAG_SPARSE));
+  if (want_sparse) {
+    if (ctx.sp_key != plan_key(hp)) {
+      if (!pilot_known) {  // device-resident frequencies: fetch one representative value
+        CUDA_TRY(cudaMemcpyAsync(&pilot_f, args.freqs + args.p_begin + args.p_count / 2, sizeof(double),
+                                 cudaMemcpyDeviceToHost, stream));
+        CUDA_TRY(cudaStreamSynchronize(stream));
+      }
+      int rc = prepare_sparse(ctx, hp, pilot_f, stream);
+      if (rc) return rc;
+    }
+    if (ctx.sp_valid) return launch_ac_sparse(ctx, hp, dp, args, flags, stream, tier_out, launches);
+  }
+  return launch_ac_dense(ctx, hp, dp, args, flags, stream, tier_out, launches);
 }
 
 int launch_tran(DeviceCtx& ctx, const HostPlan& hp, const DevPlan& dp, const TranArgs& args, uint32_t flags,
@@ -429,7 +591,7 @@ void spicey_destroy(spicey_handle* h) {
     cudaSetDevice(c.dev);
     cudaDeviceSynchronize();
     Buffer* bufs[] = {&c.plan, &c.scratch, &c.in0, &c.in1, &c.in2, &c.out_x[0], &c.out_x[1], &c.out_i[0],
-                      &c.out_i[1], &c.out_s[0], &c.out_s[1], &c.aux0, &c.aux1};
+                      &c.out_i[1], &c.out_s[0], &c.out_s[1], &c.aux0, &c.aux1, &c.sp_blob, &c.sp_work, &c.sp_fb};
     for (Buffer* b : bufs) b->release();
     for (auto e : c.events) cudaEventDestroy(e);
     cudaStreamDestroy(c.compute);
@@ -441,6 +603,16 @@ void spicey_destroy(spicey_handle* h) {
 int32_t spicey_get_stats(const spicey_handle* h, spicey_stats* out) {
   if (!h || !out) return fail(SPICEY_ERR_INVALID, "NULL argument");
   *out = h->stats;
+  if (out->fallback_solves < 0) {  // read the device-side counters (synchronises the devices)
+    long long total = 0;
+    for (const auto& c : h->devs) {
+      if (!c.sp_fb.p) continue;
+      unsigned long long v = 0;
+      cudaSetDevice(c.dev);
+      if (cudaMemcpy(&v, (const char*)c.sp_fb.p + 32, sizeof(v), cudaMemcpyDeviceToHost) == cudaSuccess) total += (long long)v;
+    }
+    out->fallback_solves = total;
+  }
   return SPICEY_SUCCESS;
 }
 
@@ -477,13 +649,17 @@ int32_t spicey_ac_solve_device(spicey_handle* h, int32_t dev_index, const spicey
   dp.var_values = sweep ? sweep->var_values : nullptr;
   AcArgs a;
   a.freqs = d_freqs; a.n_freq = n_freq; a.p_begin = 0; a.p_count = dp.n_inst * n_freq;
-  a.x = (double2*)d_x; a.ielem = (double2*)d_ielem; a.status = d_status; a.scratch = nullptr;
+  a.x = (double2*)d_x; a.ielem = (double2*)d_ielem; a.status = d_status; a.scratch = nullptr; a.plist = nullptr; a.pcount = nullptr; a.fb_total = nullptr;
   int tier = 0;
   int64_t launches = 0;
-  rc = launch_ac(ctx, hp, dp, a, flags, st, &tier, &launches);
+  if ((rc = ctx.sp_fb.ensure(sizeof(long long) * a.p_count + 64))) return rc;
+  CUDA_TRY(cudaMemsetAsync(ctx.sp_fb.p, 0, 64, st));
+  rc = launch_ac(ctx, hp, dp, a, flags, st, &tier, &launches, 0.0, false);
   if (rc) return rc;
   h->stats.kernel_launches = launches;
   h->stats.tier = tier;
+  h->stats.fallback_solves = -1;  // resolved lazily by spicey_get_stats
+  h->stats.program_cfma = tier == SPICEY_TIER_SPARSE ? ctx.sp.n_fma : 0;
   h->stats.solves = a.p_count;
   h->stats.h2d_bytes = (int64_t)h->blob.size();
   h->stats.d2h_bytes = 0;
@@ -536,6 +712,8 @@ int32_t spicey_ac_solve(spicey_handle* h, const spicey_elem_table* table, const 
     }
     const long long cnt = s.hi - s.lo;
     const long long csz = std::min(chunk, cnt);
+    if ((rc = ctx.sp_fb.ensure(sizeof(long long) * csz + 64))) return rc;
+    CUDA_TRY(cudaMemsetAsync(ctx.sp_fb.p, 0, 64, ctx.compute));
     for (int b = 0; b < 2; ++b) {
       if ((rc = ctx.out_x[b].ensure(xrow * csz))) return rc;
       if (ielem && (rc = ctx.out_i[b].ensure(irow * csz))) return rc;
@@ -551,9 +729,9 @@ int32_t spicey_ac_solve(spicey_handle* h, const spicey_elem_table* table, const 
       AcArgs a;
       a.freqs = (const double*)ctx.in0.p; a.n_freq = n_freq; a.p_begin = lo; a.p_count = n;
       a.x = (double2*)ctx.out_x[b].p; a.ielem = ielem ? (double2*)ctx.out_i[b].p : nullptr;
-      a.status = (int*)ctx.out_s[b].p; a.scratch = nullptr;
+      a.status = (int*)ctx.out_s[b].p; a.scratch = nullptr; a.plist = nullptr; a.pcount = nullptr; a.fb_total = nullptr;
       CUDA_TRY(cudaEventRecord(ks, ctx.compute));
-      rc = launch_ac(ctx, hp, dp, a, flags, ctx.compute, &tier, &launches);
+      rc = launch_ac(ctx, hp, dp, a, flags, ctx.compute, &tier, &launches, freqs[n_freq / 2], true);
       if (rc) return rc;
       CUDA_TRY(cudaEventRecord(ke, ctx.compute));
       CUDA_TRY(cudaStreamWaitEvent(ctx.copy, ke, 0));
@@ -588,6 +766,8 @@ int32_t spicey_ac_solve(spicey_handle* h, const spicey_elem_table* table, const 
   h->stats.d2h_bytes = d2h;
   h->stats.solves = P;
   h->stats.tier = tier;
+  h->stats.fallback_solves = -1;
+  h->stats.program_cfma = tier == SPICEY_TIER_SPARSE ? h->devs[0].sp.n_fma : 0;
   return SPICEY_SUCCESS;
 }
 

@@ -15,8 +15,8 @@ from . import build as _build
 ELEM_R, ELEM_C, ELEM_L, ELEM_V, ELEM_S, ELEM_D = range(6)
 VALUE_SLOTS = {ELEM_R: 1, ELEM_C: 1, ELEM_L: 1, ELEM_V: 3, ELEM_S: 4, ELEM_D: 2}
 ST_OK, ST_SINGULAR, ST_CDIV, ST_R_NONPOS = 0, 1, 2, 3
-FLAG_STRICT, FLAG_FORCE_GMEM, FLAG_FORCE_CTA = 1, 2, 4
-TIER_THREAD, TIER_CTA_SMEM, TIER_CTA_GMEM = 1, 2, 3
+FLAG_STRICT, FLAG_FORCE_GMEM, FLAG_FORCE_CTA, FLAG_DENSE, FLAG_SPARSE = 1, 2, 4, 8, 16
+TIER_THREAD, TIER_CTA_SMEM, TIER_CTA_GMEM, TIER_SPARSE = 1, 2, 3, 4
 SUCCESS, ERR_INVALID, ERR_NO_DEVICE, ERR_CUDA, ERR_UNSUPPORTED = 0, 1, 2, 3, 4
 
 EXPORTS = [
@@ -43,7 +43,7 @@ class SweepStruct(C.Structure):
 class StatsStruct(C.Structure):
     _fields_ = [("kernel_ms", C.c_double), ("total_ms", C.c_double), ("kernel_launches", C.c_int64),
                 ("h2d_bytes", C.c_int64), ("d2h_bytes", C.c_int64), ("solves", C.c_int64), ("tier", C.c_int32),
-                ("n_devices", C.c_int32)]
+                ("n_devices", C.c_int32), ("fallback_solves", C.c_int64), ("program_cfma", C.c_int64)]
 
 
 class NativeError(RuntimeError):

@@ -74,7 +74,8 @@ def test_ac_readme_rc(eng, flags, tol):
     assert rel_err(out["ielem"], ie) <= tol
 
 
-@pytest.mark.parametrize("flags,tol", [(0, AC_TOL), (native.FLAG_STRICT, 1e-12), (native.FLAG_FORCE_GMEM, AC_TOL)])
+@pytest.mark.parametrize("flags,tol", [(native.FLAG_DENSE, AC_TOL), (native.FLAG_STRICT, 1e-12),
+                                       (native.FLAG_FORCE_GMEM, AC_TOL), (native.FLAG_SPARSE, AC_TOL)])
 def test_ac_ladder64_slice(eng, flags, tol):
     """cfg 2 topology (Nvar = 65), every 997th of the 1,000,001 frequencies."""
     import spicey_b200 as sp
@@ -83,6 +84,9 @@ def test_ac_ladder64_slice(eng, flags, tol):
     assert freqs.shape[0] == 1000001
     sub = freqs[::997]
     out, x, ie, st, _ = ac_case(eng, text, sub, flags)
+    if flags == native.FLAG_SPARSE:
+        stt = eng.stats()
+        assert stt["tier"] == native.TIER_SPARSE and stt["fallback_solves"] == 0 and stt["program_cfma"] > 0
     assert out["status"].max() == 0 and st.max() == 0
     assert rel_err(out["x"], x) <= tol, rel_err(out["x"], x)
     assert rel_err(out["ielem"], ie) <= tol
@@ -92,18 +96,23 @@ def test_ac_ladder64_slice(eng, flags, tol):
     assert np.max(np.abs(dphi)) <= tol
 
 
-def test_ac_mesh16_slice_global_scratch_tier(eng):
-    """cfg 4 topology (Nvar = 257): does not fit one SM's shared memory -> global-scratch tier."""
+@pytest.mark.parametrize("flags,tier", [(native.FLAG_DENSE, native.TIER_CTA_GMEM), (native.FLAG_SPARSE, native.TIER_SPARSE)])
+def test_ac_mesh16_slice(eng, flags, tier):
+    """cfg 4 topology (Nvar = 257): does not fit one SM's shared memory -> global-scratch tier (dense)
+    or the sparse program tier."""
     import spicey_b200 as sp
     text = w.rc_mesh(16)
     freqs = np.array(sp.analysis.ac_frequencies(parse_netlist(text)))
     assert freqs.shape[0] == 8000001
     sub = freqs[::200003]
-    out, x, ie, st, _ = ac_case(eng, text, sub)
-    assert eng.stats()["tier"] == native.TIER_CTA_GMEM
+    out, x, ie, st, _ = ac_case(eng, text, sub, flags)
+    assert eng.stats()["tier"] == tier
     assert out["status"].max() == 0 and st.max() == 0
     assert rel_err(out["x"], x) <= AC_TOL, rel_err(out["x"], x)
     assert rel_err(out["ielem"], ie) <= AC_TOL
+
+
+FALLBACKS = []
 
 
 def random_rlc_netlist(rng, n_nodes, n_elem, n_v=2):
@@ -129,14 +138,22 @@ def test_ac_random_rlc_networks(eng, n_nodes, n_elem):
     rng = np.random.default_rng(n_nodes * 1000 + n_elem)
     text = random_rlc_netlist(rng, n_nodes, n_elem, n_v=min(2, n_nodes))
     freqs = sp.analysis.ac_frequencies(parse_netlist(text))
-    for flags, tol in ((0, AC_TOL), (native.FLAG_STRICT, 1e-11)):
+    for flags, tol in ((native.FLAG_DENSE, AC_TOL), (native.FLAG_STRICT, 1e-11), (native.FLAG_SPARSE, AC_TOL)):
         out, x, ie, st, _ = ac_case(eng, text, freqs, flags)
+        if flags == native.FLAG_SPARSE:
+            FALLBACKS.append(eng.stats()["fallback_solves"])
         assert np.array_equal(out["status"], st)
         assert st.max() == 0
         scale = np.max(np.abs(x), axis=2, keepdims=True)  # mixed-magnitude solutions: error relative to the row's max
         assert np.max(np.abs(out["x"] - x) / scale) <= tol
         iscale = np.max(np.abs(ie), axis=2, keepdims=True)
         assert np.max(np.abs(out["ielem"] - ie) / iscale) <= tol
+
+
+def test_sparse_fallback_path_was_exercised():
+    """Across the random networks the pivot order changes along the 5-decade sweep for some points:
+    those must have gone through the dense fallback (and matched the oracle above)."""
+    assert len(FALLBACKS) >= 8 and sum(FALLBACKS) > 0, FALLBACKS
 
 
 def test_ac_sweep_instances(eng):
@@ -169,8 +186,14 @@ def test_ac_error_statuses_do_not_poison_batch(eng):
     assert (st == native.ST_SINGULAR).all() and np.array_equal(out["status"], st)
     # inductor with 1e-15 <= 2*pi*f*L < 3.2e-8 -> "Complex divide by ~0" (hazard H5)
     text = "* cdiv\nv1 a 0 ac 1\nl1 a b 1e-10\nr1 b 0 1k\n.ac lin 2 1 2\n"
-    out, x, ie, st, _ = ac_case(eng, text, [1.0, 1e6])
-    assert st[0, 0] == native.ST_CDIV and st[0, 1] == 0 and np.array_equal(out["status"], st)
+    for flags in (0, native.FLAG_SPARSE):
+        out, x, ie, st, _ = ac_case(eng, text, [1.0, 1e6], flags)
+        assert st[0, 0] == native.ST_CDIV and st[0, 1] == 0 and np.array_equal(out["status"], st)
+        assert rel_err(out["x"][0, 1], x[0, 1]) <= AC_TOL
+    for text in ("* sing\nv1 a 0 ac 1\nv2 a 0 ac 1\nr1 a 0 1k\n.ac lin 2 1 2\n",
+                 "* bad\nv1 1 0 ac 1\nr1 1 2 -5\nc1 2 0 1u\n.ac dec 2 1 10\n"):
+        out, x, ie, st, _ = ac_case(eng, text, [1.0, 2.0], native.FLAG_SPARSE)
+        assert st.min() > 0 and np.array_equal(out["status"], st)
     import spicey_b200 as sp
     with pytest.raises(ValueError, match="R r1 must be > 0"):
         sp.simulate("* bad\nv1 1 0 ac 1\nr1 1 2 -5\nc1 2 0 1u\n.ac dec 2 1 10\n")
@@ -287,9 +310,11 @@ def test_full_size_properties_cfg2(eng):
     ck = parse_netlist(w.rc_ladder(64))
     freqs = np.array(sp.analysis.ac_frequencies(ck))
     out = sp.simulate_ac_batch(ck, freqs, engine=eng)
+    stt = eng.stats()
+    assert stt["tier"] == native.TIER_SPARSE and stt["fallback_solves"] == 0
     assert out["status"].max() == 0
     x, ie = out["x"][0], out["ielem"][0]
-    assert np.all(x[:, 0] == 1.0 + 0j)
+    assert np.max(np.abs(x[:, 0] - 1.0)) <= 1e-15
     assert np.max(np.abs(ie[:, -1] + ie[:, 0])) <= 1e-12 * np.max(np.abs(ie[:, 0]))
     mags = np.abs(x[:, :64])
     assert np.all(np.diff(mags, axis=1) <= 1e-12 * mags[:, :-1])
