@@ -1,0 +1,55 @@
+// Drop-in replacement of lib/analysis/simulateAC.ts: same signature and result shape,
+// loop body (:80-127 of the reference) replaced by pack -> FFI -> unpack.
+import { Complex } from "../math/Complex"
+import type { ParsedCircuit } from "../parsing/parseNetlist"
+import { logspace } from "../utils/logspace"
+import { acSolve, STATUS } from "../native/spiceyNative"
+import { packCircuit } from "./packCircuit"
+
+function buildFrequencyArray(mode: "dec" | "lin", N: number, f1: number, f2: number) {
+  if (mode === "dec") return logspace(f1, f2, N)
+  const npts = Math.max(2, N)
+  const step = (f2 - f1) / (npts - 1)
+  return Array.from({ length: npts }, (_, i) => f1 + i * step)
+}
+
+/** Complex[] view over an interleaved Float64Array slab (SURVEY.md §8 f1). */
+function complexSeries(slab: Float64Array, offset: number, stride: number, count: number): Complex[] {
+  return new Proxy([] as Complex[], {
+    get(_t, key) {
+      if (key === "length") return count
+      const k = typeof key === "string" ? Number(key) : NaN
+      if (Number.isInteger(k) && k >= 0 && k < count)
+        return new Complex(slab[2 * (offset + k * stride)], slab[2 * (offset + k * stride) + 1])
+      return (Array.prototype as any)[key]
+    },
+  })
+}
+
+function simulateAC(ckt: ParsedCircuit) {
+  if (!ckt.analyses.ac) return null
+  const { mode, N, f1, f2 } = ckt.analyses.ac
+  const freqs = buildFrequencyArray(mode, N, f1, f2)
+  const table = packCircuit(ckt)
+  const { x, ielem, status, nvar } = acSolve(table, Float64Array.from(freqs))
+  for (let k = 0; k < status.length; k++) {
+    const st = status[k]
+    if (st === STATUS.OK) continue
+    if (st === STATUS.R_NONPOS) {
+      const bad = ckt.R.find((r) => r.R <= 0)
+      throw new Error(`R ${bad?.name} must be > 0`)
+    }
+    throw new Error(st === STATUS.SINGULAR ? "Singular matrix (complex)" : "Complex divide by ~0")
+  }
+  const nodeVoltages: Record<string, Complex[]> = {}
+  ckt.nodes.rev.forEach((name, id) => {
+    if (id !== 0) nodeVoltages[name] = complexSeries(x, id - 1, nvar, freqs.length)
+  })
+  const elementCurrents: Record<string, Complex[]> = {}
+  table.names.slice(0, table.nAcElem).forEach((name, e) => {
+    elementCurrents[name] ||= complexSeries(ielem, e, table.nAcElem, freqs.length)
+  })
+  return { freqs, nodeVoltages, elementCurrents }
+}
+
+export { simulateAC }

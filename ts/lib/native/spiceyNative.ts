@@ -1,0 +1,116 @@
+// lib/native/spiceyNative.ts — bun:ffi binding of include/spicey_native.h.
+//
+// NOT EXECUTED IN THIS REPO: the build image and the GPU box have no bun/node
+// (SURVEY.md §8c), so this file is the reference-side half of the drop-in, kept
+// thin and mechanical; the same ABI is exercised from Python (spicey_b200/native.py)
+// by tests/.  Drop it into the reference as lib/native/spiceyNative.ts.
+import { dlopen, FFIType, ptr, CString, type Pointer } from "bun:ffi"
+
+const { i32, i64, u32, f64, ptr: p, cstring } = FFIType
+
+const LIB_PATH =
+  process.env.SPICEY_NATIVE_LIB ?? `${import.meta.dir}/libspicey_native.so`
+
+const { symbols: C } = dlopen(LIB_PATH, {
+  spicey_native_abi_version: { args: [], returns: i32 },
+  spicey_device_count: { args: [], returns: i32 },
+  spicey_last_error: { args: [], returns: cstring },
+  spicey_create: { args: [p, i32, p], returns: i32 },
+  spicey_destroy: { args: [p], returns: FFIType.void },
+  spicey_get_stats: { args: [p, p], returns: i32 },
+  spicey_ac_solve: { args: [p, p, p, p, i64, p, p, p, u32], returns: i32 },
+  spicey_tran_solve: {
+    args: [p, p, p, f64, i64, p, p, p, p, p, p, p, p, u32],
+    returns: i32,
+  },
+})
+
+export const ELEM = { R: 0, C: 1, L: 2, V: 3, S: 4, D: 5 } as const
+export const STATUS = { OK: 0, SINGULAR: 1, CDIV: 2, R_NONPOS: 3 } as const
+
+/** Flat element table: typed arrays in the layout of `spicey_elem_table`. */
+export type ElemTable = {
+  nNodes: number
+  type: Int32Array
+  n1: Int32Array
+  n2: Int32Array
+  nc1: Int32Array
+  nc2: Int32Array
+  valueIdx: Int32Array
+  values: Float64Array
+  names: string[]
+  nVsrc: number
+  nAcElem: number
+  nState: number
+}
+
+function check(rc: number) {
+  if (rc !== 0)
+    throw new Error(`spicey_native error ${rc}: ${C.spicey_last_error()}`)
+}
+
+/** struct spicey_elem_table: 4 x int32 then 7 pointers (64 bytes). */
+function tableStruct(t: ElemTable) {
+  const buf = new ArrayBuffer(16 + 7 * 8)
+  const dv = new DataView(buf)
+  dv.setInt32(0, t.nNodes, true)
+  dv.setInt32(4, t.type.length, true)
+  dv.setInt32(8, t.values.length, true)
+  const ptrs = [t.type, t.n1, t.n2, t.nc1, t.nc2, t.valueIdx, t.values]
+  ptrs.forEach((a, i) =>
+    dv.setBigUint64(16 + 8 * i, BigInt(a.length ? ptr(a) : 0), true),
+  )
+  return new Uint8Array(buf)
+}
+
+let handle: Pointer | null = null
+function getHandle(): Pointer {
+  if (handle) return handle
+  if (C.spicey_native_abi_version() !== 1)
+    throw new Error("spicey_native ABI version mismatch")
+  const out = new BigUint64Array(1)
+  check(C.spicey_create(null, 0, ptr(out)))
+  handle = Number(out[0]) as unknown as Pointer
+  return handle
+}
+
+export function acSolve(t: ElemTable, freqs: Float64Array) {
+  const nvar = t.nNodes + t.nVsrc
+  const P = freqs.length
+  const x = new Float64Array(P * nvar * 2)
+  const ielem = new Float64Array(P * t.nAcElem * 2)
+  const status = new Int32Array(P)
+  const ts = tableStruct(t)
+  check(
+    C.spicey_ac_solve(
+      getHandle(), ptr(ts), null, ptr(freqs), BigInt(P), ptr(x),
+      t.nAcElem ? ptr(ielem) : null, ptr(status), 0,
+    ),
+  )
+  return { x, ielem, status, nvar }
+}
+
+export function tranSolve(
+  t: ElemTable,
+  dt: number,
+  steps: number,
+  vsrc: Float64Array,
+  vsrcMask: Int32Array,
+  state0: Float64Array,
+) {
+  const S1 = steps + 1
+  const v = new Float64Array(S1 * t.nNodes)
+  const ielem = new Float64Array(S1 * t.type.length)
+  const stateOut = new Float64Array(Math.max(1, t.nState))
+  const status = new Int32Array(1)
+  const ts = tableStruct(t)
+  check(
+    C.spicey_tran_solve(
+      getHandle(), ptr(ts), null, dt, BigInt(steps),
+      vsrc.length ? ptr(vsrc) : null, ptr(vsrcMask),
+      state0.length ? ptr(state0) : null, ptr(v),
+      t.type.length ? ptr(ielem) : null, ptr(stateOut), null, ptr(status), 0,
+    ),
+  )
+  return { v, ielem, stateOut, status }
+}
