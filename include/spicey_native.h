@@ -199,7 +199,8 @@ enum {
   SPICEY_FLAG_FORCE_GMEM = 2u,  /* testing: force the global-scratch tier */
   SPICEY_FLAG_FORCE_CTA = 4u,   /* testing: force a CTA tier even for tiny systems */
   SPICEY_FLAG_DENSE = 8u,       /* never use the sparse program path */
-  SPICEY_FLAG_SPARSE = 16u      /* use the sparse program path even for small batches */
+  SPICEY_FLAG_SPARSE = 16u,     /* use the sparse program path even for small batches */
+  SPICEY_FLAG_GENERIC_THREAD = 32u /* testing: transient thread tier without the register-resident kernel */
 };
 
 /* Measures this GPU's FP64 FMA peak with a register-only DFMA loop (GFLOP/s), the

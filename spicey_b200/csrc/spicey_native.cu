@@ -19,6 +19,7 @@
 #include "ac_kernels.cuh"
 #include "ac_sparse.cuh"
 #include "tran_kernels.cuh"
+#include "tran_small.cuh"
 
 using namespace spicey;
 
@@ -476,6 +477,30 @@ int launch_tran(DeviceCtx& ctx, const HostPlan& hp, const DevPlan& dp, const Tra
   if (args.n_local <= 0) return SPICEY_SUCCESS;
   const bool strict = flags & SPICEY_FLAG_STRICT;
   const int n_ent = (int)hp.tran.ent_col.size(), n_con = (int)hp.tran.contrib.size();
+  // Register-resident small-system kernel (Nvar <= 6).
+  if (!(flags & (SPICEY_FLAG_FORCE_CTA | SPICEY_FLAG_FORCE_GMEM | SPICEY_FLAG_GENERIC_THREAD)) && hp.nvar <= 6) {
+    const bool dyn = hp.off[ELEM_D + 1] > hp.off[ELEM_S];
+    typedef void (*KernT)(DevPlan, TranArgs);
+    KernT kern = nullptr;
+    int nv = hp.nvar <= 2 ? 2 : hp.nvar <= 3 ? 3 : hp.nvar <= 4 ? 4 : 6;
+    switch (nv) {
+      case 2: kern = strict ? (KernT)tran_small_kernel<2, true> : (KernT)tran_small_kernel<2, false>; break;
+      case 3: kern = strict ? (KernT)tran_small_kernel<3, true> : (KernT)tran_small_kernel<3, false>; break;
+      case 4: kern = strict ? (KernT)tran_small_kernel<4, true> : (KernT)tran_small_kernel<4, false>; break;
+      default: kern = strict ? (KernT)tran_small_kernel<6, true> : (KernT)tran_small_kernel<6, false>; break;
+    }
+    for (int nt = 128; nt >= 32; nt >>= 1) {
+      TranSmallSmem L(nv, hp.n_elem, hp.n_state, dyn, nt);
+      if (L.total > (nt == 32 ? ctx.smem_optin : (size_t)74 * 1024)) continue;
+      CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total));
+      long long grid = (args.n_local + nt - 1) / nt;
+      kern<<<(unsigned)grid, nt, L.total, stream>>>(dp, args);
+      CUDA_TRY(cudaGetLastError());
+      if (tier_out) *tier_out = SPICEY_TIER_THREAD;
+      if (launches) ++*launches;
+      return SPICEY_SUCCESS;
+    }
+  }
   // Thread tier when the per-thread footprint leaves room for >= 32 threads per CTA.
   if (!(flags & (SPICEY_FLAG_FORCE_CTA | SPICEY_FLAG_FORCE_GMEM)) && hp.nvar <= 16) {
     for (int nt = 128; nt >= 32; nt >>= 1) {

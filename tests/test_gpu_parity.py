@@ -208,7 +208,9 @@ GOLDEN_TRAN = ["transient01_rc_pulse", "two_probes", "switch_vt_vh", "vswitch_pw
 
 
 @pytest.mark.parametrize("name", GOLDEN_TRAN)
-@pytest.mark.parametrize("flags", [0, native.FLAG_STRICT, native.FLAG_FORCE_CTA, native.FLAG_FORCE_GMEM])
+@pytest.mark.parametrize("flags", [0, native.FLAG_STRICT, native.FLAG_GENERIC_THREAD,
+                                   native.FLAG_GENERIC_THREAD | native.FLAG_STRICT, native.FLAG_FORCE_CTA,
+                                   native.FLAG_FORCE_GMEM])
 def test_tran_reference_netlists(eng, golden, name, flags):
     """Every transient netlist of the reference's tests through the drop-in simulateTRAN, all tiers."""
     import spicey_b200 as sp
@@ -257,10 +259,10 @@ def tran_batch_case(eng, text, n_inst, overrides, flags=0):
     return got, v, ie, iters, st
 
 
-@pytest.mark.parametrize("flags", [0, native.FLAG_FORCE_CTA])
+@pytest.mark.parametrize("flags", [0, native.FLAG_GENERIC_THREAD, native.FLAG_FORCE_CTA])
 def test_tran_rlc_tank_monte_carlo_slice(eng, flags):
     """cfg 3 on its first 512 instances: steps = 1001 (hazard H2), +-5 % R/L/C."""
-    n = 512 if flags == 0 else 64
+    n = 64 if flags == native.FLAG_FORCE_CTA else 512
     ov = {k: v[:n] for k, v in w.rlc_tank_overrides(65536).items()}
     got, v, ie, iters, st = tran_batch_case(eng, w.RLC_TANK, n, ov, flags)
     assert got["steps"] == 1001 and got["v"].shape == (1002, 2, n)
@@ -272,10 +274,10 @@ def test_tran_rlc_tank_monte_carlo_slice(eng, flags):
     assert np.max(np.abs(got["ielem"] - ref_i)) <= TRAN_TOL * np.max(np.abs(ref_i))
 
 
-@pytest.mark.parametrize("flags", [0, native.FLAG_FORCE_CTA])
+@pytest.mark.parametrize("flags", [0, native.FLAG_GENERIC_THREAD, native.FLAG_FORCE_CTA])
 def test_tran_rectifier_sweep_slice(eng, flags):
     """cfg 5 (diode, single linearisation per step) on 400 instances spread over the sweep."""
-    n = 400 if flags == 0 else 48
+    n = 48 if flags == native.FLAG_FORCE_CTA else 400
     full = w.rectifier_overrides(100000)
     pick = np.linspace(0, 99999, n).astype(int)
     ov = {k: v[pick] for k, v in full.items()}
