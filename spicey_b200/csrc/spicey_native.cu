@@ -482,19 +482,19 @@ int launch_tran(DeviceCtx& ctx, const HostPlan& hp, const DevPlan& dp, const Tra
     const bool dyn = hp.off[ELEM_D + 1] > hp.off[ELEM_S];
     typedef void (*KernT)(DevPlan, TranArgs);
     KernT kern = nullptr;
+    constexpr int NT = 64;  // small CTAs: more CTAs per SM, better balance for ~1e5-instance batches
     int nv = hp.nvar <= 2 ? 2 : hp.nvar <= 3 ? 3 : hp.nvar <= 4 ? 4 : 6;
     switch (nv) {
-      case 2: kern = strict ? (KernT)tran_small_kernel<2, true> : (KernT)tran_small_kernel<2, false>; break;
-      case 3: kern = strict ? (KernT)tran_small_kernel<3, true> : (KernT)tran_small_kernel<3, false>; break;
-      case 4: kern = strict ? (KernT)tran_small_kernel<4, true> : (KernT)tran_small_kernel<4, false>; break;
-      default: kern = strict ? (KernT)tran_small_kernel<6, true> : (KernT)tran_small_kernel<6, false>; break;
+      case 2: kern = strict ? (KernT)tran_small_kernel<2, NT, true> : (KernT)tran_small_kernel<2, NT, false>; break;
+      case 3: kern = strict ? (KernT)tran_small_kernel<3, NT, true> : (KernT)tran_small_kernel<3, NT, false>; break;
+      case 4: kern = strict ? (KernT)tran_small_kernel<4, NT, true> : (KernT)tran_small_kernel<4, NT, false>; break;
+      default: kern = strict ? (KernT)tran_small_kernel<6, NT, true> : (KernT)tran_small_kernel<6, NT, false>; break;
     }
-    for (int nt = 128; nt >= 32; nt >>= 1) {
-      TranSmallSmem L(nv, hp.n_elem, hp.n_state, dyn, nt);
-      if (L.total > (nt == 32 ? ctx.smem_optin : (size_t)74 * 1024)) continue;
+    TranSmallSmem L(nv, hp.n_elem, hp.n_state, dyn, NT);
+    if (L.total <= ctx.smem_optin) {
       CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total));
-      long long grid = (args.n_local + nt - 1) / nt;
-      kern<<<(unsigned)grid, nt, L.total, stream>>>(dp, args);
+      long long grid = (args.n_local + NT - 1) / NT;
+      kern<<<(unsigned)grid, NT, L.total, stream>>>(dp, args);
       CUDA_TRY(cudaGetLastError());
       if (tier_out) *tier_out = SPICEY_TIER_THREAD;
       if (launches) ++*launches;

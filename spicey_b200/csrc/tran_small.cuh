@@ -3,28 +3,39 @@
 // simulateTRAN.ts:146-238) in one launch.
 //
 // What differs from the generic thread tier (tran_kernels.cuh):
-//  * NV is a template parameter: the LU factors, the right-hand side and the solution live in
-//    REGISTERS, every loop over matrix indices is unrolled, pivoting is a chain of selects.
+//  * NV (padded system size) and NT (threads per CTA) are template parameters: the LU factors, the
+//    right-hand side and the solution live in REGISTERS, every loop over matrix indices is unrolled
+//    without run-time guards (a system smaller than NV is padded with identity rows, which never win
+//    a pivot search), pivoting is a chain of selects, and every shared-memory address is
+//    base + compile-time stride.
 //  * Stamping follows the reference literally — per-type element loops in the order R, C, L, S,
 //    V, D (simulateTRAN.ts:35-101) scattering into a per-thread [entry][thread] shared-memory
 //    image with one extra row/column that absorbs ground stamps, so the loops are branch-free
-//    and the floating-point summation order is the reference's.
+//    and the floating-point summation order is the reference's.  Node ids are converted once per
+//    CTA into byte offsets of that image.
 //  * The reference re-stamps and re-factors the matrix at every step (:152-157).  The matrix
 //    only changes when a switch toggles or a diode is re-linearised, and Gaussian elimination is
 //    deterministic, so the kernel factors once and afterwards only replays the recorded row
 //    swaps and multipliers on the new right-hand side: the same operations on the same operands
 //    in the same order, i.e. the reference's numbers, at O(n^2) instead of O(n^3) per step.
 //    (Circuits with diodes re-factor every solve; circuits with switches when a state changed.)
-//  * x, the companion state and per-element constants stay in shared memory because element
-//    loops index them with run-time node ids.
 #pragma once
 #include "tran_kernels.cuh"
 
 namespace spicey {
 
+// Per-element record in shared memory: byte offsets into the per-thread arrays.
+struct SmallElem {
+  int x1, x2;    // offsets of x[n1], x[n2] (also of b[n1], b[n2]); ground -> slot NV
+  int c1, c2;    // switch control nodes
+  int st;        // offset of the element's state slot (or of a scratch slot)
+  int ec;        // offset of the element's 4 constants
+  int a11, a22, a12, a21;  // offsets of A(n1,n1), A(n2,n2), A(n1,n2), A(n2,n1)
+};
+
 struct TranSmallSmem {
-  size_t per_thread_doubles, ends_off, total;
-  int o_ac, o_as, o_b, o_x, o_st, o_ec;  // per-thread array offsets in doubles (each scaled by NT)
+  size_t total, elem_off;
+  int o_ac, o_as, o_b, o_x, o_st, o_ec, per_thread;
   __host__ __device__ TranSmallSmem(int nv, int n_elem, int n_state, bool dyn, int nt) {
     const int n1 = nv + 1;
     int o = 0;
@@ -32,13 +43,13 @@ struct TranSmallSmem {
     o_as = o; o += dyn ? n1 * n1 : 0;
     o_b = o; o += n1;
     o_x = o; o += n1;
-    o_st = o; o += n_state;
+    o_st = o; o += n_state + 1;
     o_ec = o; o += 4 * n_elem;
-    per_thread_doubles = (size_t)o;
-    size_t bytes = sizeof(double) * per_thread_doubles * nt;
+    per_thread = o;
+    size_t bytes = sizeof(double) * (size_t)o * nt;
     bytes = (bytes + 15) & ~(size_t)15;
-    ends_off = bytes;
-    bytes += sizeof(int4) * n_elem + sizeof(int) * n_elem;
+    elem_off = bytes;
+    bytes += sizeof(SmallElem) * (size_t)(n_elem > 0 ? n_elem : 1);
     total = (bytes + 15) & ~(size_t)15;
   }
 };
@@ -49,260 +60,296 @@ struct SmallLU {
   int perm[NV];      // row chosen at step k (solveReal.ts:16-26)
 
   // solveReal.ts:14-54 on the matrix part; returns status.
-  __device__ __forceinline__ int factor(int n) {
+  __device__ __forceinline__ int factor() {
+    int status = ST_OK;
 #pragma unroll
     for (int k = 0; k < NV; ++k) {
-      if (k < n) {
-        int imax = k;
-        double vmax = fabs(f[k][k]);
+      int imax = k;
+      double vmax = fabs(f[k][k]);
 #pragma unroll
-        for (int i = k + 1; i < NV; ++i)
-          if (i < n) {
-            double v = fabs(f[i][k]);
-            if (v > vmax) { vmax = v; imax = i; }
-          }
-        if (vmax < kEps) return ST_SINGULAR;
-        perm[k] = imax;
-#pragma unroll
-        for (int i = k + 1; i < NV; ++i)
-          if (imax == i) {
-#pragma unroll
-            for (int j = 0; j < NV; ++j) { double t = f[k][j]; f[k][j] = f[i][j]; f[i][j] = t; }
-          }
-        const double pivot = f[k][k];
-        const double rp = 1.0 / pivot;
-#pragma unroll
-        for (int i = k + 1; i < NV; ++i)
-          if (i < n) {
-            double m = STRICT ? __ddiv_rn(f[i][k], pivot) : f[i][k] * rp;
-            if (fabs(m) < kEps) m = 0.0;  // :45 skip == zero multiplier
-            f[i][k] = m;
-#pragma unroll
-            for (int j = k + 1; j < NV; ++j) f[i][j] = Num<double>::submul<STRICT>(f[i][j], m, f[k][j]);
-          }
-        if (!STRICT) f[k][k] = rp;
+      for (int i = k + 1; i < NV; ++i) {
+        double v = fabs(f[i][k]);
+        if (v > vmax) { vmax = v; imax = i; }
       }
+      if (vmax < kEps) status = ST_SINGULAR;   // :28 (the caller stops; the arithmetic below is harmless)
+      perm[k] = imax;
+#pragma unroll
+      for (int i = k + 1; i < NV; ++i) {
+        const bool sw = (imax == i);
+#pragma unroll
+        for (int j = 0; j < NV; ++j) {
+          const double u = f[k][j], w = f[i][j];
+          f[k][j] = sw ? w : u;
+          f[i][j] = sw ? u : w;
+        }
+      }
+      const double pivot = f[k][k];
+      const double rp = 1.0 / pivot;
+#pragma unroll
+      for (int i = k + 1; i < NV; ++i) {
+        double m = STRICT ? __ddiv_rn(f[i][k], pivot) : f[i][k] * rp;
+        m = (fabs(m) < kEps) ? 0.0 : m;  // :45 skip == zero multiplier
+        f[i][k] = m;
+#pragma unroll
+        for (int j = k + 1; j < NV; ++j) f[i][j] = Num<double>::submul<STRICT>(f[i][j], m, f[k][j]);
+      }
+      if (!STRICT) f[k][k] = rp;
     }
-    return ST_OK;
+    return status;
   }
 
   // Replays the elimination on b (the augmented column of solveReal.ts) and back-substitutes (:56-71).
-  __device__ __forceinline__ void solve(int n, double (&b)[NV]) const {
-    // factor() swapped whole rows, stored multipliers included (as LAPACK does), so the multipliers are
-    // in FINAL row order: apply every interchange to b first, then eliminate.  Each b entry still meets
-    // the same multipliers in the same order as in the reference's augmented elimination.
+  // factor() swapped whole rows, stored multipliers included (as LAPACK does), so the multipliers are in
+  // FINAL row order: every interchange is applied to b first, then the eliminations.  Each b entry still
+  // meets the same multipliers in the same order as in the reference's augmented elimination.
+  __device__ __forceinline__ void solve(double (&b)[NV]) const {
 #pragma unroll
     for (int k = 0; k < NV; ++k)
-      if (k < n) {
 #pragma unroll
-        for (int i = k + 1; i < NV; ++i)
-          if (perm[k] == i) { double t = b[k]; b[k] = b[i]; b[i] = t; }
+      for (int i = k + 1; i < NV; ++i) {
+        const bool sw = (perm[k] == i);
+        const double u = b[k], w = b[i];
+        b[k] = sw ? w : u;
+        b[i] = sw ? u : w;
       }
 #pragma unroll
     for (int k = 0; k < NV; ++k)
-      if (k < n) {
 #pragma unroll
-        for (int i = k + 1; i < NV; ++i)
-          if (i < n && f[i][k] != 0.0) b[i] = Num<double>::submul<STRICT>(b[i], f[i][k], b[k]);
-      }
+      for (int i = k + 1; i < NV; ++i) b[i] = Num<double>::submul<STRICT>(b[i], f[i][k], b[k]);
 #pragma unroll
-    for (int i = NV - 1; i >= 0; --i)
-      if (i < n) {
-        double s = b[i];
+    for (int i = NV - 1; i >= 0; --i) {
+      double s = b[i];
 #pragma unroll
-        for (int j = i + 1; j < NV; ++j)
-          if (j < n) s = Num<double>::submul<STRICT>(s, f[i][j], b[j]);
-        b[i] = STRICT ? __ddiv_rn(s, f[i][i]) : s * f[i][i];
-      }
+      for (int j = i + 1; j < NV; ++j) s = Num<double>::submul<STRICT>(s, f[i][j], b[j]);
+      b[i] = STRICT ? __ddiv_rn(s, f[i][i]) : s * f[i][i];
+    }
   }
 };
 
-template <int NV, bool STRICT>
-__global__ void __launch_bounds__(128) tran_small_kernel(DevPlan P, TranArgs a) {
+#define SM_D(base, off) (*(double*)((base) + (off)))
+
+template <int NV, int NT, bool STRICT>
+__global__ void __launch_bounds__(NT) tran_small_kernel(DevPlan P, TranArgs a) {
   extern __shared__ __align__(16) unsigned char smem[];
-  const int t = threadIdx.x, NT = blockDim.x;
+  constexpr int N1 = NV + 1;        // row/column NV absorbs ground stamps
+  constexpr int SB = NT * 8;        // byte stride between consecutive per-thread array entries
+  const int t = threadIdx.x;
   const int nvar = P.nvar, nn = P.nn, ne = P.n_elem, ns = P.n_state;
-  const bool dyn = P.off[ELEM_S + 1] > P.off[ELEM_S] || P.off[ELEM_D + 1] > P.off[ELEM_D];
-  const bool has_diode = P.off[ELEM_D + 1] > P.off[ELEM_D];
+  const int oC = P.off[ELEM_C], oL = P.off[ELEM_L], oV = P.off[ELEM_V], oS = P.off[ELEM_S], oD = P.off[ELEM_D],
+            oE = P.off[ELEM_D + 1];
+  const bool dyn = oE > oS, has_diode = oE > oD;
   const TranSmallSmem L(NV, ne, ns, dyn, NT);
-  constexpr int N1 = NV + 1;  // row/column NV absorbs ground stamps
-  double* base = (double*)smem + t;
-  double* Ac = base + (size_t)L.o_ac * NT;
-  double* As = base + (size_t)L.o_as * NT;
-  double* bs = base + (size_t)L.o_b * NT;
-  double* xs = base + (size_t)L.o_x * NT;
-  double* st = base + (size_t)L.o_st * NT;
-  double* ec = base + (size_t)L.o_ec * NT;
-  int4* ends = (int4*)(smem + L.ends_off);   // node ids mapped to matrix indices, ground -> NV
-  int* sidx = (int*)(ends + ne);
+  unsigned char* tb = smem + t * 8;
+  unsigned char* Ac = tb + (size_t)L.o_ac * SB;
+  unsigned char* As = tb + (size_t)L.o_as * SB;
+  unsigned char* bs = tb + (size_t)L.o_b * SB;
+  unsigned char* xs = tb + (size_t)L.o_x * SB;
+  unsigned char* st = tb + (size_t)L.o_st * SB;
+  unsigned char* ec = tb + (size_t)L.o_ec * SB;
+  SmallElem* el = (SmallElem*)(smem + L.elem_off);
   for (int e = t; e < ne; e += NT) {
-    int4 q = P.ends[e];
-    ends[e] = make_int4(q.x ? q.x - 1 : NV, q.y ? q.y - 1 : NV, q.z ? q.z - 1 : NV, q.w ? q.w - 1 : NV);
-    sidx[e] = P.state_idx[e];
+    const int4 q = P.ends[e];
+    const int i1 = q.x ? q.x - 1 : NV, i2 = q.y ? q.y - 1 : NV;
+    SmallElem r;
+    r.x1 = i1 * SB; r.x2 = i2 * SB;
+    r.c1 = (q.z ? q.z - 1 : NV) * SB; r.c2 = (q.w ? q.w - 1 : NV) * SB;
+    const int s = P.state_idx[e];
+    r.st = (s >= 0 ? s : ns) * SB;
+    r.ec = 4 * e * SB;
+    r.a11 = (i1 * N1 + i1) * SB; r.a22 = (i2 * N1 + i2) * SB;
+    r.a12 = (i1 * N1 + i2) * SB; r.a21 = (i2 * N1 + i1) * SB;
+    el[e] = r;
   }
   __syncthreads();
   const long long li = (long long)blockIdx.x * NT + t;
   if (li >= a.n_local) return;
   const long long inst = a.inst0 + li, NL = a.n_local, S1 = a.steps + 1;
   const double dtc = fmax(a.dt, kEps);
-  const int oR = 0, oC = P.off[ELEM_C], oL = P.off[ELEM_L], oV = P.off[ELEM_V], oS = P.off[ELEM_S],
-            oD = P.off[ELEM_D], oE = P.off[ELEM_D + 1];
 
   for (int e = 0; e < ne; ++e) {
     double c4[4];
     element_constants(P, P.meta[e].x, P.meta[e].y, inst, dtc, c4);
-    for (int q = 0; q < 4; ++q) ec[(4 * e + q) * NT] = c4[q];
+    SM_D(ec, (4 * e + 0) * SB) = c4[0]; SM_D(ec, (4 * e + 1) * SB) = c4[1];
+    SM_D(ec, (4 * e + 2) * SB) = c4[2]; SM_D(ec, (4 * e + 3) * SB) = c4[3];
   }
-  for (int s = 0; s < ns; ++s) st[s * NT] = a.state0 ? a.state0[(long long)s * P.n_inst + inst] : 0.0;
-  // Constant part of A: R, C, L admittances then V incidence (the entries of V never overlap an admittance).
-  for (int i = 0; i < N1 * N1; ++i) Ac[i * NT] = 0.0;
-#define STAMP_Y(M, i1, i2, g)                                   \
-  do {                                                          \
-    M[((i1) * N1 + (i1)) * NT] += (g);                          \
-    M[((i2) * N1 + (i2)) * NT] += (g);                          \
-    M[((i1) * N1 + (i2)) * NT] -= (g);                          \
-    M[((i2) * N1 + (i1)) * NT] -= (g);                          \
+  for (int s = 0; s < ns; ++s) SM_D(st, s * SB) = a.state0 ? a.state0[(long long)s * P.n_inst + inst] : 0.0;
+  // Constant part of A: R, C, L admittances then V incidence (V entries never overlap an admittance),
+  // identity on the padding rows nvar..NV-1.
+  for (int i = 0; i < N1 * N1; ++i) SM_D(Ac, i * SB) = 0.0;
+  for (int p = nvar; p < NV; ++p) SM_D(Ac, (p * N1 + p) * SB) = 1.0;
+#define STAMP_Y(M, r, g)                                      \
+  do {  /* stampAdmittanceReal.ts:3-29, same order */         \
+    SM_D(M, (r).a11) += (g);                                  \
+    SM_D(M, (r).a22) += (g);                                  \
+    SM_D(M, (r).a12) -= (g);                                  \
+    SM_D(M, (r).a21) -= (g);                                  \
   } while (0)
-  for (int e = oR; e < oS; ++e) {
-    const int4 q = ends[e];
-    if (e < oV) {
-      // stampAdmittanceReal.ts:3-29 — when n1 == n2 the reference also adds and subtracts in this order
-      STAMP_Y(Ac, q.x, q.y, ec[(4 * e) * NT]);
-    } else {  // stampVoltageSourceReal.ts:4-32
-      const int j = nn + (e - oV);
-      Ac[(q.x * N1 + j) * NT] += 1.0;
-      Ac[(q.y * N1 + j) * NT] -= 1.0;
-      Ac[(j * N1 + q.x) * NT] += 1.0;
-      Ac[(j * N1 + q.y) * NT] -= 1.0;
-    }
+  #pragma unroll 1
+  for (int e = 0; e < oV; ++e) {
+    const SmallElem r = el[e];
+    STAMP_Y(Ac, r, SM_D(ec, r.ec));
   }
+  #pragma unroll 1
+  for (int e = oV; e < oS; ++e) {  // stampVoltageSourceReal.ts:4-32
+    const SmallElem r = el[e];
+    const int j = nn + (e - oV);
+    SM_D(Ac, (r.x1 / SB * N1 + j) * SB) += 1.0;
+    SM_D(Ac, (r.x2 / SB * N1 + j) * SB) -= 1.0;
+    SM_D(Ac, j * N1 * SB + r.x1) += 1.0;
+    SM_D(Ac, j * N1 * SB + r.x2) -= 1.0;
+  }
+  SM_D(xs, NV * SB) = 0.0;  // ground
+#pragma unroll
+  for (int i = 0; i < NV; ++i) SM_D(xs, i * SB) = 0.0;
 
-  xs[NV * NT] = 0.0;  // ground
   SmallLU<NV, STRICT> lu;
   bool factored = false;
   int status = ST_OK;
   long long step = 0;
   double x[NV];
+  double* vo = a.v + li;
+  double* io = a.ielem ? a.ielem + li : nullptr;
+  int* ito = a.iters ? a.iters + li : nullptr;
+  const long long v_stride = (long long)nn * NL, i_stride = (long long)ne * NL;
+  const double* vsrc = a.vsrc;
+  unsigned vmask = 0;
+  for (int k = 0; k < oS - oV; ++k) vmask |= a.vsrc_mask[k] ? (1u << k) : 0u;
   for (; step < S1; ++step) {
     // :149 zeroes x every step; nothing reads x before the step's first solve (the diode uses vdPrev at
     // iteration 0, :85), so the zeroing is not materialised.
     int it = 0;
     for (; it < 20; ++it) {                                                  // :151
       // ---- right-hand side, reference order C, L, V, D (:41-53, :66-69, :98-100) ----
-      for (int i = 0; i < N1; ++i) bs[i * NT] = 0.0;
+#pragma unroll
+      for (int i = 0; i < N1; ++i) SM_D(bs, i * SB) = 0.0;
+      #pragma unroll 1
       for (int e = oC; e < oL; ++e) {
-        const int4 q = ends[e];
-        const double ieq = t_mul<STRICT>(-ec[(4 * e) * NT], st[sidx[e] * NT]);
-        bs[q.x * NT] -= ieq;
-        bs[q.y * NT] += ieq;
+        const SmallElem r = el[e];
+        const double ieq = t_mul<STRICT>(-SM_D(ec, r.ec), SM_D(st, r.st));
+        SM_D(bs, r.x1) -= ieq;
+        SM_D(bs, r.x2) += ieq;
       }
+      #pragma unroll 1
       for (int e = oL; e < oV; ++e) {
-        const int4 q = ends[e];
-        const double ip = st[sidx[e] * NT];
-        bs[q.x * NT] -= ip;
-        bs[q.y * NT] += ip;
+        const SmallElem r = el[e];
+        const double ip = SM_D(st, r.st);
+        SM_D(bs, r.x1) -= ip;
+        SM_D(bs, r.x2) += ip;
       }
+      #pragma unroll 1
       for (int e = oV; e < oS; ++e) {
         const int k = e - oV;
-        bs[(nn + k) * NT] += a.vsrc_mask[k] ? a.vsrc[(long long)k * S1 + step] : ec[(4 * e) * NT];
+        SM_D(bs, (nn + k) * SB) += ((vmask >> k) & 1u) ? __ldg(vsrc + (long long)k * S1 + step) : SM_D(ec, 4 * e * SB);
       }
       // ---- dynamic part of A: switches then diodes (:56-63, :72-101) ----
       if (dyn) {
         // switches only: `factored` is cleared where a switch toggles; diodes: re-linearised every solve
         const bool dirty = !factored || has_diode;
         if (dirty) {
-          for (int i = 0; i < N1 * N1; ++i) As[i * NT] = Ac[i * NT];
+#pragma unroll
+          for (int i = 0; i < N1 * N1; ++i) SM_D(As, i * SB) = SM_D(Ac, i * SB);
+          #pragma unroll 1
           for (int e = oS; e < oD; ++e) {
-            const int4 q = ends[e];
-            const double g = 1 / (st[sidx[e] * NT] != 0.0 ? ec[(4 * e) * NT] : ec[(4 * e + 1) * NT]);
-            STAMP_Y(As, q.x, q.y, g);
+            const SmallElem r = el[e];
+            const double g = 1 / (SM_D(st, r.st) != 0.0 ? SM_D(ec, r.ec) : SM_D(ec, r.ec + SB));
+            STAMP_Y(As, r, g);
           }
         }
+        #pragma unroll 1
         for (int e = oD; e < oE; ++e) {
-          const int4 q = ends[e];
-          const double vd = it == 0 ? st[sidx[e] * NT] : xs[q.x * NT] - xs[q.y * NT];   // :85
+          const SmallElem r = el[e];
+          const double vd = it == 0 ? SM_D(st, r.st) : SM_D(xs, r.x1) - SM_D(xs, r.x2);   // :85
           double gd, ieq;
-          diode_companion<STRICT>(vd, ec[(4 * e) * NT], ec[(4 * e + 1) * NT], gd, ieq);
-          STAMP_Y(As, q.x, q.y, gd);
-          bs[q.x * NT] -= ieq;
-          bs[q.y * NT] += ieq;
+          diode_companion<STRICT>(vd, SM_D(ec, r.ec), SM_D(ec, r.ec + SB), gd, ieq);
+          STAMP_Y(As, r, gd);
+          SM_D(bs, r.x1) -= ieq;
+          SM_D(bs, r.x2) += ieq;
         }
         if (dirty) {
 #pragma unroll
           for (int i = 0; i < NV; ++i)
 #pragma unroll
-            for (int j = 0; j < NV; ++j) lu.f[i][j] = As[(i * N1 + j) * NT];
-          status = lu.factor(nvar);
+            for (int j = 0; j < NV; ++j) lu.f[i][j] = SM_D(As, (i * N1 + j) * SB);
+          status = lu.factor();
           factored = true;
         }
       } else if (!factored) {
 #pragma unroll
         for (int i = 0; i < NV; ++i)
 #pragma unroll
-          for (int j = 0; j < NV; ++j) lu.f[i][j] = Ac[(i * N1 + j) * NT];
-        status = lu.factor(nvar);
+          for (int j = 0; j < NV; ++j) lu.f[i][j] = SM_D(Ac, (i * N1 + j) * SB);
+        status = lu.factor();
         factored = true;
       }
       if (status != ST_OK) break;
 #pragma unroll
-      for (int i = 0; i < NV; ++i) x[i] = bs[i * NT];
-      lu.solve(nvar, x);
+      for (int i = 0; i < NV; ++i) x[i] = SM_D(bs, i * SB);
+      lu.solve(x);
 #pragma unroll
-      for (int i = 0; i < NV; ++i) xs[i * NT] = x[i];
+      for (int i = 0; i < NV; ++i) SM_D(xs, i * SB) = x[i];
       bool switched = false;                                                 // :108-128
+      #pragma unroll 1
       for (int e = oS; e < oD; ++e) {
-        const int4 q = ends[e];
-        const double vctrl = xs[q.z * NT] - xs[q.w * NT];
-        const bool on = st[sidx[e] * NT] != 0.0;
+        const SmallElem r = el[e];
+        const double vctrl = SM_D(xs, r.c1) - SM_D(xs, r.c2);
+        const bool on = SM_D(st, r.st) != 0.0;
         bool nxt = on;
-        if (on) { if (vctrl < ec[(4 * e + 3) * NT]) nxt = false; }
-        else if (vctrl > ec[(4 * e + 2) * NT]) nxt = true;
-        if (nxt != on) { st[sidx[e] * NT] = nxt ? 1.0 : 0.0; switched = true; }
+        if (on) { if (vctrl < SM_D(ec, r.ec + 3 * SB)) nxt = false; }
+        else if (vctrl > SM_D(ec, r.ec + 2 * SB)) nxt = true;
+        if (nxt != on) { SM_D(st, r.st) = nxt ? 1.0 : 0.0; switched = true; }
       }
       if (switched) factored = false;  // conductances changed: re-factor at the next solve
       if (!switched) break;
     }
     if (status != ST_OK) break;
-    if (a.iters) a.iters[step * NL + li] = it < 20 ? it + 1 : 20;
+    if (ito) { *ito = it < 20 ? it + 1 : 20; ito += NL; }
     // ---- recording (:164-219) + state update (:221-237), per-type loops in table order ----
 #pragma unroll
     for (int i = 0; i < NV; ++i)
-      if (i < nn) a.v[(step * nn + i) * NL + li] = x[i];
-    double* io = a.ielem ? a.ielem + step * ne * NL + li : nullptr;
-    for (int e = oR; e < oC; ++e) {
-      const int4 q = ends[e];
-      const double d = xs[q.x * NT] - xs[q.y * NT];
-      const double cur = STRICT ? __ddiv_rn(d, ec[(4 * e + 1) * NT]) : d * ec[(4 * e) * NT];
-      if (io) io[(long long)e * NL] = cur;
+      if (i < nn) vo[(long long)i * NL] = x[i];
+    vo += v_stride;
+    double* ie = io;
+    #pragma unroll 1
+    for (int e = 0; e < oC; ++e, ie += NL) {
+      const SmallElem r = el[e];
+      const double d = SM_D(xs, r.x1) - SM_D(xs, r.x2);
+      const double cur = STRICT ? __ddiv_rn(d, SM_D(ec, r.ec + SB)) : d * SM_D(ec, r.ec);
+      if (io) *ie = cur;
     }
-    for (int e = oC; e < oL; ++e) {
-      const int4 q = ends[e];
-      const double d = xs[q.x * NT] - xs[q.y * NT];
-      const double dv = d - st[sidx[e] * NT];
-      const double cur = STRICT ? __ddiv_rn(__dmul_rn(ec[(4 * e + 1) * NT], dv), dtc) : ec[(4 * e) * NT] * dv;
-      st[sidx[e] * NT] = d;
-      if (io) io[(long long)e * NL] = cur;
+    #pragma unroll 1
+    for (int e = oC; e < oL; ++e, ie += NL) {
+      const SmallElem r = el[e];
+      const double d = SM_D(xs, r.x1) - SM_D(xs, r.x2);
+      const double dv = d - SM_D(st, r.st);
+      const double cur = STRICT ? __ddiv_rn(__dmul_rn(SM_D(ec, r.ec + SB), dv), dtc) : SM_D(ec, r.ec) * dv;
+      SM_D(st, r.st) = d;
+      if (io) *ie = cur;
     }
-    for (int e = oL; e < oV; ++e) {
-      const int4 q = ends[e];
-      const double d = xs[q.x * NT] - xs[q.y * NT];
-      const double cur = t_add<STRICT>(t_mul<STRICT>(ec[(4 * e) * NT], d), st[sidx[e] * NT]);
-      st[sidx[e] * NT] = cur;
-      if (io) io[(long long)e * NL] = cur;
+    #pragma unroll 1
+    for (int e = oL; e < oV; ++e, ie += NL) {
+      const SmallElem r = el[e];
+      const double d = SM_D(xs, r.x1) - SM_D(xs, r.x2);
+      const double cur = t_add<STRICT>(t_mul<STRICT>(SM_D(ec, r.ec), d), SM_D(st, r.st));
+      SM_D(st, r.st) = cur;
+      if (io) *ie = cur;
     }
-    for (int e = oV; e < oS; ++e)
-      if (io) io[(long long)e * NL] = xs[(nn + e - oV) * NT];
-    for (int e = oS; e < oD; ++e) {
-      const int4 q = ends[e];
-      const double d = xs[q.x * NT] - xs[q.y * NT];
-      if (io) io[(long long)e * NL] = d / (st[sidx[e] * NT] != 0.0 ? ec[(4 * e) * NT] : ec[(4 * e + 1) * NT]);
+    #pragma unroll 1
+    for (int e = oV; e < oS; ++e, ie += NL)
+      if (io) *ie = SM_D(xs, (nn + e - oV) * SB);
+    #pragma unroll 1
+    for (int e = oS; e < oD; ++e, ie += NL) {
+      const SmallElem r = el[e];
+      const double d = SM_D(xs, r.x1) - SM_D(xs, r.x2);
+      if (io) *ie = d / (SM_D(st, r.st) != 0.0 ? SM_D(ec, r.ec) : SM_D(ec, r.ec + SB));
     }
-    for (int e = oD; e < oE; ++e) {
-      const int4 q = ends[e];
-      const double d = xs[q.x * NT] - xs[q.y * NT];
-      if (io) io[(long long)e * NL] = t_mul<STRICT>(ec[(4 * e) * NT], t_sub<STRICT>(exp(d / ec[(4 * e + 1) * NT]), 1.0));
-      st[sidx[e] * NT] = d;
+    #pragma unroll 1
+    for (int e = oD; e < oE; ++e, ie += NL) {
+      const SmallElem r = el[e];
+      const double d = SM_D(xs, r.x1) - SM_D(xs, r.x2);
+      if (io) *ie = t_mul<STRICT>(SM_D(ec, r.ec), t_sub<STRICT>(exp(d / SM_D(ec, r.ec + SB)), 1.0));  // unclamped (H6)
+      SM_D(st, r.st) = d;
     }
+    if (io) io += i_stride;
   }
 #undef STAMP_Y
   if (status != ST_OK) {
@@ -312,8 +359,10 @@ __global__ void __launch_bounds__(128) tran_small_kernel(DevPlan P, TranArgs a) 
       if (a.iters) a.iters[step * NL + li] = 0;
     }
   }
-  if (a.state_out) for (int s = 0; s < ns; ++s) a.state_out[(long long)s * NL + li] = st[s * NT];
+  if (a.state_out) for (int s = 0; s < ns; ++s) a.state_out[(long long)s * NL + li] = SM_D(st, s * SB);
   a.status[li] = status;
 }
+
+#undef SM_D
 
 }  // namespace spicey
