@@ -389,7 +389,10 @@ int launch_ac_sparse(DeviceCtx& ctx, const HostPlan& hp, const DevPlan& dp, cons
                      cudaStream_t stream, int* tier_out, int64_t* launches) {
   const int block = 128;
   long long T = std::min<long long>((args.p_count + block - 1) / block, (long long)ctx.sm_count * 8) * block;
-  size_t wbytes = sizeof(double2) * (size_t)(ctx.sp.n_slots + hp.nvar) * T;
+  const size_t per_thread = sizeof(double2) * (size_t)(ctx.sp.n_slots + hp.nvar);
+  const long long t_cap = std::max<long long>(block, (long long)(((size_t)12 << 30) / per_thread) / block * block);
+  T = std::min(T, t_cap);  // workspace <= 12 GiB (large programs: fewer resident threads, same grid-stride loop)
+  size_t wbytes = per_thread * T;
   int rc = ctx.sp_work.ensure(wbytes);
   if (rc) return rc;
   if ((rc = ctx.sp_fb.ensure(sizeof(long long) * args.p_count + 64))) return rc;
