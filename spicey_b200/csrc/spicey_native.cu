@@ -312,12 +312,9 @@ int prepare_sparse(DeviceCtx& ctx, const HostPlan& hp, double pilot_f, cudaStrea
   const int n_ent = (int)G.ent_col.size();
   sp.ent_alpha.assign(n_ent, 0.0); sp.ent_beta.assign(n_ent, 0.0); sp.ent_gamma.assign(n_ent, 0.0);
   sp.ent_jre.assign(n_ent, 0.0); sp.ent_jim.assign(n_ent, 0.0);
-  std::vector<int> rhs_slot;
-  std::vector<double> rhs_re, rhs_im;
   for (int e = 0; e < hp.n_ac_elem; ++e)
     if (hp.meta[e].x == ELEM_R && !(hp.values[hp.meta[e].y] > 0)) return SPICEY_SUCCESS;  // R<=0: dense kernel reports it
   for (int en = 0; en < n_ent; ++en) {
-    bool has_j = false;
     for (int c = G.ent_ptr[en]; c < G.ent_ptr[en + 1]; ++c) {
       const int w = G.contrib[c], src = (w >> 1) & 3, idx = w >> 3;
       const double sgn = (w & 1) ? -1.0 : 1.0;
@@ -328,12 +325,10 @@ int prepare_sparse(DeviceCtx& ctx, const HostPlan& hp, double pilot_f, cudaStrea
         const double ph = (v[2] * kPi) / 180;
         sp.ent_jre[en] += sgn * (v[1] * cos(ph));
         sp.ent_jim[en] += sgn * (v[1] * sin(ph));
-        has_j = true;
       } else if (ty == ELEM_R) sp.ent_alpha[en] += sgn * (1 / v[0]);
       else if (ty == ELEM_C) sp.ent_beta[en] += sgn * v[0];
       else if (ty == ELEM_L) sp.ent_gamma[en] += sgn * (1 / v[0]);
     }
-    if (has_j) { rhs_slot.push_back(en); rhs_re.push_back(sp.ent_jre[en]); rhs_im.push_back(sp.ent_jim[en]); }
   }
   sp.el_a.assign(hp.n_ac_elem, 0.0); sp.el_b.assign(hp.n_ac_elem, 0.0); sp.el_g.assign(hp.n_ac_elem, 0.0);
   for (int e = 0; e < hp.n_ac_elem; ++e) {
@@ -355,12 +350,15 @@ int prepare_sparse(DeviceCtx& ctx, const HostPlan& hp, double pilot_f, cudaStrea
   build_sparse_program(pin, sp);
   if (!sp.ok) return SPICEY_SUCCESS;
   // upload
+  std::vector<double2> c0(n_ent), c1(n_ent);
+  for (int en = 0; en < n_ent; ++en) {
+    c0[en] = make_double2(sp.ent_alpha[en] + sp.ent_jre[en], sp.ent_jim[en]);
+    c1[en] = make_double2(sp.ent_beta[en], sp.ent_gamma[en]);
+  }
   std::vector<unsigned char> blob;
-  size_t o_code = push_blob(blob, sp.code), o_a = push_blob(blob, sp.ent_alpha), o_b = push_blob(blob, sp.ent_beta);
-  size_t o_g = push_blob(blob, sp.ent_gamma), o_rs = push_blob(blob, rhs_slot), o_rr = push_blob(blob, rhs_re);
-  size_t o_ri = push_blob(blob, rhs_im), o_ea = push_blob(blob, sp.el_a), o_eb = push_blob(blob, sp.el_b);
+  size_t o_code = push_blob(blob, sp.code), o_xs = push_blob(blob, sp.x_slot), o_c0 = push_blob(blob, c0);
+  size_t o_c1 = push_blob(blob, c1), o_ea = push_blob(blob, sp.el_a), o_eb = push_blob(blob, sp.el_b);
   size_t o_eg = push_blob(blob, sp.el_g), o_l = push_blob(blob, sp.ind_L), o_ends = push_blob(blob, hp.ends);
-  size_t o_meta = push_blob(blob, hp.meta);
   int rc = ctx.sp_blob.ensure(blob.size() + 16);
   if (rc) return rc;
   CUDA_TRY(cudaMemcpyAsync(ctx.sp_blob.p, blob.data(), blob.size(), cudaMemcpyHostToDevice, stream));
@@ -369,12 +367,12 @@ int prepare_sparse(DeviceCtx& ctx, const HostPlan& hp, double pilot_f, cudaStrea
   SparseArgs& a = ctx.sp_args;
   memset(&a, 0, sizeof(a));
   a.code = (const int*)(b + o_code);
-  a.n = hp.nvar; a.n_stamp = sp.n_stamp; a.n_slots = sp.n_slots; a.n_rhs_src = (int)rhs_slot.size();
-  a.ent_alpha = (const double*)(b + o_a); a.ent_beta = (const double*)(b + o_b); a.ent_gamma = (const double*)(b + o_g);
-  a.rhs_slot = (const int*)(b + o_rs); a.rhs_re = (const double*)(b + o_rr); a.rhs_im = (const double*)(b + o_ri);
+  a.x_slot = (const int*)(b + o_xs);
+  a.n = hp.nvar; a.n_stamp = sp.n_stamp; a.n_slots = sp.n_slots;
+  a.ent_c0 = (const double2*)(b + o_c0); a.ent_c1 = (const double2*)(b + o_c1);
   a.el_a = (const double*)(b + o_ea); a.el_b = (const double*)(b + o_eb); a.el_g = (const double*)(b + o_eg);
   a.ind_L = (const double*)(b + o_l); a.n_ind = (int)sp.ind_L.size();
-  a.ends = (const int4*)(b + o_ends); a.meta = (const int2*)(b + o_meta);
+  a.ends = (const int4*)(b + o_ends);
   a.n_ac_elem = hp.n_ac_elem; a.nn = hp.nn; a.v_first = hp.off[ELEM_V];
   ctx.sp_valid = true;
   return SPICEY_SUCCESS;
@@ -389,7 +387,7 @@ int launch_ac_sparse(DeviceCtx& ctx, const HostPlan& hp, const DevPlan& dp, cons
                      cudaStream_t stream, int* tier_out, int64_t* launches) {
   const int block = 128;
   long long T = std::min<long long>((args.p_count + block - 1) / block, (long long)ctx.sm_count * 8) * block;
-  const size_t per_thread = sizeof(double2) * (size_t)(ctx.sp.n_slots + hp.nvar);
+  const size_t per_thread = sizeof(double2) * (size_t)std::max(1, ctx.sp.n_slots);
   const long long t_cap = std::max<long long>(block, (long long)(((size_t)12 << 30) / per_thread) / block * block);
   T = std::min(T, t_cap);  // workspace <= 12 GiB (large programs: fewer resident threads, same grid-stride loop)
   size_t wbytes = per_thread * T;
