@@ -223,23 +223,25 @@ def run_native(args):
     if wl["kind"] == "ac":
         P = wl["units"]
         d_freqs = torch.from_numpy(wl["freqs"]).to(dev)
-        d_x = torch.empty((P, table.nvar), dtype=torch.complex128, device=dev)
-        d_i = torch.empty((P, table.n_ac_elem), dtype=torch.complex128, device=dev)
+        # series-major results (x[Nvar][P], ielem[nAc][P]): the layout the drop-in simulateAC uses
+        d_x = torch.empty((table.nvar, P), dtype=torch.complex128, device=dev)
+        d_i = torch.empty((table.n_ac_elem, P), dtype=torch.complex128, device=dev)
         d_s = torch.empty(P, dtype=torch.int32, device=dev)
+        ac_flags = native.FLAG_SERIES_MAJOR
 
         def step_resident():
             eng.ac_solve_device(table, d_freqs.data_ptr(), P, d_x.data_ptr(), d_i.data_ptr(), d_s.data_ptr(),
-                                stream=stream.cuda_stream)
+                                flags=ac_flags, stream=stream.cuda_stream)
 
         h_freqs, p0 = native.pinned_empty(eng.lib, (P,), np.float64)
         h_freqs[:] = wl["freqs"]
-        h_x, p1 = native.pinned_empty(eng.lib, (P, table.nvar), np.complex128)
-        h_i, p2 = native.pinned_empty(eng.lib, (P, table.n_ac_elem), np.complex128)
+        h_x, p1 = native.pinned_empty(eng.lib, (table.nvar, P), np.complex128)
+        h_i, p2 = native.pinned_empty(eng.lib, (table.n_ac_elem, P), np.complex128)
         h_s, p3 = native.pinned_empty(eng.lib, (P,), np.int32)
         pins = [p0, p1, p2, p3]
 
         def step_e2e():
-            eng.ac_solve(table, h_freqs, out=(h_x, h_i, h_s))
+            eng.ac_solve(table, h_freqs, out=(h_x, h_i, h_s), flags=ac_flags)
             return int(h_s.max())
 
         def check():
@@ -359,6 +361,7 @@ def run_native(args):
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "c128" if wl["kind"] == "ac" else "f64", "data": "synthetic",
             "config": {"workload": wl["label"], "per_gpu_units_per_step": units, "tier": tier,
+                       "result_layout": "series-major x[Nvar][P], ielem[nAc][P]" if wl["kind"] == "ac" else "v[step][node][inst]",
                        "fallback_solves_last_step": int(fallback),
                        "l2": "no flush: each step writes %.2f GB of results, larger than the 126 MB L2" % (
                            working_set / 1e9),

@@ -152,6 +152,7 @@ void spicey_host_free(void* p);
  *   x      [n_inst*n_freq][Nvar][2]    solution: node voltages then V branch currents
  *   ielem  [n_inst*n_freq][nAc][2]     currents of the R, C, L, V elements in table order
  *                                      (nAc = their count); may be NULL
+ *          with SPICEY_FLAG_SERIES_MAJOR the two are transposed: x[Nvar][P][2], ielem[nAc][P][2]
  *   status [n_inst*n_freq]             SPICEY_ST_*; rows of a failed point are NaN
  * Host pointers.  flags: SPICEY_FLAG_*.
  */
@@ -200,7 +201,9 @@ enum {
   SPICEY_FLAG_FORCE_CTA = 4u,   /* testing: force a CTA tier even for tiny systems */
   SPICEY_FLAG_DENSE = 8u,       /* never use the sparse program path */
   SPICEY_FLAG_SPARSE = 16u,     /* use the sparse program path even for small batches */
-  SPICEY_FLAG_GENERIC_THREAD = 32u /* testing: transient thread tier without the register-resident kernel */
+  SPICEY_FLAG_GENERIC_THREAD = 32u, /* testing: transient thread tier without the register-resident kernel */
+  SPICEY_FLAG_SERIES_MAJOR = 64u   /* AC: x is [Nvar][P] and ielem [nAc][P] (one contiguous series per node /
+                                      element, coalesced stores on the device) instead of [P][Nvar] / [P][nAc] */
 };
 
 /* Measures this GPU's FP64 FMA peak with a register-only DFMA loop (GFLOP/s), the

@@ -131,11 +131,12 @@ def simulateAC(ckt: ParsedCircuit, engine: Optional[native.Engine] = None, flags
     eng = engine or get_engine()
     freqs = ac_frequencies(ckt)
     table = pack_circuit(ckt)
-    x, ie, st = eng.ac_solve(table, freqs, flags=flags)
+    # series-major results: every node / element series is one contiguous slab
+    x, ie, st = eng.ac_solve(table, freqs, flags=flags | native.FLAG_SERIES_MAJOR)
     _raise_first_failure(st, table, ckt, _AC_ERRORS)
     node_names = ckt.nodes.rev[1:]
-    volt = _series_by_name(node_names, x[:, :table.n_nodes])
-    cur = _series_by_name(table.names[:table.n_ac_elem], ie)
+    volt = _series_by_name(node_names, x[:table.n_nodes].T)
+    cur = _series_by_name(table.names[:table.n_ac_elem], ie.T)
     return {
         "freqs": freqs,
         "nodeVoltages": {k: ComplexSeries(v) for k, v in volt.items()},
@@ -183,6 +184,9 @@ def simulate_ac_batch(ckt: ParsedCircuit, freqs=None, n_inst: int = 1, overrides
     F = len(freqs)
     x, ie, st = eng.ac_solve(table, freqs, sweep=make_sweep(table, n_inst, overrides),
                              want_currents=want_currents, flags=flags)
+    if flags & native.FLAG_SERIES_MAJOR:  # [rows, P] slabs -> logical [n_inst, F, rows] views (no copy)
+        x = x.T
+        ie = None if ie is None else ie.T
     return {"freqs": np.asarray(freqs), "x": x.reshape(n_inst, F, table.nvar),
             "ielem": None if ie is None else ie.reshape(n_inst, F, table.n_ac_elem),
             "status": st.reshape(n_inst, F), "node_names": ckt.nodes.rev[1:],

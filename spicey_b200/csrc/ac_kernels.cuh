@@ -26,6 +26,7 @@ struct AcArgs {
   const long long* plist;  // optional: launch-local point indices to solve (fallback of the sparse path)
   const int* pcount;       // optional: number of entries of plist (device-resident)
   unsigned long long* fb_total;  // optional: running total of fallback solves (statistics)
+  long long series_ld;     // 0: x[q][var], ielem[q][e] (point-major); else x[var][series_ld], ielem[e][series_ld]
 };
 
 // Shared-memory carve-up, identical on host (sizing) and device.
@@ -142,11 +143,13 @@ __global__ void ac_cta_kernel(DevPlan P, AcArgs a) {
     }
 
     // Phase 4: unpack (simulateAC.ts:85-126).
-    cplx* xo = a.x + (size_t)q * nvar;
+    const long long sld = a.series_ld;
+    cplx* xo = sld ? a.x + q : a.x + (size_t)q * nvar;
+    const long long xst = sld ? sld : 1;   // stride between consecutive variables / elements of one point
     if (status == ST_OK) {
-      if (t < nvar) xo[t] = xs[t];
+      if (t < nvar) xo[t * xst] = xs[t];
       if (a.ielem) {
-        cplx* io = a.ielem + (size_t)q * P.n_ac_elem;
+        cplx* io = sld ? a.ielem + q : a.ielem + (size_t)q * P.n_ac_elem;
         for (int e = t; e < P.n_ac_elem; e += blockDim.x) {
           int4 en = ends[e];
           cplx cur;
@@ -158,14 +161,16 @@ __global__ void ac_cta_kernel(DevPlan P, AcArgs a) {
             cplx d = csub(v1, v2);
             cur = STRICT ? Num<cplx>::mul_strict(Yv[e], d) : Num<cplx>::mul(Yv[e], d);
           }
-          io[e] = cur;
+          io[e * xst] = cur;
         }
       }
     } else {
       const cplx qn = Num<cplx>::nan();
-      if (t < nvar) xo[t] = qn;
-      if (a.ielem)
-        for (int e = t; e < P.n_ac_elem; e += blockDim.x) a.ielem[(size_t)q * P.n_ac_elem + e] = qn;
+      if (t < nvar) xo[t * xst] = qn;
+      if (a.ielem) {
+        cplx* io = sld ? a.ielem + q : a.ielem + (size_t)q * P.n_ac_elem;
+        for (int e = t; e < P.n_ac_elem; e += blockDim.x) io[e * xst] = qn;
+      }
     }
     if (t == 0) a.status[q] = status;
     __syncthreads();  // s_status / xs / Yv are reused by the next point

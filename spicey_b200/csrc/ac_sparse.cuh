@@ -29,45 +29,69 @@
 namespace spicey {
 
 struct SparseArgs {
-  const int* code;
-  const int* x_slot;                               // [n] slot of x_i after the program
-  int n, n_stamp, n_slots;
+  const int4* code;      // micro-ops (sparse_program.h); slot operands pre-scaled by the workspace stride
+  const unsigned* x_off; // [n] workspace offset (in double2 units) of x_i after the program
+  const uint2* el_x;     // [n_ac_elem] workspace offsets of v(n1), v(n2); 0xffffffff = ground
+  int n, n_stamp, n_slots, n_fast, n_const;
+  const int* const_entry;                          // [n_const] entry whose value fast slot c holds
   const double2 *ent_c0, *ent_c1;                  // [n_stamp] (alpha + Re J, Im J), (beta, gamma)
   const double *el_a, *el_b, *el_g;                // [n_ac_elem]
   const double* ind_L;
   int n_ind;
-  const int4* ends;
   int n_ac_elem, nn, v_first;
   const double* freqs;
   long long p_count;
   double2* W;       // [n_slots][T]
-  long long T;      // threads of the grid
-  double2* x;       // [p_count][n]
-  double2* ielem;   // [p_count][n_ac_elem] or null
+  long long T;      // workspace stride = resident threads the workspace was sized for
+  double2* x;       // [p_count][n], or [n][series_ld] when series_ld != 0
+  double2* ielem;   // [p_count][n_ac_elem] / [n_ac_elem][series_ld], or null
+  long long series_ld;
   int* status;      // [p_count]
   long long* fb_list;  // points handed to the dense kernel
   int* fb_count;
 };
 
+// Small programs (<= kConstProgWords micro-ops) are served from constant memory: every lane reads the
+// same word, which is exactly what the constant cache broadcasts, and the compiler keeps opcode and
+// operand words in uniform registers (uniform branches, no reconvergence bookkeeping).  Larger
+// programs stream from global memory through the read-only path.
+constexpr int kConstProgWords = 3840;  // 60 KiB of the 64 KiB constant bank
+__constant__ int4 c_sparse_prog[kConstProgWords];
+
+template <bool CONST_PROG>
 __global__ void __launch_bounds__(128) ac_sparse_kernel(SparseArgs a) {
   typedef Num<cplx> N;
   const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  const long long T = a.T;
+  const long long nthreads = (long long)gridDim.x * blockDim.x;
+  extern __shared__ __align__(16) double2 fast_pool[];   // [n_fast][128]: short-lived values and constants
   double2* __restrict__ W = a.W + tid;
-  const int* __restrict__ code = a.code;
+  double2* __restrict__ F = fast_pool + threadIdx.x;
+  const int4* __restrict__ code = a.code;
+  const double2* __restrict__ c0p = a.ent_c0;
+  const double2* __restrict__ c1p = a.ent_c1;
   const double thr = kEps * kEps;  // squared-magnitude metric
 
-  for (long long p = tid; p < a.p_count; p += T) {
+  for (long long p = tid; p < a.p_count; p += nthreads) {
     const double f = a.freqs[p];
     const double w = (2 * kPi) * f;
     const double iw = 1.0 / w;
-    // Operand fetch: >= 0 workspace slot, < 0 pristine stamped entry ~idx (lazy stamping), INT_MIN zero.
-    auto fetch = [&](int o) -> cplx {
-      if (o >= 0) return W[(long long)o * T];
-      if (o == kNoOperand) return make_double2(0.0, 0.0);
-      const double2 c0 = __ldg(a.ent_c0 + ~o), c1 = __ldg(a.ent_c1 + ~o);
+    auto pristine = [&](int en) -> cplx {
+      const double2 c0 = __ldg(c0p + en), c1 = __ldg(c1p + en);
       return make_double2(c0.x, fma(w, c1.x, -c1.y * iw) + c0.y);
     };
+    // Operand fetch by kind: 3 fast slot (shared memory), 1 global workspace slot, 2 pristine stamped
+    // entry computed in place (lazy stamping), 0 zero.
+    auto fetch = [&](int kind, int v) -> cplx {
+      cplx r = make_double2(0.0, 0.0);
+      if (kind == 3) r = F[v];
+      else if (kind == 1) r = W[(unsigned)v];
+      else if (kind == 2) r = pristine(v);
+      return r;
+    };
+    auto put = [&](int kind, int v, cplx val) {
+      if (kind == 3) F[v] = val; else W[(unsigned)v] = val;
+    };
+    for (int c = 0; c < a.n_const; ++c) F[c * 128] = pristine(__ldg(a.const_entry + c));
     bool diverged = false;
     int status = ST_OK;
     // inductor guards of simulateAC.ts:47-51 / Complex.ts:41 are value dependent: leave them to the dense kernel
@@ -75,45 +99,48 @@ __global__ void __launch_bounds__(128) ac_sparse_kernel(SparseArgs a) {
       double d = w * a.ind_L[l];
       if (fabs(d) < kEps || d * d < kEps) diverged = true;
     }
+    const long long sld = a.series_ld, xst = sld ? sld : 1;
+    cplx* __restrict__ xout = sld ? a.x + p : a.x + p * a.n;
     int pc = 0;
-    cplx r = N::zero();
+    cplx r = N::zero(), fm = N::zero(), ap = N::zero(), acc = N::zero(), rc = N::zero();
+    double mp = 0.0;
+    bool ok = true;
+    int4 nxt = CONST_PROG ? c_sparse_prog[0] : __ldg(code);
     while (!diverged && status == ST_OK) {
-      const int op = __ldg(code + pc);
-      if (op == SOP_PIVOT) {
-        const int nc = __ldg(code + pc + 1), pidx = __ldg(code + pc + 2);
-        const cplx ap = fetch(__ldg(code + pc + 3 + pidx));
-        const double mp = N::metric<false>(ap);
-        bool ok = (mp == mp);
-        for (int c = 0; c < nc; ++c) {
-          if (c == pidx) continue;
-          const double m = N::metric<false>(fetch(__ldg(code + pc + 3 + c)));
-          ok = ok && (c < pidx ? (m < mp) : !(m > mp));   // first maximum wins (solveComplex.ts:20-28)
-        }
+      const int4 u = nxt;
+      ++pc;
+      nxt = CONST_PROG ? c_sparse_prog[pc] : __ldg(code + pc);   // prefetch: the program ends with two END words
+      const int hdr = u.x;
+      const int op = hdr & 15, ka = (hdr >> 4) & 3, kb = (hdr >> 6) & 3, kc = (hdr >> 10) & 3;
+      if (op == MOP_UPD) {
+        const cplx dst = fetch(ka, u.y);
+        const cplx src = fetch(kb, u.z);
+        put(kc, u.w, N::submul<false>(dst, fm, src));                       // solveComplex.ts:47-52
+      } else if (op == MOP_BTERM) {
+        acc = N::submul<false>(acc, fetch(ka, u.y), fetch(kb, u.z));        // :62-68
+      } else if (op == MOP_ELIM) {
+        fm = N::mul(fetch(ka, u.y), r);                                     // :45
+        if (N::metric<false>(fm) < thr) fm = N::zero();                     // :46 (zero multiplier = row untouched)
+      } else if (op == MOP_CAND) {
+        const double m = N::metric<false>(fetch(ka, u.y));
+        ok = ok && ((hdr >> 8) & 1 ? (m < mp) : !(m > mp));                 // first maximum wins (:20-28)
+      } else if (op == MOP_PIVHEAD) {
+        ap = fetch(ka, u.y);
+        mp = N::metric<false>(ap);
+        ok = (mp == mp);
+      } else if (op == MOP_PIVEND) {
         if (!ok) { diverged = true; break; }
-        if (mp < thr) { status = ST_SINGULAR; break; }      // :29
-        if (mp < kEps) { status = ST_CDIV; break; }         // Complex.ts:41-42
+        if (mp < thr) { status = ST_SINGULAR; break; }                      // :29
+        if (mp < kEps) { status = ST_CDIV; break; }                         // Complex.ts:41-42
         r = N::recip(ap);
-        W[(long long)__ldg(code + pc + 3 + nc) * T] = r;    // 1/u_kk for the back-substitution
-        pc += 4 + nc;
-      } else if (op == SOP_ELIM) {
-        cplx fm = N::mul(fetch(__ldg(code + pc + 1)), r);
-        if (N::metric<false>(fm) < thr) fm = N::zero();     // :46 (a zero multiplier leaves the row unchanged)
-        const int nu = __ldg(code + pc + 2);
-        pc += 3;
-        for (int u = 0; u < nu; ++u, pc += 3) {
-          const cplx dst = fetch(__ldg(code + pc));
-          const cplx src = fetch(__ldg(code + pc + 1));
-          W[(long long)__ldg(code + pc + 2) * T] = N::submul<false>(dst, fm, src);   // :47-52
-        }
-      } else if (op == SOP_BSUB) {
-        const int nt = __ldg(code + pc + 4);
-        cplx acc = fetch(__ldg(code + pc + 2));
-        const cplx rc = fetch(__ldg(code + pc + 3));
-        pc += 5;
-        for (int q = 0; q < nt; ++q, pc += 2)
-          acc = N::submul<false>(acc, fetch(__ldg(code + pc)), fetch(__ldg(code + pc + 1)));
-        W[(long long)__ldg(code + pc) * T] = N::mul(acc, rc);   // :56-71
-        pc += 1;
+        put(kc, u.w, r);                                                    // 1/u_kk for the back-substitution
+      } else if (op == MOP_BHEAD) {
+        acc = fetch(ka, u.y);
+        rc = fetch(kb, u.z);
+      } else if (op == MOP_BEND) {
+        const cplx xi = N::mul(acc, rc);                                    // :69-70
+        put(kc, u.w, xi);
+        xout[(long long)u.y * xst] = xi;                                    // u.y = variable index: straight to the result
       } else {
         break;
       }
@@ -125,30 +152,24 @@ __global__ void __launch_bounds__(128) ac_sparse_kernel(SparseArgs a) {
       a.fb_list[slot] = p;
       continue;
     }
-    cplx* xo = a.x + p * a.n;
+    cplx* __restrict__ io = a.ielem ? (sld ? a.ielem + p : a.ielem + p * a.n_ac_elem) : nullptr;
     if (status != ST_OK) {
-      for (int i = 0; i < a.n; ++i) xo[i] = N::nan();
-      if (a.ielem)
-        for (int e = 0; e < a.n_ac_elem; ++e) a.ielem[p * a.n_ac_elem + e] = N::nan();
+      for (int i = 0; i < a.n; ++i) xout[i * xst] = N::nan();
+      if (io)
+        for (int e = 0; e < a.n_ac_elem; ++e) io[e * xst] = N::nan();
       a.status[p] = status;
       continue;
     }
-    for (int i = 0; i < a.n; ++i) xo[i] = W[(long long)__ldg(a.x_slot + i) * T];
-    if (a.ielem) {
-      cplx* io = a.ielem + p * a.n_ac_elem;
-      for (int e = 0; e < a.n_ac_elem; ++e) {
-        const int4 en = __ldg(a.ends + e);
-        cplx cur;
-        if (e >= a.v_first) {
-          cur = W[(long long)__ldg(a.x_slot + a.nn + e - a.v_first) * T];
-        } else {
-          cplx v1 = en.x == 0 ? N::zero() : W[(long long)__ldg(a.x_slot + en.x - 1) * T];
-          cplx v2 = en.y == 0 ? N::zero() : W[(long long)__ldg(a.x_slot + en.y - 1) * T];
-          cplx y = make_double2(__ldg(a.el_a + e), fma(w, __ldg(a.el_b + e), -__ldg(a.el_g + e) * iw));
-          cur = N::mul(y, csub(v1, v2));
-        }
-        io[e] = cur;
+    if (io) {
+#pragma unroll 4
+      for (int e = 0; e < a.v_first; ++e) {
+        const uint2 q = __ldg(a.el_x + e);
+        const cplx v1 = q.x == 0xffffffffu ? N::zero() : W[q.x];
+        const cplx v2 = q.y == 0xffffffffu ? N::zero() : W[q.y];
+        const cplx y = make_double2(__ldg(a.el_a + e), fma(w, __ldg(a.el_b + e), -__ldg(a.el_g + e) * iw));
+        io[e * xst] = N::mul(y, csub(v1, v2));
       }
+      for (int e = a.v_first; e < a.n_ac_elem; ++e) io[e * xst] = W[__ldg(a.x_off + a.nn + e - a.v_first)];
     }
     a.status[p] = ST_OK;
   }

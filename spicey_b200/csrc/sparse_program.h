@@ -38,18 +38,38 @@
 
 namespace spicey {
 
-enum SparseOp { SOP_PIVOT = 1, SOP_ELIM = 2, SOP_BSUB = 3, SOP_END = 4 };
+enum SparseOp { SOP_PIVOT = 1, SOP_ELIM = 2, SOP_BSUB = 3, SOP_END = 4 };  // intermediate program
+
+// Device micro-ops: one 16-byte word {hdr, A, B, C} each (a single uniform 128-bit load, prefetched one
+// micro-op ahead).  hdr = opcode | kindA << 4 | kindB << 6 | flag << 8 | kindC << 10; operand kinds:
+// 0 zero, 1 global workspace slot, 2 pristine stamped entry (lazy stamping), 3 fast slot (shared
+// memory).  A/B/C hold slot numbers (the uploader scales them by the pool strides) or entry indices.
+enum MicroOp {
+  MOP_END = 0,
+  MOP_PIVHEAD = 1,   // A = pilot's pivot candidate:           ap = A, mp = |ap|^2
+  MOP_CAND = 2,      // A = another candidate, flag = scanned before the pivot:  ok &= flag ? m < mp : !(m > mp)
+  MOP_PIVEND = 3,    // C = slot of 1/pivot:                   verify, r = 1/ap, W[C] = r
+  MOP_ELIM = 4,      // A = a_ik:                              f = A * r (zeroed when |f| < EPS)
+  MOP_UPD = 5,       // A = a_ij (old), B = a_kj, C = a_ij:    W[C] = A - f * B
+  MOP_BHEAD = 6,     // A = b_i, B = 1/u_ii:                   acc = A, rc = B
+  MOP_BTERM = 7,     // A = u_ij, B = x_j:                     acc -= A * B
+  MOP_BEND = 8       // C = slot of x_i, A = i:                W[C] = acc * rc, result[i] = W[C]
+};
+struct MicroWord { int hdr, a, b, c; };
 constexpr int kNoOperand = INT_MIN;  // "structurally zero" operand
 
 struct SparseProgram {
   bool ok = false;
   int n = 0;
   int n_stamp = 0;   // gather-plan entries (pristine operands index these)
-  int n_slots = 0;   // physical workspace slots per system
+  int n_slots = 0;   // global workspace slots per system
+  int n_fast = 0;    // fast (shared-memory) slots per system, the first n_const of them hold constants
+  int n_const = 0;   // distinct pristine values materialised once per system (0 = computed where used)
+  std::vector<int> const_entry;  // [n_const] a stamped entry whose value the constant slot holds
   int n_virtual = 0; // single-assignment values before allocation (statistics)
   long long n_fma = 0, n_div = 0;  // executed complex FMAs / reciprocals per system
-  std::vector<int> code;     // program words, then nothing else
-  std::vector<int> x_slot;   // [n] physical slot of x_i at the end of the program
+  std::vector<MicroWord> code;  // micro-ops, terminated by MOP_END (+ one pad word for the prefetch)
+  std::vector<int> x_slot;      // [n] global slot of x_i at the end of the program
   // per stamped entry: value = (alpha + j*aim0) + j*(omega*beta - gamma/omega)
   std::vector<double> ent_alpha, ent_beta, ent_gamma, ent_jre, ent_jim;
   // per AC element (R,C,L,V order): current = Y_e * (v1 - v2), Y_e = ya + j*(omega*yb - yg/omega)
@@ -81,7 +101,8 @@ struct IrOp {
 
 // Builds the program from the pilot point.  Returns ok=false when the pilot itself is
 // singular / hits the divide guard (the dense kernel then reports the exact status).
-inline void build_sparse_program(const PilotInput& in, SparseProgram& sp) {
+inline void build_sparse_program(const PilotInput& in, SparseProgram& sp, int fast_slots = 12,
+                                 const std::vector<int>* entry_class = nullptr, int n_class = 0) {
   using namespace sparse_detail;
   typedef std::complex<double> cd;
   const int n = in.n, ld = n + 1;
@@ -199,57 +220,109 @@ inline void build_sparse_program(const PilotInput& in, SparseProgram& sp) {
     }
     for (int i = 0; i < n; ++i) last[x_virtual[i]] = INT_MAX;  // x is read by the unpack phase
   }
-  // ---- linear-scan allocation with a LIFO free list ----
-  std::vector<int> phys(nv, -1), free_list;
-  int high = 0;
-  auto alloc = [&]() { if (!free_list.empty()) { int s = free_list.back(); free_list.pop_back(); return s; } return high++; };
-  auto release = [&](int o, int now) {
-    if (o >= 0 && last[o] == now && phys[o] >= 0) { free_list.push_back(phys[o]); last[o] = -2; }
-  };
-  auto P = [&](int o) { return o >= 0 ? phys[o] : o; };  // operand -> physical encoding
+  // ---- definition time of every virtual slot (for lifetimes) ----
+  std::vector<int> deft(nv, 0);
   {
     int t = 0;
     for (const IrOp& op : ir) {
-      if (op.kind == SOP_PIVOT) {
-        sp.code.push_back(SOP_PIVOT);
-        sp.code.push_back((int)op.reads.size());
-        sp.code.push_back(op.pidx);
-        for (int o : op.reads) sp.code.push_back(P(o));
-        for (int o : op.reads) release(o, t);
-        phys[op.def] = alloc();
-        sp.code.push_back(phys[op.def]);
+      if (op.kind == SOP_ELIM) {
         ++t;
-      } else if (op.kind == SOP_ELIM) {
-        sp.code.push_back(SOP_ELIM);
-        sp.code.push_back(P(op.reads[0]));
-        sp.code.push_back((int)op.upd.size());
-        release(op.reads[0], t);
-        ++t;
-        for (const Update& u : op.upd) {
-          const int eo = P(u.dst_old), es = P(u.src);
-          release(u.dst_old, t);   // in-place update when the old version dies here
-          release(u.src, t);
-          phys[u.dst_new] = alloc();
-          sp.code.push_back(eo);
-          sp.code.push_back(es);
-          sp.code.push_back(phys[u.dst_new]);
-          ++t;
-        }
+        for (const Update& u : op.upd) { deft[u.dst_new] = t; ++t; }
       } else {
-        sp.code.push_back(SOP_BSUB);
-        sp.code.push_back(op.var);
-        sp.code.push_back(P(op.reads[0]));
-        sp.code.push_back(P(op.reads[1]));
-        sp.code.push_back((int)(op.reads.size() - 2) / 2);
-        for (size_t q = 2; q < op.reads.size(); ++q) sp.code.push_back(P(op.reads[q]));
-        for (int o : op.reads) release(o, t);
-        phys[op.def] = alloc();
-        sp.code.push_back(phys[op.def]);
+        deft[op.def] = t;
         ++t;
       }
     }
   }
-  sp.code.push_back(SOP_END);
+  // ---- two-pool linear-scan allocation, LIFO free lists ----
+  // Fast pool (shared memory, `fast_slots` per system): constants first (distinct pristine values, when
+  // few enough), then values whose lifetime is short.  Slow pool: global workspace.
+  // x_i always lives in the global pool (the unpack phase gathers it from there).
+  const int kWindow = 96;
+  int n_const = 0;
+  if (entry_class && n_class > 0 && n_class <= fast_slots / 2) n_const = n_class;
+  sp.n_const = n_const;
+  sp.const_entry.assign(n_const, -1);
+  if (n_const)
+    for (int en = 0; en < n_ent; ++en)
+      if (sp.const_entry[(*entry_class)[en]] < 0) sp.const_entry[(*entry_class)[en]] = en;
+  std::vector<int> phys(nv, -1), pool(nv, 0), free_fast, free_slow;
+  int high_fast = n_const, high_slow = 0;
+  std::vector<char> is_x(nv, 0);
+  for (int i = 0; i < n; ++i) is_x[x_virtual[i]] = 1;
+  auto alloc = [&](int v) {
+    const bool want_fast = !is_x[v] && last[v] >= 0 && last[v] != INT_MAX && last[v] - deft[v] <= kWindow;
+    if (want_fast) {
+      if (!free_fast.empty()) { phys[v] = free_fast.back(); free_fast.pop_back(); pool[v] = 3; return; }
+      if (high_fast < fast_slots) { phys[v] = high_fast++; pool[v] = 3; return; }
+    }
+    pool[v] = 1;
+    if (!free_slow.empty()) { phys[v] = free_slow.back(); free_slow.pop_back(); return; }
+    phys[v] = high_slow++;
+  };
+  auto release = [&](int o, int now) {
+    if (o >= 0 && last[o] == now && phys[o] >= 0) {
+      (pool[o] == 3 ? free_fast : free_slow).push_back(phys[o]);
+      last[o] = -2;
+    }
+  };
+  // operand -> (kind, value): 1 global slot, 3 fast slot, 2 pristine entry (or its constant slot), 0 zero
+  auto K = [&](int o) {
+    if (o >= 0) return pool[o];
+    if (o == kNoOperand) return 0;
+    return n_const ? 3 : 2;
+  };
+  auto V = [&](int o) {
+    if (o >= 0) return phys[o];
+    if (o == kNoOperand) return 0;
+    return n_const ? (*entry_class)[~o] : ~o;
+  };
+  auto emit = [&](int opc, int oa, int ob, int def, int flag) {
+    MicroWord w;
+    w.hdr = opc | (K(oa) << 4) | (K(ob) << 6) | (flag << 8) | ((def >= 0 ? pool[def] : 0) << 10);
+    w.a = V(oa); w.b = V(ob); w.c = def >= 0 ? phys[def] : 0;
+    sp.code.push_back(w);
+  };
+  {
+    int t = 0;
+    for (const IrOp& op : ir) {
+      if (op.kind == SOP_PIVOT) {
+        emit(MOP_PIVHEAD, op.reads[op.pidx], kNoOperand, -1, 0);
+        for (int c = 0; c < (int)op.reads.size(); ++c)
+          if (c != op.pidx) emit(MOP_CAND, op.reads[c], kNoOperand, -1, c < op.pidx ? 1 : 0);
+        for (int o : op.reads) release(o, t);
+        alloc(op.def);
+        emit(MOP_PIVEND, kNoOperand, kNoOperand, op.def, 0);
+        ++t;
+      } else if (op.kind == SOP_ELIM) {
+        emit(MOP_ELIM, op.reads[0], kNoOperand, -1, 0);
+        release(op.reads[0], t);
+        ++t;
+        for (const Update& u : op.upd) {
+          const int ka = K(u.dst_old), va = V(u.dst_old), kb = K(u.src), vb = V(u.src);
+          release(u.dst_old, t);   // in-place update when the old version dies here
+          release(u.src, t);
+          alloc(u.dst_new);
+          MicroWord w;
+          w.hdr = MOP_UPD | (ka << 4) | (kb << 6) | (pool[u.dst_new] << 10);
+          w.a = va; w.b = vb; w.c = phys[u.dst_new];
+          sp.code.push_back(w);
+          ++t;
+        }
+      } else {
+        emit(MOP_BHEAD, op.reads[0], op.reads[1], -1, 0);
+        for (size_t q = 2; q + 1 < op.reads.size(); q += 2) emit(MOP_BTERM, op.reads[q], op.reads[q + 1], -1, 0);
+        for (int o : op.reads) release(o, t);
+        alloc(op.def);
+        emit(MOP_BEND, kNoOperand, kNoOperand, op.def, 0);
+        sp.code.back().a = op.var;  // variable index: the device also stores x_i straight into the result
+        ++t;
+      }
+    }
+  }
+  const int high = high_slow;
+  sp.n_fast = high_fast;
+  { MicroWord e = {MOP_END, 0, 0, 0}; sp.code.push_back(e); sp.code.push_back(e); }
   sp.n_slots = high;
   sp.x_slot.resize(n);
   for (int i = 0; i < n; ++i) sp.x_slot[i] = phys[x_virtual[i]];

@@ -13,6 +13,7 @@
 #include <cstdio>
 #include <cstring>
 #include <map>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -212,6 +213,8 @@ struct DeviceCtx {
   SparseProgram sp;
   SparseArgs sp_args;
   uint64_t sp_key = 0;
+  long long sp_T = 0;
+  std::vector<int4> sp_code_scaled;  // program with slot operands scaled by the pool strides
   bool sp_valid = false;
   std::vector<cudaEvent_t> events;
   cudaEvent_t get_event(size_t i) {
@@ -284,6 +287,17 @@ struct spicey_handle {
 namespace {
 
 
+struct ConstProgOwner {
+  std::mutex mu;
+  uint64_t key = 0;
+  long long T = 0;
+  cudaEvent_t ev = nullptr;
+};
+ConstProgOwner& const_owner(int dev) {
+  static ConstProgOwner owners[64];
+  return owners[dev & 63];
+}
+
 uint64_t fnv1a(uint64_t h, const void* data, size_t n) {
   const unsigned char* p = (const unsigned char*)data;
   for (size_t i = 0; i < n; ++i) { h ^= p[i]; h *= 1099511628211ull; }
@@ -347,18 +361,61 @@ int prepare_sparse(DeviceCtx& ctx, const HostPlan& hp, double pilot_f, cudaStrea
   for (int en = 0; en < n_ent; ++en)
     pin.ent_val[en] = std::complex<double>(sp.ent_alpha[en] + sp.ent_jre[en],
                                            w * sp.ent_beta[en] - sp.ent_gamma[en] / w + sp.ent_jim[en]);
-  build_sparse_program(pin, sp);
+  // Entries with identical constants share one value: when few distinct values exist they are
+  // materialised once per system in the fast pool instead of being recomputed where used.
+  std::vector<int> entry_class(n_ent, 0);
+  int n_class = 0;
+  {
+    std::map<std::vector<double>, int> seen;
+    for (int en = 0; en < n_ent; ++en) {
+      std::vector<double> key = {sp.ent_alpha[en] + sp.ent_jre[en], sp.ent_jim[en], sp.ent_beta[en], sp.ent_gamma[en]};
+      auto it = seen.find(key);
+      if (it == seen.end()) it = seen.insert(std::make_pair(key, n_class++)).first;
+      entry_class[en] = it->second;
+    }
+  }
+  const int kFastSlots = 12;  // 12 x 16 B x 128 threads = 24 KiB per CTA, 8 CTAs per SM
+  build_sparse_program(pin, sp, kFastSlots, &entry_class, n_class);
   if (!sp.ok) return SPICEY_SUCCESS;
-  // upload
+  // Workspace stride: the resident grid the workspace is sized for (offsets are baked into the program).
+  {
+    const int block = 128;
+    const size_t per_thread = sizeof(double2) * (size_t)std::max(1, sp.n_slots);
+    long long T = (long long)ctx.sm_count * 10 * block;
+    const long long t_cap = std::max<long long>(block, (long long)(((size_t)12 << 30) / per_thread) / block * block);
+    T = std::min(T, t_cap);                       // workspace <= 12 GiB
+    while ((unsigned long long)sp.n_slots * (unsigned long long)T > 0xfffffff0ull && T > block) T -= block;  // 32-bit offsets
+    ctx.sp_T = T;
+  }
+  const long long T = ctx.sp_T;
+  std::vector<int4>& code = ctx.sp_code_scaled;
+  code.assign(sp.code.size(), make_int4(0, 0, 0, 0));
+  for (size_t i = 0; i < sp.code.size(); ++i) {
+    const MicroWord& m = sp.code[i];
+    const int ka = (m.hdr >> 4) & 3, kb = (m.hdr >> 6) & 3, kc = (m.hdr >> 10) & 3;
+    int4 q = make_int4(m.hdr, m.a, m.b, m.c);
+    if (ka == 1) q.y = (int)(unsigned)((long long)m.a * T); else if (ka == 3) q.y = m.a * 128;
+    if (kb == 1) q.z = (int)(unsigned)((long long)m.b * T); else if (kb == 3) q.z = m.b * 128;
+    if (kc == 1) q.w = (int)(unsigned)((long long)m.c * T); else if (kc == 3) q.w = m.c * 128;
+    code[i] = q;
+  }
+  std::vector<unsigned> x_off(hp.nvar);
+  for (int i = 0; i < hp.nvar; ++i) x_off[i] = (unsigned)((long long)sp.x_slot[i] * T);
+  std::vector<uint2> el_x(std::max(1, hp.n_ac_elem));
+  for (int e = 0; e < hp.n_ac_elem; ++e) {
+    const int n1 = hp.ends[e].x, n2 = hp.ends[e].y;
+    el_x[e] = make_uint2(n1 ? x_off[n1 - 1] : 0xffffffffu, n2 ? x_off[n2 - 1] : 0xffffffffu);
+  }
   std::vector<double2> c0(n_ent), c1(n_ent);
   for (int en = 0; en < n_ent; ++en) {
     c0[en] = make_double2(sp.ent_alpha[en] + sp.ent_jre[en], sp.ent_jim[en]);
     c1[en] = make_double2(sp.ent_beta[en], sp.ent_gamma[en]);
   }
   std::vector<unsigned char> blob;
-  size_t o_code = push_blob(blob, sp.code), o_xs = push_blob(blob, sp.x_slot), o_c0 = push_blob(blob, c0);
-  size_t o_c1 = push_blob(blob, c1), o_ea = push_blob(blob, sp.el_a), o_eb = push_blob(blob, sp.el_b);
-  size_t o_eg = push_blob(blob, sp.el_g), o_l = push_blob(blob, sp.ind_L), o_ends = push_blob(blob, hp.ends);
+  size_t o_code = push_blob(blob, code), o_xs = push_blob(blob, x_off), o_ex = push_blob(blob, el_x);
+  size_t o_c0 = push_blob(blob, c0), o_c1 = push_blob(blob, c1), o_ea = push_blob(blob, sp.el_a);
+  size_t o_eb = push_blob(blob, sp.el_b), o_eg = push_blob(blob, sp.el_g), o_l = push_blob(blob, sp.ind_L);
+  size_t o_ce = push_blob(blob, sp.const_entry);
   int rc = ctx.sp_blob.ensure(blob.size() + 16);
   if (rc) return rc;
   CUDA_TRY(cudaMemcpyAsync(ctx.sp_blob.p, blob.data(), blob.size(), cudaMemcpyHostToDevice, stream));
@@ -366,13 +423,14 @@ int prepare_sparse(DeviceCtx& ctx, const HostPlan& hp, double pilot_f, cudaStrea
   unsigned char* b = (unsigned char*)ctx.sp_blob.p;
   SparseArgs& a = ctx.sp_args;
   memset(&a, 0, sizeof(a));
-  a.code = (const int*)(b + o_code);
-  a.x_slot = (const int*)(b + o_xs);
-  a.n = hp.nvar; a.n_stamp = sp.n_stamp; a.n_slots = sp.n_slots;
+  a.code = (const int4*)(b + o_code);
+  a.x_off = (const unsigned*)(b + o_xs);
+  a.el_x = (const uint2*)(b + o_ex);
+  a.n = hp.nvar; a.n_stamp = sp.n_stamp; a.n_slots = sp.n_slots; a.n_fast = sp.n_fast; a.n_const = sp.n_const;
+  a.const_entry = (const int*)(b + o_ce);
   a.ent_c0 = (const double2*)(b + o_c0); a.ent_c1 = (const double2*)(b + o_c1);
   a.el_a = (const double*)(b + o_ea); a.el_b = (const double*)(b + o_eb); a.el_g = (const double*)(b + o_eg);
   a.ind_L = (const double*)(b + o_l); a.n_ind = (int)sp.ind_L.size();
-  a.ends = (const int4*)(b + o_ends);
   a.n_ac_elem = hp.n_ac_elem; a.nn = hp.nn; a.v_first = hp.off[ELEM_V];
   ctx.sp_valid = true;
   return SPICEY_SUCCESS;
@@ -386,11 +444,9 @@ int launch_ac_dense(DeviceCtx& ctx, const HostPlan& hp, const DevPlan& dp, const
 int launch_ac_sparse(DeviceCtx& ctx, const HostPlan& hp, const DevPlan& dp, const AcArgs& args, uint32_t flags,
                      cudaStream_t stream, int* tier_out, int64_t* launches) {
   const int block = 128;
-  long long T = std::min<long long>((args.p_count + block - 1) / block, (long long)ctx.sm_count * 8) * block;
-  const size_t per_thread = sizeof(double2) * (size_t)std::max(1, ctx.sp.n_slots);
-  const long long t_cap = std::max<long long>(block, (long long)(((size_t)12 << 30) / per_thread) / block * block);
-  T = std::min(T, t_cap);  // workspace <= 12 GiB (large programs: fewer resident threads, same grid-stride loop)
-  size_t wbytes = per_thread * T;
+  const long long T = ctx.sp_T;  // workspace stride (fixed when the program was uploaded)
+  const long long nthreads = std::min<long long>((args.p_count + block - 1) / block * block, T);
+  size_t wbytes = sizeof(double2) * (size_t)std::max(1, ctx.sp.n_slots) * T;
   int rc = ctx.sp_work.ensure(wbytes);
   if (rc) return rc;
   if ((rc = ctx.sp_fb.ensure(sizeof(long long) * args.p_count + 64))) return rc;
@@ -402,9 +458,27 @@ int launch_ac_sparse(DeviceCtx& ctx, const HostPlan& hp, const DevPlan& dp, cons
   a.p_count = args.p_count;
   a.W = (double2*)ctx.sp_work.p;
   a.T = T;
-  a.x = args.x; a.ielem = args.ielem; a.status = args.status;
+  a.x = args.x; a.ielem = args.ielem; a.status = args.status; a.series_ld = args.series_ld;
   a.fb_list = fb_list; a.fb_count = fb_count;
-  ac_sparse_kernel<<<(unsigned)(T / block), block, 0, stream>>>(a);
+  const size_t fast_bytes = sizeof(double2) * (size_t)std::max(1, ctx.sp.n_fast) * block;
+  if ((int)ctx.sp.code.size() <= kConstProgWords) {
+    // Constant-memory program: one resident program per device at a time.  The upload is ordered after
+    // the last kernel that used the previous contents.
+    ConstProgOwner& own = const_owner(ctx.dev);
+    std::lock_guard<std::mutex> lock(own.mu);
+    if (own.key != ctx.sp_key || own.T != T) {
+      if (own.ev) CUDA_TRY(cudaStreamWaitEvent(stream, own.ev, 0));
+      CUDA_TRY(cudaMemcpyToSymbolAsync(c_sparse_prog, ctx.sp_code_scaled.data(), sizeof(int4) * ctx.sp_code_scaled.size(),
+                                       0, cudaMemcpyHostToDevice, stream));
+      own.key = ctx.sp_key;
+      own.T = T;
+    }
+    ac_sparse_kernel<true><<<(unsigned)(nthreads / block), block, fast_bytes, stream>>>(a);
+    if (!own.ev) CUDA_TRY(cudaEventCreateWithFlags(&own.ev, cudaEventDisableTiming));
+    CUDA_TRY(cudaEventRecord(own.ev, stream));
+  } else {
+    ac_sparse_kernel<false><<<(unsigned)(nthreads / block), block, fast_bytes, stream>>>(a);
+  }
   CUDA_TRY(cudaGetLastError());
   if (launches) ++*launches;
   AcArgs d = args;
@@ -676,6 +750,7 @@ int32_t spicey_ac_solve_device(spicey_handle* h, int32_t dev_index, const spicey
   AcArgs a;
   a.freqs = d_freqs; a.n_freq = n_freq; a.p_begin = 0; a.p_count = dp.n_inst * n_freq;
   a.x = (double2*)d_x; a.ielem = (double2*)d_ielem; a.status = d_status; a.scratch = nullptr; a.plist = nullptr; a.pcount = nullptr; a.fb_total = nullptr;
+  a.series_ld = (flags & SPICEY_FLAG_SERIES_MAJOR) ? a.p_count : 0;
   int tier = 0;
   int64_t launches = 0;
   if ((rc = ctx.sp_fb.ensure(sizeof(long long) * a.p_count + 64))) return rc;
@@ -706,6 +781,7 @@ int32_t spicey_ac_solve(spicey_handle* h, const spicey_elem_table* table, const 
   const long long P = n_inst * n_freq;
   const int D = (int)h->devs.size();
   const size_t xrow = sizeof(double2) * hp.nvar, irow = sizeof(double2) * hp.n_ac_elem;
+  const bool series = (flags & SPICEY_FLAG_SERIES_MAJOR) != 0;
   // Chunk size: ~96 MiB of results per chunk so that copies overlap the next chunk's kernel.
   long long chunk = std::max<long long>(1024, (long long)((96ull << 20) / (xrow + (ielem ? irow : 0) + 4)));
   int64_t launches = 0, h2d = 0, d2h = 0;
@@ -756,14 +832,24 @@ int32_t spicey_ac_solve(spicey_handle* h, const spicey_elem_table* table, const 
       a.freqs = (const double*)ctx.in0.p; a.n_freq = n_freq; a.p_begin = lo; a.p_count = n;
       a.x = (double2*)ctx.out_x[b].p; a.ielem = ielem ? (double2*)ctx.out_i[b].p : nullptr;
       a.status = (int*)ctx.out_s[b].p; a.scratch = nullptr; a.plist = nullptr; a.pcount = nullptr; a.fb_total = nullptr;
+      a.series_ld = series ? n : 0;
       CUDA_TRY(cudaEventRecord(ks, ctx.compute));
       rc = launch_ac(ctx, hp, dp, a, flags, ctx.compute, &tier, &launches, freqs[n_freq / 2], true);
       if (rc) return rc;
       CUDA_TRY(cudaEventRecord(ke, ctx.compute));
       CUDA_TRY(cudaStreamWaitEvent(ctx.copy, ke, 0));
-      CUDA_TRY(cudaMemcpyAsync((char*)x + xrow * lo, a.x, xrow * n, cudaMemcpyDeviceToHost, ctx.copy));
-      if (ielem)
-        CUDA_TRY(cudaMemcpyAsync((char*)ielem + irow * lo, a.ielem, irow * n, cudaMemcpyDeviceToHost, ctx.copy));
+      if (series) {  // device chunk [rows][n] -> host [rows][P] at column lo
+        const size_t w = sizeof(double2) * n;
+        CUDA_TRY(cudaMemcpy2DAsync((char*)x + sizeof(double2) * lo, sizeof(double2) * P, a.x, w, w, hp.nvar,
+                                   cudaMemcpyDeviceToHost, ctx.copy));
+        if (ielem && hp.n_ac_elem > 0)
+          CUDA_TRY(cudaMemcpy2DAsync((char*)ielem + sizeof(double2) * lo, sizeof(double2) * P, a.ielem, w, w,
+                                     hp.n_ac_elem, cudaMemcpyDeviceToHost, ctx.copy));
+      } else {
+        CUDA_TRY(cudaMemcpyAsync((char*)x + xrow * lo, a.x, xrow * n, cudaMemcpyDeviceToHost, ctx.copy));
+        if (ielem)
+          CUDA_TRY(cudaMemcpyAsync((char*)ielem + irow * lo, a.ielem, irow * n, cudaMemcpyDeviceToHost, ctx.copy));
+      }
       CUDA_TRY(cudaMemcpyAsync(status + lo, a.status, sizeof(int) * n, cudaMemcpyDeviceToHost, ctx.copy));
       CUDA_TRY(cudaEventRecord(cd, ctx.copy));
       d2h += (int64_t)((xrow + (ielem ? irow : 0) + 4) * n);

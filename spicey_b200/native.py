@@ -16,6 +16,7 @@ ELEM_R, ELEM_C, ELEM_L, ELEM_V, ELEM_S, ELEM_D = range(6)
 VALUE_SLOTS = {ELEM_R: 1, ELEM_C: 1, ELEM_L: 1, ELEM_V: 3, ELEM_S: 4, ELEM_D: 2}
 ST_OK, ST_SINGULAR, ST_CDIV, ST_R_NONPOS = 0, 1, 2, 3
 FLAG_STRICT, FLAG_FORCE_GMEM, FLAG_FORCE_CTA, FLAG_DENSE, FLAG_SPARSE, FLAG_GENERIC_THREAD = 1, 2, 4, 8, 16, 32
+FLAG_SERIES_MAJOR = 64
 TIER_THREAD, TIER_CTA_SMEM, TIER_CTA_GMEM, TIER_SPARSE = 1, 2, 3, 4
 SUCCESS, ERR_INVALID, ERR_NO_DEVICE, ERR_CUDA, ERR_UNSUPPORTED = 0, 1, 2, 3, 4
 
@@ -191,13 +192,17 @@ class Engine:
     # -- host-buffer entry points ------------------------------------------------
     def ac_solve(self, table: ElemTable, freqs, sweep: Optional[Sweep] = None, want_currents=True, flags=0,
                  out=None):
-        """Returns (x[P,nvar] c128, ielem[P,nAc] c128 | None, status[P] i32); P = n_inst*n_freq."""
+        """Returns (x[P,nvar] c128, ielem[P,nAc] c128 | None, status[P] i32); P = n_inst*n_freq.
+        With FLAG_SERIES_MAJOR in flags the arrays are x[nvar,P], ielem[nAc,P]."""
         freqs = np.ascontiguousarray(freqs, dtype=np.float64)
         F = int(freqs.shape[0])
         P = F * (sweep.n_inst if sweep else 1)
         if out is None:
-            x = np.empty((P, table.nvar), dtype=np.complex128)
-            ie = np.empty((P, table.n_ac_elem), dtype=np.complex128) if want_currents else None
+            sm = bool(flags & FLAG_SERIES_MAJOR)
+            x = np.empty((table.nvar, P) if sm else (P, table.nvar), dtype=np.complex128)
+            ie = None
+            if want_currents:
+                ie = np.empty((table.n_ac_elem, P) if sm else (P, table.n_ac_elem), dtype=np.complex128)
             st = np.empty(P, dtype=np.int32)
         else:
             x, ie, st = out
