@@ -105,11 +105,16 @@ __global__ void __launch_bounds__(128) ac_sparse_kernel(SparseArgs a) {
     cplx r = N::zero(), fm = N::zero(), ap = N::zero(), acc = N::zero(), rc = N::zero();
     double mp = 0.0;
     bool ok = true;
-    int4 nxt = CONST_PROG ? c_sparse_prog[0] : __ldg(code);
+    // Three micro-ops are in flight ahead of the one being executed (the program ends with END padding).
+    int4 n1 = CONST_PROG ? c_sparse_prog[0] : __ldg(code);
+    int4 n2 = CONST_PROG ? c_sparse_prog[1] : __ldg(code + 1);
+    int4 n3 = CONST_PROG ? c_sparse_prog[2] : __ldg(code + 2);
     while (!diverged && status == ST_OK) {
-      const int4 u = nxt;
+      const int4 u = n1;
+      n1 = n2;
+      n2 = n3;
+      n3 = CONST_PROG ? c_sparse_prog[pc + 3] : __ldg(code + pc + 3);
       ++pc;
-      nxt = CONST_PROG ? c_sparse_prog[pc] : __ldg(code + pc);   // prefetch: the program ends with two END words
       const int hdr = u.x;
       const int op = hdr & 15, ka = (hdr >> 4) & 3, kb = (hdr >> 6) & 3, kc = (hdr >> 10) & 3;
       if (op == MOP_UPD) {
@@ -161,7 +166,7 @@ __global__ void __launch_bounds__(128) ac_sparse_kernel(SparseArgs a) {
       continue;
     }
     if (io) {
-#pragma unroll 4
+#pragma unroll 8
       for (int e = 0; e < a.v_first; ++e) {
         const uint2 q = __ldg(a.el_x + e);
         const cplx v1 = q.x == 0xffffffffu ? N::zero() : W[q.x];

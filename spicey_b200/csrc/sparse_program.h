@@ -322,7 +322,7 @@ inline void build_sparse_program(const PilotInput& in, SparseProgram& sp, int fa
   }
   const int high = high_slow;
   sp.n_fast = high_fast;
-  { MicroWord e = {MOP_END, 0, 0, 0}; sp.code.push_back(e); sp.code.push_back(e); }
+  { MicroWord e = {MOP_END, 0, 0, 0}; for (int q = 0; q < 4; ++q) sp.code.push_back(e); }  // END + prefetch padding
   sp.n_slots = high;
   sp.x_slot.resize(n);
   for (int i = 0; i < n; ++i) sp.x_slot[i] = phys[x_virtual[i]];
