@@ -58,14 +58,21 @@ struct SparseArgs {
 constexpr int kConstProgWords = 3840;  // 60 KiB of the 64 KiB constant bank
 __constant__ int4 c_sparse_prog[kConstProgWords];
 
-template <bool CONST_PROG>
+// Operand words of pointer kind: bit 31 selects the pool (1 = fast shared-memory pool, 0 = global
+// workspace), bits 0-30 are the offset in double2 units.  Both pools are reached through generic
+// addresses, so an operand fetch is select-base + one load, without branches.  A structural zero is
+// the fast pool's zero slot.  HAS_PRISTINE: some operands are stamped entries recomputed in place
+// (only when the circuit has too many distinct entry values to materialise them as constants).
+template <bool CONST_PROG, bool HAS_PRISTINE, bool UNIFIED>
 __global__ void __launch_bounds__(128) ac_sparse_kernel(SparseArgs a) {
   typedef Num<cplx> N;
   const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const long long nthreads = (long long)gridDim.x * blockDim.x;
-  extern __shared__ __align__(16) double2 fast_pool[];   // [n_fast][128]: short-lived values and constants
-  double2* __restrict__ W = a.W + tid;
-  double2* __restrict__ F = fast_pool + threadIdx.x;
+  extern __shared__ __align__(16) double2 fast_pool[];   // [n_fast][128]: short-lived values, constants, zero
+  double2* W = a.W + tid;
+  // UNIFIED: the fast pool is just the tail of the global workspace (slots n_slots..), kept hot by L1/L2
+  double2* F = UNIFIED ? W + (long long)a.n_slots * a.T : fast_pool + threadIdx.x;
+  const int fstride = UNIFIED ? (int)a.T : 128;
   const int4* __restrict__ code = a.code;
   const double2* __restrict__ c0p = a.ent_c0;
   const double2* __restrict__ c1p = a.ent_c1;
@@ -79,19 +86,16 @@ __global__ void __launch_bounds__(128) ac_sparse_kernel(SparseArgs a) {
       const double2 c0 = __ldg(c0p + en), c1 = __ldg(c1p + en);
       return make_double2(c0.x, fma(w, c1.x, -c1.y * iw) + c0.y);
     };
-    // Operand fetch by kind: 3 fast slot (shared memory), 1 global workspace slot, 2 pristine stamped
-    // entry computed in place (lazy stamping), 0 zero.
+    auto slot = [&](int v) -> double2* {
+      if (UNIFIED) return W + (unsigned)v;
+      return (v < 0 ? F : W) + (unsigned)(v & 0x7fffffff);
+    };
     auto fetch = [&](int kind, int v) -> cplx {
-      cplx r = make_double2(0.0, 0.0);
-      if (kind == 3) r = F[v];
-      else if (kind == 1) r = W[(unsigned)v];
-      else if (kind == 2) r = pristine(v);
-      return r;
+      if (HAS_PRISTINE && kind == 2) return pristine(v);
+      return *slot(v);
     };
-    auto put = [&](int kind, int v, cplx val) {
-      if (kind == 3) F[v] = val; else W[(unsigned)v] = val;
-    };
-    for (int c = 0; c < a.n_const; ++c) F[c * 128] = pristine(__ldg(a.const_entry + c));
+    for (int c = 0; c < a.n_const; ++c) F[(long long)c * fstride] = pristine(__ldg(a.const_entry + c));
+    F[(long long)a.n_const * fstride] = make_double2(0.0, 0.0);   // the zero slot
     bool diverged = false;
     int status = ST_OK;
     // inductor guards of simulateAC.ts:47-51 / Complex.ts:41 are value dependent: leave them to the dense kernel
@@ -105,50 +109,61 @@ __global__ void __launch_bounds__(128) ac_sparse_kernel(SparseArgs a) {
     cplx r = N::zero(), fm = N::zero(), ap = N::zero(), acc = N::zero(), rc = N::zero();
     double mp = 0.0;
     bool ok = true;
-    // Three micro-ops are in flight ahead of the one being executed (the program ends with END padding).
-    int4 n1 = CONST_PROG ? c_sparse_prog[0] : __ldg(code);
-    int4 n2 = CONST_PROG ? c_sparse_prog[1] : __ldg(code + 1);
-    int4 n3 = CONST_PROG ? c_sparse_prog[2] : __ldg(code + 2);
+    int4 nxt = CONST_PROG ? c_sparse_prog[0] : __ldg(code);
     while (!diverged && status == ST_OK) {
-      const int4 u = n1;
-      n1 = n2;
-      n2 = n3;
-      n3 = CONST_PROG ? c_sparse_prog[pc + 3] : __ldg(code + pc + 3);
+      const int4 u = nxt;
       ++pc;
+      nxt = CONST_PROG ? c_sparse_prog[pc] : __ldg(code + pc);   // prefetch (the program ends with END padding)
       const int hdr = u.x;
-      const int op = hdr & 15, ka = (hdr >> 4) & 3, kb = (hdr >> 6) & 3, kc = (hdr >> 10) & 3;
-      if (op == MOP_UPD) {
-        const cplx dst = fetch(ka, u.y);
-        const cplx src = fetch(kb, u.z);
-        put(kc, u.w, N::submul<false>(dst, fm, src));                       // solveComplex.ts:47-52
-      } else if (op == MOP_BTERM) {
-        acc = N::submul<false>(acc, fetch(ka, u.y), fetch(kb, u.z));        // :62-68
-      } else if (op == MOP_ELIM) {
-        fm = N::mul(fetch(ka, u.y), r);                                     // :45
-        if (N::metric<false>(fm) < thr) fm = N::zero();                     // :46 (zero multiplier = row untouched)
-      } else if (op == MOP_CAND) {
-        const double m = N::metric<false>(fetch(ka, u.y));
-        ok = ok && ((hdr >> 8) & 1 ? (m < mp) : !(m > mp));                 // first maximum wins (:20-28)
-      } else if (op == MOP_PIVHEAD) {
-        ap = fetch(ka, u.y);
-        mp = N::metric<false>(ap);
-        ok = (mp == mp);
-      } else if (op == MOP_PIVEND) {
-        if (!ok) { diverged = true; break; }
-        if (mp < thr) { status = ST_SINGULAR; break; }                      // :29
-        if (mp < kEps) { status = ST_CDIV; break; }                         // Complex.ts:41-42
-        r = N::recip(ap);
-        put(kc, u.w, r);                                                    // 1/u_kk for the back-substitution
-      } else if (op == MOP_BHEAD) {
-        acc = fetch(ka, u.y);
-        rc = fetch(kb, u.z);
-      } else if (op == MOP_BEND) {
-        const cplx xi = N::mul(acc, rc);                                    // :69-70
-        put(kc, u.w, xi);
-        xout[(long long)u.y * xst] = xi;                                    // u.y = variable index: straight to the result
-      } else {
-        break;
+      const int op = hdr & 15, ka = (hdr >> 4) & 3, kb = (hdr >> 6) & 3;
+      switch (op) {
+        case MOP_UPD: {
+          const cplx dst = fetch(ka, u.y);
+          const cplx src = fetch(kb, u.z);
+          *slot(u.w) = N::submul<false>(dst, fm, src);                      // solveComplex.ts:47-52
+          break;
+        }
+        case MOP_BTERM:
+          acc = N::submul<false>(acc, fetch(ka, u.y), fetch(kb, u.z));      // :62-68
+          break;
+        case MOP_CAND: {
+          const double m = N::metric<false>(fetch(ka, u.y));
+          ok = ok && ((hdr >> 8) & 1 ? (m < mp) : !(m > mp));               // first maximum wins (:20-28)
+          break;
+        }
+        case MOP_ELIM:
+          fm = N::mul(fetch(ka, u.y), r);                                   // :45
+          if (N::metric<false>(fm) < thr) fm = N::zero();                   // :46 (zero multiplier = row untouched)
+          break;
+        case MOP_PIVHEAD:
+          ap = fetch(ka, u.y);
+          mp = N::metric<false>(ap);
+          ok = (mp == mp);
+          break;
+        case MOP_PIVEND:
+          if (!ok) diverged = true;
+          else if (mp < thr) status = ST_SINGULAR;                          // :29
+          else if (mp < kEps) status = ST_CDIV;                             // Complex.ts:41-42
+          else {
+            r = N::recip(ap);
+            *slot(u.w) = r;                                                 // 1/u_kk for the back-substitution
+          }
+          break;
+        case MOP_BHEAD:
+          acc = fetch(ka, u.y);
+          rc = fetch(kb, u.z);
+          break;
+        case MOP_BEND: {
+          const cplx xi = N::mul(acc, rc);                                  // :69-70
+          *slot(u.w) = xi;
+          xout[(long long)u.y * xst] = xi;                                  // u.y = variable index: straight to the result
+          break;
+        }
+        default:
+          pc = -1;
+          break;
       }
+      if (pc < 0) break;
     }
     // ---- unpack (simulateAC.ts:85-126) ----
     if (diverged) {

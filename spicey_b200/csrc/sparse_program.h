@@ -42,8 +42,9 @@ enum SparseOp { SOP_PIVOT = 1, SOP_ELIM = 2, SOP_BSUB = 3, SOP_END = 4 };  // in
 
 // Device micro-ops: one 16-byte word {hdr, A, B, C} each (a single uniform 128-bit load, prefetched one
 // micro-op ahead).  hdr = opcode | kindA << 4 | kindB << 6 | flag << 8 | kindC << 10; operand kinds:
-// 0 zero, 1 global workspace slot, 2 pristine stamped entry (lazy stamping), 3 fast slot (shared
-// memory).  A/B/C hold slot numbers (the uploader scales them by the pool strides) or entry indices.
+// 1 global workspace slot, 2 pristine stamped entry (lazy stamping), 3 fast slot (shared memory; one
+// fast slot permanently holds 0 and stands for structural zeros).  A/B/C hold slot numbers (the
+// uploader turns them into pool-tagged, stride-scaled offsets) or entry indices.
 enum MicroOp {
   MOP_END = 0,
   MOP_PIVHEAD = 1,   // A = pilot's pivot candidate:           ap = A, mp = |ap|^2
@@ -240,14 +241,15 @@ inline void build_sparse_program(const PilotInput& in, SparseProgram& sp, int fa
   // x_i always lives in the global pool (the unpack phase gathers it from there).
   const int kWindow = 96;
   int n_const = 0;
-  if (entry_class && n_class > 0 && n_class <= fast_slots / 2) n_const = n_class;
+  if (entry_class && n_class > 0 && n_class <= (fast_slots - 1) / 2) n_const = n_class;
   sp.n_const = n_const;
   sp.const_entry.assign(n_const, -1);
   if (n_const)
     for (int en = 0; en < n_ent; ++en)
       if (sp.const_entry[(*entry_class)[en]] < 0) sp.const_entry[(*entry_class)[en]] = en;
   std::vector<int> phys(nv, -1), pool(nv, 0), free_fast, free_slow;
-  int high_fast = n_const, high_slow = 0;
+  const int zero_slot = n_const;            // fast slot that always holds 0 (structural zeros)
+  int high_fast = n_const + 1, high_slow = 0;
   std::vector<char> is_x(nv, 0);
   for (int i = 0; i < n; ++i) is_x[x_virtual[i]] = 1;
   auto alloc = [&](int v) {
@@ -269,12 +271,12 @@ inline void build_sparse_program(const PilotInput& in, SparseProgram& sp, int fa
   // operand -> (kind, value): 1 global slot, 3 fast slot, 2 pristine entry (or its constant slot), 0 zero
   auto K = [&](int o) {
     if (o >= 0) return pool[o];
-    if (o == kNoOperand) return 0;
+    if (o == kNoOperand) return 3;          // the zero slot
     return n_const ? 3 : 2;
   };
   auto V = [&](int o) {
     if (o >= 0) return phys[o];
-    if (o == kNoOperand) return 0;
+    if (o == kNoOperand) return zero_slot;
     return n_const ? (*entry_class)[~o] : ~o;
   };
   auto emit = [&](int opc, int oa, int ob, int def, int flag) {
@@ -316,6 +318,7 @@ inline void build_sparse_program(const PilotInput& in, SparseProgram& sp, int fa
         alloc(op.def);
         emit(MOP_BEND, kNoOperand, kNoOperand, op.def, 0);
         sp.code.back().a = op.var;  // variable index: the device also stores x_i straight into the result
+        sp.code.back().hdr &= ~(3 << 4);  // A is a plain integer here, not an operand
         ++t;
       }
     }

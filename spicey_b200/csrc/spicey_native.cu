@@ -214,6 +214,7 @@ struct DeviceCtx {
   SparseArgs sp_args;
   uint64_t sp_key = 0;
   long long sp_T = 0;
+  bool sp_unified = false;
   std::vector<int4> sp_code_scaled;  // program with slot operands scaled by the pool strides
   bool sp_valid = false;
   std::vector<cudaEvent_t> events;
@@ -380,23 +381,30 @@ int prepare_sparse(DeviceCtx& ctx, const HostPlan& hp, double pilot_f, cudaStrea
   // Workspace stride: the resident grid the workspace is sized for (offsets are baked into the program).
   {
     const int block = 128;
-    const size_t per_thread = sizeof(double2) * (size_t)std::max(1, sp.n_slots);
+    const size_t per_thread = sizeof(double2) * (size_t)std::max(1, sp.n_slots + sp.n_fast);
     long long T = (long long)ctx.sm_count * 10 * block;
     const long long t_cap = std::max<long long>(block, (long long)(((size_t)12 << 30) / per_thread) / block * block);
     T = std::min(T, t_cap);                       // workspace <= 12 GiB
-    while ((unsigned long long)sp.n_slots * (unsigned long long)T > 0xfffffff0ull && T > block) T -= block;  // 32-bit offsets
+    while ((unsigned long long)(sp.n_slots + sp.n_fast) * (unsigned long long)T > 0x7ffffff0ull && T > block) T -= block;  // 31-bit offsets
     ctx.sp_T = T;
   }
   const long long T = ctx.sp_T;
+  // A/B-measured alternative (fast pool as the tail of the global workspace, kept hot by L1): within 5 % on
+  // cfg2 and 15 % slower on cfg4 than the shared-memory pool, so it stays off.
+  const bool unified = ctx.sp_unified = false;
   std::vector<int4>& code = ctx.sp_code_scaled;
   code.assign(sp.code.size(), make_int4(0, 0, 0, 0));
   for (size_t i = 0; i < sp.code.size(); ++i) {
     const MicroWord& m = sp.code[i];
     const int ka = (m.hdr >> 4) & 3, kb = (m.hdr >> 6) & 3, kc = (m.hdr >> 10) & 3;
     int4 q = make_int4(m.hdr, m.a, m.b, m.c);
-    if (ka == 1) q.y = (int)(unsigned)((long long)m.a * T); else if (ka == 3) q.y = m.a * 128;
-    if (kb == 1) q.z = (int)(unsigned)((long long)m.b * T); else if (kb == 3) q.z = m.b * 128;
-    if (kc == 1) q.w = (int)(unsigned)((long long)m.c * T); else if (kc == 3) q.w = m.c * 128;
+    // pointer operands: bit 31 = fast pool, low bits = offset in double2 units
+    auto enc = [&](int kind, int v) -> int {
+      if (kind == 1) return (int)(unsigned)((long long)v * T);
+      if (kind == 3) return unified ? (int)(unsigned)((long long)(sp.n_slots + v) * T) : (int)(0x80000000u | (unsigned)(v * 128));
+      return v;
+    };
+    q.y = enc(ka, m.a); q.z = enc(kb, m.b); q.w = enc(kc, m.c);
     code[i] = q;
   }
   std::vector<unsigned> x_off(hp.nvar);
@@ -446,7 +454,7 @@ int launch_ac_sparse(DeviceCtx& ctx, const HostPlan& hp, const DevPlan& dp, cons
   const int block = 128;
   const long long T = ctx.sp_T;  // workspace stride (fixed when the program was uploaded)
   const long long nthreads = std::min<long long>((args.p_count + block - 1) / block * block, T);
-  size_t wbytes = sizeof(double2) * (size_t)std::max(1, ctx.sp.n_slots) * T;
+  size_t wbytes = sizeof(double2) * (size_t)std::max(1, ctx.sp.n_slots + ctx.sp.n_fast) * T;
   int rc = ctx.sp_work.ensure(wbytes);
   if (rc) return rc;
   if ((rc = ctx.sp_fb.ensure(sizeof(long long) * args.p_count + 64))) return rc;
@@ -461,6 +469,19 @@ int launch_ac_sparse(DeviceCtx& ctx, const HostPlan& hp, const DevPlan& dp, cons
   a.x = args.x; a.ielem = args.ielem; a.status = args.status; a.series_ld = args.series_ld;
   a.fb_list = fb_list; a.fb_count = fb_count;
   const size_t fast_bytes = sizeof(double2) * (size_t)std::max(1, ctx.sp.n_fast) * block;
+  const bool pristine_ops = ctx.sp.n_const == 0;
+  const bool uni = ctx.sp_unified;
+  const unsigned grid = (unsigned)(nthreads / block);
+#define SPARSE_LAUNCH(CP)                                                                              \
+  do {                                                                                                 \
+    if (uni) {                                                                                         \
+      if (pristine_ops) ac_sparse_kernel<CP, true, true><<<grid, block, 0, stream>>>(a);               \
+      else ac_sparse_kernel<CP, false, true><<<grid, block, 0, stream>>>(a);                           \
+    } else {                                                                                           \
+      if (pristine_ops) ac_sparse_kernel<CP, true, false><<<grid, block, fast_bytes, stream>>>(a);     \
+      else ac_sparse_kernel<CP, false, false><<<grid, block, fast_bytes, stream>>>(a);                 \
+    }                                                                                                  \
+  } while (0)
   if ((int)ctx.sp.code.size() <= kConstProgWords) {
     // Constant-memory program: one resident program per device at a time.  The upload is ordered after
     // the last kernel that used the previous contents.
@@ -473,12 +494,13 @@ int launch_ac_sparse(DeviceCtx& ctx, const HostPlan& hp, const DevPlan& dp, cons
       own.key = ctx.sp_key;
       own.T = T;
     }
-    ac_sparse_kernel<true><<<(unsigned)(nthreads / block), block, fast_bytes, stream>>>(a);
+    SPARSE_LAUNCH(true);
     if (!own.ev) CUDA_TRY(cudaEventCreateWithFlags(&own.ev, cudaEventDisableTiming));
     CUDA_TRY(cudaEventRecord(own.ev, stream));
   } else {
-    ac_sparse_kernel<false><<<(unsigned)(nthreads / block), block, fast_bytes, stream>>>(a);
+    SPARSE_LAUNCH(false);
   }
+#undef SPARSE_LAUNCH
   CUDA_TRY(cudaGetLastError());
   if (launches) ++*launches;
   AcArgs d = args;
