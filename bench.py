@@ -99,6 +99,22 @@ def load_workload(name, points=None, instances=None):
     import spicey_b200 as sp
     from spicey_b200.packing import make_sweep, pack_circuit, sample_sources, initial_state
     wl = {"name": name}
+    if name == "cfg2mc":  # not a BASELINE config: cfg2's ladder with every R and C swept +-5 % (AC Monte-Carlo axis)
+        ck = parse_netlist(W.rc_ladder(64))
+        n = instances or 4096
+        freqs = np.logspace(0, 5, 245)
+        u = W.splitmix_uniform_pm1(n, 126)
+        ov = {}
+        for k in range(1, 64):
+            ov["r%d" % k] = 1000.0 * (1 + 0.05 * u[:, k - 1])
+            ov["c%d" % k] = 1e-9 * (1 + 0.05 * u[:, 62 + k])
+        table = pack_circuit(ck)
+        wl.update(kind="ac", ckt=ck, table=table, freqs=freqs, units=int(n * freqs.shape[0]),
+                  sweep=make_sweep(table, n, ov), n_inst=n, overrides=ov,
+                  label="cfg2mc: 64-node RC ladder, %d Monte-Carlo instances x %d frequencies (all R, C +-5 %%)" % (
+                      n, freqs.shape[0]),
+                  flops_per_unit=f_cplx(table.nvar), bytes_per_unit=8 + 16 * table.nvar + 16 * table.n_ac_elem)
+        return wl
     if name in ("cfg2", "cfg4", "cfg1"):
         text = {"cfg2": W.rc_ladder(64), "cfg4": W.rc_mesh(16), "cfg1": W.README_RC}[name]
         ck = parse_netlist(text)
@@ -136,6 +152,17 @@ def cpu_rate(wl, target_s=12.0, threads=None):
     """solves/s of oracle/oracle.c on a bounded sample of the workload (about target_s of CPU work)."""
     from oracle import c_oracle as co
     threads = threads or os.cpu_count() or 1
+    if wl["kind"] == "ac" and wl.get("overrides"):
+        freqs, n_inst = wl["freqs"], wl["n_inst"]
+        m = min(n_inst, 4 * threads)
+        t0 = time.perf_counter()
+        co.ac_solve(wl["ckt"], freqs, n_inst=m, overrides={k: v[:m] for k, v in wl["overrides"].items()}, nthreads=threads)
+        rate = m * len(freqs) / max(1e-9, time.perf_counter() - t0)
+        m2 = int(min(n_inst, max(m, rate * target_s / len(freqs))))
+        t0 = time.perf_counter()
+        co.ac_solve(wl["ckt"], freqs, n_inst=m2, overrides={k: v[:m2] for k, v in wl["overrides"].items()}, nthreads=threads)
+        dt = time.perf_counter() - t0
+        return m2 * len(freqs) / dt, threads, "first %d of %d instances x %d frequencies (%.1f s)" % (m2, n_inst, len(freqs), dt)
     if wl["kind"] == "ac":
         freqs = wl["freqs"]
         probe = freqs[:: max(1, len(freqs) // (64 * threads))][: 64 * threads]
@@ -222,6 +249,9 @@ def run_native(args):
     launches = 0
     if wl["kind"] == "ac":
         P = wl["units"]
+        F = int(wl["freqs"].shape[0])
+        sweep = wl.get("sweep")
+        d_var = torch.from_numpy(sweep.var_values).to(dev) if sweep is not None else None
         d_freqs = torch.from_numpy(wl["freqs"]).to(dev)
         # series-major results (x[Nvar][P], ielem[nAc][P]): the layout the drop-in simulateAC uses
         d_x = torch.empty((table.nvar, P), dtype=torch.complex128, device=dev)
@@ -230,10 +260,11 @@ def run_native(args):
         ac_flags = native.FLAG_SERIES_MAJOR
 
         def step_resident():
-            eng.ac_solve_device(table, d_freqs.data_ptr(), P, d_x.data_ptr(), d_i.data_ptr(), d_s.data_ptr(),
+            eng.ac_solve_device(table, d_freqs.data_ptr(), F, d_x.data_ptr(), d_i.data_ptr(), d_s.data_ptr(),
+                                sweep=sweep, d_var_values=None if d_var is None else d_var.data_ptr(),
                                 flags=ac_flags, stream=stream.cuda_stream)
 
-        h_freqs, p0 = native.pinned_empty(eng.lib, (P,), np.float64)
+        h_freqs, p0 = native.pinned_empty(eng.lib, (F,), np.float64)
         h_freqs[:] = wl["freqs"]
         h_x, p1 = native.pinned_empty(eng.lib, (table.nvar, P), np.complex128)
         h_i, p2 = native.pinned_empty(eng.lib, (table.n_ac_elem, P), np.complex128)
@@ -241,7 +272,7 @@ def run_native(args):
         pins = [p0, p1, p2, p3]
 
         def step_e2e():
-            eng.ac_solve(table, h_freqs, out=(h_x, h_i, h_s), flags=ac_flags)
+            eng.ac_solve(table, h_freqs, sweep=sweep, out=(h_x, h_i, h_s), flags=ac_flags)
             return int(h_s.max())
 
         def check():
@@ -389,7 +420,7 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
-    ap.add_argument("--workload", default="cfg2", choices=["cfg1", "cfg2", "cfg3", "cfg4", "cfg5"])
+    ap.add_argument("--workload", default="cfg2", choices=["cfg1", "cfg2", "cfg2mc", "cfg3", "cfg4", "cfg5"])
     ap.add_argument("--points", type=int, default=None, help="AC: subsample to this many frequency points")
     ap.add_argument("--instances", type=int, default=None, help="TRAN: number of instances")
     args = ap.parse_args()

@@ -23,7 +23,7 @@
 //    broadcast load through the read-only path); control flow is divergence-free except
 //    for the rare early exit of a failed / diverged point.
 #pragma once
-#include "common.cuh"
+#include "ac_kernels.cuh"
 #include "sparse_program.h"
 
 namespace spicey {
@@ -40,7 +40,10 @@ struct SparseArgs {
   int n_ind;
   int n_ac_elem, nn, v_first;
   const double* freqs;
+  long long n_freq;  // eager / sweep mode: global point p_begin + p = inst * n_freq + k; otherwise freqs is pre-offset
+  long long p_begin;
   long long p_count;
+  DevPlan plan;      // eager mode: element table, sweep values and the gather stamping lists
   double2* W;       // [n_slots][T]
   long long T;      // workspace stride = resident threads the workspace was sized for
   double2* x;       // [p_count][n], or [n][series_ld] when series_ld != 0
@@ -63,7 +66,10 @@ __constant__ int4 c_sparse_prog[kConstProgWords];
 // addresses, so an operand fetch is select-base + one load, without branches.  A structural zero is
 // the fast pool's zero slot.  HAS_PRISTINE: some operands are stamped entries recomputed in place
 // (only when the circuit has too many distinct entry values to materialise them as constants).
-template <bool CONST_PROG, bool HAS_PRISTINE, bool UNIFIED>
+// EAGER (sweeps / Monte-Carlo over component values): the stamped entries depend on the instance, so
+// they are summed per system from the element admittances — the reference's stamping order, as in
+// ac_cta_kernel — into a per-thread array that the pristine operands then read.
+template <bool CONST_PROG, bool HAS_PRISTINE, bool UNIFIED, bool EAGER>
 __global__ void __launch_bounds__(128) ac_sparse_kernel(SparseArgs a) {
   typedef Num<cplx> N;
   const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -78,11 +84,18 @@ __global__ void __launch_bounds__(128) ac_sparse_kernel(SparseArgs a) {
   const double2* __restrict__ c1p = a.ent_c1;
   const double thr = kEps * kEps;  // squared-magnitude metric
 
+  // eager mode arrays behind the program's slots: stamped entries E[n_stamp], element admittances Y[n_elem]
+  double2* E = W + (long long)a.n_slots * a.T;
+  double2* Yw = E + (long long)a.n_stamp * a.T;
+
   for (long long p = tid; p < a.p_count; p += nthreads) {
-    const double f = a.freqs[p];
+    const long long gp = EAGER ? a.p_begin + p : p;
+    const long long inst = EAGER ? gp / a.n_freq : 0;
+    const double f = a.freqs[EAGER ? gp - inst * a.n_freq : p];
     const double w = (2 * kPi) * f;
     const double iw = 1.0 / w;
     auto pristine = [&](int en) -> cplx {
+      if (EAGER) return E[(long long)en * a.T];
       const double2 c0 = __ldg(c0p + en), c1 = __ldg(c1p + en);
       return make_double2(c0.x, fma(w, c1.x, -c1.y * iw) + c0.y);
     };
@@ -98,10 +111,31 @@ __global__ void __launch_bounds__(128) ac_sparse_kernel(SparseArgs a) {
     F[(long long)a.n_const * fstride] = make_double2(0.0, 0.0);   // the zero slot
     bool diverged = false;
     int status = ST_OK;
-    // inductor guards of simulateAC.ts:47-51 / Complex.ts:41 are value dependent: leave them to the dense kernel
-    for (int l = 0; l < a.n_ind; ++l) {
-      double d = w * a.ind_L[l];
-      if (fabs(d) < kEps || d * d < kEps) diverged = true;
+    if (EAGER) {
+      // element admittances / source phasors of this instance (simulateAC.ts:36-57), then the gather stamp
+      const DevPlan& P = a.plan;
+      for (int e = 0; e < a.n_ac_elem; ++e) {
+        const int2 m = __ldg(P.meta + e);
+        cplx Y, J;
+        if (ac_element_values<false>(P, m.x, m.y, inst, f, Y, J) != ST_OK) diverged = true;  // exact status: dense kernel
+        Yw[(long long)e * a.T] = m.x == ELEM_V ? J : Y;
+      }
+      const GatherPlan& G = P.ac;
+      for (int en = 0; en < a.n_stamp; ++en) {
+        cplx acc = make_double2(0.0, 0.0);
+        for (int c = __ldg(G.ent_ptr + en); c < __ldg(G.ent_ptr + en + 1); ++c) {
+          const int cw = __ldg(G.contrib + c);
+          const cplx v = ((cw >> 1) & 3) == SRC_ONE ? make_double2(1.0, 0.0) : Yw[(long long)(cw >> 3) * a.T];
+          if (cw & 1) { acc.x -= v.x; acc.y -= v.y; } else { acc.x += v.x; acc.y += v.y; }
+        }
+        E[(long long)en * a.T] = acc;
+      }
+    } else {
+      // inductor guards of simulateAC.ts:47-51 / Complex.ts:41 are value dependent: leave them to the dense kernel
+      for (int l = 0; l < a.n_ind; ++l) {
+        double d = w * a.ind_L[l];
+        if (fabs(d) < kEps || d * d < kEps) diverged = true;
+      }
     }
     const long long sld = a.series_ld, xst = sld ? sld : 1;
     cplx* __restrict__ xout = sld ? a.x + p : a.x + p * a.n;
@@ -186,7 +220,8 @@ __global__ void __launch_bounds__(128) ac_sparse_kernel(SparseArgs a) {
         const uint2 q = __ldg(a.el_x + e);
         const cplx v1 = q.x == 0xffffffffu ? N::zero() : W[q.x];
         const cplx v2 = q.y == 0xffffffffu ? N::zero() : W[q.y];
-        const cplx y = make_double2(__ldg(a.el_a + e), fma(w, __ldg(a.el_b + e), -__ldg(a.el_g + e) * iw));
+        const cplx y = EAGER ? Yw[(long long)e * a.T]
+                             : make_double2(__ldg(a.el_a + e), fma(w, __ldg(a.el_b + e), -__ldg(a.el_g + e) * iw));
         io[e * xst] = N::mul(y, csub(v1, v2));
       }
       for (int e = a.v_first; e < a.n_ac_elem; ++e) io[e * xst] = W[__ldg(a.x_off + a.nn + e - a.v_first)];

@@ -215,6 +215,7 @@ struct DeviceCtx {
   uint64_t sp_key = 0;
   long long sp_T = 0;
   bool sp_unified = false;
+  bool sp_eager = false;
   std::vector<int4> sp_code_scaled;  // program with slot operands scaled by the pool strides
   bool sp_valid = false;
   std::vector<cudaEvent_t> events;
@@ -316,8 +317,8 @@ uint64_t plan_key(const HostPlan& hp) {
 
 // Builds (or reuses) the sparse program of this topology on ctx.  pilot_f: a representative frequency.
 // Returns SPICEY_SUCCESS with ctx.sp_valid=false when the sparse path does not apply.
-int prepare_sparse(DeviceCtx& ctx, const HostPlan& hp, double pilot_f, cudaStream_t stream) {
-  const uint64_t key = plan_key(hp);
+int prepare_sparse(DeviceCtx& ctx, const HostPlan& hp, double pilot_f, bool eager, cudaStream_t stream) {
+  const uint64_t key = plan_key(hp) ^ (eager ? 0x9e3779b97f4a7c15ull : 0ull);
   if (ctx.sp_key == key) return SPICEY_SUCCESS;  // cached (valid or known not to apply)
   ctx.sp_key = key;
   ctx.sp_valid = false;
@@ -376,16 +377,18 @@ int prepare_sparse(DeviceCtx& ctx, const HostPlan& hp, double pilot_f, cudaStrea
     }
   }
   const int kFastSlots = 12;  // 12 x 16 B x 128 threads = 24 KiB per CTA, 8 CTAs per SM
-  build_sparse_program(pin, sp, kFastSlots, &entry_class, n_class);
+  // sweep mode: entry values differ per instance, so no constants are materialised (n_class = 0)
+  build_sparse_program(pin, sp, kFastSlots, &entry_class, eager ? 0 : n_class);
+  ctx.sp_eager = eager;
   if (!sp.ok) return SPICEY_SUCCESS;
   // Workspace stride: the resident grid the workspace is sized for (offsets are baked into the program).
   {
     const int block = 128;
-    const size_t per_thread = sizeof(double2) * (size_t)std::max(1, sp.n_slots + sp.n_fast);
+    const size_t per_thread = sizeof(double2) * (size_t)std::max(1, sp.n_slots + sp.n_fast + (eager ? sp.n_stamp + hp.n_ac_elem : 0));
     long long T = (long long)ctx.sm_count * 10 * block;
     const long long t_cap = std::max<long long>(block, (long long)(((size_t)12 << 30) / per_thread) / block * block);
     T = std::min(T, t_cap);                       // workspace <= 12 GiB
-    while ((unsigned long long)(sp.n_slots + sp.n_fast) * (unsigned long long)T > 0x7ffffff0ull && T > block) T -= block;  // 31-bit offsets
+    while ((unsigned long long)(sp.n_slots + sp.n_fast + (eager ? sp.n_stamp + hp.n_ac_elem : 0)) * (unsigned long long)T > 0x7ffffff0ull && T > block) T -= block;  // 31-bit offsets
     ctx.sp_T = T;
   }
   const long long T = ctx.sp_T;
@@ -454,7 +457,7 @@ int launch_ac_sparse(DeviceCtx& ctx, const HostPlan& hp, const DevPlan& dp, cons
   const int block = 128;
   const long long T = ctx.sp_T;  // workspace stride (fixed when the program was uploaded)
   const long long nthreads = std::min<long long>((args.p_count + block - 1) / block * block, T);
-  size_t wbytes = sizeof(double2) * (size_t)std::max(1, ctx.sp.n_slots + ctx.sp.n_fast) * T;
+  size_t wbytes = sizeof(double2) * (size_t)std::max(1, ctx.sp.n_slots + ctx.sp.n_fast + (ctx.sp_eager ? ctx.sp.n_stamp + hp.n_ac_elem : 0)) * T;
   int rc = ctx.sp_work.ensure(wbytes);
   if (rc) return rc;
   if ((rc = ctx.sp_fb.ensure(sizeof(long long) * args.p_count + 64))) return rc;
@@ -462,8 +465,11 @@ int launch_ac_sparse(DeviceCtx& ctx, const HostPlan& hp, const DevPlan& dp, cons
   long long* fb_list = (long long*)((char*)ctx.sp_fb.p + 64);
   CUDA_TRY(cudaMemsetAsync(fb_count, 0, sizeof(int), stream));
   SparseArgs a = ctx.sp_args;
-  a.freqs = args.freqs + args.p_begin;
+  a.freqs = ctx.sp_eager ? args.freqs : args.freqs + args.p_begin;
+  a.n_freq = args.n_freq;
+  a.p_begin = args.p_begin;
   a.p_count = args.p_count;
+  a.plan = dp;
   a.W = (double2*)ctx.sp_work.p;
   a.T = T;
   a.x = args.x; a.ielem = args.ielem; a.status = args.status; a.series_ld = args.series_ld;
@@ -472,15 +478,16 @@ int launch_ac_sparse(DeviceCtx& ctx, const HostPlan& hp, const DevPlan& dp, cons
   const bool pristine_ops = ctx.sp.n_const == 0;
   const bool uni = ctx.sp_unified;
   const unsigned grid = (unsigned)(nthreads / block);
-#define SPARSE_LAUNCH(CP)                                                                              \
-  do {                                                                                                 \
-    if (uni) {                                                                                         \
-      if (pristine_ops) ac_sparse_kernel<CP, true, true><<<grid, block, 0, stream>>>(a);               \
-      else ac_sparse_kernel<CP, false, true><<<grid, block, 0, stream>>>(a);                           \
-    } else {                                                                                           \
-      if (pristine_ops) ac_sparse_kernel<CP, true, false><<<grid, block, fast_bytes, stream>>>(a);     \
-      else ac_sparse_kernel<CP, false, false><<<grid, block, fast_bytes, stream>>>(a);                 \
-    }                                                                                                  \
+#define SPARSE_LAUNCH(CP)                                                                                  \
+  do {                                                                                                     \
+    if (ctx.sp_eager) ac_sparse_kernel<CP, true, false, true><<<grid, block, fast_bytes, stream>>>(a);     \
+    else if (uni) {                                                                                        \
+      if (pristine_ops) ac_sparse_kernel<CP, true, true, false><<<grid, block, 0, stream>>>(a);            \
+      else ac_sparse_kernel<CP, false, true, false><<<grid, block, 0, stream>>>(a);                        \
+    } else {                                                                                               \
+      if (pristine_ops) ac_sparse_kernel<CP, true, false, false><<<grid, block, fast_bytes, stream>>>(a);  \
+      else ac_sparse_kernel<CP, false, false, false><<<grid, block, fast_bytes, stream>>>(a);              \
+    }                                                                                                      \
   } while (0)
   if ((int)ctx.sp.code.size() <= kConstProgWords) {
     // Constant-memory program: one resident program per device at a time.  The upload is ordered after
@@ -552,16 +559,17 @@ int launch_ac_dense(DeviceCtx& ctx, const HostPlan& hp, const DevPlan& dp, const
 int launch_ac(DeviceCtx& ctx, const HostPlan& hp, const DevPlan& dp, const AcArgs& args, uint32_t flags,
               cudaStream_t stream, int* tier_out, int64_t* launches, double pilot_f, bool pilot_known) {
   const bool want_sparse = !(flags & (SPICEY_FLAG_STRICT | SPICEY_FLAG_FORCE_GMEM | SPICEY_FLAG_DENSE)) &&
-                           dp.n_inst == 1 && dp.n_var == 0 &&
                            (args.p_count >= 2048 || (flags & SPICEY_FLAG_SPARSE));
   if (want_sparse) {
-    if (ctx.sp_key != plan_key(hp)) {
+    const bool eager = dp.n_inst > 1 || dp.n_var > 0;  // component sweep / Monte-Carlo: per-instance stamping
+    const uint64_t key = plan_key(hp) ^ (eager ? 0x9e3779b97f4a7c15ull : 0ull);
+    if (ctx.sp_key != key) {
       if (!pilot_known) {  // device-resident frequencies: fetch one representative value
-        CUDA_TRY(cudaMemcpyAsync(&pilot_f, args.freqs + args.p_begin + args.p_count / 2, sizeof(double),
-                                 cudaMemcpyDeviceToHost, stream));
+        const long long mid = eager ? args.n_freq / 2 : args.p_begin + args.p_count / 2;
+        CUDA_TRY(cudaMemcpyAsync(&pilot_f, args.freqs + mid, sizeof(double), cudaMemcpyDeviceToHost, stream));
         CUDA_TRY(cudaStreamSynchronize(stream));
       }
-      int rc = prepare_sparse(ctx, hp, pilot_f, stream);
+      int rc = prepare_sparse(ctx, hp, pilot_f, eager, stream);
       if (rc) return rc;
     }
     if (ctx.sp_valid) return launch_ac_sparse(ctx, hp, dp, args, flags, stream, tier_out, launches);

@@ -175,6 +175,41 @@ def test_ac_sweep_instances(eng):
     assert rel_err(out["ielem"], ie) <= AC_TOL
 
 
+@pytest.mark.parametrize("flags", [native.FLAG_SPARSE, native.FLAG_SPARSE | SM, 0])
+def test_ac_monte_carlo_ladder_sparse_eager(eng, flags):
+    """Component-tolerance Monte-Carlo on the AC axis (64-node ladder, 40 instances x 53 frequencies, every
+    R and C swept): the sparse program with per-instance (eager) stamping; flags=0 checks the automatic
+    tier choice (2120 points >= 2048 -> sparse)."""
+    text = w.rc_ladder(64)
+    n = 40
+    u = w.splitmix_uniform_pm1(n, 126)
+    ov = {}
+    for k in range(1, 64):
+        ov["r%d" % k] = 1000.0 * (1 + 0.05 * u[:, k - 1])
+        ov["c%d" % k] = 1e-9 * (1 + 0.05 * u[:, 62 + k])
+    freqs = np.logspace(0, 5, 53)
+    out, x, ie, st, _ = ac_case(eng, text, freqs, flags, n_inst=n, overrides=ov)
+    assert eng.stats()["tier"] == native.TIER_SPARSE
+    assert out["status"].max() == 0 and st.max() == 0
+    assert rel_err(out["x"], x) <= AC_TOL
+    assert rel_err(out["ielem"], ie) <= AC_TOL
+
+
+def test_ac_sweep_sparse_bad_instances_fall_back(eng):
+    """Sweep with one R<=0 instance and random RLC values: failures and pivot changes go through the dense
+    fallback with exact statuses."""
+    n = 16
+    rng = np.random.default_rng(11)
+    r = rng.uniform(10, 100, n)
+    r[5] = 0.0
+    ov = {"r1": r, "c1": rng.uniform(1e-5, 1e-3, n)}
+    out, x, ie, st, _ = ac_case(eng, w.README_RC, np.logspace(0, 3, 7), native.FLAG_SPARSE, n_inst=n, overrides=ov)
+    assert np.array_equal(out["status"], st) and (st[5] == native.ST_R_NONPOS).all()
+    ok = [i for i in range(n) if i != 5]
+    assert rel_err(out["x"][ok], x[ok]) <= AC_TOL and rel_err(out["ielem"][ok], ie[ok]) <= AC_TOL
+    assert eng.stats()["fallback_solves"] == 7
+
+
 def test_ac_error_statuses_do_not_poison_batch(eng):
     """R<=0 (simulateAC.ts:37), singular matrix (solveComplex.ts:29), Complex.div guard (Complex.ts:42)."""
     n = 8
