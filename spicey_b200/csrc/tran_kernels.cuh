@@ -48,21 +48,23 @@ template <bool STRICT> __device__ __forceinline__ double t_add(double a, double 
   return STRICT ? __dadd_rn(a, b) : a + b;
 }
 
-// Diode companion (simulateTRAN.ts:87-97): clamp, exp, gd floor, ieq.
+// Diode companion (simulateTRAN.ts:87-97): clamp, exp, gd floor, ieq.  is_over_vth = Is / vth is the
+// reference's own sub-expression, computed once per instance; the fast path multiplies by 1/vth.
 template <bool STRICT>
-__device__ __forceinline__ void diode_companion(double vd, double Is, double vth, double& gd, double& ieq) {
+__device__ __forceinline__ void diode_companion(double vd, double Is, double vth, double is_over_vth,
+                                                double inv_vth, double& gd, double& ieq) {
   double vlim = vd;
   if (vd > 0.8) vlim = 0.8;
   if (vd < -1.0) vlim = -1.0;
-  double e = exp(vlim / vth);
+  double e = exp(STRICT ? __ddiv_rn(vlim, vth) : vlim * inv_vth);
   double id = t_mul<STRICT>(Is, t_sub<STRICT>(e, 1.0));
-  gd = fmax(t_mul<STRICT>(Is / vth, e), 1e-12);
+  gd = fmax(t_mul<STRICT>(is_over_vth, e), 1e-12);
   ieq = t_sub<STRICT>(id, t_mul<STRICT>(gd, vlim));
 }
 
 // Per-element constants, 4 doubles per element (derived once per instance):
 //  R: G=1/R, R        C: Gc=C/dtc, C       L: Gl=dtc/L       V: dc
-//  S: Ron', Roff' (clamped), Von, Voff     D: Is, vth=N*VT, Is/vth
+//  S: Ron', Roff' (clamped), Von, Voff     D: Is, vth=N*VT, Is/vth, 1/vth
 __device__ __forceinline__ void element_constants(const DevPlan& P, int type, int vidx, long long inst,
                                                   double dtc, double* c4) {
   c4[0] = c4[1] = c4[2] = c4[3] = 0.0;
@@ -83,7 +85,7 @@ __device__ __forceinline__ void element_constants(const DevPlan& P, int type, in
     c4[3] = inst_value(P, vidx + 3, inst);
   } else {  // ELEM_D
     double Is = inst_value(P, vidx, inst), N = inst_value(P, vidx + 1, inst);
-    c4[0] = Is; c4[1] = N * kVt300; c4[2] = Is / c4[1];
+    c4[0] = Is; c4[1] = N * kVt300; c4[2] = Is / c4[1]; c4[3] = 1.0 / c4[1];
   }
 }
 
@@ -213,7 +215,7 @@ __global__ void tran_thread_kernel(DevPlan P, TranArgs a, int n_ent, int n_con) 
         int4 en = ends[e];
         double vd = it == 0 ? st[sidx[e] * NT] : VOLT(en.x) - VOLT(en.y);  // :85
         double gd, ieq;
-        diode_companion<STRICT>(vd, ec[(4 * e) * NT], ec[(4 * e + 1) * NT], gd, ieq);
+        diode_companion<STRICT>(vd, ec[(4 * e) * NT], ec[(4 * e + 1) * NT], ec[(4 * e + 2) * NT], ec[(4 * e + 3) * NT], gd, ieq);
         g[e * NT] = gd;
         jj[e * NT] = ieq;
       }
@@ -362,7 +364,7 @@ __global__ void tran_cta_kernel(DevPlan P, TranArgs a, double* scratch) {
             int4 en = ends[e];
             double vd = it == 0 ? st[sidx[e]] : VOLT(en.x) - VOLT(en.y);
             double gd, ieq;
-            diode_companion<STRICT>(vd, ec[4 * e], ec[4 * e + 1], gd, ieq);
+            diode_companion<STRICT>(vd, ec[4 * e], ec[4 * e + 1], ec[4 * e + 2], ec[4 * e + 3], gd, ieq);
             g[e] = gd;
             jj[e] = ieq;
           }

@@ -198,6 +198,8 @@ __global__ void __launch_bounds__(NT) tran_small_kernel(DevPlan P, TranArgs a) {
     SM_D(Ac, j * N1 * SB + r.x1) += 1.0;
     SM_D(Ac, j * N1 * SB + r.x2) -= 1.0;
   }
+  if (dyn)
+    for (int i = 0; i < N1 * N1; ++i) SM_D(As, i * SB) = SM_D(Ac, i * SB);
   SM_D(xs, NV * SB) = 0.0;  // ground
 #pragma unroll
   for (int i = 0; i < NV; ++i) SM_D(xs, i * SB) = 0.0;
@@ -260,7 +262,7 @@ __global__ void __launch_bounds__(NT) tran_small_kernel(DevPlan P, TranArgs a) {
           const SmallElem r = el[e];
           const double vd = it == 0 ? SM_D(st, r.st) : SM_D(xs, r.x1) - SM_D(xs, r.x2);   // :85
           double gd, ieq;
-          diode_companion<STRICT>(vd, SM_D(ec, r.ec), SM_D(ec, r.ec + SB), gd, ieq);
+          diode_companion<STRICT>(vd, SM_D(ec, r.ec), SM_D(ec, r.ec + SB), SM_D(ec, r.ec + 2 * SB), SM_D(ec, r.ec + 3 * SB), gd, ieq);
           STAMP_Y(As, r, gd);
           SM_D(bs, r.x1) -= ieq;
           SM_D(bs, r.x2) += ieq;
@@ -346,7 +348,8 @@ __global__ void __launch_bounds__(NT) tran_small_kernel(DevPlan P, TranArgs a) {
     for (int e = oD; e < oE; ++e, ie += NL) {
       const SmallElem r = el[e];
       const double d = SM_D(xs, r.x1) - SM_D(xs, r.x2);
-      if (io) *ie = t_mul<STRICT>(SM_D(ec, r.ec), t_sub<STRICT>(exp(d / SM_D(ec, r.ec + SB)), 1.0));  // unclamped (H6)
+      const double ex = exp(STRICT ? __ddiv_rn(d, SM_D(ec, r.ec + SB)) : d * SM_D(ec, r.ec + 3 * SB));
+      if (io) *ie = t_mul<STRICT>(SM_D(ec, r.ec), t_sub<STRICT>(ex, 1.0));  // unclamped vd (H6)
       SM_D(st, r.st) = d;
     }
     if (io) io += i_stride;

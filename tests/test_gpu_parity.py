@@ -364,3 +364,27 @@ def test_full_size_properties_cfg2(eng):
     sub = slice(0, None, 997)
     xr, ier, st = co.ac_solve(ck, freqs[sub], nthreads=8)
     assert rel_err(x[sub], xr) <= AC_TOL
+
+
+def test_multi_device_handle_shards_contiguous_ranges(eng):
+    """spicey_create with two devices: the library shards the batch axis in contiguous ranges (no collective)
+    and the result equals the single-device one.  Skipped on a one-GPU box."""
+    if eng.lib.spicey_device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    import spicey_b200 as sp
+    e2 = native.Engine([0, 1])
+    try:
+        ck = parse_netlist(w.rc_ladder(64))
+        freqs = np.array(sp.analysis.ac_frequencies(ck))[::97]
+        a = sp.simulate_ac_batch(ck, freqs, engine=e2, flags=SM)
+        b = sp.simulate_ac_batch(ck, freqs, engine=eng, flags=SM)
+        assert e2.stats()["n_devices"] == 2
+        assert np.array_equal(a["x"], b["x"]) and np.array_equal(a["ielem"], b["ielem"]) and a["status"].max() == 0
+        n = 4096
+        ov = {k: v[:n] for k, v in w.rlc_tank_overrides(65536).items()}
+        ck = parse_netlist(w.RLC_TANK)
+        ta = sp.simulate_tran_batch(ck, n_inst=n, overrides=ov, engine=e2)
+        tb = sp.simulate_tran_batch(ck, n_inst=n, overrides=ov, engine=eng)
+        assert np.array_equal(ta["v"], tb["v"]) and np.array_equal(ta["ielem"], tb["ielem"])
+    finally:
+        e2.close()
