@@ -257,7 +257,7 @@ def run_native(args):
         d_x = torch.empty((table.nvar, P), dtype=torch.complex128, device=dev)
         d_i = torch.empty((table.n_ac_elem, P), dtype=torch.complex128, device=dev)
         d_s = torch.empty(P, dtype=torch.int32, device=dev)
-        ac_flags = native.FLAG_SERIES_MAJOR
+        ac_flags = native.FLAG_SERIES_MAJOR | (native.FLAG_DENSE if args.dense else 0)
 
         def step_resident():
             eng.ac_solve_device(table, d_freqs.data_ptr(), F, d_x.data_ptr(), d_i.data_ptr(), d_s.data_ptr(),
@@ -421,6 +421,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
     ap.add_argument("--workload", default="cfg2", choices=["cfg1", "cfg2", "cfg2mc", "cfg3", "cfg4", "cfg5"])
+    ap.add_argument("--dense", action="store_true", help="AC: force the dense pivoted-LU kernel (no sparse program)")
     ap.add_argument("--points", type=int, default=None, help="AC: subsample to this many frequency points")
     ap.add_argument("--instances", type=int, default=None, help="TRAN: number of instances")
     args = ap.parse_args()

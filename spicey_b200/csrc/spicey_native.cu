@@ -813,7 +813,10 @@ int32_t spicey_ac_solve(spicey_handle* h, const spicey_elem_table* table, const 
   const size_t xrow = sizeof(double2) * hp.nvar, irow = sizeof(double2) * hp.n_ac_elem;
   const bool series = (flags & SPICEY_FLAG_SERIES_MAJOR) != 0;
   // Chunk size: ~96 MiB of results per chunk so that copies overlap the next chunk's kernel.
-  long long chunk = std::max<long long>(1024, (long long)((96ull << 20) / (xrow + (ielem ? irow : 0) + 4)));
+  // ... but never fewer points than fill the GPU (one thread per point in the sparse tier), within 4 GiB per buffer.
+  const size_t prow = xrow + (ielem ? irow : 0) + 4;
+  long long chunk = std::max<long long>(1024, (long long)((96ull << 20) / prow));
+  chunk = std::max<long long>(chunk, std::min<long long>((long long)h->devs[0].sm_count * 1024, (long long)((4ull << 30) / prow)));
   int64_t launches = 0, h2d = 0, d2h = 0;
   int tier = 0;
   struct Shard { long long lo, hi; size_t ev0; int nchunks; };

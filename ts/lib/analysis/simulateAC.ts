@@ -13,14 +13,15 @@ function buildFrequencyArray(mode: "dec" | "lin", N: number, f1: number, f2: num
   return Array.from({ length: npts }, (_, i) => f1 + i * step)
 }
 
-/** Complex[] view over an interleaved Float64Array slab (SURVEY.md §8 f1). */
-function complexSeries(slab: Float64Array, offset: number, stride: number, count: number): Complex[] {
+/** Complex[] view over one contiguous series of a series-major slab (SURVEY.md §8 f1):
+ *  row `row` of a [rows][count] complex array, materialising Complex objects only on access. */
+function complexSeries(slab: Float64Array, row: number, count: number): Complex[] {
+  const view = slab.subarray(2 * row * count, 2 * (row + 1) * count)
   return new Proxy([] as Complex[], {
     get(_t, key) {
       if (key === "length") return count
       const k = typeof key === "string" ? Number(key) : NaN
-      if (Number.isInteger(k) && k >= 0 && k < count)
-        return new Complex(slab[2 * (offset + k * stride)], slab[2 * (offset + k * stride) + 1])
+      if (Number.isInteger(k) && k >= 0 && k < count) return new Complex(view[2 * k], view[2 * k + 1])
       return (Array.prototype as any)[key]
     },
   })
@@ -31,7 +32,7 @@ function simulateAC(ckt: ParsedCircuit) {
   const { mode, N, f1, f2 } = ckt.analyses.ac
   const freqs = buildFrequencyArray(mode, N, f1, f2)
   const table = packCircuit(ckt)
-  const { x, ielem, status, nvar } = acSolve(table, Float64Array.from(freqs))
+  const { x, ielem, status } = acSolve(table, Float64Array.from(freqs))
   for (let k = 0; k < status.length; k++) {
     const st = status[k]
     if (st === STATUS.OK) continue
@@ -43,11 +44,11 @@ function simulateAC(ckt: ParsedCircuit) {
   }
   const nodeVoltages: Record<string, Complex[]> = {}
   ckt.nodes.rev.forEach((name, id) => {
-    if (id !== 0) nodeVoltages[name] = complexSeries(x, id - 1, nvar, freqs.length)
+    if (id !== 0) nodeVoltages[name] = complexSeries(x, id - 1, freqs.length)
   })
   const elementCurrents: Record<string, Complex[]> = {}
   table.names.slice(0, table.nAcElem).forEach((name, e) => {
-    elementCurrents[name] ||= complexSeries(ielem, e, table.nAcElem, freqs.length)
+    elementCurrents[name] ||= complexSeries(ielem, e, freqs.length)
   })
   return { freqs, nodeVoltages, elementCurrents }
 }

@@ -26,6 +26,8 @@ const { symbols: C } = dlopen(LIB_PATH, {
 })
 
 export const ELEM = { R: 0, C: 1, L: 2, V: 3, S: 4, D: 5 } as const
+/** SPICEY_FLAG_SERIES_MAJOR: x is [Nvar][P], ielem [nAc][P] — one contiguous slab per series. */
+export const FLAG_SERIES_MAJOR = 64
 export const STATUS = { OK: 0, SINGULAR: 1, CDIV: 2, R_NONPOS: 3 } as const
 
 /** Flat element table: typed arrays in the layout of `spicey_elem_table`. */
@@ -84,10 +86,10 @@ export function acSolve(t: ElemTable, freqs: Float64Array) {
   check(
     C.spicey_ac_solve(
       getHandle(), ptr(ts), null, ptr(freqs), BigInt(P), ptr(x),
-      t.nAcElem ? ptr(ielem) : null, ptr(status), 0,
+      t.nAcElem ? ptr(ielem) : null, ptr(status), FLAG_SERIES_MAJOR,
     ),
   )
-  return { x, ielem, status, nvar }
+  return { x, ielem, status, nvar, nPoints: P }
 }
 
 export function tranSolve(
