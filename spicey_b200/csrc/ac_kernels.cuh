@@ -41,8 +41,12 @@ struct AcSmem {
     red_off = o; o += sizeof(PivotPartial) * 2 * nwarps;
     ends_off = o; o += sizeof(int4) * n_elem;
     meta_off = o; o += sizeof(int2) * n_elem;
-    mask_off = o; o += sizeof(unsigned) * (size_t)nvar * MW;
+    mask_off = o; o += gmem ? 0 : sizeof(unsigned) * (size_t)nvar * MW;  // global tier: masks follow the matrix in the scratch
     total = (o + 15) & ~(size_t)15;
+  }
+  // bytes of global scratch per CTA in the global tier: matrix + row masks
+  static __host__ __device__ size_t scratch_bytes(int nvar, int MW) {
+    return ((sizeof(double2) * (size_t)nvar * (nvar + 1) + sizeof(unsigned) * (size_t)nvar * MW) + 15) & ~(size_t)15;
   }
 };
 
@@ -84,11 +88,12 @@ __global__ void ac_cta_kernel(DevPlan P, AcArgs a) {
   const int nvar = P.nvar, ne = P.n_elem, MW = P.MW;
   const int nwarps = (blockDim.x + 31) >> 5;
   const AcSmem L(nvar, ne, P.nV, MW, nwarps, GMEM);
-  cplx* A = GMEM ? (a.scratch + (size_t)blockIdx.x * nvar * (nvar + 1)) : (cplx*)(smem + L.a_off);
+  unsigned char* gscr = GMEM ? (unsigned char*)a.scratch + (size_t)blockIdx.x * AcSmem::scratch_bytes(nvar, MW) : nullptr;
+  cplx* A = GMEM ? (cplx*)gscr : (cplx*)(smem + L.a_off);
   cplx* Yv = (cplx*)(smem + L.y_off);
   cplx* Jv = (cplx*)(smem + L.j_off);
   cplx* xs = (cplx*)(smem + L.xs_off);
-  unsigned* mask = (unsigned*)(smem + L.mask_off);
+  unsigned* mask = GMEM ? (unsigned*)(gscr + sizeof(double2) * (size_t)nvar * (nvar + 1)) : (unsigned*)(smem + L.mask_off);
   PivotPartial* red = (PivotPartial*)(smem + L.red_off);
   int4* ends = (int4*)(smem + L.ends_off);
   int2* meta = (int2*)(smem + L.meta_off);

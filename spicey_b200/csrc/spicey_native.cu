@@ -542,7 +542,7 @@ int launch_ac_dense(DeviceCtx& ctx, const HostPlan& hp, const DevPlan& dp, const
   long long grid = std::min<long long>(args.p_count, (long long)occ * ctx.sm_count);
   AcArgs a = args;
   if (gmem) {
-    size_t per = sizeof(double2) * (size_t)hp.nvar * (hp.nvar + 1);
+    size_t per = AcSmem::scratch_bytes(hp.nvar, hp.MW);
     int rc = ctx.scratch.ensure(per * grid);
     if (rc) return rc;
     a.scratch = (double2*)ctx.scratch.p;
@@ -637,7 +637,7 @@ int launch_tran(DeviceCtx& ctx, const HostPlan& hp, const DevPlan& dp, const Tra
   long long grid = std::min<long long>(args.n_local, (long long)occ * ctx.sm_count);
   double* scratch = nullptr;
   if (gmem) {
-    int rc = ctx.scratch.ensure(sizeof(double) * (size_t)hp.nvar * (hp.nvar + 1) * grid);
+    int rc = ctx.scratch.ensure(TranCtaSmem::scratch_bytes(hp.nvar, hp.MW) * grid);
     if (rc) return rc;
     scratch = (double*)ctx.scratch.p;
   }

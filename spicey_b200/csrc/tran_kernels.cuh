@@ -303,8 +303,11 @@ struct TranCtaSmem {
     ends_off = o; o += sizeof(int4) * n_elem;
     meta_off = o; o += sizeof(int2) * n_elem;
     sidx_off = o; o += sizeof(int) * n_elem;
-    mask_off = o; o += sizeof(unsigned) * (size_t)nvar * MW;
+    mask_off = o; o += gmem ? 0 : sizeof(unsigned) * (size_t)nvar * MW;
     total = (o + 15) & ~(size_t)15;
+  }
+  static __host__ __device__ size_t scratch_bytes(int nvar, int MW) {
+    return ((sizeof(double) * (size_t)nvar * (nvar + 1) + sizeof(unsigned) * (size_t)nvar * MW) + 15) & ~(size_t)15;
   }
 };
 
@@ -315,7 +318,8 @@ __global__ void tran_cta_kernel(DevPlan P, TranArgs a, double* scratch) {
   const int nvar = P.nvar, nn = P.nn, ne = P.n_elem, ns = P.n_state, MW = P.MW;
   const int nwarps = (NT + 31) >> 5;
   const TranCtaSmem L(nvar, ne, ns, MW, nwarps, GMEM);
-  double* A = GMEM ? scratch + (size_t)blockIdx.x * nvar * (nvar + 1) : (double*)(smem + L.a_off);
+  unsigned char* gscr = GMEM ? (unsigned char*)scratch + (size_t)blockIdx.x * TranCtaSmem::scratch_bytes(nvar, MW) : nullptr;
+  double* A = GMEM ? (double*)gscr : (double*)(smem + L.a_off);
   double* xs = (double*)(smem + L.xs_off);
   double* st = (double*)(smem + L.st_off);
   double* ec = (double*)(smem + L.ec_off);
@@ -325,7 +329,7 @@ __global__ void tran_cta_kernel(DevPlan P, TranArgs a, double* scratch) {
   int4* ends = (int4*)(smem + L.ends_off);
   int2* meta = (int2*)(smem + L.meta_off);
   int* sidx = (int*)(smem + L.sidx_off);
-  unsigned* mask = (unsigned*)(smem + L.mask_off);
+  unsigned* mask = GMEM ? (unsigned*)(gscr + sizeof(double) * (size_t)nvar * (nvar + 1)) : (unsigned*)(smem + L.mask_off);
   const GatherPlan& G = P.tran;
   const int ldr = nvar;
   const long long S1 = a.steps + 1, NL = a.n_local;

@@ -388,3 +388,78 @@ def test_multi_device_handle_shards_contiguous_ranges(eng):
         assert np.array_equal(ta["v"], tb["v"]) and np.array_equal(ta["ielem"], tb["ielem"])
     finally:
         e2.close()
+
+
+def test_tran_second_call_continues_from_mutated_state(eng, golden):
+    """The reference mutates ckt (vPrev/iPrev/vdPrev/isOn, simulateTRAN.ts:221-237): a second simulateTRAN on the
+    same ParsedCircuit continues from the end state instead of restarting.  Same here."""
+    import spicey_b200 as sp
+    text = golden("boost_converter_probe")["netlist"]
+    ref = o.simulate(text)
+    ref2 = o.simulate_tran(ref["circuit"])
+    ck = parse_netlist(text)
+    sp.simulateTRAN(ck)
+    got2 = sp.simulateTRAN(ck)
+    for k, b in ref2["nodeVoltages"].items():
+        a, b = np.asarray(got2["nodeVoltages"][k]), np.asarray(b)
+        assert np.max(np.abs(a - b)) <= TRAN_TOL * max(1e-30, np.max(np.abs(b)))
+
+
+def test_edge_cases_and_argument_errors(eng):
+    """Degenerate and maximum sizes, optional outputs, call-level errors (no crash, clear message)."""
+    import spicey_b200 as sp
+    from spicey_b200.packing import pack_circuit
+    # smallest system: one node, one source (Nvar = 2), single frequency, no element currents requested
+    ck = parse_netlist("* one\nv1 a 0 ac 2 45\nr1 a 0 10\n.ac lin 1 5 5\n")
+    out = sp.simulate_ac_batch(ck, [5.0], want_currents=False, engine=eng)
+    assert out["ielem"] is None and out["status"][0, 0] == 0
+    assert abs(out["x"][0, 0, 0] - 2 * np.exp(1j * np.pi / 4)) < 1e-15
+    # a netlist without analyses: simulate() returns None for both, like the reference (:63, :131)
+    res = sp.simulate("* none\nv1 a 0 dc 1\nr1 a 0 1\n")
+    assert res["ac"] is None and res["tran"] is None
+    # empty frequency list / zero steps are argument errors, not crashes
+    table = pack_circuit(ck)
+    with pytest.raises(native.NativeError) as ei:
+        eng.ac_solve(table, np.zeros(0))
+    assert ei.value.code == native.ERR_INVALID
+    with pytest.raises(native.NativeError):
+        eng.tran_solve(table, 1e-6, 0)
+    # elements out of R,C,L,V,S,D order are rejected
+    bad = native.ElemTable(1, [native.ELEM_V, native.ELEM_R], [1, 1], [0, 0], [0, 0], [0, 0], [0, 3], [0, 1, 0, 10.0])
+    with pytest.raises(native.NativeError, match="grouped"):
+        eng.ac_solve(bad, [1.0])
+    # node id out of range
+    bad = native.ElemTable(1, [native.ELEM_R], [2], [0], [0], [0], [0], [10.0])
+    with pytest.raises(native.NativeError, match="node id"):
+        eng.ac_solve(bad, [1.0])
+    # largest supported system: Nvar = 1024 runs (global-scratch tier), 1025 is refused with UNSUPPORTED
+    for n_nodes, ok in ((1023, True), (1024, False)):
+        lines = ["* big", "v1 n1 0 ac 1"] + ["r%d n%d n%d 1k" % (k, k, k + 1) for k in range(1, n_nodes)] + \
+                ["c%d n%d 0 1n" % (k, k + 1) for k in range(1, n_nodes)]
+        ckb = parse_netlist("\n".join(lines) + "\n.ac lin 2 10 20\n")
+        if ok:
+            outb = sp.simulate_ac_batch(ckb, [10.0, 20.0], engine=eng, flags=native.FLAG_DENSE)
+            xr, ier, st = co.ac_solve(ckb, [10.0, 20.0])
+            assert eng.stats()["tier"] == native.TIER_CTA_GMEM and outb["status"].max() == 0
+            assert rel_err(outb["x"][0], xr) <= AC_TOL
+        else:
+            with pytest.raises(native.NativeError) as ei:
+                sp.simulate_ac_batch(ckb, [10.0], engine=eng)
+            assert ei.value.code == native.ERR_UNSUPPORTED
+
+
+def test_tran_mid_sized_circuit_cta_tiers(eng):
+    """A 40-node RC ladder transient (Nvar = 41 > the thread tiers): CTA tier with the matrix in shared memory
+    and in the global scratch, against the oracle."""
+    import spicey_b200 as sp
+    lines = ["* ladder tran", "V1 n1 0 PULSE(0 1 0 1u 1u 20u 50u)"] + \
+            ["r%d n%d n%d 1k" % (k, k, k + 1) for k in range(1, 40)] + ["c%d n%d 0 1n" % (k, k + 1) for k in range(1, 40)]
+    text = "\n".join(lines) + "\n.tran 1u 60u\n"
+    ref = o.simulate(text)["tran"]
+    for flags, tier in ((0, native.TIER_CTA_SMEM), (native.FLAG_FORCE_GMEM, native.TIER_CTA_GMEM)):
+        got = sp.simulateTRAN(parse_netlist(text), flags=flags)
+        assert eng.stats()["tier"] == tier
+        for kind in ("nodeVoltages", "elementCurrents"):
+            for k, b in ref[kind].items():
+                a, b = np.asarray(got[kind][k]), np.asarray(b)
+                assert np.max(np.abs(a - b)) <= TRAN_TOL * max(1e-30, float(np.max(np.abs(b)))), (kind, k)
