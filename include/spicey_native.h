@@ -123,8 +123,10 @@ enum {
   SPICEY_TIER_THREAD = 1,    /* one thread per system (Nvar <= 16) */
   SPICEY_TIER_CTA_SMEM = 2,  /* one CTA per system, matrix resident in shared memory */
   SPICEY_TIER_CTA_GMEM = 3,  /* one CTA per system, matrix in an L2-resident global scratch */
-  SPICEY_TIER_SPARSE = 4     /* one thread per system, static-pivot sparse LU program verified per
-                                system, dense pivoting kernel as fallback (single-instance sweeps) */
+  SPICEY_TIER_SPARSE = 4,    /* one thread per system, static-pivot sparse LU program verified per
+                                system (interpreted), dense pivoting kernel as fallback */
+  SPICEY_TIER_SPARSE_JIT = 5 /* the same program written out as a straight-line sm_100a kernel and compiled
+                                with NVRTC once per topology (large single-instance sweeps, small programs) */
 };
 
 typedef struct spicey_handle spicey_handle;
@@ -202,8 +204,10 @@ enum {
   SPICEY_FLAG_DENSE = 8u,       /* never use the sparse program path */
   SPICEY_FLAG_SPARSE = 16u,     /* use the sparse program path even for small batches */
   SPICEY_FLAG_GENERIC_THREAD = 32u, /* testing: transient thread tier without the register-resident kernel */
-  SPICEY_FLAG_SERIES_MAJOR = 64u   /* AC: x is [Nvar][P] and ielem [nAc][P] (one contiguous series per node /
+  SPICEY_FLAG_SERIES_MAJOR = 64u,  /* AC: x is [Nvar][P] and ielem [nAc][P] (one contiguous series per node /
                                       element, coalesced stores on the device) instead of [P][Nvar] / [P][nAc] */
+  SPICEY_FLAG_JIT = 128u,          /* compile the straight-line sparse kernel even for batches below 200,000 points */
+  SPICEY_FLAG_NO_JIT = 256u        /* never compile: always interpret the sparse program */
 };
 
 /* Measures this GPU's FP64 FMA peak with a register-only DFMA loop (GFLOP/s), the

@@ -10,12 +10,12 @@ CSRC = os.path.join(HERE, "csrc")
 LIB_DIR = os.path.join(HERE, "lib")
 LIB_PATH = os.path.join(LIB_DIR, "libspicey_native.so")
 SOURCES = ["spicey_native.cu"]
-HEADERS = ["common.cuh", "lu_rowthread.cuh", "ac_kernels.cuh", "ac_sparse.cuh", "sparse_program.h", "tran_kernels.cuh", "tran_small.cuh",
+HEADERS = ["common.cuh", "lu_rowthread.cuh", "ac_kernels.cuh", "ac_sparse.cuh", "sparse_program.h", "sparse_codegen.h", "tran_kernels.cuh", "tran_small.cuh",
            os.path.join("..", "..", "include", "spicey_native.h")]
 
 NVCC_FLAGS = [
     "-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
-    "-Xcompiler", "-fPIC", "-shared",
+    "-Xcompiler", "-fPIC", "-shared", "-ldl",
 ]
 
 

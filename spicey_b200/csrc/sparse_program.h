@@ -59,6 +59,21 @@ enum MicroOp {
 struct MicroWord { int hdr, a, b, c; };
 constexpr int kNoOperand = INT_MIN;  // "structurally zero" operand
 
+namespace sparse_detail {
+
+// Operand of the intermediate program: >= 0 virtual slot, < 0 pristine entry ~idx, kNoOperand none.
+struct Update { int dst_old, dst_new, src; };
+struct IrOp {
+  int kind = 0;
+  std::vector<int> reads;       // PIVOT: candidates; ELIM: {a_ik}; BSUB: {b, rcp, a_0, x_0, a_1, x_1, ...}
+  int pidx = 0;                 // PIVOT
+  int def = -1;                 // PIVOT: 1/pivot; BSUB: x_i
+  int var = 0;                  // BSUB: i
+  std::vector<Update> upd;      // ELIM
+};
+
+}  // namespace sparse_detail
+
 struct SparseProgram {
   bool ok = false;
   int n = 0;
@@ -70,6 +85,8 @@ struct SparseProgram {
   int n_virtual = 0; // single-assignment values before allocation (statistics)
   long long n_fma = 0, n_div = 0;  // executed complex FMAs / reciprocals per system
   std::vector<MicroWord> code;  // micro-ops, terminated by MOP_END (+ one pad word for the prefetch)
+  std::vector<sparse_detail::IrOp> ir;  // single-assignment intermediate program (input of the code generator)
+  std::vector<int> x_virtual;           // [n] virtual slot of x_i
   std::vector<int> x_slot;      // [n] global slot of x_i at the end of the program
   // per stamped entry: value = (alpha + j*aim0) + j*(omega*beta - gamma/omega)
   std::vector<double> ent_alpha, ent_beta, ent_gamma, ent_jre, ent_jim;
@@ -85,20 +102,6 @@ struct PilotInput {
   std::vector<std::complex<double>> ent_val;   // numeric pilot matrix entries, plan order
 };
 
-namespace sparse_detail {
-
-// Operand of the intermediate program: >= 0 virtual slot, < 0 pristine entry ~idx, kNoOperand none.
-struct Update { int dst_old, dst_new, src; };
-struct IrOp {
-  int kind = 0;
-  std::vector<int> reads;       // PIVOT: candidates; ELIM: {a_ik}; BSUB: {b, rcp, a_0, x_0, a_1, x_1, ...}
-  int pidx = 0;                 // PIVOT
-  int def = -1;                 // PIVOT: 1/pivot; BSUB: x_i
-  int var = 0;                  // BSUB: i
-  std::vector<Update> upd;      // ELIM
-};
-
-}  // namespace sparse_detail
 
 // Builds the program from the pilot point.  Returns ok=false when the pilot itself is
 // singular / hits the divide guard (the dense kernel then reports the exact status).
@@ -202,6 +205,8 @@ inline void build_sparse_program(const PilotInput& in, SparseProgram& sp, int fa
     ir.push_back(bs);
   }
   sp.n_virtual = nv;
+  sp.ir = ir;
+  sp.x_virtual = x_virtual;
 
   // ---- liveness: last reader of every virtual slot (micro-op granularity) ----
   // Micro-op index: PIVOT = 1, ELIM = 1 (header) + one per update, BSUB = 1.

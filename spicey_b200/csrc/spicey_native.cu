@@ -8,6 +8,8 @@
 // entry point fails with SPICEY_ERR_NO_DEVICE.
 #include "../../include/spicey_native.h"
 
+#include <dlfcn.h>
+
 #include <algorithm>
 #include <chrono>
 #include <cstdio>
@@ -19,6 +21,7 @@
 
 #include "ac_kernels.cuh"
 #include "ac_sparse.cuh"
+#include "sparse_codegen.h"
 #include "tran_kernels.cuh"
 #include "tran_small.cuh"
 
@@ -216,6 +219,14 @@ struct DeviceCtx {
   long long sp_T = 0;
   bool sp_unified = false;
   bool sp_eager = false;
+  // straight-line (NVRTC-compiled) variant of the program, when it was built
+  cudaLibrary_t sp_jit_lib = nullptr;
+  cudaKernel_t sp_jit_kernel = nullptr;
+  uint64_t sp_jit_key = 0;   // plan key the module was compiled for (0 = none / failed)
+  bool sp_jit_failed = false;
+  int sp_jit_minb = 2;   // 255 registers per thread: measured best (fewer spills beat occupancy: 1.90 ms vs 2.25 / 3.02 ms at 4 / 8)
+  double sp_jit_compile_ms = 0;
+  std::string sp_jit_note;
   std::vector<int4> sp_code_scaled;  // program with slot operands scaled by the pool strides
   bool sp_valid = false;
   std::vector<cudaEvent_t> events;
@@ -289,6 +300,8 @@ struct spicey_handle {
 namespace {
 
 
+double now_ms();
+
 struct ConstProgOwner {
   std::mutex mu;
   uint64_t key = 0;
@@ -298,6 +311,68 @@ struct ConstProgOwner {
 ConstProgOwner& const_owner(int dev) {
   static ConstProgOwner owners[64];
   return owners[dev & 63];
+}
+
+
+// ---------------------------------------------------------------------------------
+// NVRTC (loaded lazily with dlopen so that the library itself has no link-time dependency on it):
+// compiles the straight-line kernel of sparse_codegen.h for sm_100a.
+struct JitArgs {   // must match sparse_jit_prelude()
+  const double* freqs; long long p_count;
+  double2* x; double2* ielem; int* status; long long series_ld;
+  long long* fb_list; int* fb_count; int n; int n_ac_elem;
+};
+
+struct Nvrtc {
+  typedef int (*create_t)(void**, const char*, const char*, int, const char* const*, const char* const*);
+  typedef int (*compile_t)(void*, int, const char* const*);
+  typedef int (*size_t_fn)(void*, size_t*);
+  typedef int (*get_t)(void*, char*);
+  typedef int (*destroy_t)(void**);
+  void* lib = nullptr;
+  create_t create = nullptr; compile_t compile = nullptr; size_t_fn cubin_size = nullptr; get_t cubin = nullptr;
+  size_t_fn log_size = nullptr; get_t log = nullptr; destroy_t destroy = nullptr;
+  bool ok = false;
+  Nvrtc() {
+    const char* names[] = {"libnvrtc.so.12", "libnvrtc.so", "/usr/local/cuda/lib64/libnvrtc.so.12", "/usr/local/cuda/lib64/libnvrtc.so"};
+    for (const char* n : names) if ((lib = dlopen(n, RTLD_NOW | RTLD_LOCAL))) break;
+    if (!lib) return;
+    create = (create_t)dlsym(lib, "nvrtcCreateProgram");
+    compile = (compile_t)dlsym(lib, "nvrtcCompileProgram");
+    cubin_size = (size_t_fn)dlsym(lib, "nvrtcGetCUBINSize");
+    cubin = (get_t)dlsym(lib, "nvrtcGetCUBIN");
+    log_size = (size_t_fn)dlsym(lib, "nvrtcGetProgramLogSize");
+    log = (get_t)dlsym(lib, "nvrtcGetProgramLog");
+    destroy = (destroy_t)dlsym(lib, "nvrtcDestroyProgram");
+    ok = create && compile && cubin_size && cubin && log_size && log && destroy;
+  }
+};
+Nvrtc& nvrtc() { static Nvrtc n; return n; }
+
+// source -> cubin (sm_100a).  Returns false with `why` filled when NVRTC is missing or the compile fails.
+bool jit_compile(const std::string& src, int min_blocks, std::vector<char>& cubin, std::string& why) {
+  Nvrtc& N = nvrtc();
+  if (!N.ok) { why = "libnvrtc not available"; return false; }
+  void* prog = nullptr;
+  if (N.create(&prog, src.c_str(), "spicey_sparse_jit.cu", 0, nullptr, nullptr) != 0) { why = "nvrtcCreateProgram failed"; return false; }
+  std::string minb = "-DMINB=" + std::to_string(min_blocks);
+  const char* opts[] = {"--gpu-architecture=sm_100a", "-std=c++17", "-lineinfo", "-default-device", minb.c_str()};
+  int rc = N.compile(prog, 5, opts);
+  if (rc != 0) {
+    size_t n = 0;
+    N.log_size(prog, &n);
+    std::string lg(n, '\0');
+    if (n) N.log(prog, &lg[0]);
+    why = "nvrtcCompileProgram failed: " + lg.substr(0, 2000);
+    N.destroy(&prog);
+    return false;
+  }
+  size_t n = 0;
+  N.cubin_size(prog, &n);
+  cubin.resize(n);
+  N.cubin(prog, cubin.data());
+  N.destroy(&prog);
+  return n > 0;
 }
 
 uint64_t fnv1a(uint64_t h, const void* data, size_t n) {
@@ -452,6 +527,39 @@ int prepare_sparse(DeviceCtx& ctx, const HostPlan& hp, double pilot_f, bool eage
 int launch_ac_dense(DeviceCtx& ctx, const HostPlan& hp, const DevPlan& dp, const AcArgs& args, uint32_t flags,
                     cudaStream_t stream, int* tier_out, int64_t* launches);
 
+constexpr size_t kJitMaxOps = 6000;          // larger programs stay on the interpreter (compile time)
+constexpr long long kJitMinPoints = 200000;  // below this the ~4 s compile does not pay off (unless forced)
+
+// Compiles (once per topology and handle) the straight-line kernel of the cached sparse program.
+// Returns true when ctx.sp_jit_kernel is usable.
+bool ensure_jit(DeviceCtx& ctx, const HostPlan& hp) {
+  if (ctx.sp_jit_key == ctx.sp_key && ctx.sp_jit_kernel) return true;
+  if (ctx.sp_jit_key == ctx.sp_key && ctx.sp_jit_failed) return false;
+  ctx.sp_jit_key = ctx.sp_key;
+  ctx.sp_jit_failed = true;
+  if (ctx.sp_jit_lib) { cudaLibraryUnload(ctx.sp_jit_lib); ctx.sp_jit_lib = nullptr; ctx.sp_jit_kernel = nullptr; }
+  const double t0 = now_ms();
+  std::vector<int> n1(hp.n_ac_elem), n2(hp.n_ac_elem);
+  for (int e = 0; e < hp.n_ac_elem; ++e) { n1[e] = hp.ends[e].x; n2[e] = hp.ends[e].y; }
+  CodegenInput ci;
+  ci.sp = &ctx.sp; ci.nn = hp.nn; ci.n_ac_elem = hp.n_ac_elem; ci.v_first = hp.off[ELEM_V];
+  ci.n1 = n1.data(); ci.n2 = n2.data();
+  const std::string src = generate_sparse_kernel_source(ci);
+  std::vector<char> cubin;
+  if (const char* e = getenv("SPICEY_JIT_MINB")) ctx.sp_jit_minb = std::max(1, atoi(e));
+  if (!jit_compile(src, ctx.sp_jit_minb, cubin, ctx.sp_jit_note)) return false;
+  if (cudaLibraryLoadData(&ctx.sp_jit_lib, cubin.data(), nullptr, nullptr, 0, nullptr, nullptr, 0) != cudaSuccess ||
+      cudaLibraryGetKernel(&ctx.sp_jit_kernel, ctx.sp_jit_lib, "spicey_sparse_jit") != cudaSuccess) {
+    ctx.sp_jit_note = std::string("loading the compiled kernel failed: ") + cudaGetErrorString(cudaGetLastError());
+    ctx.sp_jit_kernel = nullptr;
+    return false;
+  }
+  ctx.sp_jit_failed = false;
+  ctx.sp_jit_compile_ms = now_ms() - t0;
+  ctx.sp_jit_note = "ok";
+  return true;
+}
+
 int launch_ac_sparse(DeviceCtx& ctx, const HostPlan& hp, const DevPlan& dp, const AcArgs& args, uint32_t flags,
                      cudaStream_t stream, int* tier_out, int64_t* launches) {
   const int block = 128;
@@ -464,6 +572,27 @@ int launch_ac_sparse(DeviceCtx& ctx, const HostPlan& hp, const DevPlan& dp, cons
   int* fb_count = (int*)ctx.sp_fb.p;
   long long* fb_list = (long long*)((char*)ctx.sp_fb.p + 64);
   CUDA_TRY(cudaMemsetAsync(fb_count, 0, sizeof(int), stream));
+  const bool want_jit = !ctx.sp_eager && !(flags & SPICEY_FLAG_NO_JIT) && ctx.sp.code.size() <= kJitMaxOps &&
+                        (args.p_count >= kJitMinPoints || (flags & SPICEY_FLAG_JIT));
+  if (want_jit && ensure_jit(ctx, hp)) {
+    JitArgs j;
+    j.freqs = args.freqs + args.p_begin; j.p_count = args.p_count;
+    j.x = args.x; j.ielem = args.ielem; j.status = args.status; j.series_ld = args.series_ld;
+    j.fb_list = fb_list; j.fb_count = fb_count; j.n = hp.nvar; j.n_ac_elem = hp.n_ac_elem;
+    const long long resident = (long long)ctx.sm_count * ctx.sp_jit_minb * block;
+    const unsigned jgrid = (unsigned)(std::min<long long>((args.p_count + block - 1) / block * block, resident) / block);
+    void* kargs[] = {&j};
+    CUDA_TRY(cudaLaunchKernel((const void*)ctx.sp_jit_kernel, dim3(jgrid), dim3(block), kargs, 0, stream));
+    if (launches) ++*launches;
+    AcArgs d = args;
+    d.plist = fb_list;
+    d.pcount = fb_count;
+    d.fb_total = (unsigned long long*)((char*)ctx.sp_fb.p + 32);
+    rc = launch_ac_dense(ctx, hp, dp, d, flags, stream, nullptr, launches);
+    if (rc) return rc;
+    if (tier_out) *tier_out = SPICEY_TIER_SPARSE_JIT;
+    return SPICEY_SUCCESS;
+  }
   SparseArgs a = ctx.sp_args;
   a.freqs = ctx.sp_eager ? args.freqs : args.freqs + args.p_begin;
   a.n_freq = args.n_freq;
@@ -723,6 +852,7 @@ void spicey_destroy(spicey_handle* h) {
     Buffer* bufs[] = {&c.plan, &c.scratch, &c.in0, &c.in1, &c.in2, &c.out_x[0], &c.out_x[1], &c.out_i[0],
                       &c.out_i[1], &c.out_s[0], &c.out_s[1], &c.aux0, &c.aux1, &c.sp_blob, &c.sp_work, &c.sp_fb};
     for (Buffer* b : bufs) b->release();
+    if (c.sp_jit_lib) cudaLibraryUnload(c.sp_jit_lib);
     for (auto e : c.events) cudaEventDestroy(e);
     cudaStreamDestroy(c.compute);
     cudaStreamDestroy(c.copy);
@@ -790,7 +920,7 @@ int32_t spicey_ac_solve_device(spicey_handle* h, int32_t dev_index, const spicey
   h->stats.kernel_launches = launches;
   h->stats.tier = tier;
   h->stats.fallback_solves = -1;  // resolved lazily by spicey_get_stats
-  h->stats.program_cfma = tier == SPICEY_TIER_SPARSE ? ctx.sp.n_fma : 0;
+  h->stats.program_cfma = (tier == SPICEY_TIER_SPARSE || tier == SPICEY_TIER_SPARSE_JIT) ? ctx.sp.n_fma : 0;
   h->stats.solves = a.p_count;
   h->stats.h2d_bytes = (int64_t)h->blob.size();
   h->stats.d2h_bytes = 0;
@@ -810,6 +940,8 @@ int32_t spicey_ac_solve(spicey_handle* h, const spicey_elem_table* table, const 
   const int n_var = sweep ? sweep->n_var : 0;
   const long long P = n_inst * n_freq;
   const int D = (int)h->devs.size();
+  // the compile-or-interpret decision looks at the whole call, not at one pipeline chunk
+  if (P >= kJitMinPoints && !(flags & SPICEY_FLAG_NO_JIT)) flags |= SPICEY_FLAG_JIT;
   const size_t xrow = sizeof(double2) * hp.nvar, irow = sizeof(double2) * hp.n_ac_elem;
   const bool series = (flags & SPICEY_FLAG_SERIES_MAJOR) != 0;
   // Chunk size: ~96 MiB of results per chunk so that copies overlap the next chunk's kernel.
@@ -912,7 +1044,7 @@ int32_t spicey_ac_solve(spicey_handle* h, const spicey_elem_table* table, const 
   h->stats.solves = P;
   h->stats.tier = tier;
   h->stats.fallback_solves = -1;
-  h->stats.program_cfma = tier == SPICEY_TIER_SPARSE ? h->devs[0].sp.n_fma : 0;
+  h->stats.program_cfma = (tier == SPICEY_TIER_SPARSE || tier == SPICEY_TIER_SPARSE_JIT) ? h->devs[0].sp.n_fma : 0;
   return SPICEY_SUCCESS;
 }
 

@@ -16,8 +16,8 @@ ELEM_R, ELEM_C, ELEM_L, ELEM_V, ELEM_S, ELEM_D = range(6)
 VALUE_SLOTS = {ELEM_R: 1, ELEM_C: 1, ELEM_L: 1, ELEM_V: 3, ELEM_S: 4, ELEM_D: 2}
 ST_OK, ST_SINGULAR, ST_CDIV, ST_R_NONPOS = 0, 1, 2, 3
 FLAG_STRICT, FLAG_FORCE_GMEM, FLAG_FORCE_CTA, FLAG_DENSE, FLAG_SPARSE, FLAG_GENERIC_THREAD = 1, 2, 4, 8, 16, 32
-FLAG_SERIES_MAJOR = 64
-TIER_THREAD, TIER_CTA_SMEM, TIER_CTA_GMEM, TIER_SPARSE = 1, 2, 3, 4
+FLAG_SERIES_MAJOR, FLAG_JIT, FLAG_NO_JIT = 64, 128, 256
+TIER_THREAD, TIER_CTA_SMEM, TIER_CTA_GMEM, TIER_SPARSE, TIER_SPARSE_JIT = 1, 2, 3, 4, 5
 SUCCESS, ERR_INVALID, ERR_NO_DEVICE, ERR_CUDA, ERR_UNSUPPORTED = 0, 1, 2, 3, 4
 
 EXPORTS = [

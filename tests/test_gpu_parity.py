@@ -80,6 +80,8 @@ SM = native.FLAG_SERIES_MAJOR
 @pytest.mark.parametrize("flags,tol", [(native.FLAG_DENSE, AC_TOL), (native.FLAG_STRICT, 1e-12),
                                        (native.FLAG_FORCE_GMEM, AC_TOL), (native.FLAG_SPARSE, AC_TOL),
                                        (native.FLAG_DENSE | SM, AC_TOL), (native.FLAG_SPARSE | SM, AC_TOL),
+                                       (native.FLAG_SPARSE | native.FLAG_JIT, AC_TOL),
+                                       (native.FLAG_SPARSE | native.FLAG_JIT | SM, AC_TOL),
                                        (native.FLAG_FORCE_GMEM | native.FLAG_STRICT | SM, 1e-12)])
 def test_ac_ladder64_slice(eng, flags, tol):
     """cfg 2 topology (Nvar = 65), every 997th of the 1,000,001 frequencies."""
@@ -91,7 +93,8 @@ def test_ac_ladder64_slice(eng, flags, tol):
     out, x, ie, st, _ = ac_case(eng, text, sub, flags)
     if flags & native.FLAG_SPARSE:
         stt = eng.stats()
-        assert stt["tier"] == native.TIER_SPARSE and stt["fallback_solves"] == 0 and stt["program_cfma"] > 0
+        want = native.TIER_SPARSE_JIT if flags & native.FLAG_JIT else native.TIER_SPARSE
+        assert stt["tier"] == want and stt["fallback_solves"] == 0 and stt["program_cfma"] > 0
     assert out["status"].max() == 0 and st.max() == 0
     assert rel_err(out["x"], x) <= tol, rel_err(out["x"], x)
     assert rel_err(out["ielem"], ie) <= tol
@@ -144,7 +147,7 @@ def test_ac_random_rlc_networks(eng, n_nodes, n_elem):
     text = random_rlc_netlist(rng, n_nodes, n_elem, n_v=min(2, n_nodes))
     freqs = sp.analysis.ac_frequencies(parse_netlist(text))
     for flags, tol in ((native.FLAG_DENSE, AC_TOL), (native.FLAG_STRICT, 1e-11), (native.FLAG_SPARSE, AC_TOL),
-                       (native.FLAG_SPARSE | SM, AC_TOL)):
+                       (native.FLAG_SPARSE | SM, AC_TOL), (native.FLAG_SPARSE | native.FLAG_JIT | SM, AC_TOL)):
         out, x, ie, st, _ = ac_case(eng, text, freqs, flags)
         if flags == native.FLAG_SPARSE:
             FALLBACKS.append(eng.stats()["fallback_solves"])
@@ -227,7 +230,7 @@ def test_ac_error_statuses_do_not_poison_batch(eng):
     assert (st == native.ST_SINGULAR).all() and np.array_equal(out["status"], st)
     # inductor with 1e-15 <= 2*pi*f*L < 3.2e-8 -> "Complex divide by ~0" (hazard H5)
     text = "* cdiv\nv1 a 0 ac 1\nl1 a b 1e-10\nr1 b 0 1k\n.ac lin 2 1 2\n"
-    for flags in (0, native.FLAG_SPARSE, native.FLAG_SPARSE | SM):
+    for flags in (0, native.FLAG_SPARSE, native.FLAG_SPARSE | SM, native.FLAG_SPARSE | native.FLAG_JIT):
         out, x, ie, st, _ = ac_case(eng, text, [1.0, 1e6], flags)
         assert st[0, 0] == native.ST_CDIV and st[0, 1] == 0 and np.array_equal(out["status"], st)
         assert rel_err(out["x"][0, 1], x[0, 1]) <= AC_TOL
@@ -354,7 +357,10 @@ def test_full_size_properties_cfg2(eng):
     freqs = np.array(sp.analysis.ac_frequencies(ck))
     out = sp.simulate_ac_batch(ck, freqs, engine=eng, flags=SM)
     stt = eng.stats()
-    assert stt["tier"] == native.TIER_SPARSE and stt["fallback_solves"] == 0
+    assert stt["tier"] == native.TIER_SPARSE_JIT and stt["fallback_solves"] == 0   # 1e6 points: compiled program
+    out_i = sp.simulate_ac_batch(ck, freqs[::7], engine=eng, flags=SM | native.FLAG_NO_JIT)
+    assert eng.stats()["tier"] == native.TIER_SPARSE
+    assert rel_err(out_i["x"][0], out["x"][0][::7]) <= 1e-12   # interpreter and compiled program agree
     assert out["status"].max() == 0
     x, ie = out["x"][0], out["ielem"][0]
     assert np.max(np.abs(x[:, 0] - 1.0)) <= 1e-15
