@@ -254,15 +254,17 @@ def run_native(args):
         d_var = torch.from_numpy(sweep.var_values).to(dev) if sweep is not None else None
         d_freqs = torch.from_numpy(wl["freqs"]).to(dev)
         # series-major results (x[Nvar][P], ielem[nAc][P]): the layout the drop-in simulateAC uses
-        d_x = torch.empty((table.nvar, P), dtype=torch.complex128, device=dev)
-        d_i = torch.empty((table.n_ac_elem, P), dtype=torch.complex128, device=dev)
+        # (rows padded to spicey_series_ld(P) points so that every row starts on a 512-byte boundary)
+        ld = eng.series_ld(P)
+        d_x = torch.empty((table.nvar, ld), dtype=torch.complex128, device=dev)
+        d_i = torch.empty((table.n_ac_elem, ld), dtype=torch.complex128, device=dev)
         d_s = torch.empty(P, dtype=torch.int32, device=dev)
         ac_flags = native.FLAG_SERIES_MAJOR | (native.FLAG_DENSE if args.dense else 0)
 
         def step_resident():
             eng.ac_solve_device(table, d_freqs.data_ptr(), F, d_x.data_ptr(), d_i.data_ptr(), d_s.data_ptr(),
                                 sweep=sweep, d_var_values=None if d_var is None else d_var.data_ptr(),
-                                flags=ac_flags, stream=stream.cuda_stream)
+                                flags=ac_flags, stream=stream.cuda_stream, series_ld=ld)
 
         h_freqs, p0 = native.pinned_empty(eng.lib, (F,), np.float64)
         h_freqs[:] = wl["freqs"]
@@ -393,7 +395,7 @@ def run_native(args):
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "c128" if wl["kind"] == "ac" else "f64", "data": "synthetic",
             "config": {"workload": wl["label"], "per_gpu_units_per_step": units, "tier": tier,
-                       "result_layout": "series-major x[Nvar][P], ielem[nAc][P]" if wl["kind"] == "ac" else "v[step][node][inst]",
+                       "result_layout": "series-major x[Nvar][ld], ielem[nAc][ld], ld = P rounded up to 32 points" if wl["kind"] == "ac" else "v[step][node][inst]",
                        "fallback_solves_last_step": int(fallback),
                        "l2": "no flush: each step writes %.2f GB of results, larger than the 126 MB L2" % (
                            working_set / 1e9),

@@ -41,7 +41,7 @@
 extern "C" {
 #endif
 
-#define SPICEY_NATIVE_ABI_VERSION 1
+#define SPICEY_NATIVE_ABI_VERSION 2
 
 /* Element kinds of the flat element table (ParsedCircuit, lib/parsing/parseNetlist.ts:12-105). */
 enum {
@@ -164,11 +164,20 @@ int32_t spicey_ac_solve(spicey_handle* h, const spicey_elem_table* table, const 
 
 /* Same, on ONE device with device pointers (freqs, sweep->var_values, x, ielem, status
  * live on device devices[dev_index]); the table arrays stay on the host.  Launches on
- * `stream` (a cudaStream_t, NULL = default stream) and does not synchronise. */
+ * `stream` (a cudaStream_t, NULL = default stream) and does not synchronise.
+ * series_ld: 0 = point-major x[P][Nvar] (or, with SPICEY_FLAG_SERIES_MAJOR, series-major with
+ * leading dimension P); otherwise series-major x[Nvar][series_ld], ielem[nAc][series_ld] with
+ * series_ld >= P points per row.  Use spicey_series_ld(P): rows that start on a 512-byte boundary
+ * make every warp's store whole 128-byte lines (measured on B200: 6.0 instead of 3.4 TB/s of
+ * store bandwidth for this pattern). */
 int32_t spicey_ac_solve_device(spicey_handle* h, int32_t dev_index, const spicey_elem_table* table,
                                const spicey_sweep* sweep, const double* d_freqs, int64_t n_freq,
-                               double* d_x, double* d_ielem, int32_t* d_status, uint32_t flags,
-                               void* stream);
+                               double* d_x, double* d_ielem, int32_t* d_status, int64_t series_ld,
+                               uint32_t flags, void* stream);
+
+/* Recommended leading dimension (in points) of a series-major device result of n_points points:
+ * n_points rounded up to a multiple of 32 (32 points x 16 B = 512 B). */
+int64_t spicey_series_ld(int64_t n_points);
 
 /*
  * Transient batch: fixed-step backward Euler from state0, steps+1 recorded samples
@@ -209,6 +218,15 @@ enum {
   SPICEY_FLAG_JIT = 128u,          /* compile the straight-line sparse kernel even for batches below 200,000 points */
   SPICEY_FLAG_NO_JIT = 256u        /* never compile: always interpret the sparse program */
 };
+
+/* Tooling (no device needed): writes the CUDA source of the compiled straight-line sparse kernel
+ * (tier 5) for this element table into buf (NUL-terminated, truncated to cap) and returns the
+ * size needed, or -1 when the sparse path does not apply.  stats_out[8], optional: values crossing
+ * into the back-substitution, of those in shared memory, distinct stamped values, micro-ops,
+ * complex FMAs, reciprocals, bulk-copy groups, staging waits.  with_ielem: bit 0 element currents, bit 1
+ * bulk (series-major) stores, bits 8-15 staging ring slots, bits 16-23 __syncthreads period. */
+int64_t spicey_debug_sparse_source(const spicey_elem_table* table, double pilot_f, int32_t block, int32_t min_blocks,
+                                   int32_t smem_slots, int32_t with_ielem, char* buf, int64_t cap, int32_t* stats_out);
 
 /* Measures this GPU's FP64 FMA peak with a register-only DFMA loop (GFLOP/s), the
  * denominator the FP64-bound roofline is reported against. */

@@ -3,14 +3,30 @@
 // The interpreter in ac_sparse.cuh spends ~50 instructions of decode and operand addressing on every
 // micro-op that does 4 DFMAs of work.  For programs small enough to compile in seconds, the same
 // single-assignment program (sparse_program.h: pilot pivot sequence, symbolic fill, per-system pivot
-// verification) is instead *written out* as one straight-line sm_100a kernel: every value is a local
-// `double2`, every operand a name, every stamped entry a literal expression in w = 2*pi*f — the CUDA
-// compiler then does what the interpreter's host-side liveness pass approximates (register allocation,
-// spilling only what survives until the back-substitution) and no decode work remains.  NVRTC compiles
-// the source once per topology (cached per handle); semantics, verification and the dense fallback are
-// exactly those of the interpreter, which stays the path for large programs and for component sweeps.
+// verification) is instead *written out* as one straight-line sm_100a kernel that NVRTC compiles once
+// per topology (cached per handle).  Semantics, verification and the dense fallback are exactly those
+// of the interpreter, which stays the path for large programs and for component sweeps.
+//
+// What the generator decides (the compiler cannot):
+//  * Where the factorisation lives between the two phases.  One thread owns one system; the values the
+//    forward elimination produces for the back-substitution (1/u_kk, eliminated rhs, modified U) are
+//    ~2 KB per system.  Left to the register allocator they spill to local memory and the dependent
+//    chain of the back-substitution then waits on L2 for every one of them.  Here the values with the
+//    longest def->use distance are placed in a per-thread column of shared memory ([slot][thread], one
+//    conflict-free 16-byte access per lane) and re-loaded by name in the back phase; the short-lived
+//    rest stays in registers.  Nothing of the matrix touches HBM.
+//  * Element currents are emitted as soon as both node voltages exist, so an x_i dies a few
+//    instructions after it is produced instead of surviving until an unpack loop.
+//  * Arithmetic is specialised on what the operand structurally is: a stamped entry that is purely real
+//    (1/R sums), purely imaginary (w*C - 1/(w*L)) or +-1 (source rows) costs half the DFMAs of a
+//    complex multiply, with bit-identical results (the dropped terms are exact zeros).
+//  * The reference's `|f| < EPS -> skip row` (solveComplex.ts:46) is applied as a select on the updated
+//    values, so the test is off the dependent chain pivot -> multiplier -> update -> next pivot.
 #pragma once
+#include <algorithm>
 #include <cstdio>
+#include <cstring>
+#include <map>
 #include <string>
 #include <vector>
 
@@ -25,14 +41,41 @@ struct CodegenInput {
   const int* n2 = nullptr;
 };
 
+struct CodegenOptions {
+  int block = 128;        // threads per CTA
+  int min_blocks = 2;     // __launch_bounds__ second argument
+  int smem_slots = 48;    // shared-memory double2 slots per thread (factor values + staging ring)
+  bool with_ielem = true; // false: the caller passed ielem = NULL, no current is computed
+  bool bulk_store = false; // series-major results leave through shared memory and cp.async.bulk (needs series_ld != 0; measured slower)
+  int ring_slots = 6;     // bulk_store: slots reserved for staging results (more become free as factors are consumed)
+  int sync_every = 0;     // > 0: __syncthreads() every that many pivots / back-substitution rows (instruction-cache locality)
+};
+
+struct CodegenStats {
+  int n_saved = 0;        // values crossing from the elimination into the back-substitution
+  int smem_slots = 0;     // of those, placed in shared memory
+  size_t smem_bytes = 0;  // dynamic shared memory per CTA
+  int n_classes = 0;      // distinct stamped values
+  int n_groups = 0;       // bulk-copy groups per system
+  int n_waits = 0;        // of which had to wait for a staging slot
+};
+
 namespace codegen_detail {
 
-inline std::string lit(double v) {  // exact hexadecimal floating literal
+inline std::string hexlit(double v) {  // exact hexadecimal floating literal
   char buf[64];
   if (v == 0.0) return "0.0";
   snprintf(buf, sizeof buf, "%a", v);
-  return buf;
+  return v < 0 ? std::string("(") + buf + ")" : std::string(buf);
 }
+
+// A complex operand as two scalar expressions plus what is structurally known about it.
+struct Opnd {
+  std::string re, im;
+  bool re0 = false, im0 = false;   // component is an exact structural zero
+  double re_c = 0;                 // value of re when it is a literal
+  bool re_lit = false;
+};
 
 }  // namespace codegen_detail
 
@@ -46,105 +89,381 @@ struct JitArgs {
 };
 #define EPS 1e-15
 #define THR 1e-30
-__device__ __forceinline__ double2 cmul(double2 a, double2 b) {
-  return make_double2(fma(a.x, b.x, -a.y * b.y), fma(a.x, b.y, a.y * b.x));
+#define D2(a, b) make_double2((a), (b))
+// 1/a for a in [1e-15, huge): MUFU seed + two Newton steps (<= 1 ulp off the correctly rounded quotient,
+// no slow-path branch, so the whole elimination stays one basic block)
+__device__ __forceinline__ double rcp_nr(double a) {
+  double y, e;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(a));
+  e = fma(-a, y, 1.0); y = fma(y, e, y);
+  e = fma(-a, y, 1.0); y = fma(y, e, y);
+  return y;
 }
-__device__ __forceinline__ double2 csub(double2 a, double2 b) { return make_double2(a.x - b.x, a.y - b.y); }
-__device__ __forceinline__ double2 submul(double2 a, double2 f, double2 p) {
-  return make_double2(fma(-f.x, p.x, fma(f.y, p.y, a.x)), fma(-f.x, p.y, fma(-f.y, p.x, a.y)));
-}
-__device__ __forceinline__ double nrm(double2 a) { return fma(a.x, a.x, a.y * a.y); }
+extern __shared__ double2 sm[];
+// Shared-memory column of this thread, addressed with immediate offsets.  Inline PTX on purpose: with plain
+// C++ accesses the compiler forwards every stored value to its re-load and keeps it in a register (or in
+// local memory) across the whole elimination, which is exactly what the placement is meant to avoid.
+#define SMST(off, v) asm volatile("st.shared.v2.f64 [%0+" #off "], {%1, %2};" :: "r"(sbase), "d"((v).x), "d"((v).y) : "memory")
+#define SMLD(v, off) asm volatile("ld.shared.v2.f64 {%0, %1}, [%2+" #off "];" : "=d"((v).x), "=d"((v).y) : "r"(sbase) : "memory")
+// Results: a staged slot row of one warp is 32 points x 16 B = one contiguous 512-byte piece of a series.
+// Lane 0 hands it to the bulk-copy engine (no registers are held by stores in flight, full lines reach L2).
+#define FENCE_ASYNC() asm volatile("fence.proxy.async.shared::cta;" ::: "memory")
+#define BULK_ST(gptr, off) asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1+" #off "], %2;" :: "l"(gptr), "r"(sbase), "r"(wbytes) : "memory")
+#define BULK_COMMIT() asm volatile("cp.async.bulk.commit_group;" ::: "memory")
+#define BULK_WAIT_READ(n) asm volatile("cp.async.bulk.wait_group.read " #n ";" ::: "memory")
+#define BULK_WAIT_ALL() asm volatile("cp.async.bulk.wait_group 0;" ::: "memory")
 )SRC";
 }
 
-inline std::string generate_sparse_kernel_source(const CodegenInput& in) {
+inline std::string generate_sparse_kernel_source(const CodegenInput& in, const CodegenOptions& opt = CodegenOptions(),
+                                                 CodegenStats* stats_out = nullptr) {
   using namespace codegen_detail;
   using namespace sparse_detail;
   const SparseProgram& sp = *in.sp;
-  std::string s = sparse_jit_prelude();
-  s.reserve(1 << 20);
-  auto entry_expr = [&](int en) {
-    // (alpha + Re J) + j*(w*beta - gamma/w + Im J), constants summed on the host in stamping order
+  const std::vector<IrOp>& ir = sp.ir;
+  const int n_ir = (int)ir.size();
+  CodegenStats st;
+  // Real constants live in a __constant__ table: a DFMA/DMUL takes c[bank][offset] as an operand for free,
+  // whereas a 64-bit immediate costs two extra instructions every time it is used.
+  std::vector<double> ktab;
+  std::map<unsigned long long, int> kidx;
+  auto lit = [&](double v) -> std::string {
+    if (v == 0.0) return "0.0";
+    unsigned long long bits;
+    memcpy(&bits, &v, 8);
+    auto it = kidx.find(bits);
+    if (it == kidx.end()) { it = kidx.insert(std::make_pair(bits, (int)ktab.size())).first; ktab.push_back(v); }
+    return "KC[" + std::to_string(it->second) + "]";
+  };
+
+  // ---- stamped entries -> classes of identical constants ----
+  std::vector<int> cls(sp.n_stamp, -1);
+  std::vector<int> cls_rep;
+  {
+    std::map<std::vector<double>, int> seen;
+    for (int en = 0; en < sp.n_stamp; ++en) {
+      std::vector<double> key = {sp.ent_alpha[en] + sp.ent_jre[en], sp.ent_jim[en], sp.ent_beta[en], sp.ent_gamma[en]};
+      auto it = seen.find(key);
+      if (it == seen.end()) { it = seen.insert(std::make_pair(key, (int)cls_rep.size())).first; cls_rep.push_back(en); }
+      cls[en] = it->second;
+    }
+  }
+  st.n_classes = (int)cls_rep.size();
+  const bool named_classes = st.n_classes <= 32;  // otherwise expressions are written where they are used
+  bool need_iw = false;
+  for (int en = 0; en < sp.n_stamp; ++en) need_iw = need_iw || sp.ent_gamma[en] != 0.0;
+  for (int e = 0; e < in.n_ac_elem; ++e) need_iw = need_iw || sp.el_g[e] != 0.0;
+
+  auto im_expr = [&](double b, double g, double ji) -> std::string {  // w*b - g/w + ji
     std::string im;
-    const double b = sp.ent_beta[en], g = sp.ent_gamma[en], ji = sp.ent_jim[en];
-    if (b != 0.0 && g != 0.0) im = "fma(w, " + lit(b) + ", -(" + lit(g) + ") * iw)";
+    if (b != 0.0 && g != 0.0) im = "fma(w, " + lit(b) + ", -" + lit(g) + " * iw)";
     else if (b != 0.0) im = "w * " + lit(b);
-    else if (g != 0.0) im = "-(" + lit(g) + ") * iw";
-    else im = "0.0";
-    if (ji != 0.0) im += " + " + lit(ji);
-    return "make_double2(" + lit(sp.ent_alpha[en] + sp.ent_jre[en]) + ", " + im + ")";
+    else if (g != 0.0) im = "-" + lit(g) + " * iw";
+    else return ji != 0.0 ? lit(ji) : "0.0";
+    if (ji != 0.0) im = "(" + im + " + " + lit(ji) + ")";
+    return im;
   };
-  auto opnd = [&](int o) -> std::string {
-    if (o >= 0) return "v" + std::to_string(o);
-    if (o == kNoOperand) return "Z";
-    return "e" + std::to_string(~o);
+  auto entry_opnd = [&](int en) -> Opnd {
+    Opnd o;
+    const double re = sp.ent_alpha[en] + sp.ent_jre[en];
+    const double b = sp.ent_beta[en], g = sp.ent_gamma[en], ji = sp.ent_jim[en];
+    o.re = lit(re); o.re0 = re == 0.0; o.re_lit = true; o.re_c = re;
+    o.im0 = b == 0.0 && g == 0.0 && ji == 0.0;
+    if (o.im0) o.im = "0.0";
+    else if (named_classes) o.im = "q" + std::to_string(cls[en]);
+    else o.im = "(" + im_expr(b, g, ji) + ")";
+    return o;
   };
-  s += "#ifndef MINB\n#define MINB 4\n#endif\n";
-  s += "extern \"C\" __global__ void __launch_bounds__(128, MINB) spicey_sparse_jit(JitArgs a) {\n";
-  s += "  const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x;\n";
-  s += "  const long long nthreads = (long long)gridDim.x * blockDim.x;\n";
-  s += "  const double2 Z = make_double2(0.0, 0.0);\n";
-  s += "  for (long long p = tid; p < a.p_count; p += nthreads) {\n";
-  s += "    const double w = 6.283185307179586 * a.freqs[p];\n    const double iw = 1.0 / w;\n";
-  s += "    const long long xst = a.series_ld ? a.series_ld : 1;\n";
-  s += "    double2* __restrict__ xout = a.series_ld ? a.x + p : a.x + p * a.n;\n";
-  s += "    bool ok = true, bad = false;\n    int status = 0;\n    double mp, m;\n    double2 ap, r, fm, acc;\n";
+
+  // ---- positions: op index; boundary B = first BSUB ----
+  int B = n_ir;
+  for (int t = 0; t < n_ir; ++t) if (ir[t].kind == SOP_BSUB) { B = t; break; }
+  std::vector<int> deft(sp.n_virtual, -1), last(sp.n_virtual, -1);
+  for (int t = 0; t < n_ir; ++t) {
+    const IrOp& op = ir[t];
+    auto use = [&](int o) { if (o >= 0) last[o] = std::max(last[o], t); };
+    for (int o : op.reads) use(o);
+    for (const Update& u : op.upd) { use(u.dst_old); use(u.src); deft[u.dst_new] = t; }
+    if (op.def >= 0) deft[op.def] = t;
+  }
+  // element currents: emitted after the BSUB that produces the later of the two node voltages
+  std::vector<std::vector<int>> cur_at(n_ir);
+  auto xv_of = [&](int node) { return node == 0 ? -1 : sp.x_virtual[node - 1]; };
+  for (int e = 0; e < in.n_ac_elem; ++e) {
+    int when = -1;
+    if (e >= in.v_first) when = deft[sp.x_virtual[in.nn + e - in.v_first]];
+    else {
+      const int a = xv_of(in.n1[e]), b = xv_of(in.n2[e]);
+      if (a >= 0) when = std::max(when, deft[a]);
+      if (b >= 0) when = std::max(when, deft[b]);
+    }
+    if (when < 0) when = n_ir - 1;  // both ends grounded: current is zero, emit at the end
+    cur_at[when].push_back(e);
+    if (e < in.v_first) {
+      const int a = xv_of(in.n1[e]), b = xv_of(in.n2[e]);
+      if (a >= 0) last[a] = std::max(last[a], when);
+      if (b >= 0) last[b] = std::max(last[b], when);
+    }
+  }
+  // ---- shared-memory placement of the cross-phase values ----
+  // direct stores: the longest-lived values go to shared memory (registers keep what is consumed first);
+  // bulk stores:   the longest-lived values stay in registers, so that the back-substitution frees shared
+  //                memory slots from its first row on — they become the staging ring of the results.
+  const bool bulk = opt.bulk_store;
+  const int ring0 = bulk ? std::max(1, std::min(opt.ring_slots, opt.smem_slots)) : 0;
+  std::vector<int> slot_of(sp.n_virtual, -1);
+  int ns = 0;
+  {
+    std::vector<std::pair<int, int>> saved;  // (lifetime key, v)
+    for (int v = 0; v < sp.n_virtual; ++v)
+      if (deft[v] >= 0 && deft[v] < B && last[v] >= B)
+        saved.push_back(std::make_pair(bulk ? (last[v] - deft[v]) : -(last[v] - deft[v]), v));
+    std::sort(saved.begin(), saved.end());
+    st.n_saved = (int)saved.size();
+    ns = std::min<int>(std::max(0, opt.smem_slots - ring0), (int)saved.size());
+    for (int i = 0; i < ns; ++i) slot_of[saved[i].second] = i;
+    st.smem_slots = ns;
+    const int total = bulk ? std::max(opt.smem_slots, ring0) : ns;
+    st.smem_bytes = (size_t)total * opt.block * 16;
+  }
+  const int total_slots = (int)(st.smem_bytes / ((size_t)opt.block * 16));
+  auto soff = [&](int slot) { return std::to_string((long long)slot * opt.block * 16); };
+
+  auto opnd = [&](int o) -> Opnd {
+    Opnd r;
+    if (o == kNoOperand) { r.re = r.im = "0.0"; r.re0 = r.im0 = true; r.re_lit = true; return r; }
+    if (o < 0) return entry_opnd(~o);
+    const std::string nm = "v" + std::to_string(o);
+    r.re = nm + ".x"; r.im = nm + ".y";
+    return r;
+  };
+
+  std::string s;
+  s.reserve(1 << 20);
+  s += "#define BLOCK " + std::to_string(opt.block) + "\n";
+  s += "extern \"C\" __global__ void __launch_bounds__(BLOCK, " + std::to_string(opt.min_blocks) + ") spicey_sparse_jit(JitArgs a) {\n";
+  s += "  if (a.p_count <= 0) return;\n";
+  s += "  const unsigned ld = a.series_ld ? (unsigned)a.series_ld : 1u;\n";
+  s += "  const unsigned sbase = (unsigned)__cvta_generic_to_shared(sm) + threadIdx.x * 16u;\n";
+  s += "  const long long stride = (long long)gridDim.x * BLOCK, plast = a.p_count - 1;\n";
+  if (bulk) s += "  const unsigned lane = threadIdx.x & 31u;\n";
+  s += "  double fnext = a.freqs[min((long long)blockIdx.x * BLOCK + threadIdx.x, plast)];\n";
+  // block-uniform trip count: lanes past the end solve the last point again and store nothing
+  s += "  for (long long base = (long long)blockIdx.x * BLOCK; base < a.p_count; base += stride) {\n";
+  s += "    const long long p = base + threadIdx.x;\n    const bool valid = p < a.p_count;\n";
+  s += "    const double w = 6.283185307179586 * fnext;\n";
+  s += "    fnext = a.freqs[min(p + stride, plast)];\n";
+  if (need_iw) s += "    const double iw = 1.0 / w;\n";
+  s += "    char* const xb = (char*)(a.series_ld ? a.x + p : a.x + p * a.n);\n";
+  if (opt.with_ielem) s += "    char* const ib = (char*)(a.series_ld ? a.ielem + p : a.ielem + p * a.n_ac_elem);\n";
+  if (bulk) s += "    const unsigned wbytes = (unsigned)max(0ll, min(32ll, a.p_count - p)) * 16u;  // lane 0: bytes of this warp's piece\n";
+  s += "    bool ok = true, bad = false;\n    double mp, m, inv;\n    double2 r, fm;\n";
   for (double L : sp.ind_L)  // inductor guards of simulateAC.ts:47-51 are value dependent: dense kernel decides
     s += "    { const double d = w * " + lit(L) + "; bad = bad || fabs(d) < EPS || d * d < EPS; }\n";
-  // stamped entries used by the program, one expression each (the compiler merges identical ones)
-  {
-    std::vector<char> used(sp.n_stamp, 0);
-    auto mark = [&](int o) { if (o < 0 && o != kNoOperand) used[~o] = 1; };
-    for (const IrOp& op : sp.ir) {
-      for (int o : op.reads) mark(o);
-      for (const Update& u : op.upd) { mark(u.dst_old); mark(u.src); }
+  if (named_classes)
+    for (int c = 0; c < st.n_classes; ++c) {
+      const int en = cls_rep[c];
+      if (sp.ent_beta[en] != 0.0 || sp.ent_gamma[en] != 0.0 || sp.ent_jim[en] != 0.0)
+        s += "    const double q" + std::to_string(c) + " = " + im_expr(sp.ent_beta[en], sp.ent_gamma[en], sp.ent_jim[en]) + ";\n";
     }
-    for (int en = 0; en < sp.n_stamp; ++en)
-      if (used[en]) s += "    const double2 e" + std::to_string(en) + " = " + entry_expr(en) + ";\n";
-  }
-  for (const IrOp& op : sp.ir) {
+
+  // a - f*p, component expressions; f is the double2 named `fn`
+  auto submul = [&](const Opnd& a, const std::string& fn, const Opnd& p, std::string& re, std::string& im) {
+    // re = a.re - f.x p.re + f.y p.im ; im = a.im - f.x p.im - f.y p.re
+    std::string inner_re = a.re, inner_im = a.im;
+    if (!p.im0) inner_re = "fma(" + fn + ".y, " + p.im + ", " + a.re + ")";
+    if (!p.re0) inner_im = "fma(-" + fn + ".y, " + p.re + ", " + a.im + ")";
+    re = p.re0 ? inner_re : "fma(-" + fn + ".x, " + p.re + ", " + inner_re + ")";
+    im = p.im0 ? inner_im : "fma(-" + fn + ".x, " + p.im + ", " + inner_im + ")";
+  };
+  // a * b, component expressions
+  auto cmul = [&](const Opnd& a, const Opnd& b, std::string& re, std::string& im) {
+    auto prod = [&](const std::string& x, bool x0, const std::string& y, bool y0) { return (x0 || y0) ? std::string() : x + " * " + y; };
+    // re = a.re b.re - a.im b.im ; im = a.re b.im + a.im b.re
+    const std::string t1 = prod(a.im, a.im0, b.im, b.im0), t2 = prod(a.im, a.im0, b.re, b.re0);
+    if (a.re0 || b.re0) re = t1.empty() ? "0.0" : "-(" + t1 + ")";
+    else re = t1.empty() ? a.re + " * " + b.re : "fma(" + a.re + ", " + b.re + ", -(" + t1 + "))";
+    if (a.re0 || b.im0) im = t2.empty() ? "0.0" : t2;
+    else im = t2.empty() ? a.re + " * " + b.im : "fma(" + a.re + ", " + b.im + ", " + t2 + ")";
+  };
+  auto nrm = [&](const Opnd& a) -> std::string {
+    if (a.re0 && a.im0) return "0.0";
+    if (a.im0) return a.re + " * " + a.re;
+    if (a.re0) return a.im + " * " + a.im;
+    return "fma(" + a.re + ", " + a.re + ", " + a.im + " * " + a.im + ")";
+  };
+  auto off = [&](int k) { return "(size_t)ld * " + std::to_string(16ll * k) + "u"; };
+
+  // ---- results: direct predicated stores, or staged rows handed to the bulk-copy engine ----
+  struct Out { bool cur; int k; std::string re, im; };
+  std::vector<Out> pending;
+  std::vector<int> free_slots;                   // LIFO
+  std::vector<std::pair<int, int>> inflight;     // (slot, group), oldest first
+  size_t inflight_head = 0;
+  int n_groups = 0;
+  for (int q = total_slots - 1; q >= ns; --q) free_slots.push_back(q);
+  const int chunk_cap = std::max(1, total_slots - ns);
+  auto flush_outputs = [&]() {
+    if (pending.empty()) return;
+    if (!bulk) {
+      for (const Out& o : pending)
+        s += std::string("    if (valid) *(double2*)(") + (o.cur ? "ib" : "xb") + " + " + off(o.k) + ") = D2(" + o.re + ", " + o.im + ");\n";
+      pending.clear();
+      return;
+    }
+    for (size_t b0 = 0; b0 < pending.size(); b0 += chunk_cap) {
+      const size_t b1 = std::min(pending.size(), b0 + (size_t)chunk_cap);
+      std::vector<int> slots;
+      int wait_n = -1;
+      for (size_t q = b0; q < b1; ++q) {
+        if (free_slots.empty()) {
+          // recycle the oldest staged row: its bulk copy must have finished READING shared memory
+          const int g = inflight[inflight_head].second;
+          wait_n = n_groups - 1 - g;
+          while (inflight_head < inflight.size() && inflight[inflight_head].second <= g) free_slots.push_back(inflight[inflight_head++].first);
+        }
+        slots.push_back(free_slots.back());
+        free_slots.pop_back();
+      }
+      if (wait_n >= 0) {
+        s += "    if (lane == 0) BULK_WAIT_READ(" + std::to_string(wait_n) + ");\n    __syncwarp();\n";
+        st.n_waits++;
+      }
+      for (size_t q = b0; q < b1; ++q)
+        s += "    { const double2 o = D2(" + pending[q].re + ", " + pending[q].im + "); SMST(" + soff(slots[q - b0]) + ", o); }\n";
+      s += "    FENCE_ASYNC(); __syncwarp();\n    if (lane == 0 && wbytes) {\n";
+      for (size_t q = b0; q < b1; ++q)
+        s += std::string("      BULK_ST(") + (pending[q].cur ? "ib" : "xb") + " + " + off(pending[q].k) + ", " + soff(slots[q - b0]) + ");\n";
+      s += "      BULK_COMMIT();\n    }\n";
+      for (int sl : slots) inflight.push_back(std::make_pair(sl, n_groups));
+      ++n_groups;
+    }
+    pending.clear();
+  };
+
+  auto emit_currents = [&](int t) {
+    if (cur_at[t].empty() || !opt.with_ielem) return;
+    for (int e : cur_at[t]) {
+      std::string re, im;
+      if (e >= in.v_first) {
+        const Opnd x = opnd(sp.x_virtual[in.nn + e - in.v_first]);
+        re = x.re; im = x.im;
+      } else {
+        const int va = xv_of(in.n1[e]), vb = xv_of(in.n2[e]);
+        Opnd d;  // v1 - v2
+        if (va >= 0 && vb >= 0) {
+          const Opnd A = opnd(va), Bq = opnd(vb);
+          d.re = "(" + A.re + " - " + Bq.re + ")"; d.im = "(" + A.im + " - " + Bq.im + ")";
+        } else if (va >= 0) d = opnd(va);
+        else if (vb >= 0) { const Opnd Bq = opnd(vb); d.re = "(0.0 - " + Bq.re + ")"; d.im = "(0.0 - " + Bq.im + ")"; }
+        else { d.re = d.im = "0.0"; d.re0 = d.im0 = true; }
+        Opnd y;  // element admittance ya + j(w*yb - yg/w)
+        y.re = lit(sp.el_a[e]); y.re0 = sp.el_a[e] == 0.0;
+        y.im0 = sp.el_b[e] == 0.0 && sp.el_g[e] == 0.0;
+        y.im = y.im0 ? "0.0" : "(" + im_expr(sp.el_b[e], sp.el_g[e], 0.0) + ")";
+        cmul(y, d, re, im);
+      }
+      pending.push_back(Out{true, e, re, im});
+    }
+  };
+
+  int n_piv = 0, n_bs = 0;
+  for (int t = 0; t < n_ir; ++t) {
+    const IrOp& op = ir[t];
+    if (t == B) {
+      // Every pivot has been verified.  A system whose pivot order differs from the pilot's, or that trips a
+      // guard of the reference (singular, Complex.div, inductor), goes to the dense kernel, which also
+      // reports the exact status; whatever the rows below write for it is overwritten there.
+      s += "    { const bool fb = bad || !ok;\n";
+      s += "      if (valid) { a.status[p] = fb ? -1 : 0; if (fb) a.fb_list[atomicAdd(a.fb_count, 1)] = p; } }\n";
+    }
     if (op.kind == SOP_PIVOT) {
-      s += "    ap = " + opnd(op.reads[op.pidx]) + "; mp = nrm(ap); ok = ok && (mp == mp);\n";
+      if (opt.sync_every > 0 && n_piv % opt.sync_every == 0) s += "    __syncthreads();\n";
+      ++n_piv;
+      const Opnd ap = opnd(op.reads[op.pidx]);
+      s += "    mp = " + nrm(ap) + ";\n";
       for (int c = 0; c < (int)op.reads.size(); ++c) {
         if (c == op.pidx) continue;
-        s += "    m = nrm(" + opnd(op.reads[c]) + "); ok = ok && " + (c < op.pidx ? "(m < mp)" : "!(m > mp)") + ";\n";
+        s += "    m = " + nrm(opnd(op.reads[c])) + "; ok = ok && " + (c < op.pidx ? "(m < mp)" : "!(m > mp)") + ";\n";
       }
-      s += "    if (status == 0) status = mp < THR ? 1 : (mp < EPS ? 2 : 0);\n";
-      s += "    { const double inv = 1.0 / mp; r = make_double2(ap.x * inv, -ap.y * inv); }\n";
-      s += "    const double2 v" + std::to_string(op.def) + " = r;\n";
+      s += "    ok = ok && (mp >= EPS);   // singular / Complex.div guard (or NaN): the dense kernel reports which\n";
+      s += "    inv = rcp_nr(mp);\n";
+      const std::string v = "v" + std::to_string(op.def);
+      s += "    const double2 " + v + " = D2(" + (ap.re0 ? std::string("0.0") : ap.re + " * inv") + ", " +
+           (ap.im0 ? std::string("0.0") : "-" + ap.im + " * inv") + ");\n";
+      s += "    r = " + v + ";\n";
+      if (slot_of[op.def] >= 0) s += "    SMST(" + soff(slot_of[op.def]) + ", " + v + ");\n";
     } else if (op.kind == SOP_ELIM) {
-      s += "    fm = cmul(" + opnd(op.reads[0]) + ", r); if (nrm(fm) < THR) fm = Z;\n";
-      for (const Update& u : op.upd)
-        s += "    const double2 v" + std::to_string(u.dst_new) + " = submul(" + opnd(u.dst_old) + ", fm, " + opnd(u.src) + ");\n";
+      std::string re, im;
+      Opnd rr; rr.re = "r.x"; rr.im = "r.y";
+      cmul(opnd(op.reads[0]), rr, re, im);
+      // solveComplex.ts:46 skips the row when |f| < EPS: a zero multiplier leaves every updated value as it was
+      // (strongly attenuating circuits do produce such multipliers at the far end of a sweep)
+      s += "    fm = D2(" + re + ", " + im + "); if (fma(fm.x, fm.x, fm.y * fm.y) < THR) fm = D2(0.0, 0.0);\n";
+      for (const Update& u : op.upd) {
+        const Opnd a = opnd(u.dst_old), pq = opnd(u.src);
+        const std::string v = "v" + std::to_string(u.dst_new);
+        submul(a, "fm", pq, re, im);
+        s += "    const double2 " + v + " = D2(" + re + ", " + im + ");\n";
+        if (slot_of[u.dst_new] >= 0) s += "    SMST(" + soff(slot_of[u.dst_new]) + ", " + v + ");\n";
+      }
     } else {
-      s += "    acc = " + opnd(op.reads[0]) + ";\n";
-      for (size_t q = 2; q + 1 < op.reads.size(); q += 2)
-        s += "    acc = submul(acc, " + opnd(op.reads[q]) + ", " + opnd(op.reads[q + 1]) + ");\n";
-      s += "    const double2 v" + std::to_string(op.def) + " = cmul(acc, " + opnd(op.reads[1]) + ");\n";
-      s += "    xout[" + std::to_string(op.var) + " * xst] = v" + std::to_string(op.def) + ";\n";
+      if (opt.sync_every > 0 && n_bs % opt.sync_every == 0) s += "    __syncthreads();\n";
+      ++n_bs;
+      // x_i = (b_i - sum u_ij x_j) * (1/u_ii); the most recently produced x_j is applied last
+      std::vector<std::pair<int, int>> terms;  // (def time of x_j, index into reads)
+      for (size_t q = 2; q + 1 < op.reads.size(); q += 2) terms.push_back(std::make_pair(deft[op.reads[q + 1]], (int)q));
+      std::sort(terms.begin(), terms.end());
+      // shared-memory residents read by this op are loaded under a per-use name
+      std::map<int, std::string> local;
+      for (int o : op.reads)
+        if (o >= 0 && slot_of[o] >= 0 && !local.count(o)) {
+          const std::string nm = "s" + std::to_string(o) + "_" + std::to_string(t);
+          s += "    double2 " + nm + "; SMLD(" + nm + ", " + soff(slot_of[o]) + ");\n";
+          local[o] = nm;
+          if (bulk && last[o] == t) free_slots.push_back(slot_of[o]);  // consumed: the row joins the staging ring
+        }
+      auto bop = [&](int o) -> Opnd {
+        if (o >= 0 && local.count(o)) { Opnd r2; r2.re = local[o] + ".x"; r2.im = local[o] + ".y"; return r2; }
+        return opnd(o);
+      };
+      Opnd acc = bop(op.reads[0]);
+      int k = 0;
+      for (const auto& tm : terms) {
+        const Opnd u = bop(op.reads[tm.second]), xj = bop(op.reads[tm.second + 1]);
+        // acc - u * x_j, u in the role of the structurally known factor
+        std::string re, im;
+        const std::string xn = "xj" + std::to_string(t) + "_" + std::to_string(k);
+        s += "    const double2 " + xn + " = D2(" + xj.re + ", " + xj.im + ");\n";
+        submul(acc, xn, u, re, im);
+        const std::string an = "ac" + std::to_string(t) + "_" + std::to_string(k);
+        s += "    const double2 " + an + " = D2(" + re + ", " + im + ");\n";
+        acc = Opnd(); acc.re = an + ".x"; acc.im = an + ".y";
+        ++k;
+      }
+      std::string re, im;
+      cmul(acc, bop(op.reads[1]), re, im);
+      const std::string v = "v" + std::to_string(op.def);
+      s += "    const double2 " + v + " = D2(" + re + ", " + im + ");\n";
+      pending.push_back(Out{false, op.var, v + ".x", v + ".y"});
     }
+    if (t >= B) { emit_currents(t); flush_outputs(); }
   }
-  s += "    if (bad || !ok) { a.status[p] = -1; a.fb_list[atomicAdd(a.fb_count, 1)] = p; continue; }\n";
-  s += "    double2* __restrict__ io = a.ielem ? (a.series_ld ? a.ielem + p : a.ielem + p * a.n_ac_elem) : nullptr;\n";
-  s += "    if (status != 0) {\n      const double qn = __longlong_as_double(0x7ff8000000000000ll);\n";
-  s += "      for (int i = 0; i < a.n; ++i) xout[i * xst] = make_double2(qn, qn);\n";
-  s += "      if (io) for (int e = 0; e < a.n_ac_elem; ++e) io[e * xst] = make_double2(qn, qn);\n";
-  s += "      a.status[p] = status;\n      continue;\n    }\n";
-  s += "    if (io) {\n";
-  auto xv = [&](int node) { return node == 0 ? std::string("Z") : "v" + std::to_string(sp.x_virtual[node - 1]); };
-  for (int e = 0; e < in.n_ac_elem; ++e) {
-    if (e >= in.v_first) {
-      s += "      io[" + std::to_string(e) + " * xst] = v" + std::to_string(sp.x_virtual[in.nn + e - in.v_first]) + ";\n";
-      continue;
-    }
-    std::string y = "make_double2(" + lit(sp.el_a[e]) + ", ";
-    if (sp.el_b[e] != 0.0) y += "w * " + lit(sp.el_b[e]);
-    else if (sp.el_g[e] != 0.0) y += "-(" + lit(sp.el_g[e]) + ") * iw";
-    else y += "0.0";
-    y += ")";
-    s += "      io[" + std::to_string(e) + " * xst] = cmul(" + y + ", csub(" + xv(in.n1[e]) + ", " + xv(in.n2[e]) + "));\n";
+  // the staged rows are rewritten by the next system's elimination: all bulk reads must be done
+  if (bulk) s += "    if (lane == 0) BULK_WAIT_READ(0);\n    __syncwarp();\n";
+  s += "  }\n";
+  if (bulk) s += "  if (lane == 0) BULK_WAIT_ALL();\n";
+  s += "}\n";
+  {
+    std::string head = sparse_jit_prelude();
+    head += "__constant__ double KC[" + std::to_string(std::max<size_t>(1, ktab.size())) + "] = {";
+    for (size_t i = 0; i < ktab.size(); ++i) head += (i ? ", " : "") + hexlit(ktab[i]);
+    if (ktab.empty()) head += "0.0";
+    head += "};\n";
+    s = head + s;
   }
-  s += "    }\n    a.status[p] = 0;\n  }\n}\n";
+  st.n_groups = n_groups;
+  if (stats_out) *stats_out = st;
   return s;
 }
 

@@ -70,6 +70,7 @@ struct IrOp {
   int def = -1;                 // PIVOT: 1/pivot; BSUB: x_i
   int var = 0;                  // BSUB: i
   std::vector<Update> upd;      // ELIM
+  bool active = true;           // ELIM: false when the pilot skipped the row (|f| < EPS, solveComplex.ts:46)
 };
 
 }  // namespace sparse_detail
@@ -172,6 +173,7 @@ inline void build_sparse_program(const PilotInput& in, SparseProgram& sp, int fa
       el.reads.push_back(cur[(size_t)r * ld + k]);
       const cd f = M[(size_t)r * ld + k] / pivot;
       const bool act = !(std::abs(f) < EPS);
+      el.active = act;
       for (int j : pcols) {
         Update u;
         u.dst_old = cur[(size_t)r * ld + j];

@@ -220,11 +220,21 @@ struct DeviceCtx {
   bool sp_unified = false;
   bool sp_eager = false;
   // straight-line (NVRTC-compiled) variant of the program, when it was built
-  cudaLibrary_t sp_jit_lib = nullptr;
-  cudaKernel_t sp_jit_kernel = nullptr;
-  uint64_t sp_jit_key = 0;   // plan key the module was compiled for (0 = none / failed)
-  bool sp_jit_failed = false;
-  int sp_jit_minb = 2;   // 255 registers per thread: measured best (fewer spills beat occupancy: 1.90 ms vs 2.25 / 3.02 ms at 4 / 8)
+  // compiled straight-line variants of the sparse program: index = with element currents | bulk (series-major) stores << 1
+  struct JitVariant {
+    cudaLibrary_t lib = nullptr;
+    cudaKernel_t kernel = nullptr;
+    uint64_t key = 0;   // plan key the module was compiled for (0 = none)
+    bool failed = false;
+    size_t smem_bytes = 0;
+  } sp_jit[4];
+  // Launch shape of the compiled kernel, measured on cfg2 (tools/jit_sweep.py): one CTA of 6 warps per SM with
+  // 255 registers per thread and 75 shared-memory slots per thread for the factor values (0.76 ms per 1e6
+  // points); 5 warps x 90 slots: 0.81 ms, 4 x 113: 1.03 ms, 8 x 55 (spills): 1.0 ms.  A __syncthreads every
+  // 4 pivots keeps the warps of a CTA on the same instruction-cache lines (-8 %).  The bulk-copy (TMA)
+  // epilogue stays off: one cp.async.bulk issue costs its warp ~90 cycles (tools/micro/bulk_store.cu), more
+  // than the store stalls it removes.  Overridable for experiments: SPICEY_JIT_CFG=block,minb,slots[,ring,sync].
+  int sp_jit_block = 192, sp_jit_minb = 1, sp_jit_slots = 75, sp_jit_ring = 0, sp_jit_sync = 4;
   double sp_jit_compile_ms = 0;
   std::string sp_jit_note;
   std::vector<int4> sp_code_scaled;  // program with slot operands scaled by the pool strides
@@ -350,14 +360,13 @@ struct Nvrtc {
 Nvrtc& nvrtc() { static Nvrtc n; return n; }
 
 // source -> cubin (sm_100a).  Returns false with `why` filled when NVRTC is missing or the compile fails.
-bool jit_compile(const std::string& src, int min_blocks, std::vector<char>& cubin, std::string& why) {
+bool jit_compile(const std::string& src, std::vector<char>& cubin, std::string& why) {
   Nvrtc& N = nvrtc();
   if (!N.ok) { why = "libnvrtc not available"; return false; }
   void* prog = nullptr;
   if (N.create(&prog, src.c_str(), "spicey_sparse_jit.cu", 0, nullptr, nullptr) != 0) { why = "nvrtcCreateProgram failed"; return false; }
-  std::string minb = "-DMINB=" + std::to_string(min_blocks);
-  const char* opts[] = {"--gpu-architecture=sm_100a", "-std=c++17", "-lineinfo", "-default-device", minb.c_str()};
-  int rc = N.compile(prog, 5, opts);
+  const char* opts[] = {"--gpu-architecture=sm_100a", "-std=c++17", "-lineinfo", "-default-device"};
+  int rc = N.compile(prog, 4, opts);
   if (rc != 0) {
     size_t n = 0;
     N.log_size(prog, &n);
@@ -390,21 +399,16 @@ uint64_t plan_key(const HostPlan& hp) {
   return h ? h : 1;
 }
 
-// Builds (or reuses) the sparse program of this topology on ctx.  pilot_f: a representative frequency.
-// Returns SPICEY_SUCCESS with ctx.sp_valid=false when the sparse path does not apply.
-int prepare_sparse(DeviceCtx& ctx, const HostPlan& hp, double pilot_f, bool eager, cudaStream_t stream) {
-  const uint64_t key = plan_key(hp) ^ (eager ? 0x9e3779b97f4a7c15ull : 0ull);
-  if (ctx.sp_key == key) return SPICEY_SUCCESS;  // cached (valid or known not to apply)
-  ctx.sp_key = key;
-  ctx.sp_valid = false;
-  SparseProgram& sp = ctx.sp;
+// Host half of the sparse path: per-entry constants, pilot matrix and the program itself (no device needed).
+// Leaves sp.ok=false when the sparse path does not apply (R<=0, singular pilot).
+void build_sparse_host(const HostPlan& hp, double pilot_f, bool eager, SparseProgram& sp) {
   sp = SparseProgram();
   const HostGather& G = hp.ac;
   const int n_ent = (int)G.ent_col.size();
   sp.ent_alpha.assign(n_ent, 0.0); sp.ent_beta.assign(n_ent, 0.0); sp.ent_gamma.assign(n_ent, 0.0);
   sp.ent_jre.assign(n_ent, 0.0); sp.ent_jim.assign(n_ent, 0.0);
   for (int e = 0; e < hp.n_ac_elem; ++e)
-    if (hp.meta[e].x == ELEM_R && !(hp.values[hp.meta[e].y] > 0)) return SPICEY_SUCCESS;  // R<=0: dense kernel reports it
+    if (hp.meta[e].x == ELEM_R && !(hp.values[hp.meta[e].y] > 0)) return;  // R<=0: dense kernel reports it
   for (int en = 0; en < n_ent; ++en) {
     for (int c = G.ent_ptr[en]; c < G.ent_ptr[en + 1]; ++c) {
       const int w = G.contrib[c], src = (w >> 1) & 3, idx = w >> 3;
@@ -454,6 +458,18 @@ int prepare_sparse(DeviceCtx& ctx, const HostPlan& hp, double pilot_f, bool eage
   const int kFastSlots = 12;  // 12 x 16 B x 128 threads = 24 KiB per CTA, 8 CTAs per SM
   // sweep mode: entry values differ per instance, so no constants are materialised (n_class = 0)
   build_sparse_program(pin, sp, kFastSlots, &entry_class, eager ? 0 : n_class);
+}
+
+// Builds (or reuses) the sparse program of this topology on ctx.  pilot_f: a representative frequency.
+// Returns SPICEY_SUCCESS with ctx.sp_valid=false when the sparse path does not apply.
+int prepare_sparse(DeviceCtx& ctx, const HostPlan& hp, double pilot_f, bool eager, cudaStream_t stream) {
+  const uint64_t key = plan_key(hp) ^ (eager ? 0x9e3779b97f4a7c15ull : 0ull);
+  if (ctx.sp_key == key) return SPICEY_SUCCESS;  // cached (valid or known not to apply)
+  ctx.sp_key = key;
+  ctx.sp_valid = false;
+  SparseProgram& sp = ctx.sp;
+  build_sparse_host(hp, pilot_f, eager, sp);
+  const int n_ent = (int)hp.ac.ent_col.size();
   ctx.sp_eager = eager;
   if (!sp.ok) return SPICEY_SUCCESS;
   // Workspace stride: the resident grid the workspace is sized for (offsets are baked into the program).
@@ -530,34 +546,51 @@ int launch_ac_dense(DeviceCtx& ctx, const HostPlan& hp, const DevPlan& dp, const
 constexpr size_t kJitMaxOps = 6000;          // larger programs stay on the interpreter (compile time)
 constexpr long long kJitMinPoints = 200000;  // below this the ~4 s compile does not pay off (unless forced)
 
-// Compiles (once per topology and handle) the straight-line kernel of the cached sparse program.
-// Returns true when ctx.sp_jit_kernel is usable.
-bool ensure_jit(DeviceCtx& ctx, const HostPlan& hp) {
-  if (ctx.sp_jit_key == ctx.sp_key && ctx.sp_jit_kernel) return true;
-  if (ctx.sp_jit_key == ctx.sp_key && ctx.sp_jit_failed) return false;
-  ctx.sp_jit_key = ctx.sp_key;
-  ctx.sp_jit_failed = true;
-  if (ctx.sp_jit_lib) { cudaLibraryUnload(ctx.sp_jit_lib); ctx.sp_jit_lib = nullptr; ctx.sp_jit_kernel = nullptr; }
-  const double t0 = now_ms();
+void jit_source(const SparseProgram& sp, const HostPlan& hp, const CodegenOptions& opt, std::string& src, CodegenStats& st) {
   std::vector<int> n1(hp.n_ac_elem), n2(hp.n_ac_elem);
   for (int e = 0; e < hp.n_ac_elem; ++e) { n1[e] = hp.ends[e].x; n2[e] = hp.ends[e].y; }
   CodegenInput ci;
-  ci.sp = &ctx.sp; ci.nn = hp.nn; ci.n_ac_elem = hp.n_ac_elem; ci.v_first = hp.off[ELEM_V];
+  ci.sp = &sp; ci.nn = hp.nn; ci.n_ac_elem = hp.n_ac_elem; ci.v_first = hp.off[ELEM_V];
   ci.n1 = n1.data(); ci.n2 = n2.data();
-  const std::string src = generate_sparse_kernel_source(ci);
-  std::vector<char> cubin;
-  if (const char* e = getenv("SPICEY_JIT_MINB")) ctx.sp_jit_minb = std::max(1, atoi(e));
-  if (!jit_compile(src, ctx.sp_jit_minb, cubin, ctx.sp_jit_note)) return false;
-  if (cudaLibraryLoadData(&ctx.sp_jit_lib, cubin.data(), nullptr, nullptr, 0, nullptr, nullptr, 0) != cudaSuccess ||
-      cudaLibraryGetKernel(&ctx.sp_jit_kernel, ctx.sp_jit_lib, "spicey_sparse_jit") != cudaSuccess) {
-    ctx.sp_jit_note = std::string("loading the compiled kernel failed: ") + cudaGetErrorString(cudaGetLastError());
-    ctx.sp_jit_kernel = nullptr;
-    return false;
+  src = generate_sparse_kernel_source(ci, opt, &st);
+}
+
+// Compiles (once per topology, handle and variant) the straight-line kernel of the cached sparse program.
+// Returns the usable variant or nullptr.
+DeviceCtx::JitVariant* ensure_jit(DeviceCtx& ctx, const HostPlan& hp, bool with_ielem, bool bulk) {
+  DeviceCtx::JitVariant& jv = ctx.sp_jit[(with_ielem ? 1 : 0) | (bulk ? 2 : 0)];
+  if (jv.key == ctx.sp_key) return jv.failed ? nullptr : &jv;
+  jv.key = ctx.sp_key;
+  jv.failed = true;
+  if (jv.lib) { cudaLibraryUnload(jv.lib); jv.lib = nullptr; jv.kernel = nullptr; }
+  const double t0 = now_ms();
+  if (const char* e = getenv("SPICEY_JIT_CFG")) {
+    int b = 0, m = 0, sl = 0, rg = ctx.sp_jit_ring, sy = ctx.sp_jit_sync;
+    if (sscanf(e, "%d,%d,%d,%d,%d", &b, &m, &sl, &rg, &sy) >= 3 && b >= 32 && b <= 1024 && b % 32 == 0 && m >= 1 && sl >= 0) {
+      ctx.sp_jit_block = b; ctx.sp_jit_minb = m; ctx.sp_jit_slots = sl; ctx.sp_jit_ring = rg; ctx.sp_jit_sync = sy;
+    }
   }
-  ctx.sp_jit_failed = false;
+  CodegenOptions opt;
+  opt.block = ctx.sp_jit_block; opt.min_blocks = ctx.sp_jit_minb; opt.with_ielem = with_ielem;
+  opt.bulk_store = bulk && ctx.sp_jit_ring > 0; opt.ring_slots = ctx.sp_jit_ring; opt.sync_every = ctx.sp_jit_sync;
+  opt.smem_slots = std::min<int>(ctx.sp_jit_slots, (int)((size_t)(227 * 1024 / opt.min_blocks - 1024) / ((size_t)opt.block * 16)));
+  std::string src;
+  CodegenStats st;
+  jit_source(ctx.sp, hp, opt, src, st);
+  std::vector<char> cubin;
+  if (!jit_compile(src, cubin, ctx.sp_jit_note)) return nullptr;
+  if (cudaLibraryLoadData(&jv.lib, cubin.data(), nullptr, nullptr, 0, nullptr, nullptr, 0) != cudaSuccess ||
+      cudaLibraryGetKernel(&jv.kernel, jv.lib, "spicey_sparse_jit") != cudaSuccess ||
+      cudaFuncSetAttribute((const void*)jv.kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)st.smem_bytes) != cudaSuccess) {
+    ctx.sp_jit_note = std::string("loading the compiled kernel failed: ") + cudaGetErrorString(cudaGetLastError());
+    jv.kernel = nullptr;
+    return nullptr;
+  }
+  jv.smem_bytes = st.smem_bytes;
+  jv.failed = false;
   ctx.sp_jit_compile_ms = now_ms() - t0;
   ctx.sp_jit_note = "ok";
-  return true;
+  return &jv;
 }
 
 int launch_ac_sparse(DeviceCtx& ctx, const HostPlan& hp, const DevPlan& dp, const AcArgs& args, uint32_t flags,
@@ -574,15 +607,17 @@ int launch_ac_sparse(DeviceCtx& ctx, const HostPlan& hp, const DevPlan& dp, cons
   CUDA_TRY(cudaMemsetAsync(fb_count, 0, sizeof(int), stream));
   const bool want_jit = !ctx.sp_eager && !(flags & SPICEY_FLAG_NO_JIT) && ctx.sp.code.size() <= kJitMaxOps &&
                         (args.p_count >= kJitMinPoints || (flags & SPICEY_FLAG_JIT));
-  if (want_jit && ensure_jit(ctx, hp)) {
+  DeviceCtx::JitVariant* jv = (want_jit && args.series_ld < (1ll << 32)) ? ensure_jit(ctx, hp, args.ielem != nullptr, args.series_ld != 0) : nullptr;
+  if (jv) {
     JitArgs j;
     j.freqs = args.freqs + args.p_begin; j.p_count = args.p_count;
     j.x = args.x; j.ielem = args.ielem; j.status = args.status; j.series_ld = args.series_ld;
     j.fb_list = fb_list; j.fb_count = fb_count; j.n = hp.nvar; j.n_ac_elem = hp.n_ac_elem;
-    const long long resident = (long long)ctx.sm_count * ctx.sp_jit_minb * block;
-    const unsigned jgrid = (unsigned)(std::min<long long>((args.p_count + block - 1) / block * block, resident) / block);
+    const int jblock = ctx.sp_jit_block;
+    const long long resident = (long long)ctx.sm_count * ctx.sp_jit_minb;
+    const unsigned jgrid = (unsigned)std::min<long long>((args.p_count + jblock - 1) / jblock, resident);
     void* kargs[] = {&j};
-    CUDA_TRY(cudaLaunchKernel((const void*)ctx.sp_jit_kernel, dim3(jgrid), dim3(block), kargs, 0, stream));
+    CUDA_TRY(cudaLaunchKernel((const void*)jv->kernel, dim3(jgrid), dim3(jblock), kargs, jv->smem_bytes, stream));
     if (launches) ++*launches;
     AcArgs d = args;
     d.plist = fb_list;
@@ -852,7 +887,7 @@ void spicey_destroy(spicey_handle* h) {
     Buffer* bufs[] = {&c.plan, &c.scratch, &c.in0, &c.in1, &c.in2, &c.out_x[0], &c.out_x[1], &c.out_i[0],
                       &c.out_i[1], &c.out_s[0], &c.out_s[1], &c.aux0, &c.aux1, &c.sp_blob, &c.sp_work, &c.sp_fb};
     for (Buffer* b : bufs) b->release();
-    if (c.sp_jit_lib) cudaLibraryUnload(c.sp_jit_lib);
+    for (auto& jv : c.sp_jit) if (jv.lib) cudaLibraryUnload(jv.lib);
     for (auto e : c.events) cudaEventDestroy(e);
     cudaStreamDestroy(c.compute);
     cudaStreamDestroy(c.copy);
@@ -891,10 +926,11 @@ void spicey_host_free(void* p) {
 
 int32_t spicey_ac_solve_device(spicey_handle* h, int32_t dev_index, const spicey_elem_table* table,
                                const spicey_sweep* sweep, const double* d_freqs, int64_t n_freq, double* d_x,
-                               double* d_ielem, int32_t* d_status, uint32_t flags, void* stream) {
+                               double* d_ielem, int32_t* d_status, int64_t series_ld, uint32_t flags, void* stream) {
   if (!h) return fail(SPICEY_ERR_INVALID, "handle is NULL");
   if (dev_index < 0 || dev_index >= (int)h->devs.size()) return fail(SPICEY_ERR_INVALID, "dev_index out of range");
   if (!d_freqs || n_freq < 1 || !d_x || !d_status) return fail(SPICEY_ERR_INVALID, "NULL buffer or empty sweep");
+  if (series_ld != 0 && series_ld < (sweep ? sweep->n_inst : 1) * n_freq) return fail(SPICEY_ERR_INVALID, "series_ld smaller than the number of points");
   DeviceCtx& ctx = h->devs[dev_index];
   HostPlan hp;
   int rc = build_plan(table, sweep, hp);
@@ -910,7 +946,7 @@ int32_t spicey_ac_solve_device(spicey_handle* h, int32_t dev_index, const spicey
   AcArgs a;
   a.freqs = d_freqs; a.n_freq = n_freq; a.p_begin = 0; a.p_count = dp.n_inst * n_freq;
   a.x = (double2*)d_x; a.ielem = (double2*)d_ielem; a.status = d_status; a.scratch = nullptr; a.plist = nullptr; a.pcount = nullptr; a.fb_total = nullptr;
-  a.series_ld = (flags & SPICEY_FLAG_SERIES_MAJOR) ? a.p_count : 0;
+  a.series_ld = series_ld ? series_ld : ((flags & SPICEY_FLAG_SERIES_MAJOR) ? a.p_count : 0);
   int tier = 0;
   int64_t launches = 0;
   if ((rc = ctx.sp_fb.ensure(sizeof(long long) * a.p_count + 64))) return rc;
@@ -979,11 +1015,12 @@ int32_t spicey_ac_solve(spicey_handle* h, const spicey_elem_table* table, const 
     }
     const long long cnt = s.hi - s.lo;
     const long long csz = std::min(chunk, cnt);
+    const long long cld = series ? spicey_series_ld(csz) : csz;  // device rows start on 512-byte boundaries
     if ((rc = ctx.sp_fb.ensure(sizeof(long long) * csz + 64))) return rc;
     CUDA_TRY(cudaMemsetAsync(ctx.sp_fb.p, 0, 64, ctx.compute));
     for (int b = 0; b < 2; ++b) {
-      if ((rc = ctx.out_x[b].ensure(xrow * csz))) return rc;
-      if (ielem && (rc = ctx.out_i[b].ensure(irow * csz))) return rc;
+      if ((rc = ctx.out_x[b].ensure(xrow * cld))) return rc;
+      if (ielem && (rc = ctx.out_i[b].ensure(irow * cld))) return rc;
       if ((rc = ctx.out_s[b].ensure(sizeof(int) * csz))) return rc;
     }
     int ci = 0;
@@ -997,18 +1034,18 @@ int32_t spicey_ac_solve(spicey_handle* h, const spicey_elem_table* table, const 
       a.freqs = (const double*)ctx.in0.p; a.n_freq = n_freq; a.p_begin = lo; a.p_count = n;
       a.x = (double2*)ctx.out_x[b].p; a.ielem = ielem ? (double2*)ctx.out_i[b].p : nullptr;
       a.status = (int*)ctx.out_s[b].p; a.scratch = nullptr; a.plist = nullptr; a.pcount = nullptr; a.fb_total = nullptr;
-      a.series_ld = series ? n : 0;
+      a.series_ld = series ? cld : 0;
       CUDA_TRY(cudaEventRecord(ks, ctx.compute));
       rc = launch_ac(ctx, hp, dp, a, flags, ctx.compute, &tier, &launches, freqs[n_freq / 2], true);
       if (rc) return rc;
       CUDA_TRY(cudaEventRecord(ke, ctx.compute));
       CUDA_TRY(cudaStreamWaitEvent(ctx.copy, ke, 0));
       if (series) {  // device chunk [rows][n] -> host [rows][P] at column lo
-        const size_t w = sizeof(double2) * n;
-        CUDA_TRY(cudaMemcpy2DAsync((char*)x + sizeof(double2) * lo, sizeof(double2) * P, a.x, w, w, hp.nvar,
+        const size_t w = sizeof(double2) * n, dpitch = sizeof(double2) * cld;
+        CUDA_TRY(cudaMemcpy2DAsync((char*)x + sizeof(double2) * lo, sizeof(double2) * P, a.x, dpitch, w, hp.nvar,
                                    cudaMemcpyDeviceToHost, ctx.copy));
         if (ielem && hp.n_ac_elem > 0)
-          CUDA_TRY(cudaMemcpy2DAsync((char*)ielem + sizeof(double2) * lo, sizeof(double2) * P, a.ielem, w, w,
+          CUDA_TRY(cudaMemcpy2DAsync((char*)ielem + sizeof(double2) * lo, sizeof(double2) * P, a.ielem, dpitch, w,
                                      hp.n_ac_elem, cudaMemcpyDeviceToHost, ctx.copy));
       } else {
         CUDA_TRY(cudaMemcpyAsync((char*)x + xrow * lo, a.x, xrow * n, cudaMemcpyDeviceToHost, ctx.copy));
@@ -1203,6 +1240,33 @@ int32_t spicey_tran_solve(spicey_handle* h, const spicey_elem_table* table, cons
   h->stats.tier = tier;
   return SPICEY_SUCCESS;
 }
+
+int64_t spicey_debug_sparse_source(const spicey_elem_table* table, double pilot_f, int32_t block, int32_t min_blocks,
+                                   int32_t smem_slots, int32_t with_ielem, char* buf, int64_t cap, int32_t* stats_out) {
+  HostPlan hp;
+  if (build_plan(table, nullptr, hp) != SPICEY_SUCCESS) return -1;
+  SparseProgram sp;
+  build_sparse_host(hp, pilot_f, false, sp);
+  if (!sp.ok) { fail(SPICEY_ERR_UNSUPPORTED, "the sparse path does not apply to this circuit"); return -1; }
+  CodegenOptions opt;
+  opt.block = block; opt.min_blocks = min_blocks; opt.smem_slots = smem_slots; opt.with_ielem = (with_ielem & 1) != 0;
+  opt.bulk_store = (with_ielem & 2) != 0; opt.ring_slots = std::max(1, (with_ielem >> 8) & 0xff); opt.sync_every = (with_ielem >> 16) & 0xff;
+  std::string src;
+  CodegenStats st;
+  jit_source(sp, hp, opt, src, st);
+  if (stats_out) {
+    stats_out[0] = st.n_saved; stats_out[1] = st.smem_slots; stats_out[2] = st.n_classes; stats_out[3] = (int32_t)sp.code.size();
+    stats_out[4] = (int32_t)sp.n_fma; stats_out[5] = (int32_t)sp.n_div; stats_out[6] = st.n_groups; stats_out[7] = st.n_waits;
+  }
+  if (buf && cap > 0) {
+    const size_t n = std::min<size_t>(src.size(), (size_t)cap - 1);
+    memcpy(buf, src.data(), n);
+    buf[n] = 0;
+  }
+  return (int64_t)src.size() + 1;
+}
+
+int64_t spicey_series_ld(int64_t n_points) { return (n_points + 31) / 32 * 32; }
 
 int32_t spicey_measure_fp64_peak(spicey_handle* h, int32_t dev_index, double* gflops_out) {
   if (!h || !gflops_out) return fail(SPICEY_ERR_INVALID, "NULL argument");

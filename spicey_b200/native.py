@@ -24,6 +24,7 @@ EXPORTS = [
     "spicey_native_abi_version", "spicey_device_count", "spicey_last_error", "spicey_create",
     "spicey_destroy", "spicey_get_stats", "spicey_host_alloc", "spicey_host_free", "spicey_ac_solve",
     "spicey_ac_solve_device", "spicey_tran_solve", "spicey_tran_solve_device", "spicey_measure_fp64_peak",
+    "spicey_debug_sparse_source", "spicey_series_ld",
 ]
 
 _ip = C.POINTER(C.c_int32)
@@ -86,7 +87,9 @@ def load_library(path: Optional[str] = None):
     lib.spicey_ac_solve.restype = C.c_int32
     lib.spicey_ac_solve.argtypes = [vp, tb, sw, vp, C.c_int64, vp, vp, vp, C.c_uint32]
     lib.spicey_ac_solve_device.restype = C.c_int32
-    lib.spicey_ac_solve_device.argtypes = [vp, C.c_int32, tb, sw, vp, C.c_int64, vp, vp, vp, C.c_uint32, vp]
+    lib.spicey_ac_solve_device.argtypes = [vp, C.c_int32, tb, sw, vp, C.c_int64, vp, vp, vp, C.c_int64, C.c_uint32, vp]
+    lib.spicey_series_ld.restype = C.c_int64
+    lib.spicey_series_ld.argtypes = [C.c_int64]
     lib.spicey_tran_solve.restype = C.c_int32
     lib.spicey_tran_solve.argtypes = [vp, tb, sw, C.c_double, C.c_int64, vp, vp, vp, vp, vp, vp, vp, vp, C.c_uint32]
     lib.spicey_tran_solve_device.restype = C.c_int32
@@ -94,9 +97,29 @@ def load_library(path: Optional[str] = None):
                                              vp, vp, C.c_uint32, vp]
     lib.spicey_measure_fp64_peak.restype = C.c_int32
     lib.spicey_measure_fp64_peak.argtypes = [vp, C.c_int32, _dp]
+    lib.spicey_debug_sparse_source.restype = C.c_int64
+    lib.spicey_debug_sparse_source.argtypes = [tb, C.c_double, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_char_p,
+                                               C.c_int64, _ip]
     if path == _build.LIB_PATH:
         _LIB = lib
     return lib
+
+
+def sparse_kernel_source(table: "ElemTable", pilot_f: float, block=160, min_blocks=1, smem_slots=90, with_ielem=True,
+                         bulk=True, ring=6, sync=0):
+    """CUDA source of the compiled straight-line sparse kernel (tier 5) for a circuit, plus the generator's
+    statistics.  Host-only tooling: lets the generated code be inspected / compiled offline with nvcc."""
+    lib = load_library()
+    st = (C.c_int32 * 8)()
+    ts = table.struct()
+    mode = int(with_ielem) | (2 if bulk else 0) | (ring << 8) | (sync << 16)
+    need = lib.spicey_debug_sparse_source(C.byref(ts), pilot_f, block, min_blocks, smem_slots, mode, None, 0, st)
+    if need < 0:
+        raise NativeError(-1, (lib.spicey_last_error() or b"").decode())
+    buf = C.create_string_buffer(need)
+    lib.spicey_debug_sparse_source(C.byref(ts), pilot_f, block, min_blocks, smem_slots, mode, buf, need, st)
+    keys = ("saved_values", "smem_slots", "classes", "micro_ops", "cfma", "reciprocals", "bulk_groups", "staging_waits")
+    return buf.value.decode(), dict(zip(keys, list(st)))
 
 
 def _check(lib, rc):
@@ -160,7 +183,7 @@ class Engine:
 
     def __init__(self, devices: Optional[Sequence[int]] = None, lib_path: Optional[str] = None):
         self.lib = load_library(lib_path)
-        if self.lib.spicey_native_abi_version() != 1:
+        if self.lib.spicey_native_abi_version() != 2:
             raise NativeError(ERR_INVALID, "ABI version mismatch")
         self._h = C.c_void_p()
         arr = None if devices is None else np.ascontiguousarray(devices, dtype=np.int32)
@@ -244,12 +267,17 @@ class Engine:
     # -- device-resident entry points (raw device pointers as ints) ----------------
     def ac_solve_device(self, table: ElemTable, d_freqs: int, n_freq: int, d_x: int, d_ielem: Optional[int],
                         d_status: int, sweep: Optional[Sweep] = None, d_var_values: Optional[int] = None,
-                        flags=0, stream: int = 0, dev_index: int = 0):
+                        flags=0, stream: int = 0, dev_index: int = 0, series_ld: int = 0):
+        """series_ld != 0: series-major results x[Nvar][series_ld], ielem[nAc][series_ld] (see series_ld())."""
         ts = table.struct()
         ss = sweep.struct(d_var_values) if sweep else None
         _check(self.lib, self.lib.spicey_ac_solve_device(
             self._h, dev_index, C.byref(ts), C.byref(ss) if ss else None, d_freqs, n_freq, d_x, d_ielem, d_status,
-            flags, stream))
+            series_ld, flags, stream))
+
+    def series_ld(self, n_points: int) -> int:
+        """Recommended leading dimension of a series-major device result (512-byte aligned rows)."""
+        return int(self.lib.spicey_series_ld(n_points))
 
     def tran_solve_device(self, table: ElemTable, dt: float, steps: int, d_vsrc: Optional[int], vsrc_mask,
                           d_state0: Optional[int], d_v: int, d_ielem: Optional[int], d_state_out: Optional[int],
