@@ -125,8 +125,11 @@ enum {
   SPICEY_TIER_CTA_GMEM = 3,  /* one CTA per system, matrix in an L2-resident global scratch */
   SPICEY_TIER_SPARSE = 4,    /* one thread per system, static-pivot sparse LU program verified per
                                 system (interpreted), dense pivoting kernel as fallback */
-  SPICEY_TIER_SPARSE_JIT = 5 /* the same program written out as a straight-line sm_100a kernel and compiled
+  SPICEY_TIER_SPARSE_JIT = 5, /* the same program written out as a straight-line sm_100a kernel and compiled
                                 with NVRTC once per topology (large single-instance sweeps, small programs) */
+  SPICEY_TIER_TRAN_JIT = 6   /* transient: the persistent time loop written out for the netlist at hand (every
+                                element a few named registers) and compiled with NVRTC once per topology;
+                                Nvar <= 8, batches of >= 2e6 instance-steps or SPICEY_FLAG_JIT */
 };
 
 typedef struct spicey_handle spicey_handle;
@@ -215,8 +218,8 @@ enum {
   SPICEY_FLAG_GENERIC_THREAD = 32u, /* testing: transient thread tier without the register-resident kernel */
   SPICEY_FLAG_SERIES_MAJOR = 64u,  /* AC: x is [Nvar][P] and ielem [nAc][P] (one contiguous series per node /
                                       element, coalesced stores on the device) instead of [P][Nvar] / [P][nAc] */
-  SPICEY_FLAG_JIT = 128u,          /* compile the straight-line sparse kernel even for batches below 200,000 points */
-  SPICEY_FLAG_NO_JIT = 256u        /* never compile: always interpret the sparse program */
+  SPICEY_FLAG_JIT = 128u,          /* compile the per-topology kernel (AC tier 5, TRAN tier 6) even for small batches */
+  SPICEY_FLAG_NO_JIT = 256u        /* never compile: interpreted sparse program (AC), generic kernels (TRAN) */
 };
 
 /* Tooling (no device needed): writes the CUDA source of the compiled straight-line sparse kernel
@@ -227,6 +230,11 @@ enum {
  * bulk (series-major) stores, bits 8-15 staging ring slots, bits 16-23 __syncthreads period. */
 int64_t spicey_debug_sparse_source(const spicey_elem_table* table, double pilot_f, int32_t block, int32_t min_blocks,
                                    int32_t smem_slots, int32_t with_ielem, char* buf, int64_t cap, int32_t* stats_out);
+
+/* Tooling (no device needed): CUDA source of the compiled transient kernel (tier 6) for this element
+ * table and sweep (which value slots vary per instance); returns the size needed or -1. */
+int64_t spicey_debug_tran_source(const spicey_elem_table* table, const spicey_sweep* sweep, int32_t with_ielem,
+                                 char* buf, int64_t cap);
 
 /* Measures this GPU's FP64 FMA peak with a register-only DFMA loop (GFLOP/s), the
  * denominator the FP64-bound roofline is reported against. */

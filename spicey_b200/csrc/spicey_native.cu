@@ -22,6 +22,7 @@
 #include "ac_kernels.cuh"
 #include "ac_sparse.cuh"
 #include "sparse_codegen.h"
+#include "tran_codegen.h"
 #include "tran_kernels.cuh"
 #include "tran_small.cuh"
 
@@ -237,6 +238,7 @@ struct DeviceCtx {
   int sp_jit_block = 192, sp_jit_minb = 1, sp_jit_slots = 75, sp_jit_ring = 0, sp_jit_sync = 4;
   double sp_jit_compile_ms = 0;
   std::string sp_jit_note;
+  JitVariant tr_jit[2];   // compiled transient kernel of the last topology: [0] without, [1] with element currents
   std::vector<int4> sp_code_scaled;  // program with slot operands scaled by the pool strides
   bool sp_valid = false;
   std::vector<cudaEvent_t> events;
@@ -741,10 +743,74 @@ int launch_ac(DeviceCtx& ctx, const HostPlan& hp, const DevPlan& dp, const AcArg
   return launch_ac_dense(ctx, hp, dp, args, flags, stream, tier_out, launches);
 }
 
+struct TranJitArgs {   // must match tran_jit_prelude()
+  const double* var_values; long long n_inst;
+  double dt; long long steps;
+  const double* vsrc; unsigned vmask;
+  const double* state0; long long inst0; long long n_local;
+  double* v; double* ielem; double* state_out; int* iters; int* status;
+};
+constexpr int kTranJitBlock = 64;                 // 65,536 instances -> 1024 CTAs: 6.9 per SM, 1 % tail
+constexpr long long kTranJitMinSteps = 2000000;   // instance-steps below which the ~1 s compile does not pay off
+
+void tran_jit_source(const HostPlan& hp, bool with_ielem, std::string& src) {
+  std::vector<int> n1(hp.n_elem), n2(hp.n_elem), c1(hp.n_elem), c2(hp.n_elem), vi(hp.n_elem);
+  for (int e = 0; e < hp.n_elem; ++e) {
+    n1[e] = hp.ends[e].x; n2[e] = hp.ends[e].y; c1[e] = hp.ends[e].z; c2[e] = hp.ends[e].w; vi[e] = hp.meta[e].y;
+  }
+  TranCodegenInput in;
+  in.nn = hp.nn; in.nV = hp.nV; in.nvar = hp.nvar; in.n_elem = hp.n_elem; in.n_state = hp.n_state;
+  in.off = hp.off; in.n1 = n1.data(); in.n2 = n2.data(); in.nc1 = c1.data(); in.nc2 = c2.data();
+  in.value_idx = vi.data(); in.state_idx = hp.state_idx.data(); in.values = hp.values.data();
+  in.var_of_slot = hp.var_of_slot.data(); in.with_ielem = with_ielem; in.block = kTranJitBlock;
+  src = generate_tran_kernel_source(in);
+}
+
+DeviceCtx::JitVariant* ensure_tran_jit(DeviceCtx& ctx, const HostPlan& hp, bool with_ielem) {
+  DeviceCtx::JitVariant& jv = ctx.tr_jit[with_ielem ? 1 : 0];
+  uint64_t key = plan_key(hp);
+  key = fnv1a(key, hp.var_of_slot.data(), sizeof(int) * hp.var_of_slot.size());
+  key = fnv1a(key, hp.state_idx.data(), sizeof(int) * hp.state_idx.size());
+  if (!key) key = 1;
+  if (jv.key == key) return jv.failed ? nullptr : &jv;
+  jv.key = key;
+  jv.failed = true;
+  if (jv.lib) { cudaLibraryUnload(jv.lib); jv.lib = nullptr; jv.kernel = nullptr; }
+  std::string src;
+  tran_jit_source(hp, with_ielem, src);
+  std::vector<char> cubin;
+  if (!jit_compile(src, cubin, ctx.sp_jit_note)) return nullptr;
+  if (cudaLibraryLoadData(&jv.lib, cubin.data(), nullptr, nullptr, 0, nullptr, nullptr, 0) != cudaSuccess ||
+      cudaLibraryGetKernel(&jv.kernel, jv.lib, "spicey_tran_jit") != cudaSuccess) {
+    ctx.sp_jit_note = std::string("loading the compiled transient kernel failed: ") + cudaGetErrorString(cudaGetLastError());
+    jv.kernel = nullptr;
+    return nullptr;
+  }
+  jv.failed = false;
+  return &jv;
+}
+
 int launch_tran(DeviceCtx& ctx, const HostPlan& hp, const DevPlan& dp, const TranArgs& args, uint32_t flags,
                 cudaStream_t stream, int* tier_out, int64_t* launches) {
   if (args.n_local <= 0) return SPICEY_SUCCESS;
   const bool strict = flags & SPICEY_FLAG_STRICT;
+  // Compiled per-topology kernel (tran_codegen.h): small systems, batches large enough to pay for the compile.
+  if (!strict && !(flags & (SPICEY_FLAG_FORCE_CTA | SPICEY_FLAG_FORCE_GMEM | SPICEY_FLAG_GENERIC_THREAD | SPICEY_FLAG_NO_JIT)) &&
+      hp.nvar <= 8 && hp.n_elem <= 48 && hp.nV <= 32 &&
+      ((flags & SPICEY_FLAG_JIT) || args.n_local * (args.steps + 1) >= kTranJitMinSteps)) {
+    if (DeviceCtx::JitVariant* jv = ensure_tran_jit(ctx, hp, args.ielem != nullptr)) {
+      TranJitArgs j;
+      j.var_values = dp.var_values; j.n_inst = dp.n_inst; j.dt = args.dt; j.steps = args.steps;
+      j.vsrc = args.vsrc; j.vmask = args.vmask_bits; j.state0 = args.state0; j.inst0 = args.inst0; j.n_local = args.n_local;
+      j.v = args.v; j.ielem = args.ielem; j.state_out = args.state_out; j.iters = args.iters; j.status = args.status;
+      void* kargs[] = {&j};
+      const unsigned grid = (unsigned)((args.n_local + kTranJitBlock - 1) / kTranJitBlock);
+      CUDA_TRY(cudaLaunchKernel((const void*)jv->kernel, dim3(grid), dim3(kTranJitBlock), kargs, 0, stream));
+      if (tier_out) *tier_out = SPICEY_TIER_TRAN_JIT;
+      if (launches) ++*launches;
+      return SPICEY_SUCCESS;
+    }
+  }
   const int n_ent = (int)hp.tran.ent_col.size(), n_con = (int)hp.tran.contrib.size();
   // Register-resident small-system kernel (Nvar <= 6).
   if (!(flags & (SPICEY_FLAG_FORCE_CTA | SPICEY_FLAG_FORCE_GMEM | SPICEY_FLAG_GENERIC_THREAD)) && hp.nvar <= 6) {
@@ -888,6 +954,7 @@ void spicey_destroy(spicey_handle* h) {
                       &c.out_i[1], &c.out_s[0], &c.out_s[1], &c.aux0, &c.aux1, &c.sp_blob, &c.sp_work, &c.sp_fb};
     for (Buffer* b : bufs) b->release();
     for (auto& jv : c.sp_jit) if (jv.lib) cudaLibraryUnload(jv.lib);
+    for (auto& jv : c.tr_jit) if (jv.lib) cudaLibraryUnload(jv.lib);
     for (auto e : c.events) cudaEventDestroy(e);
     cudaStreamDestroy(c.compute);
     cudaStreamDestroy(c.copy);
@@ -1115,6 +1182,8 @@ int32_t spicey_tran_solve_device(spicey_handle* h, int32_t dev_index, const spic
   dp.var_values = sweep ? sweep->var_values : nullptr;
   TranArgs a;
   a.dt = dt; a.steps = steps; a.vsrc = d_vsrc; a.vsrc_mask = (const int*)ctx.aux0.p; a.state0 = d_state0;
+  a.vmask_bits = 0;
+  for (int k = 0; k < hp.nV && k < 32; ++k) a.vmask_bits |= mask[k] ? (1u << k) : 0u;
   a.inst0 = 0; a.n_local = dp.n_inst; a.v = d_v; a.ielem = d_ielem; a.state_out = d_state_out;
   a.iters = d_iters; a.status = d_status;
   int tier = 0;
@@ -1167,6 +1236,8 @@ int32_t spicey_tran_solve(spicey_handle* h, const spicey_elem_table* table, cons
     dp.n_inst = n_inst; dp.n_var = n_var;
     TranArgs a;
     a.dt = dt; a.steps = steps; a.vsrc = nullptr; a.vsrc_mask = (const int*)ctx.aux0.p; a.state0 = nullptr;
+    a.vmask_bits = 0;
+    for (int k = 0; k < hp.nV && k < 32; ++k) a.vmask_bits |= mask[k] ? (1u << k) : 0u;
     if (any_wave) {
       size_t b = sizeof(double) * (size_t)hp.nV * S1;
       if ((rc = ctx.in0.ensure(b))) return rc;
@@ -1258,6 +1329,21 @@ int64_t spicey_debug_sparse_source(const spicey_elem_table* table, double pilot_
     stats_out[0] = st.n_saved; stats_out[1] = st.smem_slots; stats_out[2] = st.n_classes; stats_out[3] = (int32_t)sp.code.size();
     stats_out[4] = (int32_t)sp.n_fma; stats_out[5] = (int32_t)sp.n_div; stats_out[6] = st.n_groups; stats_out[7] = st.n_waits;
   }
+  if (buf && cap > 0) {
+    const size_t n = std::min<size_t>(src.size(), (size_t)cap - 1);
+    memcpy(buf, src.data(), n);
+    buf[n] = 0;
+  }
+  return (int64_t)src.size() + 1;
+}
+
+int64_t spicey_debug_tran_source(const spicey_elem_table* table, const spicey_sweep* sweep, int32_t with_ielem,
+                                 char* buf, int64_t cap) {
+  HostPlan hp;
+  if (build_plan(table, sweep, hp) != SPICEY_SUCCESS) return -1;
+  if (hp.nvar > 8 || hp.n_elem > 48 || hp.nV > 32) { fail(SPICEY_ERR_UNSUPPORTED, "the compiled transient kernel covers Nvar <= 8"); return -1; }
+  std::string src;
+  tran_jit_source(hp, with_ielem != 0, src);
   if (buf && cap > 0) {
     const size_t n = std::min<size_t>(src.size(), (size_t)cap - 1);
     memcpy(buf, src.data(), n);

@@ -28,6 +28,7 @@ struct TranArgs {
   long long steps;
   const double* vsrc;       // [nV][steps+1] or null
   const int* vsrc_mask;     // [nV]
+  unsigned vmask_bits;      // the same mask as bits (first 32 sources), for the compiled kernel
   const double* state0;     // [n_state][n_inst] or null
   long long inst0;          // global index of local instance 0 (for sweep values / state0)
   long long n_local;        // instances handled by this launch

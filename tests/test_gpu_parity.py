@@ -254,14 +254,17 @@ GOLDEN_TRAN = ["transient01_rc_pulse", "two_probes", "switch_vt_vh", "vswitch_pw
 @pytest.mark.parametrize("name", GOLDEN_TRAN)
 @pytest.mark.parametrize("flags", [0, native.FLAG_STRICT, native.FLAG_GENERIC_THREAD,
                                    native.FLAG_GENERIC_THREAD | native.FLAG_STRICT, native.FLAG_FORCE_CTA,
-                                   native.FLAG_FORCE_GMEM])
+                                   native.FLAG_FORCE_GMEM, native.FLAG_JIT])
 def test_tran_reference_netlists(eng, golden, name, flags):
-    """Every transient netlist of the reference's tests through the drop-in simulateTRAN, all tiers."""
+    """Every transient netlist of the reference's tests through the drop-in simulateTRAN, all tiers
+    (FLAG_JIT: the kernel compiled for the netlist, tier 6)."""
     import spicey_b200 as sp
     text = golden(name)["netlist"]
     ref = o.simulate(text)
     ck = parse_netlist(text)
     got = sp.simulateTRAN(ck, flags=flags)
+    if flags == native.FLAG_JIT:
+        assert eng.stats()["tier"] == native.TIER_TRAN_JIT
     assert got["times"] == ref["tran"]["times"]
     assert list(got["nodeVoltages"].keys()) == list(ref["tran"]["nodeVoltages"].keys())
     assert list(got["elementCurrents"].keys()) == list(ref["tran"]["elementCurrents"].keys())
@@ -303,12 +306,14 @@ def tran_batch_case(eng, text, n_inst, overrides, flags=0):
     return got, v, ie, iters, st
 
 
-@pytest.mark.parametrize("flags", [0, native.FLAG_GENERIC_THREAD, native.FLAG_FORCE_CTA])
+@pytest.mark.parametrize("flags", [0, native.FLAG_GENERIC_THREAD, native.FLAG_FORCE_CTA, native.FLAG_JIT])
 def test_tran_rlc_tank_monte_carlo_slice(eng, flags):
     """cfg 3 on its first 512 instances: steps = 1001 (hazard H2), +-5 % R/L/C."""
     n = 64 if flags == native.FLAG_FORCE_CTA else 512
     ov = {k: v[:n] for k, v in w.rlc_tank_overrides(65536).items()}
     got, v, ie, iters, st = tran_batch_case(eng, w.RLC_TANK, n, ov, flags)
+    assert eng.stats()["tier"] == (native.TIER_TRAN_JIT if flags == native.FLAG_JIT else
+                                   native.TIER_CTA_SMEM if flags == native.FLAG_FORCE_CTA else native.TIER_THREAD)
     assert got["steps"] == 1001 and got["v"].shape == (1002, 2, n)
     assert got["status"].max() == 0 and st.max() == 0
     assert np.array_equal(got["iters"].T, iters)
@@ -318,7 +323,7 @@ def test_tran_rlc_tank_monte_carlo_slice(eng, flags):
     assert np.max(np.abs(got["ielem"] - ref_i)) <= TRAN_TOL * np.max(np.abs(ref_i))
 
 
-@pytest.mark.parametrize("flags", [0, native.FLAG_GENERIC_THREAD, native.FLAG_FORCE_CTA])
+@pytest.mark.parametrize("flags", [0, native.FLAG_GENERIC_THREAD, native.FLAG_FORCE_CTA, native.FLAG_JIT])
 def test_tran_rectifier_sweep_slice(eng, flags):
     """cfg 5 (diode, single linearisation per step) on 400 instances spread over the sweep."""
     n = 48 if flags == native.FLAG_FORCE_CTA else 400
@@ -326,6 +331,8 @@ def test_tran_rectifier_sweep_slice(eng, flags):
     pick = np.linspace(0, 99999, n).astype(int)
     ov = {k: v[pick] for k, v in full.items()}
     got, v, ie, iters, st = tran_batch_case(eng, w.RECTIFIER, n, ov, flags)
+    if flags == native.FLAG_JIT:
+        assert eng.stats()["tier"] == native.TIER_TRAN_JIT
     assert got["steps"] == 3000
     assert got["status"].max() == 0 and st.max() == 0
     ref_v = np.transpose(v, (1, 2, 0))
