@@ -184,6 +184,38 @@ int build_plan(const spicey_elem_table* tb, const spicey_sweep* sw, HostPlan& hp
   return SPICEY_SUCCESS;
 }
 
+uint64_t fnv1a_raw(uint64_t h, const void* data, size_t n) {
+  const unsigned char* p = (const unsigned char*)data;
+  for (size_t i = 0; i < n; ++i) { h ^= p[i]; h *= 1099511628211ull; }
+  return h;
+}
+
+// Key of the raw inputs build_plan() reads (everything but the per-instance values themselves).
+uint64_t table_key(const spicey_elem_table* tb, const spicey_sweep* sw) {
+  if (!tb || tb->n_elem < 0 || tb->n_values < 0 || (tb->n_elem > 0 && (!tb->type || !tb->n1 || !tb->n2 || !tb->value_idx || !tb->values)))
+    return 0;  // let build_plan produce the error
+  uint64_t h = 1469598103934665603ull;
+  const int hdr[3] = {tb->n_nodes, tb->n_elem, tb->n_values};
+  h = fnv1a_raw(h, hdr, sizeof hdr);
+  h = fnv1a_raw(h, tb->type, sizeof(int32_t) * tb->n_elem);
+  h = fnv1a_raw(h, tb->n1, sizeof(int32_t) * tb->n_elem);
+  h = fnv1a_raw(h, tb->n2, sizeof(int32_t) * tb->n_elem);
+  if (tb->nc1) h = fnv1a_raw(h, tb->nc1, sizeof(int32_t) * tb->n_elem);
+  if (tb->nc2) h = fnv1a_raw(h, tb->nc2, sizeof(int32_t) * tb->n_elem);
+  h = fnv1a_raw(h, tb->value_idx, sizeof(int32_t) * tb->n_elem);
+  h = fnv1a_raw(h, tb->values, sizeof(double) * tb->n_values);
+  if (sw) {
+    if (sw->n_inst < 1 || sw->n_var < 0 || (sw->n_var > 0 && (!sw->var_slot || !sw->var_values))) return 0;
+    const int nv = sw->n_var;
+    h = fnv1a_raw(h, &nv, sizeof nv);
+    if (nv > 0) h = fnv1a_raw(h, sw->var_slot, sizeof(int32_t) * nv);
+  } else {
+    const int nv = -1;
+    h = fnv1a_raw(h, &nv, sizeof nv);
+  }
+  return h ? h : 1;
+}
+
 // ---------------------------------------------------------------------------------
 // Device context
 struct Buffer {
@@ -238,6 +270,8 @@ struct DeviceCtx {
   int sp_jit_block = 192, sp_jit_minb = 1, sp_jit_slots = 75, sp_jit_ring = 0, sp_jit_sync = 4;
   double sp_jit_compile_ms = 0;
   std::string sp_jit_note;
+  uint64_t plan_up_key = 0;   // plan currently resident in `plan` (its device pointers are in plan_dp)
+  DevPlan plan_dp;
   JitVariant tr_jit[2];   // compiled transient kernel of the last topology: [0] without, [1] with element currents
   std::vector<int4> sp_code_scaled;  // program with slot operands scaled by the pool strides
   bool sp_valid = false;
@@ -260,8 +294,19 @@ template <typename T> size_t push_blob(std::vector<unsigned char>& blob, const s
 }
 
 // Uploads the plan into ctx.plan on `stream` and fills the device-pointer view.
+uint64_t fnv1a(uint64_t h, const void* data, size_t n);
+uint64_t plan_key(const HostPlan& hp);
+
 int upload_plan(DeviceCtx& ctx, const HostPlan& hp, cudaStream_t stream, DevPlan& dp,
                 std::vector<unsigned char>& blob) {
+  uint64_t key = plan_key(hp);
+  key = fnv1a(key, hp.var_of_slot.data(), sizeof(int) * hp.var_of_slot.size());
+  if (!key) key = 1;
+  if (ctx.plan_up_key == key) {  // same netlist as the previous call on this device: nothing to copy
+    dp = ctx.plan_dp;
+    return SPICEY_SUCCESS;
+  }
+  ctx.plan_up_key = 0;
   blob.clear();
   size_t o_ends = push_blob(blob, hp.ends), o_meta = push_blob(blob, hp.meta);
   size_t o_sidx = push_blob(blob, hp.state_idx), o_val = push_blob(blob, hp.values);
@@ -296,6 +341,8 @@ int upload_plan(DeviceCtx& ctx, const HostPlan& hp, cudaStream_t stream, DevPlan
     gp[k]->contrib = (const int*)(b + o[k][3]);
     gp[k]->rowmask = (const unsigned*)(b + o[k][4]);
   }
+  ctx.plan_dp = dp;
+  ctx.plan_up_key = key;
   return SPICEY_SUCCESS;
 }
 
@@ -307,10 +354,25 @@ struct spicey_handle {
   std::vector<DeviceCtx> devs;
   spicey_stats stats;
   std::vector<unsigned char> blob;  // plan staging (kept alive until the stream has consumed it)
+  // host plan of the last element table: repeated calls on one netlist (a bench loop, chunked sweeps, a
+  // Monte-Carlo driver) skip the rebuild (~0.1 ms of std::map work that otherwise sits in front of every launch)
+  uint64_t hp_key = 0;
+  HostPlan hp;
 };
 
 namespace {
 
+// build_plan() through the handle's one-entry cache.
+int cached_plan(spicey_handle* h, const spicey_elem_table* table, const spicey_sweep* sweep) {
+  const uint64_t key = table_key(table, sweep);
+  if (key && key == h->hp_key) return SPICEY_SUCCESS;
+  h->hp_key = 0;
+  h->hp = HostPlan();
+  int rc = build_plan(table, sweep, h->hp);
+  if (rc) return rc;
+  h->hp_key = key;
+  return SPICEY_SUCCESS;
+}
 
 double now_ms();
 
@@ -796,7 +858,7 @@ int launch_tran(DeviceCtx& ctx, const HostPlan& hp, const DevPlan& dp, const Tra
   const bool strict = flags & SPICEY_FLAG_STRICT;
   // Compiled per-topology kernel (tran_codegen.h): small systems, batches large enough to pay for the compile.
   if (!strict && !(flags & (SPICEY_FLAG_FORCE_CTA | SPICEY_FLAG_FORCE_GMEM | SPICEY_FLAG_GENERIC_THREAD | SPICEY_FLAG_NO_JIT)) &&
-      hp.nvar <= 8 && hp.n_elem <= 48 && hp.nV <= 32 &&
+      hp.nvar <= 8 && hp.n_elem <= 48 && hp.nV <= 32 && args.n_local < (1ll << 29) &&
       ((flags & SPICEY_FLAG_JIT) || args.n_local * (args.steps + 1) >= kTranJitMinSteps)) {
     if (DeviceCtx::JitVariant* jv = ensure_tran_jit(ctx, hp, args.ielem != nullptr)) {
       TranJitArgs j;
@@ -999,9 +1061,9 @@ int32_t spicey_ac_solve_device(spicey_handle* h, int32_t dev_index, const spicey
   if (!d_freqs || n_freq < 1 || !d_x || !d_status) return fail(SPICEY_ERR_INVALID, "NULL buffer or empty sweep");
   if (series_ld != 0 && series_ld < (sweep ? sweep->n_inst : 1) * n_freq) return fail(SPICEY_ERR_INVALID, "series_ld smaller than the number of points");
   DeviceCtx& ctx = h->devs[dev_index];
-  HostPlan hp;
-  int rc = build_plan(table, sweep, hp);
+  int rc = cached_plan(h, table, sweep);
   if (rc) return rc;
+  const HostPlan& hp = h->hp;
   CUDA_TRY(cudaSetDevice(ctx.dev));
   cudaStream_t st = (cudaStream_t)stream;
   DevPlan dp;
@@ -1036,9 +1098,9 @@ int32_t spicey_ac_solve(spicey_handle* h, const spicey_elem_table* table, const 
   if (!h) return fail(SPICEY_ERR_INVALID, "handle is NULL");
   if (!freqs || n_freq < 1 || !x || !status) return fail(SPICEY_ERR_INVALID, "NULL buffer or empty sweep");
   const double t0 = now_ms();
-  HostPlan hp;
-  int rc = build_plan(table, sweep, hp);
+  int rc = cached_plan(h, table, sweep);
   if (rc) return rc;
+  const HostPlan& hp = h->hp;
   const long long n_inst = sweep ? sweep->n_inst : 1;
   const int n_var = sweep ? sweep->n_var : 0;
   const long long P = n_inst * n_freq;
@@ -1161,9 +1223,9 @@ int32_t spicey_tran_solve_device(spicey_handle* h, int32_t dev_index, const spic
   if (dev_index < 0 || dev_index >= (int)h->devs.size()) return fail(SPICEY_ERR_INVALID, "dev_index out of range");
   if (steps < 1 || !d_v || !d_status) return fail(SPICEY_ERR_INVALID, "NULL buffer or steps < 1");
   DeviceCtx& ctx = h->devs[dev_index];
-  HostPlan hp;
-  int rc = build_plan(table, sweep, hp);
+  int rc = cached_plan(h, table, sweep);
   if (rc) return rc;
+  const HostPlan& hp = h->hp;
   CUDA_TRY(cudaSetDevice(ctx.dev));
   cudaStream_t st = (cudaStream_t)stream;
   std::vector<int> mask(std::max(1, hp.nV), 0);
@@ -1203,9 +1265,9 @@ int32_t spicey_tran_solve(spicey_handle* h, const spicey_elem_table* table, cons
   if (!h) return fail(SPICEY_ERR_INVALID, "handle is NULL");
   if (steps < 1 || !v || !status) return fail(SPICEY_ERR_INVALID, "NULL buffer or steps < 1");
   const double t0 = now_ms();
-  HostPlan hp;
-  int rc = build_plan(table, sweep, hp);
+  int rc = cached_plan(h, table, sweep);
   if (rc) return rc;
+  const HostPlan& hp = h->hp;
   const long long n_inst = sweep ? sweep->n_inst : 1;
   const int n_var = sweep ? sweep->n_var : 0;
   const long long S1 = steps + 1;

@@ -50,6 +50,15 @@ struct TranJitArgs {
 };
 #define EPS 1e-15
 #define VT300 0.02585
+// 1/a: MUFU seed + two Newton steps (<= 1 ulp from the correctly rounded quotient; no slow-path branch and
+// 4 instead of ~10 FP64-pipe instructions — the diode circuits are bound by that pipe)
+__device__ __forceinline__ double rcp_nr(double a) {
+  double y, e;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(a));
+  e = fma(-a, y, 1.0); y = fma(y, e, y);
+  e = fma(-a, y, 1.0); y = fma(y, e, y);
+  return y;
+}
 // solveReal.ts:14-71 for an NV x NV system held in registers: factor() once per matrix, solve() per
 // right-hand side (replays the recorded interchanges and multipliers: the same operations on the same
 // operands as the reference's augmented elimination).
@@ -80,7 +89,7 @@ struct SmallLU {
           f[i][j] = sw ? u : w;
         }
       }
-      const double rp = 1.0 / f[k][k];
+      const double rp = rcp_nr(f[k][k]);
 #pragma unroll
       for (int i = k + 1; i < NV; ++i) {
         double m = f[i][k] * rp;
@@ -219,10 +228,11 @@ inline std::string generate_tran_kernel_source(const TranCodegenInput& in) {
   for (int i = 0; i < nvar; ++i) s += "  x[" + N(i) + "] = 0.0;\n";
   if (!dyn) s += load_matrix("  ") + "  status = lu.factor();\n";
   if (has_sw && !has_d) s += "  bool factored = false;\n";
-  s += "  double* vo = a.v + li;\n";
-  if (in.with_ielem) s += "  double* io = a.ielem + li;\n";
+  s += "  char* vo = (char*)(a.v + li);\n";
+  if (in.with_ielem) s += "  char* io = (char*)(a.ielem + li);\n";
+  s += "  const unsigned pitch = (unsigned)NL * 8u;   // bytes between consecutive rows (n_local < 2^29 checked by the host)\n";
   s += "  int* ito = a.iters ? a.iters + li : nullptr;\n";
-  s += "  const long long v_stride = " + N(nn) + "ll * NL, i_stride = " + N(ne) + "ll * NL;\n";
+  s += "  const size_t v_stride = (size_t)pitch * " + N(nn) + "u, i_stride = (size_t)pitch * " + N(ne) + "u;\n";
   s += "  long long step = 0;\n";
   s += "  for (; step < S1 && status == 0; ++step) {\n";
   for (int e = oV; e < oS; ++e) {
@@ -280,7 +290,7 @@ inline std::string generate_tran_kernel_source(const TranCodegenInput& in) {
   if (dyn) s += "    if (status != 0) break;\n";
   s += "    if (ito) { *ito = it < 20 ? it + 1 : 20; ito += NL; }\n";
   // ---- recording (:164-219) and state update (:221-237), table order ----
-  for (int i = 0; i < nn; ++i) s += "    vo[" + N(i) + "ll * NL] = x[" + N(i) + "];\n";
+  for (int i = 0; i < nn; ++i) s += "    *(double*)(vo + (size_t)pitch * " + N(i) + "u) = x[" + N(i) + "];\n";
   s += "    vo += v_stride;\n";
   for (int e = 0; e < ne; ++e) {
     const std::string E = N(e), ST = in.state_idx[e] >= 0 ? "st" + N(in.state_idx[e]) : std::string();
@@ -298,7 +308,7 @@ inline std::string generate_tran_kernel_source(const TranCodegenInput& in) {
         cur = "is" + E + " * (ex" + E + " - 1.0)";
       }
     }
-    if (in.with_ielem) s += "      io[" + E + "ll * NL] = " + cur + ";\n";
+    if (in.with_ielem) s += "      *(double*)(io + (size_t)pitch * " + E + "u) = " + cur + ";\n";
     s += "    }\n";
   }
   if (in.with_ielem) s += "    io += i_stride;\n";
