@@ -266,7 +266,8 @@ struct DeviceCtx {
   // points); 5 warps x 90 slots: 0.81 ms, 4 x 113: 1.03 ms, 8 x 55 (spills): 1.0 ms.  A __syncthreads every
   // 4 pivots keeps the warps of a CTA on the same instruction-cache lines (-8 %).  The bulk-copy (TMA)
   // epilogue stays off: one cp.async.bulk issue costs its warp ~90 cycles (tools/micro/bulk_store.cu), more
-  // than the store stalls it removes.  Overridable for experiments: SPICEY_JIT_CFG=block,minb,slots[,ring,sync].
+  // than the store stalls it removes.  (Also tried: reserving a stored value's registers for a few rows with an
+  // empty asm so that the allocator cannot reuse them while the store drains — no gain, removed.)  Overridable for experiments: SPICEY_JIT_CFG=block,minb,slots[,ring,sync].
   int sp_jit_block = 192, sp_jit_minb = 1, sp_jit_slots = 75, sp_jit_ring = 0, sp_jit_sync = 4;
   double sp_jit_compile_ms = 0;
   std::string sp_jit_note;

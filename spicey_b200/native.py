@@ -122,7 +122,7 @@ def tran_kernel_source(table: "ElemTable", sweep: Optional["Sweep"] = None, with
 
 
 def sparse_kernel_source(table: "ElemTable", pilot_f: float, block=160, min_blocks=1, smem_slots=90, with_ielem=True,
-                         bulk=True, ring=6, sync=0):
+                         bulk=False, ring=6, sync=4):
     """CUDA source of the compiled straight-line sparse kernel (tier 5) for a circuit, plus the generator's
     statistics.  Host-only tooling: lets the generated code be inspected / compiled offline with nvcc."""
     lib = load_library()

@@ -12,7 +12,7 @@ from spicey_b200 import native, packing, parsing, workloads  # noqa: E402
 def main():
     wl, out = sys.argv[1], sys.argv[2]
     block, minb, slots = (int(v) for v in sys.argv[3:6]) if len(sys.argv) >= 6 else (160, 1, 90)
-    ring, sync = (int(v) for v in sys.argv[6:8]) if len(sys.argv) >= 8 else (6, 0)
+    ring, sync = (int(v) for v in sys.argv[6:8]) if len(sys.argv) >= 8 else (0, 4)
     ie = "noielem" not in sys.argv
     if wl == "cfg2":
         text = workloads.rc_ladder()
