@@ -26,6 +26,8 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
+# stdout carries exactly one JSON line: NCCL's version / debug banner goes to stderr
+os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
 
 from spicey_b200 import workloads as W  # noqa: E402
 from spicey_b200.parsing import compute_effective_time_step, parse_netlist  # noqa: E402
