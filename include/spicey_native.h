@@ -130,6 +130,9 @@ enum {
   SPICEY_TIER_TRAN_JIT = 6   /* transient: the persistent time loop written out for the netlist at hand (every
                                 element a few named registers) and compiled with NVRTC once per topology;
                                 Nvar <= 8, batches of >= 2e6 instance-steps or SPICEY_FLAG_JIT */
+  ,SPICEY_TIER_SPARSE_WARP = 7 /* the sparse program level-scheduled for one WARP per system: elimination working
+                                set in shared memory, U streamed to a per-warp workspace (programs whose
+                                per-system factorisation is too large for one thread's share of the chip) */
 };
 
 typedef struct spicey_handle spicey_handle;
@@ -219,6 +222,8 @@ enum {
   SPICEY_FLAG_SERIES_MAJOR = 64u,  /* AC: x is [Nvar][P] and ielem [nAc][P] (one contiguous series per node /
                                       element, coalesced stores on the device) instead of [P][Nvar] / [P][nAc] */
   SPICEY_FLAG_JIT = 128u,          /* compile the per-topology kernel (AC tier 5, TRAN tier 6) even for small batches */
+  SPICEY_FLAG_WARP = 512u,         /* AC: use the warp-per-system sparse tier even for small programs (testing) */
+  SPICEY_FLAG_NO_WARP = 1024u,     /* AC: never use the warp-per-system sparse tier */
   SPICEY_FLAG_NO_JIT = 256u        /* never compile: interpreted sparse program (AC), generic kernels (TRAN) */
 };
 
@@ -235,6 +240,11 @@ int64_t spicey_debug_sparse_source(const spicey_elem_table* table, double pilot_
  * table and sweep (which value slots vary per instance); returns the size needed or -1. */
 int64_t spicey_debug_tran_source(const spicey_elem_table* table, const spicey_sweep* sweep, int32_t with_ielem,
                                  char* buf, int64_t cap);
+
+/* Tooling (no device needed): sizes of the warp-per-system program (tier 7) of this element table:
+ * out[8] = Nvar, shared-memory pool slots, global workspace slots, rows per step (max), updates, update
+ * chunks of 32, back-substitution entries, thread-per-system workspace slots of the same circuit. */
+int32_t spicey_debug_warp_stats(const spicey_elem_table* table, double pilot_f, int32_t* out);
 
 /* Measures this GPU's FP64 FMA peak with a register-only DFMA loop (GFLOP/s), the
  * denominator the FP64-bound roofline is reported against. */

@@ -21,6 +21,7 @@
 
 #include "ac_kernels.cuh"
 #include "ac_sparse.cuh"
+#include "ac_warp.cuh"
 #include "sparse_codegen.h"
 #include "tran_codegen.h"
 #include "tran_kernels.cuh"
@@ -271,6 +272,12 @@ struct DeviceCtx {
   int sp_jit_block = 192, sp_jit_minb = 1, sp_jit_slots = 75, sp_jit_ring = 0, sp_jit_sync = 4;
   double sp_jit_compile_ms = 0;
   std::string sp_jit_note;
+  // warp-cooperative form of the sparse program (warp_program.h): large programs, one warp per system
+  WarpProgram wp;
+  uint64_t wp_key = 0;        // sparse-program key the warp program was lowered from (0 = none)
+  bool wp_valid = false;
+  Buffer wp_blob, wp_work;
+  WarpArgs wp_args;
   uint64_t plan_up_key = 0;   // plan currently resident in `plan` (its device pointers are in plan_dp)
   DevPlan plan_dp;
   JitVariant tr_jit[2];   // compiled transient kernel of the last topology: [0] without, [1] with element currents
@@ -658,6 +665,63 @@ DeviceCtx::JitVariant* ensure_jit(DeviceCtx& ctx, const HostPlan& hp, bool with_
   return &jv;
 }
 
+constexpr int kWarpTierWarps = 8;            // warps (systems) per CTA of ac_warp_kernel
+constexpr int kWarpTierMinSlots = 512;       // thread-per-system workspace (slots) from which the warp tier takes over
+
+// Lowers the cached sparse program to its warp-cooperative form and uploads it (once per topology and handle).
+int prepare_warp(DeviceCtx& ctx, const HostPlan& hp, cudaStream_t stream) {
+  if (ctx.wp_key == ctx.sp_key) return SPICEY_SUCCESS;
+  ctx.wp_key = ctx.sp_key;
+  ctx.wp_valid = false;
+  const int per_warp_cap = (int)((ctx.smem_optin - 1024 - 32 * 1024) / kWarpTierWarps / sizeof(double2));
+  build_warp_program(ctx.sp, per_warp_cap - hp.nvar - 64, ctx.wp);
+  WarpProgram& wp = ctx.wp;
+  if (!wp.ok || (size_t)(wp.n_pool + wp.n + wp.max_elim) > (size_t)per_warp_cap || wp.max_rec16 > 1024) { wp.ok = false; return SPICEY_SUCCESS; }
+  std::vector<unsigned char> blob;
+  size_t o_st = push_blob(blob, wp.stream), o_ft = push_blob(blob, wp.fwd_tab), o_bt = push_blob(blob, wp.back_tab);
+  size_t o_rh = push_blob(blob, wp.rhs_init);
+  int rc = ctx.wp_blob.ensure(blob.size() + 16);
+  if (rc) return rc;
+  CUDA_TRY(cudaMemcpyAsync(ctx.wp_blob.p, blob.data(), blob.size(), cudaMemcpyHostToDevice, stream));
+  CUDA_TRY(cudaStreamSynchronize(stream));
+  unsigned char* b = (unsigned char*)ctx.wp_blob.p;
+  WarpArgs& a = ctx.wp_args;
+  memset(&a, 0, sizeof(a));
+  a.stream = (const int4*)(b + o_st); a.fwd_tab = (const int2*)(b + o_ft); a.back_tab = (const int2*)(b + o_bt);
+  a.rhs_init = (const int*)(b + o_rh);
+  a.n_groups = wp.n_groups; a.max_rec16 = wp.max_rec16; a.g_first0 = wp.g_first0; a.g_count0 = wp.g_count0;
+  const SparseArgs& sa = ctx.sp_args;   // per-entry / per-element constants already uploaded for the interpreter
+  a.ent_c0 = sa.ent_c0; a.ent_c1 = sa.ent_c1; a.el_a = sa.el_a; a.el_b = sa.el_b; a.el_g = sa.el_g;
+  a.ind_L = sa.ind_L; a.n_ind = sa.n_ind;
+  a.n = hp.nvar; a.nn = hp.nn; a.n_ac_elem = hp.n_ac_elem; a.v_first = hp.off[ELEM_V];
+  a.n_pool = wp.n_pool; a.n_gslots = wp.n_gslots; a.max_elim = std::max(1, wp.max_elim);
+  ctx.wp_valid = true;
+  return SPICEY_SUCCESS;
+}
+
+int launch_ac_warp(DeviceCtx& ctx, const HostPlan& hp, const DevPlan& dp, const AcArgs& args, uint32_t flags,
+                   cudaStream_t stream, long long* fb_list, int* fb_count, int64_t* launches) {
+  (void)hp; (void)flags;
+  WarpArgs a = ctx.wp_args;
+  const size_t per_warp = sizeof(double2) * (size_t)(a.n_pool + a.n + a.max_elim);
+  const size_t smem = per_warp * kWarpTierWarps + 2 * sizeof(int4) * (size_t)a.max_rec16;
+  const int per_sm = (int)std::max<size_t>(1, std::min<size_t>(8, (ctx.smem_optin + 1024) / (smem + 1024)));
+  const long long want = (args.p_count + kWarpTierWarps - 1) / kWarpTierWarps;
+  const unsigned grid = (unsigned)std::min<long long>(want, (long long)ctx.sm_count * per_sm);
+  int rc = ctx.wp_work.ensure(sizeof(double2) * (size_t)a.n_gslots * grid * kWarpTierWarps);
+  if (rc) return rc;
+  a.el_ends = dp.ends;
+  a.freqs = args.freqs + args.p_begin; a.p_count = args.p_count;
+  a.G = (double2*)ctx.wp_work.p;
+  a.x = args.x; a.ielem = args.ielem; a.status = args.status; a.series_ld = args.series_ld;
+  a.fb_list = fb_list; a.fb_count = fb_count;
+  CUDA_TRY(cudaFuncSetAttribute(ac_warp_kernel<kWarpTierWarps>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  ac_warp_kernel<kWarpTierWarps><<<grid, kWarpTierWarps * 32, smem, stream>>>(a);
+  CUDA_TRY(cudaGetLastError());
+  if (launches) ++*launches;
+  return SPICEY_SUCCESS;
+}
+
 int launch_ac_sparse(DeviceCtx& ctx, const HostPlan& hp, const DevPlan& dp, const AcArgs& args, uint32_t flags,
                      cudaStream_t stream, int* tier_out, int64_t* launches) {
   const int block = 128;
@@ -692,6 +756,23 @@ int launch_ac_sparse(DeviceCtx& ctx, const HostPlan& hp, const DevPlan& dp, cons
     if (rc) return rc;
     if (tier_out) *tier_out = SPICEY_TIER_SPARSE_JIT;
     return SPICEY_SUCCESS;
+  }
+  // Large programs of a plain frequency sweep: one warp per system (warp_program.h / ac_warp.cuh).
+  if (!ctx.sp_eager && !(flags & SPICEY_FLAG_NO_WARP) && (ctx.sp.n_slots >= kWarpTierMinSlots || (flags & SPICEY_FLAG_WARP))) {
+    rc = prepare_warp(ctx, hp, stream);
+    if (rc) return rc;
+    if (ctx.wp_valid) {
+      rc = launch_ac_warp(ctx, hp, dp, args, flags, stream, fb_list, fb_count, launches);
+      if (rc) return rc;
+      AcArgs d = args;
+      d.plist = fb_list;
+      d.pcount = fb_count;
+      d.fb_total = (unsigned long long*)((char*)ctx.sp_fb.p + 32);
+      rc = launch_ac_dense(ctx, hp, dp, d, flags, stream, nullptr, launches);
+      if (rc) return rc;
+      if (tier_out) *tier_out = SPICEY_TIER_SPARSE_WARP;
+      return SPICEY_SUCCESS;
+    }
   }
   SparseArgs a = ctx.sp_args;
   a.freqs = ctx.sp_eager ? args.freqs : args.freqs + args.p_begin;
@@ -1086,7 +1167,7 @@ int32_t spicey_ac_solve_device(spicey_handle* h, int32_t dev_index, const spicey
   h->stats.kernel_launches = launches;
   h->stats.tier = tier;
   h->stats.fallback_solves = -1;  // resolved lazily by spicey_get_stats
-  h->stats.program_cfma = (tier == SPICEY_TIER_SPARSE || tier == SPICEY_TIER_SPARSE_JIT) ? ctx.sp.n_fma : 0;
+  h->stats.program_cfma = (tier == SPICEY_TIER_SPARSE || tier == SPICEY_TIER_SPARSE_JIT || tier == SPICEY_TIER_SPARSE_WARP) ? ctx.sp.n_fma : 0;
   h->stats.solves = a.p_count;
   h->stats.h2d_bytes = (int64_t)h->blob.size();
   h->stats.d2h_bytes = 0;
@@ -1211,7 +1292,7 @@ int32_t spicey_ac_solve(spicey_handle* h, const spicey_elem_table* table, const 
   h->stats.solves = P;
   h->stats.tier = tier;
   h->stats.fallback_solves = -1;
-  h->stats.program_cfma = (tier == SPICEY_TIER_SPARSE || tier == SPICEY_TIER_SPARSE_JIT) ? h->devs[0].sp.n_fma : 0;
+  h->stats.program_cfma = (tier == SPICEY_TIER_SPARSE || tier == SPICEY_TIER_SPARSE_JIT || tier == SPICEY_TIER_SPARSE_WARP) ? h->devs[0].sp.n_fma : 0;
   return SPICEY_SUCCESS;
 }
 
@@ -1413,6 +1494,23 @@ int64_t spicey_debug_tran_source(const spicey_elem_table* table, const spicey_sw
     buf[n] = 0;
   }
   return (int64_t)src.size() + 1;
+}
+
+int32_t spicey_debug_warp_stats(const spicey_elem_table* table, double pilot_f, int32_t* out) {
+  HostPlan hp;
+  int rc = build_plan(table, nullptr, hp);
+  if (rc) return rc;
+  SparseProgram sp;
+  build_sparse_host(hp, pilot_f, false, sp);
+  if (!sp.ok) return fail(SPICEY_ERR_UNSUPPORTED, "the sparse path does not apply to this circuit");
+  WarpProgram wp;
+  build_warp_program(sp, 1 << 24, wp);
+  if (!wp.ok) return fail(SPICEY_ERR_UNSUPPORTED, "the warp program builder refused this circuit");
+  long long chunks = 0;
+  for (const WarpStep& st : wp.steps) chunks += (st.n_upd + 31) / 32;
+  out[0] = wp.n; out[1] = wp.n_pool; out[2] = wp.n_gslots; out[3] = wp.max_elim;
+  out[4] = (int32_t)wp.n_upd_total; out[5] = (int32_t)chunks; out[6] = (int32_t)wp.colent.size(); out[7] = sp.n_slots;
+  return SPICEY_SUCCESS;
 }
 
 int64_t spicey_series_ld(int64_t n_points) { return (n_points + 31) / 32 * 32; }

@@ -1,0 +1,317 @@
+// Warp-cooperative form of the sparse LU program (host side).
+//
+// sparse_program.h runs one THREAD per system; that stops scaling when the factorisation of one system no
+// longer fits a thread's share of the chip (cfg 4, the 16x16 mesh: 4,400 U entries = 70 KB per system, so
+// the thread-per-system workspace lives in L2/HBM and every update moves 48 bytes through it).  Here one
+// WARP owns one system: the single-assignment program is re-scheduled into levels of mutually independent
+// operations that the 32 lanes execute side by side,
+//
+//   step k:  A  verify the pilot's pivot against every structural candidate, r = 1/pivot
+//            B  one multiplier per row to eliminate           (lanes = rows)
+//            C  a_ij <- a_ij - f_i * a_kj                     (lanes = (row, column) pairs)
+//   back-substitution, column oriented: x_j = acc_j / u_jj, then acc_i -= u_ij * x_j for the rows i of
+//   column j (lanes = rows; no reduction across lanes)
+//
+// and the values are placed by what reads them: everything the elimination itself reads lives in a
+// per-warp pool in shared memory (linear-scan allocation in program order, LIFO free list, in-place
+// updates); what the back-substitution reads (U, 1/u_kk, the eliminated right-hand side) is written once
+// to a per-warp global workspace whose slots are numbered in the order the back-substitution consumes them
+// (contiguous reads).  A value with readers in both phases is stored to both.
+//
+// Safety of the slot reuse under parallel execution: slots are released at a value's last reader in
+// program order and handed out to later operations only, so a writer never precedes a reader of the old
+// value in program order; the kernel executes a level in chunks of 32 consecutive operations and loads all
+// operands of a chunk before it stores any result (warp barrier in between), and levels are separated by
+// warp barriers.
+#pragma once
+#include <algorithm>
+#include <climits>
+#include <cstring>
+#include <map>
+#include <vector>
+
+#include "sparse_program.h"
+
+namespace spicey {
+
+struct WarpStep {
+  int cand_begin, n_cand, pidx, rcp_g;   // candidates [cand_begin, +n_cand) in scan order, pilot's choice, global slot of 1/pivot
+  int elim_begin, n_elim, upd_begin, n_upd;
+  int stamp_begin, n_stamp;              // stamped entries this step reads, materialised into temporary pool slots
+};
+struct WarpStamp { int entry, slot; };
+struct WarpUpd { int old_enc, src_enc, f_idx, dst; };   // dst: pool slot or -1 (no forward reader)
+struct WarpCol { int rcp_g, begin, count, pad; };        // column j of the back-substitution
+struct WarpColEnt { int row, u_enc; };
+
+constexpr int kWarpZero = INT_MIN;   // back-phase operand: structural zero
+
+struct WarpProgram {
+  bool ok = false;
+  int n = 0;
+  int n_pool = 0;     // shared-memory pool slots per system (slot 0 holds zero)
+  int n_gslots = 0;   // global workspace slots per system
+  int max_elim = 0;   // largest number of rows eliminated in one step (size of the multiplier array)
+  long long n_upd_total = 0;
+  std::vector<WarpStep> steps;
+  std::vector<WarpStamp> stamp;
+  std::vector<int> cand;         // forward operands: pool slots (stamped entries are materialised per step, see stamp)
+  std::vector<int> elim;         // a_ik per eliminated row
+  std::vector<WarpUpd> upd;
+  std::vector<int> upd_g;        // per update: global copy slot or -1
+  std::vector<int> rhs_init;     // [n] back operands: >= 0 global slot, < 0 stamped entry ~idx, kWarpZero
+  std::vector<WarpCol> cols;     // [n]
+  std::vector<WarpColEnt> colent;
+  // Packed form the kernel stages through shared memory, one record per pivot step / per group of
+  // kWarpColGroup back-substitution columns (all sizes in 16-byte units; see pack_warp_program):
+  std::vector<int> stream;        // records, each a multiple of 4 ints
+  std::vector<int> fwd_tab;       // [n][2]  (offset, length) of step s
+  std::vector<int> back_tab;      // [n_groups][2]
+  int n_groups = 0;
+  int max_rec16 = 0;              // largest record
+  int g_first0 = 0, g_count0 = 0; // global slots the first back-substitution group reads
+};
+
+constexpr int kWarpColGroup = 16;
+
+// step record:  {n_cand, pidx, rcp_g, n_elim, n_upd, n_stamp, 0, 0}
+//               stamp[n_stamp][12] = {slot, 0, 0, 0, (alpha + Re J), Im J, beta, gamma as doubles}
+//               cand[n_cand] elim[n_elim] pad4 upd[n_upd][4] upd_g[n_upd] pad4
+// back record:  {n_cols, first global slot the NEXT group reads, number of slots it reads, 0}
+//               cols[n_cols][4] = {rcp_g, ent_begin (ints from record start), count, j} ents[...][2] pad4
+inline void pack_warp_program(WarpProgram& wp, const SparseProgram& sp) {
+  wp.stream.clear(); wp.fwd_tab.clear(); wp.back_tab.clear();
+  wp.max_rec16 = 0;
+  auto pad4 = [&]() { while (wp.stream.size() & 3) wp.stream.push_back(0); };
+  for (const WarpStep& st : wp.steps) {
+    const size_t o = wp.stream.size();
+    const int hdr[8] = {st.n_cand, st.pidx, st.rcp_g, st.n_elim, st.n_upd, st.n_stamp, 0, 0};
+    wp.stream.insert(wp.stream.end(), hdr, hdr + 8);
+    for (int q = 0; q < st.n_stamp; ++q) {
+      const WarpStamp& m = wp.stamp[st.stamp_begin + q];
+      double c[4] = {0.0, 0.0, 0.0, 0.0};
+      if ((size_t)m.entry < sp.ent_alpha.size()) {
+        c[0] = sp.ent_alpha[m.entry] + sp.ent_jre[m.entry]; c[1] = sp.ent_jim[m.entry];
+        c[2] = sp.ent_beta[m.entry]; c[3] = sp.ent_gamma[m.entry];
+      }
+      int w[12] = {m.slot, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+      memcpy(w + 4, c, sizeof c);
+      wp.stream.insert(wp.stream.end(), w, w + 12);
+    }
+    for (int c = 0; c < st.n_cand; ++c) wp.stream.push_back(wp.cand[st.cand_begin + c]);
+    for (int e = 0; e < st.n_elim; ++e) wp.stream.push_back(wp.elim[st.elim_begin + e]);
+    pad4();
+    for (int u = 0; u < st.n_upd; ++u) {
+      const WarpUpd& w = wp.upd[st.upd_begin + u];
+      wp.stream.push_back(w.old_enc); wp.stream.push_back(w.src_enc); wp.stream.push_back(w.f_idx); wp.stream.push_back(w.dst);
+    }
+    for (int u = 0; u < st.n_upd; ++u) wp.stream.push_back(wp.upd_g[st.upd_begin + u]);
+    pad4();
+    const int len16 = (int)((wp.stream.size() - o) / 4);
+    wp.fwd_tab.push_back((int)(o / 4)); wp.fwd_tab.push_back(len16);
+    wp.max_rec16 = std::max(wp.max_rec16, len16);
+  }
+  wp.n_groups = 0;
+  // global slots a group reads: a contiguous range (slots are numbered in consumption order)
+  auto g_range = [&](int hi, int& first, int& count) {
+    const int lo = std::max(0, hi - kWarpColGroup + 1);
+    int mn = INT_MAX, mx = -1;
+    for (int j = hi; j >= lo && j >= 0; --j) {
+      const WarpCol& c = wp.cols[j];
+      if (c.rcp_g >= 0) { mn = std::min(mn, c.rcp_g); mx = std::max(mx, c.rcp_g); }
+      for (int q = 0; q < c.count; ++q) {
+        const int e = wp.colent[c.begin + q].u_enc;
+        if (e >= 0) { mn = std::min(mn, e); mx = std::max(mx, e); }
+      }
+    }
+    first = mx >= 0 ? mn : 0;
+    count = mx >= 0 ? mx - mn + 1 : 0;
+  };
+  g_range(wp.n - 1, wp.g_first0, wp.g_count0);
+  for (int hi = wp.n - 1; hi >= 0; hi -= kWarpColGroup) {
+    const int lo = std::max(0, hi - kWarpColGroup + 1), nc = hi - lo + 1;
+    const size_t o = wp.stream.size();
+    int nf = 0, ncnt = 0;
+    if (lo > 0) g_range(lo - 1, nf, ncnt);
+    const int hdr[4] = {nc, nf, ncnt, 0};
+    wp.stream.insert(wp.stream.end(), hdr, hdr + 4);
+    int ent = 4 + 4 * nc;
+    for (int j = hi; j >= lo; --j) {
+      const WarpCol& c = wp.cols[j];
+      wp.stream.push_back(c.rcp_g); wp.stream.push_back(ent); wp.stream.push_back(c.count); wp.stream.push_back(j);
+      ent += 2 * c.count;
+    }
+    for (int j = hi; j >= lo; --j) {
+      const WarpCol& c = wp.cols[j];
+      for (int q = 0; q < c.count; ++q) { wp.stream.push_back(wp.colent[c.begin + q].row); wp.stream.push_back(wp.colent[c.begin + q].u_enc); }
+    }
+    pad4();
+    const int len16 = (int)((wp.stream.size() - o) / 4);
+    wp.back_tab.push_back((int)(o / 4)); wp.back_tab.push_back(len16);
+    wp.max_rec16 = std::max(wp.max_rec16, len16);
+    ++wp.n_groups;
+  }
+}
+
+// Lowers sp.ir.  pool_cap: largest pool the kernel can give one warp; the program is rejected (ok=false)
+// when the elimination's working set does not fit, instead of spilling forward operands to global memory.
+inline void build_warp_program(const SparseProgram& sp, int pool_cap, WarpProgram& wp) {
+  using namespace sparse_detail;
+  wp = WarpProgram();
+  const int n = sp.n, nv = sp.n_virtual;
+  wp.n = n;
+  const std::vector<IrOp>& ir = sp.ir;
+  const int n_ir = (int)ir.size();
+  int B = n_ir;
+  for (int t = 0; t < n_ir; ++t) if (ir[t].kind == SOP_BSUB) { B = t; break; }
+  // ---- uses: last forward reader (fine-grained time) and whether the back-substitution reads the value ----
+  std::vector<int> fwd_last(nv, -1);
+  std::vector<char> back_use(nv, 0);
+  {
+    int tt = 0;
+    for (int t = 0; t < B; ++t) {
+      const IrOp& op = ir[t];
+      if (op.kind == SOP_PIVOT) { for (int o : op.reads) if (o >= 0) fwd_last[o] = tt; ++tt; }
+      else {
+        if (op.reads[0] >= 0) fwd_last[op.reads[0]] = tt;
+        ++tt;
+        for (const Update& u : op.upd) {
+          if (u.dst_old >= 0) fwd_last[u.dst_old] = tt;
+          if (u.src >= 0) fwd_last[u.src] = tt;
+          ++tt;
+        }
+      }
+    }
+    for (int t = B; t < n_ir; ++t)
+      for (int o : ir[t].reads) if (o >= 0) back_use[o] = 1;
+  }
+  // ---- global slots, numbered in back-substitution order: rhs of every row, then per column (descending)
+  //      1/u_jj and the column's U entries ----
+  std::vector<int> var_of_x(nv, -1);      // virtual id of x_j -> j
+  std::vector<const IrOp*> bs_of(n, nullptr);
+  for (int t = B; t < n_ir; ++t) { var_of_x[ir[t].def] = ir[t].var; bs_of[ir[t].var] = &ir[t]; }
+  for (int i = 0; i < n; ++i) if (!bs_of[i]) return;
+  std::vector<int> gslot(nv, -1);
+  int ng = 0;
+  auto g_of = [&](int o) -> int {
+    if (o == kNoOperand) return kWarpZero;
+    if (o < 0) return o;  // stamped entry ~idx, recomputed where it is read
+    if (gslot[o] < 0) gslot[o] = ng++;
+    return gslot[o];
+  };
+  wp.rhs_init.resize(n);
+  for (int i = 0; i < n; ++i) wp.rhs_init[i] = g_of(bs_of[i]->reads[0]);
+  std::vector<std::vector<WarpColEnt>> col(n);
+  for (int i = 0; i < n; ++i) {
+    const IrOp& bs = *bs_of[i];
+    for (size_t q = 2; q + 1 < bs.reads.size(); q += 2) {
+      const int j = var_of_x[bs.reads[q + 1]];
+      if (j < 0) return;
+      col[j].push_back(WarpColEnt{i, bs.reads[q]});   // operand resolved below, in consumption order
+    }
+  }
+  wp.cols.resize(n);
+  for (int j = n - 1; j >= 0; --j) {
+    WarpCol c;
+    c.rcp_g = g_of(bs_of[j]->reads[1]);
+    c.begin = (int)wp.colent.size();
+    c.count = (int)col[j].size();
+    c.pad = 0;
+    for (WarpColEnt e : col[j]) { e.u_enc = g_of(e.u_enc); wp.colent.push_back(e); }
+    wp.cols[j] = c;
+  }
+  wp.n_gslots = std::max(1, ng);
+  // ---- forward phase: pool allocation in program order ----
+  std::vector<int> pool(nv, -1), free_list;
+  int high = 1;  // slot 0 = zero
+  auto alloc = [&]() -> int {
+    if (!free_list.empty()) { int s = free_list.back(); free_list.pop_back(); return s; }
+    return high++;
+  };
+  // A stamped entry read by a step is written to a temporary pool slot at the start of that step (so that
+  // the update loop reads nothing but pool slots) and the slot is released when the step ends.
+  // Temporary slots form their own free list: they are written at the START of a step, so they must not be
+  // slots that the same step releases (and still reads) further down.
+  std::map<int, int> stamped;
+  std::vector<int> temp_free;
+  auto alloc_temp = [&]() -> int {
+    if (!temp_free.empty()) { int t = temp_free.back(); temp_free.pop_back(); return t; }
+    return high++;
+  };
+  auto enc = [&](int o) -> int {
+    if (o == kNoOperand) return 0;
+    if (o < 0) {
+      const int en = ~o;
+      auto it = stamped.find(en);
+      if (it == stamped.end()) {
+        it = stamped.insert(std::make_pair(en, alloc_temp())).first;
+        wp.stamp.push_back(WarpStamp{en, it->second});
+      }
+      return it->second;
+    }
+    return pool[o];   // defined earlier with a forward reader, hence in the pool
+  };
+  int tt = 0;
+  auto release = [&](int o) {
+    if (o >= 0 && fwd_last[o] == tt && pool[o] >= 0) { free_list.push_back(pool[o]); fwd_last[o] = -2; }
+  };
+  WarpStep cur = WarpStep();
+  bool open = false;
+  auto close_step = [&]() {
+    if (!open) return;
+    cur.n_elim = (int)wp.elim.size() - cur.elim_begin;
+    cur.n_upd = (int)wp.upd.size() - cur.upd_begin;
+    cur.n_stamp = (int)wp.stamp.size() - cur.stamp_begin;
+    for (const auto& kv : stamped) temp_free.push_back(kv.second);
+    stamped.clear();
+    wp.max_elim = std::max(wp.max_elim, cur.n_elim);
+    wp.steps.push_back(cur);
+    open = false;
+  };
+  for (int t = 0; t < B; ++t) {
+    const IrOp& op = ir[t];
+    if (op.kind == SOP_PIVOT) {
+      close_step();
+      cur = WarpStep();
+      cur.stamp_begin = (int)wp.stamp.size();
+      cur.cand_begin = (int)wp.cand.size();
+      cur.n_cand = (int)op.reads.size();
+      cur.pidx = op.pidx;
+      for (int o : op.reads) { const int e = enc(o); if (o >= 0 && e < 0) return; wp.cand.push_back(e); }
+      for (int o : op.reads) release(o);
+      cur.rcp_g = (op.def >= 0 && gslot[op.def] >= 0) ? gslot[op.def] : -1;
+      cur.elim_begin = (int)wp.elim.size();
+      cur.upd_begin = (int)wp.upd.size();
+      open = true;
+      ++tt;
+    } else {
+      const int row = (int)wp.elim.size() - cur.elim_begin;
+      { const int e = enc(op.reads[0]); if (op.reads[0] >= 0 && e < 0) return; wp.elim.push_back(e); }
+      release(op.reads[0]);
+      ++tt;
+      for (const Update& u : op.upd) {
+        WarpUpd w;
+        w.old_enc = enc(u.dst_old);
+        w.src_enc = enc(u.src);
+        if ((u.dst_old >= 0 && w.old_enc < 0) || (u.src >= 0 && w.src_enc < 0)) return;
+        w.f_idx = row;
+        release(u.dst_old);   // in-place update when the old version dies here
+        release(u.src);
+        w.dst = -1;
+        if (fwd_last[u.dst_new] >= 0) { pool[u.dst_new] = alloc(); w.dst = pool[u.dst_new]; }
+        wp.upd.push_back(w);
+        wp.upd_g.push_back(gslot[u.dst_new]);
+        ++tt;
+      }
+    }
+  }
+  close_step();
+  if ((int)wp.steps.size() != n) return;
+  wp.n_pool = high;
+  wp.n_upd_total = (long long)wp.upd.size();
+  if (high > pool_cap) return;
+  pack_warp_program(wp, sp);
+  wp.ok = true;
+}
+
+}  // namespace spicey

@@ -16,15 +16,15 @@ ELEM_R, ELEM_C, ELEM_L, ELEM_V, ELEM_S, ELEM_D = range(6)
 VALUE_SLOTS = {ELEM_R: 1, ELEM_C: 1, ELEM_L: 1, ELEM_V: 3, ELEM_S: 4, ELEM_D: 2}
 ST_OK, ST_SINGULAR, ST_CDIV, ST_R_NONPOS = 0, 1, 2, 3
 FLAG_STRICT, FLAG_FORCE_GMEM, FLAG_FORCE_CTA, FLAG_DENSE, FLAG_SPARSE, FLAG_GENERIC_THREAD = 1, 2, 4, 8, 16, 32
-FLAG_SERIES_MAJOR, FLAG_JIT, FLAG_NO_JIT = 64, 128, 256
-TIER_THREAD, TIER_CTA_SMEM, TIER_CTA_GMEM, TIER_SPARSE, TIER_SPARSE_JIT, TIER_TRAN_JIT = 1, 2, 3, 4, 5, 6
+FLAG_SERIES_MAJOR, FLAG_JIT, FLAG_NO_JIT, FLAG_WARP, FLAG_NO_WARP = 64, 128, 256, 512, 1024
+TIER_THREAD, TIER_CTA_SMEM, TIER_CTA_GMEM, TIER_SPARSE, TIER_SPARSE_JIT, TIER_TRAN_JIT, TIER_SPARSE_WARP = 1, 2, 3, 4, 5, 6, 7
 SUCCESS, ERR_INVALID, ERR_NO_DEVICE, ERR_CUDA, ERR_UNSUPPORTED = 0, 1, 2, 3, 4
 
 EXPORTS = [
     "spicey_native_abi_version", "spicey_device_count", "spicey_last_error", "spicey_create",
     "spicey_destroy", "spicey_get_stats", "spicey_host_alloc", "spicey_host_free", "spicey_ac_solve",
     "spicey_ac_solve_device", "spicey_tran_solve", "spicey_tran_solve_device", "spicey_measure_fp64_peak",
-    "spicey_debug_sparse_source", "spicey_series_ld", "spicey_debug_tran_source",
+    "spicey_debug_sparse_source", "spicey_series_ld", "spicey_debug_tran_source", "spicey_debug_warp_stats",
 ]
 
 _ip = C.POINTER(C.c_int32)
@@ -100,11 +100,24 @@ def load_library(path: Optional[str] = None):
     lib.spicey_debug_sparse_source.restype = C.c_int64
     lib.spicey_debug_sparse_source.argtypes = [tb, C.c_double, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_char_p,
                                                C.c_int64, _ip]
+    lib.spicey_debug_warp_stats.restype = C.c_int32
+    lib.spicey_debug_warp_stats.argtypes = [tb, C.c_double, _ip]
     lib.spicey_debug_tran_source.restype = C.c_int64
     lib.spicey_debug_tran_source.argtypes = [tb, sw, C.c_int32, C.c_char_p, C.c_int64]
     if path == _build.LIB_PATH:
         _LIB = lib
     return lib
+
+
+def warp_program_stats(table: "ElemTable", pilot_f: float = 1000.0) -> dict:
+    """Sizes of the warp-per-system sparse program (tier 7) of a circuit.  Host-only tooling."""
+    lib = load_library()
+    st = (C.c_int32 * 8)()
+    ts = table.struct()
+    _check(lib, lib.spicey_debug_warp_stats(C.byref(ts), pilot_f, st))
+    keys = ("nvar", "pool_slots", "global_slots", "max_rows_per_step", "updates", "update_chunks", "backsub_entries",
+            "thread_tier_slots")
+    return dict(zip(keys, list(st)))
 
 
 def tran_kernel_source(table: "ElemTable", sweep: Optional["Sweep"] = None, with_ielem=True) -> str:

@@ -7,9 +7,12 @@
 #include <algorithm>
 #include <cstdio>
 #include <cstdlib>
+#include <cstring>
+#include <climits>
 #include <map>
 #include <random>
 #include "../../spicey_b200/csrc/sparse_program.h"
+#include "../../spicey_b200/csrc/warp_program.h"
 using namespace spicey;
 typedef std::complex<double> cd;
 
@@ -123,7 +126,81 @@ int main(int argc, char** argv) {
   for (int i = 0; i < n; ++i)
     if (std::abs(W[sp.x_slot[i]] - xout[i]) != 0) { printf("FAIL x_slot mismatch\n"); return 1; }
   const double rel = err / std::max(scale, 1e-300);
-  printf("%s %.3e slots=%d fast=%d const=%d microops=%zu virtual=%d\n", rel < 1e-9 ? "OK" : "FAIL", rel, sp.n_slots,
-         sp.n_fast, sp.n_const, sp.code.size(), sp.n_virtual);
-  return rel < 1e-9 ? 0 : 1;
+  // ---- warp program (warp_program.h): emulate the kernel's schedule — levels in chunks of 32 operations,
+  //      every chunk loads all its operands before it stores any result ----
+  WarpProgram wp;
+  // per-entry constants as the library fills them (here: frequency independent)
+  sp.ent_alpha.assign(n_ent, 0.0); sp.ent_jre.assign(n_ent, 0.0); sp.ent_jim.assign(n_ent, 0.0);
+  sp.ent_beta.assign(n_ent, 0.0); sp.ent_gamma.assign(n_ent, 0.0);
+  for (int en = 0; en < n_ent; ++en) { sp.ent_alpha[en] = in.ent_val[en].real(); sp.ent_jim[en] = in.ent_val[en].imag(); }
+  build_warp_program(sp, 1 << 20, wp);
+  if (!wp.ok) { printf("FAIL warp program builder refused\n"); return 1; }
+  double relw = 0;
+  {
+    // executes the PACKED records exactly as ac_warp.cuh parses them
+    std::vector<cd> pool(wp.n_pool, cd(1e300, 1e300)), G(wp.n_gslots, cd(1e300, 1e300)), Fm(std::max(1, wp.max_elim));
+    pool[0] = cd(0, 0);
+    auto fb = [&](int e) -> cd { return e == kWarpZero ? cd(0, 0) : (e >= 0 ? G[e] : in.ent_val[~e]); };
+    for (int s = 0; s < n; ++s) {
+      const int* rec = wp.stream.data() + 4 * (size_t)wp.fwd_tab[2 * s];
+      if (wp.fwd_tab[2 * s + 1] > wp.max_rec16) { printf("FAIL warp: record larger than max_rec16\n"); return 1; }
+      const int n_cand = rec[0], pidx = rec[1], rcp_g = rec[2], n_elim = rec[3], n_upd = rec[4], n_stamp = rec[5];
+      const int* stamp = rec + 8;
+      const int* cand = stamp + 12 * n_stamp;
+      const int* elim = cand + n_cand;
+      const int* upd = rec + ((8 + 12 * n_stamp + n_cand + n_elim + 3) & ~3);
+      const int* upd_g = upd + 4 * n_upd;
+      for (int q = 0; q < n_stamp; ++q) {
+        double c[4];
+        memcpy(c, stamp + 12 * q + 4, sizeof c);
+        pool[stamp[12 * q]] = cd(c[0], c[1]);
+      }
+      const cd apv = pool[cand[pidx]];
+      const double mpv = std::norm(apv);
+      for (int c = 0; c < n_cand; ++c) {
+        const double m = std::norm(pool[cand[c]]);
+        if ((c < pidx && !(m < mpv)) || (c > pidx && (m > mpv))) { printf("FAIL warp: pivot verification rejected the pilot\n"); return 1; }
+      }
+      const cd rv = cd(1, 0) / apv;
+      if (rcp_g >= 0) G[rcp_g] = rv;
+      for (int e = 0; e < n_elim; ++e) { cd f = pool[elim[e]] * rv; if (std::norm(f) < 1e-30) f = 0; Fm[e] = f; }
+      for (int c0 = 0; c0 < n_upd; c0 += 32) {
+        const int c1 = std::min(n_upd, c0 + 32);
+        std::vector<cd> val(c1 - c0);
+        for (int q = c0; q < c1; ++q) val[q - c0] = pool[upd[4 * q]] - Fm[upd[4 * q + 2]] * pool[upd[4 * q + 1]];
+        for (int q = c0; q < c1; ++q) {
+          if (upd[4 * q + 3] >= 0) pool[upd[4 * q + 3]] = val[q - c0];
+          if (upd_g[q] >= 0) G[upd_g[q]] = val[q - c0];
+        }
+      }
+    }
+    std::vector<cd> accv(n);
+    for (int i = 0; i < n; ++i) accv[i] = fb(wp.rhs_init[i]);
+    int expect_first = wp.g_first0, expect_count = wp.g_count0;
+    for (int gi = 0; gi < wp.n_groups; ++gi) {
+      const int* rec = wp.stream.data() + 4 * (size_t)wp.back_tab[2 * gi];
+      const int nc = rec[0];
+      int mn = INT_MAX, mx = -1;
+      for (int ci = 0; ci < nc; ++ci) {
+        const int* c = rec + 4 + 4 * ci;   // {rcp_g, ent_begin, count, j}
+        const cd xj = accv[c[3]] * G[c[0]];
+        mn = std::min(mn, c[0]); mx = std::max(mx, c[0]);
+        for (int q = 0; q < c[2]; ++q) {
+          const int row = rec[c[1] + 2 * q], ue = rec[c[1] + 2 * q + 1];
+          if (ue >= 0) { mn = std::min(mn, ue); mx = std::max(mx, ue); }
+          accv[row] -= fb(ue) * xj;
+        }
+        accv[c[3]] = xj;
+      }
+      if (mx >= 0 && (mn < expect_first || mx >= expect_first + expect_count)) { printf("FAIL warp: prefetch range does not cover group %d\n", gi); return 1; }
+      expect_first = rec[1]; expect_count = rec[2];
+    }
+    double errw = 0;
+    for (int i = 0; i < n; ++i) errw = std::max(errw, std::abs(accv[i] - xref[i]));
+    relw = errw / std::max(scale, 1e-300);
+  }
+  const bool good = rel < 1e-9 && relw < 1e-9;
+  printf("%s %.3e warp %.3e slots=%d fast=%d const=%d microops=%zu virtual=%d pool=%d gslots=%d\n", good ? "OK" : "FAIL", rel, relw, sp.n_slots,
+         sp.n_fast, sp.n_const, sp.code.size(), sp.n_virtual, wp.n_pool, wp.n_gslots);
+  return good ? 0 : 1;
 }

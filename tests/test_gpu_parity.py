@@ -82,6 +82,8 @@ SM = native.FLAG_SERIES_MAJOR
                                        (native.FLAG_DENSE | SM, AC_TOL), (native.FLAG_SPARSE | SM, AC_TOL),
                                        (native.FLAG_SPARSE | native.FLAG_JIT, AC_TOL),
                                        (native.FLAG_SPARSE | native.FLAG_JIT | SM, AC_TOL),
+                                       (native.FLAG_SPARSE | native.FLAG_WARP, AC_TOL),
+                                       (native.FLAG_SPARSE | native.FLAG_WARP | SM, AC_TOL),
                                        (native.FLAG_FORCE_GMEM | native.FLAG_STRICT | SM, 1e-12)])
 def test_ac_ladder64_slice(eng, flags, tol):
     """cfg 2 topology (Nvar = 65), every 997th of the 1,000,001 frequencies."""
@@ -93,7 +95,8 @@ def test_ac_ladder64_slice(eng, flags, tol):
     out, x, ie, st, _ = ac_case(eng, text, sub, flags)
     if flags & native.FLAG_SPARSE:
         stt = eng.stats()
-        want = native.TIER_SPARSE_JIT if flags & native.FLAG_JIT else native.TIER_SPARSE
+        want = (native.TIER_SPARSE_JIT if flags & native.FLAG_JIT else
+                native.TIER_SPARSE_WARP if flags & native.FLAG_WARP else native.TIER_SPARSE)
         assert stt["tier"] == want and stt["fallback_solves"] == 0 and stt["program_cfma"] > 0
     assert out["status"].max() == 0 and st.max() == 0
     assert rel_err(out["x"], x) <= tol, rel_err(out["x"], x)
@@ -104,10 +107,13 @@ def test_ac_ladder64_slice(eng, flags, tol):
     assert np.max(np.abs(dphi)) <= tol
 
 
-@pytest.mark.parametrize("flags,tier", [(native.FLAG_DENSE, native.TIER_CTA_GMEM), (native.FLAG_SPARSE, native.TIER_SPARSE)])
+@pytest.mark.parametrize("flags,tier", [(native.FLAG_DENSE, native.TIER_CTA_GMEM),
+                                        (native.FLAG_SPARSE, native.TIER_SPARSE_WARP),
+                                        (native.FLAG_SPARSE | native.FLAG_SERIES_MAJOR, native.TIER_SPARSE_WARP),
+                                        (native.FLAG_SPARSE | native.FLAG_NO_WARP, native.TIER_SPARSE)])
 def test_ac_mesh16_slice(eng, flags, tier):
-    """cfg 4 topology (Nvar = 257): does not fit one SM's shared memory -> global-scratch tier (dense)
-    or the sparse program tier."""
+    """cfg 4 topology (Nvar = 257): does not fit one SM's shared memory -> global-scratch tier (dense), the
+    warp-per-system sparse tier (default for programs this large) or the thread-per-system sparse tier."""
     import spicey_b200 as sp
     text = w.rc_mesh(16)
     freqs = np.array(sp.analysis.ac_frequencies(parse_netlist(text)))
@@ -147,10 +153,13 @@ def test_ac_random_rlc_networks(eng, n_nodes, n_elem):
     text = random_rlc_netlist(rng, n_nodes, n_elem, n_v=min(2, n_nodes))
     freqs = sp.analysis.ac_frequencies(parse_netlist(text))
     for flags, tol in ((native.FLAG_DENSE, AC_TOL), (native.FLAG_STRICT, 1e-11), (native.FLAG_SPARSE, AC_TOL),
-                       (native.FLAG_SPARSE | SM, AC_TOL), (native.FLAG_SPARSE | native.FLAG_JIT | SM, AC_TOL)):
+                       (native.FLAG_SPARSE | SM, AC_TOL), (native.FLAG_SPARSE | native.FLAG_JIT | SM, AC_TOL),
+                       (native.FLAG_SPARSE | native.FLAG_WARP, AC_TOL), (native.FLAG_SPARSE | native.FLAG_WARP | SM, AC_TOL)):
         out, x, ie, st, _ = ac_case(eng, text, freqs, flags)
         if flags == native.FLAG_SPARSE:
             FALLBACKS.append(eng.stats()["fallback_solves"])
+        if flags & native.FLAG_WARP:
+            assert eng.stats()["tier"] in (native.TIER_SPARSE_WARP, native.TIER_SPARSE, native.TIER_CTA_SMEM, native.TIER_CTA_GMEM, native.TIER_THREAD)
         assert np.array_equal(out["status"], st)
         assert st.max() == 0
         scale = np.max(np.abs(x), axis=2, keepdims=True)  # mixed-magnitude solutions: error relative to the row's max
