@@ -114,8 +114,8 @@ __global__ void __launch_bounds__(WARPS * 32) ac_warp_kernel(WarpArgs a) {
       const int* stamp = rec + 8;
       const int* cand = stamp + 12 * n_stamp;
       const int* elim = cand + n_cand;
-      const int4* upd = (const int4*)(rec + ((8 + 12 * n_stamp + n_cand + n_elim + 3) & ~3));
-      const int* upd_g = (const int*)(upd + n_upd);
+      const int2* upd = (const int2*)(rec + ((8 + 12 * n_stamp + n_cand + n_elim + 3) & ~3));
+      const int* upd_g = (const int*)upd + ((2 * n_upd + 3) & ~3);
       // stamped entries this step reads (simulateAC.ts:24-60): alpha + j(w*beta - gamma/w), constants in the record
       for (int q = lane; q < n_stamp; q += 32) {
         const double2 c0 = *(const double2*)(stamp + 12 * q + 4), c1 = *(const double2*)(stamp + 12 * q + 8);
@@ -140,19 +140,25 @@ __global__ void __launch_bounds__(WARPS * 32) ac_warp_kernel(WarpArgs a) {
         Fm[e] = fm;
       }
       __syncwarp();
+      // Updates, 32 at a time; operation word {old | src << 16, dst | multiplier << 16 | global-copy flag << 31}.
+      // The loads of chunk c + 1 are issued before chunk c is computed and stored (no operation of a level reads
+      // what another one writes, and a slot is never re-written before its last reader in program order).
+      const int2 idle = make_int2(0, 0xffff);   // zero slot - f * zero slot, no destination
+      int2 opn = lane < n_upd ? upd[lane] : idle;
+      cplx on = pool[opn.x & 0xffff], sn = pool[(unsigned)opn.x >> 16], fn = Fm[((unsigned)opn.y >> 16) & 0x7fff];
       for (int u0 = 0; u0 < n_upd; u0 += 32) {
-        const int u = u0 + lane;
-        int dst = -1, g = -1;
-        cplx v = make_double2(0.0, 0.0);
-        if (u < n_upd) {
-          const int4 op = upd[u];   // {old, src, multiplier, dst}: pool slots only
-          g = upd_g[u];
-          dst = op.w;
-          v = N::submul<false>(pool[op.x], Fm[op.z], pool[op.y]);
+        const int2 op = opn;
+        const cplx o = on, sv = sn, f = fn;
+        if (u0 + 32 < n_upd) {
+          const int un = u0 + 32 + lane;
+          opn = un < n_upd ? upd[un] : idle;
+          on = pool[opn.x & 0xffff]; sn = pool[(unsigned)opn.x >> 16]; fn = Fm[((unsigned)opn.y >> 16) & 0x7fff];
         }
+        const cplx v = N::submul<false>(o, f, sv);
         __syncwarp();   // every operand of the chunk has been read before any slot is overwritten
-        if (dst >= 0) pool[dst] = v;
-        if (g >= 0) G[g] = v;
+        const int dst = op.y & 0xffff;
+        if (dst != 0xffff) pool[dst] = v;
+        if (op.y < 0) G[upd_g[u0 + lane]] = v;
       }
       stage_wait();
     }

@@ -62,7 +62,7 @@ constexpr int kNoOperand = INT_MIN;  // "structurally zero" operand
 namespace sparse_detail {
 
 // Operand of the intermediate program: >= 0 virtual slot, < 0 pristine entry ~idx, kNoOperand none.
-struct Update { int dst_old, dst_new, src; };
+struct Update { int dst_old, dst_new, src; int col = 0; };   // col: column of the updated entry (n = right-hand side)
 struct IrOp {
   int kind = 0;
   std::vector<int> reads;       // PIVOT: candidates; ELIM: {a_ik}; BSUB: {b, rcp, a_0, x_0, a_1, x_1, ...}
@@ -179,6 +179,7 @@ inline void build_sparse_program(const PilotInput& in, SparseProgram& sp, int fa
         u.dst_old = cur[(size_t)r * ld + j];
         u.dst_new = nv++;
         u.src = cur[(size_t)p * ld + j];
+        u.col = j;
         cur[(size_t)r * ld + j] = u.dst_new;
         el.upd.push_back(u);
         if (act) M[(size_t)r * ld + j] -= f * M[(size_t)p * ld + j];

@@ -76,7 +76,9 @@ constexpr int kWarpColGroup = 16;
 
 // step record:  {n_cand, pidx, rcp_g, n_elim, n_upd, n_stamp, 0, 0}
 //               stamp[n_stamp][12] = {slot, 0, 0, 0, (alpha + Re J), Im J, beta, gamma as doubles}
-//               cand[n_cand] elim[n_elim] pad4 upd[n_upd][4] upd_g[n_upd] pad4
+//               cand[n_cand] elim[n_elim] pad4
+//               upd[n_upd][2] = {old | src << 16, dst (0xffff = none) | multiplier << 16 | has_global_copy << 31} pad4
+//               upd_g[n_upd] (global copy slot, read only when flagged) pad4
 // back record:  {n_cols, first global slot the NEXT group reads, number of slots it reads, 0}
 //               cols[n_cols][4] = {rcp_g, ent_begin (ints from record start), count, j} ents[...][2] pad4
 inline void pack_warp_program(WarpProgram& wp, const SparseProgram& sp) {
@@ -103,8 +105,11 @@ inline void pack_warp_program(WarpProgram& wp, const SparseProgram& sp) {
     pad4();
     for (int u = 0; u < st.n_upd; ++u) {
       const WarpUpd& w = wp.upd[st.upd_begin + u];
-      wp.stream.push_back(w.old_enc); wp.stream.push_back(w.src_enc); wp.stream.push_back(w.f_idx); wp.stream.push_back(w.dst);
+      const int g = wp.upd_g[st.upd_begin + u];
+      wp.stream.push_back((int)((unsigned)w.old_enc | ((unsigned)w.src_enc << 16)));
+      wp.stream.push_back((int)((unsigned)(w.dst < 0 ? 0xffff : w.dst) | ((unsigned)w.f_idx << 16) | (g >= 0 ? 0x80000000u : 0u)));
     }
+    pad4();
     for (int u = 0; u < st.n_upd; ++u) wp.stream.push_back(wp.upd_g[st.upd_begin + u]);
     pad4();
     const int len16 = (int)((wp.stream.size() - o) / 4);
@@ -222,10 +227,15 @@ inline void build_warp_program(const SparseProgram& sp, int pool_cap, WarpProgra
   }
   wp.n_gslots = std::max(1, ng);
   // ---- forward phase: pool allocation in program order ----
-  std::vector<int> pool(nv, -1), free_list;
+  // Slots are handed out by bank group: a 16-byte pool access of a warp is served a quarter-warp at a time,
+  // conflict-free when the eight slots differ mod 8.  The lanes of a chunk work on consecutive columns of a
+  // row, so a value of column j gets a slot with slot % 8 == j % 8 (in-place updates keep it).
+  std::vector<int> pool(nv, -1), free_list[8];
   int high = 1;  // slot 0 = zero
-  auto alloc = [&]() -> int {
-    if (!free_list.empty()) { int s = free_list.back(); free_list.pop_back(); return s; }
+  auto alloc = [&](int col) -> int {
+    const int b = col & 7;
+    if (!free_list[b].empty()) { int s = free_list[b].back(); free_list[b].pop_back(); return s; }
+    while ((high & 7) != b) { free_list[high & 7].push_back(high); ++high; }
     return high++;
   };
   // A stamped entry read by a step is written to a temporary pool slot at the start of that step (so that
@@ -238,6 +248,7 @@ inline void build_warp_program(const SparseProgram& sp, int pool_cap, WarpProgra
     if (!temp_free.empty()) { int t = temp_free.back(); temp_free.pop_back(); return t; }
     return high++;
   };
+  (void)0;
   auto enc = [&](int o) -> int {
     if (o == kNoOperand) return 0;
     if (o < 0) {
@@ -253,7 +264,7 @@ inline void build_warp_program(const SparseProgram& sp, int pool_cap, WarpProgra
   };
   int tt = 0;
   auto release = [&](int o) {
-    if (o >= 0 && fwd_last[o] == tt && pool[o] >= 0) { free_list.push_back(pool[o]); fwd_last[o] = -2; }
+    if (o >= 0 && fwd_last[o] == tt && pool[o] >= 0) { free_list[pool[o] & 7].push_back(pool[o]); fwd_last[o] = -2; }
   };
   WarpStep cur = WarpStep();
   bool open = false;
@@ -298,7 +309,7 @@ inline void build_warp_program(const SparseProgram& sp, int pool_cap, WarpProgra
         release(u.dst_old);   // in-place update when the old version dies here
         release(u.src);
         w.dst = -1;
-        if (fwd_last[u.dst_new] >= 0) { pool[u.dst_new] = alloc(); w.dst = pool[u.dst_new]; }
+        if (fwd_last[u.dst_new] >= 0) { pool[u.dst_new] = alloc(u.col); w.dst = pool[u.dst_new]; }
         wp.upd.push_back(w);
         wp.upd_g.push_back(gslot[u.dst_new]);
         ++tt;
@@ -309,7 +320,7 @@ inline void build_warp_program(const SparseProgram& sp, int pool_cap, WarpProgra
   if ((int)wp.steps.size() != n) return;
   wp.n_pool = high;
   wp.n_upd_total = (long long)wp.upd.size();
-  if (high > pool_cap) return;
+  if (high > pool_cap || high >= 0xffff || wp.max_elim >= 0x7fff) return;
   pack_warp_program(wp, sp);
   wp.ok = true;
 }

@@ -149,7 +149,7 @@ int main(int argc, char** argv) {
       const int* cand = stamp + 12 * n_stamp;
       const int* elim = cand + n_cand;
       const int* upd = rec + ((8 + 12 * n_stamp + n_cand + n_elim + 3) & ~3);
-      const int* upd_g = upd + 4 * n_upd;
+      const int* upd_g = upd + ((2 * n_upd + 3) & ~3);
       for (int q = 0; q < n_stamp; ++q) {
         double c[4];
         memcpy(c, stamp + 12 * q + 4, sizeof c);
@@ -167,10 +167,15 @@ int main(int argc, char** argv) {
       for (int c0 = 0; c0 < n_upd; c0 += 32) {
         const int c1 = std::min(n_upd, c0 + 32);
         std::vector<cd> val(c1 - c0);
-        for (int q = c0; q < c1; ++q) val[q - c0] = pool[upd[4 * q]] - Fm[upd[4 * q + 2]] * pool[upd[4 * q + 1]];
         for (int q = c0; q < c1; ++q) {
-          if (upd[4 * q + 3] >= 0) pool[upd[4 * q + 3]] = val[q - c0];
-          if (upd_g[q] >= 0) G[upd_g[q]] = val[q - c0];
+          const unsigned w0 = (unsigned)upd[2 * q], w1 = (unsigned)upd[2 * q + 1];
+          val[q - c0] = pool[w0 & 0xffff] - Fm[(w1 >> 16) & 0x7fff] * pool[w0 >> 16];
+        }
+        for (int q = c0; q < c1; ++q) {
+          const unsigned w1 = (unsigned)upd[2 * q + 1];
+          if ((w1 & 0xffff) != 0xffff) pool[w1 & 0xffff] = val[q - c0];
+          if (w1 >> 31) G[upd_g[q]] = val[q - c0];
+          else if (upd_g[q] >= 0) { printf("FAIL warp: global copy not flagged\n"); return 1; }
         }
       }
     }
