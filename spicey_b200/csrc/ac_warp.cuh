@@ -110,12 +110,13 @@ __global__ void __launch_bounds__(WARPS * 32) ac_warp_kernel(WarpArgs a) {
       if (s + 1 < n) stage_record((int4*)wsm + ((s + 1) & 1) * a.max_rec16, a.stream + tnext.x, tnext.y, tid, WARPS * 32);
       if (s + 2 < n) tnext = __ldg(a.fwd_tab + s + 2);
       const int* rec = (const int*)(wsm + (s & 1) * a.max_rec16);
-      const int n_cand = rec[0], pidx = rec[1], rcp_g = rec[2], n_elim = rec[3], n_upd = rec[4], n_stamp = rec[5];
+      const int n_cand = rec[0], pidx = rec[1], rcp_g = rec[2], n_elim = rec[3], n_cols = rec[4], n_stamp = rec[5];
       const int* stamp = rec + 8;
       const int* cand = stamp + 12 * n_stamp;
       const int* elim = cand + n_cand;
-      const int2* upd = (const int2*)(rec + ((8 + 12 * n_stamp + n_cand + n_elim + 3) & ~3));
-      const int* upd_g = (const int*)upd + ((2 * n_upd + 3) & ~3);
+      const int* src = elim + n_elim;
+      const int* ops = rec + ((8 + 12 * n_stamp + n_cand + n_elim + n_cols + 3) & ~3);
+      const int* opg = ops + ((n_elim * n_cols + 3) & ~3);
       // stamped entries this step reads (simulateAC.ts:24-60): alpha + j(w*beta - gamma/w), constants in the record
       for (int q = lane; q < n_stamp; q += 32) {
         const double2 c0 = *(const double2*)(stamp + 12 * q + 4), c1 = *(const double2*)(stamp + 12 * q + 8);
@@ -140,25 +141,35 @@ __global__ void __launch_bounds__(WARPS * 32) ac_warp_kernel(WarpArgs a) {
         Fm[e] = fm;
       }
       __syncwarp();
-      // Updates, 32 at a time; operation word {old | src << 16, dst | multiplier << 16 | global-copy flag << 31}.
-      // The loads of chunk c + 1 are issued before chunk c is computed and stored (no operation of a level reads
-      // what another one writes, and a slot is never re-written before its last reader in program order).
-      const int2 idle = make_int2(0, 0xffff);   // zero slot - f * zero slot, no destination
-      int2 opn = lane < n_upd ? upd[lane] : idle;
-      cplx on = pool[opn.x & 0xffff], sn = pool[(unsigned)opn.x >> 16], fn = Fm[((unsigned)opn.y >> 16) & 0x7fff];
-      for (int u0 = 0; u0 < n_upd; u0 += 32) {
-        const int2 op = opn;
-        const cplx o = on, sv = sn, f = fn;
-        if (u0 + 32 < n_upd) {
-          const int un = u0 + 32 + lane;
-          opn = un < n_upd ? upd[un] : idle;
-          on = pool[opn.x & 0xffff]; sn = pool[(unsigned)opn.x >> 16]; fn = Fm[((unsigned)opn.y >> 16) & 0x7fff];
+      // Updates: a dense (rows to eliminate) x (columns of the pivot row) block.  Lanes = columns, so the pivot-row
+      // entry of a lane's column is loaded once per pass and the multiplier of a row is one broadcast; the loop
+      // runs over the rows, each operation word = pool byte offsets (old | flag) | dst << 16.  The loads of
+      // row e + 1 are issued before row e is computed and stored (no operation of a step reads what another one
+      // writes, and a slot is never re-written before its last reader in this execution order).
+      for (int c0 = 0; c0 < n_cols; c0 += 32) {
+        const int cl = c0 + lane;
+        const bool act = cl < n_cols;
+        const cplx sv = pool[act ? src[cl] : 0];
+        const int* opc = ops + (act ? cl : 0);
+        const int* gpc = opg + (act ? cl : 0);
+        const char* pb = (const char*)pool;
+        const unsigned idle = 0xfff00000u;   // zero slot, no destination
+        unsigned opn = (act && n_elim > 0) ? (unsigned)opc[0] : idle;
+        cplx on = *(const cplx*)(pb + (opn & 0xfff0u));
+        for (int e = 0; e < n_elim; ++e) {
+          const unsigned op = opn;
+          const cplx o = on;
+          const cplx f = Fm[e];
+          if (e + 1 < n_elim) {
+            opn = act ? (unsigned)opc[(e + 1) * n_cols] : idle;
+            on = *(const cplx*)(pb + (opn & 0xfff0u));
+          }
+          const cplx v = N::submul<false>(o, f, sv);
+          __syncwarp();   // every operand of the row has been read before any slot is overwritten
+          const unsigned dst = op >> 16;
+          if (dst != 0xfff0u) *(cplx*)((char*)pool + dst) = v;
+          if (op & 1u) G[gpc[e * n_cols]] = v;
         }
-        const cplx v = N::submul<false>(o, f, sv);
-        __syncwarp();   // every operand of the chunk has been read before any slot is overwritten
-        const int dst = op.y & 0xffff;
-        if (dst != 0xffff) pool[dst] = v;
-        if (op.y < 0) G[upd_g[u0 + lane]] = v;
       }
       stage_wait();
     }

@@ -1507,7 +1507,7 @@ int32_t spicey_debug_warp_stats(const spicey_elem_table* table, double pilot_f, 
   build_warp_program(sp, 1 << 24, wp);
   if (!wp.ok) return fail(SPICEY_ERR_UNSUPPORTED, "the warp program builder refused this circuit");
   long long chunks = 0;
-  for (const WarpStep& st : wp.steps) chunks += (st.n_upd + 31) / 32;
+  for (const WarpStep& st : wp.steps) chunks += (long long)st.n_elim * ((st.n_cols + 31) / 32);
   out[0] = wp.n; out[1] = wp.n_pool; out[2] = wp.n_gslots; out[3] = wp.max_elim;
   out[4] = (int32_t)wp.n_upd_total; out[5] = (int32_t)chunks; out[6] = (int32_t)wp.colent.size(); out[7] = sp.n_slots;
   return SPICEY_SUCCESS;

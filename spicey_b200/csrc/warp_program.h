@@ -36,11 +36,13 @@ namespace spicey {
 
 struct WarpStep {
   int cand_begin, n_cand, pidx, rcp_g;   // candidates [cand_begin, +n_cand) in scan order, pilot's choice, global slot of 1/pivot
-  int elim_begin, n_elim, upd_begin, n_upd;
+  int elim_begin, n_elim;                // rows to eliminate (a_ik operands)
+  int col_begin, n_cols;                 // columns of the pivot row right of the pivot (+ rhs): src slot per column
+  int upd_begin;                         // n_elim x n_cols updates, row-major
   int stamp_begin, n_stamp;              // stamped entries this step reads, materialised into temporary pool slots
 };
 struct WarpStamp { int entry, slot; };
-struct WarpUpd { int old_enc, src_enc, f_idx, dst; };   // dst: pool slot or -1 (no forward reader)
+struct WarpUpd { int old_enc, dst; };   // pool slots; dst -1: no forward reader
 struct WarpCol { int rcp_g, begin, count, pad; };        // column j of the back-substitution
 struct WarpColEnt { int row, u_enc; };
 
@@ -57,6 +59,7 @@ struct WarpProgram {
   std::vector<WarpStamp> stamp;
   std::vector<int> cand;         // forward operands: pool slots (stamped entries are materialised per step, see stamp)
   std::vector<int> elim;         // a_ik per eliminated row
+  std::vector<int> src;          // pivot-row entry per column of a step
   std::vector<WarpUpd> upd;
   std::vector<int> upd_g;        // per update: global copy slot or -1
   std::vector<int> rhs_init;     // [n] back operands: >= 0 global slot, < 0 stamped entry ~idx, kWarpZero
@@ -74,11 +77,12 @@ struct WarpProgram {
 
 constexpr int kWarpColGroup = 16;
 
-// step record:  {n_cand, pidx, rcp_g, n_elim, n_upd, n_stamp, 0, 0}
+// step record:  {n_cand, pidx, rcp_g, n_elim, n_cols, n_stamp, 0, 0}
 //               stamp[n_stamp][12] = {slot, 0, 0, 0, (alpha + Re J), Im J, beta, gamma as doubles}
-//               cand[n_cand] elim[n_elim] pad4
-//               upd[n_upd][2] = {old | src << 16, dst (0xffff = none) | multiplier << 16 | has_global_copy << 31} pad4
-//               upd_g[n_upd] (global copy slot, read only when flagged) pad4
+//               cand[n_cand] elim[n_elim] src[n_cols] pad4
+//               op[n_elim][n_cols] = (16 * old | has_global_copy) | (16 * dst) << 16, 0xfff0 = no destination
+//               (byte offsets into the pool: no scaling on the device; the low 4 bits are free for the flag)   pad4
+//               opg[n_elim][n_cols]  global copy slot (read only when flagged)                          pad4
 // back record:  {n_cols, first global slot the NEXT group reads, number of slots it reads, 0}
 //               cols[n_cols][4] = {rcp_g, ent_begin (ints from record start), count, j} ents[...][2] pad4
 inline void pack_warp_program(WarpProgram& wp, const SparseProgram& sp) {
@@ -87,7 +91,7 @@ inline void pack_warp_program(WarpProgram& wp, const SparseProgram& sp) {
   auto pad4 = [&]() { while (wp.stream.size() & 3) wp.stream.push_back(0); };
   for (const WarpStep& st : wp.steps) {
     const size_t o = wp.stream.size();
-    const int hdr[8] = {st.n_cand, st.pidx, st.rcp_g, st.n_elim, st.n_upd, st.n_stamp, 0, 0};
+    const int hdr[8] = {st.n_cand, st.pidx, st.rcp_g, st.n_elim, st.n_cols, st.n_stamp, 0, 0};
     wp.stream.insert(wp.stream.end(), hdr, hdr + 8);
     for (int q = 0; q < st.n_stamp; ++q) {
       const WarpStamp& m = wp.stamp[st.stamp_begin + q];
@@ -102,15 +106,16 @@ inline void pack_warp_program(WarpProgram& wp, const SparseProgram& sp) {
     }
     for (int c = 0; c < st.n_cand; ++c) wp.stream.push_back(wp.cand[st.cand_begin + c]);
     for (int e = 0; e < st.n_elim; ++e) wp.stream.push_back(wp.elim[st.elim_begin + e]);
+    for (int c = 0; c < st.n_cols; ++c) wp.stream.push_back(wp.src[st.col_begin + c]);
     pad4();
-    for (int u = 0; u < st.n_upd; ++u) {
+    const int n_upd = st.n_elim * st.n_cols;
+    for (int u = 0; u < n_upd; ++u) {
       const WarpUpd& w = wp.upd[st.upd_begin + u];
       const int g = wp.upd_g[st.upd_begin + u];
-      wp.stream.push_back((int)((unsigned)w.old_enc | ((unsigned)w.src_enc << 16)));
-      wp.stream.push_back((int)((unsigned)(w.dst < 0 ? 0xffff : w.dst) | ((unsigned)w.f_idx << 16) | (g >= 0 ? 0x80000000u : 0u)));
+      wp.stream.push_back((int)(((unsigned)w.old_enc * 16u) | (g >= 0 ? 1u : 0u) | ((w.dst < 0 ? 0xfff0u : (unsigned)w.dst * 16u) << 16)));
     }
     pad4();
-    for (int u = 0; u < st.n_upd; ++u) wp.stream.push_back(wp.upd_g[st.upd_begin + u]);
+    for (int u = 0; u < n_upd; ++u) wp.stream.push_back(wp.upd_g[st.upd_begin + u]);
     pad4();
     const int len16 = (int)((wp.stream.size() - o) / 4);
     wp.fwd_tab.push_back((int)(o / 4)); wp.fwd_tab.push_back(len16);
@@ -169,22 +174,45 @@ inline void build_warp_program(const SparseProgram& sp, int pool_cap, WarpProgra
   const int n_ir = (int)ir.size();
   int B = n_ir;
   for (int t = 0; t < n_ir; ++t) if (ir[t].kind == SOP_BSUB) { B = t; break; }
-  // ---- uses: last forward reader (fine-grained time) and whether the back-substitution reads the value ----
+  // ---- steps: a PIVOT and the ELIM rows that follow it; every row updates the same columns (the pivot row's
+  //      structural non-zeros right of the pivot, plus the right-hand side) ----
+  struct StepIr { const IrOp* piv; std::vector<const IrOp*> rows; };
+  std::vector<StepIr> sir;
+  for (int t = 0; t < B; ++t) {
+    if (ir[t].kind == SOP_PIVOT) { sir.push_back(StepIr()); sir.back().piv = &ir[t]; }
+    else if (!sir.empty()) sir.back().rows.push_back(&ir[t]);
+    else return;
+  }
+  if ((int)sir.size() != n) return;
+  for (const StepIr& si : sir)
+    for (const IrOp* r : si.rows) {
+      if (r->upd.size() != si.rows[0]->upd.size()) return;
+      for (size_t c = 0; c < r->upd.size(); ++c)
+        if (r->upd[c].col != si.rows[0]->upd[c].col || r->upd[c].src != si.rows[0]->upd[c].src) return;
+    }
+  // Execution order of the kernel (what the slot reuse must be safe for): per step the candidates, the rows'
+  // multipliers, then the updates in passes of 32 columns, each pass row by row.
+  // ---- uses: last forward reader in that order, and whether the back-substitution reads the value ----
   std::vector<int> fwd_last(nv, -1);
   std::vector<char> back_use(nv, 0);
   {
     int tt = 0;
-    for (int t = 0; t < B; ++t) {
-      const IrOp& op = ir[t];
-      if (op.kind == SOP_PIVOT) { for (int o : op.reads) if (o >= 0) fwd_last[o] = tt; ++tt; }
-      else {
-        if (op.reads[0] >= 0) fwd_last[op.reads[0]] = tt;
-        ++tt;
-        for (const Update& u : op.upd) {
-          if (u.dst_old >= 0) fwd_last[u.dst_old] = tt;
-          if (u.src >= 0) fwd_last[u.src] = tt;
-          ++tt;
+    for (const StepIr& si : sir) {
+      for (int o : si.piv->reads) if (o >= 0) fwd_last[o] = tt;
+      ++tt;
+      for (const IrOp* r : si.rows) { if (r->reads[0] >= 0) fwd_last[r->reads[0]] = tt; ++tt; }
+      const int nc = si.rows.empty() ? 0 : (int)si.rows[0]->upd.size();
+      for (int c0 = 0; c0 < nc; c0 += 32) {
+        for (int c = c0; c < std::min(nc, c0 + 32); ++c) {   // the pass loads its pivot-row entries once, up front
+          const int o = si.rows[0]->upd[c].src;
+          if (o >= 0) fwd_last[o] = tt;
         }
+        ++tt;
+        for (const IrOp* r : si.rows)
+          for (int c = c0; c < std::min(nc, c0 + 32); ++c) {
+            if (r->upd[c].dst_old >= 0) fwd_last[r->upd[c].dst_old] = tt;
+            ++tt;
+          }
       }
     }
     for (int t = B; t < n_ir; ++t)
@@ -266,61 +294,63 @@ inline void build_warp_program(const SparseProgram& sp, int pool_cap, WarpProgra
   auto release = [&](int o) {
     if (o >= 0 && fwd_last[o] == tt && pool[o] >= 0) { free_list[pool[o] & 7].push_back(pool[o]); fwd_last[o] = -2; }
   };
-  WarpStep cur = WarpStep();
-  bool open = false;
-  auto close_step = [&]() {
-    if (!open) return;
-    cur.n_elim = (int)wp.elim.size() - cur.elim_begin;
-    cur.n_upd = (int)wp.upd.size() - cur.upd_begin;
+  for (const StepIr& si : sir) {
+    WarpStep cur = WarpStep();
+    cur.stamp_begin = (int)wp.stamp.size();
+    cur.cand_begin = (int)wp.cand.size();
+    cur.n_cand = (int)si.piv->reads.size();
+    cur.pidx = si.piv->pidx;
+    for (int o : si.piv->reads) { const int e = enc(o); if (e < 0) return; wp.cand.push_back(e); }
+    for (int o : si.piv->reads) release(o);
+    cur.rcp_g = (si.piv->def >= 0 && gslot[si.piv->def] >= 0) ? gslot[si.piv->def] : -1;
+    ++tt;
+    cur.elim_begin = (int)wp.elim.size();
+    cur.n_elim = (int)si.rows.size();
+    for (const IrOp* r : si.rows) {
+      const int e = enc(r->reads[0]);
+      if (e < 0) return;
+      wp.elim.push_back(e);
+      release(r->reads[0]);
+      ++tt;
+    }
+    const int nc = si.rows.empty() ? 0 : (int)si.rows[0]->upd.size();
+    cur.col_begin = (int)wp.src.size();
+    cur.n_cols = nc;
+    cur.upd_begin = (int)wp.upd.size();
+    wp.upd.resize(wp.upd.size() + (size_t)cur.n_elim * nc);
+    wp.upd_g.resize(wp.upd.size(), -1);
+    wp.src.resize(wp.src.size() + nc);
+    for (int c0 = 0; c0 < nc; c0 += 32) {
+      for (int c = c0; c < std::min(nc, c0 + 32); ++c) {
+        const int e = enc(si.rows[0]->upd[c].src);
+        if (e < 0) return;
+        wp.src[cur.col_begin + c] = e;
+      }
+      for (int c = c0; c < std::min(nc, c0 + 32); ++c) release(si.rows[0]->upd[c].src);
+      ++tt;
+      for (int e = 0; e < cur.n_elim; ++e)
+        for (int c = c0; c < std::min(nc, c0 + 32); ++c) {
+          const Update& u = si.rows[e]->upd[c];
+          WarpUpd w;
+          w.old_enc = enc(u.dst_old);
+          if (w.old_enc < 0) return;
+          release(u.dst_old);   // in-place update when the old version dies here
+          w.dst = -1;
+          if (fwd_last[u.dst_new] >= 0) { pool[u.dst_new] = alloc(u.col); w.dst = pool[u.dst_new]; }
+          wp.upd[cur.upd_begin + (size_t)e * nc + c] = w;
+          wp.upd_g[cur.upd_begin + (size_t)e * nc + c] = gslot[u.dst_new];
+          ++tt;
+        }
+    }
     cur.n_stamp = (int)wp.stamp.size() - cur.stamp_begin;
     for (const auto& kv : stamped) temp_free.push_back(kv.second);
     stamped.clear();
     wp.max_elim = std::max(wp.max_elim, cur.n_elim);
     wp.steps.push_back(cur);
-    open = false;
-  };
-  for (int t = 0; t < B; ++t) {
-    const IrOp& op = ir[t];
-    if (op.kind == SOP_PIVOT) {
-      close_step();
-      cur = WarpStep();
-      cur.stamp_begin = (int)wp.stamp.size();
-      cur.cand_begin = (int)wp.cand.size();
-      cur.n_cand = (int)op.reads.size();
-      cur.pidx = op.pidx;
-      for (int o : op.reads) { const int e = enc(o); if (o >= 0 && e < 0) return; wp.cand.push_back(e); }
-      for (int o : op.reads) release(o);
-      cur.rcp_g = (op.def >= 0 && gslot[op.def] >= 0) ? gslot[op.def] : -1;
-      cur.elim_begin = (int)wp.elim.size();
-      cur.upd_begin = (int)wp.upd.size();
-      open = true;
-      ++tt;
-    } else {
-      const int row = (int)wp.elim.size() - cur.elim_begin;
-      { const int e = enc(op.reads[0]); if (op.reads[0] >= 0 && e < 0) return; wp.elim.push_back(e); }
-      release(op.reads[0]);
-      ++tt;
-      for (const Update& u : op.upd) {
-        WarpUpd w;
-        w.old_enc = enc(u.dst_old);
-        w.src_enc = enc(u.src);
-        if ((u.dst_old >= 0 && w.old_enc < 0) || (u.src >= 0 && w.src_enc < 0)) return;
-        w.f_idx = row;
-        release(u.dst_old);   // in-place update when the old version dies here
-        release(u.src);
-        w.dst = -1;
-        if (fwd_last[u.dst_new] >= 0) { pool[u.dst_new] = alloc(u.col); w.dst = pool[u.dst_new]; }
-        wp.upd.push_back(w);
-        wp.upd_g.push_back(gslot[u.dst_new]);
-        ++tt;
-      }
-    }
   }
-  close_step();
-  if ((int)wp.steps.size() != n) return;
   wp.n_pool = high;
   wp.n_upd_total = (long long)wp.upd.size();
-  if (high > pool_cap || high >= 0xffff || wp.max_elim >= 0x7fff) return;
+  if (high > pool_cap || high >= 0xfff) return;   // 16-bit byte offsets, 0xfff0 reserved
   pack_warp_program(wp, sp);
   wp.ok = true;
 }

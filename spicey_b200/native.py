@@ -115,7 +115,7 @@ def warp_program_stats(table: "ElemTable", pilot_f: float = 1000.0) -> dict:
     st = (C.c_int32 * 8)()
     ts = table.struct()
     _check(lib, lib.spicey_debug_warp_stats(C.byref(ts), pilot_f, st))
-    keys = ("nvar", "pool_slots", "global_slots", "max_rows_per_step", "updates", "update_chunks", "backsub_entries",
+    keys = ("nvar", "pool_slots", "global_slots", "max_rows_per_step", "updates", "update_rows", "backsub_entries",
             "thread_tier_slots")
     return dict(zip(keys, list(st)))
 
