@@ -367,15 +367,19 @@ def run_native(args):
             dense = {"bound": "fp64", "achieved": ach_f, "peak": fp64_peak, "unit": "TFLOP/s",
                      "frac": ach_f / fp64_peak, "flops_per_solve_dense": wl["flops_per_unit"],
                      "peak_source": "own DFMA-loop microbenchmark in this run (MEASURED_PEAKS.json has no FP64 figure)"}
-            if tier in (native.TIER_SPARSE, native.TIER_SPARSE_JIT):
+            if tier in (native.TIER_SPARSE, native.TIER_SPARSE_JIT, native.TIER_SPARSE_WARP):
                 # The sparse program executes ~1e3 flop per solve instead of the dense 7.7e5, so the FP64
                 # pipe cannot bind; what binds is HBM: SURVEY 8(d)'s algorithmic bytes per solve.
                 ach = units * wl["bytes_per_unit"] / (kern_ms * 1e-3) / 1e9
                 roof = {"bound": "hbm", "achieved": ach, "peak": peak_hbm, "unit": "GB/s", "frac": ach / peak_hbm,
                         "traffic": None, "peak_source": peak_src, "bytes_per_solve": wl["bytes_per_unit"],
                         "dense_fp64_equivalent": dense,
+                        "executed_fp64": {"complex_fma_per_solve": int(st_last["program_cfma"]),
+                                          "achieved": units * st_last["program_cfma"] * 8 / (kern_ms * 1e-3) / 1e12,
+                                          "peak": fp64_peak, "unit": "TFLOP/s",
+                                          "frac": units * st_last["program_cfma"] * 8 / (kern_ms * 1e-3) / 1e12 / fp64_peak},
                         "note": "sparse static-pivot LU program (verified per point, dense fallback; tier 5 = compiled "
-                                "straight-line kernel, tier 4 = interpreted): HBM-bound; "
+                                "straight-line kernel, tier 4 = interpreted, tier 7 = one warp per system): HBM-bound; "
                                 "dense_fp64_equivalent is SURVEY 8(d)'s dense flop figure per solve over the "
                                 "measured DFMA peak and exceeds 1 because structurally zero work is never executed"}
             else:
