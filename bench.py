@@ -50,14 +50,57 @@ def read_peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    """SM clock and throttle reasons sampled DURING the timed region.
+
+    NVML is polled from a thread every millisecond (a cfg2 step is 0.7 ms, far below nvidia-smi's 100 ms
+    loop); nvidia-smi is the fallback when the NVML binding is missing."""
     Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    BITS = (("hw_slowdown", 0x8), ("hw_thermal_slowdown", 0x40), ("sw_thermal_slowdown", 0x20), ("sw_power_cap", 0x4))
 
-    def __init__(self, index):
-        self.index, self.rows, self.proc = index, [], None
+    def __init__(self, index, uuid=None):
+        self.index, self.uuid, self.rows, self.proc = index, uuid, [], None
+        self.nvml, self.handle, self.samples, self.masks, self.run = None, None, [], 0, False
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            h = None
+            if uuid:
+                for cand in (uuid, "GPU-" + uuid):
+                    try:
+                        h = pynvml.nvmlDeviceGetHandleByUUID(cand.encode() if isinstance(cand, str) else cand)
+                        break
+                    except Exception:
+                        try:
+                            h = pynvml.nvmlDeviceGetHandleByUUID(cand)
+                            break
+                        except Exception:
+                            h = None
+            if h is None:
+                h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.nvml, self.handle = pynvml, h
+        except Exception:
+            self.nvml = None
+
+    def _poll(self):
+        nv, h = self.nvml, self.handle
+        while self.run:
+            try:
+                self.samples.append(float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)))
+                try:
+                    self.masks |= int(nv.nvmlDeviceGetCurrentClocksEventReasons(h))
+                except Exception:
+                    self.masks |= int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(h))
+            except Exception:
+                pass
+            time.sleep(0.001)
 
     def start(self):
+        if self.nvml is not None:
+            self.run = True
+            self.thread = threading.Thread(target=self._poll, daemon=True)
+            self.thread.start()
+            return
         try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
@@ -71,7 +114,22 @@ class ClockSampler:
         for line in self.proc.stdout:
             self.rows.append([c.strip() for c in line.split(",")])
 
+    def pause(self):
+        """End of a sampled region (NVML path): keeps what was collected."""
+        if self.nvml is not None and self.run:
+            self.run = False
+            self.thread.join(timeout=1)
+
     def stop(self):
+        if self.nvml is not None:
+            self.pause()
+            try:
+                mx = float(self.nvml.nvmlDeviceGetMaxClockInfo(self.handle, self.nvml.NVML_CLOCK_SM))
+            except Exception:
+                mx = None
+            reasons = [n for n, bit in self.BITS if self.masks & bit]
+            return {"sm_mhz": float(np.median(self.samples)) if self.samples else None, "sm_max_mhz": mx,
+                    "reasons": reasons, "samples": len(self.samples), "source": "nvml, 1 ms polling"}
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         time.sleep(0.15)
@@ -85,7 +143,7 @@ class ClockSampler:
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         reasons = [n for i, n in enumerate(names) if any(len(r) >= 6 and r[2 + i] == "Active" for r in self.rows)]
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": reasons, "samples": len(sm)}
+                "reasons": reasons, "samples": len(sm), "source": "nvidia-smi -lms 100"}
 
 
 def dist_env():
@@ -315,7 +373,11 @@ def run_native(args):
         step_resident()
     barrier()
     check()
-    sampler = ClockSampler(local)
+    try:
+        dev_uuid = str(torch.cuda.get_device_properties(local).uuid)
+    except Exception:
+        dev_uuid = None
+    sampler = ClockSampler(local, dev_uuid)
     if rank == 0:
         sampler.start()
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
@@ -329,7 +391,9 @@ def run_native(args):
         launches += eng.stats()["kernel_launches"]
     e1.record(stream)
     barrier()
-    clocks = sampler.stop() if rank == 0 else None
+    if rank == 0:
+        sampler.pause()
+    n_timed_samples = len(sampler.samples)
     total_ms = e0.elapsed_time(e1)
     kern_ms = float(np.mean([a.elapsed_time(b) for a, b in ev]))
     st_last = eng.stats()
@@ -344,12 +408,17 @@ def run_native(args):
     e2e_steps = max(1, min(args.steps, 3))
     step_e2e()
     barrier()
+    if rank == 0 and sampler.nvml is not None and n_timed_samples < 5:
+        sampler.start()   # a timed region of a few ms gives few samples: the e2e region (same kernels) adds its own
     t0 = time.perf_counter()
     for _ in range(e2e_steps):
         st = step_e2e()
         assert st == 0
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
+    clocks = sampler.stop() if rank == 0 else None
+    if clocks is not None:
+        clocks["samples_in_timed_region"] = n_timed_samples
     es = eng.stats()
     t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
     if world > 1:
@@ -411,7 +480,10 @@ def run_native(args):
             "cpu_baseline": {"value": cpu_v, "unit": "solves/s", "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": world * units * e2e_steps / e2e_s, "unit": "solves/s",
                     "h2d_bytes_per_step": int(es["h2d_bytes"]), "d2h_bytes_per_step": int(es["d2h_bytes"]),
-                    "steps": e2e_steps, "kernel_ms_per_step": es["kernel_ms"]},
+                    "steps": e2e_steps, "kernel_ms_per_step": es["kernel_ms"],
+                    "pcie_gbs": (int(es["h2d_bytes"]) + int(es["d2h_bytes"])) * e2e_steps / e2e_s / 1e9,
+                    "note": "host buffers pinned; bound by the PCIe link when pcie_gbs is near the link rate "
+                            "(results are 3,080 B per cfg2 solve)"},
             "gpu_launches": int(launches),
             "clocks": clocks,
         }
