@@ -388,6 +388,89 @@ def test_full_size_properties_cfg2(eng):
     assert rel_err(x[sub], xr) <= AC_TOL
 
 
+def test_full_size_properties_cfg3(eng):
+    """BASELINE cfg 3 at full size (65,536 instances x 1,002 recorded steps) with the default tier policy: the
+    compiled transient kernel (tier 6) takes it; every status 0; the source node follows the pulse exactly;
+    KCL at node 2 (i_R = i_L + i_C) at every step; instances spread over the batch match the oracle at 1e-6;
+    and the generic kernel (NO_JIT) agrees on a slice."""
+    import spicey_b200 as sp
+    n = 65536
+    ov = w.rlc_tank_overrides(n)
+    ck = parse_netlist(w.RLC_TANK)
+    got = sp.simulate_tran_batch(ck, n_inst=n, overrides=ov, engine=eng)
+    assert eng.stats()["tier"] == native.TIER_TRAN_JIT
+    assert got["steps"] == 1001 and got["v"].shape == (1002, 2, n) and got["status"].max() == 0
+    names = list(got["element_names"])
+    iR, iL, iC = (got["ielem"][:, names.index(k), :] for k in ("R1", "L1", "C1"))
+    scale = np.max(np.abs(iR))
+    assert np.max(np.abs(iR - iL - iC)) <= 1e-9 * scale
+    vsrc = got["v"][:, 0, :]
+    assert np.all(vsrc[0] == 0.0) and np.max(np.abs(vsrc[1:] - 1.0)) == 0.0    # PULSE(0 1 0 1n 1n 1 2), dt ~ 1 us
+    pick = np.linspace(0, n - 1, 48).astype(int)
+    ck2 = parse_netlist(w.RLC_TANK)
+    dt, steps = compute_effective_time_step(ck2.analyses.tran.dt, ck2.analyses.tran.tstop)
+    v, ie, iters, st, state = co.tran_solve(ck2, dt, steps, n_inst=len(pick), overrides={k: a[pick] for k, a in ov.items()},
+                                            nthreads=8)
+    ref_v, ref_i = np.transpose(v, (1, 2, 0)), np.transpose(ie, (1, 2, 0))
+    assert np.max(np.abs(got["v"][:, :, pick] - ref_v)) <= TRAN_TOL * np.max(np.abs(ref_v))
+    assert np.max(np.abs(got["ielem"][:, :, pick] - ref_i)) <= TRAN_TOL * np.max(np.abs(ref_i))
+    m = 2048
+    gen = sp.simulate_tran_batch(parse_netlist(w.RLC_TANK), n_inst=m, overrides={k: a[:m] for k, a in ov.items()},
+                                 engine=eng, flags=native.FLAG_NO_JIT)
+    assert eng.stats()["tier"] == native.TIER_THREAD
+    assert np.max(np.abs(gen["v"] - got["v"][:, :, :m])) <= 1e-9 * np.max(np.abs(gen["v"]))
+
+
+def test_large_slice_properties_cfg5(eng):
+    """BASELINE cfg 5 (diode rectifier) on 16,384 instances spread over the 100,000-instance sweep: 49 M
+    instance-steps, so the default policy compiles (tier 6); status 0; the diode current is never below -Is (no
+    reverse conduction), the recorded R and C currents follow from the recorded voltages; a subsample matches
+    the oracle at 1e-6."""
+    import spicey_b200 as sp
+    n = 16384
+    full = w.rectifier_overrides(100000)
+    pick = np.linspace(0, 99999, n).astype(int)
+    ov = {k: v[pick] for k, v in full.items()}
+    got = sp.simulate_tran_batch(parse_netlist(w.RECTIFIER), n_inst=n, overrides=ov, engine=eng)
+    assert eng.stats()["tier"] == native.TIER_TRAN_JIT
+    assert got["steps"] == 3000 and got["status"].max() == 0
+    names = list(got["element_names"])
+    iD, iR, iC = (got["ielem"][:, names.index(k), :] for k in ("D1", "R1", "C1"))
+    assert np.all(iD >= -1.0001 * ov["D1.is"][None, :])
+    # (no KCL check at the output node: the reference records the diode current from the unclamped exponential
+    #  at the new solution while the step was solved with the model linearised about vdPrev — hazard H6)
+    vout = got["v"][:, list(got["node_names"]).index("out"), :]
+    assert np.max(np.abs(iR - vout / ov["R1"][None, :])) <= 1e-12 * np.max(np.abs(iR))
+    assert np.max(np.abs(iC[1:] - ov["C1"][None, :] * (vout[1:] - vout[:-1]) / got["dt"])) <= 1e-9 * np.max(np.abs(iC))
+    sub = np.linspace(0, n - 1, 40).astype(int)
+    ck2 = parse_netlist(w.RECTIFIER)
+    dt, steps = compute_effective_time_step(ck2.analyses.tran.dt, ck2.analyses.tran.tstop)
+    v, ie, iters, st, state = co.tran_solve(ck2, dt, steps, n_inst=len(sub), overrides={k: a[sub] for k, a in ov.items()},
+                                            nthreads=8)
+    ref_v, ref_i = np.transpose(v, (1, 2, 0)), np.transpose(ie, (1, 2, 0))
+    vs = np.max(np.abs(ref_v), axis=0, keepdims=True)
+    assert np.max(np.abs(got["v"][:, :, sub] - ref_v) / vs) <= TRAN_TOL
+    cs = np.maximum(np.max(np.abs(ref_i), axis=0, keepdims=True), 1e-30)
+    assert np.max(np.abs(got["ielem"][:, :, sub] - ref_i) / cs) <= TRAN_TOL
+
+
+def test_mesh_default_policy_takes_the_warp_tier(eng):
+    """cfg 4 topology, 4,096 frequencies, default flags: the sparse path engages (>= 2048 points), the program is
+    large (thread-tier workspace >= 512 slots), so the warp-per-system tier runs; KCL at the source node and a
+    subsample against the oracle."""
+    import spicey_b200 as sp
+    ck = parse_netlist(w.rc_mesh(16))
+    freqs = np.array(sp.analysis.ac_frequencies(ck))[::1953][:4096]
+    out = sp.simulate_ac_batch(ck, freqs, engine=eng, flags=SM)
+    stt = eng.stats()
+    assert stt["tier"] == native.TIER_SPARSE_WARP and stt["fallback_solves"] == 0 and out["status"].max() == 0
+    x = out["x"][0]
+    assert np.max(np.abs(x[:, 0] - 1.0)) <= 1e-15              # n0_0 is the source node
+    sub = slice(0, None, 64)
+    xr, ier, st = co.ac_solve(ck, freqs[sub], nthreads=8)
+    assert rel_err(x[sub], xr) <= AC_TOL and rel_err(out["ielem"][0][sub], ier) <= AC_TOL
+
+
 def test_multi_device_handle_shards_contiguous_ranges(eng):
     """spicey_create with two devices: the library shards the batch axis in contiguous ranges (no collective)
     and the result equals the single-device one.  Skipped on a one-GPU box."""
