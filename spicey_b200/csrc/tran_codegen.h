@@ -233,7 +233,7 @@ inline std::string generate_tran_kernel_source(const TranCodegenInput& in) {
   s += "  const unsigned pitch = (unsigned)NL * 8u;   // bytes between consecutive rows (n_local < 2^29 checked by the host)\n";
   s += "  int* ito = a.iters ? a.iters + li : nullptr;\n";
   s += "  const size_t v_stride = (size_t)pitch * " + N(nn) + "u, i_stride = (size_t)pitch * " + N(ne) + "u;\n";
-  s += "  long long step = 0;\n";
+  s += "  long long step = 0;\n  int pat = -1;   // pivot sequence of the previous factorisation (diode circuits)\n";
   s += "  for (; step < S1 && status == 0; ++step) {\n";
   for (int e = oV; e < oS; ++e) {
     const int k = e - oV;
@@ -269,11 +269,78 @@ inline std::string generate_tran_kernel_source(const TranCodegenInput& in) {
     s += "        jd" + E + " = id - gd" + E + " * vlim;\n      }\n";
     rhs(e, "jd" + E);
   }
-  if (has_d) s += load_matrix("      ") + "      status = lu.factor();\n";
-  else if (has_sw) s += "      if (!factored) {\n" + load_matrix("        ") + "        status = lu.factor();\n        factored = true;\n      }\n";
-  if (dyn) s += "      if (status != 0) break;\n";
-  for (int i = 0; i < nvar; ++i) s += "      x[" + N(i) + "] = b" + N(i) + ";\n";
-  s += "      lu.solve(x);\n";
+  const bool fast_piv = has_d && nvar <= 4;
+  if (fast_piv) {
+    // Diode circuits re-factor at every solve, and the select-based pivoting is most of a step's instructions
+    // (63 of 248 for cfg 5).  The pivot sequence rarely changes from one solve to the next, so each of the NV!
+    // possible sequences gets its own straight-line elimination of [A | b] on named scalars (no selects, and
+    // the entries that are structurally 0 or 1 fold away); the case of the previous solve's sequence runs
+    // first and checks every pivot it assumes against the reference's rule (first maximum wins,
+    // solveReal.ts:16-26).  If one check fails the generic code below decides, as it does for the first solve.
+    // Same operations on the same operands in the same order either way.
+    for (int i = 0; i < nvar; ++i)
+      for (int j = 0; j < nvar; ++j) s += "      const double m_" + N(i) + "_" + N(j) + " = " + entry(i, j) + ";\n";
+    s += "      bool redo = true;\n      switch (pat) {\n";
+    std::vector<int> perm(nvar, 0);
+    for (int k = 0; k < nvar; ++k) perm[k] = k;
+    for (;;) {
+      int id = 0, mul = 1;
+      for (int k = 0; k < nvar; ++k) { id += perm[k] * mul; mul *= nvar; }
+      s += "        case " + N(id) + ": {\n";
+      std::vector<int> L(nvar);
+      for (int i = 0; i < nvar; ++i) L[i] = i;
+      auto A = [&](int r, int c) { return "a" + N(r) + "_" + N(c); };
+      for (int r = 0; r < nvar; ++r) {
+        for (int c = 0; c < nvar; ++c) s += "          double " + A(r, c) + " = m_" + N(r) + "_" + N(c) + ";\n";
+        s += "          double " + A(r, nvar) + " = b" + N(r) + ";\n";
+      }
+      s += "          bool okp = true;\n";
+      for (int k = 0; k < nvar; ++k) {
+        const int j = perm[k], prow = L[j];
+        s += "          { const double vj = fabs(" + A(prow, k) + "); okp = okp && (vj >= EPS);\n";
+        for (int q = k; q < nvar; ++q) {
+          if (q == j) continue;
+          s += "            okp = okp && " + std::string(q < j ? "(fabs(" + A(L[q], k) + ") < vj)" : "!(fabs(" + A(L[q], k) + ") > vj)") + ";\n";
+        }
+        s += "          }\n";
+        std::swap(L[k], L[j]);
+        s += "          const double rp" + N(k) + " = rcp_nr(" + A(prow, k) + ");\n";
+        for (int q = k + 1; q < nvar; ++q) {
+          const int r = L[q];
+          s += "          { double mm = " + A(r, k) + " * rp" + N(k) + "; mm = (fabs(mm) < EPS) ? 0.0 : mm;\n";
+          for (int c = k + 1; c <= nvar; ++c) s += "            " + A(r, c) + " = fma(-mm, " + A(prow, c) + ", " + A(r, c) + ");\n";
+          s += "          }\n";
+        }
+      }
+      for (int i = nvar - 1; i >= 0; --i) {
+        const int r = L[i];
+        s += "          double xx" + N(i) + " = " + A(r, nvar) + ";\n";
+        for (int c = i + 1; c < nvar; ++c) s += "          xx" + N(i) + " = fma(-" + A(r, c) + ", xx" + N(c) + ", xx" + N(i) + ");\n";
+        s += "          xx" + N(i) + " *= rp" + N(i) + ";\n";
+      }
+      s += "          if (okp) {";
+      for (int i = 0; i < nvar; ++i) s += " x[" + N(i) + "] = xx" + N(i) + ";";
+      s += " redo = false; }\n        } break;\n";
+      // next pivot sequence: perm[k] in [k, nvar)
+      int k = nvar - 1;
+      while (k >= 0 && perm[k] == nvar - 1) { perm[k] = k; --k; }
+      if (k < 0) break;
+      ++perm[k];
+    }
+    s += "        default: break;\n      }\n      if (redo) {\n";
+    for (int i = 0; i < nvar; ++i)
+      for (int j = 0; j < nvar; ++j) s += "        lu.f[" + N(i) + "][" + N(j) + "] = m_" + N(i) + "_" + N(j) + ";\n";
+    s += "        status = lu.factor();\n        if (status != 0) break;\n";
+    for (int i = 0; i < nvar; ++i) s += "        x[" + N(i) + "] = b" + N(i) + ";\n";
+    s += "        lu.solve(x);\n        pat = 0;\n";
+    s += "        { int mul = 1; for (int k = 0; k < NV; ++k) { pat += lu.perm[k] * mul; mul *= NV; } }\n      }\n";
+  } else {
+    if (has_d) s += load_matrix("      ") + "      status = lu.factor();\n";
+    else if (has_sw) s += "      if (!factored) {\n" + load_matrix("        ") + "        status = lu.factor();\n        factored = true;\n      }\n";
+    if (dyn) s += "      if (status != 0) break;\n";
+    for (int i = 0; i < nvar; ++i) s += "      x[" + N(i) + "] = b" + N(i) + ";\n";
+    s += "      lu.solve(x);\n";
+  }
   if (has_sw) {                                                     // :108-128
     s += "      bool switched = false;\n";
     for (int e = oS; e < oD; ++e) {
