@@ -231,8 +231,8 @@ enum {
  * (tier 5) for this element table into buf (NUL-terminated, truncated to cap) and returns the
  * size needed, or -1 when the sparse path does not apply.  stats_out[8], optional: values crossing
  * into the back-substitution, of those in shared memory, distinct stamped values, micro-ops,
- * complex FMAs, reciprocals, bulk-copy groups, staging waits.  with_ielem: bit 0 element currents, bit 1
- * bulk (series-major) stores, bits 8-15 staging ring slots, bits 16-23 __syncthreads period. */
+ * complex FMAs, reciprocals, virtual values, interpreter workspace slots.  with_ielem: bit 0 element
+ * currents, bits 16-23 __syncthreads period. */
 int64_t spicey_debug_sparse_source(const spicey_elem_table* table, double pilot_f, int32_t block, int32_t min_blocks,
                                    int32_t smem_slots, int32_t with_ielem, char* buf, int64_t cap, int32_t* stats_out);
 

@@ -20,8 +20,12 @@
 //  * Arithmetic is specialised on what the operand structurally is: a stamped entry that is purely real
 //    (1/R sums), purely imaginary (w*C - 1/(w*L)) or +-1 (source rows) costs half the DFMAs of a
 //    complex multiply, with bit-identical results (the dropped terms are exact zeros).
-//  * The reference's `|f| < EPS -> skip row` (solveComplex.ts:46) is applied as a select on the updated
-//    values, so the test is off the dependent chain pivot -> multiplier -> update -> next pivot.
+//  * The reference's `|f| < EPS -> skip row` (solveComplex.ts:46) zeroes the multiplier (branch-free); 1/|pivot|^2
+//    is a MUFU seed + two Newton steps, so the whole elimination is one basic block; real constants are
+//    operands from a __constant__ table instead of 64-bit immediates.
+//  * A bulk-copy (cp.async.bulk) epilogue staging the results in freed factor slots was built and measured
+//    slower (the issuing warp pays ~90 cycles per copy, tools/micro/bulk_store.cu); results leave as plain
+//    predicated 16-byte stores, 512 contiguous bytes per warp and series.
 #pragma once
 #include <algorithm>
 #include <cstdio>
@@ -44,10 +48,8 @@ struct CodegenInput {
 struct CodegenOptions {
   int block = 128;        // threads per CTA
   int min_blocks = 2;     // __launch_bounds__ second argument
-  int smem_slots = 48;    // shared-memory double2 slots per thread (factor values + staging ring)
+  int smem_slots = 48;    // shared-memory double2 slots per thread for the factor values
   bool with_ielem = true; // false: the caller passed ielem = NULL, no current is computed
-  bool bulk_store = false; // series-major results leave through shared memory and cp.async.bulk (needs series_ld != 0; measured slower)
-  int ring_slots = 6;     // bulk_store: slots reserved for staging results (more become free as factors are consumed)
   int sync_every = 0;     // > 0: __syncthreads() every that many pivots / back-substitution rows (instruction-cache locality)
 };
 
@@ -56,8 +58,6 @@ struct CodegenStats {
   int smem_slots = 0;     // of those, placed in shared memory
   size_t smem_bytes = 0;  // dynamic shared memory per CTA
   int n_classes = 0;      // distinct stamped values
-  int n_groups = 0;       // bulk-copy groups per system
-  int n_waits = 0;        // of which had to wait for a staging slot
 };
 
 namespace codegen_detail {
@@ -105,13 +105,6 @@ extern __shared__ double2 sm[];
 // local memory) across the whole elimination, which is exactly what the placement is meant to avoid.
 #define SMST(off, v) asm volatile("st.shared.v2.f64 [%0+" #off "], {%1, %2};" :: "r"(sbase), "d"((v).x), "d"((v).y) : "memory")
 #define SMLD(v, off) asm volatile("ld.shared.v2.f64 {%0, %1}, [%2+" #off "];" : "=d"((v).x), "=d"((v).y) : "r"(sbase) : "memory")
-// Results: a staged slot row of one warp is 32 points x 16 B = one contiguous 512-byte piece of a series.
-// Lane 0 hands it to the bulk-copy engine (no registers are held by stores in flight, full lines reach L2).
-#define FENCE_ASYNC() asm volatile("fence.proxy.async.shared::cta;" ::: "memory")
-#define BULK_ST(gptr, off) asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1+" #off "], %2;" :: "l"(gptr), "r"(sbase), "r"(wbytes) : "memory")
-#define BULK_COMMIT() asm volatile("cp.async.bulk.commit_group;" ::: "memory")
-#define BULK_WAIT_READ(n) asm volatile("cp.async.bulk.wait_group.read " #n ";" ::: "memory")
-#define BULK_WAIT_ALL() asm volatile("cp.async.bulk.wait_group 0;" ::: "memory")
 )SRC";
 }
 
@@ -205,28 +198,21 @@ inline std::string generate_sparse_kernel_source(const CodegenInput& in, const C
       if (b >= 0) last[b] = std::max(last[b], when);
     }
   }
-  // ---- shared-memory placement of the cross-phase values ----
-  // direct stores: the longest-lived values go to shared memory (registers keep what is consumed first);
-  // bulk stores:   the longest-lived values stay in registers, so that the back-substitution frees shared
-  //                memory slots from its first row on — they become the staging ring of the results.
-  const bool bulk = opt.bulk_store;
-  const int ring0 = bulk ? std::max(1, std::min(opt.ring_slots, opt.smem_slots)) : 0;
+  // ---- shared-memory placement of the cross-phase values: the longest-lived go to shared memory, registers
+  //      keep what the back-substitution consumes first ----
   std::vector<int> slot_of(sp.n_virtual, -1);
   int ns = 0;
   {
-    std::vector<std::pair<int, int>> saved;  // (lifetime key, v)
+    std::vector<std::pair<int, int>> saved;  // (-lifetime, v)
     for (int v = 0; v < sp.n_virtual; ++v)
-      if (deft[v] >= 0 && deft[v] < B && last[v] >= B)
-        saved.push_back(std::make_pair(bulk ? (last[v] - deft[v]) : -(last[v] - deft[v]), v));
+      if (deft[v] >= 0 && deft[v] < B && last[v] >= B) saved.push_back(std::make_pair(-(last[v] - deft[v]), v));
     std::sort(saved.begin(), saved.end());
     st.n_saved = (int)saved.size();
-    ns = std::min<int>(std::max(0, opt.smem_slots - ring0), (int)saved.size());
+    ns = std::min<int>(std::max(0, opt.smem_slots), (int)saved.size());
     for (int i = 0; i < ns; ++i) slot_of[saved[i].second] = i;
     st.smem_slots = ns;
-    const int total = bulk ? std::max(opt.smem_slots, ring0) : ns;
-    st.smem_bytes = (size_t)total * opt.block * 16;
+    st.smem_bytes = (size_t)ns * opt.block * 16;
   }
-  const int total_slots = (int)(st.smem_bytes / ((size_t)opt.block * 16));
   auto soff = [&](int slot) { return std::to_string((long long)slot * opt.block * 16); };
 
   auto opnd = [&](int o) -> Opnd {
@@ -246,7 +232,6 @@ inline std::string generate_sparse_kernel_source(const CodegenInput& in, const C
   s += "  const unsigned ld = a.series_ld ? (unsigned)a.series_ld : 1u;\n";
   s += "  const unsigned sbase = (unsigned)__cvta_generic_to_shared(sm) + threadIdx.x * 16u;\n";
   s += "  const long long stride = (long long)gridDim.x * BLOCK, plast = a.p_count - 1;\n";
-  if (bulk) s += "  const unsigned lane = threadIdx.x & 31u;\n";
   s += "  double fnext = a.freqs[min((long long)blockIdx.x * BLOCK + threadIdx.x, plast)];\n";
   // block-uniform trip count: lanes past the end solve the last point again and store nothing
   s += "  for (long long base = (long long)blockIdx.x * BLOCK; base < a.p_count; base += stride) {\n";
@@ -256,7 +241,6 @@ inline std::string generate_sparse_kernel_source(const CodegenInput& in, const C
   if (need_iw) s += "    const double iw = 1.0 / w;\n";
   s += "    char* const xb = (char*)(a.series_ld ? a.x + p : a.x + p * a.n);\n";
   if (opt.with_ielem) s += "    char* const ib = (char*)(a.series_ld ? a.ielem + p : a.ielem + p * a.n_ac_elem);\n";
-  if (bulk) s += "    const unsigned wbytes = (unsigned)max(0ll, min(32ll, a.p_count - p)) * 16u;  // lane 0: bytes of this warp's piece\n";
   s += "    bool ok = true, bad = false;\n    double mp, m, inv;\n    double2 r, fm;\n";
   for (double L : sp.ind_L)  // inductor guards of simulateAC.ts:47-51 are value dependent: dense kernel decides
     s += "    { const double d = w * " + lit(L) + "; bad = bad || fabs(d) < EPS || d * d < EPS; }\n";
@@ -294,50 +278,12 @@ inline std::string generate_sparse_kernel_source(const CodegenInput& in, const C
   };
   auto off = [&](int k) { return "(size_t)ld * " + std::to_string(16ll * k) + "u"; };
 
-  // ---- results: direct predicated stores, or staged rows handed to the bulk-copy engine ----
+  // ---- results: predicated stores, emitted as soon as the values exist ----
   struct Out { bool cur; int k; std::string re, im; };
   std::vector<Out> pending;
-  std::vector<int> free_slots;                   // LIFO
-  std::vector<std::pair<int, int>> inflight;     // (slot, group), oldest first
-  size_t inflight_head = 0;
-  int n_groups = 0;
-  for (int q = total_slots - 1; q >= ns; --q) free_slots.push_back(q);
-  const int chunk_cap = std::max(1, total_slots - ns);
   auto flush_outputs = [&]() {
-    if (pending.empty()) return;
-    if (!bulk) {
-      for (const Out& o : pending)
-        s += std::string("    if (valid) *(double2*)(") + (o.cur ? "ib" : "xb") + " + " + off(o.k) + ") = D2(" + o.re + ", " + o.im + ");\n";
-      pending.clear();
-      return;
-    }
-    for (size_t b0 = 0; b0 < pending.size(); b0 += chunk_cap) {
-      const size_t b1 = std::min(pending.size(), b0 + (size_t)chunk_cap);
-      std::vector<int> slots;
-      int wait_n = -1;
-      for (size_t q = b0; q < b1; ++q) {
-        if (free_slots.empty()) {
-          // recycle the oldest staged row: its bulk copy must have finished READING shared memory
-          const int g = inflight[inflight_head].second;
-          wait_n = n_groups - 1 - g;
-          while (inflight_head < inflight.size() && inflight[inflight_head].second <= g) free_slots.push_back(inflight[inflight_head++].first);
-        }
-        slots.push_back(free_slots.back());
-        free_slots.pop_back();
-      }
-      if (wait_n >= 0) {
-        s += "    if (lane == 0) BULK_WAIT_READ(" + std::to_string(wait_n) + ");\n    __syncwarp();\n";
-        st.n_waits++;
-      }
-      for (size_t q = b0; q < b1; ++q)
-        s += "    { const double2 o = D2(" + pending[q].re + ", " + pending[q].im + "); SMST(" + soff(slots[q - b0]) + ", o); }\n";
-      s += "    FENCE_ASYNC(); __syncwarp();\n    if (lane == 0 && wbytes) {\n";
-      for (size_t q = b0; q < b1; ++q)
-        s += std::string("      BULK_ST(") + (pending[q].cur ? "ib" : "xb") + " + " + off(pending[q].k) + ", " + soff(slots[q - b0]) + ");\n";
-      s += "      BULK_COMMIT();\n    }\n";
-      for (int sl : slots) inflight.push_back(std::make_pair(sl, n_groups));
-      ++n_groups;
-    }
+    for (const Out& o : pending)
+      s += std::string("    if (valid) *(double2*)(") + (o.cur ? "ib" : "xb") + " + " + off(o.k) + ") = D2(" + o.re + ", " + o.im + ");\n";
     pending.clear();
   };
 
@@ -421,7 +367,6 @@ inline std::string generate_sparse_kernel_source(const CodegenInput& in, const C
           const std::string nm = "s" + std::to_string(o) + "_" + std::to_string(t);
           s += "    double2 " + nm + "; SMLD(" + nm + ", " + soff(slot_of[o]) + ");\n";
           local[o] = nm;
-          if (bulk && last[o] == t) free_slots.push_back(slot_of[o]);  // consumed: the row joins the staging ring
         }
       auto bop = [&](int o) -> Opnd {
         if (o >= 0 && local.count(o)) { Opnd r2; r2.re = local[o] + ".x"; r2.im = local[o] + ".y"; return r2; }
@@ -449,10 +394,7 @@ inline std::string generate_sparse_kernel_source(const CodegenInput& in, const C
     }
     if (t >= B) { emit_currents(t); flush_outputs(); }
   }
-  // the staged rows are rewritten by the next system's elimination: all bulk reads must be done
-  if (bulk) s += "    if (lane == 0) BULK_WAIT_READ(0);\n    __syncwarp();\n";
   s += "  }\n";
-  if (bulk) s += "  if (lane == 0) BULK_WAIT_ALL();\n";
   s += "}\n";
   {
     std::string head = sparse_jit_prelude();
@@ -462,7 +404,6 @@ inline std::string generate_sparse_kernel_source(const CodegenInput& in, const C
     head += "};\n";
     s = head + s;
   }
-  st.n_groups = n_groups;
   if (stats_out) *stats_out = st;
   return s;
 }

@@ -254,22 +254,21 @@ struct DeviceCtx {
   bool sp_unified = false;
   bool sp_eager = false;
   // straight-line (NVRTC-compiled) variant of the program, when it was built
-  // compiled straight-line variants of the sparse program: index = with element currents | bulk (series-major) stores << 1
+  // compiled straight-line variants of the sparse program: [0] without, [1] with element currents
   struct JitVariant {
     cudaLibrary_t lib = nullptr;
     cudaKernel_t kernel = nullptr;
     uint64_t key = 0;   // plan key the module was compiled for (0 = none)
     bool failed = false;
     size_t smem_bytes = 0;
-  } sp_jit[4];
+  } sp_jit[2];
   // Launch shape of the compiled kernel, measured on cfg2 (tools/jit_sweep.py): one CTA of 6 warps per SM with
   // 255 registers per thread and 75 shared-memory slots per thread for the factor values (0.76 ms per 1e6
   // points); 5 warps x 90 slots: 0.81 ms, 4 x 113: 1.03 ms, 8 x 55 (spills): 1.0 ms.  A __syncthreads every
-  // 4 pivots keeps the warps of a CTA on the same instruction-cache lines (-8 %).  The bulk-copy (TMA)
-  // epilogue stays off: one cp.async.bulk issue costs its warp ~90 cycles (tools/micro/bulk_store.cu), more
-  // than the store stalls it removes.  (Also tried: reserving a stored value's registers for a few rows with an
-  // empty asm so that the allocator cannot reuse them while the store drains — no gain, removed.)  Overridable for experiments: SPICEY_JIT_CFG=block,minb,slots[,ring,sync].
-  int sp_jit_block = 192, sp_jit_minb = 1, sp_jit_slots = 75, sp_jit_ring = 0, sp_jit_sync = 4;
+  // 4 pivots keeps the warps of a CTA on the same instruction-cache lines (-8 %).  Tried and removed: a bulk-copy
+  // (TMA) epilogue (one cp.async.bulk issue costs its warp ~90 cycles, tools/micro/bulk_store.cu: 2.3 ms) and
+  // reserving a stored value's registers with an empty asm while the store drains (no gain).  Overridable for experiments: SPICEY_JIT_CFG=block,minb,slots[,sync].
+  int sp_jit_block = 192, sp_jit_minb = 1, sp_jit_slots = 75, sp_jit_sync = 4;
   double sp_jit_compile_ms = 0;
   std::string sp_jit_note;
   // warp-cooperative form of the sparse program (warp_program.h): large programs, one warp per system
@@ -629,22 +628,22 @@ void jit_source(const SparseProgram& sp, const HostPlan& hp, const CodegenOption
 
 // Compiles (once per topology, handle and variant) the straight-line kernel of the cached sparse program.
 // Returns the usable variant or nullptr.
-DeviceCtx::JitVariant* ensure_jit(DeviceCtx& ctx, const HostPlan& hp, bool with_ielem, bool bulk) {
-  DeviceCtx::JitVariant& jv = ctx.sp_jit[(with_ielem ? 1 : 0) | (bulk ? 2 : 0)];
+DeviceCtx::JitVariant* ensure_jit(DeviceCtx& ctx, const HostPlan& hp, bool with_ielem) {
+  DeviceCtx::JitVariant& jv = ctx.sp_jit[with_ielem ? 1 : 0];
   if (jv.key == ctx.sp_key) return jv.failed ? nullptr : &jv;
   jv.key = ctx.sp_key;
   jv.failed = true;
   if (jv.lib) { cudaLibraryUnload(jv.lib); jv.lib = nullptr; jv.kernel = nullptr; }
   const double t0 = now_ms();
   if (const char* e = getenv("SPICEY_JIT_CFG")) {
-    int b = 0, m = 0, sl = 0, rg = ctx.sp_jit_ring, sy = ctx.sp_jit_sync;
-    if (sscanf(e, "%d,%d,%d,%d,%d", &b, &m, &sl, &rg, &sy) >= 3 && b >= 32 && b <= 1024 && b % 32 == 0 && m >= 1 && sl >= 0) {
-      ctx.sp_jit_block = b; ctx.sp_jit_minb = m; ctx.sp_jit_slots = sl; ctx.sp_jit_ring = rg; ctx.sp_jit_sync = sy;
+    int b = 0, m = 0, sl = 0, sy = ctx.sp_jit_sync;
+    if (sscanf(e, "%d,%d,%d,%d", &b, &m, &sl, &sy) >= 3 && b >= 32 && b <= 1024 && b % 32 == 0 && m >= 1 && sl >= 0) {
+      ctx.sp_jit_block = b; ctx.sp_jit_minb = m; ctx.sp_jit_slots = sl; ctx.sp_jit_sync = sy;
     }
   }
   CodegenOptions opt;
   opt.block = ctx.sp_jit_block; opt.min_blocks = ctx.sp_jit_minb; opt.with_ielem = with_ielem;
-  opt.bulk_store = bulk && ctx.sp_jit_ring > 0; opt.ring_slots = ctx.sp_jit_ring; opt.sync_every = ctx.sp_jit_sync;
+  opt.sync_every = ctx.sp_jit_sync;
   opt.smem_slots = std::min<int>(ctx.sp_jit_slots, (int)((size_t)(227 * 1024 / opt.min_blocks - 1024) / ((size_t)opt.block * 16)));
   std::string src;
   CodegenStats st;
@@ -736,7 +735,7 @@ int launch_ac_sparse(DeviceCtx& ctx, const HostPlan& hp, const DevPlan& dp, cons
   CUDA_TRY(cudaMemsetAsync(fb_count, 0, sizeof(int), stream));
   const bool want_jit = !ctx.sp_eager && !(flags & SPICEY_FLAG_NO_JIT) && ctx.sp.code.size() <= kJitMaxOps &&
                         (args.p_count >= kJitMinPoints || (flags & SPICEY_FLAG_JIT));
-  DeviceCtx::JitVariant* jv = (want_jit && args.series_ld < (1ll << 32)) ? ensure_jit(ctx, hp, args.ielem != nullptr, args.series_ld != 0) : nullptr;
+  DeviceCtx::JitVariant* jv = (want_jit && args.series_ld < (1ll << 32)) ? ensure_jit(ctx, hp, args.ielem != nullptr) : nullptr;
   if (jv) {
     JitArgs j;
     j.freqs = args.freqs + args.p_begin; j.p_count = args.p_count;
@@ -1465,13 +1464,13 @@ int64_t spicey_debug_sparse_source(const spicey_elem_table* table, double pilot_
   if (!sp.ok) { fail(SPICEY_ERR_UNSUPPORTED, "the sparse path does not apply to this circuit"); return -1; }
   CodegenOptions opt;
   opt.block = block; opt.min_blocks = min_blocks; opt.smem_slots = smem_slots; opt.with_ielem = (with_ielem & 1) != 0;
-  opt.bulk_store = (with_ielem & 2) != 0; opt.ring_slots = std::max(1, (with_ielem >> 8) & 0xff); opt.sync_every = (with_ielem >> 16) & 0xff;
+  opt.sync_every = (with_ielem >> 16) & 0xff;
   std::string src;
   CodegenStats st;
   jit_source(sp, hp, opt, src, st);
   if (stats_out) {
     stats_out[0] = st.n_saved; stats_out[1] = st.smem_slots; stats_out[2] = st.n_classes; stats_out[3] = (int32_t)sp.code.size();
-    stats_out[4] = (int32_t)sp.n_fma; stats_out[5] = (int32_t)sp.n_div; stats_out[6] = st.n_groups; stats_out[7] = st.n_waits;
+    stats_out[4] = (int32_t)sp.n_fma; stats_out[5] = (int32_t)sp.n_div; stats_out[6] = sp.n_virtual; stats_out[7] = sp.n_slots;
   }
   if (buf && cap > 0) {
     const size_t n = std::min<size_t>(src.size(), (size_t)cap - 1);

@@ -134,20 +134,20 @@ def tran_kernel_source(table: "ElemTable", sweep: Optional["Sweep"] = None, with
     return buf.value.decode()
 
 
-def sparse_kernel_source(table: "ElemTable", pilot_f: float, block=160, min_blocks=1, smem_slots=90, with_ielem=True,
-                         bulk=False, ring=6, sync=4):
+def sparse_kernel_source(table: "ElemTable", pilot_f: float, block=192, min_blocks=1, smem_slots=75, with_ielem=True,
+                         sync=4):
     """CUDA source of the compiled straight-line sparse kernel (tier 5) for a circuit, plus the generator's
     statistics.  Host-only tooling: lets the generated code be inspected / compiled offline with nvcc."""
     lib = load_library()
     st = (C.c_int32 * 8)()
     ts = table.struct()
-    mode = int(with_ielem) | (2 if bulk else 0) | (ring << 8) | (sync << 16)
+    mode = int(with_ielem) | (sync << 16)
     need = lib.spicey_debug_sparse_source(C.byref(ts), pilot_f, block, min_blocks, smem_slots, mode, None, 0, st)
     if need < 0:
         raise NativeError(-1, (lib.spicey_last_error() or b"").decode())
     buf = C.create_string_buffer(need)
     lib.spicey_debug_sparse_source(C.byref(ts), pilot_f, block, min_blocks, smem_slots, mode, buf, need, st)
-    keys = ("saved_values", "smem_slots", "classes", "micro_ops", "cfma", "reciprocals", "bulk_groups", "staging_waits")
+    keys = ("saved_values", "smem_slots", "classes", "micro_ops", "cfma", "reciprocals", "virtual_values", "interp_slots")
     return buf.value.decode(), dict(zip(keys, list(st)))
 
 

@@ -1,5 +1,5 @@
 #!/usr/bin/env python3
-"""GPU: time the compiled sparse kernel (tier 5) on cfg2 for several launch shapes (SPICEY_JIT_CFG=block,minb,slots)
+"""GPU: time the compiled sparse kernel (tier 5) on cfg2 for several launch shapes (SPICEY_JIT_CFG=block,minb,slots[,sync])
 and check each against the C oracle on a subsample.   usage: jit_sweep.py "192,1,72" "128,1,113" ..."""
 import os
 import sys
