@@ -228,13 +228,14 @@ enum {
 };
 
 /* Tooling (no device needed): writes the CUDA source of the compiled straight-line sparse kernel
- * (tier 5) for this element table into buf (NUL-terminated, truncated to cap) and returns the
+ * (tier 5) for this element table (sweep: which value slots vary per instance, or NULL) into buf (NUL-terminated, truncated to cap) and returns the
  * size needed, or -1 when the sparse path does not apply.  stats_out[8], optional: values crossing
  * into the back-substitution, of those in shared memory, distinct stamped values, micro-ops,
  * complex FMAs, reciprocals, virtual values, interpreter workspace slots.  with_ielem: bit 0 element
  * currents, bits 16-23 __syncthreads period. */
-int64_t spicey_debug_sparse_source(const spicey_elem_table* table, double pilot_f, int32_t block, int32_t min_blocks,
-                                   int32_t smem_slots, int32_t with_ielem, char* buf, int64_t cap, int32_t* stats_out);
+int64_t spicey_debug_sparse_source(const spicey_elem_table* table, const spicey_sweep* sweep, double pilot_f, int32_t block,
+                                   int32_t min_blocks, int32_t smem_slots, int32_t with_ielem, char* buf, int64_t cap,
+                                   int32_t* stats_out);
 
 /* Tooling (no device needed): CUDA source of the compiled transient kernel (tier 6) for this element
  * table and sweep (which value slots vary per instance); returns the size needed or -1. */

@@ -28,6 +28,7 @@
 //    predicated 16-byte stores, 512 contiguous bytes per warp and series.
 #pragma once
 #include <algorithm>
+#include <cmath>
 #include <cstdio>
 #include <cstring>
 #include <map>
@@ -43,6 +44,15 @@ struct CodegenInput {
   int nn = 0, n_ac_elem = 0, v_first = 0;
   const int* n1 = nullptr;   // [n_ac_elem] node ids (0 = ground)
   const int* n2 = nullptr;
+  // Per-instance stamping (component sweeps / Monte-Carlo on the AC axis): the entries are sums of element
+  // admittances that differ from instance to instance, so the kernel builds them from the element table.
+  bool eager = false;
+  const int* ent_ptr = nullptr;      // gather plan: entry en sums contrib[ent_ptr[en] .. ent_ptr[en + 1])
+  const int* contrib = nullptr;      // (element << 3) | (source << 1) | negate; source 0 = admittance, 1 = phasor, 2 = one
+  const int* el_type = nullptr;      // [n_ac_elem] 0 R, 1 C, 2 L, 3 V
+  const int* el_vidx = nullptr;      // [n_ac_elem] first value slot
+  const int* var_of_slot = nullptr;  // [n_values] sweep variable of a slot or -1
+  const double* values = nullptr;    // [n_values] nominal values
 };
 
 struct CodegenOptions {
@@ -51,6 +61,7 @@ struct CodegenOptions {
   int smem_slots = 48;    // shared-memory double2 slots per thread for the factor values
   bool with_ielem = true; // false: the caller passed ielem = NULL, no current is computed
   int sync_every = 0;     // > 0: __syncthreads() every that many pivots / back-substitution rows (instruction-cache locality)
+  int prefetch_steps = 8; // per-instance stamping: element values are loaded this many pivots / rows ahead of their use
 };
 
 struct CodegenStats {
@@ -86,6 +97,7 @@ struct JitArgs {
   const double* freqs; long long p_count;
   double2* x; double2* ielem; int* status; long long series_ld;
   long long* fb_list; int* fb_count; int n; int n_ac_elem;
+  const double* var_values; long long n_inst; long long n_freq; long long p_begin;   // per-instance stamping
 };
 #define EPS 1e-15
 #define THR 1e-30
@@ -215,36 +227,134 @@ inline std::string generate_sparse_kernel_source(const CodegenInput& in, const C
   }
   auto soff = [&](int slot) { return std::to_string((long long)slot * opt.block * 16); };
 
+  std::string s;
+  s.reserve(1 << 20);
+  // ---- per-instance stamping: raw element values are loaded a few pivots ahead of their use, element
+  //      admittances (simulateAC.ts:36-57) and the ordered entry sums (stamp*Complex.ts) are formed where first
+  //      used; the back-substitution phase re-loads what the element currents need ----
+  char phase = 'f';
+  std::map<std::string, char> defined;   // name -> phase it was last defined in
+  auto fresh = [&](const std::string& nm) -> bool {
+    auto it = defined.find(nm);
+    if (it != defined.end() && it->second == phase) return false;
+    defined[nm] = phase;
+    return true;
+  };
+  auto ph = [&]() { return std::string(1, phase); };
+  auto raw = [&](int slot) -> std::string {   // value of a slot for this instance
+    const int v = in.var_of_slot[slot];
+    if (v < 0) return lit(in.values[slot]);
+    const std::string nm = "raw" + std::to_string(slot) + ph();
+    if (fresh(nm)) s += "    const double " + nm + " = vv[" + std::to_string(v) + "u * vs];\n";
+    return nm;
+  };
+  auto need_elem = [&](int e) {   // defines yr<e><ph> / yi<e><ph> (V: jr / ji)
+    const std::string E = std::to_string(e) + ph();
+    if (!fresh("el" + E)) return;
+    const int ty = in.el_type[e], vi = in.el_vidx[e];
+    if (ty == 0) {          // R: Y = 1/R, R <= 0 is the reference's "must be > 0" (:37): dense kernel reports it
+      const std::string R = raw(vi);
+      if (in.var_of_slot[vi] < 0) s += "    const double yr" + E + " = " + lit(1 / in.values[vi]) + ";\n";
+      else s += "    bad = bad || !(" + R + " > 0.0);\n    const double yr" + E + " = rcp_nr(" + R + ");\n";
+    } else if (ty == 1) {   // C: Y = j (2 pi f) C  (:43)
+      s += "    const double yi" + E + " = w * " + raw(vi) + ";\n";
+    } else if (ty == 2) {   // L: Y = 1 / (j (2 pi f) L), zero when |denominator| < EPS (:47-51)
+      const std::string L = raw(vi);
+      s += "    double yi" + E + ";\n    { const double d = w * " + L + ", dd = d * d; bad = bad || (!(fabs(d) < EPS) && dd < EPS);\n";
+      s += "      yi" + E + " = fabs(d) < EPS ? 0.0 : -d * rcp_nr(dd); }\n";
+    } else {                // V: phasor acMag * exp(j acPhase)  (Complex.ts:16-19)
+      if (in.var_of_slot[vi + 1] < 0 && in.var_of_slot[vi + 2] < 0) {
+        const double phs = (in.values[vi + 2] * 3.141592653589793) / 180;
+        s += "    const double jr" + E + " = " + lit(in.values[vi + 1] * cos(phs)) + ", ji" + E + " = " + lit(in.values[vi + 1] * sin(phs)) + ";\n";
+      } else {
+        const std::string mag = raw(vi + 1), deg = raw(vi + 2);
+        s += "    double jr" + E + ", ji" + E + ";\n    { double sn, cs; sincos((" + deg + " * 3.141592653589793) / 180, &sn, &cs); jr" + E +
+             " = " + mag + " * cs; ji" + E + " = " + mag + " * sn; }\n";
+      }
+    }
+  };
+  auto entry_opnd_eager = [&](int en) -> Opnd {
+    Opnd o;
+    const std::string EN = std::to_string(en) + ph();
+    std::string re, im;
+    // structure first (no code emitted): which parts exist
+    bool has_re = false, has_im = false;
+    for (int c = in.ent_ptr[en]; c < in.ent_ptr[en + 1]; ++c) {
+      const int cw = in.contrib[c], src = (cw >> 1) & 3, idx = cw >> 3;
+      if (src == 2) has_re = true;
+      else if (src == 1) { has_re = true; has_im = true; }
+      else if (in.el_type[idx] == 0) has_re = true;
+      else has_im = true;
+    }
+    o.re0 = !has_re; o.im0 = !has_im;
+    o.re = has_re ? "er" + EN : std::string("0.0");
+    o.im = has_im ? "ei" + EN : std::string("0.0");
+    if (!fresh("en" + EN)) return o;
+    for (int c = in.ent_ptr[en]; c < in.ent_ptr[en + 1]; ++c) {
+      const int cw = in.contrib[c], src = (cw >> 1) & 3, idx = cw >> 3;
+      const bool neg = cw & 1;
+      auto add = [&](std::string& acc, const std::string& t) {
+        if (acc.empty()) acc = neg ? "-" + t : t;
+        else acc = "(" + acc + (neg ? " - " : " + ") + t + ")";
+      };
+      if (src == 2) { add(re, "1.0"); continue; }
+      need_elem(idx);
+      const std::string E = std::to_string(idx) + ph();
+      if (src == 1) { add(re, "jr" + E); add(im, "ji" + E); }
+      else if (in.el_type[idx] == 0) add(re, "yr" + E);
+      else add(im, "yi" + E);
+    }
+    if (has_re) s += "    const double er" + EN + " = " + re + ";\n";
+    if (has_im) s += "    const double ei" + EN + " = " + im + ";\n";
+    return o;
+  };
+  // raw values needed by op t (forward: stamped operands; back: stamped operands and element currents)
+  auto raw_slots_of_entry = [&](int en, std::vector<int>& out) {
+    for (int c = in.ent_ptr[en]; c < in.ent_ptr[en + 1]; ++c) {
+      const int cw = in.contrib[c], src = (cw >> 1) & 3, idx = cw >> 3;
+      if (src == 2) continue;
+      const int vi = in.el_vidx[idx];
+      if (in.el_type[idx] == 3) { out.push_back(vi + 1); out.push_back(vi + 2); } else out.push_back(vi);
+    }
+  };
+
   auto opnd = [&](int o) -> Opnd {
     Opnd r;
     if (o == kNoOperand) { r.re = r.im = "0.0"; r.re0 = r.im0 = true; r.re_lit = true; return r; }
-    if (o < 0) return entry_opnd(~o);
+    if (o < 0) return in.eager ? entry_opnd_eager(~o) : entry_opnd(~o);
     const std::string nm = "v" + std::to_string(o);
     r.re = nm + ".x"; r.im = nm + ".y";
     return r;
   };
 
-  std::string s;
-  s.reserve(1 << 20);
   s += "#define BLOCK " + std::to_string(opt.block) + "\n";
   s += "extern \"C\" __global__ void __launch_bounds__(BLOCK, " + std::to_string(opt.min_blocks) + ") spicey_sparse_jit(JitArgs a) {\n";
   s += "  if (a.p_count <= 0) return;\n";
   s += "  const unsigned ld = a.series_ld ? (unsigned)a.series_ld : 1u;\n";
   s += "  const unsigned sbase = (unsigned)__cvta_generic_to_shared(sm) + threadIdx.x * 16u;\n";
   s += "  const long long stride = (long long)gridDim.x * BLOCK, plast = a.p_count - 1;\n";
-  s += "  double fnext = a.freqs[min((long long)blockIdx.x * BLOCK + threadIdx.x, plast)];\n";
+  if (!in.eager) s += "  double fnext = a.freqs[min((long long)blockIdx.x * BLOCK + threadIdx.x, plast)];\n";
   // block-uniform trip count: lanes past the end solve the last point again and store nothing
   s += "  for (long long base = (long long)blockIdx.x * BLOCK; base < a.p_count; base += stride) {\n";
   s += "    const long long p = base + threadIdx.x;\n    const bool valid = p < a.p_count;\n";
-  s += "    const double w = 6.283185307179586 * fnext;\n";
-  s += "    fnext = a.freqs[min(p + stride, plast)];\n";
-  if (need_iw) s += "    const double iw = 1.0 / w;\n";
+  if (in.eager) {
+    // point index = instance * n_freq + frequency index (the layout of spicey_ac_solve for sweeps)
+    s += "    const long long gp = a.p_begin + min(p, plast), inst = gp / a.n_freq;\n";
+    s += "    const double w = 6.283185307179586 * a.freqs[gp - inst * a.n_freq];\n";
+    s += "    const double* __restrict__ vv = a.var_values + inst;   // swept slot v of this instance: vv[v * n_inst]\n";
+    s += "    const size_t vs = (size_t)a.n_inst;\n";
+  } else {
+    s += "    const double w = 6.283185307179586 * fnext;\n";
+    s += "    fnext = a.freqs[min(p + stride, plast)];\n";
+    if (need_iw) s += "    const double iw = 1.0 / w;\n";
+  }
   s += "    char* const xb = (char*)(a.series_ld ? a.x + p : a.x + p * a.n);\n";
   if (opt.with_ielem) s += "    char* const ib = (char*)(a.series_ld ? a.ielem + p : a.ielem + p * a.n_ac_elem);\n";
   s += "    bool ok = true, bad = false;\n    double mp, m, inv;\n    double2 r, fm;\n";
-  for (double L : sp.ind_L)  // inductor guards of simulateAC.ts:47-51 are value dependent: dense kernel decides
-    s += "    { const double d = w * " + lit(L) + "; bad = bad || fabs(d) < EPS || d * d < EPS; }\n";
-  if (named_classes)
+  if (!in.eager)
+    for (double L : sp.ind_L)  // inductor guards of simulateAC.ts:47-51 are value dependent: dense kernel decides
+      s += "    { const double d = w * " + lit(L) + "; bad = bad || fabs(d) < EPS || d * d < EPS; }\n";
+  if (named_classes && !in.eager)
     for (int c = 0; c < st.n_classes; ++c) {
       const int en = cls_rep[c];
       if (sp.ent_beta[en] != 0.0 || sp.ent_gamma[en] != 0.0 || sp.ent_jim[en] != 0.0)
@@ -304,18 +414,47 @@ inline std::string generate_sparse_kernel_source(const CodegenInput& in, const C
         else if (vb >= 0) { const Opnd Bq = opnd(vb); d.re = "(0.0 - " + Bq.re + ")"; d.im = "(0.0 - " + Bq.im + ")"; }
         else { d.re = d.im = "0.0"; d.re0 = d.im0 = true; }
         Opnd y;  // element admittance ya + j(w*yb - yg/w)
-        y.re = lit(sp.el_a[e]); y.re0 = sp.el_a[e] == 0.0;
-        y.im0 = sp.el_b[e] == 0.0 && sp.el_g[e] == 0.0;
-        y.im = y.im0 ? "0.0" : "(" + im_expr(sp.el_b[e], sp.el_g[e], 0.0) + ")";
+        if (in.eager) {
+          need_elem(e);
+          const std::string E = std::to_string(e) + ph();
+          if (in.el_type[e] == 0) { y.re = "yr" + E; y.im = "0.0"; y.im0 = true; }
+          else { y.re = "0.0"; y.re0 = true; y.im = "yi" + E; }
+        } else {
+          y.re = lit(sp.el_a[e]); y.re0 = sp.el_a[e] == 0.0;
+          y.im0 = sp.el_b[e] == 0.0 && sp.el_g[e] == 0.0;
+          y.im = y.im0 ? "0.0" : "(" + im_expr(sp.el_b[e], sp.el_g[e], 0.0) + ")";
+        }
         cmul(y, d, re, im);
       }
       pending.push_back(Out{true, e, re, im});
     }
   };
 
+  // per-instance stamping: value slots op t needs, so that their loads can be issued a few steps ahead
+  std::vector<std::vector<int>> slots_at(in.eager ? n_ir : 0);
+  if (in.eager)
+    for (int t = 0; t < n_ir; ++t) {
+      const IrOp& op = ir[t];
+      auto use = [&](int o) { if (o < 0 && o != kNoOperand) raw_slots_of_entry(~o, slots_at[t]); };
+      for (int o : op.reads) use(o);
+      for (const Update& u : op.upd) { use(u.dst_old); use(u.src); }
+      if (t >= B && opt.with_ielem)
+        for (int e : cur_at[t]) if (e < in.v_first) slots_at[t].push_back(in.el_vidx[e]);
+    }
+  auto prefetch_from = [&](int t) {   // called at a PIVOT / BSUB: loads for this and the next prefetch_steps steps
+    if (!in.eager) return;
+    int steps = 0;
+    for (int q = t; q < n_ir && (t < B ? q < B : true); ++q) {
+      if (q > t && (ir[q].kind == SOP_PIVOT || ir[q].kind == SOP_BSUB) && ++steps > opt.prefetch_steps) break;
+      for (int slot : slots_at[q]) raw(slot);
+    }
+  };
+
   int n_piv = 0, n_bs = 0;
   for (int t = 0; t < n_ir; ++t) {
     const IrOp& op = ir[t];
+    if (t == B) phase = 'b';
+    if (op.kind == SOP_PIVOT || op.kind == SOP_BSUB) prefetch_from(t);
     if (t == B) {
       // Every pivot has been verified.  A system whose pivot order differs from the pilot's, or that trips a
       // guard of the reference (singular, Complex.div, inductor), goes to the dense kernel, which also

@@ -261,14 +261,17 @@ struct DeviceCtx {
     uint64_t key = 0;   // plan key the module was compiled for (0 = none)
     bool failed = false;
     size_t smem_bytes = 0;
+    int block = 0;
   } sp_jit[2];
   // Launch shape of the compiled kernel, measured on cfg2 (tools/jit_sweep.py): one CTA of 6 warps per SM with
   // 255 registers per thread and 75 shared-memory slots per thread for the factor values (0.76 ms per 1e6
   // points); 5 warps x 90 slots: 0.81 ms, 4 x 113: 1.03 ms, 8 x 55 (spills): 1.0 ms.  A __syncthreads every
   // 4 pivots keeps the warps of a CTA on the same instruction-cache lines (-8 %).  Tried and removed: a bulk-copy
   // (TMA) epilogue (one cp.async.bulk issue costs its warp ~90 cycles, tools/micro/bulk_store.cu: 2.3 ms) and
-  // reserving a stored value's registers with an empty asm while the store drains (no gain).  Overridable for experiments: SPICEY_JIT_CFG=block,minb,slots[,sync].
+  // reserving a stored value's registers with an empty asm while the store drains (no gain).  Overridable for experiments: SPICEY_JIT_CFG=block,minb,slots[,sync,prefetch].
   int sp_jit_block = 192, sp_jit_minb = 1, sp_jit_slots = 75, sp_jit_sync = 4;
+  // per-instance (eager) stamping keeps element values in flight: fewer threads, more shared memory each
+  int sp_jit_block_eager = 128, sp_jit_slots_eager = 113, sp_jit_prefetch = 8;   // cfg2mc: 1.52 ms (prefetch 4: 1.60, 2: 1.71)
   double sp_jit_compile_ms = 0;
   std::string sp_jit_note;
   // warp-cooperative form of the sparse program (warp_program.h): large programs, one warp per system
@@ -402,6 +405,7 @@ struct JitArgs {   // must match sparse_jit_prelude()
   const double* freqs; long long p_count;
   double2* x; double2* ielem; int* status; long long series_ld;
   long long* fb_list; int* fb_count; int n; int n_ac_elem;
+  const double* var_values; long long n_inst; long long n_freq; long long p_begin;   // per-instance stamping
 };
 
 struct Nvrtc {
@@ -617,12 +621,15 @@ int launch_ac_dense(DeviceCtx& ctx, const HostPlan& hp, const DevPlan& dp, const
 constexpr size_t kJitMaxOps = 6000;          // larger programs stay on the interpreter (compile time)
 constexpr long long kJitMinPoints = 200000;  // below this the ~4 s compile does not pay off (unless forced)
 
-void jit_source(const SparseProgram& sp, const HostPlan& hp, const CodegenOptions& opt, std::string& src, CodegenStats& st) {
-  std::vector<int> n1(hp.n_ac_elem), n2(hp.n_ac_elem);
-  for (int e = 0; e < hp.n_ac_elem; ++e) { n1[e] = hp.ends[e].x; n2[e] = hp.ends[e].y; }
+void jit_source(const SparseProgram& sp, const HostPlan& hp, const CodegenOptions& opt, bool eager, std::string& src,
+                CodegenStats& st) {
+  std::vector<int> n1(hp.n_ac_elem), n2(hp.n_ac_elem), ty(hp.n_ac_elem), vi(hp.n_ac_elem);
+  for (int e = 0; e < hp.n_ac_elem; ++e) { n1[e] = hp.ends[e].x; n2[e] = hp.ends[e].y; ty[e] = hp.meta[e].x; vi[e] = hp.meta[e].y; }
   CodegenInput ci;
   ci.sp = &sp; ci.nn = hp.nn; ci.n_ac_elem = hp.n_ac_elem; ci.v_first = hp.off[ELEM_V];
   ci.n1 = n1.data(); ci.n2 = n2.data();
+  ci.eager = eager; ci.ent_ptr = hp.ac.ent_ptr.data(); ci.contrib = hp.ac.contrib.data();
+  ci.el_type = ty.data(); ci.el_vidx = vi.data(); ci.var_of_slot = hp.var_of_slot.data(); ci.values = hp.values.data();
   src = generate_sparse_kernel_source(ci, opt, &st);
 }
 
@@ -630,24 +637,30 @@ void jit_source(const SparseProgram& sp, const HostPlan& hp, const CodegenOption
 // Returns the usable variant or nullptr.
 DeviceCtx::JitVariant* ensure_jit(DeviceCtx& ctx, const HostPlan& hp, bool with_ielem) {
   DeviceCtx::JitVariant& jv = ctx.sp_jit[with_ielem ? 1 : 0];
-  if (jv.key == ctx.sp_key) return jv.failed ? nullptr : &jv;
-  jv.key = ctx.sp_key;
+  // the per-instance (eager) kernel also depends on WHICH value slots are swept
+  uint64_t key = ctx.sp_eager ? fnv1a(ctx.sp_key, hp.var_of_slot.data(), sizeof(int) * hp.var_of_slot.size()) : ctx.sp_key;
+  if (!key) key = 1;
+  if (jv.key == key) return jv.failed ? nullptr : &jv;
+  jv.key = key;
   jv.failed = true;
   if (jv.lib) { cudaLibraryUnload(jv.lib); jv.lib = nullptr; jv.kernel = nullptr; }
   const double t0 = now_ms();
   if (const char* e = getenv("SPICEY_JIT_CFG")) {
-    int b = 0, m = 0, sl = 0, sy = ctx.sp_jit_sync;
-    if (sscanf(e, "%d,%d,%d,%d", &b, &m, &sl, &sy) >= 3 && b >= 32 && b <= 1024 && b % 32 == 0 && m >= 1 && sl >= 0) {
-      ctx.sp_jit_block = b; ctx.sp_jit_minb = m; ctx.sp_jit_slots = sl; ctx.sp_jit_sync = sy;
+    int b = 0, m = 0, sl = 0, sy = ctx.sp_jit_sync, pf = ctx.sp_jit_prefetch;
+    if (sscanf(e, "%d,%d,%d,%d,%d", &b, &m, &sl, &sy, &pf) >= 3 && b >= 32 && b <= 1024 && b % 32 == 0 && m >= 1 && sl >= 0) {
+      ctx.sp_jit_block = ctx.sp_jit_block_eager = b; ctx.sp_jit_minb = m; ctx.sp_jit_slots = ctx.sp_jit_slots_eager = sl;
+      ctx.sp_jit_sync = sy; ctx.sp_jit_prefetch = pf;
     }
   }
   CodegenOptions opt;
-  opt.block = ctx.sp_jit_block; opt.min_blocks = ctx.sp_jit_minb; opt.with_ielem = with_ielem;
+  opt.block = ctx.sp_eager ? ctx.sp_jit_block_eager : ctx.sp_jit_block; opt.min_blocks = ctx.sp_jit_minb; opt.with_ielem = with_ielem;
+  opt.prefetch_steps = ctx.sp_jit_prefetch;
   opt.sync_every = ctx.sp_jit_sync;
-  opt.smem_slots = std::min<int>(ctx.sp_jit_slots, (int)((size_t)(227 * 1024 / opt.min_blocks - 1024) / ((size_t)opt.block * 16)));
+  opt.smem_slots = std::min<int>(ctx.sp_eager ? ctx.sp_jit_slots_eager : ctx.sp_jit_slots,
+                                 (int)((size_t)(227 * 1024 / opt.min_blocks - 1024) / ((size_t)opt.block * 16)));
   std::string src;
   CodegenStats st;
-  jit_source(ctx.sp, hp, opt, src, st);
+  jit_source(ctx.sp, hp, opt, ctx.sp_eager, src, st);
   std::vector<char> cubin;
   if (!jit_compile(src, cubin, ctx.sp_jit_note)) return nullptr;
   if (cudaLibraryLoadData(&jv.lib, cubin.data(), nullptr, nullptr, 0, nullptr, nullptr, 0) != cudaSuccess ||
@@ -658,6 +671,7 @@ DeviceCtx::JitVariant* ensure_jit(DeviceCtx& ctx, const HostPlan& hp, bool with_
     return nullptr;
   }
   jv.smem_bytes = st.smem_bytes;
+  jv.block = opt.block;
   jv.failed = false;
   ctx.sp_jit_compile_ms = now_ms() - t0;
   ctx.sp_jit_note = "ok";
@@ -733,15 +747,16 @@ int launch_ac_sparse(DeviceCtx& ctx, const HostPlan& hp, const DevPlan& dp, cons
   int* fb_count = (int*)ctx.sp_fb.p;
   long long* fb_list = (long long*)((char*)ctx.sp_fb.p + 64);
   CUDA_TRY(cudaMemsetAsync(fb_count, 0, sizeof(int), stream));
-  const bool want_jit = !ctx.sp_eager && !(flags & SPICEY_FLAG_NO_JIT) && ctx.sp.code.size() <= kJitMaxOps &&
+  const bool want_jit = !(flags & SPICEY_FLAG_NO_JIT) && ctx.sp.code.size() <= kJitMaxOps &&
                         (args.p_count >= kJitMinPoints || (flags & SPICEY_FLAG_JIT));
   DeviceCtx::JitVariant* jv = (want_jit && args.series_ld < (1ll << 32)) ? ensure_jit(ctx, hp, args.ielem != nullptr) : nullptr;
   if (jv) {
     JitArgs j;
-    j.freqs = args.freqs + args.p_begin; j.p_count = args.p_count;
+    j.freqs = ctx.sp_eager ? args.freqs : args.freqs + args.p_begin; j.p_count = args.p_count;
     j.x = args.x; j.ielem = args.ielem; j.status = args.status; j.series_ld = args.series_ld;
     j.fb_list = fb_list; j.fb_count = fb_count; j.n = hp.nvar; j.n_ac_elem = hp.n_ac_elem;
-    const int jblock = ctx.sp_jit_block;
+    j.var_values = dp.var_values; j.n_inst = dp.n_inst; j.n_freq = args.n_freq; j.p_begin = args.p_begin;
+    const int jblock = jv->block;
     const long long resident = (long long)ctx.sm_count * ctx.sp_jit_minb;
     const unsigned jgrid = (unsigned)std::min<long long>((args.p_count + jblock - 1) / jblock, resident);
     void* kargs[] = {&j};
@@ -1455,19 +1470,21 @@ int32_t spicey_tran_solve(spicey_handle* h, const spicey_elem_table* table, cons
   return SPICEY_SUCCESS;
 }
 
-int64_t spicey_debug_sparse_source(const spicey_elem_table* table, double pilot_f, int32_t block, int32_t min_blocks,
-                                   int32_t smem_slots, int32_t with_ielem, char* buf, int64_t cap, int32_t* stats_out) {
+int64_t spicey_debug_sparse_source(const spicey_elem_table* table, const spicey_sweep* sweep, double pilot_f, int32_t block,
+                                   int32_t min_blocks, int32_t smem_slots, int32_t with_ielem, char* buf, int64_t cap,
+                                   int32_t* stats_out) {
   HostPlan hp;
-  if (build_plan(table, nullptr, hp) != SPICEY_SUCCESS) return -1;
+  if (build_plan(table, sweep, hp) != SPICEY_SUCCESS) return -1;
+  const bool eager = sweep && (sweep->n_inst > 1 || sweep->n_var > 0);
   SparseProgram sp;
-  build_sparse_host(hp, pilot_f, false, sp);
+  build_sparse_host(hp, pilot_f, eager, sp);
   if (!sp.ok) { fail(SPICEY_ERR_UNSUPPORTED, "the sparse path does not apply to this circuit"); return -1; }
   CodegenOptions opt;
   opt.block = block; opt.min_blocks = min_blocks; opt.smem_slots = smem_slots; opt.with_ielem = (with_ielem & 1) != 0;
   opt.sync_every = (with_ielem >> 16) & 0xff;
   std::string src;
   CodegenStats st;
-  jit_source(sp, hp, opt, src, st);
+  jit_source(sp, hp, opt, eager, src, st);
   if (stats_out) {
     stats_out[0] = st.n_saved; stats_out[1] = st.smem_slots; stats_out[2] = st.n_classes; stats_out[3] = (int32_t)sp.code.size();
     stats_out[4] = (int32_t)sp.n_fma; stats_out[5] = (int32_t)sp.n_div; stats_out[6] = sp.n_virtual; stats_out[7] = sp.n_slots;

@@ -98,7 +98,7 @@ def load_library(path: Optional[str] = None):
     lib.spicey_measure_fp64_peak.restype = C.c_int32
     lib.spicey_measure_fp64_peak.argtypes = [vp, C.c_int32, _dp]
     lib.spicey_debug_sparse_source.restype = C.c_int64
-    lib.spicey_debug_sparse_source.argtypes = [tb, C.c_double, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_char_p,
+    lib.spicey_debug_sparse_source.argtypes = [tb, sw, C.c_double, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_char_p,
                                                C.c_int64, _ip]
     lib.spicey_debug_warp_stats.restype = C.c_int32
     lib.spicey_debug_warp_stats.argtypes = [tb, C.c_double, _ip]
@@ -135,18 +135,20 @@ def tran_kernel_source(table: "ElemTable", sweep: Optional["Sweep"] = None, with
 
 
 def sparse_kernel_source(table: "ElemTable", pilot_f: float, block=192, min_blocks=1, smem_slots=75, with_ielem=True,
-                         sync=4):
+                         sync=4, sweep: Optional["Sweep"] = None):
     """CUDA source of the compiled straight-line sparse kernel (tier 5) for a circuit, plus the generator's
     statistics.  Host-only tooling: lets the generated code be inspected / compiled offline with nvcc."""
     lib = load_library()
     st = (C.c_int32 * 8)()
     ts = table.struct()
+    ss = sweep.struct() if sweep else None
+    sp_ = C.byref(ss) if ss else None
     mode = int(with_ielem) | (sync << 16)
-    need = lib.spicey_debug_sparse_source(C.byref(ts), pilot_f, block, min_blocks, smem_slots, mode, None, 0, st)
+    need = lib.spicey_debug_sparse_source(C.byref(ts), sp_, pilot_f, block, min_blocks, smem_slots, mode, None, 0, st)
     if need < 0:
         raise NativeError(-1, (lib.spicey_last_error() or b"").decode())
     buf = C.create_string_buffer(need)
-    lib.spicey_debug_sparse_source(C.byref(ts), pilot_f, block, min_blocks, smem_slots, mode, buf, need, st)
+    lib.spicey_debug_sparse_source(C.byref(ts), sp_, pilot_f, block, min_blocks, smem_slots, mode, buf, need, st)
     keys = ("saved_values", "smem_slots", "classes", "micro_ops", "cfma", "reciprocals", "virtual_values", "interp_slots")
     return buf.value.decode(), dict(zip(keys, list(st)))
 

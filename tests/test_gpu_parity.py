@@ -181,17 +181,22 @@ def test_ac_sweep_instances(eng):
     ov = {"r1": rng.uniform(10, 100, n), "c1": rng.uniform(1e-5, 1e-3, n), "v1.acmag": rng.uniform(0.5, 2, n),
           "v1.acphase": rng.uniform(-180, 180, n)}
     freqs = np.logspace(0, 3, 11)
-    out, x, ie, st, _ = ac_case(eng, w.README_RC, freqs, n_inst=n, overrides=ov)
-    assert out["status"].max() == 0
-    assert rel_err(out["x"], x) <= AC_TOL
-    assert rel_err(out["ielem"], ie) <= AC_TOL
+    for flags, tier in ((0, native.TIER_CTA_SMEM), (native.FLAG_SPARSE, native.TIER_SPARSE),
+                        (native.FLAG_SPARSE | native.FLAG_JIT, native.TIER_SPARSE_JIT),
+                        (native.FLAG_SPARSE | native.FLAG_JIT | SM, native.TIER_SPARSE_JIT)):
+        out, x, ie, st, _ = ac_case(eng, w.README_RC, freqs, flags, n_inst=n, overrides=ov)
+        assert eng.stats()["tier"] == tier
+        assert out["status"].max() == 0
+        assert rel_err(out["x"], x) <= AC_TOL
+        assert rel_err(out["ielem"], ie) <= AC_TOL
 
 
-@pytest.mark.parametrize("flags", [native.FLAG_SPARSE, native.FLAG_SPARSE | SM, 0])
+@pytest.mark.parametrize("flags", [native.FLAG_SPARSE, native.FLAG_SPARSE | SM, 0, native.FLAG_SPARSE | native.FLAG_JIT,
+                                   native.FLAG_SPARSE | native.FLAG_JIT | SM])
 def test_ac_monte_carlo_ladder_sparse_eager(eng, flags):
     """Component-tolerance Monte-Carlo on the AC axis (64-node ladder, 40 instances x 53 frequencies, every
-    R and C swept): the sparse program with per-instance (eager) stamping; flags=0 checks the automatic
-    tier choice (2120 points >= 2048 -> sparse)."""
+    R and C swept): the sparse program with per-instance (eager) stamping, interpreted or compiled; flags=0
+    checks the automatic tier choice (2120 points >= 2048 -> sparse)."""
     text = w.rc_ladder(64)
     n = 40
     u = w.splitmix_uniform_pm1(n, 126)
@@ -201,7 +206,7 @@ def test_ac_monte_carlo_ladder_sparse_eager(eng, flags):
         ov["c%d" % k] = 1e-9 * (1 + 0.05 * u[:, 62 + k])
     freqs = np.logspace(0, 5, 53)
     out, x, ie, st, _ = ac_case(eng, text, freqs, flags, n_inst=n, overrides=ov)
-    assert eng.stats()["tier"] == native.TIER_SPARSE
+    assert eng.stats()["tier"] == (native.TIER_SPARSE_JIT if flags & native.FLAG_JIT else native.TIER_SPARSE)
     assert out["status"].max() == 0 and st.max() == 0
     assert rel_err(out["x"], x) <= AC_TOL
     assert rel_err(out["ielem"], ie) <= AC_TOL
@@ -215,11 +220,12 @@ def test_ac_sweep_sparse_bad_instances_fall_back(eng):
     r = rng.uniform(10, 100, n)
     r[5] = 0.0
     ov = {"r1": r, "c1": rng.uniform(1e-5, 1e-3, n)}
-    out, x, ie, st, _ = ac_case(eng, w.README_RC, np.logspace(0, 3, 7), native.FLAG_SPARSE, n_inst=n, overrides=ov)
-    assert np.array_equal(out["status"], st) and (st[5] == native.ST_R_NONPOS).all()
-    ok = [i for i in range(n) if i != 5]
-    assert rel_err(out["x"][ok], x[ok]) <= AC_TOL and rel_err(out["ielem"][ok], ie[ok]) <= AC_TOL
-    assert eng.stats()["fallback_solves"] == 7
+    for flags in (native.FLAG_SPARSE, native.FLAG_SPARSE | native.FLAG_JIT):
+        out, x, ie, st, _ = ac_case(eng, w.README_RC, np.logspace(0, 3, 7), flags, n_inst=n, overrides=ov)
+        assert np.array_equal(out["status"], st) and (st[5] == native.ST_R_NONPOS).all()
+        ok = [i for i in range(n) if i != 5]
+        assert rel_err(out["x"][ok], x[ok]) <= AC_TOL and rel_err(out["ielem"][ok], ie[ok]) <= AC_TOL
+        assert eng.stats()["fallback_solves"] == 7
 
 
 def test_ac_error_statuses_do_not_poison_batch(eng):
