@@ -10,7 +10,7 @@ CSRC = os.path.join(HERE, "csrc")
 LIB_DIR = os.path.join(HERE, "lib")
 LIB_PATH = os.path.join(LIB_DIR, "libspicey_native.so")
 SOURCES = ["spicey_native.cu"]
-HEADERS = ["common.cuh", "lu_rowthread.cuh", "ac_kernels.cuh", "ac_sparse.cuh", "ac_warp.cuh", "warp_program.h", "sparse_program.h", "sparse_codegen.h", "tran_kernels.cuh", "tran_small.cuh", "tran_codegen.h",
+HEADERS = ["common.cuh", "host_plan.h", "jit_runtime.h", "lu_rowthread.cuh", "ac_kernels.cuh", "ac_sparse.cuh", "ac_warp.cuh", "warp_program.h", "sparse_program.h", "sparse_codegen.h", "tran_kernels.cuh", "tran_small.cuh", "tran_codegen.h",
            os.path.join("..", "..", "include", "spicey_native.h")]
 
 NVCC_FLAGS = [
