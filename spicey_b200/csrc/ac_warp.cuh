@@ -68,14 +68,16 @@ __device__ __forceinline__ void stage_wait() { asm volatile("cp.async.wait_group
 template <int WARPS>
 __global__ void __launch_bounds__(WARPS * 32) ac_warp_kernel(WarpArgs a) {
   typedef Num<cplx> N;
-  extern __shared__ __align__(16) double2 wsm[];   // [2 staging buffers][per-warp: pool | acc | multipliers]
+  extern __shared__ __align__(16) double2 wsm[];   // [2 staging buffers][per-warp: pool (later: accumulators) | multipliers]
   const unsigned FULL = 0xffffffffu;
   const int tid = threadIdx.x, lane = tid & 31, wib = tid >> 5;
-  const int per_warp = a.n_pool + a.n + a.max_elim;
+  // The accumulators of the back-substitution take over the pool's memory: the pool is dead once the
+  // elimination is done (what the back-substitution reads comes from the global workspace).
+  const int work = max(a.n_pool, a.n), per_warp = work + a.max_elim;
   // all shared-memory pointers are offsets from the __shared__ symbol, so that every access is an LDS/STS
   double2* pool = wsm + 2 * (size_t)a.max_rec16 + (size_t)wib * per_warp;
-  double2* acc = pool + a.n_pool;
-  double2* Fm = acc + a.n;
+  double2* acc = pool;
+  double2* Fm = pool + work;
   const long long gw = (long long)blockIdx.x * WARPS + wib;
   double2* G = a.G + gw * a.n_gslots;
   const double thr = kEps * kEps;

@@ -433,9 +433,9 @@ int prepare_warp(DeviceCtx& ctx, const HostPlan& hp, cudaStream_t stream) {
   ctx.wp_key = ctx.sp_key;
   ctx.wp_valid = false;
   const int per_warp_cap = (int)((ctx.smem_optin - 1024 - 32 * 1024) / kWarpTierWarps / sizeof(double2));
-  build_warp_program(ctx.sp, per_warp_cap - hp.nvar - 64, ctx.wp);
+  build_warp_program(ctx.sp, per_warp_cap - 64, ctx.wp);
   WarpProgram& wp = ctx.wp;
-  if (!wp.ok || (size_t)(wp.n_pool + wp.n + wp.max_elim) > (size_t)per_warp_cap || wp.max_rec16 > 1024) { wp.ok = false; return SPICEY_SUCCESS; }
+  if (!wp.ok || (size_t)(std::max(wp.n_pool, wp.n) + wp.max_elim) > (size_t)per_warp_cap || wp.max_rec16 > 1024) { wp.ok = false; return SPICEY_SUCCESS; }
   std::vector<unsigned char> blob;
   size_t o_st = push_blob(blob, wp.stream), o_ft = push_blob(blob, wp.fwd_tab), o_bt = push_blob(blob, wp.back_tab);
   size_t o_rh = push_blob(blob, wp.rhs_init);
@@ -462,7 +462,7 @@ int launch_ac_warp(DeviceCtx& ctx, const HostPlan& hp, const DevPlan& dp, const 
                    cudaStream_t stream, long long* fb_list, int* fb_count, int64_t* launches) {
   (void)hp; (void)flags;
   WarpArgs a = ctx.wp_args;
-  const size_t per_warp = sizeof(double2) * (size_t)(a.n_pool + a.n + a.max_elim);
+  const size_t per_warp = sizeof(double2) * (size_t)(std::max(a.n_pool, a.n) + a.max_elim);
   const size_t smem = per_warp * kWarpTierWarps + 2 * sizeof(int4) * (size_t)a.max_rec16;
   const int per_sm = (int)std::max<size_t>(1, std::min<size_t>(8, (ctx.smem_optin + 1024) / (smem + 1024)));
   const long long want = (args.p_count + kWarpTierWarps - 1) / kWarpTierWarps;
