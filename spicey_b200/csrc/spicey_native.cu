@@ -425,6 +425,7 @@ DeviceCtx::JitVariant* ensure_jit(DeviceCtx& ctx, const HostPlan& hp, bool with_
 }
 
 constexpr int kWarpTierWarps = 8;            // warps (systems) per CTA of ac_warp_kernel
+constexpr int kWarpPoolSpare = 64;            // free slots from which the bank-residue rule of the pool is relaxed
 constexpr int kWarpTierMinSlots = 512;       // thread-per-system workspace (slots) from which the warp tier takes over
 
 // Lowers the cached sparse program to its warp-cooperative form and uploads it (once per topology and handle).
@@ -433,7 +434,11 @@ int prepare_warp(DeviceCtx& ctx, const HostPlan& hp, cudaStream_t stream) {
   ctx.wp_key = ctx.sp_key;
   ctx.wp_valid = false;
   const int per_warp_cap = (int)((ctx.smem_optin - 1024 - 32 * 1024) / kWarpTierWarps / sizeof(double2));
-  build_warp_program(ctx.sp, per_warp_cap - 64, ctx.wp);
+  // a value may take a slot of the wrong bank residue once 64 slots lie free: cfg 4's pool 482 -> 362 slots,
+  // 24 -> 32 warps per SM, 3.59 -> 3.83 M solves/s (32 / 16 free slots: 3.80 / 3.79)
+  int spare = kWarpPoolSpare;
+  if (const char* e = getenv("SPICEY_WARP_SPARE")) spare = std::max(1, atoi(e));
+  build_warp_program(ctx.sp, per_warp_cap - 64, ctx.wp, spare);
   WarpProgram& wp = ctx.wp;
   if (!wp.ok || (size_t)(std::max(wp.n_pool, wp.n) + wp.max_elim) > (size_t)per_warp_cap || wp.max_rec16 > 1024) { wp.ok = false; return SPICEY_SUCCESS; }
   std::vector<unsigned char> blob;
@@ -1266,7 +1271,9 @@ int32_t spicey_debug_warp_stats(const spicey_elem_table* table, double pilot_f, 
   build_sparse_host(hp, pilot_f, false, sp);
   if (!sp.ok) return fail(SPICEY_ERR_UNSUPPORTED, "the sparse path does not apply to this circuit");
   WarpProgram wp;
-  build_warp_program(sp, 1 << 24, wp);
+  int spare = kWarpPoolSpare;
+  if (const char* e = getenv("SPICEY_WARP_SPARE")) spare = std::max(1, atoi(e));
+  build_warp_program(sp, 1 << 24, wp, spare);
   if (!wp.ok) return fail(SPICEY_ERR_UNSUPPORTED, "the warp program builder refused this circuit");
   long long chunks = 0;
   for (const WarpStep& st : wp.steps) chunks += (long long)st.n_elim * ((st.n_cols + 31) / 32);

@@ -165,7 +165,7 @@ inline void pack_warp_program(WarpProgram& wp, const SparseProgram& sp) {
 
 // Lowers sp.ir.  pool_cap: largest pool the kernel can give one warp; the program is rejected (ok=false)
 // when the elimination's working set does not fit, instead of spilling forward operands to global memory.
-inline void build_warp_program(const SparseProgram& sp, int pool_cap, WarpProgram& wp) {
+inline void build_warp_program(const SparseProgram& sp, int pool_cap, WarpProgram& wp, int pool_spare = 1 << 30) {
   using namespace sparse_detail;
   wp = WarpProgram();
   const int n = sp.n, nv = sp.n_virtual;
@@ -260,9 +260,15 @@ inline void build_warp_program(const SparseProgram& sp, int pool_cap, WarpProgra
   // row, so a value of column j gets a slot with slot % 8 == j % 8 (in-place updates keep it).
   std::vector<int> pool(nv, -1), free_list[8];
   int high = 1;  // slot 0 = zero
+  const int kSpare = pool_spare;
   auto alloc = [&](int col) -> int {
     const int b = col & 7;
     if (!free_list[b].empty()) { int s = free_list[b].back(); free_list[b].pop_back(); return s; }
+    // no free slot of the right residue: growing the pool costs occupancy, a wrong residue costs a bank
+    // conflict — take a foreign slot when plenty are lying around
+    int total = 0, best = -1;
+    for (int q = 0; q < 8; ++q) { total += (int)free_list[q].size(); if (best < 0 || free_list[q].size() > free_list[best].size()) best = q; }
+    if (total >= kSpare && !free_list[best].empty()) { int s = free_list[best].back(); free_list[best].pop_back(); return s; }
     while ((high & 7) != b) { free_list[high & 7].push_back(high); ++high; }
     return high++;
   };
