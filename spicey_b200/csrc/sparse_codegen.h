@@ -120,6 +120,25 @@ extern __shared__ double2 sm[];
 )SRC";
 }
 
+// Values the elimination hands to the back-substitution (1/u_kk, eliminated rhs, modified U): what has to fit the
+// registers and shared memory of one thread.  The launcher checks it before it asks for a compile.
+inline int count_cross_phase_values(const SparseProgram& sp) {
+  using namespace sparse_detail;
+  const int n_ir = (int)sp.ir.size();
+  int B = n_ir;
+  for (int t = 0; t < n_ir; ++t) if (sp.ir[t].kind == SOP_BSUB) { B = t; break; }
+  std::vector<char> fwd_def(sp.n_virtual, 0), back_use(sp.n_virtual, 0);
+  for (int t = 0; t < B; ++t) {
+    if (sp.ir[t].def >= 0) fwd_def[sp.ir[t].def] = 1;
+    for (const Update& u : sp.ir[t].upd) fwd_def[u.dst_new] = 1;
+  }
+  for (int t = B; t < n_ir; ++t)
+    for (int o : sp.ir[t].reads) if (o >= 0) back_use[o] = 1;
+  int n = 0;
+  for (int v = 0; v < sp.n_virtual; ++v) n += fwd_def[v] && back_use[v];
+  return n;
+}
+
 inline std::string generate_sparse_kernel_source(const CodegenInput& in, const CodegenOptions& opt = CodegenOptions(),
                                                  CodegenStats* stats_out = nullptr) {
   using namespace codegen_detail;

@@ -88,11 +88,14 @@ struct DeviceCtx {
   // per-instance (eager) stamping keeps element values in flight: fewer threads, more shared memory each
   int sp_jit_block_eager = 128, sp_jit_slots_eager = 113, sp_jit_prefetch = 8;   // cfg2mc: 1.52 ms (prefetch 4: 1.60, 2: 1.71)
   double sp_jit_compile_ms = 0;
+  uint64_t sp_jit_fit_key = 0;   // sparse program the fit check below was made for
+  bool sp_jit_fits = false;
   std::string sp_jit_note;
   // warp-cooperative form of the sparse program (warp_program.h): large programs, one warp per system
   WarpProgram wp;
   uint64_t wp_key = 0;        // sparse-program key the warp program was lowered from (0 = none)
   bool wp_valid = false;
+  bool wp_chainlike = false;   // fewer than 32 updates per pivot step on average: the warp tier is only used when forced
   Buffer wp_blob, wp_work;
   WarpArgs wp_args;
   uint64_t plan_up_key = 0;   // plan currently resident in `plan` (its device pointers are in plan_dp)
@@ -364,7 +367,8 @@ int prepare_sparse(DeviceCtx& ctx, const HostPlan& hp, double pilot_f, bool eage
 int launch_ac_dense(DeviceCtx& ctx, const HostPlan& hp, const DevPlan& dp, const AcArgs& args, uint32_t flags,
                     cudaStream_t stream, int* tier_out, int64_t* launches);
 
-constexpr size_t kJitMaxOps = 6000;          // larger programs stay on the interpreter (compile time)
+constexpr size_t kJitMaxOps = 3000;          // larger programs stay on the interpreter (compile time: cfg2's 831 micro-ops take 4 s)
+constexpr int kJitSpareValues = 64;          // cross-phase values the registers can hold beside the shared-memory slots
 constexpr long long kJitMinPoints = 200000;  // below this the ~4 s compile does not pay off (unless forced)
 
 void jit_source(const SparseProgram& sp, const HostPlan& hp, const CodegenOptions& opt, bool eager, std::string& src,
@@ -440,7 +444,10 @@ int prepare_warp(DeviceCtx& ctx, const HostPlan& hp, cudaStream_t stream) {
   if (const char* e = getenv("SPICEY_WARP_SPARE")) spare = std::max(1, atoi(e));
   build_warp_program(ctx.sp, per_warp_cap - 64, ctx.wp, spare);
   WarpProgram& wp = ctx.wp;
+  // lanes = columns of a pivot row: chain-like circuits (a ladder updates 2-3 entries per row) would leave the
+  // warp idle; they stay with one thread per system
   if (!wp.ok || (size_t)(std::max(wp.n_pool, wp.n) + wp.max_elim) > (size_t)per_warp_cap || wp.max_rec16 > 1024) { wp.ok = false; return SPICEY_SUCCESS; }
+  ctx.wp_chainlike = wp.n_upd_total < 32ll * wp.n;
   std::vector<unsigned char> blob;
   size_t o_st = push_blob(blob, wp.stream), o_ft = push_blob(blob, wp.fwd_tab), o_bt = push_blob(blob, wp.back_tab);
   size_t o_rh = push_blob(blob, wp.rhs_init);
@@ -498,7 +505,13 @@ int launch_ac_sparse(DeviceCtx& ctx, const HostPlan& hp, const DevPlan& dp, cons
   int* fb_count = (int*)ctx.sp_fb.p;
   long long* fb_list = (long long*)((char*)ctx.sp_fb.p + 64);
   CUDA_TRY(cudaMemsetAsync(fb_count, 0, sizeof(int), stream));
-  const bool want_jit = !(flags & SPICEY_FLAG_NO_JIT) && ctx.sp.code.size() <= kJitMaxOps &&
+  // the factorisation of one system must fit one thread's registers + shared memory (cfg2: 129 values), or the
+  // compiled kernel spills kilobytes per thread and takes minutes to compile (a 400-node ladder: 801 values)
+  if (ctx.sp_jit_fit_key != ctx.sp_key) {
+    ctx.sp_jit_fit_key = ctx.sp_key;
+    ctx.sp_jit_fits = count_cross_phase_values(ctx.sp) <= (ctx.sp_eager ? ctx.sp_jit_slots_eager : ctx.sp_jit_slots) + kJitSpareValues;
+  }
+  const bool want_jit = !(flags & SPICEY_FLAG_NO_JIT) && ctx.sp.code.size() <= kJitMaxOps && ctx.sp_jit_fits &&
                         (args.p_count >= kJitMinPoints || (flags & SPICEY_FLAG_JIT));
   DeviceCtx::JitVariant* jv = (want_jit && args.series_ld < (1ll << 32)) ? ensure_jit(ctx, hp, args.ielem != nullptr) : nullptr;
   if (jv) {
@@ -526,7 +539,7 @@ int launch_ac_sparse(DeviceCtx& ctx, const HostPlan& hp, const DevPlan& dp, cons
   if (!ctx.sp_eager && !(flags & SPICEY_FLAG_NO_WARP) && (ctx.sp.n_slots >= kWarpTierMinSlots || (flags & SPICEY_FLAG_WARP))) {
     rc = prepare_warp(ctx, hp, stream);
     if (rc) return rc;
-    if (ctx.wp_valid) {
+    if (ctx.wp_valid && (!ctx.wp_chainlike || (flags & SPICEY_FLAG_WARP))) {
       rc = launch_ac_warp(ctx, hp, dp, args, flags, stream, fb_list, fb_count, launches);
       if (rc) return rc;
       AcArgs d = args;

@@ -477,6 +477,21 @@ def test_mesh_default_policy_takes_the_warp_tier(eng):
     assert rel_err(x[sub], xr) <= AC_TOL and rel_err(out["ielem"][0][sub], ier) <= AC_TOL
 
 
+def test_long_ladder_default_policy(eng):
+    """A 400-node ladder (Nvar = 401, 3,200 points): chain-like, so the warp tier declines (2-3 updates per row
+    would idle the lanes), and 801 values cross into the back-substitution, far more than a thread's registers
+    and shared memory hold, so the compiled tier declines even when asked for: the thread-per-system program runs."""
+    import spicey_b200 as sp
+    ck = parse_netlist(w.rc_ladder(400, ppd=640))
+    freqs = np.array(sp.analysis.ac_frequencies(ck))[:3200]
+    xr, ier, st = co.ac_solve(ck, freqs[::50], nthreads=8)
+    for flags, tier in ((SM, native.TIER_SPARSE), (SM | native.FLAG_SPARSE | native.FLAG_JIT, native.TIER_SPARSE)):
+        out = sp.simulate_ac_batch(ck, freqs, engine=eng, flags=flags)
+        assert eng.stats()["tier"] == tier, (flags, eng.stats())
+        assert out["status"].max() == 0
+        assert rel_err(out["x"][0][::50], xr) <= AC_TOL and rel_err(out["ielem"][0][::50], ier) <= AC_TOL
+
+
 def test_multi_device_handle_shards_contiguous_ranges(eng):
     """spicey_create with two devices: the library shards the batch axis in contiguous ranges (no collective)
     and the result equals the single-device one.  Skipped on a one-GPU box."""
