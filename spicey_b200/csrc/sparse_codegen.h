@@ -61,6 +61,7 @@ struct CodegenOptions {
   int smem_slots = 48;    // shared-memory double2 slots per thread for the factor values
   bool with_ielem = true; // false: the caller passed ielem = NULL, no current is computed
   int sync_every = 0;     // > 0: __syncthreads() every that many pivots / back-substitution rows (instruction-cache locality)
+  int stagger_ns = 0;     // > 0: CTAs start in four phases this many ns apart, so that the SMs are not all storing at once
   int prefetch_steps = 8; // per-instance stamping: element values are loaded this many pivots / rows ahead of their use
 };
 
@@ -349,6 +350,11 @@ inline std::string generate_sparse_kernel_source(const CodegenInput& in, const C
   s += "#define BLOCK " + std::to_string(opt.block) + "\n";
   s += "extern \"C\" __global__ void __launch_bounds__(BLOCK, " + std::to_string(opt.min_blocks) + ") spicey_sparse_jit(JitArgs a) {\n";
   s += "  if (a.p_count <= 0) return;\n";
+  // long sweeps: the CTAs start in four phases, so that the SMs do not all reach their store-heavy
+  // back-substitution at the same moment (-2 % on cfg 2)
+  if (opt.stagger_ns > 0)
+    s += "  { const unsigned phs = blockIdx.x & 3u; if (phs && a.p_count > 16ll * gridDim.x * BLOCK) __nanosleep(phs * " +
+         std::to_string(opt.stagger_ns) + "u); }\n";
   s += "  const unsigned ld = a.series_ld ? (unsigned)a.series_ld : 1u;\n";
   s += "  const unsigned sbase = (unsigned)__cvta_generic_to_shared(sm) + threadIdx.x * 16u;\n";
   s += "  const long long stride = (long long)gridDim.x * BLOCK, plast = a.p_count - 1;\n";

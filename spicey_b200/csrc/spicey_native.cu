@@ -86,6 +86,7 @@ struct DeviceCtx {
   // reserving a stored value's registers with an empty asm while the store drains (no gain).  Overridable for experiments: SPICEY_JIT_CFG=block,minb,slots[,sync,prefetch].
   int sp_jit_block = 192, sp_jit_minb = 1, sp_jit_slots = 75, sp_jit_sync = 4;
   // per-instance (eager) stamping keeps element values in flight: fewer threads, more shared memory each
+  int sp_jit_stagger = 4000;   // ns between the four start phases of the CTAs (0.682 -> 0.669 ms on cfg 2)
   int sp_jit_block_eager = 128, sp_jit_slots_eager = 113, sp_jit_prefetch = 8;   // cfg2mc: 1.52 ms (prefetch 4: 1.60, 2: 1.71)
   double sp_jit_compile_ms = 0;
   uint64_t sp_jit_fit_key = 0;   // sparse program the fit check below was made for
@@ -396,15 +397,16 @@ DeviceCtx::JitVariant* ensure_jit(DeviceCtx& ctx, const HostPlan& hp, bool with_
   if (jv.lib) { cudaLibraryUnload(jv.lib); jv.lib = nullptr; jv.kernel = nullptr; }
   const double t0 = now_ms();
   if (const char* e = getenv("SPICEY_JIT_CFG")) {
-    int b = 0, m = 0, sl = 0, sy = ctx.sp_jit_sync, pf = ctx.sp_jit_prefetch;
-    if (sscanf(e, "%d,%d,%d,%d,%d", &b, &m, &sl, &sy, &pf) >= 3 && b >= 32 && b <= 1024 && b % 32 == 0 && m >= 1 && sl >= 0) {
+    int b = 0, m = 0, sl = 0, sy = ctx.sp_jit_sync, pf = ctx.sp_jit_prefetch, sg = ctx.sp_jit_stagger;
+    if (sscanf(e, "%d,%d,%d,%d,%d,%d", &b, &m, &sl, &sy, &pf, &sg) >= 3 && b >= 32 && b <= 1024 && b % 32 == 0 && m >= 1 && sl >= 0) {
+      ctx.sp_jit_stagger = sg;
       ctx.sp_jit_block = ctx.sp_jit_block_eager = b; ctx.sp_jit_minb = m; ctx.sp_jit_slots = ctx.sp_jit_slots_eager = sl;
       ctx.sp_jit_sync = sy; ctx.sp_jit_prefetch = pf;
     }
   }
   CodegenOptions opt;
   opt.block = ctx.sp_eager ? ctx.sp_jit_block_eager : ctx.sp_jit_block; opt.min_blocks = ctx.sp_jit_minb; opt.with_ielem = with_ielem;
-  opt.prefetch_steps = ctx.sp_jit_prefetch;
+  opt.prefetch_steps = ctx.sp_jit_prefetch; opt.stagger_ns = ctx.sp_jit_stagger;
   opt.sync_every = ctx.sp_jit_sync;
   opt.smem_slots = std::min<int>(ctx.sp_eager ? ctx.sp_jit_slots_eager : ctx.sp_jit_slots,
                                  (int)((size_t)(227 * 1024 / opt.min_blocks - 1024) / ((size_t)opt.block * 16)));
