@@ -388,7 +388,6 @@ def run_native(args):
         ev[k][0].record(stream)
         step_resident()
         ev[k][1].record(stream)
-        launches += eng.stats()["kernel_launches"]
     e1.record(stream)
     barrier()
     if rank == 0:
@@ -396,7 +395,8 @@ def run_native(args):
     n_timed_samples = len(sampler.samples)
     total_ms = e0.elapsed_time(e1)
     kern_ms = float(np.mean([a.elapsed_time(b) for a, b in ev]))
-    st_last = eng.stats()
+    st_last = eng.stats()   # (reads the fallback counter back: synchronises, hence outside the timed loop)
+    launches += st_last["kernel_launches"] * args.steps
     tier, fallback = st_last["tier"], st_last["fallback_solves"]
     check()
     t = torch.tensor([total_ms, kern_ms], dtype=torch.float64, device=dev)
