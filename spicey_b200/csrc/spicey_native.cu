@@ -167,6 +167,8 @@ int upload_plan(DeviceCtx& ctx, const HostPlan& hp, cudaStream_t stream, DevPlan
     gp[k]->contrib = (const int*)(b + o[k][3]);
     gp[k]->rowmask = (const unsigned*)(b + o[k][4]);
   }
+  // the cached copy may be used from another stream by a later call: make sure it has landed (cache misses only)
+  CUDA_TRY(cudaStreamSynchronize(stream));
   ctx.plan_dp = dp;
   ctx.plan_up_key = key;
   return SPICEY_SUCCESS;
