@@ -1,8 +1,17 @@
 // NVRTC, loaded lazily with dlopen so that the library itself has no link-time dependency on it: compiles the
 // kernels the generators (sparse_codegen.h, tran_codegen.h) write for one netlist to an sm_100a cubin.
+//
+// Compiled cubins are kept on disk, keyed by a hash of the source text (which contains the netlist's structure,
+// constants and launch shape) and of the NVRTC version: a topology is compiled once per machine, not once per
+// process (cfg 2: ~4 s of compile against 0.66 ms per sweep).  Directory: $SPICEY_CACHE_DIR, else
+// $XDG_CACHE_HOME/spicey_b200, else ~/.cache/spicey_b200; SPICEY_CACHE_DIR=off disables it.
 #pragma once
 #include <dlfcn.h>
+#include <sys/stat.h>
+#include <unistd.h>
 
+#include <cstdio>
+#include <cstdlib>
 #include <string>
 #include <vector>
 
@@ -18,6 +27,7 @@ struct Nvrtc {
   void* lib = nullptr;
   create_t create = nullptr; compile_t compile = nullptr; size_t_fn cubin_size = nullptr; get_t cubin = nullptr;
   size_t_fn log_size = nullptr; get_t log = nullptr; destroy_t destroy = nullptr;
+  int (*version)(int*, int*) = nullptr;
   bool ok = false;
   Nvrtc() {
     const char* names[] = {"libnvrtc.so.12", "libnvrtc.so", "/usr/local/cuda/lib64/libnvrtc.so.12", "/usr/local/cuda/lib64/libnvrtc.so"};
@@ -30,6 +40,7 @@ struct Nvrtc {
     log_size = (size_t_fn)dlsym(lib, "nvrtcGetProgramLogSize");
     log = (get_t)dlsym(lib, "nvrtcGetProgramLog");
     destroy = (destroy_t)dlsym(lib, "nvrtcDestroyProgram");
+    version = (int (*)(int*, int*))dlsym(lib, "nvrtcVersion");
     ok = create && compile && cubin_size && cubin && log_size && log && destroy;
   }
 };
@@ -60,6 +71,51 @@ inline bool jit_compile(const std::string& src, std::vector<char>& cubin, std::s
   return n > 0;
 }
 
+inline std::string jit_cache_dir() {
+  if (const char* e = getenv("SPICEY_CACHE_DIR")) return std::string(e) == "off" ? std::string() : std::string(e);
+  if (const char* e = getenv("XDG_CACHE_HOME")) return std::string(e) + "/spicey_b200";
+  if (const char* e = getenv("HOME")) return std::string(e) + "/.cache/spicey_b200";
+  return std::string();
+}
+
+// jit_compile through the on-disk cache.  `from_cache` (optional) tells which way it went.
+inline bool jit_compile_cached(const std::string& src, std::vector<char>& cubin, std::string& why, bool* from_cache = nullptr) {
+  if (from_cache) *from_cache = false;
+  const std::string dir = jit_cache_dir();
+  std::string path;
+  if (!dir.empty()) {
+    unsigned long long h = 1469598103934665603ull;
+    auto mix = [&](const void* p, size_t n) { const unsigned char* q = (const unsigned char*)p; for (size_t i = 0; i < n; ++i) { h ^= q[i]; h *= 1099511628211ull; } };
+    mix(src.data(), src.size());
+    int ver[2] = {0, 0};
+    if (nvrtc().ok && nvrtc().version) nvrtc().version(&ver[0], &ver[1]);
+    mix(ver, sizeof ver);
+    char name[64];
+    snprintf(name, sizeof name, "/%016llx_%zu.sm_100a.cubin", h, src.size());
+    path = dir + name;
+    if (FILE* f = fopen(path.c_str(), "rb")) {
+      fseek(f, 0, SEEK_END);
+      const long n = ftell(f);
+      fseek(f, 0, SEEK_SET);
+      cubin.resize(n > 0 ? (size_t)n : 0);
+      const bool got = n > 0 && fread(cubin.data(), 1, (size_t)n, f) == (size_t)n;
+      fclose(f);
+      if (got) { if (from_cache) *from_cache = true; return true; }
+    }
+  }
+  if (!jit_compile(src, cubin, why)) return false;
+  if (!path.empty()) {   // best effort: write to a temporary name, then rename (concurrent ranks compile the same source)
+    mkdir(dir.substr(0, dir.find_last_of('/')).c_str(), 0755);
+    mkdir(dir.c_str(), 0755);
+    const std::string tmp = path + "." + std::to_string((long long)getpid()) + ".tmp";
+    if (FILE* f = fopen(tmp.c_str(), "wb")) {
+      const bool okw = fwrite(cubin.data(), 1, cubin.size(), f) == cubin.size();
+      fclose(f);
+      if (!okw || rename(tmp.c_str(), path.c_str()) != 0) remove(tmp.c_str());
+    }
+  }
+  return true;
+}
 
 }  // namespace host
 }  // namespace spicey

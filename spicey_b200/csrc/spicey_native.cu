@@ -416,7 +416,7 @@ DeviceCtx::JitVariant* ensure_jit(DeviceCtx& ctx, const HostPlan& hp, bool with_
   CodegenStats st;
   jit_source(ctx.sp, hp, opt, ctx.sp_eager, src, st);
   std::vector<char> cubin;
-  if (!jit_compile(src, cubin, ctx.sp_jit_note)) return nullptr;
+  if (!jit_compile_cached(src, cubin, ctx.sp_jit_note)) return nullptr;
   if (cudaLibraryLoadData(&jv.lib, cubin.data(), nullptr, nullptr, 0, nullptr, nullptr, 0) != cudaSuccess ||
       cudaLibraryGetKernel(&jv.kernel, jv.lib, "spicey_sparse_jit") != cudaSuccess ||
       cudaFuncSetAttribute((const void*)jv.kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)st.smem_bytes) != cudaSuccess) {
@@ -705,7 +705,7 @@ DeviceCtx::JitVariant* ensure_tran_jit(DeviceCtx& ctx, const HostPlan& hp, bool 
   std::string src;
   tran_jit_source(hp, with_ielem, src);
   std::vector<char> cubin;
-  if (!jit_compile(src, cubin, ctx.sp_jit_note)) return nullptr;
+  if (!jit_compile_cached(src, cubin, ctx.sp_jit_note)) return nullptr;
   if (cudaLibraryLoadData(&jv.lib, cubin.data(), nullptr, nullptr, 0, nullptr, nullptr, 0) != cudaSuccess ||
       cudaLibraryGetKernel(&jv.kernel, jv.lib, "spicey_tran_jit") != cudaSuccess) {
     ctx.sp_jit_note = std::string("loading the compiled transient kernel failed: ") + cudaGetErrorString(cudaGetLastError());
