@@ -290,6 +290,11 @@ def run_native(args):
     rank, local, world = dist_env()
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device — the product has no CPU path (use --impl reference for the CPU port)")
+    # stdout carries exactly one JSON line: anything a library prints there (NCCL's version banner does, whatever
+    # NCCL_DEBUG_FILE says) is sent to stderr at the file-descriptor level, the line itself goes to the saved fd
+    sys.stdout.flush()
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
     torch.cuda.set_device(local)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
@@ -487,7 +492,9 @@ def run_native(args):
             "gpu_launches": int(launches),
             "clocks": clocks,
         }
-        print(json.dumps(line))
+        sys.stdout.flush()
+        os.write(json_fd, (json.dumps(line) + "\n").encode())
+    os.close(json_fd)
     for p in pins:
         eng.lib.spicey_host_free(p)
     eng.close()
