@@ -212,6 +212,33 @@ def test_ac_monte_carlo_ladder_sparse_eager(eng, flags):
     assert rel_err(out["ielem"], ie) <= AC_TOL
 
 
+def test_ac_sweep_random_rlc_compiled_per_instance_stamping(eng):
+    """Random RLC networks with every R, C and L value and one source phasor swept over 12 instances: the compiled
+    kernel with per-instance stamping (tier 5) — inductor admittances and their divide guards, two sources,
+    pivoting away from the diagonal — against the oracle, point-major and series-major."""
+    for n_nodes, n_elem in ((5, 12), (14, 40), (24, 70)):
+        rng = np.random.default_rng(77 + n_nodes)
+        text = random_rlc_netlist(rng, n_nodes, n_elem, n_v=2)
+        ck = parse_netlist(text)
+        n = 12
+        ov = {}
+        for el in list(ck.R) + list(ck.C) + list(ck.L):
+            val = getattr(el, "R", None) or getattr(el, "C", None) or getattr(el, "L", None)
+            ov[el.name] = val * (1 + 0.2 * rng.uniform(-1, 1, n))
+        ov["v1.acmag"] = rng.uniform(0.5, 2, n)
+        ov["v1.acphase"] = rng.uniform(-90, 90, n)
+        freqs = np.logspace(1, 6, 9)
+        for flags in (native.FLAG_SPARSE | native.FLAG_JIT, native.FLAG_SPARSE | native.FLAG_JIT | SM):
+            out, x, ie, st, _ = ac_case(eng, text, freqs, flags, n_inst=n, overrides=ov)
+            # (the largest network may exceed what one thread can hold: the interpreted program then runs)
+            assert eng.stats()["tier"] == native.TIER_SPARSE_JIT or n_nodes == 24, eng.stats()
+            assert np.array_equal(out["status"], st) and st.max() == 0
+            scale = np.max(np.abs(x), axis=2, keepdims=True)
+            assert np.max(np.abs(out["x"] - x) / scale) <= AC_TOL
+            iscale = np.max(np.abs(ie), axis=2, keepdims=True)
+            assert np.max(np.abs(out["ielem"] - ie) / iscale) <= AC_TOL
+
+
 def test_ac_sweep_sparse_bad_instances_fall_back(eng):
     """Sweep with one R<=0 instance and random RLC values: failures and pivot changes go through the dense
     fallback with exact statuses."""
