@@ -1,6 +1,7 @@
 #!/usr/bin/env python3
 """GPU: time the compiled sparse kernel (tier 5) on cfg2 for several launch shapes (SPICEY_JIT_CFG=block,minb,slots[,sync])
-and check each against the C oracle on a subsample.   usage: jit_sweep.py "192,1,72" "128,1,113" ..."""
+and check each against the strict dense pivoting kernel (reference-order arithmetic) on a subsample.
+   usage: jit_sweep.py "192,1,75,4" "128,1,113,4" ...     (tests/ hold the parity checks against the oracle)"""
 import os
 import sys
 
@@ -11,7 +12,6 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import spicey_b200 as sp  # noqa: E402
 from spicey_b200 import native, packing, parsing, workloads  # noqa: E402
-from oracle import c_oracle  # noqa: E402  (checker only)
 
 
 def main():
@@ -31,7 +31,10 @@ def main():
     d_s = torch.empty(P, dtype=torch.int32, device=dev)
     stream = torch.cuda.current_stream()
     sub = np.arange(0, P, 4999)
-    ref = c_oracle.ac_solve(ck, freqs[sub], nthreads=4)
+    eng0 = native.Engine([0])
+    r0 = eng0.ac_solve(table, freqs[sub], flags=native.FLAG_STRICT)
+    ref = (r0["x"].reshape(len(sub), -1), r0["ielem"].reshape(len(sub), -1))
+    eng0.close()
     for cfg in sys.argv[1:]:
         os.environ["SPICEY_JIT_CFG"] = cfg
         eng = native.Engine([0])
