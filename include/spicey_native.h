@@ -41,7 +41,7 @@
 extern "C" {
 #endif
 
-#define SPICEY_NATIVE_ABI_VERSION 2
+#define SPICEY_NATIVE_ABI_VERSION 3
 
 /* Element kinds of the flat element table (ParsedCircuit, lib/parsing/parseNetlist.ts:12-105). */
 enum {
@@ -212,6 +212,43 @@ int32_t spicey_tran_solve_device(spicey_handle* h, int32_t dev_index, const spic
                                  double* d_state_out, int32_t* d_iters, int32_t* d_status,
                                  uint32_t flags, void* stream);
 
+/*
+ * Source waveforms evaluated ON THE DEVICE: the reference hides a V element's PULSE / PWL
+ * in a closure (parseNetlist.ts:366-383: spec.waveform = t => pulseValue(p, t)), evaluated once per step at
+ * t = step*dt (simulateTRAN.ts:66-69, :147).  Here the parameters are value slots of the element table like
+ * any R or C, so a spicey_sweep can vary them per instance (amplitude, delay, duty ... sweeps), which a
+ * pre-sampled row shared by all instances cannot express.  Evaluation is pulseValue.ts:4-22 / pwlValue.ts:3-16
+ * with every operation separately rounded: bit-identical to the pre-sampled row of the same parameters.
+ *   kind[k]       SPICEY_WAVE_* of the k-th V element
+ *   value_idx[k]  first slot in table->values of the parameters:
+ *                   PULSE  v1, v2, td, tr, tf, ton, period, ncycles   (8 slots, PulseSpec, lib/types/simulation.ts:1-10;
+ *                          ncycles = +Infinity when the netlist gives 7 arguments, parsePulseArgs.ts)
+ *                   PWL    t0, v0, t1, v1, ...                        (2*n_pairs[k] slots)
+ *   n_pairs[k]    PWL pair count (ignored for the other kinds)
+ */
+enum { SPICEY_WAVE_DC = 0, SPICEY_WAVE_TABLE = 1, SPICEY_WAVE_PULSE = 2, SPICEY_WAVE_PWL = 3 };
+typedef struct spicey_waves {
+  int32_t n_vsrc;            /* must equal the number of V elements of the table */
+  int32_t reserved;
+  const int32_t* kind;       /* [n_vsrc] */
+  const int32_t* value_idx;  /* [n_vsrc] */
+  const int32_t* n_pairs;    /* [n_vsrc] (may be NULL when no source is PWL) */
+} spicey_waves;
+
+/* spicey_tran_solve / spicey_tran_solve_device with per-source waveform descriptors instead of the
+ * has-row mask; vsrc holds the rows of the sources of kind SPICEY_WAVE_TABLE (NULL if none). */
+int32_t spicey_tran_solve_waves(spicey_handle* h, const spicey_elem_table* table, const spicey_sweep* sweep,
+                                double dt, int64_t steps, const spicey_waves* waves, const double* vsrc,
+                                const double* state0, double* v, double* ielem, double* state_out,
+                                int32_t* iters, int32_t* status, uint32_t flags);
+
+int32_t spicey_tran_solve_waves_device(spicey_handle* h, int32_t dev_index, const spicey_elem_table* table,
+                                       const spicey_sweep* sweep, double dt, int64_t steps,
+                                       const spicey_waves* waves /* host */, const double* d_vsrc,
+                                       const double* d_state0, double* d_v, double* d_ielem,
+                                       double* d_state_out, int32_t* d_iters, int32_t* d_status,
+                                       uint32_t flags, void* stream);
+
 enum {
   SPICEY_FLAG_STRICT = 1u,      /* reference-order, unfused arithmetic (slow; parity testing) */
   SPICEY_FLAG_FORCE_GMEM = 2u,  /* testing: force the global-scratch tier */
@@ -241,6 +278,10 @@ int64_t spicey_debug_sparse_source(const spicey_elem_table* table, const spicey_
  * table and sweep (which value slots vary per instance); returns the size needed or -1. */
 int64_t spicey_debug_tran_source(const spicey_elem_table* table, const spicey_sweep* sweep, int32_t with_ielem,
                                  char* buf, int64_t cap);
+
+/* The same with device-evaluated waveforms (waves may be NULL). */
+int64_t spicey_debug_tran_source_waves(const spicey_elem_table* table, const spicey_sweep* sweep,
+                                       const spicey_waves* waves, int32_t with_ielem, char* buf, int64_t cap);
 
 /* Tooling (no device needed): sizes of the warp-per-system program (tier 7) of this element table:
  * out[8] = Nvar, shared-memory pool slots, global workspace slots, rows per step (max), updates, update

@@ -20,7 +20,7 @@ from typing import Dict, List, Optional
 import numpy as np
 
 from . import native
-from .packing import initial_state, make_sweep, pack_circuit, sample_sources, write_back_state
+from .packing import has_wave_override, initial_state, make_sweep, pack_circuit, sample_sources, write_back_state
 from .parsing import ParsedCircuit, build_frequency_array, compute_effective_time_step, parse_netlist
 
 _ENGINE: Optional[native.Engine] = None
@@ -194,15 +194,21 @@ def simulate_ac_batch(ckt: ParsedCircuit, freqs=None, n_inst: int = 1, overrides
 
 
 def simulate_tran_batch(ckt: ParsedCircuit, n_inst: int = 1, overrides=None, want_currents=True,
-                        want_iters=False, engine: Optional[native.Engine] = None, flags: int = 0):
-    """v[S1, nn, n_inst], ielem[S1, n_elem, n_inst] for a Monte-Carlo / sweep batch (state not written back)."""
+                        want_iters=False, engine: Optional[native.Engine] = None, flags: int = 0,
+                        device_waves: Optional[bool] = None):
+    """v[S1, nn, n_inst], ielem[S1, n_elem, n_inst] for a Monte-Carlo / sweep batch (state not written back).
+    device_waves: PULSE / PWL sources are evaluated by the kernels from their parameters instead of a row
+    pre-sampled here (bit-identical values); the default does so exactly when an override names a waveform
+    parameter ("v1.pulse.v2", "v1.pwl.t1", ...), which a shared pre-sampled row cannot express."""
     eng = engine or get_engine()
     dt, steps = compute_effective_time_step(ckt.analyses.tran.dt, ckt.analyses.tran.tstop)
-    table = pack_circuit(ckt)
-    vsrc, mask = sample_sources(ckt, dt, steps)
+    if device_waves is None:
+        device_waves = has_wave_override(overrides)
+    table = pack_circuit(ckt, device_waves=device_waves)
+    vsrc, mask = (None, None) if device_waves else sample_sources(ckt, dt, steps)
     res = eng.tran_solve(table, dt, steps, vsrc=vsrc, vsrc_mask=mask, sweep=make_sweep(table, n_inst, overrides),
                          state0=initial_state(ckt, table, n_inst), want_currents=want_currents,
-                         want_iters=want_iters, flags=flags)
+                         want_iters=want_iters, flags=flags, waves=table.waves)
     res.update({"dt": dt, "steps": steps, "times": np.arange(steps + 1) * dt, "node_names": ckt.nodes.rev[1:],
                 "element_names": table.names})
     return res

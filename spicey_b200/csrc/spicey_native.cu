@@ -679,7 +679,51 @@ struct TranJitArgs {   // must match tran_jit_prelude()
 constexpr int kTranJitBlock = 64;                 // 65,536 instances -> 1024 CTAs: 6.9 per SM, 1 % tail
 constexpr long long kTranJitMinSteps = 2000000;   // instance-steps below which the ~1 s compile does not pay off
 
-void tran_jit_source(const HostPlan& hp, bool with_ielem, std::string& src) {
+// Host copy of the per-source waveform descriptors {kind, first parameter slot, PWL pair count, 0}.
+typedef std::vector<int4> WaveList;
+
+// Validates a caller's spicey_waves (or the legacy has-row mask) against the plan.
+int build_waves(const HostPlan& hp, const spicey_waves* wv, const int32_t* vsrc_mask, bool have_rows, WaveList& out) {
+  out.assign(std::max(1, hp.nV), make_int4(WAVE_DC, 0, 0, 0));
+  if (!wv) {
+    for (int k = 0; k < hp.nV; ++k)
+      if (vsrc_mask && vsrc_mask[k]) {
+        if (!have_rows) return fail(SPICEY_ERR_INVALID, "vsrc_mask set but vsrc is NULL");
+        out[k].x = WAVE_TABLE;
+      }
+    return SPICEY_SUCCESS;
+  }
+  if (wv->n_vsrc != hp.nV) return fail(SPICEY_ERR_INVALID, "waves->n_vsrc differs from the table's V count");
+  if (hp.nV > 0 && !wv->kind) return fail(SPICEY_ERR_INVALID, "waves->kind is NULL");
+  for (int k = 0; k < hp.nV; ++k) {
+    const int kind = wv->kind[k];
+    if (kind == SPICEY_WAVE_DC) continue;
+    if (kind == SPICEY_WAVE_TABLE) {
+      if (!have_rows) return fail(SPICEY_ERR_INVALID, "a source of kind SPICEY_WAVE_TABLE needs vsrc");
+      out[k].x = WAVE_TABLE;
+      continue;
+    }
+    if (kind != SPICEY_WAVE_PULSE && kind != SPICEY_WAVE_PWL) return fail(SPICEY_ERR_INVALID, "unknown waveform kind");
+    if (!wv->value_idx) return fail(SPICEY_ERR_INVALID, "waves->value_idx is NULL");
+    const int vi = wv->value_idx[k];
+    const int np = kind == SPICEY_WAVE_PWL ? (wv->n_pairs ? wv->n_pairs[k] : -1) : 0;
+    if (np < 0) return fail(SPICEY_ERR_INVALID, "PWL source without a pair count");
+    const long long need = kind == SPICEY_WAVE_PULSE ? 8 : 2ll * np;
+    if (vi < 0 || vi + need > hp.n_values) return fail(SPICEY_ERR_INVALID, "waveform parameter slots out of range");
+    out[k] = make_int4(kind == SPICEY_WAVE_PULSE ? WAVE_PULSE : WAVE_PWL, vi, np, 0);
+  }
+  return SPICEY_SUCCESS;
+}
+
+void wave_masks(const HostPlan& hp, const WaveList& w, unsigned& table_bits, unsigned& dev_bits) {
+  table_bits = dev_bits = 0;
+  for (int k = 0; k < hp.nV && k < 32; ++k) {
+    if (w[k].x == WAVE_TABLE) table_bits |= 1u << k;
+    else if (w[k].x >= WAVE_PULSE) dev_bits |= 1u << k;
+  }
+}
+
+void tran_jit_source(const HostPlan& hp, const WaveList& waves, bool with_ielem, std::string& src) {
   std::vector<int> n1(hp.n_elem), n2(hp.n_elem), c1(hp.n_elem), c2(hp.n_elem), vi(hp.n_elem);
   for (int e = 0; e < hp.n_elem; ++e) {
     n1[e] = hp.ends[e].x; n2[e] = hp.ends[e].y; c1[e] = hp.ends[e].z; c2[e] = hp.ends[e].w; vi[e] = hp.meta[e].y;
@@ -689,21 +733,28 @@ void tran_jit_source(const HostPlan& hp, bool with_ielem, std::string& src) {
   in.off = hp.off; in.n1 = n1.data(); in.n2 = n2.data(); in.nc1 = c1.data(); in.nc2 = c2.data();
   in.value_idx = vi.data(); in.state_idx = hp.state_idx.data(); in.values = hp.values.data();
   in.var_of_slot = hp.var_of_slot.data(); in.with_ielem = with_ielem; in.block = kTranJitBlock;
+  // dc / pre-sampled sources are chosen at run time by a.vmask: only device-evaluated waveforms shape the code
+  std::vector<int> wk(std::max(1, hp.nV), -1), wi(std::max(1, hp.nV), 0), wn(std::max(1, hp.nV), 0);
+  for (int k = 0; k < hp.nV; ++k)
+    if (waves[k].x >= WAVE_PULSE) { wk[k] = waves[k].x; wi[k] = waves[k].y; wn[k] = waves[k].z; }
+  in.wave_kind = wk.data(); in.wave_vidx = wi.data(); in.wave_npairs = wn.data();
   src = generate_tran_kernel_source(in);
 }
 
-DeviceCtx::JitVariant* ensure_tran_jit(DeviceCtx& ctx, const HostPlan& hp, bool with_ielem) {
+DeviceCtx::JitVariant* ensure_tran_jit(DeviceCtx& ctx, const HostPlan& hp, const WaveList& waves, bool with_ielem) {
   DeviceCtx::JitVariant& jv = ctx.tr_jit[with_ielem ? 1 : 0];
   uint64_t key = plan_key(hp);
   key = fnv1a(key, hp.var_of_slot.data(), sizeof(int) * hp.var_of_slot.size());
   key = fnv1a(key, hp.state_idx.data(), sizeof(int) * hp.state_idx.size());
+  for (int k = 0; k < hp.nV; ++k)
+    if (waves[k].x >= WAVE_PULSE) { key = fnv1a(key, &k, sizeof k); key = fnv1a(key, &waves[k], sizeof(int4)); }
   if (!key) key = 1;
   if (jv.key == key) return jv.failed ? nullptr : &jv;
   jv.key = key;
   jv.failed = true;
   if (jv.lib) { cudaLibraryUnload(jv.lib); jv.lib = nullptr; jv.kernel = nullptr; }
   std::string src;
-  tran_jit_source(hp, with_ielem, src);
+  tran_jit_source(hp, waves, with_ielem, src);
   std::vector<char> cubin;
   if (!jit_compile_cached(src, cubin, ctx.sp_jit_note)) return nullptr;
   if (cudaLibraryLoadData(&jv.lib, cubin.data(), nullptr, nullptr, 0, nullptr, nullptr, 0) != cudaSuccess ||
@@ -716,15 +767,17 @@ DeviceCtx::JitVariant* ensure_tran_jit(DeviceCtx& ctx, const HostPlan& hp, bool 
   return &jv;
 }
 
-int launch_tran(DeviceCtx& ctx, const HostPlan& hp, const DevPlan& dp, const TranArgs& args, uint32_t flags,
-                cudaStream_t stream, int* tier_out, int64_t* launches) {
+int launch_tran(DeviceCtx& ctx, const HostPlan& hp, const DevPlan& dp, const TranArgs& args, const WaveList& waves,
+                uint32_t flags, cudaStream_t stream, int* tier_out, int64_t* launches) {
   if (args.n_local <= 0) return SPICEY_SUCCESS;
   const bool strict = flags & SPICEY_FLAG_STRICT;
+  bool jit_waves_ok = true;
+  for (int k = 0; k < hp.nV; ++k) jit_waves_ok &= !(waves[k].x == WAVE_PWL && waves[k].z > kTranJitMaxPwlPairs);
   // Compiled per-topology kernel (tran_codegen.h): small systems, batches large enough to pay for the compile.
   if (!strict && !(flags & (SPICEY_FLAG_FORCE_CTA | SPICEY_FLAG_FORCE_GMEM | SPICEY_FLAG_GENERIC_THREAD | SPICEY_FLAG_NO_JIT)) &&
-      hp.nvar <= 8 && hp.n_elem <= 48 && hp.nV <= 32 && args.n_local < (1ll << 29) &&
+      hp.nvar <= 8 && hp.n_elem <= 48 && hp.nV <= 32 && args.n_local < (1ll << 29) && jit_waves_ok &&
       ((flags & SPICEY_FLAG_JIT) || args.n_local * (args.steps + 1) >= kTranJitMinSteps)) {
-    if (DeviceCtx::JitVariant* jv = ensure_tran_jit(ctx, hp, args.ielem != nullptr)) {
+    if (DeviceCtx::JitVariant* jv = ensure_tran_jit(ctx, hp, waves, args.ielem != nullptr)) {
       TranJitArgs j;
       j.var_values = dp.var_values; j.n_inst = dp.n_inst; j.dt = args.dt; j.steps = args.steps;
       j.vsrc = args.vsrc; j.vmask = args.vmask_bits; j.state0 = args.state0; j.inst0 = args.inst0; j.n_local = args.n_local;
@@ -1078,9 +1131,22 @@ int32_t spicey_ac_solve(spicey_handle* h, const spicey_elem_table* table, const 
   return SPICEY_SUCCESS;
 }
 
-int32_t spicey_tran_solve_device(spicey_handle* h, int32_t dev_index, const spicey_elem_table* table,
+}  // extern "C"
+
+// Uploads the waveform descriptors of one call (a few int4) into ctx.aux0 and fills the TranArgs fields.
+static int stage_waves(DeviceCtx& ctx, const HostPlan& hp, const WaveList& waves, cudaStream_t st, TranArgs& a) {
+  int rc = ctx.aux0.ensure(sizeof(int4) * waves.size());
+  if (rc) return rc;
+  CUDA_TRY(cudaMemcpyAsync(ctx.aux0.p, waves.data(), sizeof(int4) * waves.size(), cudaMemcpyHostToDevice, st));
+  CUDA_TRY(cudaStreamSynchronize(st));  // the list is a call-lifetime staging buffer
+  a.waves = (const int4*)ctx.aux0.p;
+  wave_masks(hp, waves, a.vmask_bits, a.wmask_bits);
+  return SPICEY_SUCCESS;
+}
+
+static int32_t tran_solve_device_impl(spicey_handle* h, int32_t dev_index, const spicey_elem_table* table,
                                  const spicey_sweep* sweep, double dt, int64_t steps, const double* d_vsrc,
-                                 const int32_t* vsrc_mask, const double* d_state0, double* d_v, double* d_ielem,
+                                 const int32_t* vsrc_mask, const spicey_waves* wv, const double* d_state0, double* d_v, double* d_ielem,
                                  double* d_state_out, int32_t* d_iters, int32_t* d_status, uint32_t flags,
                                  void* stream) {
   if (!h) return fail(SPICEY_ERR_INVALID, "handle is NULL");
@@ -1092,29 +1158,22 @@ int32_t spicey_tran_solve_device(spicey_handle* h, int32_t dev_index, const spic
   const HostPlan& hp = h->hp;
   CUDA_TRY(cudaSetDevice(ctx.dev));
   cudaStream_t st = (cudaStream_t)stream;
-  std::vector<int> mask(std::max(1, hp.nV), 0);
-  for (int k = 0; k < hp.nV; ++k) {
-    mask[k] = vsrc_mask ? (vsrc_mask[k] != 0) : 0;
-    if (mask[k] && !d_vsrc) return fail(SPICEY_ERR_INVALID, "vsrc_mask set but vsrc is NULL");
-  }
+  WaveList waves;
+  if ((rc = build_waves(hp, wv, vsrc_mask, d_vsrc != nullptr, waves))) return rc;
   DevPlan dp;
   rc = upload_plan(ctx, hp, st, dp, h->blob);
   if (rc) return rc;
-  if ((rc = ctx.aux0.ensure(sizeof(int) * mask.size()))) return rc;
-  CUDA_TRY(cudaMemcpyAsync(ctx.aux0.p, mask.data(), sizeof(int) * mask.size(), cudaMemcpyHostToDevice, st));
-  CUDA_TRY(cudaStreamSynchronize(st));  // mask is a stack-lifetime staging buffer
   dp.n_inst = sweep ? sweep->n_inst : 1;
   dp.n_var = sweep ? sweep->n_var : 0;
   dp.var_values = sweep ? sweep->var_values : nullptr;
   TranArgs a;
-  a.dt = dt; a.steps = steps; a.vsrc = d_vsrc; a.vsrc_mask = (const int*)ctx.aux0.p; a.state0 = d_state0;
-  a.vmask_bits = 0;
-  for (int k = 0; k < hp.nV && k < 32; ++k) a.vmask_bits |= mask[k] ? (1u << k) : 0u;
+  a.dt = dt; a.steps = steps; a.vsrc = d_vsrc; a.state0 = d_state0;
+  if ((rc = stage_waves(ctx, hp, waves, st, a))) return rc;
   a.inst0 = 0; a.n_local = dp.n_inst; a.v = d_v; a.ielem = d_ielem; a.state_out = d_state_out;
   a.iters = d_iters; a.status = d_status;
   int tier = 0;
   int64_t launches = 0;
-  rc = launch_tran(ctx, hp, dp, a, flags, st, &tier, &launches);
+  rc = launch_tran(ctx, hp, dp, a, waves, flags, st, &tier, &launches);
   if (rc) return rc;
   h->stats.kernel_launches = launches;
   h->stats.tier = tier;
@@ -1122,8 +1181,8 @@ int32_t spicey_tran_solve_device(spicey_handle* h, int32_t dev_index, const spic
   return SPICEY_SUCCESS;
 }
 
-int32_t spicey_tran_solve(spicey_handle* h, const spicey_elem_table* table, const spicey_sweep* sweep, double dt,
-                          int64_t steps, const double* vsrc, const int32_t* vsrc_mask, const double* state0,
+static int32_t tran_solve_impl(spicey_handle* h, const spicey_elem_table* table, const spicey_sweep* sweep, double dt,
+                          int64_t steps, const double* vsrc, const int32_t* vsrc_mask, const spicey_waves* wv, const double* state0,
                           double* v, double* ielem, double* state_out, int32_t* iters, int32_t* status,
                           uint32_t flags) {
   if (!h) return fail(SPICEY_ERR_INVALID, "handle is NULL");
@@ -1136,13 +1195,10 @@ int32_t spicey_tran_solve(spicey_handle* h, const spicey_elem_table* table, cons
   const int n_var = sweep ? sweep->n_var : 0;
   const long long S1 = steps + 1;
   const int D = (int)h->devs.size();
-  std::vector<int> mask(std::max(1, hp.nV), 0);
-  bool any_wave = false;
-  for (int k = 0; k < hp.nV; ++k) {
-    mask[k] = vsrc_mask ? (vsrc_mask[k] != 0) : 0;
-    any_wave |= mask[k] != 0;
-  }
-  if (any_wave && !vsrc) return fail(SPICEY_ERR_INVALID, "vsrc_mask set but vsrc is NULL");
+  WaveList waves;
+  if ((rc = build_waves(hp, wv, vsrc_mask, vsrc != nullptr, waves))) return rc;
+  bool any_wave = false;   // any pre-sampled row to upload
+  for (int k = 0; k < hp.nV; ++k) any_wave |= waves[k].x == WAVE_TABLE;
   int64_t launches = 0, h2d = 0, d2h = 0;
   int tier = 0;
   std::vector<std::pair<long long, long long>> shards(D);
@@ -1155,15 +1211,11 @@ int32_t spicey_tran_solve(spicey_handle* h, const spicey_elem_table* table, cons
     DevPlan dp;
     rc = upload_plan(ctx, hp, ctx.compute, dp, h->blob);
     if (rc) return rc;
-    if ((rc = ctx.aux0.ensure(sizeof(int) * mask.size()))) return rc;
-    CUDA_TRY(cudaMemcpyAsync(ctx.aux0.p, mask.data(), sizeof(int) * mask.size(), cudaMemcpyHostToDevice, ctx.compute));
-    CUDA_TRY(cudaStreamSynchronize(ctx.compute));
     h2d += (int64_t)h->blob.size();
     dp.n_inst = n_inst; dp.n_var = n_var;
     TranArgs a;
-    a.dt = dt; a.steps = steps; a.vsrc = nullptr; a.vsrc_mask = (const int*)ctx.aux0.p; a.state0 = nullptr;
-    a.vmask_bits = 0;
-    for (int k = 0; k < hp.nV && k < 32; ++k) a.vmask_bits |= mask[k] ? (1u << k) : 0u;
+    a.dt = dt; a.steps = steps; a.vsrc = nullptr; a.state0 = nullptr;
+    if ((rc = stage_waves(ctx, hp, waves, ctx.compute, a))) return rc;
     if (any_wave) {
       size_t b = sizeof(double) * (size_t)hp.nV * S1;
       if ((rc = ctx.in0.ensure(b))) return rc;
@@ -1197,7 +1249,7 @@ int32_t spicey_tran_solve(spicey_handle* h, const spicey_elem_table* table, cons
     a.iters = iters ? (int*)ctx.out_s[1].p : nullptr;
     a.status = (int*)ctx.out_s[0].p;
     CUDA_TRY(cudaEventRecord(ctx.get_event(0), ctx.compute));
-    rc = launch_tran(ctx, hp, dp, a, flags, ctx.compute, &tier, &launches);
+    rc = launch_tran(ctx, hp, dp, a, waves, flags, ctx.compute, &tier, &launches);
     if (rc) return rc;
     CUDA_TRY(cudaEventRecord(ctx.get_event(1), ctx.compute));
     // [rows][n_local] device slabs -> [rows][n_inst] host arrays at column offset lo
@@ -1238,6 +1290,42 @@ int32_t spicey_tran_solve(spicey_handle* h, const spicey_elem_table* table, cons
   return SPICEY_SUCCESS;
 }
 
+extern "C" {
+
+int32_t spicey_tran_solve_device(spicey_handle* h, int32_t dev_index, const spicey_elem_table* table,
+                                 const spicey_sweep* sweep, double dt, int64_t steps, const double* d_vsrc,
+                                 const int32_t* vsrc_mask, const double* d_state0, double* d_v, double* d_ielem,
+                                 double* d_state_out, int32_t* d_iters, int32_t* d_status, uint32_t flags,
+                                 void* stream) {
+  return tran_solve_device_impl(h, dev_index, table, sweep, dt, steps, d_vsrc, vsrc_mask, nullptr, d_state0, d_v, d_ielem,
+                                d_state_out, d_iters, d_status, flags, stream);
+}
+
+int32_t spicey_tran_solve(spicey_handle* h, const spicey_elem_table* table, const spicey_sweep* sweep, double dt,
+                          int64_t steps, const double* vsrc, const int32_t* vsrc_mask, const double* state0,
+                          double* v, double* ielem, double* state_out, int32_t* iters, int32_t* status,
+                          uint32_t flags) {
+  return tran_solve_impl(h, table, sweep, dt, steps, vsrc, vsrc_mask, nullptr, state0, v, ielem, state_out, iters, status, flags);
+}
+
+int32_t spicey_tran_solve_waves(spicey_handle* h, const spicey_elem_table* table, const spicey_sweep* sweep, double dt,
+                                int64_t steps, const spicey_waves* waves, const double* vsrc, const double* state0,
+                                double* v, double* ielem, double* state_out, int32_t* iters, int32_t* status,
+                                uint32_t flags) {
+  if (!waves) return fail(SPICEY_ERR_INVALID, "waves is NULL");
+  return tran_solve_impl(h, table, sweep, dt, steps, vsrc, nullptr, waves, state0, v, ielem, state_out, iters, status, flags);
+}
+
+int32_t spicey_tran_solve_waves_device(spicey_handle* h, int32_t dev_index, const spicey_elem_table* table,
+                                       const spicey_sweep* sweep, double dt, int64_t steps, const spicey_waves* waves,
+                                       const double* d_vsrc, const double* d_state0, double* d_v, double* d_ielem,
+                                       double* d_state_out, int32_t* d_iters, int32_t* d_status, uint32_t flags,
+                                       void* stream) {
+  if (!waves) return fail(SPICEY_ERR_INVALID, "waves is NULL");
+  return tran_solve_device_impl(h, dev_index, table, sweep, dt, steps, d_vsrc, nullptr, waves, d_state0, d_v, d_ielem,
+                                d_state_out, d_iters, d_status, flags, stream);
+}
+
 int64_t spicey_debug_sparse_source(const spicey_elem_table* table, const spicey_sweep* sweep, double pilot_f, int32_t block,
                                    int32_t min_blocks, int32_t smem_slots, int32_t with_ielem, char* buf, int64_t cap,
                                    int32_t* stats_out) {
@@ -1267,11 +1355,20 @@ int64_t spicey_debug_sparse_source(const spicey_elem_table* table, const spicey_
 
 int64_t spicey_debug_tran_source(const spicey_elem_table* table, const spicey_sweep* sweep, int32_t with_ielem,
                                  char* buf, int64_t cap) {
+  return spicey_debug_tran_source_waves(table, sweep, nullptr, with_ielem, buf, cap);
+}
+
+int64_t spicey_debug_tran_source_waves(const spicey_elem_table* table, const spicey_sweep* sweep, const spicey_waves* waves,
+                                       int32_t with_ielem, char* buf, int64_t cap) {
   HostPlan hp;
   if (build_plan(table, sweep, hp) != SPICEY_SUCCESS) return -1;
   if (hp.nvar > 8 || hp.n_elem > 48 || hp.nV > 32) { fail(SPICEY_ERR_UNSUPPORTED, "the compiled transient kernel covers Nvar <= 8"); return -1; }
   std::string src;
-  tran_jit_source(hp, with_ielem != 0, src);
+  WaveList wl;
+  if (build_waves(hp, waves, nullptr, true, wl) != SPICEY_SUCCESS) return -1;
+  for (int k = 0; k < hp.nV; ++k)
+    if (wl[k].x == WAVE_PWL && wl[k].z > kTranJitMaxPwlPairs) { fail(SPICEY_ERR_UNSUPPORTED, "PWL source with more pairs than the compiled kernel unrolls"); return -1; }
+  tran_jit_source(hp, wl, with_ielem != 0, src);
   if (buf && cap > 0) {
     const size_t n = std::min<size_t>(src.size(), (size_t)cap - 1);
     memcpy(buf, src.data(), n);

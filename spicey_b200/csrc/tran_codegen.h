@@ -37,7 +37,12 @@ struct TranCodegenInput {
   const int* var_of_slot = nullptr;  // [n_values] sweep variable of a slot or -1
   bool with_ielem = true;
   int block = 64;
+  // Device-evaluated source waveforms (null: every source is dc or a pre-sampled row, chosen by a.vmask):
+  const int* wave_kind = nullptr;    // [nV] 0 dc, 1 pre-sampled row, 2 PULSE, 3 PWL
+  const int* wave_vidx = nullptr;    // [nV] first value slot of the parameters
+  const int* wave_npairs = nullptr;  // [nV] PWL pair count
 };
+constexpr int kTranJitMaxPwlPairs = 32;
 
 inline const char* tran_jit_prelude() {
   return R"SRC(
@@ -58,6 +63,25 @@ __device__ __forceinline__ double rcp_nr(double a) {
   e = fma(-a, y, 1.0); y = fma(y, e, y);
   e = fma(-a, y, 1.0); y = fma(y, e, y);
   return y;
+}
+// pulseValue.ts:4-22 and one segment of pwlValue.ts:9-13, every operation separately rounded (the branch
+// conditions sit on pulse edges; the result must equal the host's pre-sampled table bit for bit).
+__device__ __forceinline__ double pulse_value(double v1, double v2, double td, double tr, double tf, double ton,
+                                              double period, double ncycles, double t) {
+  if (t < td) return v1;
+  const double tt = __dsub_rn(t, td);
+  const double cycles = floor(__ddiv_rn(tt, period));
+  if (cycles >= ncycles) return v1;
+  const double tc = __dsub_rn(tt, __dmul_rn(cycles, period));
+  if (tc < tr) return __dadd_rn(v1, __dmul_rn(__dsub_rn(v2, v1), __ddiv_rn(tc, fmax(tr, EPS))));
+  const double t1 = __dadd_rn(tr, ton);
+  if (tc < t1) return v2;
+  if (tc < __dadd_rn(t1, tf)) return __dadd_rn(v2, __dmul_rn(__dsub_rn(v1, v2), __ddiv_rn(__dsub_rn(tc, t1), fmax(tf, EPS))));
+  return v1;
+}
+__device__ __forceinline__ double pwl_segment(double pt, double pv, double ct, double cv, double t) {
+  const double a = __ddiv_rn(__dsub_rn(t, pt), fmax(__dsub_rn(ct, pt), EPS));
+  return __dadd_rn(pv, __dmul_rn(__dsub_rn(cv, pv), a));
 }
 // solveReal.ts:14-71 for an NV x NV system held in registers: factor() once per matrix, solve() per
 // right-hand side (replays the recorded interchanges and multipliers: the same operations on the same
@@ -137,6 +161,12 @@ inline std::string generate_tran_kernel_source(const TranCodegenInput& in) {
   auto hexlit = [](double v) {
     char buf[64];
     if (v == 0.0) return std::string("0.0");
+    if (v != v || v - v != 0.0) {   // NaN / +-Infinity (PULSE ncycles defaults to Infinity): no literal form
+      unsigned long long bits;
+      memcpy(&bits, &v, sizeof bits);
+      snprintf(buf, sizeof buf, "__longlong_as_double(0x%llxll)", bits);
+      return std::string(buf);
+    }
     snprintf(buf, sizeof buf, "%a", v);
     return v < 0 ? std::string("(") + buf + ")" : std::string(buf);
   };
@@ -175,6 +205,19 @@ inline std::string generate_tran_kernel_source(const TranCodegenInput& in) {
       s += "  const double is" + E + " = " + val(vi) + ", vth" + E + " = " + val(vi + 1) + " * VT300;\n";
       s += "  const double isv" + E + " = is" + E + " / vth" + E + ", ivth" + E + " = 1.0 / vth" + E + ";\n";
       s += "  const double elo" + E + " = exp(-1.0 * ivth" + E + "), ehi" + E + " = exp(0.8 * ivth" + E + ");\n";
+    }
+  }
+  // ---- per-instance waveform parameters (value slots like any other: a sweep may vary them) ----
+  auto wkind = [&](int k) { return in.wave_kind ? in.wave_kind[k] : -1; };
+  for (int e = oV; e < oS; ++e) {
+    const int k = e - oV, ws = in.wave_vidx ? in.wave_vidx[k] : 0;
+    const std::string E = N(e);
+    if (wkind(k) == 2) {
+      const char* nm[8] = {"v1", "v2", "td", "tr", "tf", "ton", "per", "ncy"};
+      for (int q = 0; q < 8; ++q) s += "  const double pw" + E + nm[q] + " = " + val(ws + q) + ";\n";
+    } else if (wkind(k) == 3) {
+      for (int q = 0; q < in.wave_npairs[k]; ++q)
+        s += "  const double pl" + E + "t" + N(q) + " = " + val(ws + 2 * q) + ", pl" + E + "v" + N(q) + " = " + val(ws + 2 * q + 1) + ";\n";
     }
   }
   for (int e = 0; e < ne; ++e)
@@ -235,9 +278,26 @@ inline std::string generate_tran_kernel_source(const TranCodegenInput& in) {
   s += "  const size_t v_stride = (size_t)pitch * " + N(nn) + "u, i_stride = (size_t)pitch * " + N(ne) + "u;\n";
   s += "  long long step = 0;\n  int pat = -1;   // pivot sequence of the previous factorisation (diode circuits)\n";
   s += "  for (; step < S1 && status == 0; ++step) {\n";
+  bool any_dev_wave = false;
+  for (int e = oV; e < oS; ++e) any_dev_wave |= wkind(e - oV) >= 2;
+  if (any_dev_wave) s += "    const double tnow = __dmul_rn((double)step, a.dt);   // t = step * dt (simulateTRAN.ts:147)\n";
   for (int e = oV; e < oS; ++e) {
     const int k = e - oV;
-    s += "    const double vs" + N(e) + " = ((a.vmask >> " + N(k) + ") & 1u) ? __ldg(a.vsrc + " + N(k) + "ll * S1 + step) : dc" + N(e) + ";\n";
+    const std::string E = N(e);
+    if (wkind(k) == 2) {
+      s += "    const double vs" + E + " = pulse_value(pw" + E + "v1, pw" + E + "v2, pw" + E + "td, pw" + E + "tr, pw" + E + "tf, pw" + E +
+           "ton, pw" + E + "per, pw" + E + "ncy, tnow);\n";
+    } else if (wkind(k) == 3) {   // pwlValue.ts:3-16, the pair loop written out
+      const int np = in.wave_npairs[k];
+      if (np <= 0) { s += "    const double vs" + E + " = 0.0;\n"; continue; }
+      s += "    double vs" + E + " = pl" + E + "v" + N(np - 1) + ";\n";
+      s += "    if (tnow <= pl" + E + "t0) vs" + E + " = pl" + E + "v0;\n";
+      for (int q = 1; q < np; ++q)
+        s += "    else if (tnow <= pl" + E + "t" + N(q) + ") vs" + E + " = pwl_segment(pl" + E + "t" + N(q - 1) + ", pl" + E + "v" + N(q - 1) +
+             ", pl" + E + "t" + N(q) + ", pl" + E + "v" + N(q) + ", tnow);\n";
+    } else {
+      s += "    const double vs" + E + " = ((a.vmask >> " + N(k) + ") & 1u) ? __ldg(a.vsrc + " + N(k) + "ll * S1 + step) : dc" + E + ";\n";
+    }
   }
   s += "    int it = 0;\n";
   if (has_sw) s += "    for (; it < 20; ++it) {\n";

@@ -26,9 +26,10 @@ namespace spicey {
 struct TranArgs {
   double dt;
   long long steps;
-  const double* vsrc;       // [nV][steps+1] or null
-  const int* vsrc_mask;     // [nV]
-  unsigned vmask_bits;      // the same mask as bits (first 32 sources), for the compiled kernel
+  const double* vsrc;       // [nV][steps+1] or null: rows of the sources of kind WAVE_TABLE
+  const int4* waves;        // [nV] {kind, first value slot of the parameters, PWL pair count, 0}
+  unsigned vmask_bits;      // sources of kind WAVE_TABLE as bits (first 32 sources), for the compiled kernel
+  unsigned wmask_bits;      // sources evaluated on the device (WAVE_PULSE / WAVE_PWL) as bits
   const double* state0;     // [n_state][n_inst] or null
   long long inst0;          // global index of local instance 0 (for sweep values / state0)
   long long n_local;        // instances handled by this launch
@@ -38,6 +39,62 @@ struct TranArgs {
   int* iters;               // [steps+1][n_local] or null
   int* status;              // [n_local]
 };
+
+// Source waveforms (simulateTRAN.ts:66-69: V = waveform ? waveform(t) : dc).
+enum { WAVE_DC = 0, WAVE_TABLE = 1, WAVE_PULSE = 2, WAVE_PWL = 3 };
+
+// pulseValue (lib/parsing/pulseValue.ts:4-22) for one instance: the eight parameters v1, v2, td, tr, tf, ton,
+// period, ncycles are value slots like any element value, so a sweep can vary them per instance.  Every
+// operation is a separately rounded IEEE operation (no FMA contraction): the branch conditions compare
+// times that differ in the last bit at a pulse edge, and the host's pre-sampled table is what the result
+// must equal bit for bit.  period == 0 and ncycles == Infinity behave as in JavaScript (IEEE division).
+__device__ __forceinline__ double pulse_value(double v1, double v2, double td, double tr, double tf, double ton,
+                                              double period, double ncycles, double t) {
+  if (t < td) return v1;
+  const double tt = __dsub_rn(t, td);
+  const double cycles = floor(__ddiv_rn(tt, period));
+  if (cycles >= ncycles) return v1;
+  const double tc = __dsub_rn(tt, __dmul_rn(cycles, period));
+  if (tc < tr) return __dadd_rn(v1, __dmul_rn(__dsub_rn(v2, v1), __ddiv_rn(tc, fmax(tr, kEps))));
+  const double t1 = __dadd_rn(tr, ton);
+  if (tc < t1) return v2;
+  if (tc < __dadd_rn(t1, tf)) return __dadd_rn(v2, __dmul_rn(__dsub_rn(v1, v2), __ddiv_rn(__dsub_rn(tc, t1), fmax(tf, kEps))));
+  return v1;
+}
+
+// One segment of pwlValue (lib/parsing/pwlValue.ts:9-13).
+__device__ __forceinline__ double pwl_segment(double pt, double pv, double ct, double cv, double t) {
+  const double a = __ddiv_rn(__dsub_rn(t, pt), fmax(__dsub_rn(ct, pt), kEps));
+  return __dadd_rn(pv, __dmul_rn(__dsub_rn(cv, pv), a));
+}
+
+// Value of a device-evaluated source at t = step * dt (simulateTRAN.ts:147) for instance `inst`.
+__device__ __noinline__ double wave_value(const DevPlan& P, int4 w, long long inst, double t) {
+  const int s = w.y;
+  if (w.x == WAVE_PULSE)
+    return pulse_value(inst_value(P, s, inst), inst_value(P, s + 1, inst), inst_value(P, s + 2, inst),
+                       inst_value(P, s + 3, inst), inst_value(P, s + 4, inst), inst_value(P, s + 5, inst),
+                       inst_value(P, s + 6, inst), inst_value(P, s + 7, inst), t);
+  // pwlValue.ts:3-16
+  if (w.z <= 0) return 0.0;
+  double pt = inst_value(P, s, inst), pv = inst_value(P, s + 1, inst);
+  if (t <= pt) return pv;
+  for (int i = 1; i < w.z; ++i) {
+    const double ct = inst_value(P, s + 2 * i, inst), cv = inst_value(P, s + 2 * i + 1, inst);
+    if (t <= ct) return pwl_segment(pt, pv, ct, cv, t);
+    pt = ct; pv = cv;
+  }
+  return pv;
+}
+
+// The k-th V element's value at this step: dc, its pre-sampled row, or the waveform evaluated here.
+__device__ __forceinline__ double source_value(const DevPlan& P, const TranArgs& a, int k, long long step,
+                                               long long inst, double dc) {
+  const int4 w = a.waves[k];
+  if (w.x == WAVE_DC) return dc;
+  if (w.x == WAVE_TABLE) return a.vsrc[(long long)k * (a.steps + 1) + step];
+  return wave_value(P, w, inst, __dmul_rn((double)step, a.dt));
+}
 
 template <bool STRICT> __device__ __forceinline__ double t_mul(double a, double b) {
   return STRICT ? __dmul_rn(a, b) : a * b;
@@ -202,7 +259,7 @@ __global__ void tran_thread_kernel(DevPlan P, TranArgs a, int n_ent, int n_con) 
     for (int i = 0; i < nvar; ++i) x[i * NT] = 0.0;                       // :149
     for (int e = P.off[ELEM_V]; e < P.off[ELEM_V + 1]; ++e) {             // :66-69
       int k = e - P.off[ELEM_V];
-      jj[e * NT] = a.vsrc_mask[k] ? a.vsrc[(long long)k * S1 + step] : ec[(4 * e) * NT];
+      jj[e * NT] = source_value(P, a, k, step, inst, ec[(4 * e) * NT]);
     }
     int it = 0;
     for (; it < 20; ++it) {                                               // :151
@@ -364,7 +421,7 @@ __global__ void tran_cta_kernel(DevPlan P, TranArgs a, double* scratch) {
           else if (type == ELEM_S) g[e] = 1 / (st[sidx[e]] != 0.0 ? ec[4 * e] : ec[4 * e + 1]);
           else if (type == ELEM_V) {
             int k = e - P.off[ELEM_V];
-            jj[e] = a.vsrc_mask[k] ? a.vsrc[(long long)k * S1 + step] : ec[4 * e];
+            jj[e] = source_value(P, a, k, step, inst, ec[4 * e]);
           } else if (type == ELEM_D) {
             int4 en = ends[e];
             double vd = it == 0 ? st[sidx[e]] : VOLT(en.x) - VOLT(en.y);

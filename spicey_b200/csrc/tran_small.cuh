@@ -214,8 +214,7 @@ __global__ void __launch_bounds__(NT) tran_small_kernel(DevPlan P, TranArgs a) {
   int* ito = a.iters ? a.iters + li : nullptr;
   const long long v_stride = (long long)nn * NL, i_stride = (long long)ne * NL;
   const double* vsrc = a.vsrc;
-  unsigned vmask = 0;
-  for (int k = 0; k < oS - oV; ++k) vmask |= a.vsrc_mask[k] ? (1u << k) : 0u;
+  const unsigned vmask = a.vmask_bits, wmask = a.wmask_bits;   // the host routes nV > 32 to the generic tiers
   for (; step < S1; ++step) {
     // :149 zeroes x every step; nothing reads x before the step's first solve (the diode uses vdPrev at
     // iteration 0, :85), so the zeroing is not materialised.
@@ -241,7 +240,10 @@ __global__ void __launch_bounds__(NT) tran_small_kernel(DevPlan P, TranArgs a) {
       #pragma unroll 1
       for (int e = oV; e < oS; ++e) {
         const int k = e - oV;
-        SM_D(bs, (nn + k) * SB) += ((vmask >> k) & 1u) ? __ldg(vsrc + (long long)k * S1 + step) : SM_D(ec, 4 * e * SB);
+        double vs;
+        if ((wmask >> k) & 1u) vs = wave_value(P, a.waves[k], inst, __dmul_rn((double)step, a.dt));   // :147 t = step*dt
+        else vs = ((vmask >> k) & 1u) ? __ldg(vsrc + (long long)k * S1 + step) : SM_D(ec, 4 * e * SB);
+        SM_D(bs, (nn + k) * SB) += vs;
       }
       // ---- dynamic part of A: switches then diodes (:56-63, :72-101) ----
       if (dyn) {

@@ -25,7 +25,9 @@ EXPORTS = [
     "spicey_destroy", "spicey_get_stats", "spicey_host_alloc", "spicey_host_free", "spicey_ac_solve",
     "spicey_ac_solve_device", "spicey_tran_solve", "spicey_tran_solve_device", "spicey_measure_fp64_peak",
     "spicey_debug_sparse_source", "spicey_series_ld", "spicey_debug_tran_source", "spicey_debug_warp_stats",
+    "spicey_tran_solve_waves", "spicey_tran_solve_waves_device", "spicey_debug_tran_source_waves",
 ]
+WAVE_DC, WAVE_TABLE, WAVE_PULSE, WAVE_PWL = 0, 1, 2, 3
 
 _ip = C.POINTER(C.c_int32)
 _dp = C.POINTER(C.c_double)
@@ -40,6 +42,10 @@ class ElemTableStruct(C.Structure):
 class SweepStruct(C.Structure):
     _fields_ = [("n_inst", C.c_int64), ("n_var", C.c_int32), ("reserved", C.c_int32), ("var_slot", _ip),
                 ("var_values", C.c_void_p)]
+
+
+class WavesStruct(C.Structure):
+    _fields_ = [("n_vsrc", C.c_int32), ("reserved", C.c_int32), ("kind", _ip), ("value_idx", _ip), ("n_pairs", _ip)]
 
 
 class StatsStruct(C.Structure):
@@ -95,6 +101,14 @@ def load_library(path: Optional[str] = None):
     lib.spicey_tran_solve_device.restype = C.c_int32
     lib.spicey_tran_solve_device.argtypes = [vp, C.c_int32, tb, sw, C.c_double, C.c_int64, vp, vp, vp, vp, vp, vp,
                                              vp, vp, C.c_uint32, vp]
+    wv = C.POINTER(WavesStruct)
+    lib.spicey_tran_solve_waves.restype = C.c_int32
+    lib.spicey_tran_solve_waves.argtypes = [vp, tb, sw, C.c_double, C.c_int64, wv, vp, vp, vp, vp, vp, vp, vp, C.c_uint32]
+    lib.spicey_tran_solve_waves_device.restype = C.c_int32
+    lib.spicey_tran_solve_waves_device.argtypes = [vp, C.c_int32, tb, sw, C.c_double, C.c_int64, wv, vp, vp, vp, vp,
+                                                   vp, vp, vp, C.c_uint32, vp]
+    lib.spicey_debug_tran_source_waves.restype = C.c_int64
+    lib.spicey_debug_tran_source_waves.argtypes = [tb, sw, wv, C.c_int32, C.c_char_p, C.c_int64]
     lib.spicey_measure_fp64_peak.restype = C.c_int32
     lib.spicey_measure_fp64_peak.argtypes = [vp, C.c_int32, _dp]
     lib.spicey_debug_sparse_source.restype = C.c_int64
@@ -120,17 +134,20 @@ def warp_program_stats(table: "ElemTable", pilot_f: float = 1000.0) -> dict:
     return dict(zip(keys, list(st)))
 
 
-def tran_kernel_source(table: "ElemTable", sweep: Optional["Sweep"] = None, with_ielem=True) -> str:
+def tran_kernel_source(table: "ElemTable", sweep: Optional["Sweep"] = None, with_ielem=True,
+                       waves: Optional["Waves"] = None) -> str:
     """CUDA source of the compiled transient kernel (tier 6) for a circuit.  Host-only tooling."""
     lib = load_library()
     ts = table.struct()
     ss = sweep.struct() if sweep else None
     sp_ = C.byref(ss) if ss else None
-    need = lib.spicey_debug_tran_source(C.byref(ts), sp_, int(with_ielem), None, 0)
+    ws = waves.struct() if waves else None
+    wp_ = C.byref(ws) if ws else None
+    need = lib.spicey_debug_tran_source_waves(C.byref(ts), sp_, wp_, int(with_ielem), None, 0)
     if need < 0:
         raise NativeError(-1, (lib.spicey_last_error() or b"").decode())
     buf = C.create_string_buffer(need)
-    lib.spicey_debug_tran_source(C.byref(ts), sp_, int(with_ielem), buf, need)
+    lib.spicey_debug_tran_source_waves(C.byref(ts), sp_, wp_, int(with_ielem), buf, need)
     return buf.value.decode()
 
 
@@ -177,6 +194,8 @@ class ElemTable:
         self.n_ac_elem = int((self.type <= ELEM_V).sum())
         self.n_state = int(np.isin(self.type, (ELEM_C, ELEM_L, ELEM_S, ELEM_D)).sum())
         self.nvar = self.n_nodes + self.n_vsrc
+        self.waves = None        # native.Waves when packed with device_waves (packing.pack_circuit)
+        self.wave_params = {}
 
     def struct(self) -> ElemTableStruct:
         s = ElemTableStruct()
@@ -205,6 +224,23 @@ class Sweep:
         return s
 
 
+class Waves:
+    """Per-source waveform descriptors (spicey_waves): kind, first parameter slot, PWL pair count."""
+
+    def __init__(self, kind, value_idx, n_pairs):
+        self.kind = np.ascontiguousarray(kind, dtype=np.int32)
+        self.value_idx = np.ascontiguousarray(value_idx, dtype=np.int32)
+        self.n_pairs = np.ascontiguousarray(n_pairs, dtype=np.int32)
+
+    def struct(self) -> WavesStruct:
+        s = WavesStruct()
+        s.n_vsrc = int(self.kind.shape[0])
+        s.kind = self.kind.ctypes.data_as(_ip)
+        s.value_idx = self.value_idx.ctypes.data_as(_ip)
+        s.n_pairs = self.n_pairs.ctypes.data_as(_ip)
+        return s
+
+
 def _ptr(a):
     return None if a is None else C.c_void_p(a.ctypes.data)
 
@@ -214,7 +250,7 @@ class Engine:
 
     def __init__(self, devices: Optional[Sequence[int]] = None, lib_path: Optional[str] = None):
         self.lib = load_library(lib_path)
-        if self.lib.spicey_native_abi_version() != 2:
+        if self.lib.spicey_native_abi_version() != 3:
             raise NativeError(ERR_INVALID, "ABI version mismatch")
         self._h = C.c_void_p()
         arr = None if devices is None else np.ascontiguousarray(devices, dtype=np.int32)
@@ -268,8 +304,9 @@ class Engine:
 
     def tran_solve(self, table: ElemTable, dt: float, steps: int, vsrc=None, vsrc_mask=None,
                    sweep: Optional[Sweep] = None, state0=None, want_currents=True, want_iters=False, flags=0,
-                   out=None):
-        """Returns dict(v[S1,nn,n_inst], ielem[S1,n_elem,n_inst]|None, state[n_state,n_inst], iters, status)."""
+                   out=None, waves: Optional[Waves] = None):
+        """Returns dict(v[S1,nn,n_inst], ielem[S1,n_elem,n_inst]|None, state[n_state,n_inst], iters, status).
+        waves: per-source descriptors (PULSE / PWL evaluated on the device); vsrc_mask is then ignored."""
         n_inst = sweep.n_inst if sweep else 1
         S1 = steps + 1
         nV = table.n_vsrc
@@ -290,9 +327,15 @@ class Engine:
         status = np.empty(n_inst, dtype=np.int32)
         ts = table.struct()
         ss = sweep.struct() if sweep else None
-        _check(self.lib, self.lib.spicey_tran_solve(
-            self._h, C.byref(ts), C.byref(ss) if ss else None, float(dt), int(steps), _ptr(vsrc), _ptr(mask),
-            _ptr(state0), _ptr(v), _ptr(ie), _ptr(state), _ptr(iters), _ptr(status), flags))
+        if waves is not None:
+            ws = waves.struct()
+            _check(self.lib, self.lib.spicey_tran_solve_waves(
+                self._h, C.byref(ts), C.byref(ss) if ss else None, float(dt), int(steps), C.byref(ws), _ptr(vsrc),
+                _ptr(state0), _ptr(v), _ptr(ie), _ptr(state), _ptr(iters), _ptr(status), flags))
+        else:
+            _check(self.lib, self.lib.spicey_tran_solve(
+                self._h, C.byref(ts), C.byref(ss) if ss else None, float(dt), int(steps), _ptr(vsrc), _ptr(mask),
+                _ptr(state0), _ptr(v), _ptr(ie), _ptr(state), _ptr(iters), _ptr(status), flags))
         return {"v": v, "ielem": ie, "state": state, "iters": iters, "status": status}
 
     # -- device-resident entry points (raw device pointers as ints) ----------------
@@ -313,9 +356,16 @@ class Engine:
     def tran_solve_device(self, table: ElemTable, dt: float, steps: int, d_vsrc: Optional[int], vsrc_mask,
                           d_state0: Optional[int], d_v: int, d_ielem: Optional[int], d_state_out: Optional[int],
                           d_iters: Optional[int], d_status: int, sweep: Optional[Sweep] = None,
-                          d_var_values: Optional[int] = None, flags=0, stream: int = 0, dev_index: int = 0):
+                          d_var_values: Optional[int] = None, flags=0, stream: int = 0, dev_index: int = 0,
+                          waves: Optional[Waves] = None):
         ts = table.struct()
         ss = sweep.struct(d_var_values) if sweep else None
+        if waves is not None:
+            ws = waves.struct()
+            _check(self.lib, self.lib.spicey_tran_solve_waves_device(
+                self._h, dev_index, C.byref(ts), C.byref(ss) if ss else None, float(dt), int(steps), C.byref(ws), d_vsrc,
+                d_state0, d_v, d_ielem, d_state_out, d_iters, d_status, flags, stream))
+            return
         mask = np.zeros(max(1, table.n_vsrc), dtype=np.int32)
         if vsrc_mask is not None:
             mask[:table.n_vsrc] = np.asarray(vsrc_mask, dtype=np.int32)

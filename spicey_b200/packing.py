@@ -11,7 +11,8 @@ from typing import Dict, Optional
 
 import numpy as np
 
-from .native import ELEM_C, ELEM_D, ELEM_L, ELEM_R, ELEM_S, ELEM_V, ElemTable, Sweep
+from .native import (ELEM_C, ELEM_D, ELEM_L, ELEM_R, ELEM_S, ELEM_V, WAVE_DC, WAVE_PULSE, WAVE_PWL, ElemTable, Sweep,
+                     Waves)
 
 _PARAM_OFFSETS = {
     ELEM_V: {"dc": 0, "acmag": 1, "acphase": 2},
@@ -20,7 +21,13 @@ _PARAM_OFFSETS = {
 }
 
 
-def pack_circuit(ckt) -> ElemTable:
+_PULSE_PARAMS = ("v1", "v2", "td", "tr", "tf", "ton", "period", "ncycles")  # PulseSpec, lib/types/simulation.ts:1-10
+
+
+def pack_circuit(ckt, device_waves: bool = False) -> ElemTable:
+    """device_waves: also append the PULSE / PWL parameters of the V elements as value slots (after the element
+    values) and attach `table.waves` (native.Waves) so the kernels evaluate pulseValue / pwlValue themselves
+     — the parameters can then be swept per instance like any R or C."""
     types, n1, n2, c1, c2, vidx, values, names = [], [], [], [], [], [], [], []
 
     def add(t, a, b, vals, name, ca=0, cb=0):
@@ -43,19 +50,52 @@ def pack_circuit(ckt) -> ElemTable:
         if d.model is None:
             continue
         add(ELEM_D, d.nPlus, d.nMinus, [d.model.Is, d.model.N], d.name)
-    return ElemTable(ckt.nodes.count() - 1, types, n1, n2, c1, c2, vidx, values, names=names,
-                     node_names=ckt.nodes.rev[1:])
+    kinds, widx, npairs, wparams = [], [], [], {}
+    if device_waves:
+        for v in ckt.V:
+            kinds.append(WAVE_DC); widx.append(0); npairs.append(0)
+            if getattr(v, "pulse", None) is not None:
+                kinds[-1], widx[-1] = WAVE_PULSE, len(values)
+                for q, nm in enumerate(_PULSE_PARAMS):
+                    wparams["%s.pulse.%s" % (v.name.lower(), nm)] = len(values) + q
+                values.extend(float(getattr(v.pulse, nm)) for nm in _PULSE_PARAMS)
+            elif getattr(v, "pwl", None) is not None:
+                kinds[-1], widx[-1], npairs[-1] = WAVE_PWL, len(values), len(v.pwl)
+                for q, (t, val) in enumerate(v.pwl):
+                    wparams["%s.pwl.t%d" % (v.name.lower(), q)] = len(values)
+                    wparams["%s.pwl.v%d" % (v.name.lower(), q)] = len(values) + 1
+                    values.extend((float(t), float(val)))
+    table = ElemTable(ckt.nodes.count() - 1, types, n1, n2, c1, c2, vidx, values, names=names,
+                      node_names=ckt.nodes.rev[1:])
+    table.waves = Waves(kinds, widx, npairs) if device_waves else None
+    table.wave_params = wparams   # "v1.pulse.v2" / "v1.pwl.t3" -> value slot, for make_sweep
+    return table
+
+
+def has_wave_override(overrides) -> bool:
+    return any(".pulse." in k.lower() or ".pwl." in k.lower() for k in (overrides or {}))
 
 
 def make_sweep(table: ElemTable, n_inst: int, overrides: Optional[Dict[str, np.ndarray]]) -> Optional[Sweep]:
     """overrides: element name -> per-instance values (R/C/L), or "name.param" with param in
-    dc/acmag/acphase (V), ron/roff/von/voff (S), is/n (D).  Case-insensitive."""
+    dc/acmag/acphase (V), ron/roff/von/voff (S), is/n (D); for a table packed with device_waves also
+    "name.pulse.v1|v2|td|tr|tf|ton|period|ncycles" and "name.pwl.t<k>|v<k>".  Case-insensitive."""
     if n_inst == 1 and not overrides:
         return None
     slots, rows = [], []
     lower = {n.lower(): i for i, n in reversed(list(enumerate(table.names)))}
     for key, vals in (overrides or {}).items():
         k = key.lower()
+        wave_slots = getattr(table, "wave_params", None) or {}
+        if ".pulse." in k or ".pwl." in k:
+            if k not in wave_slots:
+                raise KeyError("no waveform parameter %r (table packed with device_waves=True?)" % key)
+            slots.append(wave_slots[k])
+            arr = np.asarray(vals, dtype=np.float64).reshape(-1)
+            if arr.shape[0] != n_inst:
+                raise ValueError("override %r has %d values, expected %d" % (key, arr.shape[0], n_inst))
+            rows.append(arr)
+            continue
         name, _, param = k.partition(".")
         if name not in lower and k in lower:
             name, param = k, ""

@@ -72,6 +72,39 @@ def test_transient_kernel_source_compiles(tmp_path, golden, name):
     assert spill == 0
 
 
+WAVE_NETLIST = ("* device-evaluated sources\nV1 1 0 PULSE(0 5 1u 1u 1u 3u 10u)\nV2 3 0 PWL(0 0 1u 1 2u 0.5 4u 2)\n"
+                "R1 1 2 1k\nR2 3 2 2k\nC1 2 0 1u\n.tran 0.1u 20u\n")
+
+
+def test_transient_kernel_source_with_device_waveforms_compiles(tmp_path):
+    """PULSE / PWL parameters are value slots; the generated kernel evaluates pulseValue / pwlValue
+    itself with separately rounded operations, swept parameters are per-instance loads."""
+    ck = parsing.parse_netlist(WAVE_NETLIST)
+    table = packing.pack_circuit(ck, device_waves=True)
+    assert list(table.waves.kind) == [native.WAVE_PULSE, native.WAVE_PWL] and list(table.waves.n_pairs) == [0, 4]
+    p0 = int(table.waves.value_idx[0])
+    assert list(table.values[p0:p0 + 8]) == [0.0, 5.0, 1e-6, 1e-6, 1e-6, 3 * 1e-6, 10 * 1e-6, float("inf")]
+    assert table.wave_params["v2.pwl.t1"] == int(table.waves.value_idx[1]) + 2
+    sweep = packing.make_sweep(table, 4, {"V1.pulse.v2": [1.0, 2.0, 3.0, 4.0], "v2.pwl.t1": [1e-6, 1.1e-6, 1.2e-6, 1.3e-6]})
+    assert list(sweep.var_slot) == [p0 + 1, table.wave_params["v2.pwl.t1"]]
+    src = native.tran_kernel_source(table, sweep, waves=table.waves)
+    body = src.split("spicey_tran_jit")[-1]
+    assert "pulse_value(pw3v1" in body and body.count("pwl_segment(") == 3 and "__dmul_rn((double)step, a.dt)" in body
+    assert "pw3v2 = a.var_values[0ll" in body and "pl4t1 = a.var_values[1ll" in body
+    assert "__longlong_as_double(0x7ff0000000000000ll)" in body        # ncycles = Infinity has no literal form
+    assert "a.vsrc" not in body.split("for (; step")[1]                 # no pre-sampled row is read
+    regs, spill = _compile(src, tmp_path, "tran_waves")
+    assert spill == 0
+    # without descriptors the same table compiles to the row-reading kernel
+    assert "__ldg(a.vsrc" in native.tran_kernel_source(table, sweep)
+    # descriptor validation happens on the host
+    bad = native.Waves([native.WAVE_PULSE, native.WAVE_DC], [len(table.values) - 3, 0], [0, 0])
+    with pytest.raises(native.NativeError, match="waveform parameter slots out of range"):
+        native.tran_kernel_source(table, sweep, waves=bad)
+    with pytest.raises(KeyError):
+        packing.make_sweep(packing.pack_circuit(ck), 2, {"v1.pulse.v2": [1.0, 2.0]})
+
+
 def test_warp_program_sizes_cfg4():
     table = packing.pack_circuit(parsing.parse_netlist(workloads.rc_mesh(16)))
     st = native.warp_program_stats(table)

@@ -385,6 +385,121 @@ def test_tran_rectifier_sweep_slice(eng, flags):
     assert np.max(np.abs(got["ielem"] - ref_i) / cs) <= TRAN_TOL
 
 
+# ---- source waveforms evaluated on the device ---------------------------------
+
+WAVE_FLAGS = [0, native.FLAG_STRICT, native.FLAG_GENERIC_THREAD, native.FLAG_FORCE_CTA, native.FLAG_JIT]
+
+
+@pytest.mark.parametrize("name", ["transient01_rc_pulse", "vswitch_pwl", "boost_converter_probe", "switch_vt_vh"])
+@pytest.mark.parametrize("flags", WAVE_FLAGS)
+def test_tran_device_waveforms_equal_presampled_rows(eng, golden, name, flags):
+    """pulseValue / pwlValue evaluated by the kernels (t = step*dt, separately rounded operations) against the
+    rows the host samples with the reference's own functions: the waveforms of the reference's tests, every tier.
+    The source values are bit-identical, so the recorded source node voltage is too."""
+    import spicey_b200 as sp
+    text = golden(name)["netlist"]
+    a = sp.simulate_tran_batch(parse_netlist(text), engine=eng, flags=flags, want_iters=True, device_waves=False)
+    tier_rows = eng.stats()["tier"]
+    b = sp.simulate_tran_batch(parse_netlist(text), engine=eng, flags=flags, want_iters=True, device_waves=True)
+    assert eng.stats()["tier"] == tier_rows
+    if flags == native.FLAG_JIT:
+        assert tier_rows == native.TIER_TRAN_JIT
+    assert b["status"].max() == 0 and np.array_equal(a["iters"], b["iters"])
+    assert np.array_equal(a["v"], b["v"]) and np.array_equal(a["ielem"], b["ielem"])
+    assert np.array_equal(a["state"], b["state"])
+
+
+def _per_instance_oracle(text, n, mutate, overrides=None):
+    """The reference has no sweep API: one oracle run per instance on a circuit whose parsed PULSE / PWL (the
+    object the waveform closure reads) is changed in place."""
+    vs, ies = [], []
+    for i in range(n):
+        ck = parse_netlist(text)
+        mutate(ck, i)
+        dt, steps = compute_effective_time_step(ck.analyses.tran.dt, ck.analyses.tran.tstop)
+        ov = {k: np.asarray(v)[i:i + 1] for k, v in (overrides or {}).items()}
+        v, ie, iters, st, _ = co.tran_solve(ck, dt, steps, n_inst=1, overrides=ov or None)
+        assert st.max() == 0
+        vs.append(v[0]); ies.append(ie[0])
+    return np.stack(vs, axis=2), np.stack(ies, axis=2)   # [S1, rows, n]
+
+
+@pytest.mark.parametrize("flags", WAVE_FLAGS)
+def test_tran_pulse_parameter_sweep_per_instance(eng, flags):
+    """A sweep over the SOURCE: amplitude, delay, rise time, width and period of a PULSE differ per instance (plus R),
+    evaluated on the device; each instance against its own oracle run."""
+    import spicey_b200 as sp
+    text = "* pulse sweep\nV1 in 0 PULSE(0 5 1u 0.5u 0.5u 2u 8u)\nR1 in out 1k\nC1 out 0 1n\nL1 out x 10u\nR2 x 0 50\n.tran 0.1u 30u\n"
+    n = 24 if flags == native.FLAG_FORCE_CTA else 96
+    rng = np.random.default_rng(7)
+    ov = {"v1.pulse.v1": rng.uniform(-1, 1, n), "v1.pulse.v2": rng.uniform(2, 6, n), "v1.pulse.td": rng.uniform(0, 3e-6, n),
+          "v1.pulse.tr": rng.choice([0.0, 0.1e-6, 0.5e-6, 1e-6], n), "v1.pulse.tf": rng.choice([0.0, 0.3e-6, 0.5e-6], n),
+          "v1.pulse.ton": rng.uniform(0.5e-6, 3e-6, n), "v1.pulse.period": rng.uniform(5e-6, 12e-6, n),
+          "v1.pulse.ncycles": rng.choice([1.0, 2.0, np.inf], n), "R1": rng.uniform(500, 2000, n)}
+    ov["v1.pulse.period"][0] = 0.0     # JavaScript semantics of tt / 0 (Infinity / NaN): the pulse never fires
+    got = sp.simulate_tran_batch(parse_netlist(text), n_inst=n, overrides=ov, engine=eng, flags=flags)
+    if flags == native.FLAG_JIT:
+        assert eng.stats()["tier"] == native.TIER_TRAN_JIT
+    assert got["status"].max() == 0
+
+    def mutate(ck, i):
+        p = ck.V[0].pulse
+        for nm in ("v1", "v2", "td", "tr", "tf", "ton", "period", "ncycles"):
+            setattr(p, nm, float(ov["v1.pulse." + nm][i]))
+
+    ref_v, ref_i = _per_instance_oracle(text, n, mutate, {"R1": ov["R1"]})
+    in_row = [k.lower() for k in got["node_names"]].index("in")
+    assert np.array_equal(got["v"][:, in_row, :], ref_v[:, in_row, :])     # the source itself: bit for bit
+    assert np.max(np.abs(got["v"][:, in_row, 0])) == abs(ov["v1.pulse.v1"][0])
+    tol = 1e-12 if flags & native.FLAG_STRICT else TRAN_TOL
+    assert np.max(np.abs(got["v"] - ref_v)) <= tol * np.max(np.abs(ref_v))
+    assert np.max(np.abs(got["ielem"] - ref_i)) <= tol * np.max(np.abs(ref_i))
+
+
+@pytest.mark.parametrize("flags", WAVE_FLAGS)
+def test_tran_pwl_parameter_sweep_with_switch(eng, golden, flags):
+    """The reference's PWL-driven voltage switch with the PWL breakpoints and levels varied per instance: the
+    switch toggles at different steps in different instances (per-instance re-solve masks)."""
+    import spicey_b200 as sp
+    text = golden("vswitch_pwl")["netlist"]
+    ck0 = parse_netlist(text)
+    k = [i for i, v in enumerate(ck0.V) if v.pwl is not None][0]
+    name = ck0.V[k].name.lower()
+    pairs = ck0.V[k].pwl
+    n = 16 if flags == native.FLAG_FORCE_CTA else 64
+    rng = np.random.default_rng(11)
+    tscale = rng.uniform(0.7, 1.3, n)
+    vscale = rng.uniform(0.8, 1.2, n)
+    ov = {}
+    for q, (t, v) in enumerate(pairs):
+        ov["%s.pwl.t%d" % (name, q)] = t * tscale
+        ov["%s.pwl.v%d" % (name, q)] = v * vscale
+    got = sp.simulate_tran_batch(parse_netlist(text), n_inst=n, overrides=ov, engine=eng, flags=flags, want_iters=True)
+    assert got["status"].max() == 0
+    assert len(set(map(tuple, got["iters"].T))) > 1      # instances really toggle at different steps
+
+    def mutate(ck, i):
+        ck.V[k].pwl[:] = [(float(ov["%s.pwl.t%d" % (name, q)][i]), float(ov["%s.pwl.v%d" % (name, q)][i]))
+                          for q in range(len(pairs))]
+
+    ref_v, ref_i = _per_instance_oracle(text, n, mutate)
+    tol = 1e-12 if flags & native.FLAG_STRICT else TRAN_TOL
+    assert np.max(np.abs(got["v"] - ref_v)) <= tol * np.max(np.abs(ref_v))
+    assert np.max(np.abs(got["ielem"] - ref_i)) <= tol * np.max(np.abs(ref_i))
+
+
+def test_tran_waves_argument_errors(eng):
+    from spicey_b200 import packing
+    ck = parse_netlist("* t\nV1 1 0 PULSE(0 5 0 1n 1n 5u 10u)\nR1 1 2 1k\nC1 2 0 1u\n.tran 0.1u 2u\n")
+    table = packing.pack_circuit(ck, device_waves=True)
+    for waves, msg in ((native.Waves([native.WAVE_PULSE, 0], [0, 0], [0, 0]), "n_vsrc differs"),
+                       (native.Waves([7], [0], [0]), "unknown waveform kind"),
+                       (native.Waves([native.WAVE_PULSE], [len(table.values) - 7], [0]), "slots out of range"),
+                       (native.Waves([native.WAVE_TABLE], [0], [0]), "needs vsrc")):
+        with pytest.raises(native.NativeError, match=msg):
+            eng.tran_solve(table, 1e-7, 20, waves=waves)
+
+
 def test_tran_singular_instance_is_isolated(eng):
     """A singular instance (two sources fighting) reports status 1 and NaNs; neighbours are untouched."""
     import spicey_b200 as sp

@@ -116,7 +116,7 @@ def test_library_loads_and_exports_every_declared_symbol():
     assert declared == set(native.EXPORTS), declared ^ set(native.EXPORTS)
     for sym in declared:
         assert getattr(lib, sym) is not None
-    assert lib.spicey_native_abi_version() == 2
+    assert lib.spicey_native_abi_version() == 3
 
 
 def test_no_cpu_fallback_without_device():

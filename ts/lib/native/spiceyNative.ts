@@ -68,7 +68,7 @@ function tableStruct(t: ElemTable) {
 let handle: Pointer | null = null
 function getHandle(): Pointer {
   if (handle) return handle
-  if (C.spicey_native_abi_version() !== 2)
+  if (C.spicey_native_abi_version() !== 3)
     throw new Error("spicey_native ABI version mismatch")
   const out = new BigUint64Array(1)
   check(C.spicey_create(null, 0, ptr(out)))
