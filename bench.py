@@ -155,7 +155,7 @@ def dist_env():
 
 # ---- workloads --------------------------------------------------------------------------
 
-def load_workload(name, points=None, instances=None):
+def load_workload(name, points=None, instances=None, device_waves=False):
     import spicey_b200 as sp
     from spicey_b200.packing import make_sweep, pack_circuit, sample_sources, initial_state
     wl = {"name": name}
@@ -194,7 +194,7 @@ def load_workload(name, points=None, instances=None):
         ck = parse_netlist(text)
         ov = {k: v[:n] for k, v in ovf(n_full).items()}
         dt, steps = compute_effective_time_step(ck.analyses.tran.dt, ck.analyses.tran.tstop)
-        table = pack_circuit(ck)
+        table = pack_circuit(ck, device_waves=device_waves)   # device_waves: PULSE evaluated by the kernel
         vsrc, mask = sample_sources(ck, dt, steps)
         wl.update(kind="tran", ckt=ck, table=table, dt=dt, steps=steps, vsrc=vsrc, mask=mask, overrides=ov,
                   sweep=make_sweep(table, n, ov), n_inst=n, units=n * (steps + 1),
@@ -300,7 +300,7 @@ def run_native(args):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     dev = torch.device("cuda", local)
     eng = native.Engine([local])
-    wl = load_workload(args.workload, args.points, args.instances)
+    wl = load_workload(args.workload, args.points, args.instances, getattr(args, "device_waves", False))
     table = wl["table"]
     stream = torch.cuda.current_stream()
     peaks, peak_src = read_peaks()
@@ -358,7 +358,7 @@ def run_native(args):
         def step_resident():
             eng.tran_solve_device(table, wl["dt"], wl["steps"], d_vsrc.data_ptr(), wl["mask"], d_st0.data_ptr(),
                                   d_v.data_ptr(), d_i.data_ptr(), None, None, d_s.data_ptr(), sweep=sweep,
-                                  d_var_values=d_var.data_ptr(), stream=stream.cuda_stream)
+                                  d_var_values=d_var.data_ptr(), stream=stream.cuda_stream, waves=table.waves)
 
         h_v, p1 = native.pinned_empty(eng.lib, (S1, table.n_nodes, n), np.float64)
         h_i, p2 = native.pinned_empty(eng.lib, (S1, table.n_elem, n), np.float64)
@@ -366,7 +366,7 @@ def run_native(args):
 
         def step_e2e():
             r = eng.tran_solve(table, wl["dt"], wl["steps"], vsrc=wl["vsrc"], vsrc_mask=wl["mask"], sweep=sweep,
-                               state0=wl["state0"], out=(h_v, h_i))
+                               state0=wl["state0"], out=(h_v, h_i), waves=table.waves)
             return int(r["status"].max())
 
         def check():
@@ -469,6 +469,9 @@ def run_native(args):
             except Exception:
                 pass
         cpu_v, cores, sample = cpu_rate(wl, target_s=12.0)
+        if wl["kind"] == "tran":
+            src_note = "PULSE evaluated on the device from its parameters" if getattr(args, "device_waves", False) \
+                else "pre-sampled row [nV][steps+1], one load per step"
         line = {
             "metric": "batched MNA solves/sec", "value": value, "unit": "solves/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": total_ms / args.steps,
@@ -492,6 +495,8 @@ def run_native(args):
             "gpu_launches": int(launches),
             "clocks": clocks,
         }
+        if wl["kind"] == "tran":
+            line["config"]["sources"] = src_note
         sys.stdout.flush()
         os.write(json_fd, (json.dumps(line) + "\n").encode())
     os.close(json_fd)
@@ -512,6 +517,8 @@ def main():
     ap.add_argument("--dense", action="store_true", help="AC: force the dense pivoted-LU kernel (no sparse program)")
     ap.add_argument("--points", type=int, default=None, help="AC: subsample to this many frequency points")
     ap.add_argument("--instances", type=int, default=None, help="TRAN: number of instances")
+    ap.add_argument("--device-waves", action="store_true",
+                    help="TRAN: evaluate the PULSE source on the device from its parameters instead of a pre-sampled row")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
