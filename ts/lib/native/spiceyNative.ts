@@ -23,12 +23,23 @@ const { symbols: C } = dlopen(LIB_PATH, {
     args: [p, p, p, f64, i64, p, p, p, p, p, p, p, p, u32],
     returns: i32,
   },
+  // (h, table, sweep, dt, steps, waves, vsrc, state0, v, ielem, state_out, iters, status, flags)
+  spicey_tran_solve_waves: {
+    args: [p, p, p, f64, i64, p, p, p, p, p, p, p, p, u32],
+    returns: i32,
+  },
 })
 
 export const ELEM = { R: 0, C: 1, L: 2, V: 3, S: 4, D: 5 } as const
 /** SPICEY_FLAG_SERIES_MAJOR: x is [Nvar][P], ielem [nAc][P] — one contiguous slab per series. */
 export const FLAG_SERIES_MAJOR = 64
 export const STATUS = { OK: 0, SINGULAR: 1, CDIV: 2, R_NONPOS: 3 } as const
+export const WAVE = { DC: 0, TABLE: 1, PULSE: 2, PWL: 3 } as const
+
+/** Sweep / Monte-Carlo batch: value slots varSlot[v] take varValues[v * nInst + inst]. */
+export type Sweep = { nInst: number; varSlot: Int32Array; varValues: Float64Array }
+/** Per-source waveform descriptors (spicey_waves): parameters are value slots of the table. */
+export type Waves = { kind: Int32Array; valueIdx: Int32Array; nPairs: Int32Array }
 
 /** Flat element table: typed arrays in the layout of `spicey_elem_table`. */
 export type ElemTable = {
@@ -63,6 +74,26 @@ function tableStruct(t: ElemTable) {
     dv.setBigUint64(16 + 8 * i, BigInt(a.length ? ptr(a) : 0), true),
   )
   return new Uint8Array(buf)
+}
+
+/** struct spicey_sweep: int64 n_inst, int32 n_var, int32 reserved, 2 pointers (32 bytes). */
+function sweepStruct(s: Sweep) {
+  const dv = new DataView(new ArrayBuffer(32))
+  dv.setBigInt64(0, BigInt(s.nInst), true)
+  dv.setInt32(8, s.varSlot.length, true)
+  dv.setBigUint64(16, BigInt(s.varSlot.length ? ptr(s.varSlot) : 0), true)
+  dv.setBigUint64(24, BigInt(s.varValues.length ? ptr(s.varValues) : 0), true)
+  return new Uint8Array(dv.buffer)
+}
+
+/** struct spicey_waves: int32 n_vsrc, int32 reserved, 3 pointers (32 bytes). */
+function wavesStruct(w: Waves) {
+  const dv = new DataView(new ArrayBuffer(32))
+  dv.setInt32(0, w.kind.length, true)
+  ;[w.kind, w.valueIdx, w.nPairs].forEach((a, i) =>
+    dv.setBigUint64(8 + 8 * i, BigInt(a.length ? ptr(a) : 0), true),
+  )
+  return new Uint8Array(dv.buffer)
 }
 
 let handle: Pointer | null = null
@@ -115,4 +146,40 @@ export function tranSolve(
     ),
   )
   return { v, ielem, stateOut, status }
+}
+
+/** AC batch: point p = inst * F + k; series-major slabs x[Nvar][P], ielem[nAc][P]. */
+export function acSolveBatch(t: ElemTable, freqs: Float64Array, sweep: Sweep) {
+  const nvar = t.nNodes + t.nVsrc
+  const P = freqs.length * sweep.nInst
+  const x = new Float64Array(P * nvar * 2)
+  const ielem = new Float64Array(P * t.nAcElem * 2)
+  const status = new Int32Array(P)
+  const ts = tableStruct(t), ss = sweepStruct(sweep)
+  check(
+    C.spicey_ac_solve(
+      getHandle(), ptr(ts), ptr(ss), ptr(freqs), BigInt(freqs.length), ptr(x),
+      t.nAcElem ? ptr(ielem) : null, ptr(status), FLAG_SERIES_MAJOR,
+    ),
+  )
+  return { x, ielem, status, nvar, nPoints: P }
+}
+
+/** TRAN batch with the sources evaluated on the device: v[steps+1][nn][nInst], ielem[steps+1][nElem][nInst]. */
+export function tranSolveBatch(
+  t: ElemTable, dt: number, steps: number, sweep: Sweep, waves: Waves, state0: Float64Array,
+) {
+  const S1 = steps + 1, n = sweep.nInst
+  const v = new Float64Array(S1 * t.nNodes * n)
+  const ielem = new Float64Array(S1 * t.type.length * n)
+  const status = new Int32Array(n)
+  const ts = tableStruct(t), ss = sweepStruct(sweep), ws = wavesStruct(waves)
+  check(
+    C.spicey_tran_solve_waves(
+      getHandle(), ptr(ts), ptr(ss), dt, BigInt(steps), ptr(ws), null,
+      state0.length ? ptr(state0) : null, ptr(v), t.type.length ? ptr(ielem) : null,
+      null, null, ptr(status), 0,
+    ),
+  )
+  return { v, ielem, status }
 }
