@@ -468,7 +468,8 @@ def run_native(args):
                 roof["traffic"] = json.load(open(tr)).get("dram_bytes_per_launch")
             except Exception:
                 pass
-        cpu_v, cores, sample = cpu_rate(wl, target_s=12.0)
+        # the CPU port is timed beside the GPU at N = 1 only (the contract's cpu_baseline); larger N reuse that line
+        cpu_v, cores, sample = cpu_rate(wl, target_s=12.0) if world == 1 else (None, None, "measured at N=1 only")
         if wl["kind"] == "tran":
             src_note = "PULSE evaluated on the device from its parameters" if getattr(args, "device_waves", False) \
                 else "pre-sampled row [nV][steps+1], one load per step"
