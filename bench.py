@@ -146,6 +146,41 @@ class ClockSampler:
                 "reasons": reasons, "samples": len(sm), "source": "nvidia-smi -lms 100"}
 
 
+def bind_to_gpu_numa(local):
+    """Multi-rank runs: pin this rank to the CPUs NVML names as local to its GPU, so that the pinned host buffers
+    of the e2e leg are allocated on the NUMA node the GPU's PCIe link hangs off (eight ranks left floating put
+    most buffers on one node and share its memory controller and the inter-socket link).  Returns a note."""
+    try:
+        import pynvml
+        import torch
+        pynvml.nvmlInit()
+        uuid = str(torch.cuda.get_device_properties(local).uuid)
+        h = None
+        for cand in ("GPU-" + uuid, uuid):
+            try:
+                h = pynvml.nvmlDeviceGetHandleByUUID(cand)
+                break
+            except Exception:
+                try:
+                    h = pynvml.nvmlDeviceGetHandleByUUID(cand.encode())
+                    break
+                except Exception:
+                    h = None
+        if h is None:
+            h = pynvml.nvmlDeviceGetHandleByIndex(local)
+        ncpu = os.cpu_count() or 1
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (ncpu + 63) // 64)
+        cpus = {64 * w + b for w, word in enumerate(words) for b in range(64) if (int(word) >> b) & 1}
+        allowed = os.sched_getaffinity(0)
+        pick = cpus & allowed
+        if not pick or pick == allowed:
+            return "no NUMA binding (affinity mask %d cpus, allowed %d)" % (len(cpus), len(allowed))
+        os.sched_setaffinity(0, pick)
+        return "rank bound to the %d CPUs local to its GPU" % len(pick)
+    except Exception as e:  # no NVML / no permission: run unbound
+        return "no NUMA binding (%s)" % type(e).__name__
+
+
 def dist_env():
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -296,6 +331,7 @@ def run_native(args):
     json_fd = os.dup(1)
     os.dup2(2, 1)
     torch.cuda.set_device(local)
+    numa_note = bind_to_gpu_numa(local) if world > 1 else "single rank: not bound"
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     dev = torch.device("cuda", local)
@@ -498,6 +534,7 @@ def run_native(args):
         }
         if wl["kind"] == "tran":
             line["config"]["sources"] = src_note
+        line["e2e"]["host_numa"] = numa_note
         sys.stdout.flush()
         os.write(json_fd, (json.dumps(line) + "\n").encode())
     os.close(json_fd)
