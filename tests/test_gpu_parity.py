@@ -488,6 +488,63 @@ def test_tran_pwl_parameter_sweep_with_switch(eng, golden, flags):
     assert np.max(np.abs(got["ielem"] - ref_i)) <= tol * np.max(np.abs(ref_i))
 
 
+def random_linear_tran_netlist(rng, n_nodes, n_elem):
+    """Random connected R / C / L network driven by one PULSE and one PWL source (parsed by the reference grammar)."""
+    nodes = ["n%d" % i for i in range(1, n_nodes + 1)]
+    lines = ["* random transient network", "V1 n1 0 PULSE(0 %g 1u 0.5u 0.7u 3u 9u)" % rng.uniform(1, 5)]
+    if n_nodes >= 2:
+        lines.append("V2 n2 0 PWL(0 0 2u %g 5u %g 11u 0 30u %g)" % (rng.uniform(0.5, 2), rng.uniform(-1, 1), rng.uniform(0.5, 2)))
+    for i in range(n_nodes):   # spanning chain of resistors, every node has a resistive path to a source
+        lines.append("r%d %s %s %g" % (i, nodes[i], nodes[i + 1] if i + 1 < n_nodes else "0", rng.uniform(100, 5e3)))
+    for k in range(n_elem):
+        a = rng.integers(0, n_nodes)
+        b = rng.integers(-1, n_nodes)
+        if a == b:
+            b = -1
+        kind = "rcl"[rng.integers(0, 3)]
+        val = {"r": rng.uniform(100, 1e4), "c": rng.uniform(1e-10, 1e-8), "l": rng.uniform(1e-5, 1e-3)}[kind]
+        lines.append("%s%d %s %s %g" % (kind, 100 + k, nodes[a], "0" if b < 0 else nodes[b], val))
+    lines.append(".tran 0.25u 40u")
+    return "\n".join(lines) + "\n"
+
+
+@pytest.mark.parametrize("n_nodes,n_elem", [(1, 2), (3, 5), (5, 9), (10, 20), (22, 50)])
+def test_tran_random_linear_networks_with_swept_sources(eng, n_nodes, n_elem):
+    """Random R / C / L networks with a PULSE and a PWL source whose parameters (and two resistors) differ per
+    instance: every transient tier the system size admits (register-resident, compiled, generic thread, CTA with
+    the matrix in shared memory / in the global scratch), device-evaluated sources, one oracle run per instance."""
+    import spicey_b200 as sp
+    rng = np.random.default_rng(500 + n_nodes)
+    text = random_linear_tran_netlist(rng, n_nodes, n_elem)
+    n = 12
+    ov = {"v1.pulse.v2": rng.uniform(1, 5, n), "v1.pulse.td": rng.uniform(0, 4e-6, n), "v1.pulse.period": rng.uniform(6e-6, 15e-6, n),
+          "r0": rng.uniform(100, 5e3, n)}
+    if n_nodes >= 2:
+        ov.update({"v2.pwl.t1": rng.uniform(1e-6, 4e-6, n), "v2.pwl.v2": rng.uniform(-1, 1, n), "r1": rng.uniform(100, 5e3, n)})
+
+    def mutate(ck, i):
+        p = ck.V[0].pulse
+        p.v2, p.td, p.period = (float(ov["v1.pulse." + k][i]) for k in ("v2", "td", "period"))
+        if n_nodes >= 2:
+            q = ck.V[1].pwl
+            q[1] = (float(ov["v2.pwl.t1"][i]), q[1][1])
+            q[2] = (q[2][0], float(ov["v2.pwl.v2"][i]))
+
+    ref_v, ref_i = _per_instance_oracle(text, n, mutate, {k: v for k, v in ov.items() if k.startswith("r")})
+    nvar = n_nodes + min(2, n_nodes)
+    seen = set()
+    for flags in (0, native.FLAG_JIT, native.FLAG_GENERIC_THREAD, native.FLAG_FORCE_CTA, native.FLAG_FORCE_GMEM, native.FLAG_STRICT):
+        got = sp.simulate_tran_batch(parse_netlist(text), n_inst=n, overrides=ov, engine=eng, flags=flags)
+        seen.add(eng.stats()["tier"])
+        assert got["status"].max() == 0
+        tol = 1e-11 if flags & native.FLAG_STRICT else TRAN_TOL
+        assert np.array_equal(got["v"][:, 0, :], ref_v[:, 0, :])            # node n1 is the PULSE source itself
+        assert np.max(np.abs(got["v"] - ref_v)) <= tol * np.max(np.abs(ref_v)), flags
+        assert np.max(np.abs(got["ielem"] - ref_i)) <= tol * np.max(np.abs(ref_i)), flags
+    assert native.TIER_CTA_SMEM in seen and native.TIER_CTA_GMEM in seen
+    assert (native.TIER_TRAN_JIT in seen) == (nvar <= 8) and (native.TIER_THREAD in seen) == (nvar <= 16)
+
+
 def test_tran_waves_argument_errors(eng):
     from spicey_b200 import packing
     ck = parse_netlist("* t\nV1 1 0 PULSE(0 5 0 1n 1n 5u 10u)\nR1 1 2 1k\nC1 2 0 1u\n.tran 0.1u 2u\n")
