@@ -63,6 +63,8 @@ struct CodegenOptions {
   int sync_every = 0;     // > 0: __syncthreads() every that many pivots / back-substitution rows (instruction-cache locality)
   int stagger_ns = 0;     // > 0: CTAs start in four phases this many ns apart, so that the SMs are not all storing at once
   int prefetch_steps = 8; // per-instance stamping: element values are loaded this many pivots / rows ahead of their use
+  bool fold_newton = false; // pivot reciprocal: fold the last Newton step into the product conj(a) * (1/|a|^2)
+  bool early_skip = false;  // |f| < EPS row skip decided from |b|^2 < EPS^2 |a|^2 instead of from the finished multiplier
 };
 
 struct CodegenStats {
@@ -111,6 +113,13 @@ __device__ __forceinline__ double rcp_nr(double a) {
   e = fma(-a, y, 1.0); y = fma(y, e, y);
   e = fma(-a, y, 1.0); y = fma(y, e, y);
   return y;
+}
+// The same up to the last step: y1 (one Newton step) and e1 = 1 - a*y1, so that 1/a = y1*(1 + e1) (+ e1^2 ~ 2^-80)
+__device__ __forceinline__ void rcp_nr1(double a, double& y1, double& e1) {
+  double y, e;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(a));
+  e = fma(-a, y, 1.0); y1 = fma(y, e, y);
+  e1 = fma(-a, y1, 1.0);
 }
 extern __shared__ double2 sm[];
 // Shared-memory column of this thread, addressed with immediate offsets.  Inline PTX on purpose: with plain
@@ -497,10 +506,21 @@ inline std::string generate_sparse_kernel_source(const CodegenInput& in, const C
         s += "    m = " + nrm(opnd(op.reads[c])) + "; ok = ok && " + (c < op.pidx ? "(m < mp)" : "!(m > mp)") + ";\n";
       }
       s += "    ok = ok && (mp >= EPS);   // singular / Complex.div guard (or NaN): the dense kernel reports which\n";
-      s += "    inv = rcp_nr(mp);\n";
+      // r = conj(a) / |a|^2.  The dependent chain pivot -> reciprocal -> multiplier -> next pivot bounds the kernel
+      // (1.5 warps per scheduler), so the last Newton step is folded into the product: with y1 the reciprocal after
+      // one step and e1 = 1 - mp*y1, conj(a)*y1*(1 + e1) is conj(a)/mp to the same <= 2 ulp as (y1 + y1*e1)*conj(a),
+      // one FP64 latency shorter.  thm: the reference's |f| < EPS row skip (solveComplex.ts:46) as |b|^2 < EPS^2 * |a|^2
+      // (|f|^2 = |b|^2 / |a|^2), known as soon as mp is, instead of from the finished multiplier.
       const std::string v = "v" + std::to_string(op.def);
-      s += "    const double2 " + v + " = D2(" + (ap.re0 ? std::string("0.0") : ap.re + " * inv") + ", " +
-           (ap.im0 ? std::string("0.0") : "-" + ap.im + " * inv") + ");\n";
+      if (opt.fold_newton) {
+        s += "    rcp_nr1(mp, inv, m);\n";
+        s += "    const double2 " + v + " = D2(" + (ap.re0 ? std::string("0.0") : "fma(" + ap.re + " * inv, m, " + ap.re + " * inv)") + ", " +
+             (ap.im0 ? std::string("0.0") : "fma(-" + ap.im + " * inv, m, -" + ap.im + " * inv)") + ");\n";
+      } else {
+        s += "    inv = rcp_nr(mp);\n";
+        s += "    const double2 " + v + " = D2(" + (ap.re0 ? std::string("0.0") : ap.re + " * inv") + ", " +
+             (ap.im0 ? std::string("0.0") : "-" + ap.im + " * inv") + ");\n";
+      }
       s += "    r = " + v + ";\n";
       if (slot_of[op.def] >= 0) s += "    SMST(" + soff(slot_of[op.def]) + ", " + v + ");\n";
     } else if (op.kind == SOP_ELIM) {
@@ -509,7 +529,8 @@ inline std::string generate_sparse_kernel_source(const CodegenInput& in, const C
       cmul(opnd(op.reads[0]), rr, re, im);
       // solveComplex.ts:46 skips the row when |f| < EPS: a zero multiplier leaves every updated value as it was
       // (strongly attenuating circuits do produce such multipliers at the far end of a sweep)
-      s += "    fm = D2(" + re + ", " + im + "); if (fma(fm.x, fm.x, fm.y * fm.y) < THR) fm = D2(0.0, 0.0);\n";
+      if (opt.early_skip) s += "    fm = D2(" + re + ", " + im + "); if (" + nrm(opnd(op.reads[0])) + " < THR * mp) fm = D2(0.0, 0.0);\n";
+      else s += "    fm = D2(" + re + ", " + im + "); if (fma(fm.x, fm.x, fm.y * fm.y) < THR) fm = D2(0.0, 0.0);\n";
       for (const Update& u : op.upd) {
         const Opnd a = opnd(u.dst_old), pq = opnd(u.src);
         const std::string v = "v" + std::to_string(u.dst_new);

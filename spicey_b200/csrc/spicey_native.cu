@@ -388,6 +388,17 @@ void jit_source(const SparseProgram& sp, const HostPlan& hp, const CodegenOption
 
 // Compiles (once per topology, handle and variant) the straight-line kernel of the cached sparse program.
 // Returns the usable variant or nullptr.
+// Dependent-chain options of the compiled sparse kernel (sparse_codegen.h); SPICEY_JIT_CHAIN=<bits> overrides
+// (bit 0: fold the last Newton step of the pivot reciprocal into the product, bit 1: early row-skip test).
+constexpr int kJitChainDefault = 0;
+void chain_options(CodegenOptions& opt) {
+  int bits = kJitChainDefault;
+  if (const char* e = getenv("SPICEY_JIT_CHAIN")) bits = atoi(e);
+  opt.fold_newton = bits & 1;
+  opt.early_skip = bits & 2;
+}
+
+// Returns the usable variant or nullptr.
 DeviceCtx::JitVariant* ensure_jit(DeviceCtx& ctx, const HostPlan& hp, bool with_ielem) {
   DeviceCtx::JitVariant& jv = ctx.sp_jit[with_ielem ? 1 : 0];
   // the per-instance (eager) kernel also depends on WHICH value slots are swept
@@ -410,6 +421,7 @@ DeviceCtx::JitVariant* ensure_jit(DeviceCtx& ctx, const HostPlan& hp, bool with_
   opt.block = ctx.sp_eager ? ctx.sp_jit_block_eager : ctx.sp_jit_block; opt.min_blocks = ctx.sp_jit_minb; opt.with_ielem = with_ielem;
   opt.prefetch_steps = ctx.sp_jit_prefetch; opt.stagger_ns = ctx.sp_jit_stagger;
   opt.sync_every = ctx.sp_jit_sync;
+  chain_options(opt);
   opt.smem_slots = std::min<int>(ctx.sp_eager ? ctx.sp_jit_slots_eager : ctx.sp_jit_slots,
                                  (int)((size_t)(227 * 1024 / opt.min_blocks - 1024) / ((size_t)opt.block * 16)));
   std::string src;
@@ -1338,6 +1350,7 @@ int64_t spicey_debug_sparse_source(const spicey_elem_table* table, const spicey_
   CodegenOptions opt;
   opt.block = block; opt.min_blocks = min_blocks; opt.smem_slots = smem_slots; opt.with_ielem = (with_ielem & 1) != 0;
   opt.sync_every = (with_ielem >> 16) & 0xff;
+  chain_options(opt);
   std::string src;
   CodegenStats st;
   jit_source(sp, hp, opt, eager, src, st);

@@ -32,8 +32,8 @@ def main():
     stream = torch.cuda.current_stream()
     sub = np.arange(0, P, 4999)
     eng0 = native.Engine([0])
-    r0 = eng0.ac_solve(table, freqs[sub], flags=native.FLAG_STRICT)
-    ref = (r0["x"].reshape(len(sub), -1), r0["ielem"].reshape(len(sub), -1))
+    x0, i0, _ = eng0.ac_solve(table, freqs[sub], flags=native.FLAG_STRICT)
+    ref = (x0.reshape(len(sub), -1), i0.reshape(len(sub), -1))
     eng0.close()
     for cfg in sys.argv[1:]:
         os.environ["SPICEY_JIT_CFG"] = cfg
@@ -41,7 +41,7 @@ def main():
         flags = native.FLAG_SERIES_MAJOR | native.FLAG_JIT
 
         def step():
-            eng.ac_solve_device(table, d_f.data_ptr(), P, d_x.data_ptr(), d_i.data_ptr(), d_s.data_ptr(), flags=flags,
+            eng.ac_solve_device(table, d_f.data_ptr(), P, d_x.data_ptr(), None if os.environ.get("JIT_SWEEP_NO_IELEM") else d_i.data_ptr(), d_s.data_ptr(), flags=flags,
                                 stream=stream.cuda_stream, series_ld=ld)
         d_x.zero_(); d_i.zero_()
         for _ in range(3):
