@@ -76,7 +76,7 @@ struct DeviceCtx {
     uint64_t key = 0;   // plan key the module was compiled for (0 = none)
     bool failed = false;
     size_t smem_bytes = 0;
-    int block = 0;
+    int block = 0, min_blocks = 1;
   } sp_jit[2];
   // Launch shape of the compiled kernel, measured on cfg2 (tools/jit_sweep.py): one CTA of 6 warps per SM with
   // 255 registers per thread and 75 shared-memory slots per thread for the factor values (0.76 ms per 1e6
@@ -84,9 +84,15 @@ struct DeviceCtx {
   // 4 pivots keeps the warps of a CTA on the same instruction-cache lines (-8 %).  Tried and removed: a bulk-copy
   // (TMA) epilogue (one cp.async.bulk issue costs its warp ~90 cycles, tools/micro/bulk_store.cu: 2.3 ms) and
   // reserving a stored value's registers with an empty asm while the store drains (no gain).  Overridable for experiments: SPICEY_JIT_CFG=block,minb,slots[,sync,prefetch].
-  int sp_jit_block = 192, sp_jit_minb = 1, sp_jit_slots = 75, sp_jit_sync = 4;
-  // per-instance (eager) stamping keeps element values in flight: fewer threads, more shared memory each
-  int sp_jit_stagger = 4000;   // ns between the four start phases of the CTAs (0.682 -> 0.669 ms on cfg 2)
+  // Since then: the back-substitution issues all 3,080 B of a point's results and is bound by the SM's store port
+  // (32 B/clk, tools/micro/write_bw.cu) while the elimination stores nothing, so the shape is now TWO CTAs of 3 warps
+  // per SM started half an iteration apart (CTA i and i + grid/2 share an SM): one eliminates while the other stores.
+  // 1 x 192 in phase: 0.67 ms; 2 x 96 in phase: 0.67; 2 x 96 half an iteration apart: 0.61 - 0.64 ms.
+  int sp_jit_block = 96, sp_jit_minb = 2, sp_jit_slots = 75, sp_jit_sync = 4;
+  int sp_jit_stagger = 0;           // ns between four start phases of the CTAs (helped the 1 x 192 shape by 2 %)
+  double sp_jit_antiphase_ns_per_op = 10.4;   // start delay of the second wave: half an iteration, ~20.8 ns per micro-op
+  // per-instance (eager) stamping keeps element values in flight: fewer threads, more shared memory each, one CTA per SM
+  int sp_jit_minb_eager = 1, sp_jit_stagger_eager = 4000;
   int sp_jit_block_eager = 128, sp_jit_slots_eager = 113, sp_jit_prefetch = 8;   // cfg2mc: 1.52 ms (prefetch 4: 1.60, 2: 1.71)
   double sp_jit_compile_ms = 0;
   uint64_t sp_jit_fit_key = 0;   // sparse program the fit check below was made for
@@ -389,13 +395,18 @@ void jit_source(const SparseProgram& sp, const HostPlan& hp, const CodegenOption
 // Compiles (once per topology, handle and variant) the straight-line kernel of the cached sparse program.
 // Returns the usable variant or nullptr.
 // Dependent-chain options of the compiled sparse kernel (sparse_codegen.h); SPICEY_JIT_CHAIN=<bits> overrides
-// (bit 0: fold the last Newton step of the pivot reciprocal into the product, bit 1: early row-skip test).
+// (bit 0: fold the last Newton step of the pivot reciprocal into the product, bit 1: early row-skip test,
+// bits 2-3: cache hint of the result stores, 1 = .cs, 2 = .wt, bit 4: two phase-locked warp groups per CTA).
 constexpr int kJitChainDefault = 0;
 void chain_options(CodegenOptions& opt) {
   int bits = kJitChainDefault;
   if (const char* e = getenv("SPICEY_JIT_CHAIN")) bits = atoi(e);
   opt.fold_newton = bits & 1;
   opt.early_skip = bits & 2;
+  opt.store_hint = (bits >> 2) & 3;
+  opt.two_groups = bits & 16;
+  if (const char* e = getenv("SPICEY_JIT_ANTIPHASE")) opt.antiphase_ns = atoi(e);
+  if (const char* e = getenv("SPICEY_JIT_ANTIPHASE_MODE")) opt.antiphase_mode = atoi(e);
 }
 
 // Returns the usable variant or nullptr.
@@ -412,15 +423,18 @@ DeviceCtx::JitVariant* ensure_jit(DeviceCtx& ctx, const HostPlan& hp, bool with_
   if (const char* e = getenv("SPICEY_JIT_CFG")) {
     int b = 0, m = 0, sl = 0, sy = ctx.sp_jit_sync, pf = ctx.sp_jit_prefetch, sg = ctx.sp_jit_stagger;
     if (sscanf(e, "%d,%d,%d,%d,%d,%d", &b, &m, &sl, &sy, &pf, &sg) >= 3 && b >= 32 && b <= 1024 && b % 32 == 0 && m >= 1 && sl >= 0) {
-      ctx.sp_jit_stagger = sg;
-      ctx.sp_jit_block = ctx.sp_jit_block_eager = b; ctx.sp_jit_minb = m; ctx.sp_jit_slots = ctx.sp_jit_slots_eager = sl;
+      ctx.sp_jit_stagger = ctx.sp_jit_stagger_eager = sg;
+      ctx.sp_jit_block = ctx.sp_jit_block_eager = b; ctx.sp_jit_minb = ctx.sp_jit_minb_eager = m; ctx.sp_jit_slots = ctx.sp_jit_slots_eager = sl;
       ctx.sp_jit_sync = sy; ctx.sp_jit_prefetch = pf;
     }
   }
   CodegenOptions opt;
-  opt.block = ctx.sp_eager ? ctx.sp_jit_block_eager : ctx.sp_jit_block; opt.min_blocks = ctx.sp_jit_minb; opt.with_ielem = with_ielem;
-  opt.prefetch_steps = ctx.sp_jit_prefetch; opt.stagger_ns = ctx.sp_jit_stagger;
+  opt.block = ctx.sp_eager ? ctx.sp_jit_block_eager : ctx.sp_jit_block; opt.with_ielem = with_ielem;
+  opt.min_blocks = ctx.sp_eager ? ctx.sp_jit_minb_eager : ctx.sp_jit_minb;
+  opt.prefetch_steps = ctx.sp_jit_prefetch; opt.stagger_ns = ctx.sp_eager ? ctx.sp_jit_stagger_eager : ctx.sp_jit_stagger;
   opt.sync_every = ctx.sp_jit_sync;
+  if (!ctx.sp_eager && opt.min_blocks >= 2)
+    opt.antiphase_ns = (int)std::min(200000.0, ctx.sp_jit_antiphase_ns_per_op * (double)ctx.sp.code.size() * 2.0 / opt.min_blocks);
   chain_options(opt);
   opt.smem_slots = std::min<int>(ctx.sp_eager ? ctx.sp_jit_slots_eager : ctx.sp_jit_slots,
                                  (int)((size_t)(227 * 1024 / opt.min_blocks - 1024) / ((size_t)opt.block * 16)));
@@ -438,6 +452,7 @@ DeviceCtx::JitVariant* ensure_jit(DeviceCtx& ctx, const HostPlan& hp, bool with_
   }
   jv.smem_bytes = st.smem_bytes;
   jv.block = opt.block;
+  jv.min_blocks = opt.min_blocks;
   jv.failed = false;
   ctx.sp_jit_compile_ms = now_ms() - t0;
   ctx.sp_jit_note = "ok";
@@ -537,8 +552,9 @@ int launch_ac_sparse(DeviceCtx& ctx, const HostPlan& hp, const DevPlan& dp, cons
     j.fb_list = fb_list; j.fb_count = fb_count; j.n = hp.nvar; j.n_ac_elem = hp.n_ac_elem;
     j.var_values = dp.var_values; j.n_inst = dp.n_inst; j.n_freq = args.n_freq; j.p_begin = args.p_begin;
     const int jblock = jv->block;
-    const long long resident = (long long)ctx.sm_count * ctx.sp_jit_minb;
-    const unsigned jgrid = (unsigned)std::min<long long>((args.p_count + jblock - 1) / jblock, resident);
+    const long long resident = (long long)ctx.sm_count * jv->min_blocks;
+    unsigned jgrid = (unsigned)std::min<long long>((args.p_count + jblock - 1) / jblock, resident);
+    if (const char* e = getenv("SPICEY_JIT_GRID")) jgrid = std::min<unsigned>(jgrid, (unsigned)std::max(1, atoi(e)));   // experiments: fewer SMs
     void* kargs[] = {&j};
     CUDA_TRY(cudaLaunchKernel((const void*)jv->kernel, dim3(jgrid), dim3(jblock), kargs, jv->smem_bytes, stream));
     if (launches) ++*launches;

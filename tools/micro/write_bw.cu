@@ -47,7 +47,8 @@ int main(int argc, char** argv) {
   constexpr int NS = 192;
   const size_t n = (size_t)P * NS;
   double2* buf;
-  cudaMalloc(&buf, n * sizeof(double2));
+  if (cudaMalloc(&buf, n * sizeof(double2)) != cudaSuccess) { printf("cudaMalloc failed\n"); return 1; }
+  setvbuf(stdout, nullptr, _IOLBF, 0);
   const double gb = n * 16.0 / 1e9;
   for (int blocks : {148, 296}) {
     for (int threads : {96, 128, 160, 192, 224, 256, 512}) {
@@ -56,6 +57,20 @@ int main(int argc, char** argv) {
       double t3 = time_ms([&] { fill_point_major<NS><<<blocks, threads>>>(buf, P); });
       printf("grid %5d x %4d : linear %.3f ms %.0f GB/s | series-major %.3f ms %.0f GB/s | point-major %.3f ms %.0f GB/s\n", blocks, threads, t1,
              gb / t1 * 1e3, t2, gb / t2 * 1e3, t3, gb / t3 * 1e3);
+    }
+  }
+  // Store rate of ONE SM for the series-major pattern (few CTAs, one per SM): what an SM whose warps are all in
+  // their store phase can push, against its 1/148 share of the HBM rate.
+  int clk_khz = 0;
+  cudaDeviceGetAttribute(&clk_khz, cudaDevAttrClockRate, 0);
+  for (int blocks : {1, 4, 16, 37, 74}) {
+    for (int threads : {32, 96, 192, 384}) {
+      long long Ps = (long long)blocks * threads * 256;
+      if (Ps > P) Ps = P / ((long long)blocks * threads) * blocks * threads;   // stay inside the buffer
+      const double gbs = (double)Ps * NS * 16.0 / 1e9;
+      double t = time_ms([&] { fill_series<NS><<<blocks, threads>>>(buf, Ps); });
+      printf("per-SM: grid %3d x %3d : %.3f ms, %.1f GB/s per SM = %.1f B/clk at %.0f MHz\n", blocks, threads, t, gbs / t * 1e3 / blocks,
+             gbs / t * 1e3 / blocks * 1e9 / (clk_khz * 1e3), clk_khz / 1e3);
     }
   }
   double t4 = time_ms([&] { cudaMemsetAsync(buf, 0, n * 16); });
