@@ -63,13 +63,7 @@ struct CodegenOptions {
   int sync_every = 0;     // > 0: __syncthreads() every that many pivots / back-substitution rows (instruction-cache locality)
   int stagger_ns = 0;     // > 0: CTAs start in four phases this many ns apart, so that the SMs are not all storing at once
   int prefetch_steps = 8; // per-instance stamping: element values are loaded this many pivots / rows ahead of their use
-  bool fold_newton = false; // pivot reciprocal: fold the last Newton step into the product conj(a) * (1/|a|^2)
-  bool two_groups = false;  // the CTA's warps form two groups that run half an iteration apart, phase-locked by a
-                            // CTA barrier at every phase change: one group eliminates while the other stores
-  int antiphase_mode = 0;   // 0: CTA i pairs with i + grid/min_blocks, 1: with its neighbour
   int antiphase_ns = 0;     // min_blocks >= 2: start delay of the k-th wave of CTAs (k * antiphase_ns)
-  int store_hint = 0;       // result stores: 0 plain, 1 st.global.cs (streaming), 2 st.global.wt
-  bool early_skip = false;  // |f| < EPS row skip decided from |b|^2 < EPS^2 |a|^2 instead of from the finished multiplier
 };
 
 struct CodegenStats {
@@ -118,13 +112,6 @@ __device__ __forceinline__ double rcp_nr(double a) {
   e = fma(-a, y, 1.0); y = fma(y, e, y);
   e = fma(-a, y, 1.0); y = fma(y, e, y);
   return y;
-}
-// The same up to the last step: y1 (one Newton step) and e1 = 1 - a*y1, so that 1/a = y1*(1 + e1) (+ e1^2 ~ 2^-80)
-__device__ __forceinline__ void rcp_nr1(double a, double& y1, double& e1) {
-  double y, e;
-  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(a));
-  e = fma(-a, y, 1.0); y1 = fma(y, e, y);
-  e1 = fma(-a, y1, 1.0);
 }
 extern __shared__ double2 sm[];
 // Shared-memory column of this thread, addressed with immediate offsets.  Inline PTX on purpose: with plain
@@ -369,32 +356,19 @@ inline std::string generate_sparse_kernel_source(const CodegenInput& in, const C
   if (opt.stagger_ns > 0)
     s += "  { const unsigned phs = blockIdx.x & 3u; if (phs && a.p_count > 16ll * gridDim.x * BLOCK) __nanosleep(phs * " +
          std::to_string(opt.stagger_ns) + "u); }\n";
-  // Several CTAs per SM: the second wave of the grid (the CTAs that share an SM with the first wave) starts half an
-  // iteration late, so that on every SM one CTA eliminates (no stores) while the other back-substitutes (all the
-  // stores): the SM's store port, which bounds the back-substitution, is then busy all the time.
+  // Several CTAs per SM: the back-substitution issues every result store of a point and is bound by the SM's store
+  // port (32 B/clk measured, tools/micro/write_bw.cu) while the elimination stores nothing, so with all warps of an SM in
+  // the same phase the port idles for the first 40 % of an iteration and throttles the rest.  The second wave of the
+  // grid — CTA i + grid/min_blocks shares an SM with CTA i on B200 (measured: delaying the odd CTAs instead changes
+  // nothing) — starts half an iteration late, so that one CTA eliminates while the other stores.
   if (opt.antiphase_ns > 0 && opt.min_blocks >= 2) {
     const std::string mb = std::to_string(opt.min_blocks) + "u";
-    // which CTAs share an SM is the block scheduler's choice: mode 0 assumes waves (i, i + grid/2), mode 1 neighbours
-    // (2k, 2k + 1); measured on B200, see DESIGN.md
-    const std::string wave = opt.antiphase_mode == 0 ? "(blockIdx.x / (gridDim.x / " + mb + "))" : "(blockIdx.x % " + mb + ")";
-    s += "  if (a.p_count > 4ll * gridDim.x * BLOCK) { const unsigned wv = " + wave + "; if (wv) __nanosleep(wv * " +
+    s += "  if (a.p_count > 4ll * gridDim.x * BLOCK) { const unsigned wv = blockIdx.x / (gridDim.x / " + mb + "); if (wv) __nanosleep(wv * " +
          std::to_string(opt.antiphase_ns) + "u); }\n";
   }
   s += "  const unsigned ld = a.series_ld ? (unsigned)a.series_ld : 1u;\n";
   s += "  const unsigned sbase = (unsigned)__cvta_generic_to_shared(sm) + threadIdx.x * 16u;\n";
   s += "  const long long stride = (long long)gridDim.x * BLOCK, plast = a.p_count - 1;\n";
-  // Two warp groups, half an iteration apart.  The back-substitution issues every result store of a point and is
-  // bound by the SM's store port (32 B/clk measured, tools/micro/write_bw.cu), the elimination stores nothing: with
-  // all warps in the same phase the port idles for the first 40 % of an iteration and throttles the rest.  Group 1
-  // skips one phase at the start, and a CTA barrier at every phase change keeps the groups locked in opposite phases;
-  // inside a phase the instruction-cache barrier is per group (named barriers 1 and 2).
-  const bool groups = opt.two_groups && opt.block % 64 == 0;
-  const std::string half = std::to_string(opt.block / 2);
-  // the group is re-derived from %tid.x at every barrier (literal barrier ids, no register held across the kernel)
-  const std::string gsync = groups ? "    asm volatile(\"{ .reg .pred p; .reg .u32 t; mov.u32 t, %tid.x; setp.lt.u32 p, t, " + half + "; @p bar.sync 1, " + half +
-                                         "; @!p bar.sync 2, " + half + "; }\" ::: \"memory\");\n"
-                                   : std::string("    __syncthreads();\n");
-  if (groups) s += "  if (threadIdx.x >= " + half + "u) __syncthreads();\n";
   if (!in.eager) s += "  double fnext = a.freqs[min((long long)blockIdx.x * BLOCK + threadIdx.x, plast)];\n";
   // block-uniform trip count: lanes past the end solve the last point again and store nothing
   s += "  for (long long base = (long long)blockIdx.x * BLOCK; base < a.p_count; base += stride) {\n";
@@ -455,11 +429,7 @@ inline std::string generate_sparse_kernel_source(const CodegenInput& in, const C
   std::vector<Out> pending;
   auto flush_outputs = [&]() {
     for (const Out& o : pending)
-      if (opt.store_hint == 0)
-        s += std::string("    if (valid) *(double2*)(") + (o.cur ? "ib" : "xb") + " + " + off(o.k) + ") = D2(" + o.re + ", " + o.im + ");\n";
-      else
-        s += std::string("    if (valid) ") + (opt.store_hint == 1 ? "__stcs" : "__stwt") + "((double2*)(" + (o.cur ? "ib" : "xb") + " + " + off(o.k) +
-             "), D2(" + o.re + ", " + o.im + "));\n";
+      s += std::string("    if (valid) *(double2*)(") + (o.cur ? "ib" : "xb") + " + " + off(o.k) + ") = D2(" + o.re + ", " + o.im + ");\n";
     pending.clear();
   };
 
@@ -521,7 +491,6 @@ inline std::string generate_sparse_kernel_source(const CodegenInput& in, const C
     const IrOp& op = ir[t];
     if (t == B) phase = 'b';
     if (op.kind == SOP_PIVOT || op.kind == SOP_BSUB) prefetch_from(t);
-    if (t == B && groups) s += "    __syncthreads();   // phase change: this group starts storing, the other one eliminating\n";
     if (t == B) {
       // Every pivot has been verified.  A system whose pivot order differs from the pilot's, or that trips a
       // guard of the reference (singular, Complex.div, inductor), goes to the dense kernel, which also
@@ -530,7 +499,7 @@ inline std::string generate_sparse_kernel_source(const CodegenInput& in, const C
       s += "      if (valid) { a.status[p] = fb ? -1 : 0; if (fb) a.fb_list[atomicAdd(a.fb_count, 1)] = p; } }\n";
     }
     if (op.kind == SOP_PIVOT) {
-      if (opt.sync_every > 0 && n_piv % opt.sync_every == 0) s += gsync;
+      if (opt.sync_every > 0 && n_piv % opt.sync_every == 0) s += "    __syncthreads();\n";
       ++n_piv;
       const Opnd ap = opnd(op.reads[op.pidx]);
       s += "    mp = " + nrm(ap) + ";\n";
@@ -539,21 +508,10 @@ inline std::string generate_sparse_kernel_source(const CodegenInput& in, const C
         s += "    m = " + nrm(opnd(op.reads[c])) + "; ok = ok && " + (c < op.pidx ? "(m < mp)" : "!(m > mp)") + ";\n";
       }
       s += "    ok = ok && (mp >= EPS);   // singular / Complex.div guard (or NaN): the dense kernel reports which\n";
-      // r = conj(a) / |a|^2.  The dependent chain pivot -> reciprocal -> multiplier -> next pivot bounds the kernel
-      // (1.5 warps per scheduler), so the last Newton step is folded into the product: with y1 the reciprocal after
-      // one step and e1 = 1 - mp*y1, conj(a)*y1*(1 + e1) is conj(a)/mp to the same <= 2 ulp as (y1 + y1*e1)*conj(a),
-      // one FP64 latency shorter.  thm: the reference's |f| < EPS row skip (solveComplex.ts:46) as |b|^2 < EPS^2 * |a|^2
-      // (|f|^2 = |b|^2 / |a|^2), known as soon as mp is, instead of from the finished multiplier.
+      s += "    inv = rcp_nr(mp);\n";
       const std::string v = "v" + std::to_string(op.def);
-      if (opt.fold_newton) {
-        s += "    rcp_nr1(mp, inv, m);\n";
-        s += "    const double2 " + v + " = D2(" + (ap.re0 ? std::string("0.0") : "fma(" + ap.re + " * inv, m, " + ap.re + " * inv)") + ", " +
-             (ap.im0 ? std::string("0.0") : "fma(-" + ap.im + " * inv, m, -" + ap.im + " * inv)") + ");\n";
-      } else {
-        s += "    inv = rcp_nr(mp);\n";
-        s += "    const double2 " + v + " = D2(" + (ap.re0 ? std::string("0.0") : ap.re + " * inv") + ", " +
-             (ap.im0 ? std::string("0.0") : "-" + ap.im + " * inv") + ");\n";
-      }
+      s += "    const double2 " + v + " = D2(" + (ap.re0 ? std::string("0.0") : ap.re + " * inv") + ", " +
+           (ap.im0 ? std::string("0.0") : "-" + ap.im + " * inv") + ");\n";
       s += "    r = " + v + ";\n";
       if (slot_of[op.def] >= 0) s += "    SMST(" + soff(slot_of[op.def]) + ", " + v + ");\n";
     } else if (op.kind == SOP_ELIM) {
@@ -562,8 +520,7 @@ inline std::string generate_sparse_kernel_source(const CodegenInput& in, const C
       cmul(opnd(op.reads[0]), rr, re, im);
       // solveComplex.ts:46 skips the row when |f| < EPS: a zero multiplier leaves every updated value as it was
       // (strongly attenuating circuits do produce such multipliers at the far end of a sweep)
-      if (opt.early_skip) s += "    fm = D2(" + re + ", " + im + "); if (" + nrm(opnd(op.reads[0])) + " < THR * mp) fm = D2(0.0, 0.0);\n";
-      else s += "    fm = D2(" + re + ", " + im + "); if (fma(fm.x, fm.x, fm.y * fm.y) < THR) fm = D2(0.0, 0.0);\n";
+      s += "    fm = D2(" + re + ", " + im + "); if (fma(fm.x, fm.x, fm.y * fm.y) < THR) fm = D2(0.0, 0.0);\n";
       for (const Update& u : op.upd) {
         const Opnd a = opnd(u.dst_old), pq = opnd(u.src);
         const std::string v = "v" + std::to_string(u.dst_new);
@@ -572,7 +529,7 @@ inline std::string generate_sparse_kernel_source(const CodegenInput& in, const C
         if (slot_of[u.dst_new] >= 0) s += "    SMST(" + soff(slot_of[u.dst_new]) + ", " + v + ");\n";
       }
     } else {
-      if (opt.sync_every > 0 && n_bs % opt.sync_every == 0) s += gsync;
+      if (opt.sync_every > 0 && n_bs % opt.sync_every == 0) s += "    __syncthreads();\n";
       ++n_bs;
       // x_i = (b_i - sum u_ij x_j) * (1/u_ii); the most recently produced x_j is applied last
       std::vector<std::pair<int, int>> terms;  // (def time of x_j, index into reads)
@@ -612,9 +569,7 @@ inline std::string generate_sparse_kernel_source(const CodegenInput& in, const C
     }
     if (t >= B) { emit_currents(t); flush_outputs(); }
   }
-  if (groups) s += "    __syncthreads();   // phase change\n";
   s += "  }\n";
-  if (groups) s += "  if (threadIdx.x < " + half + "u) __syncthreads();   // group 1 is one phase behind\n";
   s += "}\n";
   {
     std::string head = sparse_jit_prelude();

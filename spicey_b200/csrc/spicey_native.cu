@@ -394,21 +394,6 @@ void jit_source(const SparseProgram& sp, const HostPlan& hp, const CodegenOption
 
 // Compiles (once per topology, handle and variant) the straight-line kernel of the cached sparse program.
 // Returns the usable variant or nullptr.
-// Dependent-chain options of the compiled sparse kernel (sparse_codegen.h); SPICEY_JIT_CHAIN=<bits> overrides
-// (bit 0: fold the last Newton step of the pivot reciprocal into the product, bit 1: early row-skip test,
-// bits 2-3: cache hint of the result stores, 1 = .cs, 2 = .wt, bit 4: two phase-locked warp groups per CTA).
-constexpr int kJitChainDefault = 0;
-void chain_options(CodegenOptions& opt) {
-  int bits = kJitChainDefault;
-  if (const char* e = getenv("SPICEY_JIT_CHAIN")) bits = atoi(e);
-  opt.fold_newton = bits & 1;
-  opt.early_skip = bits & 2;
-  opt.store_hint = (bits >> 2) & 3;
-  opt.two_groups = bits & 16;
-  if (const char* e = getenv("SPICEY_JIT_ANTIPHASE")) opt.antiphase_ns = atoi(e);
-  if (const char* e = getenv("SPICEY_JIT_ANTIPHASE_MODE")) opt.antiphase_mode = atoi(e);
-}
-
 // Returns the usable variant or nullptr.
 DeviceCtx::JitVariant* ensure_jit(DeviceCtx& ctx, const HostPlan& hp, bool with_ielem) {
   DeviceCtx::JitVariant& jv = ctx.sp_jit[with_ielem ? 1 : 0];
@@ -435,7 +420,7 @@ DeviceCtx::JitVariant* ensure_jit(DeviceCtx& ctx, const HostPlan& hp, bool with_
   opt.sync_every = ctx.sp_jit_sync;
   if (!ctx.sp_eager && opt.min_blocks >= 2)
     opt.antiphase_ns = (int)std::min(200000.0, ctx.sp_jit_antiphase_ns_per_op * (double)ctx.sp.code.size() * 2.0 / opt.min_blocks);
-  chain_options(opt);
+  if (const char* e = getenv("SPICEY_JIT_ANTIPHASE")) opt.antiphase_ns = atoi(e);   // experiments
   opt.smem_slots = std::min<int>(ctx.sp_eager ? ctx.sp_jit_slots_eager : ctx.sp_jit_slots,
                                  (int)((size_t)(227 * 1024 / opt.min_blocks - 1024) / ((size_t)opt.block * 16)));
   std::string src;
@@ -1366,7 +1351,6 @@ int64_t spicey_debug_sparse_source(const spicey_elem_table* table, const spicey_
   CodegenOptions opt;
   opt.block = block; opt.min_blocks = min_blocks; opt.smem_slots = smem_slots; opt.with_ielem = (with_ielem & 1) != 0;
   opt.sync_every = (with_ielem >> 16) & 0xff;
-  chain_options(opt);
   std::string src;
   CodegenStats st;
   jit_source(sp, hp, opt, eager, src, st);
