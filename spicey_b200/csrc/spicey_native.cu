@@ -1351,6 +1351,7 @@ int64_t spicey_debug_sparse_source(const spicey_elem_table* table, const spicey_
   CodegenOptions opt;
   opt.block = block; opt.min_blocks = min_blocks; opt.smem_slots = smem_slots; opt.with_ielem = (with_ielem & 1) != 0;
   opt.sync_every = (with_ielem >> 16) & 0xff;
+  if (const char* e = getenv("SPICEY_JIT_ANTIPHASE")) opt.antiphase_ns = atoi(e);
   std::string src;
   CodegenStats st;
   jit_source(sp, hp, opt, eager, src, st);
