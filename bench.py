@@ -214,12 +214,16 @@ def load_workload(name, points=None, instances=None, device_waves=False):
         text = {"cfg2": W.rc_ladder(64), "cfg4": W.rc_mesh(16), "cfg1": W.README_RC}[name]
         ck = parse_netlist(text)
         freqs = np.array(sp.analysis.ac_frequencies(ck), dtype=np.float64)
+        if name == "cfg4" and not points:
+            # the full 8,000,001-point sweep is 127 GB of results (it is the 8-GPU configuration: 1e6 points per GPU);
+            # the default bench line is a 400,000-point slice per GPU, every 20th frequency of the same sweep
+            points = 400000
         if points:
             freqs = freqs[:: max(1, freqs.shape[0] // points)][:points]
         table = pack_circuit(ck)
         wl.update(kind="ac", ckt=ck, table=table, freqs=freqs, units=int(freqs.shape[0]), sweep=None,
                   label={"cfg2": "cfg2: 64-node RC ladder .ac dec 200000 1 100k (1,000,001 points, Nvar=65, c128 LU)",
-                         "cfg4": "cfg4: 16x16 RC mesh .ac (Nvar=257)", "cfg1": "cfg1: README RC low-pass"}[name],
+                         "cfg4": "cfg4: 16x16 RC mesh .ac dec 1600000 1 100k, %d-point slice of the 8,000,001 (Nvar=257, c128 LU)" % freqs.shape[0], "cfg1": "cfg1: README RC low-pass"}[name],
                   flops_per_unit=f_cplx(table.nvar),
                   bytes_per_unit=8 + 16 * table.nvar + 16 * table.n_ac_elem)
     else:
