@@ -384,8 +384,12 @@ inline std::string generate_sparse_kernel_source(const CodegenInput& in, const C
     s += "    fnext = a.freqs[min(p + stride, plast)];\n";
     if (need_iw) s += "    const double iw = 1.0 / w;\n";
   }
-  s += "    char* const xb = (char*)(a.series_ld ? a.x + p : a.x + p * a.n);\n";
-  if (opt.with_ielem) s += "    char* const ib = (char*)(a.series_ld ? a.ielem + p : a.ielem + p * a.n_ac_elem);\n";
+  // Lanes past the end of the sweep solve the LAST point again (same frequency, same instructions, so the same bits)
+  // and store it to the last point's rows: a benign duplicate write instead of a predicate, which keeps every result
+  // store unconditional and the back-substitution one basic block (no BSSY / BRA / BSYNC around each row's stores).
+  s += "    const long long pc = min(p, plast);\n";
+  s += "    char* const xb = (char*)(a.series_ld ? a.x + pc : a.x + pc * a.n);\n";
+  if (opt.with_ielem) s += "    char* const ib = (char*)(a.series_ld ? a.ielem + pc : a.ielem + pc * a.n_ac_elem);\n";
   s += "    bool ok = true, bad = false;\n    double mp, m, inv;\n    double2 r, fm;\n";
   if (!in.eager)
     for (double L : sp.ind_L)  // inductor guards of simulateAC.ts:47-51 are value dependent: dense kernel decides
@@ -429,7 +433,7 @@ inline std::string generate_sparse_kernel_source(const CodegenInput& in, const C
   std::vector<Out> pending;
   auto flush_outputs = [&]() {
     for (const Out& o : pending)
-      s += std::string("    if (valid) *(double2*)(") + (o.cur ? "ib" : "xb") + " + " + off(o.k) + ") = D2(" + o.re + ", " + o.im + ");\n";
+      s += std::string("    *(double2*)(") + (o.cur ? "ib" : "xb") + " + " + off(o.k) + ") = D2(" + o.re + ", " + o.im + ");\n";
     pending.clear();
   };
 
