@@ -91,9 +91,12 @@ struct DeviceCtx {
   int sp_jit_block = 96, sp_jit_minb = 2, sp_jit_slots = 75, sp_jit_sync = 4;
   int sp_jit_stagger = 0;           // ns between four start phases of the CTAs (helped the 1 x 192 shape by 2 %)
   double sp_jit_antiphase_ns_per_op = 10.4;   // start delay of the second wave: half an iteration, ~20.8 ns per micro-op
-  // per-instance (eager) stamping keeps element values in flight: fewer threads, more shared memory each, one CTA per SM
-  int sp_jit_minb_eager = 1, sp_jit_stagger_eager = 4000;
-  int sp_jit_block_eager = 128, sp_jit_slots_eager = 113, sp_jit_prefetch = 8;   // cfg2mc: 1.52 ms (prefetch 4: 1.60, 2: 1.71)
+  // per-instance (eager) stamping keeps element values in flight: fewer threads, more shared memory each.  cfg2mc:
+  // 2 CTAs x 64 threads x 112 slots 1.18 ms, 1 x 128 x 113 1.28 ms, 2 x 96 x 75 1.57, 1 x 160 x 90 1.50 (a start delay
+  // between the two CTAs changes nothing here: the kernel is bound by its arithmetic, not by the store port);
+  // prefetch 8 pivots ahead (4: +5 %, 2: +12 %)
+  int sp_jit_minb_eager = 2, sp_jit_stagger_eager = 0;
+  int sp_jit_block_eager = 64, sp_jit_slots_eager = 112, sp_jit_prefetch = 8;
   double sp_jit_compile_ms = 0;
   uint64_t sp_jit_fit_key = 0;   // sparse program the fit check below was made for
   bool sp_jit_fits = false;
