@@ -31,6 +31,9 @@ def test_sparse_ac_kernel_source_cfg2_compiles_without_spills(tmp_path):
     # 65 reciprocals + 64 eliminated right-hand sides cross into the back-substitution; 75 of them in shared memory
     assert st["saved_values"] == 129 and st["smem_slots"] == 75 and st["cfma"] == 313 and st["reciprocals"] == 65
     assert "rcp_nr(" in src and "__constant__ double KC[" in src and "st.shared.v2.f64" in src
+    # result stores are unconditional (lanes past the end re-solve and re-write the last point): no predicate per row
+    assert "if (valid) *(double2*)" not in src and "const long long pc = min(p, plast);" in src
+    assert src.count("*(double2*)(xb + ") == 65 and src.count("*(double2*)(ib + ") == 127
     regs, spill = _compile(src, tmp_path, "ac_cfg2")
     assert regs <= 255 and spill == 0
     # without element currents (ielem == NULL): a second variant of the same program
