@@ -12,6 +12,7 @@
 
 #include <cstdio>
 #include <cstdlib>
+#include <cstring>
 #include <string>
 #include <vector>
 
@@ -78,38 +79,63 @@ inline std::string jit_cache_dir() {
   return std::string();
 }
 
+// Path of the cache entry of one source text (empty when the cache is off).
+inline std::string jit_cache_path(const std::string& src) {
+  const std::string dir = jit_cache_dir();
+  if (dir.empty()) return std::string();
+  unsigned long long h = 1469598103934665603ull;
+  auto mix = [&](const void* p, size_t n) { const unsigned char* q = (const unsigned char*)p; for (size_t i = 0; i < n; ++i) { h ^= q[i]; h *= 1099511628211ull; } };
+  mix(src.data(), src.size());
+  int ver[2] = {0, 0};
+  if (nvrtc().ok && nvrtc().version) nvrtc().version(&ver[0], &ver[1]);
+  mix(ver, sizeof ver);
+  char name[64];
+  snprintf(name, sizeof name, "/%016llx_%zu.sm_100a.jit", h, src.size());
+  return dir + name;
+}
+
+// Drops the cache entry of `src` (a cubin that fails to load is evicted and compiled again once).
+inline void jit_cache_evict(const std::string& src) {
+  const std::string path = jit_cache_path(src);
+  if (!path.empty()) remove(path.c_str());
+}
+
 // jit_compile through the on-disk cache.  `from_cache` (optional) tells which way it went.
+// Entry layout: "SPCYJIT1" | u64 source bytes | u64 cubin bytes | source text | cubin.  The file name is only a
+// 64-bit hash: a hit is accepted when the stored source text equals `src` byte for byte and the sizes add up, so a
+// hash collision, a truncated file or a foreign file is a miss (and is overwritten), never a wrong kernel.
 inline bool jit_compile_cached(const std::string& src, std::vector<char>& cubin, std::string& why, bool* from_cache = nullptr) {
   if (from_cache) *from_cache = false;
-  const std::string dir = jit_cache_dir();
-  std::string path;
-  if (!dir.empty()) {
-    unsigned long long h = 1469598103934665603ull;
-    auto mix = [&](const void* p, size_t n) { const unsigned char* q = (const unsigned char*)p; for (size_t i = 0; i < n; ++i) { h ^= q[i]; h *= 1099511628211ull; } };
-    mix(src.data(), src.size());
-    int ver[2] = {0, 0};
-    if (nvrtc().ok && nvrtc().version) nvrtc().version(&ver[0], &ver[1]);
-    mix(ver, sizeof ver);
-    char name[64];
-    snprintf(name, sizeof name, "/%016llx_%zu.sm_100a.cubin", h, src.size());
-    path = dir + name;
+  const std::string path = jit_cache_path(src);
+  static const char kMagic[8] = {'S', 'P', 'C', 'Y', 'J', 'I', 'T', '1'};
+  if (!path.empty()) {
     if (FILE* f = fopen(path.c_str(), "rb")) {
-      fseek(f, 0, SEEK_END);
-      const long n = ftell(f);
-      fseek(f, 0, SEEK_SET);
-      cubin.resize(n > 0 ? (size_t)n : 0);
-      const bool got = n > 0 && fread(cubin.data(), 1, (size_t)n, f) == (size_t)n;
+      char magic[8];
+      unsigned long long ns = 0, nc = 0;
+      bool got = fread(magic, 1, 8, f) == 8 && memcmp(magic, kMagic, 8) == 0 && fread(&ns, 8, 1, f) == 1 && fread(&nc, 8, 1, f) == 1 &&
+                 ns == src.size() && nc > 0 && nc < (1ull << 31);
+      if (got) {
+        std::string stored(ns, '\0');
+        got = fread(&stored[0], 1, ns, f) == ns && stored == src;
+      }
+      if (got) {
+        cubin.resize(nc);
+        got = fread(cubin.data(), 1, nc, f) == nc && fgetc(f) == EOF;
+      }
       fclose(f);
       if (got) { if (from_cache) *from_cache = true; return true; }
     }
   }
   if (!jit_compile(src, cubin, why)) return false;
   if (!path.empty()) {   // best effort: write to a temporary name, then rename (concurrent ranks compile the same source)
+    const std::string dir = jit_cache_dir();
     mkdir(dir.substr(0, dir.find_last_of('/')).c_str(), 0755);
     mkdir(dir.c_str(), 0755);
     const std::string tmp = path + "." + std::to_string((long long)getpid()) + ".tmp";
     if (FILE* f = fopen(tmp.c_str(), "wb")) {
-      const bool okw = fwrite(cubin.data(), 1, cubin.size(), f) == cubin.size();
+      const unsigned long long ns = src.size(), nc = cubin.size();
+      const bool okw = fwrite(kMagic, 1, 8, f) == 8 && fwrite(&ns, 8, 1, f) == 1 && fwrite(&nc, 8, 1, f) == 1 &&
+                       fwrite(src.data(), 1, src.size(), f) == src.size() && fwrite(cubin.data(), 1, cubin.size(), f) == cubin.size();
       fclose(f);
       if (!okw || rename(tmp.c_str(), path.c_str()) != 0) remove(tmp.c_str());
     }

@@ -363,7 +363,7 @@ inline std::string generate_sparse_kernel_source(const CodegenInput& in, const C
   // nothing) — starts half an iteration late, so that one CTA eliminates while the other stores.
   if (opt.antiphase_ns > 0 && opt.min_blocks >= 2) {
     const std::string mb = std::to_string(opt.min_blocks) + "u";
-    s += "  if (a.p_count > 4ll * gridDim.x * BLOCK) { const unsigned wv = blockIdx.x / (gridDim.x / " + mb + "); if (wv) __nanosleep(wv * " +
+    s += "  if (a.p_count > 4ll * gridDim.x * BLOCK) { const unsigned wv = blockIdx.x / max(1u, gridDim.x / " + mb + "); if (wv) __nanosleep(wv * " +
          std::to_string(opt.antiphase_ns) + "u); }\n";
   }
   s += "  const unsigned ld = a.series_ld ? (unsigned)a.series_ld : 1u;\n";

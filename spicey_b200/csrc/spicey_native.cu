@@ -395,6 +395,25 @@ void jit_source(const SparseProgram& sp, const HostPlan& hp, const CodegenOption
   src = generate_sparse_kernel_source(ci, opt, &st);
 }
 
+// source -> loaded kernel, through the disk cache.  A cached cubin that does not load (foreign architecture,
+// damaged file) is evicted and the source compiled again once before the variant is given up.
+bool load_jit_kernel(const std::string& src, const char* name, cudaLibrary_t* lib, cudaKernel_t* kernel, std::string& note) {
+  for (int attempt = 0; attempt < 2; ++attempt) {
+    std::vector<char> cubin;
+    bool from_cache = false;
+    if (!jit_compile_cached(src, cubin, note, &from_cache)) return false;
+    if (cudaLibraryLoadData(lib, cubin.data(), nullptr, nullptr, 0, nullptr, nullptr, 0) == cudaSuccess) {
+      if (cudaLibraryGetKernel(kernel, *lib, name) == cudaSuccess) return true;
+      cudaLibraryUnload(*lib);
+    }
+    *lib = nullptr; *kernel = nullptr;
+    note = std::string("loading the compiled kernel failed: ") + cudaGetErrorString(cudaGetLastError());
+    if (!from_cache) return false;
+    jit_cache_evict(src);
+  }
+  return false;
+}
+
 // Compiles (once per topology, handle and variant) the straight-line kernel of the cached sparse program.
 // Returns the usable variant or nullptr.
 // Returns the usable variant or nullptr.
@@ -429,12 +448,9 @@ DeviceCtx::JitVariant* ensure_jit(DeviceCtx& ctx, const HostPlan& hp, bool with_
   std::string src;
   CodegenStats st;
   jit_source(ctx.sp, hp, opt, ctx.sp_eager, src, st);
-  std::vector<char> cubin;
-  if (!jit_compile_cached(src, cubin, ctx.sp_jit_note)) return nullptr;
-  if (cudaLibraryLoadData(&jv.lib, cubin.data(), nullptr, nullptr, 0, nullptr, nullptr, 0) != cudaSuccess ||
-      cudaLibraryGetKernel(&jv.kernel, jv.lib, "spicey_sparse_jit") != cudaSuccess ||
-      cudaFuncSetAttribute((const void*)jv.kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)st.smem_bytes) != cudaSuccess) {
-    ctx.sp_jit_note = std::string("loading the compiled kernel failed: ") + cudaGetErrorString(cudaGetLastError());
+  if (!load_jit_kernel(src, "spicey_sparse_jit", &jv.lib, &jv.kernel, ctx.sp_jit_note)) return nullptr;
+  if (cudaFuncSetAttribute((const void*)jv.kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)st.smem_bytes) != cudaSuccess) {
+    ctx.sp_jit_note = std::string("the compiled kernel does not accept its shared-memory size: ") + cudaGetErrorString(cudaGetLastError());
     jv.kernel = nullptr;
     return nullptr;
   }
@@ -771,14 +787,7 @@ DeviceCtx::JitVariant* ensure_tran_jit(DeviceCtx& ctx, const HostPlan& hp, const
   if (jv.lib) { cudaLibraryUnload(jv.lib); jv.lib = nullptr; jv.kernel = nullptr; }
   std::string src;
   tran_jit_source(hp, waves, with_ielem, src);
-  std::vector<char> cubin;
-  if (!jit_compile_cached(src, cubin, ctx.sp_jit_note)) return nullptr;
-  if (cudaLibraryLoadData(&jv.lib, cubin.data(), nullptr, nullptr, 0, nullptr, nullptr, 0) != cudaSuccess ||
-      cudaLibraryGetKernel(&jv.kernel, jv.lib, "spicey_tran_jit") != cudaSuccess) {
-    ctx.sp_jit_note = std::string("loading the compiled transient kernel failed: ") + cudaGetErrorString(cudaGetLastError());
-    jv.kernel = nullptr;
-    return nullptr;
-  }
+  if (!load_jit_kernel(src, "spicey_tran_jit", &jv.lib, &jv.kernel, ctx.sp_jit_note)) return nullptr;
   jv.failed = false;
   return &jv;
 }
@@ -946,7 +955,8 @@ void spicey_destroy(spicey_handle* h) {
     cudaSetDevice(c.dev);
     cudaDeviceSynchronize();
     Buffer* bufs[] = {&c.plan, &c.scratch, &c.in0, &c.in1, &c.in2, &c.out_x[0], &c.out_x[1], &c.out_i[0],
-                      &c.out_i[1], &c.out_s[0], &c.out_s[1], &c.aux0, &c.aux1, &c.sp_blob, &c.sp_work, &c.sp_fb};
+                      &c.out_i[1], &c.out_s[0], &c.out_s[1], &c.aux0, &c.aux1, &c.sp_blob, &c.sp_work, &c.sp_fb,
+                      &c.wp_blob, &c.wp_work};
     for (Buffer* b : bufs) b->release();
     for (auto& jv : c.sp_jit) if (jv.lib) cudaLibraryUnload(jv.lib);
     for (auto& jv : c.tr_jit) if (jv.lib) cudaLibraryUnload(jv.lib);
