@@ -481,7 +481,7 @@ def run_native(args):
             dense = {"bound": "fp64", "achieved": ach_f, "peak": fp64_peak, "unit": "TFLOP/s",
                      "frac": ach_f / fp64_peak, "flops_per_solve_dense": wl["flops_per_unit"],
                      "peak_source": "own DFMA-loop microbenchmark in this run (MEASURED_PEAKS.json has no FP64 figure)"}
-            if tier in (native.TIER_SPARSE, native.TIER_SPARSE_JIT, native.TIER_SPARSE_WARP):
+            if tier in (native.TIER_SPARSE, native.TIER_SPARSE_JIT, native.TIER_SPARSE_WARP, native.TIER_BAND):
                 # The sparse program executes ~1e3 flop per solve instead of the dense 7.7e5, so the FP64
                 # pipe cannot bind; what binds is HBM: SURVEY 8(d)'s algorithmic bytes per solve.
                 ach = units * wl["bytes_per_unit"] / (kern_ms * 1e-3) / 1e9

@@ -133,6 +133,9 @@ enum {
   ,SPICEY_TIER_SPARSE_WARP = 7 /* the sparse program level-scheduled for one WARP per system: elimination working
                                 set in shared memory, U streamed to a per-warp workspace (programs whose
                                 per-system factorisation is too large for one thread's share of the chip) */
+  ,SPICEY_TIER_BAND = 8       /* banded + bordered systems (meshes, long ladders) after a bandwidth-reducing
+                                renumbering of the nodes: a few lanes per system, the sliding window of rows in
+                                registers, partial pivoting verified per system (band_kernel.cuh) */
 };
 
 typedef struct spicey_handle spicey_handle;
@@ -261,7 +264,9 @@ enum {
   SPICEY_FLAG_JIT = 128u,          /* compile the per-topology kernel (AC tier 5, TRAN tier 6) even for small batches */
   SPICEY_FLAG_WARP = 512u,         /* AC: use the warp-per-system sparse tier even for small programs (testing) */
   SPICEY_FLAG_NO_WARP = 1024u,     /* AC: never use the warp-per-system sparse tier */
-  SPICEY_FLAG_NO_JIT = 256u        /* never compile: interpreted sparse program (AC), generic kernels (TRAN) */
+  SPICEY_FLAG_NO_JIT = 256u,       /* never compile: interpreted sparse program (AC), generic kernels (TRAN) */
+  SPICEY_FLAG_BAND = 2048u,        /* AC: use the banded + bordered tier even for small batches / small programs (testing) */
+  SPICEY_FLAG_NO_BAND = 4096u      /* AC: never use the banded + bordered tier */
 };
 
 /* Tooling (no device needed): writes the CUDA source of the compiled straight-line sparse kernel
@@ -287,6 +292,15 @@ int64_t spicey_debug_tran_source_waves(const spicey_elem_table* table, const spi
  * out[8] = Nvar, shared-memory pool slots, global workspace slots, rows per step (max), updates, update
  * chunks of 32, back-substitution entries, thread-per-system workspace slots of the same circuit. */
 int32_t spicey_debug_warp_stats(const spicey_elem_table* table, double pilot_f, int32_t* out);
+
+/* Tooling (no device needed): the banded + bordered plan (tier 8) of this element table: out[8] = window W, lanes per
+ * system, rows per lane, measured half-bandwidth, 1 when the nodes were renumbered, border rows, active border-column
+ * mask, workspace values per system.  SPICEY_ERR_UNSUPPORTED when the circuit does not qualify. */
+int32_t spicey_debug_band_stats(const spicey_elem_table* table, double pilot_f, int32_t* out);
+
+/* Tooling (no device needed): the CUDA source NVRTC compiles for one band shape; returns the size needed. */
+int64_t spicey_debug_band_source(int32_t L, int32_t RPL, int32_t NB, uint32_t abmask, int32_t with_ielem, int32_t warps,
+                                 int32_t minb, char* buf, int64_t cap);
 
 /* Measures this GPU's FP64 FMA peak with a register-only DFMA loop (GFLOP/s), the
  * denominator the FP64-bound roofline is reported against. */

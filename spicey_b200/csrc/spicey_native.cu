@@ -20,6 +20,8 @@
 #include "ac_kernels.cuh"
 #include "ac_sparse.cuh"
 #include "ac_warp.cuh"
+#include "band_kernel_embed.h"
+#include "band_plan.h"
 #include "host_plan.h"
 #include "jit_runtime.h"
 #include "sparse_codegen.h"
@@ -108,6 +110,21 @@ struct DeviceCtx {
   bool wp_chainlike = false;   // fewer than 32 updates per pivot step on average: the warp tier is only used when forced
   Buffer wp_blob, wp_work;
   WarpArgs wp_args;
+  // banded + bordered tier (band_plan.h / band_kernel.cuh): plan of the last topology, its tables, the workspace
+  BandPlan bp;
+  uint64_t bp_key = 0;        // sparse-program key the band plan was built for (0 = none)
+  bool bp_valid = false;
+  Buffer bp_blob, bp_work;
+  struct BandDev { const void *tab, *flags, *newvar, *el_idx; } bp_dev = {nullptr, nullptr, nullptr, nullptr};
+  struct BandJit {
+    cudaLibrary_t lib = nullptr;
+    cudaKernel_t kernel = nullptr;
+    uint64_t key = 0;
+    bool failed = false;
+    int warps = 0, minb = 0;
+    size_t smem_bytes = 0;
+  } band_jit[2];              // [0] without, [1] with element currents
+  double sp_pilot_f = 0;      // frequency of the pilot point the cached programs were built from
   uint64_t plan_up_key = 0;   // plan currently resident in `plan` (its device pointers are in plan_dp)
   DevPlan plan_dp;
   JitVariant tr_jit[2];   // compiled transient kernel of the last topology: [0] without, [1] with element currents
@@ -307,6 +324,7 @@ int prepare_sparse(DeviceCtx& ctx, const HostPlan& hp, double pilot_f, bool eage
   build_sparse_host(hp, pilot_f, eager, sp);
   const int n_ent = (int)hp.ac.ent_col.size();
   ctx.sp_eager = eager;
+  ctx.sp_pilot_f = pilot_f;
   if (!sp.ok) return SPICEY_SUCCESS;
   // Workspace stride: the resident grid the workspace is sized for (offsets are baked into the program).
   {
@@ -528,6 +546,146 @@ int launch_ac_warp(DeviceCtx& ctx, const HostPlan& hp, const DevPlan& dp, const 
   return SPICEY_SUCCESS;
 }
 
+
+// ---------------------------------------------------------------------------------
+// Banded + bordered tier (SPICEY_TIER_BAND): band_plan.h decides whether the topology qualifies and lays out the
+// tables, band_kernel.cuh (embedded as text, compiled by NVRTC once per band shape and cached on disk) solves.
+struct BandArgs {   // must match band_kernel.cuh
+  const double* freqs; long long p_count;
+  double2* x; double2* ielem; int* status; long long series_ld;
+  long long* fb_list; int* fb_count;
+  double2* G; long long g_stride;
+  const double2* tab; const uint2* flags; const int* newvar; const int2* el_idx;
+  const double *el_a, *el_b, *el_g; const double* ind_L;
+  int n, nb, n_ac_elem, v_first, n_ind;
+  int o_init, o_initb, o_nc, o_lc, o_e0, o_erb, o_brd0, o_brdnc, o_bb0;
+};
+
+constexpr int kBandMinBandwidth = 1;   // every banded + bordered circuit the thread-per-system compiled tier refuses
+
+void band_input(const HostPlan& hp, const SparseProgram& sp, double pilot_f, BandInput& in) {
+  in.n = hp.nvar; in.nn = hp.nn; in.nV = hp.nV;
+  in.row_ptr = &hp.ac.row_ptr; in.ent_col = &hp.ac.ent_col;
+  in.ent_alpha = &sp.ent_alpha; in.ent_beta = &sp.ent_beta; in.ent_gamma = &sp.ent_gamma;
+  in.ent_jre = &sp.ent_jre; in.ent_jim = &sp.ent_jim;
+  in.pilot_w = (2 * kPi) * pilot_f;
+}
+
+void band_force_shape(int& L, int& RPL) {   // experiments: SPICEY_BAND_SHAPE=L,RPL
+  L = RPL = 0;
+  if (const char* e = getenv("SPICEY_BAND_SHAPE")) {
+    int a = 0, b = 0;
+    if (sscanf(e, "%d,%d", &a, &b) == 2 && a >= 1 && a <= 32 && (a & (a - 1)) == 0 && b >= 1 && b <= 4 && (b & (b - 1)) == 0) { L = a; RPL = b; }
+  }
+}
+
+// Builds (once per topology and handle) the band plan of the cached sparse program's circuit and uploads its tables.
+int prepare_band(DeviceCtx& ctx, const HostPlan& hp, cudaStream_t stream) {
+  if (ctx.bp_key == ctx.sp_key) return SPICEY_SUCCESS;
+  ctx.bp_key = ctx.sp_key;
+  ctx.bp_valid = false;
+  BandInput in;
+  band_input(hp, ctx.sp, ctx.sp_pilot_f, in);
+  int fl = 0, fr = 0;
+  band_force_shape(fl, fr);
+  build_band_plan(in, ctx.bp, fl, fr);
+  BandPlan& bp = ctx.bp;
+  if (!bp.ok || bp.bandwidth < kBandMinBandwidth) return SPICEY_SUCCESS;
+  std::vector<int2> el_idx(std::max(1, hp.n_ac_elem));
+  for (int e = 0; e < hp.n_ac_elem; ++e) {
+    const int n1 = hp.ends[e].x, n2 = hp.ends[e].y;
+    el_idx[e] = make_int2(n1 ? bp.newvar[n1 - 1] : -1, n2 ? bp.newvar[n2 - 1] : -1);
+  }
+  std::vector<unsigned char> blob;
+  const size_t o_tab = push_blob(blob, bp.tab), o_fl = push_blob(blob, bp.flags), o_nv = push_blob(blob, bp.newvar),
+               o_ei = push_blob(blob, el_idx);
+  int rc = ctx.bp_blob.ensure(blob.size() + 16);
+  if (rc) return rc;
+  CUDA_TRY(cudaMemcpyAsync(ctx.bp_blob.p, blob.data(), blob.size(), cudaMemcpyHostToDevice, stream));
+  CUDA_TRY(cudaStreamSynchronize(stream));
+  unsigned char* b = (unsigned char*)ctx.bp_blob.p;
+  ctx.bp_dev.tab = b + o_tab; ctx.bp_dev.flags = b + o_fl; ctx.bp_dev.newvar = b + o_nv; ctx.bp_dev.el_idx = b + o_ei;
+  ctx.bp_valid = true;
+  return SPICEY_SUCCESS;
+}
+
+std::string band_source(const BandPlan& bp, bool with_ielem, int warps, int minb) {
+  char head[512];
+  snprintf(head, sizeof head,
+           "#define BAND_L %d\n#define BAND_RPL %d\n#define BAND_NB %d\n#define BAND_ABMASK %uu\n#define BAND_IELEM %d\n"
+           "#define BAND_WARPS %d\n#define BAND_MINB %d\n",
+           bp.L, bp.RPL, bp.NB, bp.abmask, with_ielem ? 1 : 0, warps, minb);
+  return std::string(head) + kBandKernelSource;
+}
+
+// Shared memory of one CTA: per system the solution vector and two pivot records.
+size_t band_smem_bytes(const BandPlan& bp, int warps) {
+  return sizeof(double2) * (size_t)warps * (32 / bp.L) * ((size_t)bp.n + 2 * (size_t)(bp.W + bp.NB + 2));
+}
+
+// Launch shape: as many warps per SM as shared memory and the register file (255 per thread) allow.
+bool band_launch_shape(const DeviceCtx& ctx, const BandPlan& bp, int& warps, int& minb) {
+  if (const char* e = getenv("SPICEY_BAND_CFG")) {   // experiments: warps per CTA, CTAs per SM
+    int a = 0, b = 0;
+    if (sscanf(e, "%d,%d", &a, &b) == 2 && a >= 1 && a <= 16 && b >= 1 && b <= 8 && band_smem_bytes(bp, a) * b + 1024 * b <= ctx.smem_optin + 1024) {
+      warps = a; minb = b;
+      return true;
+    }
+  }
+  const int shapes[][2] = {{4, 2}, {2, 2}, {2, 1}, {1, 1}};
+  for (const auto& sh : shapes)
+    if ((band_smem_bytes(bp, sh[0]) + 1024) * sh[1] <= ctx.smem_optin) { warps = sh[0]; minb = sh[1]; return true; }
+  return false;
+}
+
+DeviceCtx::BandJit* ensure_band_jit(DeviceCtx& ctx, bool with_ielem) {
+  DeviceCtx::BandJit& jv = ctx.band_jit[with_ielem ? 1 : 0];
+  const BandPlan& bp = ctx.bp;
+  int warps = 0, minb = 0;
+  if (!band_launch_shape(ctx, bp, warps, minb)) return nullptr;
+  const int shape[8] = {bp.L, bp.RPL, bp.NB, (int)bp.abmask, warps, minb, with_ielem ? 1 : 0, 1};
+  uint64_t key = fnv1a(1469598103934665603ull, shape, sizeof shape);
+  if (!key) key = 1;
+  if (jv.key == key) return jv.failed ? nullptr : &jv;
+  jv.key = key;
+  jv.failed = true;
+  if (jv.lib) { cudaLibraryUnload(jv.lib); jv.lib = nullptr; jv.kernel = nullptr; }
+  const std::string src = band_source(bp, with_ielem, warps, minb);
+  if (!load_jit_kernel(src, "spicey_band_jit", &jv.lib, &jv.kernel, ctx.sp_jit_note)) return nullptr;
+  jv.warps = warps; jv.minb = minb;
+  jv.failed = false;
+  return &jv;
+}
+
+int launch_ac_band(DeviceCtx& ctx, const HostPlan& hp, const AcArgs& args, DeviceCtx::BandJit* jv, cudaStream_t stream,
+                   long long* fb_list, int* fb_count, int64_t* launches) {
+  const BandPlan& bp = ctx.bp;
+  const int gpb = jv->warps * (32 / bp.L);   // systems per CTA
+  const size_t smem = band_smem_bytes(bp, jv->warps);
+  unsigned grid = (unsigned)std::min<long long>((args.p_count + gpb - 1) / gpb, (long long)ctx.sm_count * jv->minb);
+  if (const char* e = getenv("SPICEY_BAND_GRID")) grid = std::min<unsigned>(grid, (unsigned)std::max(1, atoi(e)));   // experiments
+  int rc = ctx.bp_work.ensure(sizeof(double2) * (size_t)bp.g_stride * grid * gpb);
+  if (rc) return rc;
+  CUDA_TRY(cudaFuncSetAttribute((const void*)jv->kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const SparseArgs& sa = ctx.sp_args;   // per-element constants already uploaded for the interpreter
+  BandArgs a;
+  memset(&a, 0, sizeof a);
+  a.freqs = args.freqs + args.p_begin; a.p_count = args.p_count;
+  a.x = args.x; a.ielem = args.ielem; a.status = args.status; a.series_ld = args.series_ld;
+  a.fb_list = fb_list; a.fb_count = fb_count;
+  a.G = (double2*)ctx.bp_work.p; a.g_stride = bp.g_stride;
+  a.tab = (const double2*)ctx.bp_dev.tab; a.flags = (const uint2*)ctx.bp_dev.flags;
+  a.newvar = (const int*)ctx.bp_dev.newvar; a.el_idx = (const int2*)ctx.bp_dev.el_idx;
+  a.el_a = sa.el_a; a.el_b = sa.el_b; a.el_g = sa.el_g; a.ind_L = sa.ind_L;
+  a.n = hp.nvar; a.nb = bp.nb; a.n_ac_elem = hp.n_ac_elem; a.v_first = hp.off[ELEM_V]; a.n_ind = sa.n_ind;
+  a.o_init = bp.o_init; a.o_initb = bp.o_initb; a.o_nc = bp.o_nc; a.o_lc = bp.o_lc; a.o_e0 = bp.o_e0; a.o_erb = bp.o_erb;
+  a.o_brd0 = bp.o_brd0; a.o_brdnc = bp.o_brdnc; a.o_bb0 = bp.o_bb0;
+  void* kargs[] = {&a};
+  CUDA_TRY(cudaLaunchKernel((const void*)jv->kernel, dim3(grid), dim3(jv->warps * 32), kargs, smem, stream));
+  if (launches) ++*launches;
+  return SPICEY_SUCCESS;
+}
+
 int launch_ac_sparse(DeviceCtx& ctx, const HostPlan& hp, const DevPlan& dp, const AcArgs& args, uint32_t flags,
                      cudaStream_t stream, int* tier_out, int64_t* launches) {
   const int block = 128;
@@ -546,7 +704,7 @@ int launch_ac_sparse(DeviceCtx& ctx, const HostPlan& hp, const DevPlan& dp, cons
     ctx.sp_jit_fit_key = ctx.sp_key;
     ctx.sp_jit_fits = count_cross_phase_values(ctx.sp) <= (ctx.sp_eager ? ctx.sp_jit_slots_eager : ctx.sp_jit_slots) + kJitSpareValues;
   }
-  const bool want_jit = !(flags & SPICEY_FLAG_NO_JIT) && ctx.sp.code.size() <= kJitMaxOps && ctx.sp_jit_fits &&
+  const bool want_jit = !(flags & (SPICEY_FLAG_NO_JIT | SPICEY_FLAG_BAND)) && ctx.sp.code.size() <= kJitMaxOps && ctx.sp_jit_fits &&
                         (args.p_count >= kJitMinPoints || (flags & SPICEY_FLAG_JIT));
   DeviceCtx::JitVariant* jv = (want_jit && args.series_ld < (1ll << 32)) ? ensure_jit(ctx, hp, args.ielem != nullptr) : nullptr;
   if (jv) {
@@ -570,6 +728,27 @@ int launch_ac_sparse(DeviceCtx& ctx, const HostPlan& hp, const DevPlan& dp, cons
     if (rc) return rc;
     if (tier_out) *tier_out = SPICEY_TIER_SPARSE_JIT;
     return SPICEY_SUCCESS;
+  }
+  // Banded + bordered circuits the thread-per-system compiled kernel does not take (meshes, long ladders): a few
+  // lanes per system, register-blocked (band_plan.h / band_kernel.cuh).  Compiled once per band shape and machine.
+  if (!ctx.sp_eager && !(flags & (SPICEY_FLAG_NO_BAND | SPICEY_FLAG_NO_JIT)) && args.series_ld < (1ll << 31) &&
+      ((flags & SPICEY_FLAG_BAND) || args.p_count >= kJitMinPoints || (flags & SPICEY_FLAG_JIT))) {
+    rc = prepare_band(ctx, hp, stream);
+    if (rc) return rc;
+    if (ctx.bp_valid) {
+      if (DeviceCtx::BandJit* bj = ensure_band_jit(ctx, args.ielem != nullptr)) {
+        rc = launch_ac_band(ctx, hp, args, bj, stream, fb_list, fb_count, launches);
+        if (rc) return rc;
+        AcArgs d = args;
+        d.plist = fb_list;
+        d.pcount = fb_count;
+        d.fb_total = (unsigned long long*)((char*)ctx.sp_fb.p + 32);
+        rc = launch_ac_dense(ctx, hp, dp, d, flags, stream, nullptr, launches);
+        if (rc) return rc;
+        if (tier_out) *tier_out = SPICEY_TIER_BAND;
+        return SPICEY_SUCCESS;
+      }
+    }
   }
   // Large programs of a plain frequency sweep: one warp per system (warp_program.h / ac_warp.cuh).
   if (!ctx.sp_eager && !(flags & SPICEY_FLAG_NO_WARP) && (ctx.sp.n_slots >= kWarpTierMinSlots || (flags & SPICEY_FLAG_WARP))) {
@@ -956,10 +1135,11 @@ void spicey_destroy(spicey_handle* h) {
     cudaDeviceSynchronize();
     Buffer* bufs[] = {&c.plan, &c.scratch, &c.in0, &c.in1, &c.in2, &c.out_x[0], &c.out_x[1], &c.out_i[0],
                       &c.out_i[1], &c.out_s[0], &c.out_s[1], &c.aux0, &c.aux1, &c.sp_blob, &c.sp_work, &c.sp_fb,
-                      &c.wp_blob, &c.wp_work};
+                      &c.wp_blob, &c.wp_work, &c.bp_blob, &c.bp_work};
     for (Buffer* b : bufs) b->release();
     for (auto& jv : c.sp_jit) if (jv.lib) cudaLibraryUnload(jv.lib);
     for (auto& jv : c.tr_jit) if (jv.lib) cudaLibraryUnload(jv.lib);
+    for (auto& jv : c.band_jit) if (jv.lib) cudaLibraryUnload(jv.lib);
     for (auto e : c.events) cudaEventDestroy(e);
     cudaStreamDestroy(c.compute);
     cudaStreamDestroy(c.copy);
@@ -1028,7 +1208,7 @@ int32_t spicey_ac_solve_device(spicey_handle* h, int32_t dev_index, const spicey
   h->stats.kernel_launches = launches;
   h->stats.tier = tier;
   h->stats.fallback_solves = -1;  // resolved lazily by spicey_get_stats
-  h->stats.program_cfma = (tier == SPICEY_TIER_SPARSE || tier == SPICEY_TIER_SPARSE_JIT || tier == SPICEY_TIER_SPARSE_WARP) ? ctx.sp.n_fma : 0;
+  h->stats.program_cfma = tier == SPICEY_TIER_BAND ? ctx.bp.n_cfma : (tier == SPICEY_TIER_SPARSE || tier == SPICEY_TIER_SPARSE_JIT || tier == SPICEY_TIER_SPARSE_WARP) ? ctx.sp.n_fma : 0;
   h->stats.solves = a.p_count;
   h->stats.h2d_bytes = (int64_t)h->blob.size();
   h->stats.d2h_bytes = 0;
@@ -1153,7 +1333,7 @@ int32_t spicey_ac_solve(spicey_handle* h, const spicey_elem_table* table, const 
   h->stats.solves = P;
   h->stats.tier = tier;
   h->stats.fallback_solves = -1;
-  h->stats.program_cfma = (tier == SPICEY_TIER_SPARSE || tier == SPICEY_TIER_SPARSE_JIT || tier == SPICEY_TIER_SPARSE_WARP) ? h->devs[0].sp.n_fma : 0;
+  h->stats.program_cfma = tier == SPICEY_TIER_BAND ? h->devs[0].bp.n_cfma : (tier == SPICEY_TIER_SPARSE || tier == SPICEY_TIER_SPARSE_JIT || tier == SPICEY_TIER_SPARSE_WARP) ? h->devs[0].sp.n_fma : 0;
   return SPICEY_SUCCESS;
 }
 
@@ -1421,6 +1601,38 @@ int32_t spicey_debug_warp_stats(const spicey_elem_table* table, double pilot_f, 
   out[0] = wp.n; out[1] = wp.n_pool; out[2] = wp.n_gslots; out[3] = wp.max_elim;
   out[4] = (int32_t)wp.n_upd_total; out[5] = (int32_t)chunks; out[6] = (int32_t)wp.colent.size(); out[7] = sp.n_slots;
   return SPICEY_SUCCESS;
+}
+
+int32_t spicey_debug_band_stats(const spicey_elem_table* table, double pilot_f, int32_t* out) {
+  HostPlan hp;
+  int rc = build_plan(table, nullptr, hp);
+  if (rc) return rc;
+  SparseProgram sp;
+  build_sparse_host(hp, pilot_f, false, sp);
+  if (!sp.ok) return fail(SPICEY_ERR_UNSUPPORTED, "the sparse path does not apply to this circuit");
+  BandInput in;
+  band_input(hp, sp, pilot_f, in);
+  BandPlan bp;
+  int fl = 0, fr = 0;
+  band_force_shape(fl, fr);
+  build_band_plan(in, bp, fl, fr);
+  if (!bp.ok) return fail(SPICEY_ERR_UNSUPPORTED, "the circuit is not banded + bordered within the kernel's window");
+  out[0] = bp.W; out[1] = bp.L; out[2] = bp.RPL; out[3] = bp.bandwidth; out[4] = bp.renumbered ? 1 : 0; out[5] = bp.NB;
+  out[6] = (int32_t)bp.abmask; out[7] = (int32_t)std::min<long long>(bp.g_stride, 0x7fffffff);
+  return SPICEY_SUCCESS;
+}
+
+int64_t spicey_debug_band_source(int32_t L, int32_t RPL, int32_t NB, uint32_t abmask, int32_t with_ielem, int32_t warps,
+                                 int32_t minb, char* buf, int64_t cap) {
+  BandPlan bp;
+  bp.L = L; bp.RPL = RPL; bp.NB = NB; bp.abmask = abmask;
+  const std::string src = band_source(bp, with_ielem != 0, warps, minb);
+  if (buf && cap > 0) {
+    const size_t n = std::min<size_t>(src.size(), (size_t)cap - 1);
+    memcpy(buf, src.data(), n);
+    buf[n] = 0;
+  }
+  return (int64_t)src.size() + 1;
 }
 
 int64_t spicey_series_ld(int64_t n_points) { return (n_points + 31) / 32 * 32; }

@@ -17,7 +17,9 @@ VALUE_SLOTS = {ELEM_R: 1, ELEM_C: 1, ELEM_L: 1, ELEM_V: 3, ELEM_S: 4, ELEM_D: 2}
 ST_OK, ST_SINGULAR, ST_CDIV, ST_R_NONPOS = 0, 1, 2, 3
 FLAG_STRICT, FLAG_FORCE_GMEM, FLAG_FORCE_CTA, FLAG_DENSE, FLAG_SPARSE, FLAG_GENERIC_THREAD = 1, 2, 4, 8, 16, 32
 FLAG_SERIES_MAJOR, FLAG_JIT, FLAG_NO_JIT, FLAG_WARP, FLAG_NO_WARP = 64, 128, 256, 512, 1024
+FLAG_BAND, FLAG_NO_BAND = 2048, 4096
 TIER_THREAD, TIER_CTA_SMEM, TIER_CTA_GMEM, TIER_SPARSE, TIER_SPARSE_JIT, TIER_TRAN_JIT, TIER_SPARSE_WARP = 1, 2, 3, 4, 5, 6, 7
+TIER_BAND = 8
 SUCCESS, ERR_INVALID, ERR_NO_DEVICE, ERR_CUDA, ERR_UNSUPPORTED = 0, 1, 2, 3, 4
 
 EXPORTS = [
@@ -26,6 +28,7 @@ EXPORTS = [
     "spicey_ac_solve_device", "spicey_tran_solve", "spicey_tran_solve_device", "spicey_measure_fp64_peak",
     "spicey_debug_sparse_source", "spicey_series_ld", "spicey_debug_tran_source", "spicey_debug_warp_stats",
     "spicey_tran_solve_waves", "spicey_tran_solve_waves_device", "spicey_debug_tran_source_waves",
+    "spicey_debug_band_stats", "spicey_debug_band_source",
 ]
 WAVE_DC, WAVE_TABLE, WAVE_PULSE, WAVE_PWL = 0, 1, 2, 3
 
@@ -118,6 +121,11 @@ def load_library(path: Optional[str] = None):
     lib.spicey_debug_warp_stats.argtypes = [tb, C.c_double, _ip]
     lib.spicey_debug_tran_source.restype = C.c_int64
     lib.spicey_debug_tran_source.argtypes = [tb, sw, C.c_int32, C.c_char_p, C.c_int64]
+    lib.spicey_debug_band_stats.restype = C.c_int32
+    lib.spicey_debug_band_stats.argtypes = [tb, C.c_double, _ip]
+    lib.spicey_debug_band_source.restype = C.c_int64
+    lib.spicey_debug_band_source.argtypes = [C.c_int32, C.c_int32, C.c_int32, C.c_uint32, C.c_int32, C.c_int32, C.c_int32,
+                                             C.c_char_p, C.c_int64]
     if path == _build.LIB_PATH:
         _LIB = lib
     return lib
@@ -132,6 +140,30 @@ def warp_program_stats(table: "ElemTable", pilot_f: float = 1000.0) -> dict:
     keys = ("nvar", "pool_slots", "global_slots", "max_rows_per_step", "updates", "update_rows", "backsub_entries",
             "thread_tier_slots")
     return dict(zip(keys, list(st)))
+
+
+def band_plan_stats(table: "ElemTable", pilot_f: float = 1000.0) -> dict:
+    """Banded + bordered plan (tier 8) of a circuit: window, lanes per system, rows per lane, measured
+    half-bandwidth, whether the nodes were renumbered, border rows.  Host-only tooling; raises NativeError
+    (ERR_UNSUPPORTED) when the circuit does not qualify."""
+    lib = load_library()
+    st = (C.c_int32 * 8)()
+    ts = table.struct()
+    _check(lib, lib.spicey_debug_band_stats(C.byref(ts), pilot_f, st))
+    keys = ("window", "lanes", "rows_per_lane", "bandwidth", "renumbered", "border_rows", "border_col_mask",
+            "workspace_values")
+    return dict(zip(keys, list(st)))
+
+
+def band_kernel_source(lanes=8, rows_per_lane=2, border_rows=1, border_col_mask=0, with_ielem=True, warps=4,
+                       min_blocks=2) -> str:
+    """CUDA source NVRTC compiles for one band shape (tier 8).  Host-only tooling."""
+    lib = load_library()
+    args = (lanes, rows_per_lane, border_rows, border_col_mask, int(with_ielem), warps, min_blocks)
+    need = lib.spicey_debug_band_source(*args, None, 0)
+    buf = C.create_string_buffer(need)
+    lib.spicey_debug_band_source(*args, buf, need)
+    return buf.value.decode()
 
 
 def tran_kernel_source(table: "ElemTable", sweep: Optional["Sweep"] = None, with_ielem=True,

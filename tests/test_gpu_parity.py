@@ -676,15 +676,109 @@ def test_mesh_default_policy_takes_the_warp_tier(eng):
     assert rel_err(x[sub], xr) <= AC_TOL and rel_err(out["ielem"][0][sub], ier) <= AC_TOL
 
 
+BAND = native.FLAG_SPARSE | native.FLAG_BAND
+
+
+@pytest.mark.parametrize("flags", [BAND, BAND | SM])
+def test_ac_mesh16_band_tier(eng, flags):
+    """cfg 4 topology through the banded + bordered tier (tier 8): the nodes are renumbered to half-bandwidth 16
+    (netlist numbering: 30), 8 lanes x 2 rows per system; 4,097 points spread over the 8,000,001-point sweep,
+    every node voltage and element current against the oracle at 1e-9, no system flagged for the fallback."""
+    import spicey_b200 as sp
+    ck = parse_netlist(w.rc_mesh(16))
+    st_plan = native.band_plan_stats(sp.packing.pack_circuit(ck), 300.0)
+    assert st_plan["window"] == 16 and st_plan["lanes"] == 8 and st_plan["rows_per_lane"] == 2 and st_plan["renumbered"] == 1
+    freqs = np.array(sp.analysis.ac_frequencies(ck))
+    assert freqs.shape[0] == 8000001
+    sub = np.ascontiguousarray(freqs[::1953][:4097])
+    out = sp.simulate_ac_batch(ck, sub, engine=eng, flags=flags)
+    stt = eng.stats()
+    assert stt["tier"] == native.TIER_BAND and stt["fallback_solves"] == 0 and stt["program_cfma"] > 0, stt
+    assert out["status"].max() == 0
+    x, ie, st = co.ac_solve(ck, sub, nthreads=8)
+    assert st.max() == 0
+    assert rel_err(out["x"][0], x) <= AC_TOL, rel_err(out["x"][0], x)
+    assert rel_err(out["ielem"][0], ie) <= AC_TOL, rel_err(out["ielem"][0], ie)
+    assert rel_err(np.abs(out["x"][0]), np.abs(x)) <= AC_TOL
+    assert np.max(np.abs(np.angle(out["x"][0] * np.conj(x)))) <= AC_TOL
+    # without element currents: the other compiled variant
+    out2 = sp.simulate_ac_batch(ck, sub[:300], engine=eng, flags=flags, want_currents=False)
+    assert eng.stats()["tier"] == native.TIER_BAND and np.array_equal(out2["x"], out["x"][:, :300])
+
+
+@pytest.mark.parametrize("name,text,shape", [
+    ("mesh8", w.rc_mesh(8, ppd=50), (8, 1)), ("mesh5", w.rc_mesh(5, ppd=50), (8, 1)), ("mesh3", w.rc_mesh(3, ppd=50), (4, 1)),
+    ("ladder64", w.rc_ladder(64, ppd=50), (2, 1)), ("ladder400", w.rc_ladder(400, ppd=50), (2, 1)),
+    ("ladder3", w.rc_ladder(3, ppd=50), (2, 1))])
+def test_ac_band_tier_shapes(eng, name, text, shape):
+    """Every lanes x rows-per-lane shape the plan picks: narrow bands use fewer lanes per system."""
+    import spicey_b200 as sp
+    ck = parse_netlist(text)
+    stp = native.band_plan_stats(sp.packing.pack_circuit(ck), 300.0)
+    assert (stp["lanes"], stp["rows_per_lane"]) == shape, stp
+    freqs = np.array(sp.analysis.ac_frequencies(ck))
+    for flags in (BAND, BAND | SM):
+        out, x, ie, st, _ = ac_case(eng, text, freqs, flags)
+        assert eng.stats()["tier"] == native.TIER_BAND, eng.stats()
+        assert out["status"].max() == 0 and st.max() == 0
+        assert rel_err(out["x"], x) <= AC_TOL, (name, rel_err(out["x"], x))
+        assert rel_err(out["ielem"], ie) <= AC_TOL
+
+
+@pytest.mark.parametrize("shape", ["16,1", "32,1", "4,4", "16,2"])
+def test_ac_band_tier_forced_shapes_mesh16(shape, monkeypatch):
+    """The same mesh with other lane / row splits of the window (SPICEY_BAND_SHAPE): 16 x 1, 32 x 1 (window 32), 4 x 4."""
+    import spicey_b200 as sp
+    monkeypatch.setenv("SPICEY_BAND_SHAPE", shape)
+    e = native.Engine()
+    try:
+        ck = parse_netlist(w.rc_mesh(16))
+        freqs = np.ascontiguousarray(np.array(sp.analysis.ac_frequencies(ck))[::40001])
+        out = sp.simulate_ac_batch(ck, freqs, engine=e, flags=BAND)
+        stt = e.stats()
+        if stt["tier"] != native.TIER_BAND:
+            pytest.skip("shape %s does not fit the register file / shared memory: %s" % (shape, stt))
+        x, ie, st = co.ac_solve(ck, freqs, nthreads=8)
+        assert out["status"].max() == 0 and stt["fallback_solves"] == 0
+        assert rel_err(out["x"][0], x) <= AC_TOL and rel_err(out["ielem"][0], ie) <= AC_TOL
+    finally:
+        e.close()
+
+
+def test_ac_band_tier_pivot_changes_fall_back(eng):
+    """An RLC ladder with two sources swept over seven decades: the pivot order of the pilot point does not hold
+    everywhere, those points go to the dense kernel; statuses and values equal the oracle's either way."""
+    import spicey_b200 as sp
+    lines = ["* rlc ladder", "v1 n1 0 ac 1", "v2 n40 n39 ac 0.5 30"]
+    for k in range(1, 60):
+        lines.append("r%d n%d n%d %g" % (k, k, k + 1, 50 + 7 * (k % 5)))
+        lines.append("l%d n%d n%d %g" % (k, k, k + 2 if k + 2 <= 60 else 0, 1e-3 * (1 + k % 3)))
+        lines.append("c%d n%d 0 %g" % (k, k + 1, 1e-8 * (1 + k % 4)))
+    lines += [".ac dec 40 1 10meg", ".end"]
+    text = "\n".join(lines) + "\n"
+    freqs = np.array(sp.analysis.ac_frequencies(parse_netlist(text)))
+    out, x, ie, st, _ = ac_case(eng, text, freqs, BAND)
+    stt = eng.stats()
+    assert stt["tier"] == native.TIER_BAND, stt
+    assert np.array_equal(out["status"], st) and st.max() == 0
+    scale = np.max(np.abs(x), axis=2, keepdims=True)
+    assert np.max(np.abs(out["x"] - x) / scale) <= AC_TOL
+    iscale = np.max(np.abs(ie), axis=2, keepdims=True)
+    assert np.max(np.abs(out["ielem"] - ie) / iscale) <= AC_TOL
+    assert 0 < stt["fallback_solves"] < freqs.shape[0], stt
+
+
 def test_long_ladder_default_policy(eng):
     """A 400-node ladder (Nvar = 401, 3,200 points): chain-like, so the warp tier declines (2-3 updates per row
     would idle the lanes), and 801 values cross into the back-substitution, far more than a thread's registers
-    and shared memory hold, so the compiled tier declines even when asked for: the thread-per-system program runs."""
+    and shared memory hold, so the straight-line compiled tier declines: small batches run the thread-per-system
+    program, and when a compiled kernel is asked for (or the sweep has >= 200,000 points) the banded tier takes it
+    with two lanes per system (half-bandwidth 1)."""
     import spicey_b200 as sp
     ck = parse_netlist(w.rc_ladder(400, ppd=640))
     freqs = np.array(sp.analysis.ac_frequencies(ck))[:3200]
     xr, ier, st = co.ac_solve(ck, freqs[::50], nthreads=8)
-    for flags, tier in ((SM, native.TIER_SPARSE), (SM | native.FLAG_SPARSE | native.FLAG_JIT, native.TIER_SPARSE)):
+    for flags, tier in ((SM, native.TIER_SPARSE), (SM | native.FLAG_SPARSE | native.FLAG_JIT, native.TIER_BAND)):
         out = sp.simulate_ac_batch(ck, freqs, engine=eng, flags=flags)
         assert eng.stats()["tier"] == tier, (flags, eng.stats())
         assert out["status"].max() == 0
