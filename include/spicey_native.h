@@ -298,7 +298,8 @@ int32_t spicey_debug_warp_stats(const spicey_elem_table* table, double pilot_f, 
  * mask, workspace values per system.  SPICEY_ERR_UNSUPPORTED when the circuit does not qualify. */
 int32_t spicey_debug_band_stats(const spicey_elem_table* table, double pilot_f, int32_t* out);
 
-/* Tooling (no device needed): the CUDA source NVRTC compiles for one band shape; returns the size needed. */
+/* Tooling (no device needed): the CUDA source NVRTC compiles for one band shape; returns the size needed.
+ * abmask: bits 0-15 active border columns of band rows, bit 16: (alpha, beta)-only tables (RC circuits). */
 int64_t spicey_debug_band_source(int32_t L, int32_t RPL, int32_t NB, uint32_t abmask, int32_t with_ielem, int32_t warps,
                                  int32_t minb, char* buf, int64_t cap);
 

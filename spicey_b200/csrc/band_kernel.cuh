@@ -15,6 +15,8 @@
 //   BAND_ABMASK   bit j set: border column j has structural non-zeros in band rows (the right-hand side always has)
 //   BAND_IELEM    1: element currents are computed and stored
 //   BAND_WARPS    warps per CTA,  BAND_MINB  CTAs per SM (launch bounds)
+//   BAND_RC       1: tables hold (alpha, beta) only (no inductors, real source phasors)
+//   BAND_SYNC     1: the warps of a CTA meet at a barrier once per W steps (instruction-cache locality)
 //
 // Mapping.  One group of L lanes owns one system.  Pivot step k (column k, pivot row k of the pilot's order) touches
 // the W rows k+1 .. k+W: row i lives in lane i mod L, row slot (i / L) mod RPL, as W band entries (column c in
@@ -27,7 +29,9 @@
 // U (the pivot rows), 1/u_kk and the eliminated right-hand side go to a per-group global workspace, written once,
 // column-major in the band so that the column-oriented back-substitution reads one contiguous 16*W bytes per
 // unknown.  Stamped values (simulateAC.ts:24-60) are delivered from per-topology tables of (alpha, Im J, beta, gamma)
-// constants, value = alpha + j (w beta - gamma / w + Im J), where the window first needs them.
+// constants, value = alpha + j (w beta - gamma / w + Im J), where the window first needs them: one record per step,
+// staged into a per-warp ring in shared memory with cp.async two steps ahead (the tables are the same for every system
+// but stream through: nothing would keep them in L1), so that no instruction of a step waits on L2.
 //
 // Pivoting.  The pilot (band_plan.h) ran the reference's rule (solveComplex.ts:18-28: largest |a_ik|, first maximum
 // wins, row swap) on one representative point; every system re-checks every step on its own numbers — every
@@ -39,9 +43,26 @@
 #error "define BAND_L, BAND_RPL, BAND_NB, BAND_ABMASK, BAND_IELEM, BAND_WARPS, BAND_MINB"
 #endif
 
+#ifndef BAND_RC
+#define BAND_RC 0
+#endif
+#ifndef BAND_SYNC
+#define BAND_SYNC 1
+#endif
 #define BW (BAND_L * BAND_RPL)
 #define BNB BAND_NB
 #define BPS (BW + BNB + 2)          /* pivot record: W band entries | NB border columns | rhs | diagonal */
+// per-step record of the stamp tables (entries): new column [W] | column k+1 [W] | entering row: entry (k+W, k),
+// border columns + rhs [NB+1] | border rows' new column [NB]; padded to a multiple of 8 entries
+#define BST_NC 0
+#define BST_LC BW
+#define BST_E0 (2 * BW)
+#define BST_ERB (2 * BW + 1)
+#define BST_BRD (2 * BW + 1 + BNB + 1)
+#define BST_FLAGS (2 * BW + 2 * BNB + 2)   /* tie-rule masks of the step, as the bits of the entry's first double */
+#define BST_STRIDE ((2 * BW + 2 * BNB + 3 + 7) / 8 * 8)
+#define BRING 4                       /* records in flight per warp */
+#define BREC (BAND_RC ? 1 : 2)      /* double2 per table entry */
 #define BGPW (32 / BAND_L)           /* systems per warp */
 #define B_EPS 1e-15
 #define B_THR 1e-30
@@ -55,11 +76,11 @@ struct BandArgs {   // must match BandArgs in spicey_native.cu
   const double2* tab;                   // recipe tables, two double2 per entry: (alpha, Im J), (beta, gamma)
   const uint2* flags;                   // [n] strict-compare masks: .x window positions, .y border rows
   const int* newvar;                    // [n] original variable -> index in the elimination order
-  const int2* el_idx;                   // [n_ac_elem] elimination-order indices of the element's nodes (-1 = ground)
-  const double *el_a, *el_b, *el_g;     // element admittance constants
+  const double4* el_rec;                // [n_ac_elem] {bits of (i1, i2), ya, yb, yg}: current = Y (x[i1] - x[i2]),
+                                        // Y = ya + j (w yb - yg / w); i = n: the zero slot (ground); V: (branch, n, 1, 0, 0)
   const double* ind_L;
   int n, nb, n_ac_elem, v_first, n_ind;
-  int o_init, o_initb, o_nc, o_lc, o_e0, o_erb, o_brd0, o_brdnc, o_bb0;   // table offsets (entries)
+  int o_init, o_initb, o_brd0, o_bb0, o_step;   // table offsets (entries); o_step: record of step 0
 };
 
 typedef double2 bcplx;
@@ -79,11 +100,43 @@ __device__ __forceinline__ bcplx band_submul(bcplx a, bcplx f, bcplx p) {
   return make_double2(fma(-f.x, p.x, fma(f.y, p.y, a.x)), fma(-f.x, p.y, fma(-f.y, p.x, a.y)));
 }
 __device__ __forceinline__ double band_mag(bcplx a) { return fma(a.x, a.x, a.y * a.y); }
+// x = 0 in the lanes where p holds: one predicated 64-bit move, no branch (the compiler's own choice for a
+// conditional block of 32 assignments was a divergent region of ~100 moves)
+__device__ __forceinline__ void band_zero_if(bool p, double& x) {
+  asm("{\n\t.reg .pred q;\n\tsetp.ne.s32 q, %1, 0;\n\t@q mov.f64 %0, 0d0000000000000000;\n\t}" : "+d"(x) : "r"((int)p));
+}
 
 // stamped value of a table entry at angular frequency w (simulateAC.ts:36-57)
+// BAND_RC: every entry of the circuit is (alpha, w beta) — no inductors, real source phasors — and the tables hold
+// one double2 (alpha, beta) per entry
 __device__ __forceinline__ bcplx band_rec(const double2* t, int idx, double w, double iw) {
+#if BAND_RC
+  const double2 c = __ldg(t + idx);
+  return make_double2(c.x, w * c.y);
+#else
   const double2 c0 = __ldg(t + 2 * idx), c1 = __ldg(t + 2 * idx + 1);
   return make_double2(c0.x, fma(w, c1.x, -c1.y * iw) + c0.y);
+#endif
+}
+// the same from a staged record in shared memory
+__device__ __forceinline__ bcplx band_rec_sm(const double2* t, int idx, double w, double iw) {
+#if BAND_RC
+  const double2 c = t[idx];
+  return make_double2(c.x, w * c.y);
+#else
+  const double2 c0 = t[2 * idx], c1 = t[2 * idx + 1];
+  return make_double2(c0.x, fma(w, c1.x, -c1.y * iw) + c0.y);
+#endif
+}
+// one step record, global -> this warp's ring slot (16 bytes per lane and instruction), as one cp.async group
+__device__ __forceinline__ void band_stage(double2* dst, const double2* src, int lane) {
+#pragma unroll
+  for (int i = 0; i < BST_STRIDE * BREC; i += 32)
+    if (i + lane < BST_STRIDE * BREC) {
+      const unsigned d = (unsigned)__cvta_generic_to_shared(dst + i + lane);
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(src + i + lane) : "memory");
+    }
+  asm volatile("cp.async.commit_group;" ::: "memory");
 }
 
 extern __shared__ double2 band_sm[];
@@ -91,13 +144,20 @@ extern __shared__ double2 band_sm[];
 extern "C" __global__ void __launch_bounds__(BAND_WARPS * 32, BAND_MINB) spicey_band_jit(BandArgs a) {
   const unsigned FULL = 0xffffffffu;
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-  const int l = lane & (BAND_L - 1);          // lane within the group
-  const int g = lane / BAND_L;                // group within the warp
+  // The groups of a warp are interleaved: lane = l * (32 / L) + g.  The owners of one row in the 32 / L systems of a
+  // warp are then neighbouring lanes, and the store that publishes a pivot-row entry is one shared-memory wavefront
+  // instead of one per group (a 128-bit access is processed a quarter-warp at a time).
+  const int g = lane % BGPW;                  // group (system) within the warp
+  const int l = lane / BGPW;                  // lane within the group
   const int n = a.n, nb = a.nb;
-  // shared memory of this group: x in elimination order | two pivot records
-  const int sys_stride = n + 2 * BPS;
-  double2* xs = band_sm + (size_t)(wib * BGPW + g) * sys_stride;
-  double2* Pb = xs + n;
+  // shared memory: per warp a ring of BRING step records; per group x in elimination order | two pivot records
+  double2* ring = band_sm + (size_t)wib * (BRING * BST_STRIDE * BREC);
+  // x[n] is a zero (the ground node of the element records).  The stride is odd (in 16-byte units): the systems of a
+  // warp read and write the same offsets of their areas in one instruction, and an odd stride puts up to eight of
+  // them on eight different 16-byte bank groups (an even stride of 296 units made every access a 4-way conflict)
+  const int sys_stride = (n + 1 + 2 * BPS) | 1;
+  double2* xs = band_sm + (size_t)BAND_WARPS * (BRING * BST_STRIDE * BREC) + (size_t)(wib * BGPW + g) * sys_stride;
+  double2* Pb = xs + n + 1;
   const long long n_groups = (long long)gridDim.x * BAND_WARPS * BGPW;
   const long long grp = ((long long)blockIdx.x * BAND_WARPS + wib) * BGPW + g;
   double2* Gu = a.G + grp * a.g_stride;                 // [(nb + W) columns][W]
@@ -109,18 +169,26 @@ extern "C" __global__ void __launch_bounds__(BAND_WARPS * 32, BAND_MINB) spicey_
   // zeros by the back-substitution and never written by anybody, so one fill per launch is enough.
   for (int q = l; q < BW * BW; q += BAND_L) Gu[q] = make_double2(0.0, 0.0);
   for (int q = l; q < 2 * BPS; q += BAND_L) Pb[q] = make_double2(0.0, 0.0);
+  if (l == 0) xs[n] = make_double2(0.0, 0.0);
   __syncwarp();
 
-  for (long long base = ((long long)blockIdx.x * BAND_WARPS + wib) * BGPW; base < a.p_count; base += n_groups) {
+  // CTA-uniform trip count (the warps of a CTA meet at a barrier inside): groups past the end solve the last point
+  // again and store nothing
+  for (long long cta_base = (long long)blockIdx.x * BAND_WARPS * BGPW; cta_base < a.p_count; cta_base += n_groups) {
+    const long long base = cta_base + wib * BGPW;
     const bool valid = base + g < a.p_count;
     const long long p = valid ? base + g : a.p_count - 1;
     const double w = B_TWO_PI * a.freqs[p];
     const double iw = 1.0 / w;
 #define REC(idx) band_rec(tab, (idx), w, iw)
-    bool bad = false;
+    const double2* steps = tab + (size_t)a.o_step * BREC;
+    __syncwarp();   // the previous system is done with the ring
+    band_stage(ring, steps, lane);
+    band_stage(ring + BST_STRIDE * BREC, steps + (size_t)BST_STRIDE * BREC, lane);
+    unsigned bad = 0u;   // any verification of this lane failed (kept branch-free: OR of predicates)
     for (int q = l; q < a.n_ind; q += BAND_L) {   // inductor guards of simulateAC.ts:47-51: the dense kernel decides
       const double d = w * a.ind_L[q];
-      bad = bad || (fabs(d) < B_EPS || d * d < B_EPS);
+      bad |= (unsigned)(fabs(d) < B_EPS) | (unsigned)(d * d < B_EPS);
     }
 
     bcplx A[BAND_RPL][BW];            // band entries of my rows, slot = column mod W
@@ -152,7 +220,7 @@ extern "C" __global__ void __launch_bounds__(BAND_WARPS * 32, BAND_MINB) spicey_
       P0[BW + BNB + 1] = A[0][0];
 #pragma unroll
       for (int t = 1; t < BW; ++t) P0[t] = A[0][t];
-      P0[0] = REC(a.o_nc + 0);          // a[0][W]: column W enters with step 0
+      P0[0] = REC(a.o_step + BST_NC + 0);          // a[0][W]: column W enters with step 0
 #pragma unroll
       for (int j = 0; j <= BNB; ++j)
         if (j == BNB || ((BAND_ABMASK >> j) & 1)) P0[BW + j] = AB[0][j];
@@ -161,6 +229,12 @@ extern "C" __global__ void __launch_bounds__(BAND_WARPS * 32, BAND_MINB) spicey_
 
     // ---- elimination of the band columns ----
     for (int kb = 0; kb < nb; kb += BW) {
+#if BAND_SYNC
+      // The unrolled body is several times the instruction cache: warps that run different parts of it evict each
+      // other's lines (25 % of the stall samples were instruction fetch).  Meeting once per W steps keeps them on
+      // the same lines without putting them in lock step.
+      __syncthreads();
+#endif
 #pragma unroll
       for (int s = 0; s < BW; ++s) {
         const int k = kb + s;
@@ -169,10 +243,18 @@ extern "C" __global__ void __launch_bounds__(BAND_WARPS * 32, BAND_MINB) spicey_
           const int s1 = (s + 1) % BW, pl1 = s1 % BAND_L, rs1 = s1 / BAND_L;
           const double2* Pc = Pb + (s & 1) * BPS;                  // W is even: the parity of k is the parity of s
           double2* Pn = Pb + ((s + 1) & 1) * BPS;
-          const uint2 fl = __ldg(a.flags + k);
+          // records k and k + 1 have landed (all but the newest cp.async group), record k + 2 leaves now; the barrier
+          // also publishes the pivot record written at the end of the previous step
+          band_stage(ring + ((k + 2) & (BRING - 1)) * (BST_STRIDE * BREC), steps + (size_t)(k + 2) * (BST_STRIDE * BREC), lane);
+          asm volatile("cp.async.wait_group 1;" ::: "memory");
+          __syncwarp();
+          const double2* rk = ring + (k & (BRING - 1)) * (BST_STRIDE * BREC);
+          const double2* rk1 = ring + ((k + 1) & (BRING - 1)) * (BST_STRIDE * BREC);
+#define RECS(off) band_rec_sm(rk, (off), w, iw)
+          const uint2 fl = *(const uint2*)(rk + BST_FLAGS * BREC);
           const bcplx dg = Pc[BW + BNB + 1];
           const double mp = band_mag(dg);
-          bad = bad || !(mp >= B_EPS);            // singular / Complex.div guard / NaN
+          bad |= (unsigned)!(mp >= B_EPS);            // singular / Complex.div guard / NaN
           const double inv = band_rcp(mp);
           const bcplx r = make_double2(dg.x * inv, -dg.y * inv);
           // multipliers of my rows; the new column k + W takes over the slot of column k
@@ -180,20 +262,22 @@ extern "C" __global__ void __launch_bounds__(BAND_WARPS * 32, BAND_MINB) spicey_
 #pragma unroll
           for (int q = 0; q < BAND_RPL; ++q) {
             bcplx aik = A[q][s];
-            A[q][s] = REC(a.o_nc + k * BW + l + BAND_L * q);
-            if (q == rs && l == pl) {   // the pivot row's registers become the entering row k + W (zero so far)
-              aik = REC(a.o_e0 + k);
+            A[q][s] = RECS(BST_NC + l + BAND_L * q);
+            if (q == rs) {   // in lane pl the pivot row's registers become the entering row k + W (zero so far)
+              const bool own = l == pl;
+              const bcplx e0 = RECS(BST_E0);
+              aik = own ? e0 : aik;
 #pragma unroll
-              for (int t = 0; t < BW; ++t) A[q][t] = make_double2(0.0, 0.0);
+              for (int t = 0; t < BW; ++t) { band_zero_if(own, A[q][t].x); band_zero_if(own, A[q][t].y); }
 #pragma unroll
               for (int j = 0; j <= BNB; ++j)
-                if (j == BNB || ((BAND_ABMASK >> j) & 1)) AB[q][j] = REC(a.o_erb + k * (BNB + 1) + j);
+                if (j == BNB || ((BAND_ABMASK >> j) & 1)) { const bcplx eb = RECS(BST_ERB + j); AB[q][j] = own ? eb : AB[q][j]; }
             }
             // column k + 1: diagonal and lower entries of the rows k+1 .. k+W arrive one step before they are read
-            { const bcplx lc = REC(a.o_lc + k * BW + l + BAND_L * q); A[q][s1].x += lc.x; A[q][s1].y += lc.y; }
+            { const bcplx lc = RECS(BST_LC + l + BAND_L * q); A[q][s1].x += lc.x; A[q][s1].y += lc.y; }
             const double m = band_mag(aik);
             const bool strict = (fl.x >> (l + BAND_L * q)) & 1u;
-            bad = bad || (strict ? !(m < mp) : (m > mp));          // solveComplex.ts:18-28: first maximum wins
+            bad |= strict ? (unsigned)!(m < mp) : (unsigned)(m > mp);          // solveComplex.ts:18-28: first maximum wins
             bcplx f = band_mul(aik, r);
             if (band_mag(f) < B_THR) f = make_double2(0.0, 0.0);   // solveComplex.ts:46
             F[q] = f;
@@ -206,12 +290,12 @@ extern "C" __global__ void __launch_bounds__(BAND_WARPS * 32, BAND_MINB) spicey_
             const double m = band_mag(bk);
             if (l == pl) {
               const bool strict = (fl.y >> b) & 1u;
-              bad = bad || (strict ? !(m < mp) : (m > mp));
-              BR[b][rs] = REC(a.o_brdnc + k * BNB + b);
+              bad |= strict ? (unsigned)!(m < mp) : (unsigned)(m > mp);
+              BR[b][rs] = RECS(BST_BRD + b);
             }
             bcplx f = band_mul(bk, r);
-            f.x = __shfl_sync(FULL, f.x, pl, BAND_L);
-            f.y = __shfl_sync(FULL, f.y, pl, BAND_L);
+            f.x = __shfl_sync(FULL, f.x, pl * BGPW + g);
+            f.y = __shfl_sync(FULL, f.y, pl * BGPW + g);
             if (band_mag(f) < B_THR) f = make_double2(0.0, 0.0);
             FB[b] = f;
           }
@@ -239,13 +323,13 @@ extern "C" __global__ void __launch_bounds__(BAND_WARPS * 32, BAND_MINB) spicey_
 #pragma unroll
             for (int b = 0; b < BNB; ++b) BR[b][q] = band_submul(BR[b][q], FB[b], pt);
             const int c = k + 1 + ((slot - s - 1) & (BW - 1));
-            Gu[(size_t)c * BW + s] = pt;
+            __stcg(Gu + (size_t)c * BW + s, pt);
           }
           if (l == pl) {
-            Gr[k] = r;
+            __stcg(Gr + k, r);
 #pragma unroll
             for (int j = 0; j <= BNB; ++j)
-              if (j == BNB || ((BAND_ABMASK >> j) & 1)) Gb[(size_t)k * (BNB + 1) + j] = Pc[BW + j];
+              if (j == BNB || ((BAND_ABMASK >> j) & 1)) __stcg(Gb + (size_t)k * (BNB + 1) + j, Pc[BW + j]);
           }
           // row k + 1 is final: its owner publishes it as the next pivot record
           if (l == pl1) {
@@ -253,15 +337,16 @@ extern "C" __global__ void __launch_bounds__(BAND_WARPS * 32, BAND_MINB) spicey_
 #pragma unroll
             for (int t = 0; t < BW; ++t)
               if (t != s1) Pn[t] = A[rs1][t];
-            Pn[s1] = REC(a.o_nc + (k + 1) * BW + s1);    // a[k+1][k+1+W]
+            Pn[s1] = band_rec_sm(rk1, BST_NC + s1, w, iw);    // a[k+1][k+1+W]
 #pragma unroll
             for (int j = 0; j <= BNB; ++j)
               if (j == BNB || ((BAND_ABMASK >> j) & 1)) Pn[BW + j] = AB[rs1][j];
           }
-          __syncwarp();
+#undef RECS
         }
       }
     }
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
 
     // ---- the border block: NB x NB, replicated; same verification ----
     bcplx RB[BNB > 0 ? BNB : 1];
@@ -269,14 +354,14 @@ extern "C" __global__ void __launch_bounds__(BAND_WARPS * 32, BAND_MINB) spicey_
     for (int b = 0; b < BNB; ++b) {
       const uint2 fl = __ldg(a.flags + nb + b);
       const double mp = band_mag(BB[b][b]);
-      bad = bad || !(mp >= B_EPS);
+      bad |= (unsigned)!(mp >= B_EPS);
       const double inv = band_rcp(mp);
       RB[b] = make_double2(BB[b][b].x * inv, -BB[b][b].y * inv);
 #pragma unroll
       for (int b2 = b + 1; b2 < BNB; ++b2) {
         const double m = band_mag(BB[b2][b]);
         const bool strict = (fl.y >> b2) & 1u;
-        bad = bad || (strict ? !(m < mp) : (m > mp));
+        bad |= strict ? (unsigned)!(m < mp) : (unsigned)(m > mp);
         bcplx f = band_mul(BB[b2][b], RB[b]);
         if (band_mag(f) < B_THR) f = make_double2(0.0, 0.0);
 #pragma unroll
@@ -296,10 +381,10 @@ extern "C" __global__ void __launch_bounds__(BAND_WARPS * 32, BAND_MINB) spicey_
     // ---- back-substitution, column oriented: x_j by its owner, then every row of column j takes its term ----
     // row i: lane i mod L, slot (i / L) mod RPL, accumulator = b_i - sum over the border columns - sum_j u_ij x_j
     auto row_rhs = [&](int i) -> bcplx {
-      bcplx acc = Gb[(size_t)i * (BNB + 1) + BNB];
+      bcplx acc = __ldcg(Gb + (size_t)i * (BNB + 1) + BNB);
 #pragma unroll
       for (int j = 0; j < BNB; ++j)
-        if ((BAND_ABMASK >> j) & 1) acc = band_submul(acc, Gb[(size_t)i * (BNB + 1) + j], XB[j]);
+        if ((BAND_ABMASK >> j) & 1) acc = band_submul(acc, __ldcg(Gb + (size_t)i * (BNB + 1) + j), XB[j]);
       return acc;
     };
     bcplx ACC[BAND_RPL];
@@ -309,66 +394,102 @@ extern "C" __global__ void __launch_bounds__(BAND_WARPS * 32, BAND_MINB) spicey_
       const int i = nb - 1 - ((nb - 1 - slot) & (BW - 1));    // the row = slot (mod W) among nb-W .. nb-1
       ACC[q] = i >= 0 ? row_rhs(i) : make_double2(0.0, 0.0);
     }
-    for (int jb = (nb - 1) / BW * BW; jb >= 0; jb -= BW) {
-      // One batch of loads in front of BW dependent steps: the block's U columns, and — for the steps this lane owns
-      // (s = l + L q) — the reciprocal of the pivot and the accumulator of the row that enters there.
-      bcplx U[BW][BAND_RPL];
-      bcplx RJ[BAND_RPL], ENT[BAND_RPL];
-#pragma unroll
-      for (int s = 0; s < BW; ++s) {
-#pragma unroll
-        for (int q = 0; q < BAND_RPL; ++q) U[s][q] = Gu[(size_t)(jb + s) * BW + l + BAND_L * q];   // jb + s < nb + W
+    // Software pipeline over half blocks of BH = W / 2 steps: the U columns of the next half block (and, once per
+    // block, the reciprocals and entering-row accumulators of the steps this lane owns, s = l + L q) are loaded while
+    // the current half block runs its dependent chain, so the chain never waits for the workspace (which sits in L2 or DRAM).
+    {
+      constexpr int BH = BW / 2;
+      bcplx Ua[BH][BAND_RPL], Ub[BH][BAND_RPL];
+      bcplx RJ[BAND_RPL], ENT[BAND_RPL], RJn[BAND_RPL], ENTn[BAND_RPL];
+#define BAND_LOAD_U(U, j0)                                                                                   \
+      _Pragma("unroll") for (int s_ = 0; s_ < BH; ++s_)                                                      \
+        _Pragma("unroll") for (int q = 0; q < BAND_RPL; ++q) U[s_][q] = __ldcg(Gu + (size_t)((j0) + s_) * BW + l + BAND_L * q);
+#define BAND_LOAD_RE(R, E, jb_)                                                                              \
+      _Pragma("unroll") for (int q = 0; q < BAND_RPL; ++q) {                                                 \
+        const int j = (jb_) + l + BAND_L * q;                                                                \
+        R[q] = j < nb ? __ldcg(Gr + j) : make_double2(0.0, 0.0);                                             \
+        E[q] = (j < nb && j - BW >= 0) ? row_rhs(j - BW) : make_double2(0.0, 0.0);                           \
       }
-#pragma unroll
-      for (int q = 0; q < BAND_RPL; ++q) {
-        const int j = jb + l + BAND_L * q;
-        RJ[q] = j < nb ? Gr[j] : make_double2(0.0, 0.0);
-        ENT[q] = (j < nb && j - BW >= 0) ? row_rhs(j - BW) : make_double2(0.0, 0.0);
+#define BAND_BSTEP(s, uv)                                                                                    \
+      {                                                                                                      \
+        const int j = jb + (s);                                                                              \
+        if (j < nb) {                                                                                        \
+          const int pl = (s) % BAND_L, rs = (s) / BAND_L;                                                    \
+          bcplx xj = band_mul(ACC[rs], RJ[rs]);                                                              \
+          xj.x = __shfl_sync(FULL, xj.x, pl * BGPW + g);                                                     \
+          xj.y = __shfl_sync(FULL, xj.y, pl * BGPW + g);                                                     \
+          if (l == pl) {                                                                                     \
+            xs[j] = xj;                                                                                      \
+            ACC[rs] = ENT[rs];   /* row j - W enters */                                                      \
+          }                                                                                                  \
+          _Pragma("unroll") for (int q = 0; q < BAND_RPL; ++q) ACC[q] = band_submul(ACC[q], uv[q], xj);      \
+        }                                                                                                    \
       }
+      int jb = (nb - 1) / BW * BW;
+      BAND_LOAD_U(Ua, jb + BH)   // jb + BH + s < nb + W: inside the workspace
+      BAND_LOAD_RE(RJ, ENT, jb)
+      for (; jb >= 0; jb -= BW) {
+        BAND_LOAD_U(Ub, jb)
 #pragma unroll
-      for (int s = BW - 1; s >= 0; --s) {
-        const int j = jb + s;
-        if (j < nb) {
-          const int pl = s % BAND_L, rs = s / BAND_L;
-          bcplx xj = band_mul(ACC[rs], RJ[rs]);
-          xj.x = __shfl_sync(FULL, xj.x, pl, BAND_L);
-          xj.y = __shfl_sync(FULL, xj.y, pl, BAND_L);
-          if (l == pl) {
-            xs[j] = xj;
-            ACC[rs] = ENT[rs];   // row j - W enters
-          }
-#pragma unroll
-          for (int q = 0; q < BAND_RPL; ++q) ACC[q] = band_submul(ACC[q], U[s][q], xj);
+        for (int s = BW - 1; s >= BH; --s) BAND_BSTEP(s, Ua[s - BH])
+        if (jb >= BW) {
+          BAND_LOAD_U(Ua, jb - BW + BH)
+          BAND_LOAD_RE(RJn, ENTn, jb - BW)
         }
+#pragma unroll
+        for (int s = BH - 1; s >= 0; --s) BAND_BSTEP(s, Ub[s])
+#pragma unroll
+        for (int q = 0; q < BAND_RPL; ++q) { RJ[q] = RJn[q]; ENT[q] = ENTn[q]; }
       }
+#undef BAND_LOAD_U
+#undef BAND_LOAD_RE
+#undef BAND_BSTEP
     }
     __syncwarp();
 
     // ---- status, results (simulateAC.ts:85-126) ----
-    const unsigned vote = __ballot_sync(FULL, bad);
-    const unsigned gmask = BAND_L == 32 ? FULL : (((1u << BAND_L) - 1u) << (g * BAND_L));
+    const unsigned vote = __ballot_sync(FULL, bad != 0u);
+    unsigned gmask = 0u;   // the lanes of my group: g, g + 32 / L, ...
+#pragma unroll
+    for (int q = 0; q < BAND_L; ++q) gmask |= 1u << (q * BGPW + g);
     const bool good = (vote & gmask) == 0u;
     if (valid) {
       if (l == 0) {
         a.status[p] = good ? 0 : -1;
         if (!good) a.fb_list[atomicAdd(a.fb_count, 1)] = p;
       }
+      // four independent loads in flight per lane: the index / constant tables are read through L2 behind the
+      // workspace traffic, and one dependent load per iteration was 5 % of the kernel
       const long long xst = a.series_ld ? a.series_ld : 1;
       double2* xo = a.series_ld ? a.x + p : a.x + p * n;
-      for (int i = l; i < n; i += BAND_L) xo[(long long)i * xst] = xs[__ldg(a.newvar + i)];
+      for (int i0 = l; i0 < n; i0 += 4 * BAND_L) {
+        int idx[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) idx[u] = i0 + u * BAND_L < n ? __ldg(a.newvar + i0 + u * BAND_L) : n;
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+          if (i0 + u * BAND_L < n) xo[(long long)(i0 + u * BAND_L) * xst] = xs[idx[u]];
+      }
 #if BAND_IELEM
       double2* io = a.series_ld ? a.ielem + p : a.ielem + p * a.n_ac_elem;
-      for (int e = l; e < a.n_ac_elem; e += BAND_L) {
-        bcplx cur;
-        if (e >= a.v_first) cur = xs[nb + e - a.v_first];
-        else {
-          const int2 en = __ldg(a.el_idx + e);
-          const bcplx v1 = en.x >= 0 ? xs[en.x] : make_double2(0.0, 0.0);
-          const bcplx v2 = en.y >= 0 ? xs[en.y] : make_double2(0.0, 0.0);
-          const bcplx Y = make_double2(__ldg(a.el_a + e), fma(w, __ldg(a.el_b + e), -__ldg(a.el_g + e) * iw));
-          cur = band_mul(Y, make_double2(v1.x - v2.x, v1.y - v2.y));
+      const int ne = a.n_ac_elem;
+      for (int e0 = l; e0 < ne; e0 += 4 * BAND_L) {
+        double4 er[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int e = min(e0 + u * BAND_L, ne - 1);
+          const double2 lo = __ldg((const double2*)(a.el_rec + e)), hi = __ldg((const double2*)(a.el_rec + e) + 1);
+          er[u] = make_double4(lo.x, lo.y, hi.x, hi.y);
         }
-        io[(long long)e * xst] = cur;
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int e = e0 + u * BAND_L;
+          const long long ij = __double_as_longlong(er[u].x);
+          const bcplx v1 = xs[(int)(ij & 0xffffffffll)], v2 = xs[(int)(ij >> 32)];
+          const bcplx Y = make_double2(er[u].y, fma(w, er[u].z, -er[u].w * iw));
+          const bcplx cur = band_mul(Y, make_double2(v1.x - v2.x, v1.y - v2.y));
+          if (e < ne) io[(long long)e * xst] = cur;
+        }
       }
 #endif
     }

@@ -22,6 +22,7 @@
 #include <cmath>
 #include <complex>
 #include <cstdint>
+#include <cstring>
 #include <queue>
 #include <vector>
 
@@ -50,7 +51,9 @@ struct BandPlan {
   std::vector<int> prow;                               // [n] pivot row (an ORIGINAL row index) of step k
   std::vector<BandRecipe> tab;
   std::vector<unsigned> flags;                         // [n][2]
-  int o_init = 0, o_initb = 0, o_nc = 0, o_lc = 0, o_e0 = 0, o_erb = 0, o_brd0 = 0, o_brdnc = 0, o_bb0 = 0;
+  int o_init = 0, o_initb = 0, o_brd0 = 0, o_bb0 = 0, o_step = 0;   // table offsets (entries)
+  int step_stride = 0;                                 // entries per step record (band_kernel.cuh: BST_*)
+  bool rc_only = false;                                // no entry has a gamma (inductor) or Im J term: (alpha, beta) tables
   long long g_stride = 0;                              // workspace per system, complex values
   long long n_cfma = 0;                                // complex FMAs the kernel executes per system (dense band)
 };
@@ -241,26 +244,34 @@ inline void build_band_plan_for_order(const BandInput& in, const std::vector<int
   bp.o_initb = (int)T.size();
   for (int i = 0; i < W; ++i)
     for (int j = 0; j <= NB; ++j) T.push_back(rec(i, bcol(j)));
-  bp.o_nc = (int)T.size();       // step k, position t: entry of column k + W in the row = t (mod W) of k .. k+W-1
-  for (int k = 0; k <= nb; ++k)
-    for (int t = 0; t < W; ++t) T.push_back(k + W < nb ? rec(row_at(t, k), k + W) : zero);
-  bp.o_lc = (int)T.size();       // step k, position t: entry of column k + 1 in the row = t (mod W) of k+1 .. k+W
-  for (int k = 0; k <= nb; ++k)
-    for (int t = 0; t < W; ++t) T.push_back(k + 1 < nb ? rec(row_at(t, k + 1), k + 1) : zero);
-  bp.o_e0 = (int)T.size();       // step k: entry (k + W, k) of the entering row
-  for (int k = 0; k <= nb; ++k) T.push_back(k < nb ? rec(k + W, k) : zero);
-  bp.o_erb = (int)T.size();      // step k: border columns / rhs of the entering row
-  for (int k = 0; k <= nb; ++k)
-    for (int j = 0; j <= NB; ++j) T.push_back(rec(k + W, bcol(j)));
   bp.o_brd0 = (int)T.size();
   for (int b = 0; b < NB; ++b)
     for (int c = 0; c < W; ++c) T.push_back(c < nb ? recb(b, c) : zero);
-  bp.o_brdnc = (int)T.size();
-  for (int k = 0; k <= nb; ++k)
-    for (int b = 0; b < NB; ++b) T.push_back(k + W < nb ? recb(b, k + W) : zero);
   bp.o_bb0 = (int)T.size();
   for (int b = 0; b < NB; ++b)
     for (int j = 0; j <= NB; ++j) T.push_back(recb(b, bcol(j)));
+  // One record per step (what step k delivers, contiguous: the kernel prefetches a record two steps ahead):
+  //   [0, W)        position t: entry of column k + W in the row = t (mod W) of k .. k+W-1 (above the diagonal)
+  //   [W, 2W)       position t: entry of column k + 1 in the row = t (mod W) of k+1 .. k+W (diagonal and below)
+  //   2W            entry (k + W, k) of the entering row
+  //   2W+1 ..       border columns / rhs of the entering row [NB + 1], then the border rows' entries of column k + W [NB]
+  // nb + 3 records: the publisher of step k reads record k + 1, the prefetch touches record k + 2.
+  while (T.size() % 8) T.push_back(zero);
+  bp.o_step = (int)T.size();
+  bp.step_stride = (2 * W + 2 * NB + 3 + 7) / 8 * 8;
+  const size_t first_record = T.size();
+  for (int k = 0; k < nb + 3; ++k) {
+    const size_t base = T.size();
+    for (int t = 0; t < W; ++t) T.push_back(k + W < nb ? rec(row_at(t, k), k + W) : zero);
+    for (int t = 0; t < W; ++t) T.push_back(k + 1 < nb ? rec(row_at(t, k + 1), k + 1) : zero);
+    T.push_back(k < nb ? rec(k + W, k) : zero);
+    for (int j = 0; j <= NB; ++j) T.push_back(rec(k + W, bcol(j)));
+    for (int b = 0; b < NB; ++b) T.push_back(k + W < nb ? recb(b, k + W) : zero);
+    T.push_back(zero);   // the tie-rule masks of the step (filled in below)
+    while (T.size() < base + (size_t)bp.step_stride) T.push_back(zero);
+  }
+  bp.rc_only = true;
+  for (const BandRecipe& q : T) if (q.jim != 0.0 || q.gamma != 0.0) { bp.rc_only = false; break; }
 
   // ---- tie rule: is the candidate scanned before the pilot's pivot? (solveComplex.ts:18-28, strict '>') ----
   bp.flags.assign((size_t)2 * n, 0u);
@@ -278,6 +289,13 @@ inline void build_band_plan_for_order(const BandInput& in, const std::vector<int
       for (int b = k - nb + 1; b < NB; ++b) if (wh[P.prow[nb + b]] < ppos) fy |= 1u << b;
     }
     bp.flags[2 * k] = fx; bp.flags[2 * k + 1] = fy;
+    if (k < nb) {   // the kernel reads the masks of a band step from the step's record
+      const unsigned long long bits = (unsigned long long)fx | ((unsigned long long)fy << 32);
+      double asd;
+      static_assert(sizeof asd == sizeof bits, "double is 64 bits");
+      memcpy(&asd, &bits, sizeof asd);
+      T[first_record + (size_t)k * bp.step_stride + 2 * W + 2 * NB + 2].alpha_jre = asd;
+    }
   }
   bp.g_stride = ((long long)(nb + W) * W + (long long)nb * (NB + 2) + 7) / 8 * 8;
   int nbc = 1;

@@ -115,7 +115,7 @@ struct DeviceCtx {
   uint64_t bp_key = 0;        // sparse-program key the band plan was built for (0 = none)
   bool bp_valid = false;
   Buffer bp_blob, bp_work;
-  struct BandDev { const void *tab, *flags, *newvar, *el_idx; } bp_dev = {nullptr, nullptr, nullptr, nullptr};
+  struct BandDev { const void *tab, *flags, *newvar, *el_rec; } bp_dev = {nullptr, nullptr, nullptr, nullptr};
   struct BandJit {
     cudaLibrary_t lib = nullptr;
     cudaKernel_t kernel = nullptr;
@@ -555,10 +555,10 @@ struct BandArgs {   // must match band_kernel.cuh
   double2* x; double2* ielem; int* status; long long series_ld;
   long long* fb_list; int* fb_count;
   double2* G; long long g_stride;
-  const double2* tab; const uint2* flags; const int* newvar; const int2* el_idx;
-  const double *el_a, *el_b, *el_g; const double* ind_L;
+  const double2* tab; const uint2* flags; const int* newvar; const double4* el_rec;
+  const double* ind_L;
   int n, nb, n_ac_elem, v_first, n_ind;
-  int o_init, o_initb, o_nc, o_lc, o_e0, o_erb, o_brd0, o_brdnc, o_bb0;
+  int o_init, o_initb, o_brd0, o_bb0, o_step;
 };
 
 constexpr int kBandMinBandwidth = 1;   // every banded + bordered circuit the thread-per-system compiled tier refuses
@@ -591,36 +591,63 @@ int prepare_band(DeviceCtx& ctx, const HostPlan& hp, cudaStream_t stream) {
   build_band_plan(in, ctx.bp, fl, fr);
   BandPlan& bp = ctx.bp;
   if (!bp.ok || bp.bandwidth < kBandMinBandwidth) return SPICEY_SUCCESS;
-  std::vector<int2> el_idx(std::max(1, hp.n_ac_elem));
+  // element records of the unpack phase: current = Y (x[i1] - x[i2]) in elimination-order indices, index n = the
+  // zero slot (ground); a V element's current is its branch unknown: (branch, zero slot, Y = 1)
+  std::vector<double4> el_idx(std::max(1, hp.n_ac_elem));
   for (int e = 0; e < hp.n_ac_elem; ++e) {
     const int n1 = hp.ends[e].x, n2 = hp.ends[e].y;
-    el_idx[e] = make_int2(n1 ? bp.newvar[n1 - 1] : -1, n2 ? bp.newvar[n2 - 1] : -1);
+    long long ij;
+    double4 r = make_double4(0.0, 0.0, 0.0, 0.0);
+    if (e >= hp.off[ELEM_V]) {
+      ij = (long long)(bp.nb + (e - hp.off[ELEM_V])) | ((long long)hp.nvar << 32);
+      r.y = 1.0;
+    } else {
+      ij = (long long)(n1 ? bp.newvar[n1 - 1] : hp.nvar) | ((long long)(n2 ? bp.newvar[n2 - 1] : hp.nvar) << 32);
+      r.y = ctx.sp.el_a[e]; r.z = ctx.sp.el_b[e]; r.w = ctx.sp.el_g[e];
+    }
+    memcpy(&r.x, &ij, sizeof ij);
+    el_idx[e] = r;
   }
   std::vector<unsigned char> blob;
-  const size_t o_tab = push_blob(blob, bp.tab), o_fl = push_blob(blob, bp.flags), o_nv = push_blob(blob, bp.newvar),
-               o_ei = push_blob(blob, el_idx);
+  size_t o_tab = 0;
+  if (bp.rc_only) {   // (alpha, beta) per entry: half the table bytes, one multiply per stamped value
+    std::vector<double2> packed(bp.tab.size());
+    for (size_t i = 0; i < bp.tab.size(); ++i) packed[i] = make_double2(bp.tab[i].alpha_jre, bp.tab[i].beta);
+    o_tab = push_blob(blob, packed);
+  } else {
+    o_tab = push_blob(blob, bp.tab);
+  }
+  while (blob.size() % 128) blob.push_back(0);   // step records start on 128-byte lines (the kernel prefetches by line)
+  const size_t o_fl = push_blob(blob, bp.flags), o_nv = push_blob(blob, bp.newvar), o_ei = push_blob(blob, el_idx);
   int rc = ctx.bp_blob.ensure(blob.size() + 16);
   if (rc) return rc;
   CUDA_TRY(cudaMemcpyAsync(ctx.bp_blob.p, blob.data(), blob.size(), cudaMemcpyHostToDevice, stream));
   CUDA_TRY(cudaStreamSynchronize(stream));
   unsigned char* b = (unsigned char*)ctx.bp_blob.p;
-  ctx.bp_dev.tab = b + o_tab; ctx.bp_dev.flags = b + o_fl; ctx.bp_dev.newvar = b + o_nv; ctx.bp_dev.el_idx = b + o_ei;
+  ctx.bp_dev.tab = b + o_tab; ctx.bp_dev.flags = b + o_fl; ctx.bp_dev.newvar = b + o_nv; ctx.bp_dev.el_rec = b + o_ei;
   ctx.bp_valid = true;
   return SPICEY_SUCCESS;
+}
+
+int band_sync_default() {
+  if (const char* e = getenv("SPICEY_BAND_SYNC")) return atoi(e) ? 1 : 0;   // experiments
+  return 1;
 }
 
 std::string band_source(const BandPlan& bp, bool with_ielem, int warps, int minb) {
   char head[512];
   snprintf(head, sizeof head,
            "#define BAND_L %d\n#define BAND_RPL %d\n#define BAND_NB %d\n#define BAND_ABMASK %uu\n#define BAND_IELEM %d\n"
-           "#define BAND_WARPS %d\n#define BAND_MINB %d\n",
-           bp.L, bp.RPL, bp.NB, bp.abmask, with_ielem ? 1 : 0, warps, minb);
+           "#define BAND_WARPS %d\n#define BAND_MINB %d\n#define BAND_RC %d\n#define BAND_SYNC %d\n",
+           bp.L, bp.RPL, bp.NB, bp.abmask, with_ielem ? 1 : 0, warps, minb, bp.rc_only ? 1 : 0, band_sync_default());
   return std::string(head) + kBandKernelSource;
 }
 
-// Shared memory of one CTA: per system the solution vector and two pivot records.
+// Shared memory of one CTA: per warp the ring of staged step records, per system the solution vector and two pivot records.
 size_t band_smem_bytes(const BandPlan& bp, int warps) {
-  return sizeof(double2) * (size_t)warps * (32 / bp.L) * ((size_t)bp.n + 2 * (size_t)(bp.W + bp.NB + 2));
+  const size_t ring = (size_t)4 * bp.step_stride * (bp.rc_only ? 1 : 2);   // BRING step records per warp
+  const size_t sys = ((size_t)bp.n + 1 + 2 * (size_t)(bp.W + bp.NB + 2)) | 1;   // odd: see band_kernel.cuh
+  return sizeof(double2) * (size_t)warps * (ring + (32 / bp.L) * sys);
 }
 
 // Launch shape: as many warps per SM as shared memory and the register file (255 per thread) allow.
@@ -643,7 +670,7 @@ DeviceCtx::BandJit* ensure_band_jit(DeviceCtx& ctx, bool with_ielem) {
   const BandPlan& bp = ctx.bp;
   int warps = 0, minb = 0;
   if (!band_launch_shape(ctx, bp, warps, minb)) return nullptr;
-  const int shape[8] = {bp.L, bp.RPL, bp.NB, (int)bp.abmask, warps, minb, with_ielem ? 1 : 0, 1};
+  const int shape[9] = {bp.L, bp.RPL, bp.NB, (int)bp.abmask, warps, minb, with_ielem ? 1 : 0, bp.rc_only ? 1 : 0, band_sync_default()};
   uint64_t key = fnv1a(1469598103934665603ull, shape, sizeof shape);
   if (!key) key = 1;
   if (jv.key == key) return jv.failed ? nullptr : &jv;
@@ -675,11 +702,10 @@ int launch_ac_band(DeviceCtx& ctx, const HostPlan& hp, const AcArgs& args, Devic
   a.fb_list = fb_list; a.fb_count = fb_count;
   a.G = (double2*)ctx.bp_work.p; a.g_stride = bp.g_stride;
   a.tab = (const double2*)ctx.bp_dev.tab; a.flags = (const uint2*)ctx.bp_dev.flags;
-  a.newvar = (const int*)ctx.bp_dev.newvar; a.el_idx = (const int2*)ctx.bp_dev.el_idx;
-  a.el_a = sa.el_a; a.el_b = sa.el_b; a.el_g = sa.el_g; a.ind_L = sa.ind_L;
+  a.newvar = (const int*)ctx.bp_dev.newvar; a.el_rec = (const double4*)ctx.bp_dev.el_rec;
+  a.ind_L = sa.ind_L;
   a.n = hp.nvar; a.nb = bp.nb; a.n_ac_elem = hp.n_ac_elem; a.v_first = hp.off[ELEM_V]; a.n_ind = sa.n_ind;
-  a.o_init = bp.o_init; a.o_initb = bp.o_initb; a.o_nc = bp.o_nc; a.o_lc = bp.o_lc; a.o_e0 = bp.o_e0; a.o_erb = bp.o_erb;
-  a.o_brd0 = bp.o_brd0; a.o_brdnc = bp.o_brdnc; a.o_bb0 = bp.o_bb0;
+  a.o_init = bp.o_init; a.o_initb = bp.o_initb; a.o_brd0 = bp.o_brd0; a.o_bb0 = bp.o_bb0; a.o_step = bp.o_step;
   void* kargs[] = {&a};
   CUDA_TRY(cudaLaunchKernel((const void*)jv->kernel, dim3(grid), dim3(jv->warps * 32), kargs, smem, stream));
   if (launches) ++*launches;
@@ -1625,7 +1651,7 @@ int32_t spicey_debug_band_stats(const spicey_elem_table* table, double pilot_f, 
 int64_t spicey_debug_band_source(int32_t L, int32_t RPL, int32_t NB, uint32_t abmask, int32_t with_ielem, int32_t warps,
                                  int32_t minb, char* buf, int64_t cap) {
   BandPlan bp;
-  bp.L = L; bp.RPL = RPL; bp.NB = NB; bp.abmask = abmask;
+  bp.L = L; bp.RPL = RPL; bp.NB = NB; bp.abmask = abmask & 0xffffu; bp.rc_only = (abmask >> 16) & 1u;
   const std::string src = band_source(bp, with_ielem != 0, warps, minb);
   if (buf && cap > 0) {
     const size_t n = std::min<size_t>(src.size(), (size_t)cap - 1);

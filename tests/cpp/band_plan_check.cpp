@@ -13,6 +13,7 @@
 #include <algorithm>
 #include <cstdio>
 #include <cstdlib>
+#include <cstring>
 #include <map>
 #include <random>
 #include "../../spicey_b200/csrc/band_plan.h"
@@ -116,13 +117,18 @@ static std::vector<cd> emulate(const BandPlan& bp, double w, bool& bad) {
   for (int b = 0; b < NB; ++b) for (int j = 0; j <= NB; ++j) bb(b, j) = REC(bp.o_bb0 + b * (NB + 1) + j);
   P[W + NB + 1] = a(0, 0, 0);
   for (int t = 1; t < W; ++t) P[t] = a(0, 0, t);
-  P[0] = REC(bp.o_nc + 0);
+  const int ST = bp.step_stride, o_nc = 0, o_lc = W, o_e0 = 2 * W, o_erb = 2 * W + 1, o_brd = 2 * W + 1 + NB + 1;
+  P[0] = REC(bp.o_step + o_nc + 0);
   for (int j = 0; j <= NB; ++j) if (act(j)) P[W + j] = ab(0, 0, j);
   for (int k = 0; k < nb; ++k) {
     const int s = k % W, pl = s % L, rs = s / L, s1 = (s + 1) % W, pl1 = s1 % L, rs1 = s1 / L;
     cd* Pc = &P[(k & 1) * PS];
     cd* Pn = &P[((k + 1) & 1) * PS];
-    const unsigned fx = bp.flags[2 * k], fy = bp.flags[2 * k + 1];
+    const int rk = bp.o_step + k * ST;
+    unsigned long long fbits;   // the kernel reads a band step's tie-rule masks from the step's record
+    memcpy(&fbits, &bp.tab[rk + 2 * W + 2 * NB + 2].alpha_jre, sizeof fbits);
+    const unsigned fx = (unsigned)fbits, fy = (unsigned)(fbits >> 32);
+    if (fx != bp.flags[2 * k] || fy != bp.flags[2 * k + 1]) { bad = true; printf("FAIL flags of step %d differ between record and array\n", k); exit(1); }
     const cd dg = Pc[W + NB + 1];
     const double mp = mag(dg);
     bad = bad || !(mp >= EPS);
@@ -131,13 +137,13 @@ static std::vector<cd> emulate(const BandPlan& bp, double w, bool& bad) {
     for (int l = 0; l < L; ++l)
       for (int q = 0; q < RPL; ++q) {
         cd aik = a(l, q, s);
-        a(l, q, s) = REC(bp.o_nc + k * W + l + L * q);
+        a(l, q, s) = REC(rk + o_nc + l + L * q);
         if (q == rs && l == pl) {
-          aik = REC(bp.o_e0 + k);
+          aik = REC(rk + o_e0);
           for (int t = 0; t < W; ++t) a(l, q, t) = cd(0, 0);
-          for (int j = 0; j <= NB; ++j) if (act(j)) ab(l, q, j) = REC(bp.o_erb + k * (NB + 1) + j);
+          for (int j = 0; j <= NB; ++j) if (act(j)) ab(l, q, j) = REC(rk + o_erb + j);
         }
-        a(l, q, s1) += REC(bp.o_lc + k * W + l + L * q);
+        a(l, q, s1) += REC(rk + o_lc + l + L * q);
         const double m = mag(aik);
         const bool strict = (fx >> (l + L * q)) & 1u;
         bad = bad || (strict ? !(m < mp) : (m > mp));
@@ -150,7 +156,7 @@ static std::vector<cd> emulate(const BandPlan& bp, double w, bool& bad) {
       const double m = mag(bk);
       const bool strict = (fy >> b) & 1u;
       bad = bad || (strict ? !(m < mp) : (m > mp));
-      br(pl, b, rs) = REC(bp.o_brdnc + k * NB + b);
+      br(pl, b, rs) = REC(rk + o_brd + b);
       cd f = bk * r;
       if (mag(f) < THR) f = cd(0, 0);
       FB[b] = f;
@@ -174,7 +180,7 @@ static std::vector<cd> emulate(const BandPlan& bp, double w, bool& bad) {
     for (int j = 0; j <= NB; ++j) if (act(j)) Gb[(size_t)k * (NB + 1) + j] = Pc[W + j];
     Pn[W + NB + 1] = a(pl1, rs1, s1);
     for (int t = 0; t < W; ++t) if (t != s1) Pn[t] = a(pl1, rs1, t);
-    Pn[s1] = REC(bp.o_nc + (k + 1) * W + s1);
+    Pn[s1] = REC(rk + ST + o_nc + s1);
     for (int j = 0; j <= NB; ++j) if (act(j)) Pn[W + j] = ab(pl1, rs1, j);
   }
   std::vector<cd> RB(std::max(1, NB)), XB(std::max(1, NB));
