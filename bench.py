@@ -1,18 +1,25 @@
 #!/usr/bin/env python3
 """Benchmark of the batched MNA-solve hot path (BASELINE.json metric: solves/s).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload cfg2|cfg3|cfg4|cfg5]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload cfg2|cfg3|cfg4|cfg5] [--scaling weak|strong]
     python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N ...
     python bench.py --impl reference ...     # the reference algorithm's CPU port on all host cores
 
-A "step" is one pass of the hot path over one batch: for cfg2 (default, the configuration the
-metric is quoted on) one full 1,000,001-point AC sweep of the 64-node RC ladder (Nvar = 65).
+A "step" is one pass of the hot path over one batch.  The job is ONE batch sharded over the N ranks in contiguous
+ranges of its batch axis (SURVEY.md 8 e: frequency index for AC, instance index for TRAN; rank r takes
+shard_range(total, r, N); element table replicated; no collective on the data path):
+  cfg2 (default, the configuration the metric is quoted on), weak scaling: the 64-node RC ladder swept over
+       N x 1,000,000 + 1 log-spaced points from 1 Hz to 100 kHz (.ac dec 200000*N 1 100k); N = 1 is BASELINE's
+       1,000,001-point sweep.  --scaling strong keeps the 1,000,001 points and splits them.
+  cfg4 strong scaling: the 8,000,001-point sweep of the 16x16 mesh split over the ranks (solved in chunks of the
+       device result buffers); cfg3 / cfg5 strong scaling: the 65,536 / 100,000 instances split over the ranks.
   value      whole-job solves/s with inputs resident in HBM, CUDA-event timed, max over ranks
   e2e        the same through the host-buffer C-ABI call (pinned host buffers, H2D + D2H inside)
-  roofline   dominant kernel vs the FP64 (AC) or HBM-write (TRAN) roofline, SURVEY.md §8(d) figures
+  roofline   dominant kernel vs the FP64 (AC) or HBM-write (TRAN) roofline, SURVEY.md 8(d) figures
   cpu_baseline  oracle/oracle.c (C restatement of the reference algorithm) on a bounded sample
-Multi-GPU: every rank runs the same per-GPU workload on its own device (weak scaling, no
-collective on the data path); timing is barrier + synchronize on both sides, max over ranks.
+  secondary  (default line only) short legs of cfg3, cfg4 and cfg5 at their BASELINE sizes: value, roofline, e2e
+After the timed region every rank checks a sample of each of its chunks against the oracle (1e-9 AC, 1e-6 TRAN).
+Timing is barrier + synchronize on both sides, CUDA events, max over ranks.
 """
 import argparse
 import json
@@ -190,13 +197,21 @@ def dist_env():
 
 # ---- workloads --------------------------------------------------------------------------
 
-def load_workload(name, points=None, instances=None, device_waves=False):
+AC_NETLISTS = {"cfg1": lambda n: W.README_RC, "cfg2": lambda n: W.rc_ladder(64, ppd=200000 * n),
+               "cfg2mc": lambda n: W.rc_ladder(64), "cfg4": lambda n: W.rc_mesh(16)}
+DEFAULT_SCALING = {"cfg1": "strong", "cfg2": "weak", "cfg2mc": "strong", "cfg3": "strong", "cfg4": "strong", "cfg5": "strong"}
+
+
+def load_workload(name, world=1, scaling=None, points=None, instances=None, device_waves=False):
+    """The WHOLE job (all ranks): netlist, batch axis, labels.  `units` counts the metric's unit over the whole job."""
     import spicey_b200 as sp
     from spicey_b200.packing import make_sweep, pack_circuit, sample_sources, initial_state
-    wl = {"name": name}
+    scaling = scaling or DEFAULT_SCALING[name]
+    mult = world if scaling == "weak" else 1
+    wl = {"name": name, "scaling": scaling}
     if name == "cfg2mc":  # not a BASELINE config: cfg2's ladder with every R and C swept +-5 % (AC Monte-Carlo axis)
         ck = parse_netlist(W.rc_ladder(64))
-        n = instances or 4096
+        n = (instances or 4096) * mult
         freqs = np.logspace(0, 5, 245)
         u = W.splitmix_uniform_pm1(n, 126)
         ov = {}
@@ -204,45 +219,52 @@ def load_workload(name, points=None, instances=None, device_waves=False):
             ov["r%d" % k] = 1000.0 * (1 + 0.05 * u[:, k - 1])
             ov["c%d" % k] = 1e-9 * (1 + 0.05 * u[:, 62 + k])
         table = pack_circuit(ck)
-        wl.update(kind="ac", ckt=ck, table=table, freqs=freqs, units=int(n * freqs.shape[0]),
-                  sweep=make_sweep(table, n, ov), n_inst=n, overrides=ov,
+        wl.update(kind="ac", axis="instance", ckt=ck, table=table, freqs=freqs, n_inst=n, overrides=ov,
+                  units=int(n * freqs.shape[0]), batch=n, unit_per_batch=int(freqs.shape[0]),
                   label="cfg2mc: 64-node RC ladder, %d Monte-Carlo instances x %d frequencies (all R, C +-5 %%)" % (
                       n, freqs.shape[0]),
                   flops_per_unit=f_cplx(table.nvar), bytes_per_unit=8 + 16 * table.nvar + 16 * table.n_ac_elem)
         return wl
-    if name in ("cfg2", "cfg4", "cfg1"):
-        text = {"cfg2": W.rc_ladder(64), "cfg4": W.rc_mesh(16), "cfg1": W.README_RC}[name]
-        ck = parse_netlist(text)
+    if name in AC_NETLISTS:
+        ck = parse_netlist(AC_NETLISTS[name](mult))
         freqs = np.array(sp.analysis.ac_frequencies(ck), dtype=np.float64)
-        if name == "cfg4" and not points:
-            # the full 8,000,001-point sweep is 127 GB of results (it is the 8-GPU configuration: 1e6 points per GPU);
-            # the default bench line is a 400,000-point slice per GPU, every 20th frequency of the same sweep
-            points = 400000
+        full = int(freqs.shape[0])
         if points:
-            freqs = freqs[:: max(1, freqs.shape[0] // points)][:points]
+            freqs = np.ascontiguousarray(freqs[:: max(1, freqs.shape[0] // points)][:points])
         table = pack_circuit(ck)
-        wl.update(kind="ac", ckt=ck, table=table, freqs=freqs, units=int(freqs.shape[0]), sweep=None,
-                  label={"cfg2": "cfg2: 64-node RC ladder .ac dec 200000 1 100k (1,000,001 points, Nvar=65, c128 LU)",
-                         "cfg4": "cfg4: 16x16 RC mesh .ac dec 1600000 1 100k, %d-point slice of the 8,000,001 (Nvar=257, c128 LU)" % freqs.shape[0], "cfg1": "cfg1: README RC low-pass"}[name],
-                  flops_per_unit=f_cplx(table.nvar),
-                  bytes_per_unit=8 + 16 * table.nvar + 16 * table.n_ac_elem)
-    else:
-        text, ovf, n_full = {"cfg3": (W.RLC_TANK, W.rlc_tank_overrides, 65536),
-                             "cfg5": (W.RECTIFIER, W.rectifier_overrides, 100000)}[name]
-        n = instances or n_full
-        ck = parse_netlist(text)
-        ov = {k: v[:n] for k, v in ovf(n_full).items()}
-        dt, steps = compute_effective_time_step(ck.analyses.tran.dt, ck.analyses.tran.tstop)
-        table = pack_circuit(ck, device_waves=device_waves)   # device_waves: PULSE evaluated by the kernel
-        vsrc, mask = sample_sources(ck, dt, steps)
-        wl.update(kind="tran", ckt=ck, table=table, dt=dt, steps=steps, vsrc=vsrc, mask=mask, overrides=ov,
-                  sweep=make_sweep(table, n, ov), n_inst=n, units=n * (steps + 1),
-                  state0=initial_state(ck, table, n),
-                  label="%s: %s, %d instances x %d recorded steps (Nvar=%d, f64)" % (
-                      name, "RLC tank .tran 1u 1m Monte-Carlo" if name == "cfg3" else "diode half-wave rectifier .tran 1u 3m sweep",
-                      n, steps + 1, table.nvar),
-                  flops_per_unit=55, bytes_per_unit=8 * (table.n_nodes + table.n_elem))
+        P = int(freqs.shape[0])
+        what = {"cfg2": "64-node RC ladder .ac dec %d 1 100k" % (200000 * mult), "cfg4": "16x16 RC mesh .ac dec 1600000 1 100k",
+                "cfg1": "README RC low-pass"}[name]
+        wl.update(kind="ac", axis="frequency", ckt=ck, table=table, freqs=freqs, n_inst=1, overrides=None,
+                  units=P, batch=P, unit_per_batch=1,
+                  label="%s: %s (%s points%s, Nvar=%d, c128 LU)" % (
+                      name, what, "{:,}".format(P), "" if P == full else " of the {:,}".format(full), table.nvar),
+                  flops_per_unit=f_cplx(table.nvar), bytes_per_unit=8 + 16 * table.nvar + 16 * table.n_ac_elem)
+        return wl
+    text, ovf, n_full = {"cfg3": (W.RLC_TANK, W.rlc_tank_overrides, 65536),
+                         "cfg5": (W.RECTIFIER, W.rectifier_overrides, 100000)}[name]
+    n = (instances or n_full) * mult
+    ck = parse_netlist(text)
+    ov = {k: v[:n] for k, v in ovf(max(n, n_full)).items()}
+    dt, steps = compute_effective_time_step(ck.analyses.tran.dt, ck.analyses.tran.tstop)
+    table = pack_circuit(ck, device_waves=device_waves)   # device_waves: PULSE evaluated by the kernel
+    vsrc, mask = sample_sources(ck, dt, steps)
+    wl.update(kind="tran", axis="instance", ckt=ck, table=table, dt=dt, steps=steps, vsrc=vsrc, mask=mask, overrides=ov,
+              n_inst=n, units=n * (steps + 1), batch=n, unit_per_batch=steps + 1,
+              state0=initial_state(ck, table, n), device_waves=device_waves,
+              label="%s: %s, %s instances x %d recorded steps (Nvar=%d, f64)" % (
+                  name, "RLC tank .tran 1u 1m Monte-Carlo" if name == "cfg3" else "diode half-wave rectifier .tran 1u 3m sweep",
+                  "{:,}".format(n), steps + 1, table.nvar),
+              flops_per_unit=55, bytes_per_unit=8 * (table.n_nodes + table.n_elem))
+    del make_sweep
     return wl
+
+
+def config_of(wl, world):
+    """The part of the JSON line both arms print identically."""
+    return {"workload": wl["label"], "scaling": wl["scaling"],
+            "parallelism": "one batch sharded over %d rank%s in contiguous %s ranges, no collective on the data path" % (
+                world, "" if world == 1 else "s", wl["axis"])}
 
 
 # ---- reference arm: the reference algorithm's CPU port on all host cores ------------------
@@ -284,7 +306,7 @@ def cpu_rate(wl, target_s=12.0, threads=None):
     n2 = int(min(wl["n_inst"], max(n, rate * target_s)))
     ov = {k: v[:n2] for k, v in wl["overrides"].items()}
     t0 = time.perf_counter()
-    _, _, iters, _, _ = co.tran_solve(wl["ckt"], wl["dt"], wl["steps"], n_inst=n2, overrides=ov, nthreads=threads)
+    co.tran_solve(wl["ckt"], wl["dt"], wl["steps"], n_inst=n2, overrides=ov, nthreads=threads)
     dt = time.perf_counter() - t0
     return n2 * (wl["steps"] + 1) / dt, threads, "first %d of %d instances (%d recorded steps, %.1f s)" % (
         n2, wl["n_inst"], n2 * (wl["steps"] + 1), dt)
@@ -294,7 +316,7 @@ def run_reference(args):
     rank, local, world = dist_env()
     if rank != 0:
         return
-    wl = load_workload(args.workload, args.points, args.instances)
+    wl = load_workload(args.workload, max(1, args.gpus), args.scaling, args.points, args.instances)
     for _ in range(max(0, min(args.warmup, 1))):
         cpu_rate(wl, target_s=0.5)
     rates, sample = [], ""
@@ -308,8 +330,8 @@ def run_reference(args):
         "impl": "reference", "metric": "batched MNA solves/sec", "value": value, "unit": "solves/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": 1e3 * (time.perf_counter() - t0) / max(1, args.steps), "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "c128" if wl["kind"] == "ac" else "f64",
-        "data": "synthetic", "config": {"workload": wl["label"]},
+        "scaling": wl["scaling"], "vs_baseline": None, "dtype": "c128" if wl["kind"] == "ac" else "f64",
+        "data": "synthetic", "config": config_of(wl, max(1, args.gpus)),
         "cpu_baseline": {"value": value, "unit": "solves/s", "cores": threads, "kind": "port", "sample": sample,
                          "note": "C restatement of the reference algorithm (oracle/oracle.c); the reference itself "
                                  "is TypeScript and no JS runtime exists in this image"},
@@ -320,10 +342,242 @@ def run_reference(args):
 
 # ---- native arm -------------------------------------------------------------------------
 
+DEVICE_RESULT_BYTES = 12 << 30     # device result buffers of one AC chunk (x + ielem): larger sweeps are solved in chunks
+HOST_RESULT_BYTES = 8 << 30        # pinned host buffers of the end-to-end leg: larger shards time a slab of this size
+
+
+class Leg:
+    """One rank's share [lo, hi) of one workload's batch axis: buffers, the resident step, the end-to-end step, checks."""
+
+    def __init__(self, eng, wl, rank, world, dev, stream, dense=False):
+        import torch
+        from spicey_b200 import native
+        from spicey_b200.packing import make_sweep
+        from spicey_b200.sharding import shard_range
+        self.eng, self.wl, self.dev, self.stream, self.native, self.torch = eng, wl, dev, stream, native, torch
+        self.table = table = wl["table"]
+        self.lo, self.hi = shard_range(wl["batch"], rank, world)
+        self.nb = nb = self.hi - self.lo                      # my slice of the batch axis
+        self.units = nb * wl["unit_per_batch"]
+        self.pins, self.launches_per_step, self.tier, self.fallback = [], 0, 0, 0
+        ov = wl.get("overrides")
+        self.ov = None if ov is None else {k: np.ascontiguousarray(v[self.lo:self.hi]) for k, v in ov.items()}
+        if wl["kind"] == "ac":
+            self.flags = native.FLAG_SERIES_MAJOR | (native.FLAG_DENSE if dense else 0)
+            if wl["axis"] == "frequency":
+                self.freqs = np.ascontiguousarray(wl["freqs"][self.lo:self.hi])
+                self.sweep, self.P = None, nb
+            else:
+                self.freqs = wl["freqs"]
+                self.sweep, self.P = make_sweep(table, nb, self.ov), nb * int(wl["freqs"].shape[0])
+            per_point = 16 * (table.nvar + table.n_ac_elem)
+            self.chunk = self.P if self.sweep is not None else max(1, min(self.P, DEVICE_RESULT_BYTES // per_point))
+            if self.chunk < self.P and self.P >= native_jit_min_points():
+                self.flags |= native.FLAG_JIT    # the compile-or-interpret decision looks at the whole sweep, not at one chunk
+            self.ld = eng.series_ld(self.chunk)
+            self.d_freqs = torch.from_numpy(self.freqs).to(dev)
+            self.d_var = torch.from_numpy(self.sweep.var_values).to(dev) if self.sweep is not None else None
+            self.d_x = torch.empty((table.nvar, self.ld), dtype=torch.complex128, device=dev)
+            self.d_i = torch.empty((table.n_ac_elem, self.ld), dtype=torch.complex128, device=dev)
+            self.d_s = torch.empty(self.chunk, dtype=torch.int32, device=dev)
+            self.result_bytes = self.P * per_point
+        else:
+            self.sweep = make_sweep(table, nb, self.ov)
+            S1 = wl["steps"] + 1
+            self.d_var = torch.from_numpy(self.sweep.var_values).to(dev)
+            self.d_vsrc = torch.from_numpy(wl["vsrc"]).to(dev)
+            self.state0 = np.ascontiguousarray(wl["state0"][:, self.lo:self.hi])
+            self.d_st0 = torch.from_numpy(self.state0).to(dev)
+            self.d_v = torch.empty((S1, table.n_nodes, nb), dtype=torch.float64, device=dev)
+            self.d_i = torch.empty((S1, table.n_elem, nb), dtype=torch.float64, device=dev)
+            self.d_s = torch.empty(nb, dtype=torch.int32, device=dev)
+            self.result_bytes = self.units * wl["bytes_per_unit"]
+
+    # -- device-resident --------------------------------------------------------------
+    def chunks(self):
+        return [(c, min(self.chunk, self.P - c)) for c in range(0, self.P, self.chunk)] if self.wl["kind"] == "ac" else [(0, self.nb)]
+
+    def solve_chunk(self, c0, n):
+        if self.sweep is not None:   # instance axis: one call
+            self.eng.ac_solve_device(self.table, self.d_freqs.data_ptr(), int(self.freqs.shape[0]), self.d_x.data_ptr(),
+                                     self.d_i.data_ptr(), self.d_s.data_ptr(), sweep=self.sweep,
+                                     d_var_values=self.d_var.data_ptr(), flags=self.flags, stream=self.stream.cuda_stream,
+                                     series_ld=self.ld)
+        else:
+            self.eng.ac_solve_device(self.table, self.d_freqs.data_ptr() + 8 * c0, n, self.d_x.data_ptr(), self.d_i.data_ptr(),
+                                     self.d_s.data_ptr(), flags=self.flags, stream=self.stream.cuda_stream, series_ld=self.ld)
+
+    def step_resident(self):
+        wl = self.wl
+        if wl["kind"] == "ac":
+            for c0, n in self.chunks():
+                self.solve_chunk(c0, n)
+        else:
+            self.eng.tran_solve_device(self.table, wl["dt"], wl["steps"], self.d_vsrc.data_ptr(), wl["mask"], self.d_st0.data_ptr(),
+                                       self.d_v.data_ptr(), self.d_i.data_ptr(), None, None, self.d_s.data_ptr(), sweep=self.sweep,
+                                       d_var_values=self.d_var.data_ptr(), stream=self.stream.cuda_stream, waves=self.table.waves)
+
+    def note_stats(self):
+        st = self.eng.stats()   # reads the fallback counter back: synchronises, hence outside any timed loop
+        self.tier, self.fallback, self.cfma = st["tier"], int(st["fallback_solves"]), int(st["program_cfma"])
+        self.launches_per_step = int(st["kernel_launches"]) * len(self.chunks())
+
+    def verify(self, per_chunk=4):
+        """Untimed pass over every chunk of my range: status 0 everywhere, a sample of each chunk against the oracle."""
+        from oracle import c_oracle as co
+        torch, wl = self.torch, self.wl
+        worst = 0.0
+        if wl["kind"] == "ac":
+            nac, nv = self.table.n_ac_elem, self.table.nvar
+            for c0, n in self.chunks():
+                self.solve_chunk(c0, n)
+                torch.cuda.synchronize()
+                npts = n if self.sweep is None else self.P
+                assert int(self.d_s[:npts].max().item()) == 0, "non-zero status in the bench run (%s)" % wl["name"]
+                pick = np.unique(np.linspace(0, npts - 1, per_chunk).astype(np.int64))
+                sel = torch.from_numpy(pick).to(self.dev)
+                x = self.d_x[:, sel].T.cpu().numpy()
+                ie = self.d_i[:, sel].T.cpu().numpy()
+                if self.sweep is None:
+                    xr, ir, st = co.ac_solve(wl["ckt"], self.freqs[c0 + pick], nthreads=4)
+                else:
+                    F = int(self.freqs.shape[0])
+                    rows = []
+                    for p_ in pick:
+                        inst, k = int(p_) // F, int(p_) % F
+                        rows.append(co.ac_solve(wl["ckt"], self.freqs[k:k + 1], n_inst=1,
+                                                overrides={key: v[inst:inst + 1] for key, v in self.ov.items()}))
+                    xr = np.concatenate([r_[0] for r_ in rows]); ir = np.concatenate([r_[1] for r_ in rows])
+                    st = np.concatenate([r_[2] for r_ in rows])
+                assert int(st.max()) == 0
+                xr, ir = xr.reshape(len(pick), nv), ir.reshape(len(pick), nac)
+                ex = float(np.max(np.abs(x - xr) / np.maximum(np.abs(xr), 1e-300)))
+                ei = float(np.max(np.abs(ie - ir) / np.maximum(np.abs(ir), 1e-300))) if nac else 0.0
+                worst = max(worst, ex, ei)
+            assert worst <= 1e-9, "bench results differ from the oracle: %.3e (%s)" % (worst, wl["name"])
+        else:
+            self.step_resident()
+            torch.cuda.synchronize()
+            assert int(self.d_s.max().item()) == 0, "non-zero status in the bench run (%s)" % wl["name"]
+            pick = np.unique(np.linspace(0, self.nb - 1, per_chunk).astype(np.int64))
+            sel = torch.from_numpy(pick).to(self.dev)
+            v = self.d_v[:, :, sel].cpu().numpy()
+            ie = self.d_i[:, :, sel].cpu().numpy()
+            for j, inst in enumerate(pick):
+                vr, ir, _, st, _ = co.tran_solve(wl["ckt"], wl["dt"], wl["steps"], n_inst=1,
+                                                 overrides={key: val[inst:inst + 1] for key, val in self.ov.items()})
+                assert int(np.max(st)) == 0
+                vr, ir = vr[0], ir[0]   # [steps+1][nn], [steps+1][n_elem]; errors relative to each series' maximum
+                worst = max(worst, float(np.max(np.abs(v[:, :, j] - vr) / np.maximum(np.max(np.abs(vr), axis=0, keepdims=True), 1e-30))),
+                            float(np.max(np.abs(ie[:, :, j] - ir) / np.maximum(np.max(np.abs(ir), axis=0, keepdims=True), 1e-30))))
+            assert worst <= 1e-6, "bench results differ from the oracle: %.3e (%s)" % (worst, wl["name"])
+        return worst
+
+    # -- end to end through the host-buffer C ABI ---------------------------------------
+    def prepare_e2e(self):
+        native, eng, wl, table = self.native, self.eng, self.wl, self.table
+        if wl["kind"] == "ac":
+            per_point = 16 * (table.nvar + table.n_ac_elem)
+            if self.sweep is None:
+                self.e2e_points = max(1, min(self.P, HOST_RESULT_BYTES // per_point))
+                self.e2e_freqs = np.ascontiguousarray(self.freqs[: self.e2e_points])
+            else:
+                self.e2e_points, self.e2e_freqs = self.P, self.freqs
+            F = int(self.e2e_freqs.shape[0])
+            self.h_freqs, p0 = native.pinned_empty(eng.lib, (F,), np.float64)
+            self.h_freqs[:] = self.e2e_freqs
+            self.h_x, p1 = native.pinned_empty(eng.lib, (table.nvar, self.e2e_points), np.complex128)
+            self.h_i, p2 = native.pinned_empty(eng.lib, (table.n_ac_elem, self.e2e_points), np.complex128)
+            self.h_s, p3 = native.pinned_empty(eng.lib, (self.e2e_points,), np.int32)
+            self.pins += [p0, p1, p2, p3]
+            self.e2e_units = self.e2e_points
+            self.e2e_flags = self.flags | (native.FLAG_JIT if self.P >= native_jit_min_points() else 0)
+        else:
+            S1 = wl["steps"] + 1
+            per_inst = 8 * S1 * (table.n_nodes + table.n_elem)
+            self.e2e_inst = max(1, min(self.nb, HOST_RESULT_BYTES // per_inst))
+            from spicey_b200.packing import make_sweep
+            self.e2e_sweep = self.sweep if self.e2e_inst == self.nb else make_sweep(
+                table, self.e2e_inst, {k: v[: self.e2e_inst] for k, v in self.ov.items()})
+            self.h_v, p1 = native.pinned_empty(eng.lib, (S1, table.n_nodes, self.e2e_inst), np.float64)
+            self.h_i, p2 = native.pinned_empty(eng.lib, (S1, table.n_elem, self.e2e_inst), np.float64)
+            self.pins += [p1, p2]
+            self.e2e_units = self.e2e_inst * S1
+
+    def step_e2e(self, want_currents=True):
+        wl = self.wl
+        if wl["kind"] == "ac":
+            self.eng.ac_solve(self.table, self.h_freqs, sweep=self.sweep, out=(self.h_x, self.h_i if want_currents else None, self.h_s),
+                              flags=self.e2e_flags, want_currents=want_currents)
+            return int(self.h_s.max())
+        r = self.eng.tran_solve(self.table, wl["dt"], wl["steps"], vsrc=wl["vsrc"], vsrc_mask=wl["mask"], sweep=self.e2e_sweep,
+                                state0=np.ascontiguousarray(self.state0[:, : self.e2e_inst]), out=(self.h_v, self.h_i if want_currents else None),
+                                waves=self.table.waves, want_currents=want_currents)
+        return int(r["status"].max())
+
+    def release(self):
+        for p in self.pins:
+            self.eng.lib.spicey_host_free(p)
+        self.pins = []
+        for name in ("d_x", "d_i", "d_v", "d_s", "d_freqs", "d_var", "d_vsrc", "d_st0"):
+            if hasattr(self, name):
+                delattr(self, name)
+        self.torch.cuda.empty_cache()
+
+
+def native_jit_min_points():
+    return 200000   # spicey_native.cu: kJitMinPoints (the host entry point sets SPICEY_FLAG_JIT from the whole call's size)
+
+
+def roofline_of(leg, wl, world, kern_ms, peak_hbm, peak_src, fp64_peak):
+    """Roofline of the dominant kernel of one leg, from the per-rank kernel time (max over ranks) and per-rank units."""
+    native = leg.native
+    units = leg.units
+    if wl["kind"] == "tran":
+        ach = units * wl["bytes_per_unit"] / (kern_ms * 1e-3) / 1e9
+        roof = {"bound": "hbm", "achieved": ach, "peak": peak_hbm, "unit": "GB/s", "frac": ach / peak_hbm,
+                "traffic": None, "peak_source": peak_src, "bytes_per_solve": wl["bytes_per_unit"]}
+    else:
+        ach_f = units * wl["flops_per_unit"] / (kern_ms * 1e-3) / 1e12
+        dense = {"bound": "fp64", "achieved": ach_f, "peak": fp64_peak, "unit": "TFLOP/s", "frac": ach_f / fp64_peak,
+                 "flops_per_solve_dense": wl["flops_per_unit"],
+                 "peak_source": "own DFMA-loop microbenchmark in this run (MEASURED_PEAKS.json has no FP64 figure)"}
+        ach_b = units * wl["bytes_per_unit"] / (kern_ms * 1e-3) / 1e9
+        hbm = {"bound": "hbm", "achieved": ach_b, "peak": peak_hbm, "unit": "GB/s", "frac": ach_b / peak_hbm,
+               "peak_source": peak_src, "bytes_per_solve": wl["bytes_per_unit"]}
+        sparse_tiers = (native.TIER_SPARSE, native.TIER_SPARSE_JIT, native.TIER_SPARSE_WARP, native.TIER_BAND)
+        if leg.tier in sparse_tiers:
+            ex = units * leg.cfma * 8 / (kern_ms * 1e-3) / 1e12
+            executed = {"bound": "fp64", "complex_fma_per_solve": leg.cfma, "achieved": ex, "peak": fp64_peak, "unit": "TFLOP/s",
+                        "frac": ex / fp64_peak}
+            # which roofline binds: the structure-exploiting tiers execute 1e3 - 8e4 complex FMAs per solve instead of the
+            # dense 1e5 - 6e6; for the ladder (cfg2) the FP64 pipe cannot bind and HBM does, for the mesh (cfg4: 78,592
+            # complex FMAs against 15,896 result bytes per solve) the FP64 pipe does
+            if executed["frac"] >= hbm["frac"]:
+                roof = dict(executed, traffic=None, hbm=hbm, dense_fp64_equivalent=dense,
+                            note="banded / sparse LU verified per point: bound by the FP64 pipe on the flops it executes; "
+                                 "dense_fp64_equivalent is SURVEY 8(d)'s dense flop figure per solve (structurally zero work is never executed)")
+            else:
+                roof = dict(hbm, traffic=None, executed_fp64=executed, dense_fp64_equivalent=dense,
+                            note="sparse static-pivot LU program verified per point: HBM-bound on SURVEY 8(d)'s algorithmic bytes; "
+                                 "dense_fp64_equivalent exceeds 1 because structurally zero work is never executed")
+        else:
+            roof = dict(dense, traffic=None, hbm=hbm)
+    tr = os.path.join(ROOT, "profiles", "traffic_%s.json" % wl["name"])
+    if os.path.exists(tr):   # DRAM bytes of one ncu --set full capture: only quoted for the kernel tier it was taken on
+        try:
+            cap = json.load(open(tr))
+            if int(cap.get("tier", -1)) == int(leg.tier):
+                roof["traffic"] = cap.get("dram_bytes_per_unit", 0) * units
+                roof["traffic_capture"] = {k: cap.get(k) for k in ("capture", "kernel", "units_in_capture", "dram_bytes_per_unit")}
+        except Exception:
+            pass
+    return roof
+
+
 def run_native(args):
     import torch
     import torch.distributed as dist
-    import spicey_b200 as sp
     from spicey_b200 import native
 
     rank, local, world = dist_env()
@@ -340,10 +594,9 @@ def run_native(args):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     dev = torch.device("cuda", local)
     eng = native.Engine([local])
-    wl = load_workload(args.workload, args.points, args.instances, getattr(args, "device_waves", False))
-    table = wl["table"]
     stream = torch.cuda.current_stream()
     peaks, peak_src = read_peaks()
+    peak_hbm = float(peaks.get("hbm_gbs", 6650.0))
 
     def barrier():
         torch.cuda.synchronize()
@@ -351,199 +604,162 @@ def run_native(args):
             dist.barrier()
             torch.cuda.synchronize()
 
-    launches = 0
-    if wl["kind"] == "ac":
-        P = wl["units"]
-        F = int(wl["freqs"].shape[0])
-        sweep = wl.get("sweep")
-        d_var = torch.from_numpy(sweep.var_values).to(dev) if sweep is not None else None
-        d_freqs = torch.from_numpy(wl["freqs"]).to(dev)
-        # series-major results (x[Nvar][P], ielem[nAc][P]): the layout the drop-in simulateAC uses
-        # (rows padded to spicey_series_ld(P) points so that every row starts on a 512-byte boundary)
-        ld = eng.series_ld(P)
-        d_x = torch.empty((table.nvar, ld), dtype=torch.complex128, device=dev)
-        d_i = torch.empty((table.n_ac_elem, ld), dtype=torch.complex128, device=dev)
-        d_s = torch.empty(P, dtype=torch.int32, device=dev)
-        ac_flags = native.FLAG_SERIES_MAJOR | (native.FLAG_DENSE if args.dense else 0)
+    def allmax(vals):
+        t = torch.tensor(vals, dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return [float(v) for v in t]
 
-        def step_resident():
-            eng.ac_solve_device(table, d_freqs.data_ptr(), F, d_x.data_ptr(), d_i.data_ptr(), d_s.data_ptr(),
-                                sweep=sweep, d_var_values=None if d_var is None else d_var.data_ptr(),
-                                flags=ac_flags, stream=stream.cuda_stream, series_ld=ld)
-
-        h_freqs, p0 = native.pinned_empty(eng.lib, (F,), np.float64)
-        h_freqs[:] = wl["freqs"]
-        h_x, p1 = native.pinned_empty(eng.lib, (table.nvar, P), np.complex128)
-        h_i, p2 = native.pinned_empty(eng.lib, (table.n_ac_elem, P), np.complex128)
-        h_s, p3 = native.pinned_empty(eng.lib, (P,), np.int32)
-        pins = [p0, p1, p2, p3]
-
-        def step_e2e():
-            eng.ac_solve(table, h_freqs, sweep=sweep, out=(h_x, h_i, h_s), flags=ac_flags)
-            return int(h_s.max())
-
-        def check():
-            assert int(d_s.max().item()) == 0, "non-zero status in bench run"
-        working_set = P * wl["bytes_per_unit"]
-    else:
-        n, S1 = wl["n_inst"], wl["steps"] + 1
-        sweep = wl["sweep"]
-        d_var = torch.from_numpy(sweep.var_values).to(dev)
-        d_vsrc = torch.from_numpy(wl["vsrc"]).to(dev)
-        d_st0 = torch.from_numpy(wl["state0"]).to(dev)
-        d_v = torch.empty((S1, table.n_nodes, n), dtype=torch.float64, device=dev)
-        d_i = torch.empty((S1, table.n_elem, n), dtype=torch.float64, device=dev)
-        d_s = torch.empty(n, dtype=torch.int32, device=dev)
-
-        def step_resident():
-            eng.tran_solve_device(table, wl["dt"], wl["steps"], d_vsrc.data_ptr(), wl["mask"], d_st0.data_ptr(),
-                                  d_v.data_ptr(), d_i.data_ptr(), None, None, d_s.data_ptr(), sweep=sweep,
-                                  d_var_values=d_var.data_ptr(), stream=stream.cuda_stream, waves=table.waves)
-
-        h_v, p1 = native.pinned_empty(eng.lib, (S1, table.n_nodes, n), np.float64)
-        h_i, p2 = native.pinned_empty(eng.lib, (S1, table.n_elem, n), np.float64)
-        pins = [p1, p2]
-
-        def step_e2e():
-            r = eng.tran_solve(table, wl["dt"], wl["steps"], vsrc=wl["vsrc"], vsrc_mask=wl["mask"], sweep=sweep,
-                               state0=wl["state0"], out=(h_v, h_i), waves=table.waves)
-            return int(r["status"].max())
-
-        def check():
-            assert int(d_s.max().item()) == 0, "non-zero status in bench run"
-        working_set = wl["units"] * wl["bytes_per_unit"]
-
-    # ---- device-resident timing (value) ----
-    for _ in range(args.warmup):
-        step_resident()
-    barrier()
-    check()
     try:
         dev_uuid = str(torch.cuda.get_device_properties(local).uuid)
     except Exception:
         dev_uuid = None
     sampler = ClockSampler(local, dev_uuid)
-    if rank == 0:
-        sampler.start()
-    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    barrier()
-    e0.record(stream)
-    for k in range(args.steps):
-        ev[k][0].record(stream)
-        step_resident()
-        ev[k][1].record(stream)
-    e1.record(stream)
-    barrier()
-    if rank == 0:
-        sampler.pause()
-    n_timed_samples = len(sampler.samples)
-    total_ms = e0.elapsed_time(e1)
-    kern_ms = float(np.mean([a.elapsed_time(b) for a, b in ev]))
-    st_last = eng.stats()   # (reads the fallback counter back: synchronises, hence outside the timed loop)
-    launches += st_last["kernel_launches"] * args.steps
-    tier, fallback = st_last["tier"], st_last["fallback_solves"]
-    check()
-    t = torch.tensor([total_ms, kern_ms], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    total_ms, kern_ms = float(t[0]), float(t[1])
-
-    # ---- end-to-end through the host-buffer C ABI ----
-    e2e_steps = max(1, min(args.steps, 3))
-    step_e2e()
-    barrier()
-    if rank == 0 and sampler.nvml is not None and n_timed_samples < 5:
-        sampler.start()   # a timed region of a few ms gives few samples: the e2e region (same kernels) adds its own
-    t0 = time.perf_counter()
-    for _ in range(e2e_steps):
-        st = step_e2e()
-        assert st == 0
-    torch.cuda.synchronize()
-    e2e_s = time.perf_counter() - t0
-    clocks = sampler.stop() if rank == 0 else None
-    if clocks is not None:
-        clocks["samples_in_timed_region"] = n_timed_samples
-    es = eng.stats()
-    t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.barrier()
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e_s = float(t[0])
     fp64_peak = eng.fp64_peak_gflops() / 1e3  # TFLOP/s, own DFMA-loop microbenchmark
 
+    def time_leg(wl, steps, warmup, e2e_steps, sample_clocks, sustain_s):
+        """value / roofline / e2e of one workload, every rank on its shard.  Returns the leg's dict on every rank."""
+        leg = Leg(eng, wl, rank, world, dev, stream, dense=args.dense)
+        for _ in range(max(1, warmup)):
+            leg.step_resident()
+        barrier()
+        leg.note_stats()
+        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        if sample_clocks and rank == 0:
+            sampler.start()
+        barrier()
+        e0.record(stream)
+        for k in range(steps):
+            ev[k][0].record(stream)
+            leg.step_resident()
+            ev[k][1].record(stream)
+        e1.record(stream)
+        barrier()
+        total_ms = e0.elapsed_time(e1)
+        kern_ms = float(np.mean([a.elapsed_time(b) for a, b in ev]))
+        # sustained region: the same step repeated until sustain_s seconds have passed (clock samples need more than
+        # the few milliseconds K steps take); reported beside the K-step value, never instead of it
+        sus = None
+        if sustain_s > 0:
+            reps = int(max(1, min(2000, np.ceil(sustain_s / max(1e-6, kern_ms * 1e-3)))))
+            s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            barrier()
+            s0.record(stream)
+            for _ in range(reps):
+                leg.step_resident()
+            s1.record(stream)
+            barrier()
+            sus = (reps, s0.elapsed_time(s1))
+        if sample_clocks and rank == 0:
+            sampler.pause()
+        n_samples = len(sampler.samples)
+        worst = leg.verify()
+        total_ms, kern_ms, worst = allmax([total_ms, kern_ms, worst])
+        out = {"workload": wl["label"], "tier": leg.tier, "units_per_step": wl["units"],
+               "value": wl["units"] * steps / (total_ms * 1e-3), "unit": "solves/s", "steps": steps, "ms_per_step": total_ms / steps,
+               "kernel_ms_per_step": kern_ms, "chunks_per_step": len(leg.chunks()),
+               "fallback_solves_last_step": leg.fallback, "rank0_range": [leg.lo, leg.hi],
+               "checked_against_oracle": {"max_rel_err": worst, "tolerance": 1e-9 if wl["kind"] == "ac" else 1e-6,
+                                          "sample": "4 units of every chunk of every rank's range, plus status == 0 everywhere"},
+               "roofline": roofline_of(leg, wl, world, kern_ms, peak_hbm, peak_src, fp64_peak),
+               "gpu_launches": leg.launches_per_step * steps}
+        if sus is not None:
+            (sus_ms,) = allmax([sus[1]])
+            out["sustained"] = {"steps": sus[0], "seconds": sus_ms * 1e-3, "value": wl["units"] * sus[0] / (sus_ms * 1e-3)}
+        # ---- end-to-end through the host-buffer C ABI ----
+        if e2e_steps > 0:
+            leg.prepare_e2e()
+            assert leg.step_e2e() == 0
+            barrier()
+            if sample_clocks and rank == 0 and sampler.nvml is not None:
+                sampler.start()
+            t0 = time.perf_counter()
+            for _ in range(e2e_steps):
+                assert leg.step_e2e() == 0
+            torch.cuda.synchronize()
+            e2e_s = time.perf_counter() - t0
+            if sample_clocks and rank == 0:
+                sampler.pause()
+            es = eng.stats()
+            # the same without element currents: the lazy result objects (SURVEY 8 f1) compute Y (v1 - v2) on access, exactly
+            # as the reference does (simulateAC.ts:94-126), from the node voltages alone
+            assert leg.step_e2e(want_currents=False) == 0
+            barrier()
+            t0 = time.perf_counter()
+            for _ in range(e2e_steps):
+                assert leg.step_e2e(want_currents=False) == 0
+            torch.cuda.synchronize()
+            lazy_s = time.perf_counter() - t0
+            ls = eng.stats()
+            if world > 1:
+                dist.barrier()
+            e2e_s, lazy_s = allmax([e2e_s, lazy_s])
+            tot_units, = allmax([float(leg.e2e_units)])   # shards differ by at most one unit
+            tot_units = tot_units * world
+            out["e2e"] = {"value": tot_units * e2e_steps / e2e_s, "unit": "solves/s",
+                          "h2d_bytes_per_step": int(es["h2d_bytes"]), "d2h_bytes_per_step": int(es["d2h_bytes"]),
+                          "steps": e2e_steps, "kernel_ms_per_step": es["kernel_ms"],
+                          "pcie_gbs_per_gpu": (int(es["h2d_bytes"]) + int(es["d2h_bytes"])) * e2e_steps / e2e_s / 1e9,
+                          "units_per_step": int(tot_units),
+                          "sample": "the whole job" if int(tot_units) >= wl["units"] - world else
+                                    "the first %d units of every rank's shard (pinned host result buffers are capped at %d GiB per rank)" % (
+                                        leg.e2e_units, HOST_RESULT_BYTES >> 30),
+                          "node_voltages_only": {"value": tot_units * e2e_steps / lazy_s, "d2h_bytes_per_step": int(ls["d2h_bytes"]),
+                                                 "note": "element currents left to the lazy result objects (computed on access from the node voltages, as simulateAC.ts:94-126 does)"},
+                          "note": "host buffers pinned; bound by the PCIe link when pcie_gbs_per_gpu is near the link rate"}
+        out["n_clock_samples"] = n_samples
+        leg.release()
+        return out
+
+    wl = load_workload(args.workload, world, args.scaling, args.points, args.instances, getattr(args, "device_waves", False))
+    main = time_leg(wl, args.steps, args.warmup, max(1, min(args.steps, 3)), True, 0.5)
+    secondary = {}
+    if args.workload == "cfg2" and not args.no_secondary and not args.points and not args.dense:
+        for name in ("cfg3", "cfg5", "cfg4"):
+            w2 = load_workload(name, world, None)
+            k2 = 2 if name == "cfg4" else 5
+            secondary[name] = time_leg(w2, k2, 1, 2 if name != "cfg4" else 1, False, 0.0)
+            secondary[name]["scaling"] = w2["scaling"]
+    clocks = sampler.stop() if rank == 0 else None
+
     if rank == 0:
-        units = wl["units"]
-        value = world * units * args.steps / (total_ms * 1e-3)
-        peak_hbm = float(peaks.get("hbm_gbs", 6650.0))
-        if wl["kind"] == "ac":
-            ach_f = units * wl["flops_per_unit"] / (kern_ms * 1e-3) / 1e12
-            dense = {"bound": "fp64", "achieved": ach_f, "peak": fp64_peak, "unit": "TFLOP/s",
-                     "frac": ach_f / fp64_peak, "flops_per_solve_dense": wl["flops_per_unit"],
-                     "peak_source": "own DFMA-loop microbenchmark in this run (MEASURED_PEAKS.json has no FP64 figure)"}
-            if tier in (native.TIER_SPARSE, native.TIER_SPARSE_JIT, native.TIER_SPARSE_WARP, native.TIER_BAND):
-                # The sparse program executes ~1e3 flop per solve instead of the dense 7.7e5, so the FP64
-                # pipe cannot bind; what binds is HBM: SURVEY 8(d)'s algorithmic bytes per solve.
-                ach = units * wl["bytes_per_unit"] / (kern_ms * 1e-3) / 1e9
-                roof = {"bound": "hbm", "achieved": ach, "peak": peak_hbm, "unit": "GB/s", "frac": ach / peak_hbm,
-                        "traffic": None, "peak_source": peak_src, "bytes_per_solve": wl["bytes_per_unit"],
-                        "dense_fp64_equivalent": dense,
-                        "executed_fp64": {"complex_fma_per_solve": int(st_last["program_cfma"]),
-                                          "achieved": units * st_last["program_cfma"] * 8 / (kern_ms * 1e-3) / 1e12,
-                                          "peak": fp64_peak, "unit": "TFLOP/s",
-                                          "frac": units * st_last["program_cfma"] * 8 / (kern_ms * 1e-3) / 1e12 / fp64_peak},
-                        "note": "sparse static-pivot LU program (verified per point, dense fallback; tier 5 = compiled "
-                                "straight-line kernel, tier 4 = interpreted, tier 7 = one warp per system): HBM-bound; "
-                                "dense_fp64_equivalent is SURVEY 8(d)'s dense flop figure per solve over the "
-                                "measured DFMA peak and exceeds 1 because structurally zero work is never executed"}
-            else:
-                roof = dict(dense, traffic=None)
-        else:
-            ach = units * wl["bytes_per_unit"] / (kern_ms * 1e-3) / 1e9
-            roof = {"bound": "hbm", "achieved": ach, "peak": peak_hbm, "unit": "GB/s", "frac": ach / peak_hbm,
-                    "traffic": None, "peak_source": peak_src, "bytes_per_solve": wl["bytes_per_unit"]}
-        tr = os.path.join(ROOT, "profiles", "traffic_%s.json" % wl["name"])
-        if os.path.exists(tr):
-            try:
-                roof["traffic"] = json.load(open(tr)).get("dram_bytes_per_launch")
-            except Exception:
-                pass
+        if clocks is not None:
+            clocks["samples_in_timed_region"] = main.pop("n_clock_samples")
+        for v in secondary.values():
+            v.pop("n_clock_samples", None)
         # the CPU port is timed beside the GPU at N = 1 only (the contract's cpu_baseline); larger N reuse that line
         cpu_v, cores, sample = cpu_rate(wl, target_s=12.0) if world == 1 else (None, None, "measured at N=1 only")
-        if wl["kind"] == "tran":
-            src_note = "PULSE evaluated on the device from its parameters" if getattr(args, "device_waves", False) \
-                else "pre-sampled row [nV][steps+1], one load per step"
+        cfg = config_of(wl, world)
         line = {
-            "metric": "batched MNA solves/sec", "value": value, "unit": "solves/s", "n_gpus": world,
-            "steps": args.steps, "warmup": args.warmup, "ms_per_step": total_ms / args.steps,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "metric": "batched MNA solves/sec", "value": main["value"], "unit": "solves/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": main["ms_per_step"],
+            "higher_is_better": True, "scaling": wl["scaling"], "vs_baseline": None,
             "dtype": "c128" if wl["kind"] == "ac" else "f64", "data": "synthetic",
-            "config": {"workload": wl["label"], "per_gpu_units_per_step": units, "tier": tier,
-                       "result_layout": "series-major x[Nvar][ld], ielem[nAc][ld], ld = P rounded up to 32 points" if wl["kind"] == "ac" else "v[step][node][inst]",
-                       "fallback_solves_last_step": int(fallback),
-                       "l2": "no flush: each step writes %.2f GB of results, larger than the 126 MB L2" % (
-                           working_set / 1e9),
-                       "parallelism": "replicated sweep per GPU, contiguous ranges, no collective"},
-            "kernel_ms_per_step": kern_ms,
-            "roofline": roof,
+            "config": cfg,
+            "details": {"units_per_step_whole_job": wl["units"], "rank0_range": main["rank0_range"], "tier": main["tier"],
+                        "chunks_per_step": main["chunks_per_step"],
+                        "result_layout": "series-major x[Nvar][ld], ielem[nAc][ld], ld = chunk rounded up to 32 points" if wl["kind"] == "ac" else "v[step][node][inst]",
+                        "fallback_solves_last_step": main["fallback_solves_last_step"],
+                        "l2": "no flush: every step writes its results (GBs per rank), far more than the 126 MB L2",
+                        "checked_against_oracle": main["checked_against_oracle"]},
+            "kernel_ms_per_step": main["kernel_ms_per_step"],
+            "sustained": main.get("sustained"),
+            "roofline": main["roofline"],
             "cpu_baseline": {"value": cpu_v, "unit": "solves/s", "cores": cores, "kind": "port", "sample": sample},
-            "e2e": {"value": world * units * e2e_steps / e2e_s, "unit": "solves/s",
-                    "h2d_bytes_per_step": int(es["h2d_bytes"]), "d2h_bytes_per_step": int(es["d2h_bytes"]),
-                    "steps": e2e_steps, "kernel_ms_per_step": es["kernel_ms"],
-                    "pcie_gbs": (int(es["h2d_bytes"]) + int(es["d2h_bytes"])) * e2e_steps / e2e_s / 1e9,
-                    "note": "host buffers pinned; bound by the PCIe link when pcie_gbs is near the link rate "
-                            "(results are 3,080 B per cfg2 solve)"},
-            "gpu_launches": int(launches),
+            "e2e": main["e2e"],
+            "gpu_launches": int(main["gpu_launches"]),
             "clocks": clocks,
         }
         if wl["kind"] == "tran":
-            line["config"]["sources"] = src_note
+            line["details"]["sources"] = "PULSE evaluated on the device from its parameters" if wl.get("device_waves") \
+                else "pre-sampled row [nV][steps+1], one load per step"
         line["e2e"]["host_numa"] = numa_note
+        if secondary:
+            line["secondary"] = secondary
         sys.stdout.flush()
         os.write(json_fd, (json.dumps(line) + "\n").encode())
     os.close(json_fd)
-    for p in pins:
-        eng.lib.spicey_host_free(p)
     eng.close()
     if world > 1:
         dist.destroy_process_group()
@@ -556,6 +772,9 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
     ap.add_argument("--workload", default="cfg2", choices=["cfg1", "cfg2", "cfg2mc", "cfg3", "cfg4", "cfg5"])
+    ap.add_argument("--scaling", default=None, choices=["weak", "strong"],
+                    help="weak: the batch grows with the number of ranks (default for cfg2); strong: BASELINE's batch is split (default for the rest)")
+    ap.add_argument("--no-secondary", action="store_true", help="default line only: skip the cfg3 / cfg4 / cfg5 legs")
     ap.add_argument("--dense", action="store_true", help="AC: force the dense pivoted-LU kernel (no sparse program)")
     ap.add_argument("--points", type=int, default=None, help="AC: subsample to this many frequency points")
     ap.add_argument("--instances", type=int, default=None, help="TRAN: number of instances")

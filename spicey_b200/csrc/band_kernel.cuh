@@ -16,7 +16,7 @@
 //   BAND_IELEM    1: element currents are computed and stored
 //   BAND_WARPS    warps per CTA,  BAND_MINB  CTAs per SM (launch bounds)
 //   BAND_RC       1: tables hold (alpha, beta) only (no inductors, real source phasors)
-//   BAND_SYNC     1: the warps of a CTA meet at a barrier once per W steps (instruction-cache locality)
+//   BAND_SYNC     n > 0: the warps of a CTA meet at a barrier n times per W steps (instruction-cache locality)
 //
 // Mapping.  One group of L lanes owns one system.  Pivot step k (column k, pivot row k of the pilot's order) touches
 // the W rows k+1 .. k+W: row i lives in lane i mod L, row slot (i / L) mod RPL, as W band entries (column c in
@@ -229,15 +229,15 @@ extern "C" __global__ void __launch_bounds__(BAND_WARPS * 32, BAND_MINB) spicey_
 
     // ---- elimination of the band columns ----
     for (int kb = 0; kb < nb; kb += BW) {
-#if BAND_SYNC
-      // The unrolled body is several times the instruction cache: warps that run different parts of it evict each
-      // other's lines (25 % of the stall samples were instruction fetch).  Meeting once per W steps keeps them on
-      // the same lines without putting them in lock step.
-      __syncthreads();
-#endif
 #pragma unroll
       for (int s = 0; s < BW; ++s) {
         const int k = kb + s;
+#if BAND_SYNC
+        // The unrolled body is several times the instruction cache: warps that run different parts of it evict each
+        // other's lines (25 % of the stall samples were instruction fetch).  Meeting BAND_SYNC times per W steps keeps
+        // them on the same lines without putting them in lock step.
+        if (s % (BW / (BAND_SYNC < BW ? BAND_SYNC : BW)) == 0) __syncthreads();
+#endif
         if (k < nb) {
           const int pl = s % BAND_L, rs = s / BAND_L;              // owner lane / row slot of rows = s (mod W)
           const int s1 = (s + 1) % BW, pl1 = s1 % BAND_L, rs1 = s1 / BAND_L;
@@ -429,6 +429,12 @@ extern "C" __global__ void __launch_bounds__(BAND_WARPS * 32, BAND_MINB) spicey_
       BAND_LOAD_U(Ua, jb + BH)   // jb + BH + s < nb + W: inside the workspace
       BAND_LOAD_RE(RJ, ENT, jb)
       for (; jb >= 0; jb -= BW) {
+        if (jb >= 2 * BW) {   // the block after next, from DRAM into L2: 16 W^2 bytes of U columns, one 128-byte line per lane and pass
+          const char* nx = (const char*)(Gu + (size_t)(jb - 2 * BW) * BW);
+#pragma unroll
+          for (int ln = 0; ln < (BW * BW * 16 + 127) / 128; ln += BAND_L)
+            if (ln + l < (BW * BW * 16 + 127) / 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(nx + (ln + l) * 128));
+        }
         BAND_LOAD_U(Ub, jb)
 #pragma unroll
         for (int s = BW - 1; s >= BH; --s) BAND_BSTEP(s, Ua[s - BH])

@@ -630,7 +630,7 @@ int prepare_band(DeviceCtx& ctx, const HostPlan& hp, cudaStream_t stream) {
 }
 
 int band_sync_default() {
-  if (const char* e = getenv("SPICEY_BAND_SYNC")) return atoi(e) ? 1 : 0;   // experiments
+  if (const char* e = getenv("SPICEY_BAND_SYNC")) return std::max(0, std::min(16, atoi(e)));   // experiments: barriers per W steps
   return 1;
 }
 

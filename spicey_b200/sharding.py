@@ -33,20 +33,21 @@ def sharded_sweep(solve_slice: Callable[[int, int], np.ndarray], n_units: int, g
     is_complex = np.iscomplexobj(local)
     flat = torch.from_numpy(local.view(np.float64) if is_complex else local).to(dev)
     sizes = [shard_range(n_units, r, world) for r in range(world)]
-    row = int(np.prod(flat.shape[1:])) if flat.dim() > 1 else 1
-    bufs = [torch.empty((h - l,) + tuple(flat.shape[1:]), dtype=flat.dtype, device=dev) for l, h in sizes]
-    dist.all_gather(bufs, flat, group=group) if all(b.shape == bufs[0].shape for b in bufs) else \
-        _uneven_all_gather(bufs, flat, group)
+    # Only rank 0 needs the slabs: a gather (point-to-point sends on NCCL) moves each slab once, where an all-gather
+    # would deliver every slab to every rank.  Slabs differ in length by at most one unit, so they are padded to the
+    # longest one for the collective and trimmed afterwards.
+    longest = max(h - l for l, h in sizes)
+    tail = tuple(flat.shape[1:])
+    send = flat
+    if flat.shape[0] < longest:
+        send = torch.zeros((longest,) + tail, dtype=flat.dtype, device=dev)
+        send[: flat.shape[0]] = flat
+    dst = dist.get_global_rank(group, 0) if group is not None else 0
+    bufs = [torch.empty((longest,) + tail, dtype=flat.dtype, device=dev) for _ in sizes] if rank == 0 else None
+    dist.gather(send.contiguous(), bufs, dst=dst, group=group)
     if rank != 0:
         return None
-    out = torch.cat(bufs, dim=0).cpu().numpy()
-    del row
+    out = torch.cat([b[: h - l] for b, (l, h) in zip(bufs, sizes)], dim=0).cpu().numpy()
     return out.view(np.complex128) if is_complex else out
 
 
-def _uneven_all_gather(bufs, flat, group):
-    import torch.distributed as dist
-    for r, b in enumerate(bufs):
-        if dist.get_rank(group) == r:
-            b.copy_(flat)
-        dist.broadcast(b, src=dist.get_global_rank(group, r) if group is not None else r, group=group)
