@@ -147,7 +147,11 @@ int32_t spicey_device_count(void);
 const char* spicey_last_error(void);
 
 /* devices == NULL or n_devices <= 0 selects device 0. Work is sharded across the
- * handle's devices in contiguous index ranges (SURVEY.md §8 e); no collective. */
+ * handle's devices in contiguous index ranges (SURVEY.md §8 e); no collective.
+ * All devices of a handle are driven from the calling thread: pass page-locked output
+ * buffers (spicey_host_alloc, or memory the caller registered) to a multi-device handle —
+ * a device->host copy into pageable memory blocks the thread, and the next device then
+ * starts late.  Every entry point leaves the caller's current CUDA device unchanged. */
 int32_t spicey_create(const int32_t* devices, int32_t n_devices, spicey_handle** out);
 void spicey_destroy(spicey_handle* h);
 int32_t spicey_get_stats(const spicey_handle* h, spicey_stats* out);

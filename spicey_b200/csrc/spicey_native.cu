@@ -216,6 +216,31 @@ struct spicey_handle {
 
 namespace {
 
+// Restores the caller's current device when a multi-device call returns (a handle inside a torch process must not
+// leave later allocations on another GPU).
+struct DeviceGuard {
+  int prev = -1;
+  DeviceGuard() { if (cudaGetDevice(&prev) != cudaSuccess) { cudaGetLastError(); prev = -1; } }
+  ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+};
+
+// On an early (error) return of a host-buffer call, waits for the copies already queued on the handle's devices:
+// they write into the caller's buffers, which the caller is free to release as soon as the call has returned.
+struct DrainOnError {
+  spicey_handle* h;
+  bool ok = false;
+  explicit DrainOnError(spicey_handle* hh) : h(hh) {}
+  ~DrainOnError() {
+    if (ok) return;
+    for (auto& c : h->devs) {
+      if (cudaSetDevice(c.dev) != cudaSuccess) continue;
+      cudaStreamSynchronize(c.copy);
+      cudaStreamSynchronize(c.compute);
+    }
+    cudaGetLastError();
+  }
+};
+
 // build_plan() through the handle's one-entry cache.
 int cached_plan(spicey_handle* h, const spicey_elem_table* table, const spicey_sweep* sweep) {
   const uint64_t key = table_key(table, sweep);
@@ -1126,6 +1151,7 @@ int32_t spicey_create(const int32_t* devices, int32_t n_devices, spicey_handle**
   *out = nullptr;
   int avail = spicey_device_count();
   if (avail <= 0) return fail(SPICEY_ERR_NO_DEVICE, "no CUDA device available (this library has no CPU path)");
+  DeviceGuard device_guard;
   std::vector<int> ids;
   if (!devices || n_devices <= 0) ids.push_back(0);
   else ids.assign(devices, devices + n_devices);
@@ -1156,6 +1182,7 @@ int32_t spicey_create(const int32_t* devices, int32_t n_devices, spicey_handle**
 
 void spicey_destroy(spicey_handle* h) {
   if (!h) return;
+  DeviceGuard device_guard;
   for (auto& c : h->devs) {
     cudaSetDevice(c.dev);
     cudaDeviceSynchronize();
@@ -1176,6 +1203,7 @@ void spicey_destroy(spicey_handle* h) {
 int32_t spicey_get_stats(const spicey_handle* h, spicey_stats* out) {
   if (!h || !out) return fail(SPICEY_ERR_INVALID, "NULL argument");
   *out = h->stats;
+  DeviceGuard device_guard;
   if (out->fallback_solves < 0) {  // read the device-side counters (synchronises the devices)
     long long total = 0;
     for (const auto& c : h->devs) {
@@ -1212,6 +1240,7 @@ int32_t spicey_ac_solve_device(spicey_handle* h, int32_t dev_index, const spicey
   DeviceCtx& ctx = h->devs[dev_index];
   int rc = cached_plan(h, table, sweep);
   if (rc) return rc;
+  DeviceGuard device_guard;
   const HostPlan& hp = h->hp;
   CUDA_TRY(cudaSetDevice(ctx.dev));
   cudaStream_t st = (cudaStream_t)stream;
@@ -1249,6 +1278,8 @@ int32_t spicey_ac_solve(spicey_handle* h, const spicey_elem_table* table, const 
   const double t0 = now_ms();
   int rc = cached_plan(h, table, sweep);
   if (rc) return rc;
+  DeviceGuard device_guard;   // destroyed last: the caller's device is current again when the call returns
+  DrainOnError drain(h);
   const HostPlan& hp = h->hp;
   const long long n_inst = sweep ? sweep->n_inst : 1;
   const int n_var = sweep ? sweep->n_var : 0;
@@ -1360,6 +1391,7 @@ int32_t spicey_ac_solve(spicey_handle* h, const spicey_elem_table* table, const 
   h->stats.tier = tier;
   h->stats.fallback_solves = -1;
   h->stats.program_cfma = tier == SPICEY_TIER_BAND ? h->devs[0].bp.n_cfma : (tier == SPICEY_TIER_SPARSE || tier == SPICEY_TIER_SPARSE_JIT || tier == SPICEY_TIER_SPARSE_WARP) ? h->devs[0].sp.n_fma : 0;
+  drain.ok = true;
   return SPICEY_SUCCESS;
 }
 
@@ -1387,6 +1419,7 @@ static int32_t tran_solve_device_impl(spicey_handle* h, int32_t dev_index, const
   DeviceCtx& ctx = h->devs[dev_index];
   int rc = cached_plan(h, table, sweep);
   if (rc) return rc;
+  DeviceGuard device_guard;
   const HostPlan& hp = h->hp;
   CUDA_TRY(cudaSetDevice(ctx.dev));
   cudaStream_t st = (cudaStream_t)stream;
@@ -1422,6 +1455,8 @@ static int32_t tran_solve_impl(spicey_handle* h, const spicey_elem_table* table,
   const double t0 = now_ms();
   int rc = cached_plan(h, table, sweep);
   if (rc) return rc;
+  DeviceGuard device_guard;
+  DrainOnError drain(h);
   const HostPlan& hp = h->hp;
   const long long n_inst = sweep ? sweep->n_inst : 1;
   const int n_var = sweep ? sweep->n_var : 0;
@@ -1519,6 +1554,7 @@ static int32_t tran_solve_impl(spicey_handle* h, const spicey_elem_table* table,
   h->stats.d2h_bytes = d2h;
   h->stats.solves = n_inst * S1;
   h->stats.tier = tier;
+  drain.ok = true;
   return SPICEY_SUCCESS;
 }
 
@@ -1667,6 +1703,7 @@ int32_t spicey_measure_fp64_peak(spicey_handle* h, int32_t dev_index, double* gf
   if (!h || !gflops_out) return fail(SPICEY_ERR_INVALID, "NULL argument");
   if (dev_index < 0 || dev_index >= (int)h->devs.size()) return fail(SPICEY_ERR_INVALID, "dev_index out of range");
   DeviceCtx& ctx = h->devs[dev_index];
+  DeviceGuard device_guard;
   CUDA_TRY(cudaSetDevice(ctx.dev));
   int rc = ctx.aux1.ensure(64);
   if (rc) return rc;

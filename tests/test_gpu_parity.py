@@ -786,25 +786,40 @@ def test_long_ladder_default_policy(eng):
 
 
 def test_multi_device_handle_shards_contiguous_ranges(eng):
-    """spicey_create with two devices: the library shards the batch axis in contiguous ranges (no collective)
-    and the result equals the single-device one.  Skipped on a one-GPU box."""
-    if eng.lib.spicey_device_count() < 2:
+    """spicey_create with every device of the box (2, 4 or 8): the library shards the batch axis in contiguous
+    ranges (no collective), the result equals the single-device one bit for bit — compiled ladder kernel (tier 5),
+    banded mesh kernel (tier 8), point-major and series-major, a transient Monte-Carlo batch — and the caller's
+    current device is left alone.  Skipped on a one-GPU box."""
+    ndev = eng.lib.spicey_device_count()
+    if ndev < 2:
         pytest.skip("needs 2 GPUs")
+    import torch
     import spicey_b200 as sp
-    e2 = native.Engine([0, 1])
+    e2 = native.Engine(list(range(ndev)))
     try:
         ck = parse_netlist(w.rc_ladder(64))
         freqs = np.array(sp.analysis.ac_frequencies(ck))[::97]
-        a = sp.simulate_ac_batch(ck, freqs, engine=e2, flags=SM)
-        b = sp.simulate_ac_batch(ck, freqs, engine=eng, flags=SM)
-        assert e2.stats()["n_devices"] == 2
+        for flags in (SM, 0, SM | native.FLAG_SPARSE | native.FLAG_JIT):
+            a = sp.simulate_ac_batch(ck, freqs, engine=e2, flags=flags)
+            assert e2.stats()["n_devices"] == ndev and torch.cuda.current_device() == 0
+            b = sp.simulate_ac_batch(ck, freqs, engine=eng, flags=flags)
+            assert e2.stats()["tier"] == eng.stats()["tier"]
+            assert np.array_equal(a["x"], b["x"]) and np.array_equal(a["ielem"], b["ielem"]) and a["status"].max() == 0
+        ckm = parse_netlist(w.rc_mesh(16))
+        fm = np.ascontiguousarray(np.array(sp.analysis.ac_frequencies(ckm))[::3907])
+        a = sp.simulate_ac_batch(ckm, fm, engine=e2, flags=BAND | SM)
+        assert e2.stats()["tier"] == native.TIER_BAND
+        b = sp.simulate_ac_batch(ckm, fm, engine=eng, flags=BAND | SM)
         assert np.array_equal(a["x"], b["x"]) and np.array_equal(a["ielem"], b["ielem"]) and a["status"].max() == 0
+        xr, ir, st = co.ac_solve(ckm, fm[::64], nthreads=8)
+        assert rel_err(a["x"][0][::64], xr) <= AC_TOL and rel_err(a["ielem"][0][::64], ir) <= AC_TOL
         n = 4096
         ov = {k: v[:n] for k, v in w.rlc_tank_overrides(65536).items()}
         ck = parse_netlist(w.RLC_TANK)
         ta = sp.simulate_tran_batch(ck, n_inst=n, overrides=ov, engine=e2)
         tb = sp.simulate_tran_batch(ck, n_inst=n, overrides=ov, engine=eng)
         assert np.array_equal(ta["v"], tb["v"]) and np.array_equal(ta["ielem"], tb["ielem"])
+        assert torch.cuda.current_device() == 0
     finally:
         e2.close()
 
