@@ -41,7 +41,7 @@
 extern "C" {
 #endif
 
-#define SPICEY_NATIVE_ABI_VERSION 3
+#define SPICEY_NATIVE_ABI_VERSION 4
 
 /* Element kinds of the flat element table (ParsedCircuit, lib/parsing/parseNetlist.ts:12-105). */
 enum {
@@ -50,7 +50,11 @@ enum {
   SPICEY_ELEM_L = 2, /* values: L            state: iPrev (ParsedInductor  :20-26) */
   SPICEY_ELEM_V = 3, /* values: dc, acMag, acPhaseDeg     (ParsedVoltageSource :34-43) */
   SPICEY_ELEM_S = 4, /* values: Ron, Roff, Von, Voff  state: isOn (ParsedSwitch :62-71) */
-  SPICEY_ELEM_D = 5  /* values: Is, N        state: vdPrev (ParsedDiode :53-60)   */
+  SPICEY_ELEM_D = 5, /* values: Is, N        state: vdPrev (ParsedDiode :53-60)   */
+  SPICEY_ELEM_I = 6  /* values: dc, acMag, acPhaseDeg: independent current source from n1 (n+) to n2 (n-) through the
+                        source, b[n+] -= I, b[n-] += I (lib/stamping/stampCurrentReal.ts:3-14, stampCurrentComplex.ts:4-15;
+                        the reference's parser skips `I` lines, parseNetlist.ts:444-446, its stamps exist).  Constant in
+                        transient analysis; appears in the transient element currents (its own value), not in the AC ones */
 };
 
 /* Per-instance status, mapped by the wrapper to the reference's error messages. */
@@ -72,7 +76,7 @@ enum {
 
 /*
  * Flat element table (struct of arrays).  Elements are grouped by kind in the order
- * R, C, L, V, S, D and keep netlist order inside a kind — the order in which the
+ * R, C, L, V, S, D, I and keep netlist order inside a kind — the order in which the
  * reference pushes element currents (simulateAC.ts:94-126, simulateTRAN.ts:173-219).
  * Node ids are the reference's: 0 is ground, the matrix row of node id is id-1
  * (NodeIndex.ts:28-31); the k-th V element owns branch row n_nodes + k

@@ -196,6 +196,14 @@ def stamp_current_real(b, n_plus, n_minus, current):  # stampCurrentReal.ts:3-14
         b[im] = b[im] + current
 
 
+def stamp_current_complex(b, n_plus, n_minus, current):  # stampCurrentComplex.ts:4-15
+    ip, im = _mi(n_plus), _mi(n_minus)
+    if ip >= 0:
+        b[ip] = b[ip].sub(current)
+    if im >= 0:
+        b[im] = b[im].add(current)
+
+
 def stamp_voltage_source_real(A, b, vs, V):  # stampVoltageSourceReal.ts:4-32
     i1, i2, j = _mi(vs.n1), _mi(vs.n2), vs.index
     if i1 >= 0:
@@ -230,6 +238,8 @@ def build_linear_system_for_ac(ckt, f, nvar):  # simulateAC.ts:24-60
         stamp_admittance_complex(A, l.n1, l.n2, _inductor_admittance(f, l.L))
     for vs in ckt.V:
         stamp_voltage_source_complex(A, b, vs, Complex.from_polar(vs.acMag or 0, vs.acPhaseDeg or 0))
+    for cs in getattr(ckt, "I", []):  # extension: the reference ships stampCurrentComplex.ts:4-15 but parses no I line
+        stamp_current_complex(b, cs.n1, cs.n2, Complex.from_polar(cs.acMag or 0, cs.acPhaseDeg or 0))
     return A, b
 
 
@@ -320,6 +330,8 @@ def stamp_all_elements_at_time(A, b, ckt, t, dt, x, it):  # simulateTRAN.ts:25-1
         ieq = idd - gd * vlim
         stamp_admittance_real(A, d.nPlus, d.nMinus, gd)
         stamp_current_real(b, d.nPlus, d.nMinus, ieq)
+    for cs in getattr(ckt, "I", []):  # extension: constant current, stampCurrentReal.ts:3-14
+        stamp_current_real(b, cs.n1, cs.n2, cs.dc or 0)
 
 
 def update_switch_states_from_solution(ckt, x):  # simulateTRAN.ts:108-128
@@ -396,6 +408,8 @@ def simulate_tran(ckt):
             except OverflowError:
                 e = math.inf
             element_currents.setdefault(d.name, []).append(d.model.Is * (e - 1))
+        for cs in getattr(ckt, "I", []):  # extension: the source's own value
+            element_currents.setdefault(cs.name, []).append(cs.dc or 0)
         for c in ckt.C:  # :221-225
             c.vPrev = volt(x, c.n1) - volt(x, c.n2)
         for l in ckt.L:  # :226-231

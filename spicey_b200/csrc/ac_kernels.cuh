@@ -70,7 +70,7 @@ __device__ __forceinline__ int ac_element_values(const DevPlan& P, int type, int
     if (dd < kEps) return ST_CDIV;                        // Complex.div guard (H5)
     Y.x = 0.0 / dd;                                       // (1*0 + 0*d)/dd
     Y.y = (0.0 - d) / dd;                                 // (0*0 - 1*d)/dd
-  } else if (type == ELEM_V) {
+  } else if (type == ELEM_V || type == ELEM_I) {   // source phasor: V rows' rhs, I elements' KCL terms
     double mag = inst_value(P, vidx + 1, inst), deg = inst_value(P, vidx + 2, inst);
     double ph = (deg * kPi) / 180;                        // Complex.ts:16-19
     double s, c;
@@ -81,13 +81,18 @@ __device__ __forceinline__ int ac_element_values(const DevPlan& P, int type, int
   return ST_OK;
 }
 
+// Slot of a source element's phasor: V elements first, then I elements.
+__device__ __forceinline__ int ac_source_slot(const DevPlan& P, int e) {
+  return e < P.off[ELEM_V + 1] ? e - P.off[ELEM_V] : P.nV + (e - P.off[ELEM_I]);
+}
+
 template <bool STRICT, bool GMEM>
 __global__ void ac_cta_kernel(DevPlan P, AcArgs a) {
   extern __shared__ __align__(16) unsigned char smem[];
   const int t = threadIdx.x;
   const int nvar = P.nvar, ne = P.n_elem, MW = P.MW;
   const int nwarps = (blockDim.x + 31) >> 5;
-  const AcSmem L(nvar, ne, P.nV, MW, nwarps, GMEM);
+  const AcSmem L(nvar, ne, P.nV + (P.off[ELEM_I + 1] - P.off[ELEM_I]), MW, nwarps, GMEM);
   unsigned char* gscr = GMEM ? (unsigned char*)a.scratch + (size_t)blockIdx.x * AcSmem::scratch_bytes(nvar, MW) : nullptr;
   cplx* A = GMEM ? (cplx*)gscr : (cplx*)(smem + L.a_off);
   cplx* Yv = (cplx*)(smem + L.y_off);
@@ -119,7 +124,7 @@ __global__ void ac_cta_kernel(DevPlan P, AcArgs a) {
       cplx Y, J;
       int st = ac_element_values<STRICT>(P, meta[e].x, meta[e].y, inst, f, Y, J);
       Yv[e] = Y;
-      if (meta[e].x == ELEM_V) Jv[e - P.off[ELEM_V]] = J;
+      if (meta[e].x == ELEM_V || meta[e].x == ELEM_I) Jv[ac_source_slot(P, e)] = J;
       if (st != ST_OK) atomicMax(&s_status, st);  // R<=0 (3) outranks the L divide guard (2): R loop runs first
     }
     // Phase 2a: clear my row and reset its structural mask.
@@ -137,7 +142,7 @@ __global__ void ac_cta_kernel(DevPlan P, AcArgs a) {
           for (int c = G.ent_ptr[en]; c < G.ent_ptr[en + 1]; ++c) {
             int w = G.contrib[c];
             int src = (w >> 1) & 3, idx = w >> 3;
-            cplx v = src == SRC_Y ? Yv[idx] : (src == SRC_J ? Jv[idx - P.off[ELEM_V]] : make_double2(1.0, 0.0));
+            cplx v = src == SRC_Y ? Yv[idx] : (src == SRC_J ? Jv[ac_source_slot(P, idx)] : make_double2(1.0, 0.0));
             if (w & 1) { acc.x -= v.x; acc.y -= v.y; } else { acc.x += v.x; acc.y += v.y; }
           }
           A[(size_t)G.ent_col[en] * ldr + t] = acc;

@@ -23,7 +23,8 @@ constexpr double kEps = 1e-15;      // lib/constants/EPS.ts:1
 constexpr double kVt300 = 0.02585;  // lib/constants/physics.ts:1
 constexpr double kPi = 3.141592653589793;
 
-enum ElemType { ELEM_R = 0, ELEM_C = 1, ELEM_L = 2, ELEM_V = 3, ELEM_S = 4, ELEM_D = 5 };
+enum ElemType { ELEM_R = 0, ELEM_C = 1, ELEM_L = 2, ELEM_V = 3, ELEM_S = 4, ELEM_D = 5, ELEM_I = 6 };
+constexpr int kElemKinds = 7;
 enum Status { ST_OK = 0, ST_SINGULAR = 1, ST_CDIV = 2, ST_R_NONPOS = 3 };
 
 // Contribution word of the gather plan: idx << 3 | src << 1 | neg.
@@ -39,7 +40,7 @@ struct GatherPlan {
 
 struct DevPlan {
   int nn, nV, nvar, n_elem, n_values, n_ac_elem, n_state;
-  int off[7];                // element group offsets R,C,L,V,S,D,end
+  int off[8];                // element group offsets R,C,L,V,S,D,I,end
   int MW;                    // mask words per row = ceil((nvar+1)/32)
   int n_var;                 // swept value slots
   long long n_inst;

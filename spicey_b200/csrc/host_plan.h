@@ -42,7 +42,8 @@ struct HostGather {
 
 struct HostPlan {
   int nn = 0, nV = 0, nvar = 0, n_elem = 0, n_values = 0, n_ac_elem = 0, n_state = 0, MW = 0;
-  int off[7] = {0, 0, 0, 0, 0, 0, 0};
+  int off[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  int nI = 0;   // independent current sources (stampCurrentReal.ts / stampCurrentComplex.ts)
   std::vector<int4> ends;
   std::vector<int2> meta;
   std::vector<int> state_idx;
@@ -51,7 +52,7 @@ struct HostPlan {
   HostGather ac, tran;
 };
 
-const int kValueSlots[6] = {1, 1, 1, 3, 4, 2};
+const int kValueSlots[7] = {1, 1, 1, 3, 4, 2, 3};
 
 struct GatherBuilder {
   int nvar;
@@ -112,11 +113,11 @@ inline int build_plan(const spicey_elem_table* tb, const spicey_sweep* sw, HostP
   hp.meta.resize(hp.n_elem);
   hp.state_idx.assign(hp.n_elem, -1);
   int prev = 0, ns = 0;
-  int count[6] = {0, 0, 0, 0, 0, 0};
+  int count[7] = {0, 0, 0, 0, 0, 0, 0};
   for (int e = 0; e < hp.n_elem; ++e) {
     int ty = tb->type[e];
-    if (ty < 0 || ty > 5) return fail(SPICEY_ERR_INVALID, "unknown element type");
-    if (ty < prev) return fail(SPICEY_ERR_INVALID, "elements must be grouped in the order R,C,L,V,S,D");
+    if (ty < 0 || ty > 6) return fail(SPICEY_ERR_INVALID, "unknown element type");
+    if (ty < prev) return fail(SPICEY_ERR_INVALID, "elements must be grouped in the order R,C,L,V,S,D,I");
     prev = ty;
     count[ty]++;
     int n1 = tb->n1[e], n2 = tb->n2[e];
@@ -131,8 +132,9 @@ inline int build_plan(const spicey_elem_table* tb, const spicey_sweep* sw, HostP
   }
   hp.n_state = ns;
   hp.off[0] = 0;
-  for (int k = 0; k < 6; ++k) hp.off[k + 1] = hp.off[k] + count[k];
+  for (int k = 0; k < 7; ++k) hp.off[k + 1] = hp.off[k] + count[k];
   hp.nV = count[ELEM_V];
+  hp.nI = count[ELEM_I];
   hp.nvar = hp.nn + hp.nV;
   hp.n_ac_elem = hp.off[ELEM_V + 1];
   hp.MW = (hp.nvar + 1 + 31) / 32;
@@ -157,6 +159,10 @@ inline int build_plan(const spicey_elem_table* tb, const spicey_sweep* sw, HostP
     if (ty == ELEM_V) ac.vsource(e, hp.ends[e].x, hp.ends[e].y, hp.nn + (e - hp.off[ELEM_V]));
     else ac.admittance(e, hp.ends[e].x, hp.ends[e].y);
   }
+  // independent current sources: b[n+] -= I, b[n-] += I (stampCurrentComplex.ts:4-15 / stampCurrentReal.ts:3-14).  The
+  // reference ships the stamps but its parser skips `I` lines (parseNetlist.ts:444-446), so it defines no position for
+  // them in the stamping order; they contribute to the right-hand side only, after every other element.
+  for (int e = hp.off[ELEM_I]; e < hp.off[ELEM_I + 1]; ++e) ac.current(e, hp.ends[e].x, hp.ends[e].y);
   // TRAN stamping order R, C, L, S, V, D (simulateTRAN.ts:35-101).
   const int order[6] = {ELEM_R, ELEM_C, ELEM_L, ELEM_S, ELEM_V, ELEM_D};
   for (int oi = 0; oi < 6; ++oi) {
@@ -168,6 +174,7 @@ inline int build_plan(const spicey_elem_table* tb, const spicey_sweep* sw, HostP
       if (ty == ELEM_C || ty == ELEM_L || ty == ELEM_D) tr.current(e, n1, n2);
     }
   }
+  for (int e = hp.off[ELEM_I]; e < hp.off[ELEM_I + 1]; ++e) tr.current(e, hp.ends[e].x, hp.ends[e].y);
   ac.finish(hp.ac, hp.MW);
   tr.finish(hp.tran, hp.MW);
   return SPICEY_SUCCESS;

@@ -179,7 +179,7 @@ int upload_plan(DeviceCtx& ctx, const HostPlan& hp, cudaStream_t stream, DevPlan
   memset(&dp, 0, sizeof(dp));
   dp.nn = hp.nn; dp.nV = hp.nV; dp.nvar = hp.nvar; dp.n_elem = hp.n_elem; dp.n_values = hp.n_values;
   dp.n_ac_elem = hp.n_ac_elem; dp.n_state = hp.n_state; dp.MW = hp.MW;
-  for (int k = 0; k < 7; ++k) dp.off[k] = hp.off[k];
+  for (int k = 0; k < 8; ++k) dp.off[k] = hp.off[k];
   dp.ends = (const int4*)(b + o_ends);
   dp.meta = (const int2*)(b + o_meta);
   dp.state_idx = (const int*)(b + o_sidx);
@@ -882,9 +882,9 @@ int launch_ac_dense(DeviceCtx& ctx, const HostPlan& hp, const DevPlan& dp, const
   const bool strict = flags & SPICEY_FLAG_STRICT;
   const int NT = round32(hp.nvar);
   const int nwarps = NT / 32;
-  AcSmem sm(hp.nvar, hp.n_elem, hp.nV, hp.MW, nwarps, false);
+  AcSmem sm(hp.nvar, hp.n_elem, hp.nV + hp.nI, hp.MW, nwarps, false);
   bool gmem = (flags & SPICEY_FLAG_FORCE_GMEM) || sm.total > ctx.smem_optin;
-  AcSmem L(hp.nvar, hp.n_elem, hp.nV, hp.MW, nwarps, gmem);
+  AcSmem L(hp.nvar, hp.n_elem, hp.nV + hp.nI, hp.MW, nwarps, gmem);
   if (L.total > ctx.smem_optin) return fail(SPICEY_ERR_UNSUPPORTED, "element table too large for shared memory");
   void (*kern)(DevPlan, AcArgs) =
       gmem ? (strict ? ac_cta_kernel<true, true> : ac_cta_kernel<false, true>)
@@ -916,6 +916,9 @@ int launch_ac(DeviceCtx& ctx, const HostPlan& hp, const DevPlan& dp, const AcArg
                            (args.p_count >= 2048 || (flags & SPICEY_FLAG_SPARSE));
   if (want_sparse) {
     const bool eager = dp.n_inst > 1 || dp.n_var > 0;  // component sweep / Monte-Carlo: per-instance stamping
+    // the per-instance stamping of the sparse tiers indexes the R, C, L, V elements only: sweeps of circuits with
+    // current sources stay with the dense kernel
+    if (eager && hp.nI > 0) return launch_ac_dense(ctx, hp, dp, args, flags, stream, tier_out, launches);
     const uint64_t key = plan_key(hp) ^ (eager ? 0x9e3779b97f4a7c15ull : 0ull);
     if (ctx.sp_key != key) {
       if (!pilot_known) {  // device-resident frequencies: fetch one representative value
@@ -1030,7 +1033,7 @@ int launch_tran(DeviceCtx& ctx, const HostPlan& hp, const DevPlan& dp, const Tra
   for (int k = 0; k < hp.nV; ++k) jit_waves_ok &= !(waves[k].x == WAVE_PWL && waves[k].z > kTranJitMaxPwlPairs);
   // Compiled per-topology kernel (tran_codegen.h): small systems, batches large enough to pay for the compile.
   if (!strict && !(flags & (SPICEY_FLAG_FORCE_CTA | SPICEY_FLAG_FORCE_GMEM | SPICEY_FLAG_GENERIC_THREAD | SPICEY_FLAG_NO_JIT)) &&
-      hp.nvar <= 8 && hp.n_elem <= 48 && hp.nV <= 32 && args.n_local < (1ll << 29) && jit_waves_ok &&
+      hp.nvar <= 8 && hp.n_elem <= 48 && hp.nV <= 32 && hp.nI == 0 && args.n_local < (1ll << 29) && jit_waves_ok &&
       ((flags & SPICEY_FLAG_JIT) || args.n_local * (args.steps + 1) >= kTranJitMinSteps)) {
     if (DeviceCtx::JitVariant* jv = ensure_tran_jit(ctx, hp, waves, args.ielem != nullptr)) {
       TranJitArgs j;
@@ -1047,7 +1050,7 @@ int launch_tran(DeviceCtx& ctx, const HostPlan& hp, const DevPlan& dp, const Tra
   }
   const int n_ent = (int)hp.tran.ent_col.size(), n_con = (int)hp.tran.contrib.size();
   // Register-resident small-system kernel (Nvar <= 6).
-  if (!(flags & (SPICEY_FLAG_FORCE_CTA | SPICEY_FLAG_FORCE_GMEM | SPICEY_FLAG_GENERIC_THREAD)) && hp.nvar <= 6) {
+  if (!(flags & (SPICEY_FLAG_FORCE_CTA | SPICEY_FLAG_FORCE_GMEM | SPICEY_FLAG_GENERIC_THREAD)) && hp.nvar <= 6 && hp.nI == 0) {
     const bool dyn = hp.off[ELEM_D + 1] > hp.off[ELEM_S];
     typedef void (*KernT)(DevPlan, TranArgs);
     KernT kern = nullptr;
@@ -1631,7 +1634,7 @@ int64_t spicey_debug_tran_source_waves(const spicey_elem_table* table, const spi
                                        int32_t with_ielem, char* buf, int64_t cap) {
   HostPlan hp;
   if (build_plan(table, sweep, hp) != SPICEY_SUCCESS) return -1;
-  if (hp.nvar > 8 || hp.n_elem > 48 || hp.nV > 32) { fail(SPICEY_ERR_UNSUPPORTED, "the compiled transient kernel covers Nvar <= 8"); return -1; }
+  if (hp.nvar > 8 || hp.n_elem > 48 || hp.nV > 32 || hp.nI > 0) { fail(SPICEY_ERR_UNSUPPORTED, "the compiled transient kernel covers Nvar <= 8 without current sources"); return -1; }
   std::string src;
   WaveList wl;
   if (build_waves(hp, waves, nullptr, true, wl) != SPICEY_SUCCESS) return -1;

@@ -134,7 +134,7 @@ __device__ __forceinline__ void element_constants(const DevPlan& P, int type, in
     c4[0] = C / dtc; c4[1] = C;
   } else if (type == ELEM_L) {
     c4[0] = dtc / inst_value(P, vidx, inst);
-  } else if (type == ELEM_V) {
+  } else if (type == ELEM_V || type == ELEM_I) {   // dc value (I: constant current, stampCurrentReal.ts:3-14)
     c4[0] = inst_value(P, vidx, inst);
   } else if (type == ELEM_S) {
     c4[0] = fmax(fabs(inst_value(P, vidx, inst)), kEps);          // Rclamped :60-61
@@ -248,7 +248,7 @@ __global__ void tran_thread_kernel(DevPlan P, TranArgs a, int n_ent, int n_con) 
     element_constants(P, meta[e].x, meta[e].y, inst, dtc, c4);
     for (int q = 0; q < 4; ++q) ec[(4 * e + q) * NT] = c4[q];
     g[e * NT] = c4[0];
-    jj[e * NT] = 0.0;
+    jj[e * NT] = meta[e].x == ELEM_I ? c4[0] : 0.0;   // a current source's right-hand-side term never changes
   }
   for (int s = 0; s < ns; ++s) st[s * NT] = a.state0 ? a.state0[(long long)s * P.n_inst + inst] : 0.0;
 
@@ -325,6 +325,8 @@ __global__ void tran_thread_kernel(DevPlan P, TranArgs a, int n_ent, int n_con) 
         cur = x[(nn + e - P.off[ELEM_V]) * NT];
       } else if (type == ELEM_S) {
         cur = d / (st[sidx[e] * NT] != 0.0 ? ec[(4 * e) * NT] : ec[(4 * e + 1) * NT]);  // post-toggle state :196-204
+      } else if (type == ELEM_I) {
+        cur = ec[(4 * e) * NT];
       } else {
         cur = t_mul<STRICT>(ec[(4 * e) * NT], t_sub<STRICT>(exp(d / ec[(4 * e + 1) * NT]), 1.0));  // unclamped vd (H6)
         st[sidx[e] * NT] = d;
@@ -403,7 +405,7 @@ __global__ void tran_cta_kernel(DevPlan P, TranArgs a, double* scratch) {
       element_constants(P, meta[e].x, meta[e].y, inst, dtc, c4);
       for (int q = 0; q < 4; ++q) ec[4 * e + q] = c4[q];
       g[e] = c4[0];
-      jj[e] = 0.0;
+      jj[e] = meta[e].x == ELEM_I ? c4[0] : 0.0;
     }
     for (int s = t; s < ns; s += NT) st[s] = a.state0 ? a.state0[(long long)s * P.n_inst + inst] : 0.0;
     __syncthreads();
@@ -480,7 +482,8 @@ __global__ void tran_cta_kernel(DevPlan P, TranArgs a, double* scratch) {
         } else if (type == ELEM_V) cur = xs[nn + e - P.off[ELEM_V]];
         else if (type == ELEM_S) {
           cur = d / (st[sidx[e]] != 0.0 ? ec[4 * e] : ec[4 * e + 1]);
-        } else {
+        } else if (type == ELEM_I) cur = ec[4 * e];
+        else {
           cur = t_mul<STRICT>(ec[4 * e], t_sub<STRICT>(exp(d / ec[4 * e + 1]), 1.0));
           st[sidx[e]] = d;
         }

@@ -12,8 +12,8 @@ import numpy as np
 
 from . import build as _build
 
-ELEM_R, ELEM_C, ELEM_L, ELEM_V, ELEM_S, ELEM_D = range(6)
-VALUE_SLOTS = {ELEM_R: 1, ELEM_C: 1, ELEM_L: 1, ELEM_V: 3, ELEM_S: 4, ELEM_D: 2}
+ELEM_R, ELEM_C, ELEM_L, ELEM_V, ELEM_S, ELEM_D, ELEM_I = range(7)
+VALUE_SLOTS = {ELEM_R: 1, ELEM_C: 1, ELEM_L: 1, ELEM_V: 3, ELEM_S: 4, ELEM_D: 2, ELEM_I: 3}
 ST_OK, ST_SINGULAR, ST_CDIV, ST_R_NONPOS = 0, 1, 2, 3
 FLAG_STRICT, FLAG_FORCE_GMEM, FLAG_FORCE_CTA, FLAG_DENSE, FLAG_SPARSE, FLAG_GENERIC_THREAD = 1, 2, 4, 8, 16, 32
 FLAG_SERIES_MAJOR, FLAG_JIT, FLAG_NO_JIT, FLAG_WARP, FLAG_NO_WARP = 64, 128, 256, 512, 1024
@@ -282,7 +282,7 @@ class Engine:
 
     def __init__(self, devices: Optional[Sequence[int]] = None, lib_path: Optional[str] = None):
         self.lib = load_library(lib_path)
-        if self.lib.spicey_native_abi_version() != 3:
+        if self.lib.spicey_native_abi_version() != 4:
             raise NativeError(ERR_INVALID, "ABI version mismatch")
         self._h = C.c_void_p()
         arr = None if devices is None else np.ascontiguousarray(devices, dtype=np.int32)

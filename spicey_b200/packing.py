@@ -1,6 +1,6 @@
 """ParsedCircuit -> flat element table (the `lib/analysis` packer of the north star).
 
-Elements are grouped R, C, L, V, S, D in netlist order inside a group — the order in
+Elements are grouped R, C, L, V, S, D (then I, an extension) in netlist order inside a group — the order in
 which the reference pushes element currents (simulateAC.ts:94-126,
 simulateTRAN.ts:173-219).  Values are taken from the parsed circuit, i.e. produced by
 the reference parser's own arithmetic (hazard H1).
@@ -11,11 +11,12 @@ from typing import Dict, Optional
 
 import numpy as np
 
-from .native import (ELEM_C, ELEM_D, ELEM_L, ELEM_R, ELEM_S, ELEM_V, WAVE_DC, WAVE_PULSE, WAVE_PWL, ElemTable, Sweep,
+from .native import (ELEM_C, ELEM_D, ELEM_I, ELEM_L, ELEM_R, ELEM_S, ELEM_V, WAVE_DC, WAVE_PULSE, WAVE_PWL, ElemTable, Sweep,
                      Waves)
 
 _PARAM_OFFSETS = {
     ELEM_V: {"dc": 0, "acmag": 1, "acphase": 2},
+    ELEM_I: {"dc": 0, "acmag": 1, "acphase": 2},
     ELEM_S: {"ron": 0, "roff": 1, "von": 2, "voff": 3},
     ELEM_D: {"is": 0, "n": 1},
 }
@@ -50,6 +51,8 @@ def pack_circuit(ckt, device_waves: bool = False) -> ElemTable:
         if d.model is None:
             continue
         add(ELEM_D, d.nPlus, d.nMinus, [d.model.Is, d.model.N], d.name)
+    for cs in getattr(ckt, "I", []):   # extension (parse_netlist(current_sources=True)): last group of the table
+        add(ELEM_I, cs.n1, cs.n2, [cs.dc or 0, cs.acMag or 0, cs.acPhaseDeg or 0], cs.name)
     kinds, widx, npairs, wparams = [], [], [], {}
     if device_waves:
         for v in ckt.V:

@@ -240,6 +240,19 @@ class VoltageSource:
 
 
 @dataclass
+class CurrentSource:
+    """Independent current source, n1 (n+) -> n2 (n-) through the source.  NOT part of the reference's ParsedCircuit:
+    its parser skips `I` lines (parseNetlist.ts:444-446) although lib/stamping/stampCurrent{Real,Complex}.ts exist.
+    parse_netlist(text, current_sources=True) is the opt-in extension that fills ckt.I (north star: "R, L, C, V and I")."""
+    name: str
+    n1: int
+    n2: int
+    dc: float = 0.0
+    acMag: float = 0.0
+    acPhaseDeg: float = 0.0
+
+
+@dataclass
 class VSwitchModel:
     name: str
     Ron: float = 1.0
@@ -317,6 +330,7 @@ class ParsedCircuit:  # parseNetlist.ts:83-103
     V: List[VoltageSource] = field(default_factory=list)
     S: List[Switch] = field(default_factory=list)
     D: List[Diode] = field(default_factory=list)
+    I: List["CurrentSource"] = field(default_factory=list)   # extension, empty unless parse_netlist(current_sources=True)
     analyses: Analyses = field(default_factory=Analyses)
     probes: Probes = field(default_factory=Probes)
     skipped: List[str] = field(default_factory=list)
@@ -352,8 +366,10 @@ def _parse_model_params(params: str) -> List[tuple]:
     return out
 
 
-def parse_netlist(text: str) -> ParsedCircuit:
-    """Netlist text -> ParsedCircuit with the reference's grammar and quirks."""
+def parse_netlist(text: str, current_sources: bool = False) -> ParsedCircuit:
+    """Netlist text -> ParsedCircuit with the reference's grammar and quirks.
+    current_sources=True: `I<name> n+ n- [dc] [DC v] [AC mag [phase]]` lines fill ckt.I instead of ckt.skipped (the
+    reference skips them, parseNetlist.ts:444-446; same value grammar as a V line without waveforms)."""
     ckt = ParsedCircuit()
     seen_title = False
 
@@ -515,6 +531,30 @@ def parse_netlist(text: str) -> ParsedCircuit:
                     else:
                         i += 1
                 ckt.V.append(vs)
+            elif tc == "i" and current_sources:
+                n1 = ckt.nodes.get_or_create(_require(tokens, 1, "Current source missing node"))
+                n2 = ckt.nodes.get_or_create(_require(tokens, 2, "Current source missing node"))
+                cs = CurrentSource(name, n1, n2)
+                i = 3
+                if i < len(tokens) and not re.match(r"^[a-zA-Z]", tokens[i]):
+                    cs.dc = parse_number_with_units(tokens[i])
+                    i += 1
+                while i < len(tokens):
+                    key = tokens[i].lower()
+                    if key == "dc":
+                        cs.dc = parse_number_with_units(_require(tokens, i + 1, "DC value missing"))
+                        i += 2
+                    elif key == "ac":
+                        cs.acMag = parse_number_with_units(_require(tokens, i + 1, "AC magnitude missing"))
+                        phase = tokens[i + 2] if i + 2 < len(tokens) else None
+                        if phase is not None and re.match(r"^[+-]?\d", phase):
+                            cs.acPhaseDeg = parse_number_with_units(phase)
+                            i += 3
+                        else:
+                            i += 2
+                    else:
+                        i += 1
+                ckt.I.append(cs)
             elif tc == "s":
                 n1 = ckt.nodes.get_or_create(_require(tokens, 1, "Switch missing node"))
                 n2 = ckt.nodes.get_or_create(_require(tokens, 2, "Switch missing node"))

@@ -768,6 +768,73 @@ def test_ac_band_tier_pivot_changes_fall_back(eng):
     assert 0 < stt["fallback_solves"] < freqs.shape[0], stt
 
 
+NORTON = """* current source
+i1 0 n1 dc 1m ac 2m 30
+r0 n1 0 500
+r1 n1 n2 1k
+c1 n2 0 1u
+l1 n2 n3 1m
+r2 n3 0 50
+.ac dec 5 10 100k
+.tran 10u 5m
+.end
+"""
+THEVENIN = NORTON.replace("i1 0 n1 dc 1m ac 2m 30\nr0 n1 0 500", "v1 nx 0 dc 0.5 ac 1 30\nr0 nx n1 500")
+
+
+def test_current_sources_ac_and_tran(eng):
+    """SPICEY_ELEM_I (north star: "R, L, C, V and I"): the reference ships stampCurrentReal.ts / stampCurrentComplex.ts
+    but parses no I line, so the element enters through parse_netlist(current_sources=True).  Checked against the
+    oracle extended by the same two stamps, and against the Thevenin-equivalent V + R netlist the reference does
+    parse (every node voltage of the rest of the circuit is the same)."""
+    import spicey_b200 as sp
+    ck = parse_netlist(NORTON, current_sources=True)
+    assert len(ck.I) == 1 and ck.I[0].dc == 1e-3 and ck.I[0].acMag == 2e-3 and ck.I[0].acPhaseDeg == 30
+    assert len(parse_netlist(NORTON).I) == 0 and len(parse_netlist(NORTON).skipped) == 1   # the reference's behaviour
+    ref = o.simulate_ac(parse_netlist(NORTON, current_sources=True))
+    ckt = parse_netlist(THEVENIN)
+    freqs = np.array(ref["freqs"])
+    xt, _, stt = co.ac_solve(ckt, freqs)
+    names = ["n1", "n2", "n3"]
+    for flags in (0, native.FLAG_STRICT, native.FLAG_SPARSE, native.FLAG_SPARSE | native.FLAG_JIT | SM, BAND, BAND | SM,
+                  native.FLAG_SPARSE | native.FLAG_WARP):
+        out = sp.simulate_ac_batch(ck, freqs, engine=eng, flags=flags)
+        assert out["status"].max() == 0, (flags, eng.stats())
+        for j, nm in enumerate(out["node_names"]):
+            want = np.array([complex(z) for z in ref["nodeVoltages"][nm]])
+            assert rel_err(out["x"][0][:, j], want) <= AC_TOL, (flags, nm)
+        for j, nm in enumerate(out["element_names"]):
+            want = np.array([complex(z) for z in ref["elementCurrents"][nm]])
+            assert rel_err(out["ielem"][0][:, j], want) <= AC_TOL, (flags, nm)
+        # Thevenin equivalent: node order there is nx, n1, n2, n3
+        tn = ckt.nodes.rev[1:]
+        for nm in names:
+            assert rel_err(out["x"][0][:, out["node_names"].index(nm)], xt[:, tn.index(nm)]) <= AC_TOL, (flags, nm)
+    assert stt.max() == 0
+    # a sweep of the source magnitude (per-instance values): circuits with current sources stay with the dense kernel
+    mags = np.array([1e-3, 2e-3, 4e-3])
+    outs = sp.simulate_ac_batch(ck, freqs, n_inst=3, overrides={"i1.acmag": mags}, engine=eng)
+    assert outs["status"].max() == 0
+    base = outs["x"][1]
+    assert rel_err(outs["x"][0] * 2, base) <= 1e-12 and rel_err(outs["x"][2] / 2, base) <= 1e-12
+    # transient: constant 1 mA into R || C ... ; its own value is recorded as the element current
+    reft = o.simulate_tran(parse_netlist(NORTON, current_sources=True))
+    reftt = o.simulate_tran(parse_netlist(THEVENIN))
+    for flags in (0, native.FLAG_FORCE_CTA, native.FLAG_STRICT):
+        got = sp.simulate_tran_batch(parse_netlist(NORTON, current_sources=True), engine=eng, flags=flags)
+        assert got["status"].max() == 0
+        for j, nm in enumerate(got["node_names"]):
+            want = np.asarray(reft["nodeVoltages"][nm])
+            assert np.max(np.abs(got["v"][:, j, 0] - want)) <= TRAN_TOL * max(1.0, np.max(np.abs(want))), (flags, nm)
+            if nm in names:
+                wt = np.asarray(reftt["nodeVoltages"][nm])
+                assert np.max(np.abs(got["v"][:, j, 0] - wt)) <= TRAN_TOL * max(1.0, np.max(np.abs(wt))), (flags, nm)
+        for j, nm in enumerate(got["element_names"]):
+            want = np.asarray(reft["elementCurrents"][nm])
+            assert np.max(np.abs(got["ielem"][:, j, 0] - want)) <= TRAN_TOL * max(1e-30, np.max(np.abs(want))), (flags, nm)
+        assert got["element_names"][-1] == "i1" and np.all(got["ielem"][:, -1, 0] == 1e-3)
+
+
 def test_long_ladder_default_policy(eng):
     """A 400-node ladder (Nvar = 401, 3,200 points): chain-like, so the warp tier declines (2-3 updates per row
     would idle the lanes), and 801 values cross into the back-substitution, far more than a thread's registers

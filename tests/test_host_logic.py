@@ -116,7 +116,7 @@ def test_library_loads_and_exports_every_declared_symbol():
     assert declared == set(native.EXPORTS), declared ^ set(native.EXPORTS)
     for sym in declared:
         assert getattr(lib, sym) is not None
-    assert lib.spicey_native_abi_version() == 3
+    assert lib.spicey_native_abi_version() == 4
 
 
 def test_no_cpu_fallback_without_device():
@@ -184,3 +184,20 @@ def test_bench_reference_arm_prints_one_contract_line():
         r2 = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--workload", "cfg1", "--steps", "1",
                              "--warmup", "1"], capture_output=True, text=True, timeout=300)
         assert r2.returncode != 0 and "no CPU path" in (r2.stderr + r2.stdout)
+
+
+def test_current_source_extension_parses_and_packs():
+    """`I` lines: skipped like the reference does by default, parsed into ckt.I on request, packed as the last group."""
+    from spicey_b200 import native
+    from spicey_b200.packing import pack_circuit
+    from spicey_b200.parsing import parse_netlist
+    text = "* i\nv1 a 0 dc 1\ni1 0 b dc 2m ac 3m 45\nr1 a b 1k\nc1 b 0 1u\n.ac dec 2 1 10\n.end\n"
+    ref_like = parse_netlist(text)
+    assert ref_like.I == [] and ref_like.skipped == ["i1 0 b dc 2m ac 3m 45"]
+    ck = parse_netlist(text, current_sources=True)
+    assert len(ck.I) == 1 and (ck.I[0].n1, ck.I[0].n2) == (0, ck.nodes.get_or_create("b"))
+    tb = pack_circuit(ck)
+    assert list(tb.type) == [native.ELEM_R, native.ELEM_C, native.ELEM_V, native.ELEM_I]
+    assert tb.n_ac_elem == 3 and tb.n_elem == 4 and tb.nvar == 3 and tb.names[-1] == "i1"
+    vi = int(tb.value_idx[-1])
+    assert list(tb.values[vi:vi + 3]) == [2 * 1e-3, 3 * 1e-3, 45.0]

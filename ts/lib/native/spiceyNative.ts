@@ -30,7 +30,8 @@ const { symbols: C } = dlopen(LIB_PATH, {
   },
 })
 
-export const ELEM = { R: 0, C: 1, L: 2, V: 3, S: 4, D: 5 } as const
+/** SPICEY_ELEM_*; I (independent current source) has no ParsedCircuit counterpart yet: the parser skips `I` lines. */
+export const ELEM = { R: 0, C: 1, L: 2, V: 3, S: 4, D: 5, I: 6 } as const
 /** SPICEY_FLAG_SERIES_MAJOR: x is [Nvar][P], ielem [nAc][P] — one contiguous slab per series. */
 export const FLAG_SERIES_MAJOR = 64
 export const STATUS = { OK: 0, SINGULAR: 1, CDIV: 2, R_NONPOS: 3 } as const
@@ -62,7 +63,7 @@ function check(rc: number) {
     throw new Error(`spicey_native error ${rc}: ${C.spicey_last_error()}`)
 }
 
-/** struct spicey_elem_table: 4 x int32 then 7 pointers (64 bytes). */
+/** struct spicey_elem_table: 4 x int32 then 7 pointers (72 bytes). */
 function tableStruct(t: ElemTable) {
   const buf = new ArrayBuffer(16 + 7 * 8)
   const dv = new DataView(buf)
@@ -99,7 +100,7 @@ function wavesStruct(w: Waves) {
 let handle: Pointer | null = null
 function getHandle(): Pointer {
   if (handle) return handle
-  if (C.spicey_native_abi_version() !== 3)
+  if (C.spicey_native_abi_version() !== 4)
     throw new Error("spicey_native ABI version mismatch")
   const out = new BigUint64Array(1)
   check(C.spicey_create(null, 0, ptr(out)))
