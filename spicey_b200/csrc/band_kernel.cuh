@@ -79,7 +79,7 @@ struct BandArgs {   // must match BandArgs in spicey_native.cu
   const double4* el_rec;                // [n_ac_elem] {bits of (i1, i2), ya, yb, yg}: current = Y (x[i1] - x[i2]),
                                         // Y = ya + j (w yb - yg / w); i = n: the zero slot (ground); V: (branch, n, 1, 0, 0)
   const double* ind_L;
-  int n, nb, n_ac_elem, v_first, n_ind;
+  int n, nb, n_out, n_ac_elem, n_ind;           // n = nb + NB unknowns incl. padding (nb: a multiple of W), n_out: the circuit's own
   int o_init, o_initb, o_brd0, o_bb0, o_step;   // table offsets (entries); o_step: record of step 0
 };
 
@@ -238,6 +238,9 @@ extern "C" __global__ void __launch_bounds__(BAND_WARPS * 32, BAND_MINB) spicey_
         // them on the same lines without putting them in lock step.
         if (s % (BW / (BAND_SYNC < BW ? BAND_SYNC : BW)) == 0) __syncthreads();
 #endif
+        // (always true — nb is a multiple of W: band_plan.h pads with identity rows — but the branch keeps the W steps
+        //  separate basic blocks: scheduled as one, the compiler hoists the next step's loads over this step's updates
+        //  and spills)
         if (k < nb) {
           const int pl = s % BAND_L, rs = s / BAND_L;              // owner lane / row slot of rows = s (mod W)
           const int s1 = (s + 1) % BW, pl1 = s1 % BAND_L, rs1 = s1 / BAND_L;
@@ -251,12 +254,13 @@ extern "C" __global__ void __launch_bounds__(BAND_WARPS * 32, BAND_MINB) spicey_
           const double2* rk = ring + (k & (BRING - 1)) * (BST_STRIDE * BREC);
           const double2* rk1 = ring + ((k + 1) & (BRING - 1)) * (BST_STRIDE * BREC);
 #define RECS(off) band_rec_sm(rk, (off), w, iw)
-          const uint2 fl = *(const uint2*)(rk + BST_FLAGS * BREC);
           const bcplx dg = Pc[BW + BNB + 1];
+          const uint2 fl = *(const uint2*)(rk + BST_FLAGS * BREC);
           const double mp = band_mag(dg);
           bad |= (unsigned)!(mp >= B_EPS);            // singular / Complex.div guard / NaN
           const double inv = band_rcp(mp);
           const bcplx r = make_double2(dg.x * inv, -dg.y * inv);
+          const double thr_mp = B_THR * mp;           // |f|^2 = |a_ik|^2 / |pivot|^2 < EPS^2  (solveComplex.ts:46)
           // multipliers of my rows; the new column k + W takes over the slot of column k
           bcplx F[BAND_RPL];
 #pragma unroll
@@ -278,9 +282,8 @@ extern "C" __global__ void __launch_bounds__(BAND_WARPS * 32, BAND_MINB) spicey_
             const double m = band_mag(aik);
             const bool strict = (fl.x >> (l + BAND_L * q)) & 1u;
             bad |= strict ? (unsigned)!(m < mp) : (unsigned)(m > mp);          // solveComplex.ts:18-28: first maximum wins
-            bcplx f = band_mul(aik, r);
-            if (band_mag(f) < B_THR) f = make_double2(0.0, 0.0);   // solveComplex.ts:46
-            F[q] = f;
+            const bcplx f = band_mul(aik, r);
+            F[q] = m < thr_mp ? make_double2(0.0, 0.0) : f;
           }
           // border rows: column k's entry sits in lane pl, slot rs
           bcplx FB[BNB > 0 ? BNB : 1];
@@ -294,9 +297,9 @@ extern "C" __global__ void __launch_bounds__(BAND_WARPS * 32, BAND_MINB) spicey_
               BR[b][rs] = RECS(BST_BRD + b);
             }
             bcplx f = band_mul(bk, r);
+            f = m < thr_mp ? make_double2(0.0, 0.0) : f;
             f.x = __shfl_sync(FULL, f.x, pl * BGPW + g);
             f.y = __shfl_sync(FULL, f.y, pl * BGPW + g);
-            if (band_mag(f) < B_THR) f = make_double2(0.0, 0.0);
             FB[b] = f;
           }
           // the update: a_ij -= f_i * u_kj
@@ -314,6 +317,7 @@ extern "C" __global__ void __launch_bounds__(BAND_WARPS * 32, BAND_MINB) spicey_
               for (int q = 0; q < BAND_RPL; ++q) AB[q][j] = band_submul(AB[q][j], F[q], pt);
 #pragma unroll
               for (int b = 0; b < BNB; ++b) BB[b][j] = band_submul(BB[b][j], FB[b], pt);
+              if (l == pl) __stcg(Gb + (size_t)k * (BNB + 1) + j, pt);
             }
           // my columns of the pivot row: border rows' update, and U leaves for the workspace (column-major)
 #pragma unroll
@@ -325,12 +329,7 @@ extern "C" __global__ void __launch_bounds__(BAND_WARPS * 32, BAND_MINB) spicey_
             const int c = k + 1 + ((slot - s - 1) & (BW - 1));
             __stcg(Gu + (size_t)c * BW + s, pt);
           }
-          if (l == pl) {
-            __stcg(Gr + k, r);
-#pragma unroll
-            for (int j = 0; j <= BNB; ++j)
-              if (j == BNB || ((BAND_ABMASK >> j) & 1)) __stcg(Gb + (size_t)k * (BNB + 1) + j, Pc[BW + j]);
-          }
+          if (l == pl) __stcg(Gr + k, r);
           // row k + 1 is final: its owner publishes it as the next pivot record
           if (l == pl1) {
             Pn[BW + BNB + 1] = A[rs1][s1];
@@ -407,13 +406,13 @@ extern "C" __global__ void __launch_bounds__(BAND_WARPS * 32, BAND_MINB) spicey_
 #define BAND_LOAD_RE(R, E, jb_)                                                                              \
       _Pragma("unroll") for (int q = 0; q < BAND_RPL; ++q) {                                                 \
         const int j = (jb_) + l + BAND_L * q;                                                                \
-        R[q] = j < nb ? __ldcg(Gr + j) : make_double2(0.0, 0.0);                                             \
-        E[q] = (j < nb && j - BW >= 0) ? row_rhs(j - BW) : make_double2(0.0, 0.0);                           \
+        R[q] = __ldcg(Gr + j);                                                                               \
+        E[q] = j - BW >= 0 ? row_rhs(j - BW) : make_double2(0.0, 0.0);                                       \
       }
 #define BAND_BSTEP(s, uv)                                                                                    \
       {                                                                                                      \
         const int j = jb + (s);                                                                              \
-        if (j < nb) {                                                                                        \
+        {                                                                                                    \
           const int pl = (s) % BAND_L, rs = (s) / BAND_L;                                                    \
           bcplx xj = band_mul(ACC[rs], RJ[rs]);                                                              \
           xj.x = __shfl_sync(FULL, xj.x, pl * BGPW + g);                                                     \
@@ -425,7 +424,7 @@ extern "C" __global__ void __launch_bounds__(BAND_WARPS * 32, BAND_MINB) spicey_
           _Pragma("unroll") for (int q = 0; q < BAND_RPL; ++q) ACC[q] = band_submul(ACC[q], uv[q], xj);      \
         }                                                                                                    \
       }
-      int jb = (nb - 1) / BW * BW;
+      int jb = nb - BW;   // nb is a multiple of W
       BAND_LOAD_U(Ua, jb + BH)   // jb + BH + s < nb + W: inside the workspace
       BAND_LOAD_RE(RJ, ENT, jb)
       for (; jb >= 0; jb -= BW) {
@@ -467,14 +466,15 @@ extern "C" __global__ void __launch_bounds__(BAND_WARPS * 32, BAND_MINB) spicey_
       // four independent loads in flight per lane: the index / constant tables are read through L2 behind the
       // workspace traffic, and one dependent load per iteration was 5 % of the kernel
       const long long xst = a.series_ld ? a.series_ld : 1;
-      double2* xo = a.series_ld ? a.x + p : a.x + p * n;
-      for (int i0 = l; i0 < n; i0 += 4 * BAND_L) {
+      const int n_out = a.n_out;
+      double2* xo = a.series_ld ? a.x + p : a.x + p * n_out;
+      for (int i0 = l; i0 < n_out; i0 += 4 * BAND_L) {
         int idx[4];
 #pragma unroll
-        for (int u = 0; u < 4; ++u) idx[u] = i0 + u * BAND_L < n ? __ldg(a.newvar + i0 + u * BAND_L) : n;
+        for (int u = 0; u < 4; ++u) idx[u] = i0 + u * BAND_L < n_out ? __ldg(a.newvar + i0 + u * BAND_L) : n;
 #pragma unroll
         for (int u = 0; u < 4; ++u)
-          if (i0 + u * BAND_L < n) xo[(long long)(i0 + u * BAND_L) * xst] = xs[idx[u]];
+          if (i0 + u * BAND_L < n_out) xo[(long long)(i0 + u * BAND_L) * xst] = xs[idx[u]];
       }
 #if BAND_IELEM
       double2* io = a.series_ld ? a.ielem + p : a.ielem + p * a.n_ac_elem;

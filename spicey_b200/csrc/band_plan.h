@@ -43,7 +43,8 @@ struct BandInput {   // the AC gather plan with per-entry constants (spicey_nati
 
 struct BandPlan {
   bool ok = false;
-  int n = 0, nb = 0, NB = 0, W = 0, L = 0, RPL = 0;   // W = L * RPL >= measured half-bandwidth
+  int n = 0, nb = 0, NB = 0, W = 0, L = 0, RPL = 0;   // W = L * RPL >= measured half-bandwidth; n, nb include the padding
+  int n_orig = 0;                                      // unknowns of the circuit (n = n_orig + padding rows)
   int bandwidth = 0;                                   // measured half-bandwidth around the pivot rows
   bool renumbered = false;                             // false: netlist order kept
   unsigned abmask = 0;                                 // border columns with structural non-zeros in band rows
@@ -220,53 +221,72 @@ inline void build_band_plan_for_order(const BandInput& in, const std::vector<int
   const int W = L * RPL;
   bp.L = L; bp.RPL = RPL; bp.W = W;
 
+  // The band part is padded to a multiple of W with identity rows (diagonal 1, nothing else, right-hand side 0: the
+  // extra unknowns are exact zeros): the kernel's loops, unrolled W times, then run whole blocks without a tail test.
+  // From here on indices are PADDED: band 0 .. nbp-1, border nbp .. nbp+NB-1, right-hand side np = nbp + NB.
+  const int nbp = (nb + W - 1) / W * W, np = nbp + NB;
+  bp.n_orig = n;
+  bp.n = np; bp.nb = nbp;
+  for (int b = 0; b < NB; ++b) bp.newvar[nn + b] = nbp + b;
+  bp.oldvar.assign(np, -1);
+  for (int v = 0; v < n; ++v) bp.oldvar[bp.newvar[v]] = v;
+  auto ucol = [&](int c) -> int {   // padded column -> column of the renumbered (unpadded) system, -1 = padding
+    if (c < nb) return c;
+    if (c < nbp) return -1;
+    return c == np ? n : nb + (c - nbp);
+  };
+
   // ---- deliveries ----
-  // rec(i, c): stamped entry of band row i (pivot row of step i) at renumbered column c (n = rhs); zero outside.
-  const BandRecipe zero = {0.0, 0.0, 0.0, 0.0};
+  // rec(i, c): stamped entry of band row i (pivot row of step i) at padded column c (np = rhs); zero outside.
+  const BandRecipe zero = {0.0, 0.0, 0.0, 0.0}, one = {1.0, 0.0, 0.0, 0.0};
   auto rec_row = [&](int prow_pos, int c) -> BandRecipe {
-    const int en = E[(size_t)prow_pos * ld + c];
+    const int uc = ucol(c);
+    if (uc < 0) return zero;
+    const int en = E[(size_t)prow_pos * ld + uc];
     if (en < 0) return zero;
     BandRecipe q = {(*in.ent_alpha)[en] + (*in.ent_jre)[en], (*in.ent_jim)[en], (*in.ent_beta)[en], (*in.ent_gamma)[en]};
     return q;
   };
   auto rec = [&](int i, int c) -> BandRecipe {
-    if (i < 0 || i >= nb || c < 0 || c > n) return zero;
+    if (i < 0 || i >= nbp || c < 0 || c > np) return zero;
+    if (i >= nb) return c == i ? one : zero;   // padding row
     return rec_row(P.prow[i], c);
   };
-  auto recb = [&](int b, int c) -> BandRecipe { return (c < 0 || c > n) ? zero : rec_row(P.prow[nb + b], c); };
-  auto bcol = [&](int j) { return j < NB ? nb + j : n; };   // border column j, or the right-hand side (j = NB)
+  auto recb = [&](int b, int c) -> BandRecipe { return (c < 0 || c > np) ? zero : rec_row(P.prow[nb + b], c); };
+  auto bcol = [&](int j) { return j < NB ? nbp + j : np; };   // border column j, or the right-hand side (j = NB)
   auto row_at = [&](int t, int lo) { return lo + (((t - lo) % W) + W) % W; };   // the row = t (mod W) in [lo, lo + W)
   std::vector<BandRecipe>& T = bp.tab;
   T.clear();
   bp.o_init = (int)T.size();     // rows 0 .. W-1: column 0, and the entries above the diagonal of columns 1 .. W-1
   for (int i = 0; i < W; ++i)
-    for (int c = 0; c < W; ++c) T.push_back((c == 0 || i < c) && c < nb ? rec(i, c) : zero);
+    for (int c = 0; c < W; ++c) T.push_back((c == 0 || i < c) ? rec(i, c) : zero);
   bp.o_initb = (int)T.size();
   for (int i = 0; i < W; ++i)
     for (int j = 0; j <= NB; ++j) T.push_back(rec(i, bcol(j)));
   bp.o_brd0 = (int)T.size();
   for (int b = 0; b < NB; ++b)
-    for (int c = 0; c < W; ++c) T.push_back(c < nb ? recb(b, c) : zero);
+    for (int c = 0; c < W; ++c) T.push_back(recb(b, c));
   bp.o_bb0 = (int)T.size();
   for (int b = 0; b < NB; ++b)
     for (int j = 0; j <= NB; ++j) T.push_back(recb(b, bcol(j)));
-  // One record per step (what step k delivers, contiguous: the kernel prefetches a record two steps ahead):
+  // One record per step (what step k delivers, contiguous: the kernel stages a record two steps ahead):
   //   [0, W)        position t: entry of column k + W in the row = t (mod W) of k .. k+W-1 (above the diagonal)
   //   [W, 2W)       position t: entry of column k + 1 in the row = t (mod W) of k+1 .. k+W (diagonal and below)
   //   2W            entry (k + W, k) of the entering row
   //   2W+1 ..       border columns / rhs of the entering row [NB + 1], then the border rows' entries of column k + W [NB]
-  // nb + 3 records: the publisher of step k reads record k + 1, the prefetch touches record k + 2.
+  //   2W+2NB+2      the tie-rule masks of the step
+  // nbp + 3 records: the publisher of step k reads record k + 1, the staging reaches record k + 2.
   while (T.size() % 8) T.push_back(zero);
   bp.o_step = (int)T.size();
   bp.step_stride = (2 * W + 2 * NB + 3 + 7) / 8 * 8;
   const size_t first_record = T.size();
-  for (int k = 0; k < nb + 3; ++k) {
+  for (int k = 0; k < nbp + 3; ++k) {
     const size_t base = T.size();
-    for (int t = 0; t < W; ++t) T.push_back(k + W < nb ? rec(row_at(t, k), k + W) : zero);
-    for (int t = 0; t < W; ++t) T.push_back(k + 1 < nb ? rec(row_at(t, k + 1), k + 1) : zero);
-    T.push_back(k < nb ? rec(k + W, k) : zero);
+    for (int t = 0; t < W; ++t) T.push_back(k + W < nbp ? rec(row_at(t, k), k + W) : zero);
+    for (int t = 0; t < W; ++t) T.push_back(k + 1 < nbp ? rec(row_at(t, k + 1), k + 1) : zero);
+    T.push_back(k < nbp ? rec(k + W, k) : zero);
     for (int j = 0; j <= NB; ++j) T.push_back(rec(k + W, bcol(j)));
-    for (int b = 0; b < NB; ++b) T.push_back(k + W < nb ? recb(b, k + W) : zero);
+    for (int b = 0; b < NB; ++b) T.push_back(k + W < nbp ? recb(b, k + W) : zero);
     T.push_back(zero);   // the tie-rule masks of the step (filled in below)
     while (T.size() < base + (size_t)bp.step_stride) T.push_back(zero);
   }
@@ -274,22 +294,25 @@ inline void build_band_plan_for_order(const BandInput& in, const std::vector<int
   for (const BandRecipe& q : T) if (q.jim != 0.0 || q.gamma != 0.0) { bp.rc_only = false; break; }
 
   // ---- tie rule: is the candidate scanned before the pilot's pivot? (solveComplex.ts:18-28, strict '>') ----
-  bp.flags.assign((size_t)2 * n, 0u);
-  for (int k = 0; k < n; ++k) {
-    const int* wh = &P.where[(size_t)k * n];
-    const int ppos = P.pivpos[k];
+  // (padding rows are never candidates: their columns hold nothing but their own diagonal)
+  bp.flags.assign((size_t)2 * np, 0u);
+  for (int ku = 0; ku < n; ++ku) {   // ku: step of the unpadded pilot
+    const int* wh = &P.where[(size_t)ku * n];
+    const int ppos = P.pivpos[ku];
     unsigned fx = 0, fy = 0;
-    if (k < nb) {
+    int k = ku;                      // padded step
+    if (ku < nb) {
       for (int t = 0; t < W; ++t) {
-        const int j = row_at(t, k + 1);
+        const int j = row_at(t, ku + 1);
         if (j < nb && wh[P.prow[j]] < ppos) fx |= 1u << t;
       }
       for (int b = 0; b < NB; ++b) if (wh[P.prow[nb + b]] < ppos) fy |= 1u << b;
     } else {
-      for (int b = k - nb + 1; b < NB; ++b) if (wh[P.prow[nb + b]] < ppos) fy |= 1u << b;
+      k = nbp + (ku - nb);
+      for (int b = ku - nb + 1; b < NB; ++b) if (wh[P.prow[nb + b]] < ppos) fy |= 1u << b;
     }
     bp.flags[2 * k] = fx; bp.flags[2 * k + 1] = fy;
-    if (k < nb) {   // the kernel reads the masks of a band step from the step's record
+    if (ku < nb) {   // the kernel reads the masks of a band step from the step's record
       const unsigned long long bits = (unsigned long long)fx | ((unsigned long long)fy << 32);
       double asd;
       static_assert(sizeof asd == sizeof bits, "double is 64 bits");
@@ -297,12 +320,12 @@ inline void build_band_plan_for_order(const BandInput& in, const std::vector<int
       T[first_record + (size_t)k * bp.step_stride + 2 * W + 2 * NB + 2].alpha_jre = asd;
     }
   }
-  bp.g_stride = ((long long)(nb + W) * W + (long long)nb * (NB + 2) + 7) / 8 * 8;
+  bp.g_stride = ((long long)(nbp + W) * W + (long long)nbp * (NB + 2) + 7) / 8 * 8;
   int nbc = 1;
   for (int j = 0; j < NB; ++j) nbc += (abmask >> j) & 1;
-  bp.n_cfma = (long long)nb * ((long long)W * (W + nbc) + (long long)NB * (W + NB + 1)) + (long long)nb * (W + nbc);
+  bp.n_cfma = (long long)nbp * ((long long)W * (W + nbc) + (long long)NB * (W + NB + 1)) + (long long)nbp * (W + nbc);
   // pivot rows as ORIGINAL row indices (the dense fallback and the tests speak that language)
-  for (int k = 0; k < n; ++k) bp.prow[k] = bp.oldvar[bp.prow[k]];
+  for (int k = 0; k < n; ++k) { const int pr = bp.prow[k]; bp.prow[k] = pr < nb ? order[pr] : nn + (pr - nb); }
   bp.ok = true;
 }
 

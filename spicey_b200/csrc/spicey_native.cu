@@ -582,7 +582,7 @@ struct BandArgs {   // must match band_kernel.cuh
   double2* G; long long g_stride;
   const double2* tab; const uint2* flags; const int* newvar; const double4* el_rec;
   const double* ind_L;
-  int n, nb, n_ac_elem, v_first, n_ind;
+  int n, nb, n_out, n_ac_elem, n_ind;
   int o_init, o_initb, o_brd0, o_bb0, o_step;
 };
 
@@ -617,17 +617,18 @@ int prepare_band(DeviceCtx& ctx, const HostPlan& hp, cudaStream_t stream) {
   BandPlan& bp = ctx.bp;
   if (!bp.ok || bp.bandwidth < kBandMinBandwidth) return SPICEY_SUCCESS;
   // element records of the unpack phase: current = Y (x[i1] - x[i2]) in elimination-order indices, index n = the
-  // zero slot (ground); a V element's current is its branch unknown: (branch, zero slot, Y = 1)
+  // zero slot (ground; bp.n counts the padding rows of the band); a V element's current is its branch unknown:
+  // (branch, zero slot, Y = 1)
   std::vector<double4> el_idx(std::max(1, hp.n_ac_elem));
   for (int e = 0; e < hp.n_ac_elem; ++e) {
     const int n1 = hp.ends[e].x, n2 = hp.ends[e].y;
     long long ij;
     double4 r = make_double4(0.0, 0.0, 0.0, 0.0);
     if (e >= hp.off[ELEM_V]) {
-      ij = (long long)(bp.nb + (e - hp.off[ELEM_V])) | ((long long)hp.nvar << 32);
+      ij = (long long)(bp.nb + (e - hp.off[ELEM_V])) | ((long long)bp.n << 32);
       r.y = 1.0;
     } else {
-      ij = (long long)(n1 ? bp.newvar[n1 - 1] : hp.nvar) | ((long long)(n2 ? bp.newvar[n2 - 1] : hp.nvar) << 32);
+      ij = (long long)(n1 ? bp.newvar[n1 - 1] : bp.n) | ((long long)(n2 ? bp.newvar[n2 - 1] : bp.n) << 32);
       r.y = ctx.sp.el_a[e]; r.z = ctx.sp.el_b[e]; r.w = ctx.sp.el_g[e];
     }
     memcpy(&r.x, &ij, sizeof ij);
@@ -729,7 +730,7 @@ int launch_ac_band(DeviceCtx& ctx, const HostPlan& hp, const AcArgs& args, Devic
   a.tab = (const double2*)ctx.bp_dev.tab; a.flags = (const uint2*)ctx.bp_dev.flags;
   a.newvar = (const int*)ctx.bp_dev.newvar; a.el_rec = (const double4*)ctx.bp_dev.el_rec;
   a.ind_L = sa.ind_L;
-  a.n = hp.nvar; a.nb = bp.nb; a.n_ac_elem = hp.n_ac_elem; a.v_first = hp.off[ELEM_V]; a.n_ind = sa.n_ind;
+  a.n = bp.n; a.nb = bp.nb; a.n_out = hp.nvar; a.n_ac_elem = hp.n_ac_elem; a.n_ind = sa.n_ind;
   a.o_init = bp.o_init; a.o_initb = bp.o_initb; a.o_brd0 = bp.o_brd0; a.o_bb0 = bp.o_bb0; a.o_step = bp.o_step;
   void* kargs[] = {&a};
   CUDA_TRY(cudaLaunchKernel((const void*)jv->kernel, dim3(grid), dim3(jv->warps * 32), kargs, smem, stream));

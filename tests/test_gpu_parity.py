@@ -659,6 +659,132 @@ def test_large_slice_properties_cfg5(eng):
     assert np.max(np.abs(got["ielem"][:, :, sub] - ref_i) / cs) <= TRAN_TOL
 
 
+def test_full_size_properties_cfg5(eng):
+    """BASELINE cfg 5 at full size: 100,000 instances x 3,001 recorded steps (14.4 GB of results), default tier
+    policy (compiled, tier 6): every status 0, no reverse conduction beyond -Is, the recorded R and C currents follow
+    from the recorded voltages for EVERY instance, and 256 instances spread over the sweep match the oracle at 1e-6."""
+    import spicey_b200 as sp
+    n = 100000
+    ov = w.rectifier_overrides(n)
+    got = sp.simulate_tran_batch(parse_netlist(w.RECTIFIER), n_inst=n, overrides=ov, engine=eng)
+    assert eng.stats()["tier"] == native.TIER_TRAN_JIT
+    assert got["steps"] == 3000 and got["v"].shape == (3001, 2, n) and got["status"].max() == 0
+    names = list(got["element_names"])
+    iD, iR, iC = (got["ielem"][:, names.index(k), :] for k in ("D1", "R1", "C1"))
+    assert np.all(iD >= -1.0001 * ov["D1.is"][None, :])
+    vout = got["v"][:, list(got["node_names"]).index("out"), :]
+    assert np.max(np.abs(iR - vout / ov["R1"][None, :])) <= 1e-12 * np.max(np.abs(iR))
+    assert np.max(np.abs(iC[1:] - ov["C1"][None, :] * (vout[1:] - vout[:-1]) / got["dt"])) <= 1e-9 * np.max(np.abs(iC))
+    sub = np.linspace(0, n - 1, 256).astype(int)
+    ck2 = parse_netlist(w.RECTIFIER)
+    dt, steps = compute_effective_time_step(ck2.analyses.tran.dt, ck2.analyses.tran.tstop)
+    v, ie, iters, st, state = co.tran_solve(ck2, dt, steps, n_inst=len(sub), overrides={k: a[sub] for k, a in ov.items()},
+                                            nthreads=8)
+    assert st.max() == 0
+    ref_v, ref_i = np.transpose(v, (1, 2, 0)), np.transpose(ie, (1, 2, 0))
+    vs = np.max(np.abs(ref_v), axis=0, keepdims=True)
+    assert np.max(np.abs(got["v"][:, :, sub] - ref_v) / vs) <= TRAN_TOL
+    cs = np.maximum(np.max(np.abs(ref_i), axis=0, keepdims=True), 1e-30)
+    assert np.max(np.abs(got["ielem"][:, :, sub] - ref_i) / cs) <= TRAN_TOL
+
+
+def test_full_size_properties_cfg4(eng):
+    """BASELINE cfg 4 at full size: the 8,000,001-point sweep of the 16x16 mesh through the device entry point in
+    chunks of 500,000 points (the results of a chunk are 8 GB; the whole sweep would be 127 GB), default tier policy
+    (>= 200,000 points: the banded tier).  Per chunk: every status 0, no point handed to the fallback, V(n0_0) equals
+    the source phasor exactly, KCL at the source node (i_v1 = -(i_r1 + i_r2)); 512 points spread over the whole sweep
+    match the oracle at 1e-9 per entry."""
+    import torch
+    import spicey_b200 as sp
+    ck = parse_netlist(w.rc_mesh(16))
+    table = sp.packing.pack_circuit(ck)
+    freqs = np.array(sp.analysis.ac_frequencies(ck))
+    P, chunk = freqs.shape[0], 500000
+    assert P == 8000001
+    dev = torch.device("cuda", 0)
+    ld = eng.series_ld(chunk)
+    d_f = torch.from_numpy(freqs).to(dev)
+    d_x = torch.empty((table.nvar, ld), dtype=torch.complex128, device=dev)
+    d_i = torch.empty((table.n_ac_elem, ld), dtype=torch.complex128, device=dev)
+    d_s = torch.empty(chunk, dtype=torch.int32, device=dev)
+    names = table.names[:table.n_ac_elem]
+    src_node = list(ck.nodes.rev[1:]).index("n0_0")
+    at_src = [j for j, nm in enumerate(names) if nm[0] == "r" and src_node + 1 in (int(table.n1[j]), int(table.n2[j]))]
+    assert len(at_src) == 2
+    sgn = torch.tensor([1.0 if int(table.n1[j]) == src_node + 1 else -1.0 for j in at_src], dtype=torch.complex128, device=dev)
+    pick_all = np.linspace(0, P - 1, 512).astype(np.int64)
+    got_x, got_i = [], []
+    stream = torch.cuda.current_stream()
+    for c0 in range(0, P, chunk):
+        n = min(chunk, P - c0)
+        eng.ac_solve_device(table, d_f.data_ptr() + 8 * c0, n, d_x.data_ptr(), d_i.data_ptr(), d_s.data_ptr(),
+                            flags=SM | native.FLAG_JIT, stream=stream.cuda_stream, series_ld=ld)
+        torch.cuda.synchronize()
+        stt = eng.stats()
+        # (the last chunk is the sweep's final single point: batches below 2,048 points take the dense kernel)
+        assert stt["tier"] == (native.TIER_BAND if n >= 2048 else native.TIER_CTA_GMEM) and stt["fallback_solves"] == 0, stt
+        assert int(d_s[:n].max().item()) == 0
+        assert float((d_x[src_node, :n] - 1.0).abs().max().item()) <= 1e-15
+        iv = d_i[names.index("v1"), :n]
+        ir = (d_i[at_src, :n] * sgn[:, None]).sum(dim=0)
+        # (the currents are differences of node voltages near 1 V: 1e-6 A over 1 kOhm is a 1e-3 V difference, so a
+        #  relative 1e-16 on the voltages is 1e-13 on a current, and the residual is a sum of three of them)
+        assert float(((iv + ir).abs() / ir.abs()).max().item()) <= 1e-9
+        loc = pick_all[(pick_all >= c0) & (pick_all < c0 + n)] - c0
+        sel = torch.from_numpy(loc).to(dev)
+        got_x.append(d_x[:, sel].T.cpu().numpy())
+        got_i.append(d_i[:, sel].T.cpu().numpy())
+    xr, ir_, st = co.ac_solve(ck, freqs[pick_all], nthreads=8)
+    assert st.max() == 0
+    assert rel_err(np.concatenate(got_x), xr) <= AC_TOL and rel_err(np.concatenate(got_i), ir_) <= AC_TOL
+
+
+def _solve_extended(A, b):
+    """Gaussian elimination with partial pivoting in numpy's extended precision (the yardstick for per-entry errors)."""
+    A = A.astype(np.clongdouble).copy()
+    b = b.astype(np.clongdouble).copy()
+    n = A.shape[0]
+    for k in range(n):
+        p = k + int(np.argmax(np.abs(A[k:, k])))
+        if p != k:
+            A[[k, p]] = A[[p, k]]
+            b[[k, p]] = b[[p, k]]
+        f = A[k + 1:, k] / A[k, k]
+        A[k + 1:, k:] -= f[:, None] * A[k, k:][None, :]
+        b[k + 1:] -= f * b[k]
+    x = np.zeros(n, dtype=np.clongdouble)
+    for i in range(n - 1, -1, -1):
+        x[i] = (b[i] - A[i, i + 1:] @ x[i + 1:]) / A[i, i]
+    return x
+
+
+@pytest.mark.parametrize("n_nodes,n_elem", [(14, 60), (30, 200), (62, 300)])
+def test_ac_random_rlc_networks_per_entry(eng, n_nodes, n_elem):
+    """Per-entry relative errors on the ill-conditioned random networks (the row-maximum scale of the test above hides
+    small entries): against the same system solved in extended precision, every entry above 1e-6 of its row's maximum
+    is as accurate as the oracle's own double-precision answer (within 4x, or 1e-9), on every tier."""
+    import spicey_b200 as sp
+    rng = np.random.default_rng(n_nodes * 1000 + n_elem)
+    text = random_rlc_netlist(rng, n_nodes, n_elem, n_v=2)
+    ck = parse_netlist(text)
+    freqs = np.array(sp.analysis.ac_frequencies(ck))[::6]
+    xo, _, st = co.ac_solve(ck, freqs)
+    assert st.max() == 0
+    nvar = xo.shape[1]
+    exact = []
+    for f in freqs:
+        A, b = o.build_linear_system_for_ac(ck, float(f), nvar)
+        exact.append(_solve_extended(np.array([[complex(z) for z in row] for row in A]), np.array([complex(z) for z in b])))
+    exact = np.array(exact)
+    big = np.abs(exact) > 1e-6 * np.max(np.abs(exact), axis=1, keepdims=True)
+    e_oracle = float(np.max((np.abs(xo - exact) / np.abs(exact))[big]))
+    for flags in (native.FLAG_DENSE, native.FLAG_SPARSE, native.FLAG_SPARSE | native.FLAG_JIT | SM, native.FLAG_SPARSE | native.FLAG_WARP, BAND):
+        out = sp.simulate_ac_batch(ck, freqs, engine=eng, flags=flags)
+        assert out["status"].max() == 0
+        e_gpu = float(np.max((np.abs(out["x"][0] - exact) / np.abs(exact))[big]))
+        assert e_gpu <= max(1e-9, 4 * e_oracle), (flags, e_gpu, e_oracle)
+
+
 def test_mesh_default_policy_takes_the_warp_tier(eng):
     """cfg 4 topology, 4,096 frequencies, default flags: the sparse path engages (>= 2048 points), the program is
     large (thread-tier workspace >= 512 slots), so the warp-per-system tier runs; KCL at the source node and a
