@@ -422,6 +422,7 @@ int prepare_sparse(DeviceCtx& ctx, const HostPlan& hp, double pilot_f, bool eage
 int launch_ac_dense(DeviceCtx& ctx, const HostPlan& hp, const DevPlan& dp, const AcArgs& args, uint32_t flags,
                     cudaStream_t stream, int* tier_out, int64_t* launches);
 
+constexpr long long kSparseMinPoints = 2048;  // batches from which the sparse program path pays for its host-side analysis
 constexpr size_t kJitMaxOps = 3000;          // larger programs stay on the interpreter (compile time: cfg2's 831 micro-ops take 4 s)
 constexpr int kJitSpareValues = 64;          // cross-phase values the registers can hold beside the shared-memory slots
 constexpr long long kJitMinPoints = 200000;  // below this the ~4 s compile does not pay off (unless forced)
@@ -914,7 +915,7 @@ int launch_ac_dense(DeviceCtx& ctx, const HostPlan& hp, const DevPlan& dp, const
 int launch_ac(DeviceCtx& ctx, const HostPlan& hp, const DevPlan& dp, const AcArgs& args, uint32_t flags,
               cudaStream_t stream, int* tier_out, int64_t* launches, double pilot_f, bool pilot_known) {
   const bool want_sparse = !(flags & (SPICEY_FLAG_STRICT | SPICEY_FLAG_FORCE_GMEM | SPICEY_FLAG_DENSE)) &&
-                           (args.p_count >= 2048 || (flags & SPICEY_FLAG_SPARSE));
+                           (args.p_count >= kSparseMinPoints || (flags & SPICEY_FLAG_SPARSE));
   if (want_sparse) {
     const bool eager = dp.n_inst > 1 || dp.n_var > 0;  // component sweep / Monte-Carlo: per-instance stamping
     // the per-instance stamping of the sparse tiers indexes the R, C, L, V elements only: sweeps of circuits with
@@ -1291,6 +1292,8 @@ int32_t spicey_ac_solve(spicey_handle* h, const spicey_elem_table* table, const 
   const int D = (int)h->devs.size();
   // the compile-or-interpret decision looks at the whole call, not at one pipeline chunk
   if (P >= kJitMinPoints && !(flags & SPICEY_FLAG_NO_JIT)) flags |= SPICEY_FLAG_JIT;
+  // ... and so does the sparse-or-dense decision: eight devices' shards of a 10,000-point sweep are 1,250 points each
+  if (P >= kSparseMinPoints) flags |= SPICEY_FLAG_SPARSE;
   const size_t xrow = sizeof(double2) * hp.nvar, irow = sizeof(double2) * hp.n_ac_elem;
   const bool series = (flags & SPICEY_FLAG_SERIES_MAJOR) != 0;
   // Chunk size: ~96 MiB of results per chunk so that copies overlap the next chunk's kernel.
