@@ -81,6 +81,60 @@ class ComplexSeries:
             yield Complex(z.real, z.imag)
 
 
+class LazyCurrentSeries(ComplexSeries):
+    """Element-current series computed on access from the node-voltage slabs, exactly as the reference computes it per
+    point (simulateAC.ts:94-126): i = Y.mul(v1.sub(v2)) with Y = 1/R, j 2 pi f C, or 1 / (j 2 pi f L) (0 when
+    |2 pi f L| < EPS); a V element's current is its branch unknown.  Nothing is transferred from the device for it: the
+    host call returns the solution vector only (16 Nvar bytes per point instead of 16 (Nvar + nAc))."""
+
+    def __init__(self, kind, value, freqs, v1, v2):
+        self.kind, self.value, self.freqs, self.v1, self.v2 = kind, value, freqs, v1, v2
+        self._array = None
+
+    def _admittance(self, f):
+        two_pi = 2 * math.pi
+        if self.kind == native.ELEM_R:
+            return 1 / self.value, np.zeros_like(f)
+        if self.kind == native.ELEM_C:
+            return np.zeros_like(f), two_pi * f * self.value
+        d = two_pi * f * self.value                      # denom = Complex(0, d); Complex.div: (0*0 + 0*d)/d^2, (0*0 - 1*d)/d^2
+        with np.errstate(divide="ignore", invalid="ignore"):
+            im = np.where(np.abs(d) < 1e-15, 0.0, (0.0 - d) / (d * d))
+        return np.zeros_like(f), im
+
+    def _compute(self, sel):
+        f = np.asarray(self.freqs, dtype=np.float64)[sel]
+        if self.kind == native.ELEM_V:
+            return np.asarray(self.v1[sel])
+        z = lambda a: 0.0 if a is None else a[sel]
+        d = z(self.v1) - z(self.v2)
+        yr, yi = self._admittance(f)
+        dr, di = np.real(d), np.imag(d)
+        return (yr * dr - yi * di) + 1j * (yr * di + yi * dr)   # Complex.mul, Complex.ts:33-38
+
+    @property
+    def array(self):
+        if self._array is None:
+            self._array = np.asarray(self._compute(slice(None)), dtype=np.complex128)
+        return self._array
+
+    def __len__(self):
+        return len(self.freqs)
+
+    def __getitem__(self, k):
+        if isinstance(k, slice):
+            return ComplexSeries(self.array[k])
+        if self._array is not None:
+            zz = self._array[k]
+        else:
+            zz = complex(np.asarray(self._compute(slice(k, k + 1 if k != -1 else None)))[0])
+        return Complex(zz.real, zz.imag)
+
+    def __iter__(self):
+        for zz in self.array:
+            yield Complex(zz.real, zz.imag)
+
+
 _INT_KEY = re.compile(r"^(0|[1-9]\d*)$")
 
 
@@ -124,18 +178,39 @@ def ac_frequencies(ckt: ParsedCircuit) -> List[float]:
     return build_frequency_array(a.mode, a.N, a.f1, a.f2)
 
 
-def simulateAC(ckt: ParsedCircuit, engine: Optional[native.Engine] = None, flags: int = 0):
-    """simulateAC.ts:62-130.  Returns None without `.ac`; raises the reference's errors."""
+def simulateAC(ckt: ParsedCircuit, engine: Optional[native.Engine] = None, flags: int = 0, lazy_currents: bool = False):
+    """simulateAC.ts:62-130.  Returns None without `.ac`; raises the reference's errors.
+    lazy_currents: the device returns the solution vector only and `elementCurrents[name]` computes Y (v1 - v2) on
+    access with the reference's own formula (:94-126) — a third of the bytes over PCIe for a ladder, identical keys."""
     if ckt.analyses.ac is None:
         return None
     eng = engine or get_engine()
     freqs = ac_frequencies(ckt)
     table = pack_circuit(ckt)
     # series-major results: every node / element series is one contiguous slab (SURVEY.md 8 f1)
-    x, ie, st = eng.ac_solve(table, freqs, flags=flags | native.FLAG_SERIES_MAJOR)
+    x, ie, st = eng.ac_solve(table, freqs, flags=flags | native.FLAG_SERIES_MAJOR, want_currents=not lazy_currents)
     _raise_first_failure(st, table, ckt, _AC_ERRORS)
     node_names = ckt.nodes.rev[1:]
     volt = _series_by_name(node_names, x[:table.n_nodes].T)
+    if lazy_currents:
+        names = table.names[:table.n_ac_elem]
+        f = np.asarray(freqs, dtype=np.float64)
+        series = []
+        for e in range(table.n_ac_elem):
+            kind = int(table.type[e])
+            n1, n2 = int(table.n1[e]), int(table.n2[e])
+            if kind == native.ELEM_V:
+                k = e - int(np.argmax(table.type == native.ELEM_V))
+                series.append(LazyCurrentSeries(kind, 0.0, f, x[table.n_nodes + k], None))
+            else:
+                series.append(LazyCurrentSeries(kind, float(table.values[int(table.value_idx[e])]), f,
+                                                None if n1 == 0 else x[n1 - 1], None if n2 == 0 else x[n2 - 1]))
+        lazy = {}
+        for n in _js_key_order(names):
+            idx = [i for i, m in enumerate(names) if m == n]
+            # duplicate element names interleave per sample, as `(obj[name] ||= []).push` does: materialised
+            lazy[n] = series[idx[0]] if len(idx) == 1 else ComplexSeries(np.stack([series[i].array for i in idx], axis=1).reshape(-1))
+        return {"freqs": freqs, "nodeVoltages": {k: ComplexSeries(v) for k, v in volt.items()}, "elementCurrents": lazy}
     cur = _series_by_name(table.names[:table.n_ac_elem], ie.T)
     return {
         "freqs": freqs,

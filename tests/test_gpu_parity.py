@@ -961,6 +961,26 @@ def test_current_sources_ac_and_tran(eng):
         assert got["element_names"][-1] == "i1" and np.all(got["ielem"][:, -1, 0] == 1e-3)
 
 
+def test_simulate_ac_lazy_currents_match_the_oracle(eng):
+    """simulateAC(lazy_currents=True): the host call moves the solution vector only, element currents are computed on
+    access with the reference's formula (simulateAC.ts:94-126) — same keys, same order, values within 1e-9 of the
+    oracle (R, C, L and V elements, one element to ground on either side)."""
+    import spicey_b200 as sp
+    text = "* rlc\nv1 in 0 ac 1 15\nr1 in a 50\nl1 a b 1m\nc1 b 0 1u\nr2 0 b 2k\nc2 a b 10n\n.ac dec 20 10 1meg\n.end\n"
+    ref = o.simulate(text)["ac"]
+    got = sp.simulateAC(parse_netlist(text), engine=eng, lazy_currents=True)
+    eager = sp.simulateAC(parse_netlist(text), engine=eng)
+    assert eng.stats()["d2h_bytes"] > 0
+    assert list(got["elementCurrents"].keys()) == list(ref["elementCurrents"].keys()) == list(eager["elementCurrents"].keys())
+    for nm, series in ref["elementCurrents"].items():
+        want = np.array([complex(z) for z in series])
+        assert rel_err(got["elementCurrents"][nm].array, want) <= AC_TOL, nm
+        assert rel_err(eager["elementCurrents"][nm].array, want) <= AC_TOL, nm
+        z = got["elementCurrents"][nm][3]
+        assert abs(complex(z) - want[3]) <= AC_TOL * abs(want[3]) and len(got["elementCurrents"][nm]) == len(want)
+    assert sp.formatAcResult(got) == sp.formatAcResult(eager)
+
+
 def test_long_ladder_default_policy(eng):
     """A 400-node ladder (Nvar = 401, 3,200 points): chain-like, so the warp tier declines (2-3 updates per row
     would idle the lanes), and 801 values cross into the back-substitution, far more than a thread's registers

@@ -201,3 +201,29 @@ def test_current_source_extension_parses_and_packs():
     assert tb.n_ac_elem == 3 and tb.n_elem == 4 and tb.nvar == 3 and tb.names[-1] == "i1"
     vi = int(tb.value_idx[-1])
     assert list(tb.values[vi:vi + 3]) == [2 * 1e-3, 3 * 1e-3, 45.0]
+
+
+def test_lazy_current_series_reproduces_the_reference_formula():
+    """LazyCurrentSeries (simulateAC(lazy_currents=True)) on the oracle's own node voltages: Y.mul(v1.sub(v2)) per
+    element kind, including the inductor's Complex.div form and ground on either side (simulateAC.ts:94-126)."""
+    from oracle import spicey_oracle as o
+    from spicey_b200 import native
+    from spicey_b200.analysis import LazyCurrentSeries
+    from spicey_b200.packing import pack_circuit
+    from spicey_b200.parsing import parse_netlist
+    text = "* rlc\nv1 in 0 ac 1 15\nr1 in a 50\nl1 a b 1m\nc1 b 0 1u\nr2 0 b 2k\nc2 a b 10n\n.ac dec 7 10 1meg\n.end\n"
+    ref = o.simulate(text)["ac"]
+    ck = parse_netlist(text)
+    tb = pack_circuit(ck)
+    f = np.array(ref["freqs"])
+    volt = {nm: np.array([complex(z) for z in s]) for nm, s in ref["nodeVoltages"].items()}
+    names = ck.nodes.rev
+    for e in range(tb.n_ac_elem):
+        kind, n1, n2 = int(tb.type[e]), int(tb.n1[e]), int(tb.n2[e])
+        want = np.array([complex(z) for z in ref["elementCurrents"][tb.names[e]]])
+        if kind == native.ELEM_V:
+            continue   # the branch unknown itself
+        s = LazyCurrentSeries(kind, float(tb.values[int(tb.value_idx[e])]), f, None if n1 == 0 else volt[names[n1]],
+                              None if n2 == 0 else volt[names[n2]])
+        assert np.array_equal(s.array, want), tb.names[e]            # same operations in the same order: bit-identical
+        assert complex(s[2]) == want[2] and len(s) == len(want)

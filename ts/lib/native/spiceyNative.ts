@@ -108,17 +108,19 @@ function getHandle(): Pointer {
   return handle
 }
 
-export function acSolve(t: ElemTable, freqs: Float64Array) {
+/** wantCurrents = false: ielem is NULL for the library — the solution vector alone crosses PCIe (16 Nvar bytes per
+ *  point instead of 16 (Nvar + nAc)); simulateAC then computes element currents on access. */
+export function acSolve(t: ElemTable, freqs: Float64Array, wantCurrents = true) {
   const nvar = t.nNodes + t.nVsrc
   const P = freqs.length
   const x = new Float64Array(P * nvar * 2)
-  const ielem = new Float64Array(P * t.nAcElem * 2)
+  const ielem = new Float64Array(wantCurrents ? P * t.nAcElem * 2 : 0)
   const status = new Int32Array(P)
   const ts = tableStruct(t)
   check(
     C.spicey_ac_solve(
       getHandle(), ptr(ts), null, ptr(freqs), BigInt(P), ptr(x),
-      t.nAcElem ? ptr(ielem) : null, ptr(status), FLAG_SERIES_MAJOR,
+      wantCurrents && t.nAcElem ? ptr(ielem) : null, ptr(status), FLAG_SERIES_MAJOR,
     ),
   )
   return { x, ielem, status, nvar, nPoints: P }
