@@ -140,6 +140,10 @@ enum {
   ,SPICEY_TIER_BAND = 8       /* banded + bordered systems (meshes, long ladders) after a bandwidth-reducing
                                 renumbering of the nodes: a few lanes per system, the sliding window of rows in
                                 registers, partial pivoting verified per system (band_kernel.cuh) */
+  ,SPICEY_TIER_TILE = 9       /* dense LU with partial pivoting (lib/math/solveComplex.ts:15-53), the augmented
+                                matrix of a system resident in REGISTERS as 2-D cyclic tiles of one CTA (one warp
+                                for small Nvar), compiled per (Nvar, tile shape): dense circuits and
+                                SPICEY_FLAG_DENSE batches of >= 4096 points (tile_kernel.cuh) */
 };
 
 typedef struct spicey_handle spicey_handle;
@@ -274,7 +278,11 @@ enum {
   SPICEY_FLAG_NO_WARP = 1024u,     /* AC: never use the warp-per-system sparse tier */
   SPICEY_FLAG_NO_JIT = 256u,       /* never compile: interpreted sparse program (AC), generic kernels (TRAN) */
   SPICEY_FLAG_BAND = 2048u,        /* AC: use the banded + bordered tier even for small batches / small programs (testing) */
-  SPICEY_FLAG_NO_BAND = 4096u      /* AC: never use the banded + bordered tier */
+  SPICEY_FLAG_NO_BAND = 4096u,     /* AC: never use the banded + bordered tier */
+  SPICEY_FLAG_TILE = 8192u,        /* AC: use the dense register-tile tier even for small batches / sparse circuits (testing) */
+  SPICEY_FLAG_NO_TILE = 16384u,    /* AC: never use the dense register-tile tier */
+  SPICEY_FLAG_TILE_GENERIC = 32768u /* AC, testing: the register-tile tier stamps from the element table (as it does for
+                                      per-instance values) even when the per-topology constants of a plain sweep apply */
 };
 
 /* Tooling (no device needed): writes the CUDA source of the compiled straight-line sparse kernel
@@ -310,6 +318,13 @@ int32_t spicey_debug_band_stats(const spicey_elem_table* table, double pilot_f, 
  * abmask: bits 0-15 active border columns of band rows, bit 16: (alpha, beta)-only tables (RC circuits). */
 int64_t spicey_debug_band_source(int32_t L, int32_t RPL, int32_t NB, uint32_t abmask, int32_t with_ielem, int32_t warps,
                                  int32_t minb, char* buf, int64_t cap);
+
+/* Tooling (no device needed): the CUDA source NVRTC compiles for the dense register-tile tier (tier 9) of an
+ * Nvar-unknown circuit with n_elem elements and n_src sources; tr, tc > 0 force the thread grid, else the library's
+ * choice.  with_ielem: bit 0 element currents, bit 1 constant tables (plain frequency sweep), bit 2 (alpha, beta)-only tables.  shape_out[8], optional: TR, TC, MR, MC, warps per CTA, CTAs per SM, expected registers per thread, shared
+ * memory per CTA.  Returns the size needed, or -1 when no tile shape fits an SM (Nvar too large). */
+int64_t spicey_debug_tile_source(int32_t nvar, int32_t n_elem, int32_t n_src, int32_t tr, int32_t tc, int32_t with_ielem,
+                                 int32_t* shape_out, char* buf, int64_t cap);
 
 /* Measures this GPU's FP64 FMA peak with a register-only DFMA loop (GFLOP/s), the
  * denominator the FP64-bound roofline is reported against. */

@@ -21,7 +21,9 @@
 #include "ac_sparse.cuh"
 #include "ac_warp.cuh"
 #include "band_kernel_embed.h"
+#include "tile_kernel_embed.h"
 #include "band_plan.h"
+#include "tile_plan.h"
 #include "host_plan.h"
 #include "jit_runtime.h"
 #include "sparse_codegen.h"
@@ -124,6 +126,22 @@ struct DeviceCtx {
     int warps = 0, minb = 0;
     size_t smem_bytes = 0;
   } band_jit[2];              // [0] without, [1] with element currents
+  // dense register-tile tier (tile_kernel.cuh): per-entry gather lists of the last topology and the compiled kernels
+  Buffer tl_blob;
+  uint64_t tl_key = 0;        // plan key the entry lists were uploaded for (0 = none)
+  struct TileDev {
+    const void *ent_rc = nullptr, *ent_ptr = nullptr, *contrib = nullptr, *ctab = nullptr, *el_rec = nullptr, *ind_L = nullptr;
+    int n_ent = 0, n_ind = 0;
+    bool has_const = false, rc_only = false;
+  } tl_dev;
+  struct TileJit {
+    cudaLibrary_t lib = nullptr;
+    cudaKernel_t kernel = nullptr;
+    uint64_t key = 0;
+    bool failed = false;
+    int n = 0, tr = 0, tc = 0, warps = 0, minb = 0;
+  } tile_jit[8];              // by variant: bit 0 element currents, bit 1 constant tables, bit 2 (alpha, beta)-only tables
+  std::string tl_note;
   double sp_pilot_f = 0;      // frequency of the pilot point the cached programs were built from
   uint64_t plan_up_key = 0;   // plan currently resident in `plan` (its device pointers are in plan_dp)
   DevPlan plan_dp;
@@ -279,14 +297,16 @@ struct JitArgs {   // must match sparse_jit_prelude()
 
 // Host half of the sparse path: per-entry constants, pilot matrix and the program itself (no device needed).
 // Leaves sp.ok=false when the sparse path does not apply (R<=0, singular pilot).
-void build_sparse_host(const HostPlan& hp, double pilot_f, bool eager, SparseProgram& sp) {
-  sp = SparseProgram();
+// Per-entry constants of a plain frequency sweep: entry = alpha + Re J + j (w beta - gamma / w + Im J), the
+// contributions of simulateAC.ts:36-57 summed in the reference's stamping order; per element Y = ya + j (w yb - yg / w).
+// false: an R <= 0 (simulateAC.ts:37) — the dense kernels report it per point.
+bool entry_constants(const HostPlan& hp, SparseProgram& sp) {
   const HostGather& G = hp.ac;
   const int n_ent = (int)G.ent_col.size();
   sp.ent_alpha.assign(n_ent, 0.0); sp.ent_beta.assign(n_ent, 0.0); sp.ent_gamma.assign(n_ent, 0.0);
   sp.ent_jre.assign(n_ent, 0.0); sp.ent_jim.assign(n_ent, 0.0);
   for (int e = 0; e < hp.n_ac_elem; ++e)
-    if (hp.meta[e].x == ELEM_R && !(hp.values[hp.meta[e].y] > 0)) return;  // R<=0: dense kernel reports it
+    if (hp.meta[e].x == ELEM_R && !(hp.values[hp.meta[e].y] > 0)) return false;
   for (int en = 0; en < n_ent; ++en) {
     for (int c = G.ent_ptr[en]; c < G.ent_ptr[en + 1]; ++c) {
       const int w = G.contrib[c], src = (w >> 1) & 3, idx = w >> 3;
@@ -304,6 +324,7 @@ void build_sparse_host(const HostPlan& hp, double pilot_f, bool eager, SparsePro
     }
   }
   sp.el_a.assign(hp.n_ac_elem, 0.0); sp.el_b.assign(hp.n_ac_elem, 0.0); sp.el_g.assign(hp.n_ac_elem, 0.0);
+  sp.ind_L.clear();
   for (int e = 0; e < hp.n_ac_elem; ++e) {
     const int ty = hp.meta[e].x;
     const double v = hp.values[hp.meta[e].y];
@@ -311,6 +332,14 @@ void build_sparse_host(const HostPlan& hp, double pilot_f, bool eager, SparsePro
     else if (ty == ELEM_C) sp.el_b[e] = v;
     else if (ty == ELEM_L) { sp.el_g[e] = 1 / v; sp.ind_L.push_back(v); }
   }
+  return true;
+}
+
+void build_sparse_host(const HostPlan& hp, double pilot_f, bool eager, SparseProgram& sp) {
+  sp = SparseProgram();
+  const HostGather& G = hp.ac;
+  const int n_ent = (int)G.ent_col.size();
+  if (!entry_constants(hp, sp)) return;  // R<=0: dense kernel reports it
   PilotInput pin;
   pin.n = hp.nvar;
   pin.row_ptr = &G.row_ptr;
@@ -877,11 +906,206 @@ int launch_ac_sparse(DeviceCtx& ctx, const HostPlan& hp, const DevPlan& dp, cons
 }
 
 // ---------------------------------------------------------------------------------
+// Dense register-tile tier (SPICEY_TIER_TILE): tile_plan.h picks the thread grid for Nvar, tile_kernel.cuh (embedded as
+// text, compiled by NVRTC once per (Nvar, shape) and cached on disk) stamps, factors with partial pivoting and unpacks.
+struct TileArgs {   // must match tile_kernel.cuh
+  const double* freqs; long long n_freq, p_begin, p_count;
+  double2* x; double2* ielem; int* status; long long series_ld;
+  const int4* ends; const int2* meta; const double* values; const int* var_of_slot; const double* var_values; long long n_inst;
+  const int* ent_rc; const int* ent_ptr; const int* contrib;
+  const double2* ctab; const double4* el_rec; const double* ind_L;
+  long long* fb_list; int* fb_count;
+  int n_ind, n_ent, nn, nV, n_elem, n_ac_elem, off_v, off_v_end, off_i;
+};
+
+constexpr long long kTileMinPoints = 4096;   // below this the ~2 s compile of a new (Nvar, shape) does not pay off (unless forced)
+
+bool tile_shape_for(const DeviceCtx& ctx, const HostPlan& hp, TileShape& sh) {
+  const int n_src = hp.nV + hp.nI;
+  if (hp.nvar > 0xffff) return false;
+  if (const char* e = getenv("SPICEY_TILE_SHAPE")) {   // experiments: TR,TC[,CTAs per SM]
+    int a = 0, b = 0, c = 0;
+    if (sscanf(e, "%d,%d,%d", &a, &b, &c) >= 2) {
+      sh = tile_shape_eval(hp.nvar, a, b, hp.n_elem, n_src, ctx.smem_optin, c);
+      if (sh.ok && c > 0) sh.minb = c;
+      if (sh.ok) return true;
+    }
+  }
+  sh = choose_tile_shape(hp.nvar, hp.n_elem, n_src, ctx.smem_optin);
+  return sh.ok;
+}
+
+// variant: bit 0 element currents, bit 1 constant tables (plain frequency sweep), bit 2 (alpha, beta)-only tables
+std::string tile_source(const TileShape& sh, int variant) {
+  char head[320];
+  snprintf(head, sizeof head, "#define TL_N %d\n#define TL_TR %d\n#define TL_TC %d\n#define TL_WARPS %d\n#define TL_MINB %d\n#define TL_IELEM %d\n"
+           "#define TL_CONST %d\n#define TL_RC %d\n",
+           sh.n, sh.tr, sh.tc, sh.warps, sh.minb, variant & 1, (variant >> 1) & 1, (variant >> 2) & 1);
+  return std::string(head) + kTileKernelSource;
+}
+
+// Tables of the topology for one tile shape: the per-entry gather lists (per-instance stamping: the plan's lists are
+// per row, one thread per ENTRY balances a dense matrix) and, for plain frequency sweeps, every thread's tile entries
+// as constants in the order the kernel reads them, the element records of the unpack phase and the inductances.
+int prepare_tile(DeviceCtx& ctx, const HostPlan& hp, const TileShape& sh, cudaStream_t stream) {
+  const int shape[3] = {sh.tr, sh.tc, sh.warps};
+  uint64_t key = fnv1a(plan_key(hp), shape, sizeof shape);
+  key = fnv1a(key, hp.var_of_slot.data(), sizeof(int) * hp.var_of_slot.size());
+  if (!key) key = 1;
+  if (ctx.tl_key == key) return SPICEY_SUCCESS;
+  ctx.tl_key = 0;
+  const int n_ent = (int)hp.ac.ent_col.size();
+  std::vector<int> ent_rc(std::max(1, n_ent));
+  for (int r = 0; r < hp.nvar; ++r)
+    for (int en = hp.ac.row_ptr[r]; en < hp.ac.row_ptr[r + 1]; ++en) ent_rc[en] = r | (hp.ac.ent_col[en] << 16);
+  std::vector<unsigned char> blob;
+  const size_t o_rc = push_blob(blob, ent_rc), o_ep = push_blob(blob, hp.ac.ent_ptr), o_co = push_blob(blob, hp.ac.contrib);
+  // constants: only when no value slot varies per instance and every R > 0
+  bool swept = false;
+  for (int v : hp.var_of_slot) swept = swept || v >= 0;
+  SparseProgram sc;
+  ctx.tl_dev.has_const = !swept && entry_constants(hp, sc);
+  size_t o_ct = 0, o_er = 0, o_il = 0;
+  if (ctx.tl_dev.has_const) {
+    bool rc_only = true;
+    for (int en = 0; en < n_ent; ++en) rc_only = rc_only && sc.ent_gamma[en] == 0.0 && sc.ent_jim[en] == 0.0;
+    ctx.tl_dev.rc_only = rc_only;
+    const int n = hp.nvar, threads = sh.warps * 32, tpw = 32 / sh.tr;
+    std::vector<int> ent_of((size_t)n * (n + 1), -1);
+    for (int en = 0; en < n_ent; ++en) ent_of[(size_t)(ent_rc[en] & 0xffff) * (n + 1) + (ent_rc[en] >> 16)] = en;
+    std::vector<double2> tab((size_t)sh.mr * sh.mc * threads * (rc_only ? 1 : 2), make_double2(0.0, 0.0));
+    for (int tid = 0; tid < threads; ++tid) {
+      const int lane = tid & 31, warp = tid >> 5;
+      const int tr = lane % sh.tr, tc = std::min(warp * tpw + lane / sh.tr, sh.tc - 1);   // as the kernel maps (and mirrors) its lanes
+      for (int m = 0; m < sh.mr; ++m)
+        for (int c = 0; c < sh.mc; ++c) {
+          const int i = m * sh.tr + tr, j = c * sh.tc + tc;
+          const int en = (i < n && j <= n) ? ent_of[(size_t)i * (n + 1) + j] : -1;
+          if (en < 0) continue;
+          const size_t o = (size_t)(m * sh.mc + c) * threads + tid;
+          if (rc_only) tab[o] = make_double2(sc.ent_alpha[en] + sc.ent_jre[en], sc.ent_beta[en]);
+          else {
+            tab[2 * o] = make_double2(sc.ent_alpha[en] + sc.ent_jre[en], sc.ent_jim[en]);
+            tab[2 * o + 1] = make_double2(sc.ent_beta[en], sc.ent_gamma[en]);
+          }
+        }
+    }
+    std::vector<double4> el_rec(std::max(1, hp.n_ac_elem));
+    for (int e = 0; e < hp.n_ac_elem; ++e) {
+      const int n1 = hp.ends[e].x, n2 = hp.ends[e].y;
+      long long ij;
+      double4 r = make_double4(0.0, 0.0, 0.0, 0.0);
+      if (e >= hp.off[ELEM_V]) {   // a V element's current is its branch unknown
+        ij = (long long)(hp.nn + (e - hp.off[ELEM_V])) | ((long long)n << 32);
+        r.y = 1.0;
+      } else {
+        ij = (long long)(n1 ? n1 - 1 : n) | ((long long)(n2 ? n2 - 1 : n) << 32);
+        r.y = sc.el_a[e]; r.z = sc.el_b[e]; r.w = sc.el_g[e];
+      }
+      memcpy(&r.x, &ij, sizeof ij);
+      el_rec[e] = r;
+    }
+    ctx.tl_dev.n_ind = (int)sc.ind_L.size();
+    if (sc.ind_L.empty()) sc.ind_L.push_back(0.0);
+    o_ct = push_blob(blob, tab); o_er = push_blob(blob, el_rec); o_il = push_blob(blob, sc.ind_L);
+  }
+  int rc = ctx.tl_blob.ensure(blob.size() + 16);
+  if (rc) return rc;
+  CUDA_TRY(cudaMemcpyAsync(ctx.tl_blob.p, blob.data(), blob.size(), cudaMemcpyHostToDevice, stream));
+  CUDA_TRY(cudaStreamSynchronize(stream));
+  unsigned char* b = (unsigned char*)ctx.tl_blob.p;
+  ctx.tl_dev.ent_rc = b + o_rc; ctx.tl_dev.ent_ptr = b + o_ep; ctx.tl_dev.contrib = b + o_co; ctx.tl_dev.n_ent = n_ent;
+  ctx.tl_dev.ctab = b + o_ct; ctx.tl_dev.el_rec = b + o_er; ctx.tl_dev.ind_L = b + o_il;
+  ctx.tl_key = key;
+  return SPICEY_SUCCESS;
+}
+
+DeviceCtx::TileJit* ensure_tile_jit(DeviceCtx& ctx, const TileShape& sh, int variant) {
+  DeviceCtx::TileJit& jv = ctx.tile_jit[variant & 7];
+  const int shape[6] = {sh.n, sh.tr, sh.tc, sh.warps, sh.minb, variant};
+  uint64_t key = fnv1a(1469598103934665603ull, shape, sizeof shape);
+  if (!key) key = 1;
+  if (jv.key == key) return jv.failed ? nullptr : &jv;
+  jv.key = key;
+  jv.failed = true;
+  if (jv.lib) { cudaLibraryUnload(jv.lib); jv.lib = nullptr; jv.kernel = nullptr; }
+  const std::string src = tile_source(sh, variant);
+  if (!load_jit_kernel(src, "spicey_tile_jit", &jv.lib, &jv.kernel, ctx.tl_note)) return nullptr;
+  jv.n = sh.n; jv.tr = sh.tr; jv.tc = sh.tc; jv.warps = sh.warps; jv.minb = sh.minb;
+  jv.failed = false;
+  ctx.tl_note = "ok";
+  return &jv;
+}
+
+// Stamps, factors and unpacks args.p_count points with the register-tile kernel; *used = false when the tier does not
+// apply (no shape fits, the compile failed): the caller then takes the one-thread-per-row kernel.
+int launch_ac_tile(DeviceCtx& ctx, const HostPlan& hp, const DevPlan& dp, const AcArgs& args, uint32_t flags,
+                   cudaStream_t stream, int64_t* launches, bool* used) {
+  *used = false;
+  TileShape sh;
+  if (!tile_shape_for(ctx, hp, sh)) return SPICEY_SUCCESS;
+  int rc = prepare_tile(ctx, hp, sh, stream);
+  if (rc) return rc;
+  const bool cst = ctx.tl_dev.has_const && dp.n_inst == 1 && !(flags & SPICEY_FLAG_TILE_GENERIC);
+  const int variant = (args.ielem ? 1 : 0) | (cst ? 2 : 0) | (cst && ctx.tl_dev.rc_only ? 4 : 0);
+  DeviceCtx::TileJit* jv = ensure_tile_jit(ctx, sh, variant);
+  if (!jv) return SPICEY_SUCCESS;
+  const size_t smem = tile_smem_bytes(hp.nvar, cst ? 0 : hp.n_elem, cst ? 0 : hp.nV + hp.nI, jv->tr, jv->tc, cst);
+  CUDA_TRY(cudaFuncSetAttribute((const void*)jv->kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  unsigned grid = (unsigned)std::min<long long>(args.p_count, (long long)ctx.sm_count * jv->minb);
+  if (const char* e = getenv("SPICEY_TILE_GRID")) grid = std::min<unsigned>(grid, (unsigned)std::max(1, atoi(e)));   // experiments
+  TileArgs a;
+  memset(&a, 0, sizeof a);
+  a.freqs = args.freqs; a.n_freq = args.n_freq; a.p_begin = args.p_begin; a.p_count = args.p_count;
+  a.x = args.x; a.ielem = args.ielem; a.status = args.status; a.series_ld = args.series_ld;
+  a.ends = dp.ends; a.meta = dp.meta; a.values = dp.values; a.var_of_slot = dp.var_of_slot; a.var_values = dp.var_values;
+  a.n_inst = dp.n_inst;
+  a.ent_rc = (const int*)ctx.tl_dev.ent_rc; a.ent_ptr = (const int*)ctx.tl_dev.ent_ptr; a.contrib = (const int*)ctx.tl_dev.contrib;
+  a.n_ent = ctx.tl_dev.n_ent; a.nn = hp.nn; a.nV = hp.nV; a.n_elem = hp.n_elem; a.n_ac_elem = hp.n_ac_elem;
+  a.off_v = hp.off[ELEM_V]; a.off_v_end = hp.off[ELEM_V + 1]; a.off_i = hp.off[ELEM_I];
+  const bool guards = cst && ctx.tl_dev.n_ind > 0;   // points that trip an inductor guard go to the one-thread-per-row kernel
+  if (cst) {
+    a.ctab = (const double2*)ctx.tl_dev.ctab; a.el_rec = (const double4*)ctx.tl_dev.el_rec; a.ind_L = (const double*)ctx.tl_dev.ind_L;
+    a.n_ind = ctx.tl_dev.n_ind;
+    if (guards) {
+      if ((rc = ctx.sp_fb.ensure(sizeof(long long) * args.p_count + 64))) return rc;
+      a.fb_count = (int*)ctx.sp_fb.p;
+      a.fb_list = (long long*)((char*)ctx.sp_fb.p + 64);
+      CUDA_TRY(cudaMemsetAsync(a.fb_count, 0, sizeof(int), stream));
+    }
+  }
+  void* kargs[] = {&a};
+  CUDA_TRY(cudaLaunchKernel((const void*)jv->kernel, dim3(grid), dim3(jv->warps * 32), kargs, smem, stream));
+  if (launches) ++*launches;
+  *used = true;
+  if (guards) {
+    AcArgs d = args;
+    d.plist = a.fb_list;
+    d.pcount = a.fb_count;
+    d.fb_total = (unsigned long long*)((char*)ctx.sp_fb.p + 32);
+    return launch_ac_dense(ctx, hp, dp, d, flags, stream, nullptr, launches);
+  }
+  return SPICEY_SUCCESS;
+}
+
+// ---------------------------------------------------------------------------------
 // AC launch on one device (device pointers), asynchronous on `stream`.
 int launch_ac_dense(DeviceCtx& ctx, const HostPlan& hp, const DevPlan& dp, const AcArgs& args, uint32_t flags,
               cudaStream_t stream, int* tier_out, int64_t* launches) {
   if (args.p_count <= 0) return SPICEY_SUCCESS;
   const bool strict = flags & SPICEY_FLAG_STRICT;
+  // Large batches: the matrix in registers, 2-D tiles (tile_kernel.cuh).  Strict mode, the global-scratch tier, the
+  // fallback lists of the sparse tiers and small batches stay with one thread per row in shared memory.
+  if (!strict && !(flags & (SPICEY_FLAG_FORCE_GMEM | SPICEY_FLAG_NO_JIT | SPICEY_FLAG_NO_TILE)) && !args.plist &&
+      (args.p_count >= kTileMinPoints || (flags & (SPICEY_FLAG_JIT | SPICEY_FLAG_TILE))) && args.series_ld < (1ll << 40)) {
+    bool used = false;
+    int rc = launch_ac_tile(ctx, hp, dp, args, flags, stream, launches, &used);
+    if (rc) return rc;
+    if (used) {
+      if (tier_out) *tier_out = SPICEY_TIER_TILE;
+      return SPICEY_SUCCESS;
+    }
+  }
   const int NT = round32(hp.nvar);
   const int nwarps = NT / 32;
   AcSmem sm(hp.nvar, hp.n_elem, hp.nV + hp.nI, hp.MW, nwarps, false);
@@ -931,7 +1155,18 @@ int launch_ac(DeviceCtx& ctx, const HostPlan& hp, const DevPlan& dp, const AcArg
       int rc = prepare_sparse(ctx, hp, pilot_f, eager, stream);
       if (rc) return rc;
     }
-    if (ctx.sp_valid) return launch_ac_sparse(ctx, hp, dp, args, flags, stream, tier_out, launches);
+    if (ctx.sp_valid) {
+      // A program that executes most of the dense elimination's work has nothing to gain from the program tiers (their
+      // per-operation bookkeeping, workspaces in memory): dense circuits go to the register-tile kernel.
+      const long long nv = hp.nvar;
+      const long long dense_cfma = nv * (nv - 1) * (2 * nv + 5) / 6;   // sum_k (n - 1 - k)(n + 1 - k): the update of :47-52 without skips
+      const bool dense_like = ctx.sp.n_fma * 2 >= dense_cfma && nv >= 8;
+      if ((flags & SPICEY_FLAG_TILE) || (dense_like && args.p_count >= kTileMinPoints && !(flags & (SPICEY_FLAG_BAND | SPICEY_FLAG_WARP | SPICEY_FLAG_NO_TILE | SPICEY_FLAG_NO_JIT)))) {
+        TileShape sh;
+        if (tile_shape_for(ctx, hp, sh)) return launch_ac_dense(ctx, hp, dp, args, flags | SPICEY_FLAG_TILE, stream, tier_out, launches);
+      }
+      return launch_ac_sparse(ctx, hp, dp, args, flags, stream, tier_out, launches);
+    }
   }
   return launch_ac_dense(ctx, hp, dp, args, flags, stream, tier_out, launches);
 }
@@ -1193,11 +1428,12 @@ void spicey_destroy(spicey_handle* h) {
     cudaDeviceSynchronize();
     Buffer* bufs[] = {&c.plan, &c.scratch, &c.in0, &c.in1, &c.in2, &c.out_x[0], &c.out_x[1], &c.out_i[0],
                       &c.out_i[1], &c.out_s[0], &c.out_s[1], &c.aux0, &c.aux1, &c.sp_blob, &c.sp_work, &c.sp_fb,
-                      &c.wp_blob, &c.wp_work, &c.bp_blob, &c.bp_work};
+                      &c.wp_blob, &c.wp_work, &c.bp_blob, &c.bp_work, &c.tl_blob};
     for (Buffer* b : bufs) b->release();
     for (auto& jv : c.sp_jit) if (jv.lib) cudaLibraryUnload(jv.lib);
     for (auto& jv : c.tr_jit) if (jv.lib) cudaLibraryUnload(jv.lib);
     for (auto& jv : c.band_jit) if (jv.lib) cudaLibraryUnload(jv.lib);
+    for (auto& jv : c.tile_jit) if (jv.lib) cudaLibraryUnload(jv.lib);
     for (auto e : c.events) cudaEventDestroy(e);
     cudaStreamDestroy(c.compute);
     cudaStreamDestroy(c.copy);
@@ -1696,6 +1932,26 @@ int64_t spicey_debug_band_source(int32_t L, int32_t RPL, int32_t NB, uint32_t ab
   BandPlan bp;
   bp.L = L; bp.RPL = RPL; bp.NB = NB; bp.abmask = abmask & 0xffffu; bp.rc_only = (abmask >> 16) & 1u;
   const std::string src = band_source(bp, with_ielem != 0, warps, minb);
+  if (buf && cap > 0) {
+    const size_t n = std::min<size_t>(src.size(), (size_t)cap - 1);
+    memcpy(buf, src.data(), n);
+    buf[n] = 0;
+  }
+  return (int64_t)src.size() + 1;
+}
+
+int64_t spicey_debug_tile_source(int32_t nvar, int32_t n_elem, int32_t n_src, int32_t tr, int32_t tc, int32_t with_ielem,
+                                 int32_t* shape_out, char* buf, int64_t cap) {
+  const size_t smem_optin = 227 * 1024;   // an sm_100 SM's opt-in shared memory per CTA
+  const TileShape sh = (tr > 0 && tc > 0) ? tile_shape_eval(nvar, tr, tc, n_elem, n_src, smem_optin) : choose_tile_shape(nvar, n_elem, n_src, smem_optin);
+  if (!sh.ok) return -1;
+  if (shape_out) {
+    const bool cst = (with_ielem >> 1) & 1;
+    const int32_t v[8] = {sh.tr, sh.tc, sh.mr, sh.mc, sh.warps, sh.minb, sh.regs,
+                          (int32_t)tile_smem_bytes(nvar, cst ? 0 : n_elem, cst ? 0 : n_src, sh.tr, sh.tc, cst)};
+    memcpy(shape_out, v, sizeof v);
+  }
+  const std::string src = tile_source(sh, with_ielem);
   if (buf && cap > 0) {
     const size_t n = std::min<size_t>(src.size(), (size_t)cap - 1);
     memcpy(buf, src.data(), n);

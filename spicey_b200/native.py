@@ -18,8 +18,10 @@ ST_OK, ST_SINGULAR, ST_CDIV, ST_R_NONPOS = 0, 1, 2, 3
 FLAG_STRICT, FLAG_FORCE_GMEM, FLAG_FORCE_CTA, FLAG_DENSE, FLAG_SPARSE, FLAG_GENERIC_THREAD = 1, 2, 4, 8, 16, 32
 FLAG_SERIES_MAJOR, FLAG_JIT, FLAG_NO_JIT, FLAG_WARP, FLAG_NO_WARP = 64, 128, 256, 512, 1024
 FLAG_BAND, FLAG_NO_BAND = 2048, 4096
+FLAG_TILE, FLAG_NO_TILE, FLAG_TILE_GENERIC = 8192, 16384, 32768
 TIER_THREAD, TIER_CTA_SMEM, TIER_CTA_GMEM, TIER_SPARSE, TIER_SPARSE_JIT, TIER_TRAN_JIT, TIER_SPARSE_WARP = 1, 2, 3, 4, 5, 6, 7
 TIER_BAND = 8
+TIER_TILE = 9
 SUCCESS, ERR_INVALID, ERR_NO_DEVICE, ERR_CUDA, ERR_UNSUPPORTED = 0, 1, 2, 3, 4
 
 EXPORTS = [
@@ -28,7 +30,7 @@ EXPORTS = [
     "spicey_ac_solve_device", "spicey_tran_solve", "spicey_tran_solve_device", "spicey_measure_fp64_peak",
     "spicey_debug_sparse_source", "spicey_series_ld", "spicey_debug_tran_source", "spicey_debug_warp_stats",
     "spicey_tran_solve_waves", "spicey_tran_solve_waves_device", "spicey_debug_tran_source_waves",
-    "spicey_debug_band_stats", "spicey_debug_band_source",
+    "spicey_debug_band_stats", "spicey_debug_band_source", "spicey_debug_tile_source",
 ]
 WAVE_DC, WAVE_TABLE, WAVE_PULSE, WAVE_PWL = 0, 1, 2, 3
 
@@ -126,6 +128,9 @@ def load_library(path: Optional[str] = None):
     lib.spicey_debug_band_source.restype = C.c_int64
     lib.spicey_debug_band_source.argtypes = [C.c_int32, C.c_int32, C.c_int32, C.c_uint32, C.c_int32, C.c_int32, C.c_int32,
                                              C.c_char_p, C.c_int64]
+    lib.spicey_debug_tile_source.restype = C.c_int64
+    lib.spicey_debug_tile_source.argtypes = [C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _ip,
+                                             C.c_char_p, C.c_int64]
     if path == _build.LIB_PATH:
         _LIB = lib
     return lib
@@ -164,6 +169,22 @@ def band_kernel_source(lanes=8, rows_per_lane=2, border_rows=1, border_col_mask=
     buf = C.create_string_buffer(need)
     lib.spicey_debug_band_source(*args, buf, need)
     return buf.value.decode()
+
+
+def tile_kernel_source(nvar: int, n_elem: int = 0, n_src: int = 1, tr: int = 0, tc: int = 0, with_ielem=True,
+                       const_tables=False, rc_only=False):
+    """(CUDA source, shape dict) of the dense register-tile kernel (tier 9) for an Nvar-unknown circuit; tr, tc > 0
+    force the thread grid.  None when no shape fits an SM.  Host-only tooling."""
+    lib = load_library()
+    shp = (C.c_int32 * 8)()
+    args = (nvar, n_elem, n_src, tr, tc, (1 if with_ielem else 0) | (2 if const_tables else 0) | (4 if rc_only else 0), shp)
+    need = lib.spicey_debug_tile_source(*args, None, 0)
+    if need < 0:
+        return None
+    buf = C.create_string_buffer(need)
+    lib.spicey_debug_tile_source(*args, buf, need)
+    keys = ("tr", "tc", "mr", "mc", "warps", "ctas_per_sm", "regs", "smem_bytes")
+    return buf.value.decode(), dict(zip(keys, list(shp)))
 
 
 def tran_kernel_source(table: "ElemTable", sweep: Optional["Sweep"] = None, with_ielem=True,

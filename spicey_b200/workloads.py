@@ -60,6 +60,26 @@ def rc_mesh(side: int = 16, ppd: int = 1600000, f1: str = "1", f2: str = "100k")
     return "\n".join(lines) + "\n"
 
 
+def rc_dense(n_nodes: int = 64, ppd: int = 200000, f1: str = "10k", f2: str = "1g") -> str:
+    """A dense MNA system of cfg 2's size (Nvar = n_nodes + 1): a resistor between EVERY pair of nodes (values spread
+    over a decade so that no two matrix entries coincide), a capacitor to ground at every node but the driven one.
+    The nodal matrix has no structural zero: the workload of the dense pivoting LU (lib/math/solveComplex.ts:15-53
+    without its `|f| < EPS` shortcut ever applying).  The sweep (five decades, 1,000,001 points like cfg 2) covers the
+    range where the capacitors load the network (w C ~ G around 1 MHz): below it every node sits at the source voltage
+    and the resistor currents are differences of nearly equal numbers."""
+    lines = ["* %d-node complete RC graph AC sweep" % n_nodes, "v1 n1 0 ac 1"]
+    k = 0
+    for i in range(1, n_nodes + 1):
+        for j in range(i + 1, n_nodes + 1):
+            k += 1
+            lines.append("r%d n%d n%d %d" % (k, i, j, 1000 + 37 * ((i * 7 + j * 13) % 251)))
+    for i in range(2, n_nodes + 1):
+        lines.append("c%d n%d 0 %dp" % (i, i, 500 + 17 * i))
+    lines.append(".ac dec %d %s %s" % (ppd, f1, f2))
+    lines.append(".end")
+    return "\n".join(lines) + "\n"
+
+
 RLC_TANK = """* RLC tank Monte-Carlo
 V1 1 0 PULSE(0 1 0 1n 1n 1 2)
 R1 1 2 50

@@ -1110,3 +1110,128 @@ def test_tran_mid_sized_circuit_cta_tiers(eng):
             for k, b in ref[kind].items():
                 a, b = np.asarray(got[kind][k]), np.asarray(b)
                 assert np.max(np.abs(a - b)) <= TRAN_TOL * max(1e-30, float(np.max(np.abs(b)))), (kind, k)
+
+
+# ---- dense register-tile tier (tier 9, tile_kernel.cuh) -----------------------------------
+
+TILE = native.FLAG_DENSE | native.FLAG_TILE
+TGEN = native.FLAG_TILE_GENERIC   # stamp from the element table (the per-instance path) instead of the sweep's constants
+
+
+@pytest.mark.parametrize("flags", [TILE, TILE | SM, TILE | TGEN, TILE | TGEN | SM])
+def test_ac_tile_tier_ladder64_slice(eng, flags):
+    """cfg 2 topology through the dense register-tile kernel (2-D cyclic tiles of [A b] in registers, partial pivoting with
+    physical row swaps as solveComplex.ts:15-53): every 997th frequency against the oracle, magnitude and phase."""
+    import spicey_b200 as sp
+    text = w.rc_ladder(64)
+    freqs = np.array(sp.analysis.ac_frequencies(parse_netlist(text)))[::997]
+    out, x, ie, st, _ = ac_case(eng, text, freqs, flags)
+    assert eng.stats()["tier"] == native.TIER_TILE, eng.stats()
+    assert out["status"].max() == 0 and st.max() == 0
+    assert rel_err(out["x"], x) <= AC_TOL, rel_err(out["x"], x)
+    assert rel_err(out["ielem"], ie) <= AC_TOL
+    assert rel_err(np.abs(out["x"]), np.abs(x)) <= AC_TOL
+    assert np.max(np.abs(np.angle(out["x"] * np.conj(x)))) <= AC_TOL
+
+
+def test_ac_tile_tier_dense65_default_policy(eng):
+    """A complete RC graph on 64 nodes (Nvar = 65, no structural zero, the V row forces a row swap at the first step):
+    4,100 points with default flags must take the register-tile tier (the sparse program would execute the whole dense
+    elimination); every 64th point against the oracle, per entry."""
+    import spicey_b200 as sp
+    ck = parse_netlist(w.rc_dense(64))
+    freqs = np.array(sp.analysis.ac_frequencies(ck))
+    assert freqs.shape[0] == 1000001
+    freqs = np.ascontiguousarray(freqs[:: freqs.shape[0] // 4100][:4100])
+    xr, ier, st = co.ac_solve(ck, freqs[::64], nthreads=8)
+    iscale = np.max(np.abs(ier), axis=1, keepdims=True)   # a current is a difference of two node voltages: relative to the row's largest
+    for flags in (0, SM, TGEN):
+        out = sp.simulate_ac_batch(ck, freqs, engine=eng, flags=flags)
+        assert eng.stats()["tier"] == native.TIER_TILE, (flags, eng.stats())
+        assert out["status"].max() == 0 and st.max() == 0
+        assert rel_err(out["x"][0][::64], xr) <= AC_TOL, rel_err(out["x"][0][::64], xr)
+        assert np.max(np.abs(out["ielem"][0][::64] - ier) / iscale) <= AC_TOL
+    # the old one-thread-per-row kernel on the same points: both are partial pivoting on the same numbers
+    out2 = sp.simulate_ac_batch(ck, freqs[::64], engine=eng, flags=native.FLAG_DENSE | native.FLAG_NO_TILE)
+    assert eng.stats()["tier"] == native.TIER_CTA_SMEM
+    assert rel_err(out2["x"][0], xr) <= AC_TOL
+
+
+@pytest.mark.parametrize("n_nodes,n_elem", [(1, 0), (2, 3), (5, 12), (14, 60), (30, 200), (31, 40), (62, 300), (90, 500)])
+def test_ac_tile_tier_random_rlc_networks(eng, n_nodes, n_elem):
+    """Random RLC networks (pivoting away from the diagonal, ties, inductor guards) through the register-tile tier for
+    Nvar = 3 .. 92, point-major and series-major, statuses equal to the oracle's."""
+    import spicey_b200 as sp
+    rng = np.random.default_rng(n_nodes * 1000 + n_elem)
+    text = random_rlc_netlist(rng, n_nodes, n_elem, n_v=min(2, n_nodes))
+    freqs = sp.analysis.ac_frequencies(parse_netlist(text))
+    for flags in (TILE, TILE | SM, TILE | TGEN):
+        out, x, ie, st, _ = ac_case(eng, text, freqs, flags)
+        assert eng.stats()["tier"] == native.TIER_TILE, eng.stats()
+        assert np.array_equal(out["status"], st) and st.max() == 0
+        scale = np.max(np.abs(x), axis=2, keepdims=True)
+        assert np.max(np.abs(out["x"] - x) / scale) <= AC_TOL
+        iscale = np.max(np.abs(ie), axis=2, keepdims=True)
+        assert np.max(np.abs(out["ielem"] - ie) / iscale) <= AC_TOL
+
+
+@pytest.mark.parametrize("shape", ["16,5", "8,9", "32,3", "4,17", "13,10,1", "7,7", "1,36", "32,1"])
+def test_ac_tile_tier_forced_shapes(shape, monkeypatch):
+    """Thread grids other than the chosen one (SPICEY_TILE_SHAPE=TR,TC[,CTAs per SM]): thread columns that do not fill a
+    warp (mirror lanes), one thread row, one thread column, tiles that do not divide Nvar."""
+    import spicey_b200 as sp
+    monkeypatch.setenv("SPICEY_TILE_SHAPE", shape)
+    e = native.Engine()
+    try:
+        for n_nodes, n_elem in ((30, 200), (9, 30)):
+            rng = np.random.default_rng(n_nodes * 1000 + n_elem)
+            text = random_rlc_netlist(rng, n_nodes, n_elem, n_v=2)
+            ck = parse_netlist(text)
+            freqs = sp.analysis.ac_frequencies(ck)
+            x, ie, st = co.ac_solve(ck, freqs, nthreads=4)
+            for flags in (TILE, TILE | TGEN):
+                out = sp.simulate_ac_batch(ck, freqs, engine=e, flags=flags)
+                assert e.stats()["tier"] == native.TIER_TILE, e.stats()
+                assert out["status"].max() == 0 and st.max() == 0
+                scale = np.max(np.abs(x), axis=1, keepdims=True)
+                assert np.max(np.abs(out["x"][0] - x) / scale) <= AC_TOL, shape
+                iscale = np.max(np.abs(ie), axis=1, keepdims=True)
+                assert np.max(np.abs(out["ielem"][0] - ie) / iscale) <= AC_TOL, shape
+    finally:
+        e.close()
+
+
+def test_ac_tile_tier_statuses_sweeps_and_current_sources(eng):
+    """Error statuses (R <= 0, singular, Complex.div guard) isolated per point, per-instance value sweeps, no element
+    currents requested, and an I element, all through the register-tile tier."""
+    import spicey_b200 as sp
+    n = 8
+    r = np.full(n, 30.0)
+    r[3] = -1.0
+    out, x, ie, st, _ = ac_case(eng, w.README_RC, [1.0, 10.0], TILE, n_inst=n, overrides={"r1": r})
+    assert eng.stats()["tier"] == native.TIER_TILE
+    assert np.array_equal(out["status"], st) and (st[3] == native.ST_R_NONPOS).all()
+    ok = [0, 1, 2, 4, 5, 6, 7]
+    assert rel_err(out["x"][ok], x[ok]) <= AC_TOL and np.isnan(out["x"][3]).all()
+    out, x, ie, st, _ = ac_case(eng, "* sing\nv1 a 0 ac 1\nv2 a 0 ac 1\nr1 a 0 1k\n.ac lin 2 1 2\n", [1.0, 2.0], TILE)
+    assert (st == native.ST_SINGULAR).all() and np.array_equal(out["status"], st)
+    out, x, ie, st, _ = ac_case(eng, "* cdiv\nv1 a 0 ac 1\nl1 a b 1e-10\nr1 b 0 1k\n.ac lin 2 1 2\n", [1.0, 1e6], TILE)
+    assert st[0, 0] == native.ST_CDIV and st[0, 1] == 0 and np.array_equal(out["status"], st)
+    assert rel_err(out["x"][0, 1], x[0, 1]) <= AC_TOL
+    # Monte-Carlo axis: 37 instances x 11 frequencies with swept R / C / source phasor
+    rng = np.random.default_rng(5)
+    n = 37
+    ov = {"r1": rng.uniform(10, 100, n), "c1": rng.uniform(1e-5, 1e-3, n), "v1.acmag": rng.uniform(0.5, 2, n),
+          "v1.acphase": rng.uniform(-180, 180, n)}
+    out, x, ie, st, _ = ac_case(eng, w.README_RC, np.logspace(0, 3, 11), TILE | SM, n_inst=n, overrides=ov)
+    assert eng.stats()["tier"] == native.TIER_TILE and out["status"].max() == 0
+    assert rel_err(out["x"], x) <= AC_TOL and rel_err(out["ielem"], ie) <= AC_TOL
+    # current source (Norton) against the oracle
+    ck = parse_netlist(NORTON, current_sources=True)
+    ref = o.simulate_ac(parse_netlist(NORTON, current_sources=True))
+    got = sp.simulate_ac_batch(ck, np.array(ref["freqs"]), engine=eng, flags=TILE)
+    assert eng.stats()["tier"] == native.TIER_TILE and got["status"].max() == 0
+    for j, nm in enumerate(got["node_names"]):
+        assert rel_err(got["x"][0][:, j], np.array([complex(z) for z in ref["nodeVoltages"][nm]])) <= AC_TOL, nm
+    for j, nm in enumerate(got["element_names"]):
+        assert rel_err(got["ielem"][0][:, j], np.array([complex(z) for z in ref["elementCurrents"][nm]])) <= AC_TOL, nm
