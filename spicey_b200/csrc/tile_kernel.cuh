@@ -73,7 +73,7 @@ struct TileArgs {   // must match TileArgs in spicey_native.cu
   int n_ind, n_ent, nn, nV, n_elem, n_ac_elem, off_v, off_v_end, off_i;
 };
 
-struct __align__(16) TileWin { double2 r; int p; int status; int pad0, pad1; };   // winner record of a step: 1/a_pk, pivot row
+struct __align__(16) TileWin { int p; int pad0, pad1, pad2; };   // winner record of a step: the pivot row (0x7fffffff: the column is all zeros)
 
 __device__ __forceinline__ tcplx tl_mul(tcplx a, tcplx b) {
   return make_double2(fma(a.x, b.x, -a.y * b.y), fma(a.x, b.y, a.y * b.x));
@@ -93,8 +93,8 @@ __device__ __forceinline__ double tl_rcp(double a) {   // MUFU seed + two Newton
 __device__ __forceinline__ void tl_sts(tcplx* p, tcplx v) {
   asm volatile("st.shared.v2.f64 [%0], {%1, %2};" ::"r"((unsigned)__cvta_generic_to_shared(p)), "d"(v.x), "d"(v.y));
 }
-__device__ __forceinline__ void tl_sts2(void* p, int a, int b) {
-  asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"((unsigned)__cvta_generic_to_shared(p)), "r"(a), "r"(b));
+__device__ __forceinline__ void tl_sts1(void* p, int a) {
+  asm volatile("st.shared.b32 [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(p)), "r"(a));
 }
 
 #if !TL_CONST
@@ -141,44 +141,38 @@ struct TileCtx {   // what the step functions need besides the tile
 
 // Pivot search of step k (solveComplex.ts:17-29) on the raw column `col` (local rows KR..), executed by all 32 lanes of
 // the warp that owns column k; `owner`: this lane holds entries of the column.  Publishes the raw column (everybody's
-// multipliers come from it), the winner record and 1/u_kk.
+// reciprocal and multipliers come from it) and the pivot row p.  The dependent chain is what the whole CTA waits for, so
+// it carries nothing else: |a|^2 per candidate, a first-maximum scan in ascending row order (a NaN wins only in place,
+// as `v > vmax` never holds for it in JavaScript), redux.sync.max over the high words of the IEEE bit patterns and, when a
+// single lane holds that maximum (the usual case), one shuffle of its row index; ties go through the low words and the
+// lowest row index.
 template <int KR>
 __device__ __forceinline__ void tl_search(const TileCtx& t, int k, const tcplx (&col)[TL_MR], bool owner) {
   const int par = k & 1;
-  unsigned long long key = 0ull;
+  double bm = -1.0;
   int bi = 0x7fffffff;
-  tcplx cand = make_double2(0.0, 0.0);
-  double bm = 1.0;
 #pragma unroll
   for (int m = KR; m < TL_MR; ++m) {
     const int i = m * TL_TR + t.tr;
-    if (owner) tl_sts(t.Cb + par * TL_NP + i, col[m]);
+    if (owner) tl_sts(t.Cb + par * (TL_NP + 1) + i, col[m]);
     const tcplx v = col[m];
     const double mt = fma(v.x, v.x, v.y * v.y);
-    unsigned long long kk = (unsigned long long)__double_as_longlong(mt);
-    if (mt != mt) kk = (i == k) ? ~0ull : 0ull;   // NaN only wins in place (JS: v > vmax is false)
-    if (!(owner && i >= k && i < TL_N)) kk = 0ull;
-    if (kk > key) { key = kk; bi = i; cand = v; bm = mt; }   // ascending i, strict >: the first maximum
+    const bool in = owner && i >= k && i < TL_N;
+    const bool take = in && ((i == k) ? !(mt <= bm) : (mt > bm));
+    if (take) { bm = mt; bi = i; }
   }
-  const double inv = tl_rcp(bm);   // speculative: overlaps the reduction
-  tcplx rc = make_double2(cand.x * inv, -cand.y * inv);
+  const unsigned long long key = bi == 0x7fffffff ? 0ull : (unsigned long long)__double_as_longlong(bm);
   const unsigned hi = (unsigned)(key >> 32), lo = (unsigned)key;
   const unsigned mh = __reduce_max_sync(TL_FULL, hi);
-  const unsigned ml = __reduce_max_sync(TL_FULL, hi == mh ? lo : 0u);
-  const bool top = hi == mh && lo == ml;
-  const int p = __reduce_min_sync(TL_FULL, top ? bi : 0x7fffffff);
-  const int wl = __ffs(__ballot_sync(TL_FULL, top && bi == p)) - 1;
-  const double vmax = __longlong_as_double((long long)(((unsigned long long)mh << 32) | ml));
-  int st = 0;
-  if (vmax < TL_EPS * TL_EPS) st = 1;        // singular (:29); the metric is |a|^2
-  else if (vmax < TL_EPS) st = 2;            // Complex.div by this pivot throws (Complex.ts:41-42)
-  rc.x = __shfl_sync(TL_FULL, rc.x, wl);
-  rc.y = __shfl_sync(TL_FULL, rc.y, wl);
-  if (t.lane == wl) {
-    tl_sts(&t.Wn[par].r, rc);
-    tl_sts2(&t.Wn[par].p, p, st);
-    tl_sts(t.Rd + k, rc);
+  const unsigned tie = __ballot_sync(TL_FULL, hi == mh);
+  int p;
+  if (__popc(tie) == 1) {
+    p = __shfl_sync(TL_FULL, bi, __ffs(tie) - 1);
+  } else {
+    const unsigned ml = __reduce_max_sync(TL_FULL, hi == mh ? lo : 0u);
+    p = __reduce_min_sync(TL_FULL, (hi == mh && lo == ml) ? bi : 0x7fffffff);
   }
+  if (t.lane == 0) tl_sts1(&t.Wn[par].p, p);
 }
 
 // The update a_ij -= f_i * u_kj (:47-52) of step k on the live part of the tile.  C1 >= 0: this warp owns column k + 1,
@@ -210,6 +204,35 @@ __device__ __forceinline__ void tl_update(const TileCtx& t, int k, int p, tcplx 
   }
 }
 
+// Local row mp (uniform across the CTA) of the tile, columns KC.., to / from a shared-memory row: a chain of uniform
+// branches, one taken, instead of a select per register.
+template <int KR, int KC, int M>
+__device__ __forceinline__ void tl_row_out(const tcplx (&A)[TL_MR][TL_MC], int mp, bool mine, tcplx* row, int tc) {
+  if (M >= TL_MR) return;
+  constexpr int MM = M < TL_MR ? M : TL_MR - 1;
+  if (mp == M) {
+    if (mine) {
+#pragma unroll
+      for (int c = KC; c < TL_MC; ++c) row[c * TL_TC + tc] = A[MM][c];
+    }
+  } else {
+    tl_row_out<KR, KC, (M < TL_MR ? M + 1 : M)>(A, mp, mine, row, tc);
+  }
+}
+template <int KR, int KC, int M>
+__device__ __forceinline__ void tl_row_in(tcplx (&A)[TL_MR][TL_MC], int mp, bool mine, const tcplx* row, int tc) {
+  if (M >= TL_MR) return;
+  constexpr int MM = M < TL_MR ? M : TL_MR - 1;
+  if (mp == M) {
+    if (mine) {
+#pragma unroll
+      for (int c = KC; c < TL_MC; ++c) A[MM][c] = row[c * TL_TC + tc];
+    }
+  } else {
+    tl_row_in<KR, KC, (M < TL_MR ? M + 1 : M)>(A, mp, mine, row, tc);
+  }
+}
+
 // The steps whose row k is local row KR of its thread row and whose column k is local column KC of its thread column:
 // one rolled loop, unrolled over the live part of the tile.
 template <int KR, int KC>
@@ -219,52 +242,48 @@ __device__ __forceinline__ void tl_segment(const TileCtx& t, tcplx (&A)[TL_MR][T
   constexpr int k1 = k1a > TL_N ? TL_N : k1a;
   if (k0 >= k1) return;
   const int tr = t.tr, tc = t.tc, warp = t.warp;
-  tcplx *Cb = t.Cb, *Pb = t.Pb, *Kb = t.Kb;
+  tcplx *Cb = t.Cb, *Pb = t.Pb, *Kb = t.Kb, *Rd = t.Rd;
 #pragma unroll 1
   for (int k = k0; k < k1; ++k) {
     if (status != 0) break;
     const int trk = k - KR * TL_TR, par = k & 1;
     __syncthreads();   // the search of step k is published; everybody has finished step k - 1
-    const TileWin wv = t.Wn[par];
-    if (wv.status != 0) { status = wv.status; break; }
-    const int p = wv.p;
-    const tcplx rk = wv.r;
+    const tcplx* Ck = Cb + par * (TL_NP + 1);
+    // warp-uniform by construction (one shared-memory word): telling the compiler so turns the row selections below
+    // into uniform branches instead of MR-way select chains
+    const int p = __reduce_min_sync(TL_FULL, t.Wn[par].p);
+    if (p == 0x7fffffff) { status = 1; break; }          // no candidate above zero: singular (:29)
+    // -- 1 / a_pk by everybody (:45), and the reference's two guards on the pivot --
+    const tcplx apk = Ck[p];
+    const double vmax = fma(apk.x, apk.x, apk.y * apk.y);   // |a_pk|^2
+    if (vmax < TL_EPS * TL_EPS) { status = 1; break; }    // |a_pk| < EPS: singular (:29)
+    if (vmax < TL_EPS) { status = 2; break; }             // Complex.div by this pivot throws (Complex.ts:41-42)
+    const double inv = tl_rcp(vmax);
+    const tcplx rk = make_double2(apk.x * inv, -apk.y * inv);
     const int trp = p % TL_TR, mp = p / TL_TR;
+    if (t.lane == 0 && t.warp == 0) Rd[k] = rk;
     // -- the pivot row and (when they differ) the old row k through shared memory: the swap of :30-34 --
-    if (tr == trp) {
+    tl_row_out<KR, KC, KR>(A, mp, tr == trp, Pb, tc);
+    if (p != k) {
+      if (tr == trk) {
 #pragma unroll
-      for (int m = KR; m < TL_MR; ++m)
-        if (m == mp) {
-#pragma unroll
-          for (int c = KC; c < TL_MC; ++c) Pb[c * TL_TC + tc] = A[m][c];
-        }
-    }
-    if (p != k && tr == trk) {
-#pragma unroll
-      for (int c = KC; c < TL_MC; ++c) Kb[c * TL_TC + tc] = A[KR][c];
+        for (int c = KC; c < TL_MC; ++c) Kb[c * TL_TC + tc] = A[KR][c];
+      }
     }
     __syncthreads();
-    // -- my rows' multipliers f_i = a_ik / a_pk from the raw column (:45-46); position p holds the old row k --
+    // -- my rows' multipliers f_i = a_ik / a_pk from the raw column (:45-46): position p holds the old row k, finished
+    //    rows and padding read the zero behind the column --
     tcplx F[TL_MR];
-    const tcplx akk = Cb[par * TL_NP + k];
 #pragma unroll
     for (int m = KR; m < TL_MR; ++m) {
       const int i = m * TL_TR + tr;
-      tcplx v = Cb[par * TL_NP + i];
-      if (i == p) v = akk;
-      tcplx fm = tl_mul(v, rk);
+      int idx = (i == p) ? k : i;
+      if (i <= k || i >= TL_N) idx = TL_NP;
+      tcplx fm = tl_mul(Ck[idx], rk);
       if (fma(fm.x, fm.x, fm.y * fm.y) < TL_EPS * TL_EPS) fm = make_double2(0.0, 0.0);   // :46
-      if (i <= k || i >= TL_N) fm = make_double2(0.0, 0.0);
       F[m] = fm;
     }
-    if (p != k && tr == trp) {
-#pragma unroll
-      for (int m = KR; m < TL_MR; ++m)
-        if (m == mp) {
-#pragma unroll
-          for (int c = KC; c < TL_MC; ++c) A[m][c] = Kb[c * TL_TC + tc];
-        }
-    }
+    if (p != k) tl_row_in<KR, KC, KR>(A, mp, tr == trp, Kb, tc);
     // column k + 1 belongs to thread column (k + 1) mod TC: (k + 1) - KC TC, or 0 when it opens local column KC + 1
     const int tck1 = (k + 1 >= (KC + 1) * TL_TC) ? 0 : k + 1 - KC * TL_TC;
     if (k + 1 < TL_N && warp == tck1 / TL_TPW) {
@@ -308,14 +327,14 @@ extern "C" __global__ void __launch_bounds__(TL_THREADS, TL_MINB) spicey_tile_ji
 
   tcplx* Aimg = (tcplx*)tl_smem;                       // [TL_NC][TL_LD]
 #if TL_CONST
-  tcplx* Cb = Aimg + (size_t)TL_NC * TL_LD;            // [2][TL_NP]
+  tcplx* Cb = Aimg + (size_t)TL_NC * TL_LD;            // [2][TL_NP + 1]
 #else
   const int n_src = a.nV + (a.n_elem - a.off_i);
   tcplx* Yv = Aimg + (size_t)TL_NC * TL_LD;            // [n_elem]
   tcplx* Jv = Yv + a.n_elem;                           // [n_src]
-  tcplx* Cb = Jv + (n_src > 0 ? n_src : 1);            // [2][TL_NP]
+  tcplx* Cb = Jv + (n_src > 0 ? n_src : 1);            // [2][TL_NP + 1]
 #endif
-  tcplx* Pb = Cb + 2 * TL_NP;                          // [TL_NCP]
+  tcplx* Pb = Cb + 2 * (TL_NP + 1);                    // [TL_NCP]   (Cb: [2][TL_NP + 1], the last entry of each a zero)
   tcplx* Kb = Pb + TL_NCP;                             // [TL_NCP]
   tcplx* Rd = Kb + TL_NCP;                             // [TL_N]
   tcplx* xs = Rd + TL_N;                               // [TL_N + 1]  (xs[TL_N] = 0: the ground node)
@@ -324,6 +343,7 @@ extern "C" __global__ void __launch_bounds__(TL_THREADS, TL_MINB) spicey_tile_ji
   int* s_status = (int*)(Wn + 2);
 #endif
   t.Cb = Cb; t.Pb = Pb; t.Kb = Kb; t.Rd = Rd; t.Wn = Wn;
+  if (tid < 2) Cb[tid * (TL_NP + 1) + TL_NP] = make_double2(0.0, 0.0);   // (visible after the first barrier of the point loop)
 
   for (long long q = blockIdx.x; q < a.p_count; q += gridDim.x) {
     const long long p_abs = a.p_begin + q;
@@ -348,7 +368,9 @@ extern "C" __global__ void __launch_bounds__(TL_THREADS, TL_MINB) spicey_tile_ji
     __syncthreads();   // the previous point's readers of xs / Aimg are done
     // ---- my tile, straight from the constants of the topology ----
 #pragma unroll
-    for (int m = 0; m < TL_MR; ++m)
+    for (int m = 0; m < TL_MR; ++m) {
+      // one local row's loads in flight at a time (all MR * MC at once would take 8 registers each on top of the tile)
+      asm volatile("" ::: "memory");
 #pragma unroll
       for (int c = 0; c < TL_MC; ++c) {
         const size_t o = (size_t)(m * TL_MC + c) * TL_THREADS + tid;
@@ -360,6 +382,7 @@ extern "C" __global__ void __launch_bounds__(TL_THREADS, TL_MINB) spicey_tile_ji
         A[m][c] = make_double2(c0.x, fma(w, c1.x, -c1.y * iw) + c0.y);
 #endif
       }
+    }
 #else
     if (tid == 0) *s_status = 0;
     __syncthreads();   // the previous point's readers of xs / Yv / Aimg are done

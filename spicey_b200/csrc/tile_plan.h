@@ -28,8 +28,8 @@ struct TileShape {
 inline size_t tile_smem_bytes(int n, int n_elem, int n_src, int tr, int tc, bool const_tables = false) {
   const int nc = n + 1, ld = n | 1;
   const int mr = (n + tr - 1) / tr, mc = (nc + tc - 1) / tc;
-  const size_t cplx = (size_t)nc * ld + (const_tables ? 0 : n_elem + std::max(1, n_src)) + 2 * (size_t)(mr * tr) + 2 * (size_t)(mc * tc) + n + (n + 1);
-  return 16 * cplx + 64 /* two winner records */ + 16 /* status */;
+  const size_t cplx = (size_t)nc * ld + (const_tables ? 0 : n_elem + std::max(1, n_src)) + 2 * (size_t)(mr * tr + 1) + 2 * (size_t)(mc * tc) + n + (n + 1);
+  return 16 * cplx + 32 /* two winner records */ + 16 /* status */;
 }
 
 inline long long tile_thread_cfma(int n, int tr, int tc) {
