@@ -63,7 +63,7 @@ struct DeviceCtx {
   int sm_count = 0;
   size_t smem_optin = 0;
   cudaStream_t compute = nullptr, copy = nullptr;
-  Buffer plan, scratch, in0, in1, in2, out_x[2], out_i[2], out_s[2], aux0, aux1;
+  Buffer plan, scratch, in0, in1, in2, out_x[2], out_i[2], out_s[2], aux0, aux1, tr_iters[2], tr_state[2];
   // sparse AC path: cached program (keyed by the element table), workspace, fallback list
   Buffer sp_blob, sp_work, sp_fb;
   SparseProgram sp;
@@ -1432,7 +1432,7 @@ void spicey_destroy(spicey_handle* h) {
     cudaDeviceSynchronize();
     Buffer* bufs[] = {&c.plan, &c.scratch, &c.in0, &c.in1, &c.in2, &c.out_x[0], &c.out_x[1], &c.out_i[0],
                       &c.out_i[1], &c.out_s[0], &c.out_s[1], &c.aux0, &c.aux1, &c.sp_blob, &c.sp_work, &c.sp_fb,
-                      &c.wp_blob, &c.wp_work, &c.bp_blob, &c.bp_work, &c.tl_blob};
+                      &c.wp_blob, &c.wp_work, &c.bp_blob, &c.bp_work, &c.tl_blob, &c.tr_iters[0], &c.tr_iters[1], &c.tr_state[0], &c.tr_state[1]};
     for (Buffer* b : bufs) b->release();
     for (auto& jv : c.sp_jit) if (jv.lib) cudaLibraryUnload(jv.lib);
     for (auto& jv : c.tr_jit) if (jv.lib) cudaLibraryUnload(jv.lib);
@@ -1716,6 +1716,7 @@ static int32_t tran_solve_impl(spicey_handle* h, const spicey_elem_table* table,
   int64_t launches = 0, h2d = 0, d2h = 0;
   int tier = 0;
   std::vector<std::pair<long long, long long>> shards(D);
+  std::vector<int> nchunks(D, 0);
   for (int d = 0; d < D; ++d) {
     DeviceCtx& ctx = h->devs[d];
     const long long lo = n_inst * d / D, hi = n_inst * (d + 1) / D, nl = hi - lo;
@@ -1751,48 +1752,77 @@ static int32_t tran_solve_impl(spicey_handle* h, const spicey_elem_table* table,
       h2d += b;
       a.state0 = (const double*)ctx.in2.p;
     }
-    if ((rc = ctx.out_x[0].ensure(sizeof(double) * S1 * hp.nn * nl))) return rc;
-    if (ielem && (rc = ctx.out_i[0].ensure(sizeof(double) * S1 * hp.n_elem * nl))) return rc;
-    if ((rc = ctx.out_s[0].ensure(sizeof(int) * nl))) return rc;
-    if (state_out && (rc = ctx.aux1.ensure(sizeof(double) * std::max(1, hp.n_state) * nl))) return rc;
-    if (iters && (rc = ctx.out_s[1].ensure(sizeof(int) * S1 * nl))) return rc;
-    a.inst0 = lo; a.n_local = nl;
-    a.v = (double*)ctx.out_x[0].p;
-    a.ielem = ielem ? (double*)ctx.out_i[0].p : nullptr;
-    a.state_out = state_out ? (double*)ctx.aux1.p : nullptr;
-    a.iters = iters ? (int*)ctx.out_s[1].p : nullptr;
-    a.status = (int*)ctx.out_s[0].p;
-    CUDA_TRY(cudaEventRecord(ctx.get_event(0), ctx.compute));
-    rc = launch_tran(ctx, hp, dp, a, waves, flags, ctx.compute, &tier, &launches);
-    if (rc) return rc;
-    CUDA_TRY(cudaEventRecord(ctx.get_event(1), ctx.compute));
-    // [rows][n_local] device slabs -> [rows][n_inst] host arrays at column offset lo
-    const size_t dp_ = sizeof(double) * n_inst, sp_ = sizeof(double) * nl;
-    CUDA_TRY(cudaMemcpy2DAsync((char*)v + sizeof(double) * lo, dp_, a.v, sp_, sp_, S1 * hp.nn,
-                               cudaMemcpyDeviceToHost, ctx.compute));
-    d2h += (int64_t)(sp_ * S1 * hp.nn);
-    if (ielem && hp.n_elem > 0) {
-      CUDA_TRY(cudaMemcpy2DAsync((char*)ielem + sizeof(double) * lo, dp_, a.ielem, sp_, sp_, S1 * hp.n_elem,
-                                 cudaMemcpyDeviceToHost, ctx.compute));
-      d2h += (int64_t)(sp_ * S1 * hp.n_elem);
+    // Pipeline over instance chunks (every instance is independent: simulateTRAN.ts:146-238 runs one circuit): the
+    // persistent kernel of chunk i + 1 runs while chunk i's waveforms travel as 2-D copies, and the device holds two
+    // chunks of results (<= ~1 GiB each), not the whole batch (cfg 5: 14.4 GB).
+    const size_t per_inst = sizeof(double) * (size_t)S1 * (hp.nn + (ielem ? hp.n_elem : 0)) + (iters ? sizeof(int) * (size_t)S1 : 0);
+    size_t chunk_bytes = (size_t)1 << 30;
+    if (const char* e = getenv("SPICEY_TRAN_CHUNK_BYTES")) chunk_bytes = (size_t)std::max(1ll, atoll(e));   // tests: force several chunks
+    long long csz = std::max<long long>(1, (long long)(chunk_bytes / std::max<size_t>(1, per_inst)));
+    if (!getenv("SPICEY_TRAN_CHUNK_BYTES")) csz = std::max<long long>(csz, std::min<long long>(4096, nl));   // ... but not so few instances that a launch is all latency
+    if (csz >= nl) csz = nl;
+    else csz = (csz + 31) / 32 * 32;
+    for (int b = 0; b < 2; ++b) {
+      if (b == 1 && csz >= nl) break;
+      if ((rc = ctx.out_x[b].ensure(sizeof(double) * S1 * hp.nn * csz))) return rc;
+      if (ielem && (rc = ctx.out_i[b].ensure(sizeof(double) * S1 * hp.n_elem * csz))) return rc;
+      if ((rc = ctx.out_s[b].ensure(sizeof(int) * csz))) return rc;
+      if (state_out && (rc = ctx.tr_state[b].ensure(sizeof(double) * std::max(1, hp.n_state) * csz))) return rc;
+      if (iters && (rc = ctx.tr_iters[b].ensure(sizeof(int) * S1 * csz))) return rc;
     }
-    if (state_out && hp.n_state > 0)
-      CUDA_TRY(cudaMemcpy2DAsync((char*)state_out + sizeof(double) * lo, dp_, a.state_out, sp_, sp_, hp.n_state,
-                                 cudaMemcpyDeviceToHost, ctx.compute));
-    if (iters)
-      CUDA_TRY(cudaMemcpy2DAsync((char*)iters + sizeof(int) * lo, sizeof(int) * n_inst, a.iters, sizeof(int) * nl,
-                                 sizeof(int) * nl, S1, cudaMemcpyDeviceToHost, ctx.compute));
-    CUDA_TRY(cudaMemcpyAsync(status + lo, a.status, sizeof(int) * nl, cudaMemcpyDeviceToHost, ctx.compute));
+    int ci = 0;
+    for (long long c0 = lo; c0 < hi; c0 += csz, ++ci) {
+      const long long n = std::min(csz, hi - c0);
+      const int b = ci & 1;
+      // events per chunk: [4*ci] kernel start, [4*ci+1] kernel end, [4*ci+2] copies done
+      cudaEvent_t ks = ctx.get_event(4 * ci), ke = ctx.get_event(4 * ci + 1), cd = ctx.get_event(4 * ci + 2);
+      if (ci >= 2) CUDA_TRY(cudaStreamWaitEvent(ctx.compute, ctx.get_event(4 * (ci - 2) + 2), 0));
+      a.inst0 = c0; a.n_local = n;
+      a.v = (double*)ctx.out_x[b].p;
+      a.ielem = ielem ? (double*)ctx.out_i[b].p : nullptr;
+      a.state_out = state_out ? (double*)ctx.tr_state[b].p : nullptr;
+      a.iters = iters ? (int*)ctx.tr_iters[b].p : nullptr;
+      a.status = (int*)ctx.out_s[b].p;
+      CUDA_TRY(cudaEventRecord(ks, ctx.compute));
+      rc = launch_tran(ctx, hp, dp, a, waves, flags, ctx.compute, &tier, &launches);
+      if (rc) return rc;
+      CUDA_TRY(cudaEventRecord(ke, ctx.compute));
+      CUDA_TRY(cudaStreamWaitEvent(ctx.copy, ke, 0));
+      // [rows][n] device slabs -> [rows][n_inst] host arrays at column offset c0
+      const size_t dp_ = sizeof(double) * n_inst, sp_ = sizeof(double) * n;
+      CUDA_TRY(cudaMemcpy2DAsync((char*)v + sizeof(double) * c0, dp_, a.v, sp_, sp_, S1 * hp.nn,
+                                 cudaMemcpyDeviceToHost, ctx.copy));
+      d2h += (int64_t)(sp_ * S1 * hp.nn);
+      if (ielem && hp.n_elem > 0) {
+        CUDA_TRY(cudaMemcpy2DAsync((char*)ielem + sizeof(double) * c0, dp_, a.ielem, sp_, sp_, S1 * hp.n_elem,
+                                   cudaMemcpyDeviceToHost, ctx.copy));
+        d2h += (int64_t)(sp_ * S1 * hp.n_elem);
+      }
+      if (state_out && hp.n_state > 0)
+        CUDA_TRY(cudaMemcpy2DAsync((char*)state_out + sizeof(double) * c0, dp_, a.state_out, sp_, sp_, hp.n_state,
+                                   cudaMemcpyDeviceToHost, ctx.copy));
+      if (iters)
+        CUDA_TRY(cudaMemcpy2DAsync((char*)iters + sizeof(int) * c0, sizeof(int) * n_inst, a.iters, sizeof(int) * n,
+                                   sizeof(int) * n, S1, cudaMemcpyDeviceToHost, ctx.copy));
+      CUDA_TRY(cudaMemcpyAsync(status + c0, a.status, sizeof(int) * n, cudaMemcpyDeviceToHost, ctx.copy));
+      CUDA_TRY(cudaEventRecord(cd, ctx.copy));
+    }
+    nchunks[d] = ci;
   }
   double kmax = 0;
   for (int d = 0; d < D; ++d) {
     DeviceCtx& ctx = h->devs[d];
     if (shards[d].second <= shards[d].first) continue;
     CUDA_TRY(cudaSetDevice(ctx.dev));
+    CUDA_TRY(cudaStreamSynchronize(ctx.copy));
     CUDA_TRY(cudaStreamSynchronize(ctx.compute));
-    float ms = 0;
-    cudaEventElapsedTime(&ms, ctx.get_event(0), ctx.get_event(1));
-    kmax = std::max(kmax, (double)ms);
+    double k = 0;
+    for (int ci = 0; ci < nchunks[d]; ++ci) {
+      float ms = 0;
+      cudaEventElapsedTime(&ms, ctx.get_event(4 * ci), ctx.get_event(4 * ci + 1));
+      k += ms;
+    }
+    kmax = std::max(kmax, k);
   }
   h->stats.kernel_ms = kmax;
   h->stats.total_ms = now_ms() - t0;

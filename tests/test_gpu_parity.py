@@ -1235,3 +1235,33 @@ def test_ac_tile_tier_statuses_sweeps_and_current_sources(eng):
         assert rel_err(got["x"][0][:, j], np.array([complex(z) for z in ref["nodeVoltages"][nm]])) <= AC_TOL, nm
     for j, nm in enumerate(got["element_names"]):
         assert rel_err(got["ielem"][0][:, j], np.array([complex(z) for z in ref["elementCurrents"][nm]])) <= AC_TOL, nm
+
+
+def test_tran_host_call_pipelines_instance_chunks(monkeypatch):
+    """The host-buffer transient call splits a batch into instance chunks (two result buffers on the device, 2-D copies of
+    chunk i overlapping the kernel of chunk i + 1): forced to 9 chunks of 32 instances, ragged last chunk, the results
+    (waveforms, element currents, final state, iteration counts, statuses) are the single-launch ones bit for bit."""
+    import spicey_b200 as sp
+    n = 270
+    ov = {k: v[:n] for k, v in w.rectifier_overrides(100000).items()}
+    ck = parse_netlist(w.RECTIFIER)
+    e1 = native.Engine()
+    try:
+        one = sp.simulate_tran_batch(ck, n_inst=n, overrides=ov, want_iters=True, engine=e1)
+        l1 = e1.stats()["kernel_launches"]
+    finally:
+        e1.close()
+    monkeypatch.setenv("SPICEY_TRAN_CHUNK_BYTES", str(32 * 3001 * 8 * (2 + 4) + 32 * 3001 * 4))
+    e2 = native.Engine()
+    try:
+        many = sp.simulate_tran_batch(ck, n_inst=n, overrides=ov, want_iters=True, engine=e2)
+        l2 = e2.stats()["kernel_launches"]
+    finally:
+        e2.close()
+    assert l1 == 1 and l2 == 9, (l1, l2)
+    for key in ("v", "ielem", "iters", "status", "state"):
+        if key in one and one[key] is not None:
+            assert np.array_equal(one[key], many[key]), key
+    vr, ir, _, st, _ = co.tran_solve(ck, one["dt"], one["steps"], n_inst=n, overrides=ov, nthreads=8)
+    assert st.max() == 0 and many["status"].max() == 0
+    assert np.max(np.abs(many["v"] - np.transpose(vr, (1, 2, 0)))) <= TRAN_TOL * np.max(np.abs(vr))
