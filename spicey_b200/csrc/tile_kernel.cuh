@@ -175,28 +175,26 @@ __device__ __forceinline__ void tl_search(const TileCtx& t, int k, const tcplx (
   if (t.lane == 0) tl_sts1(&t.Wn[par].p, p);
 }
 
-// The update a_ij -= f_i * u_kj (:47-52) of step k on the live part of the tile.  C1 >= 0: this warp owns column k + 1,
-// which is local column C1 of its thread column: that column is updated first and the search of step k + 1 runs on it
-// while the other columns follow.
-template <int KR, int KC, int C1>
-__device__ __forceinline__ void tl_update(const TileCtx& t, int k, int p, tcplx (&A)[TL_MR][TL_MC], const tcplx (&F)[TL_MR]) {
+// The update a_ij -= f_i * u_kj (:47-52) of step k on the live part of the tile.  `own`: this warp owns column k + 1; it
+// first brings that column up to date in temporaries and runs the search of step k + 1 on them (the update below then
+// recomputes the same values in place: one code path for every warp, so the tile's registers need no reconciling
+// moves where paths would merge).
+template <int KR, int KC>
+__device__ __forceinline__ void tl_update(const TileCtx& t, int k, int p, bool own, tcplx (&A)[TL_MR][TL_MC], const tcplx (&F)[TL_MR]) {
   const int trk = k - KR * TL_TR;
   const bool patch = p != k && t.tr == trk;      // position k takes the pivot row (F of row k is 0)
-  if (C1 >= 0) {
-    constexpr int CC = C1 >= 0 ? C1 : 0;
-    const tcplx pv = t.Pb[CC * TL_TC + t.tc];
-    if (patch) A[KR][CC] = pv;
+  if (own) {
+    constexpr int KC1 = KC + 1 < TL_MC ? KC + 1 : KC;
+    const bool nxt = k + 1 >= (KC + 1) * TL_TC;           // column k + 1 opens local column KC + 1
+    const int c1 = nxt ? KC + 1 : KC;
+    const tcplx pv1 = t.Pb[c1 * TL_TC + t.tc];
     tcplx col1[TL_MR];
 #pragma unroll
-    for (int m = KR; m < TL_MR; ++m) {
-      A[m][CC] = tl_submul(A[m][CC], F[m], pv);
-      col1[m] = A[m][CC];
-    }
-    tl_search<KR>(t, k + 1, col1, t.act && t.tc == k + 1 - CC * TL_TC);
+    for (int m = KR; m < TL_MR; ++m) col1[m] = tl_submul(nxt ? A[m][KC1] : A[m][KC], F[m], pv1);
+    tl_search<KR>(t, k + 1, col1, t.act && t.tc == k + 1 - c1 * TL_TC);
   }
 #pragma unroll
   for (int c = KC; c < TL_MC; ++c) {
-    if (c == C1) continue;
     const tcplx pv = t.Pb[c * TL_TC + t.tc];
     if (patch) A[KR][c] = pv;
 #pragma unroll
@@ -286,12 +284,7 @@ __device__ __forceinline__ void tl_segment(const TileCtx& t, tcplx (&A)[TL_MR][T
     if (p != k) tl_row_in<KR, KC, KR>(A, mp, tr == trp, Kb, tc);
     // column k + 1 belongs to thread column (k + 1) mod TC: (k + 1) - KC TC, or 0 when it opens local column KC + 1
     const int tck1 = (k + 1 >= (KC + 1) * TL_TC) ? 0 : k + 1 - KC * TL_TC;
-    if (k + 1 < TL_N && warp == tck1 / TL_TPW) {
-      if (k + 1 >= (KC + 1) * TL_TC) tl_update<KR, KC, (KC + 1 < TL_MC ? KC + 1 : KC)>(t, k, p, A, F);
-      else tl_update<KR, KC, KC>(t, k, p, A, F);
-    } else {
-      tl_update<KR, KC, -1>(t, k, p, A, F);
-    }
+    tl_update<KR, KC>(t, k, p, k + 1 < TL_N && warp == tck1 / TL_TPW, A, F);
   }
 }
 
