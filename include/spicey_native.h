@@ -143,7 +143,8 @@ enum {
   ,SPICEY_TIER_TILE = 9       /* dense LU with partial pivoting (lib/math/solveComplex.ts:15-53), the augmented
                                 matrix of a system resident in REGISTERS as 2-D cyclic tiles of one CTA (one warp
                                 for small Nvar), compiled per (Nvar, tile shape): dense circuits and
-                                SPICEY_FLAG_DENSE batches of >= 4096 points (tile_kernel.cuh) */
+                                SPICEY_FLAG_DENSE batches of >= 4096 points (tile_kernel.cuh); plain sweeps of
+                                Nvar <= 32: one WARP per system, a lane's row in registers (warp_lu_kernel.cuh) */
 };
 
 typedef struct spicey_handle spicey_handle;
@@ -325,6 +326,11 @@ int64_t spicey_debug_band_source(int32_t L, int32_t RPL, int32_t NB, uint32_t ab
  * memory per CTA.  Returns the size needed, or -1 when no tile shape fits an SM (Nvar too large). */
 int64_t spicey_debug_tile_source(int32_t nvar, int32_t n_elem, int32_t n_src, int32_t tr, int32_t tc, int32_t with_ielem,
                                  int32_t* shape_out, char* buf, int64_t cap);
+
+/* Tooling (no device needed): the CUDA source of the one-warp-per-system dense LU (tier 9, Nvar <= 32, plain sweeps).
+ * variant: bit 0 element currents, bit 2 (alpha, beta)-only tables.  shape_out[3], optional: warps per CTA, CTAs per
+ * SM, shared memory per CTA.  Returns the size needed, or -1 when Nvar > 32. */
+int64_t spicey_debug_warp_lu_source(int32_t nvar, int32_t variant, int32_t* shape_out, char* buf, int64_t cap);
 
 /* Measures this GPU's FP64 FMA peak with a register-only DFMA loop (GFLOP/s), the
  * denominator the FP64-bound roofline is reported against. */

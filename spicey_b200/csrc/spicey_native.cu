@@ -22,6 +22,7 @@
 #include "ac_warp.cuh"
 #include "band_kernel_embed.h"
 #include "tile_kernel_embed.h"
+#include "warp_lu_kernel_embed.h"
 #include "band_plan.h"
 #include "tile_plan.h"
 #include "host_plan.h"
@@ -131,6 +132,7 @@ struct DeviceCtx {
   uint64_t tl_key = 0;        // plan key the entry lists were uploaded for (0 = none)
   struct TileDev {
     const void *ent_rc = nullptr, *ent_ptr = nullptr, *contrib = nullptr, *ctab = nullptr, *el_rec = nullptr, *ind_L = nullptr;
+    const void* wtab = nullptr;   // the constants in the one-warp-per-system layout [column][lane = row] (Nvar <= 32)
     int n_ent = 0, n_ind = 0;
     bool has_const = false, rc_only = false;
   } tl_dev;
@@ -140,7 +142,8 @@ struct DeviceCtx {
     uint64_t key = 0;
     bool failed = false;
     int n = 0, tr = 0, tc = 0, warps = 0, minb = 0;
-  } tile_jit[8];              // by variant: bit 0 element currents, bit 1 constant tables, bit 2 (alpha, beta)-only tables
+  } tile_jit[16];             // by variant: bit 0 element currents, bit 1 constant tables, bit 2 (alpha, beta)-only tables,
+                              // bit 3 the one-warp-per-system kernel (Nvar <= 32)
   std::string tl_note;
   double sp_pilot_f = 0;      // frequency of the pilot point the cached programs were built from
   uint64_t plan_up_key = 0;   // plan currently resident in `plan` (its device pointers are in plan_dp)
@@ -965,7 +968,7 @@ int prepare_tile(DeviceCtx& ctx, const HostPlan& hp, const TileShape& sh, cudaSt
   for (int v : hp.var_of_slot) swept = swept || v >= 0;
   SparseProgram sc;
   ctx.tl_dev.has_const = !swept && entry_constants(hp, sc);
-  size_t o_ct = 0, o_er = 0, o_il = 0;
+  size_t o_ct = 0, o_er = 0, o_il = 0, o_wt = 0;
   if (ctx.tl_dev.has_const) {
     bool rc_only = true;
     for (int en = 0; en < n_ent; ++en) rc_only = rc_only && sc.ent_gamma[en] == 0.0 && sc.ent_jim[en] == 0.0;
@@ -990,6 +993,21 @@ int prepare_tile(DeviceCtx& ctx, const HostPlan& hp, const TileShape& sh, cudaSt
           }
         }
     }
+    std::vector<double2> wtab;
+    if (n <= 32) {   // warp_lu_kernel.cuh: lane = row, [column][lane]
+      wtab.assign((size_t)(n + 1) * 32 * (rc_only ? 1 : 2), make_double2(0.0, 0.0));
+      for (int en = 0; en < n_ent; ++en) {
+        const int i = ent_rc[en] & 0xffff, j = ent_rc[en] >> 16;
+        const size_t o = (size_t)j * 32 + i;
+        if (rc_only) wtab[o] = make_double2(sc.ent_alpha[en] + sc.ent_jre[en], sc.ent_beta[en]);
+        else {
+          wtab[2 * o] = make_double2(sc.ent_alpha[en] + sc.ent_jre[en], sc.ent_jim[en]);
+          wtab[2 * o + 1] = make_double2(sc.ent_beta[en], sc.ent_gamma[en]);
+        }
+      }
+    } else {
+      wtab.push_back(make_double2(0.0, 0.0));
+    }
     std::vector<double4> el_rec(std::max(1, hp.n_ac_elem));
     for (int e = 0; e < hp.n_ac_elem; ++e) {
       const int n1 = hp.ends[e].x, n2 = hp.ends[e].y;
@@ -1008,6 +1026,7 @@ int prepare_tile(DeviceCtx& ctx, const HostPlan& hp, const TileShape& sh, cudaSt
     ctx.tl_dev.n_ind = (int)sc.ind_L.size();
     if (sc.ind_L.empty()) sc.ind_L.push_back(0.0);
     o_ct = push_blob(blob, tab); o_er = push_blob(blob, el_rec); o_il = push_blob(blob, sc.ind_L);
+    o_wt = push_blob(blob, wtab);
   }
   int rc = ctx.tl_blob.ensure(blob.size() + 16);
   if (rc) return rc;
@@ -1015,9 +1034,40 @@ int prepare_tile(DeviceCtx& ctx, const HostPlan& hp, const TileShape& sh, cudaSt
   CUDA_TRY(cudaStreamSynchronize(stream));
   unsigned char* b = (unsigned char*)ctx.tl_blob.p;
   ctx.tl_dev.ent_rc = b + o_rc; ctx.tl_dev.ent_ptr = b + o_ep; ctx.tl_dev.contrib = b + o_co; ctx.tl_dev.n_ent = n_ent;
-  ctx.tl_dev.ctab = b + o_ct; ctx.tl_dev.el_rec = b + o_er; ctx.tl_dev.ind_L = b + o_il;
+  ctx.tl_dev.ctab = b + o_ct; ctx.tl_dev.el_rec = b + o_er; ctx.tl_dev.ind_L = b + o_il; ctx.tl_dev.wtab = b + o_wt;
   ctx.tl_key = key;
   return SPICEY_SUCCESS;
+}
+
+// One warp per system (warp_lu_kernel.cuh, Nvar <= 32, plain frequency sweeps): 4 warps per CTA, as many CTAs per SM as
+// the row in registers (4 per entry + ~36) allows.
+constexpr int kWarpLuWarps = 4;
+int warp_lu_minb(int n) {
+  const int regs = (4 * (n + 1) + 36 + 7) / 8 * 8;
+  return std::max(1, std::min(8, 65536 / (32 * kWarpLuWarps * regs)));
+}
+size_t warp_lu_smem_bytes(int n) { return sizeof(double2) * (size_t)kWarpLuWarps * (2 * (n + 3) + n + 1); }
+std::string warp_lu_source(int n, int variant) {
+  char head[256];
+  snprintf(head, sizeof head, "#define WL_N %d\n#define WL_WARPS %d\n#define WL_MINB %d\n#define WL_IELEM %d\n#define WL_RC %d\n",
+           n, kWarpLuWarps, warp_lu_minb(n), variant & 1, (variant >> 2) & 1);
+  return std::string(head) + kWarpLuKernelSource;
+}
+
+DeviceCtx::TileJit* ensure_warp_lu_jit(DeviceCtx& ctx, int n, int variant) {
+  DeviceCtx::TileJit& jv = ctx.tile_jit[variant & 15];
+  const int shape[4] = {n, kWarpLuWarps, warp_lu_minb(n), variant};
+  uint64_t key = fnv1a(1469598103934665603ull, shape, sizeof shape);
+  if (!key) key = 1;
+  if (jv.key == key) return jv.failed ? nullptr : &jv;
+  jv.key = key;
+  jv.failed = true;
+  if (jv.lib) { cudaLibraryUnload(jv.lib); jv.lib = nullptr; jv.kernel = nullptr; }
+  if (!load_jit_kernel(warp_lu_source(n, variant), "spicey_warp_lu_jit", &jv.lib, &jv.kernel, ctx.tl_note)) return nullptr;
+  jv.n = n; jv.tr = 32; jv.tc = 1; jv.warps = kWarpLuWarps; jv.minb = warp_lu_minb(n);
+  jv.failed = false;
+  ctx.tl_note = "ok";
+  return &jv;
 }
 
 DeviceCtx::TileJit* ensure_tile_jit(DeviceCtx& ctx, const TileShape& sh, int variant) {
@@ -1047,12 +1097,17 @@ int launch_ac_tile(DeviceCtx& ctx, const HostPlan& hp, const DevPlan& dp, const 
   int rc = prepare_tile(ctx, hp, sh, stream);
   if (rc) return rc;
   const bool cst = ctx.tl_dev.has_const && dp.n_inst == 1 && !(flags & SPICEY_FLAG_TILE_GENERIC);
-  const int variant = (args.ielem ? 1 : 0) | (cst ? 2 : 0) | (cst && ctx.tl_dev.rc_only ? 4 : 0);
-  DeviceCtx::TileJit* jv = ensure_tile_jit(ctx, sh, variant);
+  // Nvar <= 32 on a plain sweep: one warp per system, the row of a lane in registers (unless a thread grid is forced)
+  bool warp_lu = cst && hp.nvar <= 32 && !getenv("SPICEY_TILE_SHAPE");
+  if (const char* e = getenv("SPICEY_WARP_LU")) warp_lu = warp_lu && atoi(e) != 0;   // experiments
+  const int variant = (args.ielem ? 1 : 0) | (cst ? 2 : 0) | (cst && ctx.tl_dev.rc_only ? 4 : 0) | (warp_lu ? 8 : 0);
+  DeviceCtx::TileJit* jv = warp_lu ? ensure_warp_lu_jit(ctx, hp.nvar, variant) : ensure_tile_jit(ctx, sh, variant);
   if (!jv) return SPICEY_SUCCESS;
-  const size_t smem = tile_smem_bytes(hp.nvar, cst ? 0 : hp.n_elem, cst ? 0 : hp.nV + hp.nI, jv->tr, jv->tc, cst);
+  const size_t smem = warp_lu ? warp_lu_smem_bytes(hp.nvar)
+                              : tile_smem_bytes(hp.nvar, cst ? 0 : hp.n_elem, cst ? 0 : hp.nV + hp.nI, jv->tr, jv->tc, cst);
   CUDA_TRY(cudaFuncSetAttribute((const void*)jv->kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  unsigned grid = (unsigned)std::min<long long>(args.p_count, (long long)ctx.sm_count * jv->minb);
+  unsigned grid = (unsigned)std::min<long long>(warp_lu ? (args.p_count + kWarpLuWarps - 1) / kWarpLuWarps : args.p_count,
+                                                (long long)ctx.sm_count * jv->minb);
   if (const char* e = getenv("SPICEY_TILE_GRID")) grid = std::min<unsigned>(grid, (unsigned)std::max(1, atoi(e)));   // experiments
   TileArgs a;
   memset(&a, 0, sizeof a);
@@ -1065,7 +1120,7 @@ int launch_ac_tile(DeviceCtx& ctx, const HostPlan& hp, const DevPlan& dp, const 
   a.off_v = hp.off[ELEM_V]; a.off_v_end = hp.off[ELEM_V + 1]; a.off_i = hp.off[ELEM_I];
   const bool guards = cst && ctx.tl_dev.n_ind > 0;   // points that trip an inductor guard go to the one-thread-per-row kernel
   if (cst) {
-    a.ctab = (const double2*)ctx.tl_dev.ctab; a.el_rec = (const double4*)ctx.tl_dev.el_rec; a.ind_L = (const double*)ctx.tl_dev.ind_L;
+    a.ctab = (const double2*)(warp_lu ? ctx.tl_dev.wtab : ctx.tl_dev.ctab); a.el_rec = (const double4*)ctx.tl_dev.el_rec; a.ind_L = (const double*)ctx.tl_dev.ind_L;
     a.n_ind = ctx.tl_dev.n_ind;
     if (guards) {
       if ((rc = ctx.sp_fb.ensure(sizeof(long long) * args.p_count + 64))) return rc;
@@ -1986,6 +2041,18 @@ int64_t spicey_debug_tile_source(int32_t nvar, int32_t n_elem, int32_t n_src, in
     memcpy(shape_out, v, sizeof v);
   }
   const std::string src = tile_source(sh, with_ielem);
+  if (buf && cap > 0) {
+    const size_t n = std::min<size_t>(src.size(), (size_t)cap - 1);
+    memcpy(buf, src.data(), n);
+    buf[n] = 0;
+  }
+  return (int64_t)src.size() + 1;
+}
+
+int64_t spicey_debug_warp_lu_source(int32_t nvar, int32_t variant, int32_t* shape_out, char* buf, int64_t cap) {
+  if (nvar < 1 || nvar > 32) return -1;
+  if (shape_out) { shape_out[0] = kWarpLuWarps; shape_out[1] = warp_lu_minb(nvar); shape_out[2] = (int32_t)warp_lu_smem_bytes(nvar); }
+  const std::string src = warp_lu_source(nvar, variant);
   if (buf && cap > 0) {
     const size_t n = std::min<size_t>(src.size(), (size_t)cap - 1);
     memcpy(buf, src.data(), n);

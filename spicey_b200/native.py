@@ -31,6 +31,7 @@ EXPORTS = [
     "spicey_debug_sparse_source", "spicey_series_ld", "spicey_debug_tran_source", "spicey_debug_warp_stats",
     "spicey_tran_solve_waves", "spicey_tran_solve_waves_device", "spicey_debug_tran_source_waves",
     "spicey_debug_band_stats", "spicey_debug_band_source", "spicey_debug_tile_source",
+    "spicey_debug_warp_lu_source",
 ]
 WAVE_DC, WAVE_TABLE, WAVE_PULSE, WAVE_PWL = 0, 1, 2, 3
 
@@ -128,6 +129,8 @@ def load_library(path: Optional[str] = None):
     lib.spicey_debug_band_source.restype = C.c_int64
     lib.spicey_debug_band_source.argtypes = [C.c_int32, C.c_int32, C.c_int32, C.c_uint32, C.c_int32, C.c_int32, C.c_int32,
                                              C.c_char_p, C.c_int64]
+    lib.spicey_debug_warp_lu_source.restype = C.c_int64
+    lib.spicey_debug_warp_lu_source.argtypes = [C.c_int32, C.c_int32, _ip, C.c_char_p, C.c_int64]
     lib.spicey_debug_tile_source.restype = C.c_int64
     lib.spicey_debug_tile_source.argtypes = [C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _ip,
                                              C.c_char_p, C.c_int64]
@@ -185,6 +188,19 @@ def tile_kernel_source(nvar: int, n_elem: int = 0, n_src: int = 1, tr: int = 0, 
     lib.spicey_debug_tile_source(*args, buf, need)
     keys = ("tr", "tc", "mr", "mc", "warps", "ctas_per_sm", "regs", "smem_bytes")
     return buf.value.decode(), dict(zip(keys, list(shp)))
+
+
+def warp_lu_kernel_source(nvar: int, with_ielem=True, rc_only=False):
+    """(CUDA source, shape dict) of the one-warp-per-system dense LU (tier 9, Nvar <= 32); None above 32.  Host-only tooling."""
+    lib = load_library()
+    shp = (C.c_int32 * 3)()
+    args = (nvar, (1 if with_ielem else 0) | 2 | (4 if rc_only else 0), shp)
+    need = lib.spicey_debug_warp_lu_source(*args, None, 0)
+    if need < 0:
+        return None
+    buf = C.create_string_buffer(need)
+    lib.spicey_debug_warp_lu_source(*args, buf, need)
+    return buf.value.decode(), dict(zip(("warps", "ctas_per_sm", "smem_bytes"), list(shp)))
 
 
 def tran_kernel_source(table: "ElemTable", sweep: Optional["Sweep"] = None, with_ielem=True,

@@ -52,3 +52,23 @@ def test_tile_kernel_compiles_within_its_register_budget(tmp_path, nvar, tr, tc,
     assert max(spills) <= 512, res.stderr
     threads = sh["warps"] * 32
     assert int(m.group(1)) * threads * sh["ctas_per_sm"] <= 65536, (m.group(1), sh)
+
+
+@pytest.mark.parametrize("nvar,rc_only", [(32, True), (17, False), (3, True)])
+def test_warp_lu_kernel_compiles_within_its_register_budget(tmp_path, nvar, rc_only):
+    """The one-warp-per-system dense LU (Nvar <= 32): a lane's row in registers at the occupancy the host asks for."""
+    nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    if not os.path.exists(nvcc):
+        pytest.skip("nvcc not found")
+    assert native.warp_lu_kernel_source(33) is None
+    src, sh = native.warp_lu_kernel_source(nvar, rc_only=rc_only)
+    assert "#define WL_N %d\n" % nvar in src and "spicey_warp_lu_jit" in src and "__reduce_max_sync" in src
+    cu = tmp_path / "wlu.cu"
+    cu.write_text(src)
+    res = subprocess.run([nvcc, "-cubin", "-gencode", "arch=compute_100a,code=sm_100a", "-std=c++17", "-Xptxas", "-v",
+                          "-o", str(tmp_path / "wlu.cubin"), str(cu)], capture_output=True, text=True)
+    assert res.returncode == 0, res.stderr[-2000:]
+    m = re.search(r"Used (\d+) registers", res.stderr)
+    spills = [int(v) for v in re.findall(r"(\d+) bytes spill stores", res.stderr)]
+    assert m and max(spills) <= 128, res.stderr
+    assert int(m.group(1)) * sh["warps"] * 32 * sh["ctas_per_sm"] <= 65536, (m.group(1), sh)
