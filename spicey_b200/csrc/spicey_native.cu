@@ -1043,20 +1043,25 @@ int prepare_tile(DeviceCtx& ctx, const HostPlan& hp, const TileShape& sh, cudaSt
 // the row in registers (4 per entry + ~36) allows.
 constexpr int kWarpLuWarps = 4;
 int warp_lu_minb(int n) {
+  if (const char* e = getenv("SPICEY_WARP_LU_MINB")) return std::max(1, std::min(16, atoi(e)));   // experiments
   const int regs = (4 * (n + 1) + 36 + 7) / 8 * 8;
   return std::max(1, std::min(8, 65536 / (32 * kWarpLuWarps * regs)));
+}
+int warp_lu_sync() {
+  if (const char* e = getenv("SPICEY_WARP_LU_SYNC")) return std::max(0, std::min(32, atoi(e)));   // experiments
+  return 4;
 }
 size_t warp_lu_smem_bytes(int n) { return sizeof(double2) * (size_t)kWarpLuWarps * (2 * (n + 3) + n + 1); }
 std::string warp_lu_source(int n, int variant) {
   char head[256];
-  snprintf(head, sizeof head, "#define WL_N %d\n#define WL_WARPS %d\n#define WL_MINB %d\n#define WL_IELEM %d\n#define WL_RC %d\n",
-           n, kWarpLuWarps, warp_lu_minb(n), variant & 1, (variant >> 2) & 1);
+  snprintf(head, sizeof head, "#define WL_N %d\n#define WL_WARPS %d\n#define WL_MINB %d\n#define WL_IELEM %d\n#define WL_RC %d\n#define WL_SYNC %d\n",
+           n, kWarpLuWarps, warp_lu_minb(n), variant & 1, (variant >> 2) & 1, warp_lu_sync());
   return std::string(head) + kWarpLuKernelSource;
 }
 
 DeviceCtx::TileJit* ensure_warp_lu_jit(DeviceCtx& ctx, int n, int variant) {
   DeviceCtx::TileJit& jv = ctx.tile_jit[variant & 15];
-  const int shape[4] = {n, kWarpLuWarps, warp_lu_minb(n), variant};
+  const int shape[5] = {n, kWarpLuWarps, warp_lu_minb(n), variant, warp_lu_sync()};
   uint64_t key = fnv1a(1469598103934665603ull, shape, sizeof shape);
   if (!key) key = 1;
   if (jv.key == key) return jv.failed ? nullptr : &jv;
