@@ -619,7 +619,10 @@ struct BandArgs {   // must match band_kernel.cuh
   int o_init, o_initb, o_brd0, o_bb0, o_step;
 };
 
-constexpr int kBandMinBandwidth = 1;   // every banded + bordered circuit the thread-per-system compiled tier refuses
+// Half-bandwidth from which the banded tier beats the interpreted thread-per-system program (measured, tools/tier_sweep.py,
+// 200,000 points: mesh4 (W 4) 567 against 440 M solves/s, mesh6 138 / 97, mesh8 87 / 25, mesh16 11.9 / 1.45; but mesh3 (W 3)
+// 735 / 1,124 and the 400-node ladder (W 1) 14 / 38: a step of the band kernel costs ~150 instructions whatever the width)
+constexpr int kBandMinBandwidth = 4;
 
 void band_input(const HostPlan& hp, const SparseProgram& sp, double pilot_f, BandInput& in) {
   in.n = hp.nvar; in.nn = hp.nn; in.nV = hp.nV;
@@ -638,9 +641,10 @@ void band_force_shape(int& L, int& RPL) {   // experiments: SPICEY_BAND_SHAPE=L,
 }
 
 // Builds (once per topology and handle) the band plan of the cached sparse program's circuit and uploads its tables.
-int prepare_band(DeviceCtx& ctx, const HostPlan& hp, cudaStream_t stream) {
-  if (ctx.bp_key == ctx.sp_key) return SPICEY_SUCCESS;
-  ctx.bp_key = ctx.sp_key;
+int prepare_band(DeviceCtx& ctx, const HostPlan& hp, cudaStream_t stream, bool force) {
+  const uint64_t want = ctx.sp_key ^ (force ? 0x5bd1e995ull : 0ull);
+  if (ctx.bp_key == want) return SPICEY_SUCCESS;
+  ctx.bp_key = want;
   ctx.bp_valid = false;
   BandInput in;
   band_input(hp, ctx.sp, ctx.sp_pilot_f, in);
@@ -648,7 +652,7 @@ int prepare_band(DeviceCtx& ctx, const HostPlan& hp, cudaStream_t stream) {
   band_force_shape(fl, fr);
   build_band_plan(in, ctx.bp, fl, fr);
   BandPlan& bp = ctx.bp;
-  if (!bp.ok || bp.bandwidth < kBandMinBandwidth) return SPICEY_SUCCESS;
+  if (!bp.ok || (bp.bandwidth < kBandMinBandwidth && !force)) return SPICEY_SUCCESS;
   // element records of the unpack phase: current = Y (x[i1] - x[i2]) in elimination-order indices, index n = the
   // zero slot (ground; bp.n counts the padding rows of the band); a V element's current is its branch unknown:
   // (branch, zero slot, Y = 1)
@@ -818,7 +822,7 @@ int launch_ac_sparse(DeviceCtx& ctx, const HostPlan& hp, const DevPlan& dp, cons
   // lanes per system, register-blocked (band_plan.h / band_kernel.cuh).  Compiled once per band shape and machine.
   if (!ctx.sp_eager && !(flags & (SPICEY_FLAG_NO_BAND | SPICEY_FLAG_NO_JIT)) && args.series_ld < (1ll << 31) &&
       ((flags & SPICEY_FLAG_BAND) || args.p_count >= kJitMinPoints || (flags & SPICEY_FLAG_JIT))) {
-    rc = prepare_band(ctx, hp, stream);
+    rc = prepare_band(ctx, hp, stream, (flags & SPICEY_FLAG_BAND) != 0);
     if (rc) return rc;
     if (ctx.bp_valid) {
       if (DeviceCtx::BandJit* bj = ensure_band_jit(ctx, args.ielem != nullptr)) {
