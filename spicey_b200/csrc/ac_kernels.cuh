@@ -25,7 +25,7 @@ struct AcArgs {
   double2* scratch;     // global-scratch tier: gridDim.x * nvar*(nvar+1)
   const long long* plist;  // optional: launch-local point indices to solve (fallback of the sparse path)
   const int* pcount;       // optional: number of entries of plist (device-resident)
-  unsigned long long* fb_total;  // optional: running total of fallback solves (statistics)
+  unsigned long long* fb_total;  // optional: [0] running total of this call's fallback solves (statistics), [1] since the program was built
   long long series_ld;     // 0: x[q][var], ielem[q][e] (point-major); else x[var][series_ld], ielem[e][series_ld]
 };
 
@@ -110,7 +110,10 @@ __global__ void ac_cta_kernel(DevPlan P, AcArgs a) {
   const GatherPlan& G = P.ac;
 
   const long long work = a.plist ? (long long)*a.pcount : a.p_count;
-  if (a.fb_total && blockIdx.x == 0 && t == 0 && work > 0) atomicAdd(a.fb_total, (unsigned long long)work);
+  if (a.fb_total && blockIdx.x == 0 && t == 0 && work > 0) {   // [0] this call's fallbacks, [1] the program's lifetime total
+    atomicAdd(a.fb_total, (unsigned long long)work);
+    atomicAdd(a.fb_total + 1, (unsigned long long)work);
+  }
   for (long long qi = blockIdx.x; qi < work; qi += gridDim.x) {
     const long long q = a.plist ? a.plist[qi] : qi;
     const long long p = a.p_begin + q;

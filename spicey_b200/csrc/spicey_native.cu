@@ -67,6 +67,10 @@ struct DeviceCtx {
   Buffer plan, scratch, in0, in1, in2, out_x[2], out_i[2], out_s[2], aux0, aux1, tr_iters[2], tr_state[2];
   // sparse AC path: cached program (keyed by the element table), workspace, fallback list
   Buffer sp_blob, sp_work, sp_fb;
+  Buffer sp_cnt;              // two counters: [0] fallback solves of the current call, [1] since the cached program was built
+  Buffer tl_fb;               // second-level fallback list (points of a fallback list that trip an inductor guard in the tile tier)
+  long long sp_launched = 0;  // points launched through the cached program since it was built
+  int sp_adapt = 0;           // 0 undecided, 1 the pilot's pivot order holds (program tiers), 2 it does not (dense tiers)
   SparseProgram sp;
   SparseArgs sp_args;
   uint64_t sp_key = 0;
@@ -223,6 +227,19 @@ int upload_plan(DeviceCtx& ctx, const HostPlan& hp, cudaStream_t stream, DevPlan
 
 int round32(int n) { return std::max(32, (n + 31) / 32 * 32); }
 
+// The fallback counters of a device ([0] current call, [1] since the cached sparse program was built): allocated once,
+// [0] cleared at the start of every call.
+int reset_call_counters(DeviceCtx& ctx, cudaStream_t stream) {
+  if (!ctx.sp_cnt.p) {
+    int rc = ctx.sp_cnt.ensure(16);
+    if (rc) return rc;
+    CUDA_TRY(cudaMemsetAsync(ctx.sp_cnt.p, 0, 16, stream));
+  } else {
+    CUDA_TRY(cudaMemsetAsync(ctx.sp_cnt.p, 0, 8, stream));
+  }
+  return SPICEY_SUCCESS;
+}
+
 }  // namespace
 
 struct spicey_handle {
@@ -377,6 +394,9 @@ int prepare_sparse(DeviceCtx& ctx, const HostPlan& hp, double pilot_f, bool eage
   if (ctx.sp_key == key) return SPICEY_SUCCESS;  // cached (valid or known not to apply)
   ctx.sp_key = key;
   ctx.sp_valid = false;
+  ctx.sp_launched = 0;
+  ctx.sp_adapt = 0;
+  if (ctx.sp_cnt.p) CUDA_TRY(cudaMemsetAsync((char*)ctx.sp_cnt.p + 8, 0, 8, stream));
   SparseProgram& sp = ctx.sp;
   build_sparse_host(hp, pilot_f, eager, sp);
   const int n_ent = (int)hp.ac.ent_col.size();
@@ -784,9 +804,11 @@ int launch_ac_sparse(DeviceCtx& ctx, const HostPlan& hp, const DevPlan& dp, cons
   int rc = ctx.sp_work.ensure(wbytes);
   if (rc) return rc;
   if ((rc = ctx.sp_fb.ensure(sizeof(long long) * args.p_count + 64))) return rc;
+  if (!ctx.sp_cnt.p && (rc = reset_call_counters(ctx, stream))) return rc;
   int* fb_count = (int*)ctx.sp_fb.p;
   long long* fb_list = (long long*)((char*)ctx.sp_fb.p + 64);
   CUDA_TRY(cudaMemsetAsync(fb_count, 0, sizeof(int), stream));
+  ctx.sp_launched += args.p_count;
   // the factorisation of one system must fit one thread's registers + shared memory (cfg2: 129 values), or the
   // compiled kernel spills kilobytes per thread and takes minutes to compile (a 400-node ladder: 801 values)
   if (ctx.sp_jit_fit_key != ctx.sp_key) {
@@ -812,7 +834,7 @@ int launch_ac_sparse(DeviceCtx& ctx, const HostPlan& hp, const DevPlan& dp, cons
     AcArgs d = args;
     d.plist = fb_list;
     d.pcount = fb_count;
-    d.fb_total = (unsigned long long*)((char*)ctx.sp_fb.p + 32);
+    d.fb_total = (unsigned long long*)ctx.sp_cnt.p;
     rc = launch_ac_dense(ctx, hp, dp, d, flags, stream, nullptr, launches);
     if (rc) return rc;
     if (tier_out) *tier_out = SPICEY_TIER_SPARSE_JIT;
@@ -831,7 +853,7 @@ int launch_ac_sparse(DeviceCtx& ctx, const HostPlan& hp, const DevPlan& dp, cons
         AcArgs d = args;
         d.plist = fb_list;
         d.pcount = fb_count;
-        d.fb_total = (unsigned long long*)((char*)ctx.sp_fb.p + 32);
+        d.fb_total = (unsigned long long*)ctx.sp_cnt.p;
         rc = launch_ac_dense(ctx, hp, dp, d, flags, stream, nullptr, launches);
         if (rc) return rc;
         if (tier_out) *tier_out = SPICEY_TIER_BAND;
@@ -849,7 +871,7 @@ int launch_ac_sparse(DeviceCtx& ctx, const HostPlan& hp, const DevPlan& dp, cons
       AcArgs d = args;
       d.plist = fb_list;
       d.pcount = fb_count;
-      d.fb_total = (unsigned long long*)((char*)ctx.sp_fb.p + 32);
+      d.fb_total = (unsigned long long*)ctx.sp_cnt.p;
       rc = launch_ac_dense(ctx, hp, dp, d, flags, stream, nullptr, launches);
       if (rc) return rc;
       if (tier_out) *tier_out = SPICEY_TIER_SPARSE_WARP;
@@ -905,7 +927,7 @@ int launch_ac_sparse(DeviceCtx& ctx, const HostPlan& hp, const DevPlan& dp, cons
   AcArgs d = args;
   d.plist = fb_list;
   d.pcount = fb_count;
-  d.fb_total = (unsigned long long*)((char*)ctx.sp_fb.p + 32);
+  d.fb_total = (unsigned long long*)ctx.sp_cnt.p;
   rc = launch_ac_dense(ctx, hp, dp, d, flags, stream, nullptr, launches);
   if (rc) return rc;
   if (tier_out) *tier_out = SPICEY_TIER_SPARSE;
@@ -922,6 +944,7 @@ struct TileArgs {   // must match tile_kernel.cuh
   const int* ent_rc; const int* ent_ptr; const int* contrib;
   const double2* ctab; const double4* el_rec; const double* ind_L;
   long long* fb_list; int* fb_count;
+  const long long* plist; const int* pcount; unsigned long long* fb_total;
   int n_ind, n_ent, nn, nV, n_elem, n_ac_elem, off_v, off_v_end, off_i;
 };
 
@@ -1127,14 +1150,17 @@ int launch_ac_tile(DeviceCtx& ctx, const HostPlan& hp, const DevPlan& dp, const 
   a.ent_rc = (const int*)ctx.tl_dev.ent_rc; a.ent_ptr = (const int*)ctx.tl_dev.ent_ptr; a.contrib = (const int*)ctx.tl_dev.contrib;
   a.n_ent = ctx.tl_dev.n_ent; a.nn = hp.nn; a.nV = hp.nV; a.n_elem = hp.n_elem; a.n_ac_elem = hp.n_ac_elem;
   a.off_v = hp.off[ELEM_V]; a.off_v_end = hp.off[ELEM_V + 1]; a.off_i = hp.off[ELEM_I];
+  a.plist = args.plist; a.pcount = args.pcount; a.fb_total = args.plist ? args.fb_total : nullptr;
   const bool guards = cst && ctx.tl_dev.n_ind > 0;   // points that trip an inductor guard go to the one-thread-per-row kernel
   if (cst) {
     a.ctab = (const double2*)(warp_lu ? ctx.tl_dev.wtab : ctx.tl_dev.ctab); a.el_rec = (const double4*)ctx.tl_dev.el_rec; a.ind_L = (const double*)ctx.tl_dev.ind_L;
     a.n_ind = ctx.tl_dev.n_ind;
     if (guards) {
-      if ((rc = ctx.sp_fb.ensure(sizeof(long long) * args.p_count + 64))) return rc;
-      a.fb_count = (int*)ctx.sp_fb.p;
-      a.fb_list = (long long*)((char*)ctx.sp_fb.p + 64);
+      // (the input may itself be the fallback list of a program tier, which lives in sp_fb: a list of its own then)
+      Buffer& fb = args.plist ? ctx.tl_fb : ctx.sp_fb;
+      if ((rc = fb.ensure(sizeof(long long) * args.p_count + 64))) return rc;
+      a.fb_count = (int*)fb.p;
+      a.fb_list = (long long*)((char*)fb.p + 64);
       CUDA_TRY(cudaMemsetAsync(a.fb_count, 0, sizeof(int), stream));
     }
   }
@@ -1146,8 +1172,8 @@ int launch_ac_tile(DeviceCtx& ctx, const HostPlan& hp, const DevPlan& dp, const 
     AcArgs d = args;
     d.plist = a.fb_list;
     d.pcount = a.fb_count;
-    d.fb_total = (unsigned long long*)((char*)ctx.sp_fb.p + 32);
-    return launch_ac_dense(ctx, hp, dp, d, flags, stream, nullptr, launches);
+    d.fb_total = args.plist ? nullptr : (unsigned long long*)ctx.sp_cnt.p;   // (points of a fallback list are counted once)
+    return launch_ac_dense(ctx, hp, dp, d, flags | SPICEY_FLAG_NO_TILE, stream, nullptr, launches);
   }
   return SPICEY_SUCCESS;
 }
@@ -1163,8 +1189,13 @@ int launch_ac_dense(DeviceCtx& ctx, const HostPlan& hp, const DevPlan& dp, const
   // Matrices that are mostly structural zeros stay with the row kernel as well: it walks the set bits of its row masks
   // (cfg 2's ladder forced dense: 5.9 M solves/s against 4.2 M with every tile entry updated).
   const bool dense_matrix = (long long)hp.ac.ent_col.size() * 4 >= (long long)hp.nvar * (hp.nvar + 1);
-  if (!strict && !(flags & (SPICEY_FLAG_FORCE_GMEM | SPICEY_FLAG_NO_JIT | SPICEY_FLAG_NO_TILE)) && !args.plist &&
-      ((flags & SPICEY_FLAG_TILE) || (dense_matrix && (args.p_count >= kTileMinPoints || (flags & SPICEY_FLAG_JIT)))) &&
+  // The fallback list of a program tier (systems whose pivot order differs from the pilot order) takes the register
+  // kernels too when the launch is large and the matrix is not nearly empty: on circuits with inductors most points of a
+  // many-decade sweep can end up there (measured, random RLC networks: 98 - 99.9 % of the points).
+  const bool fb_tile = args.plist && args.p_count >= kTileMinPoints &&
+                       (hp.nvar <= 32 || (long long)hp.ac.ent_col.size() * 12 >= (long long)hp.nvar * (hp.nvar + 1));
+  if (!strict && !(flags & (SPICEY_FLAG_FORCE_GMEM | SPICEY_FLAG_NO_JIT | SPICEY_FLAG_NO_TILE)) && (!args.plist || fb_tile) &&
+      ((flags & SPICEY_FLAG_TILE) || fb_tile || (dense_matrix && (args.p_count >= kTileMinPoints || (flags & SPICEY_FLAG_JIT)))) &&
       args.series_ld < (1ll << 40)) {
     bool used = false;
     int rc = launch_ac_tile(ctx, hp, dp, args, flags, stream, launches, &used);
@@ -1222,6 +1253,20 @@ int launch_ac(DeviceCtx& ctx, const HostPlan& hp, const DevPlan& dp, const AcArg
       }
       int rc = prepare_sparse(ctx, hp, pilot_f, eager, stream);
       if (rc) return rc;
+    }
+    // Once per cached program: how did the pilot order hold up so far?  When a quarter of the points launched through
+    // it came back on the fallback list, the program tiers only add their own pass in front of the dense solve: later
+    // launches of this topology go to the dense tiers directly.  (One stream synchronisation per topology.)
+    if (ctx.sp_valid && ctx.sp_adapt == 0 && ctx.sp_launched >= kTileMinPoints && ctx.sp_cnt.p &&
+        !(flags & (SPICEY_FLAG_BAND | SPICEY_FLAG_WARP))) {
+      unsigned long long life = 0;
+      CUDA_TRY(cudaMemcpyAsync(&life, (const char*)ctx.sp_cnt.p + 8, sizeof life, cudaMemcpyDeviceToHost, stream));
+      CUDA_TRY(cudaStreamSynchronize(stream));
+      ctx.sp_adapt = ((long long)life * 4 >= ctx.sp_launched) ? 2 : 1;
+    }
+    if (ctx.sp_valid && ctx.sp_adapt == 2 && !(flags & (SPICEY_FLAG_BAND | SPICEY_FLAG_WARP | SPICEY_FLAG_NO_TILE | SPICEY_FLAG_NO_JIT))) {
+      TileShape sh;
+      if (tile_shape_for(ctx, hp, sh)) return launch_ac_dense(ctx, hp, dp, args, flags | SPICEY_FLAG_TILE, stream, tier_out, launches);
     }
     if (ctx.sp_valid) {
       // A program that executes most of the dense elimination's work has nothing to gain from the program tiers (their
@@ -1496,7 +1541,7 @@ void spicey_destroy(spicey_handle* h) {
     cudaDeviceSynchronize();
     Buffer* bufs[] = {&c.plan, &c.scratch, &c.in0, &c.in1, &c.in2, &c.out_x[0], &c.out_x[1], &c.out_i[0],
                       &c.out_i[1], &c.out_s[0], &c.out_s[1], &c.aux0, &c.aux1, &c.sp_blob, &c.sp_work, &c.sp_fb,
-                      &c.wp_blob, &c.wp_work, &c.bp_blob, &c.bp_work, &c.tl_blob, &c.tr_iters[0], &c.tr_iters[1], &c.tr_state[0], &c.tr_state[1]};
+                      &c.wp_blob, &c.wp_work, &c.bp_blob, &c.bp_work, &c.tl_blob, &c.tr_iters[0], &c.tr_iters[1], &c.tr_state[0], &c.tr_state[1], &c.sp_cnt, &c.tl_fb};
     for (Buffer* b : bufs) b->release();
     for (auto& jv : c.sp_jit) if (jv.lib) cudaLibraryUnload(jv.lib);
     for (auto& jv : c.tr_jit) if (jv.lib) cudaLibraryUnload(jv.lib);
@@ -1516,10 +1561,10 @@ int32_t spicey_get_stats(const spicey_handle* h, spicey_stats* out) {
   if (out->fallback_solves < 0) {  // read the device-side counters (synchronises the devices)
     long long total = 0;
     for (const auto& c : h->devs) {
-      if (!c.sp_fb.p) continue;
+      if (!c.sp_cnt.p) continue;
       unsigned long long v = 0;
       cudaSetDevice(c.dev);
-      if (cudaMemcpy(&v, (const char*)c.sp_fb.p + 32, sizeof(v), cudaMemcpyDeviceToHost) == cudaSuccess) total += (long long)v;
+      if (cudaMemcpy(&v, c.sp_cnt.p, sizeof(v), cudaMemcpyDeviceToHost) == cudaSuccess) total += (long long)v;
     }
     out->fallback_solves = total;
   }
@@ -1567,6 +1612,7 @@ int32_t spicey_ac_solve_device(spicey_handle* h, int32_t dev_index, const spicey
   int64_t launches = 0;
   if ((rc = ctx.sp_fb.ensure(sizeof(long long) * a.p_count + 64))) return rc;
   CUDA_TRY(cudaMemsetAsync(ctx.sp_fb.p, 0, 64, st));
+  if ((rc = reset_call_counters(ctx, st))) return rc;
   rc = launch_ac(ctx, hp, dp, a, flags, st, &tier, &launches, 0.0, false);
   if (rc) return rc;
   h->stats.kernel_launches = launches;
@@ -1638,6 +1684,7 @@ int32_t spicey_ac_solve(spicey_handle* h, const spicey_elem_table* table, const 
     const long long cld = series ? spicey_series_ld(csz) : csz;  // device rows start on 512-byte boundaries
     if ((rc = ctx.sp_fb.ensure(sizeof(long long) * csz + 64))) return rc;
     CUDA_TRY(cudaMemsetAsync(ctx.sp_fb.p, 0, 64, ctx.compute));
+    if ((rc = reset_call_counters(ctx, ctx.compute))) return rc;
     for (int b = 0; b < 2; ++b) {
       if ((rc = ctx.out_x[b].ensure(xrow * cld))) return rc;
       if (ielem && (rc = ctx.out_i[b].ensure(irow * cld))) return rc;

@@ -70,6 +70,9 @@ struct TileArgs {   // must match TileArgs in spicey_native.cu
                            // index Nvar = the ground node; V: (branch, Nvar, 1, 0, 0)
   const double* ind_L;     // inductances: the guards of simulateAC.ts:47-51 are checked per point, a point that trips one
   long long* fb_list; int* fb_count;   // ... is left to the one-thread-per-row kernel, which also reports the exact status
+  const long long* plist; const int* pcount;   // optional: solve the launch-local points plist[0 .. *pcount) only (the
+                                               // fallback list of a program tier), adding their number to fb_total[0 .. 1]
+  unsigned long long* fb_total;
   int n_ind, n_ent, nn, nV, n_elem, n_ac_elem, off_v, off_v_end, off_i;
 };
 
@@ -338,7 +341,13 @@ extern "C" __global__ void __launch_bounds__(TL_THREADS, TL_MINB) spicey_tile_ji
   t.Cb = Cb; t.Pb = Pb; t.Kb = Kb; t.Rd = Rd; t.Wn = Wn;
   if (tid < 2) Cb[tid * (TL_NP + 1) + TL_NP] = make_double2(0.0, 0.0);   // (visible after the first barrier of the point loop)
 
-  for (long long q = blockIdx.x; q < a.p_count; q += gridDim.x) {
+  const long long work = a.plist ? (long long)*a.pcount : a.p_count;
+  if (a.plist && a.fb_total && blockIdx.x == 0 && tid == 0 && work > 0) {
+    atomicAdd(a.fb_total, (unsigned long long)work);
+    atomicAdd(a.fb_total + 1, (unsigned long long)work);
+  }
+  for (long long qi = blockIdx.x; qi < work; qi += gridDim.x) {
+    const long long q = a.plist ? a.plist[qi] : qi;
     const long long p_abs = a.p_begin + q;
     const long long inst = p_abs / a.n_freq;
     const double f = a.freqs[p_abs - inst * a.n_freq];

@@ -44,6 +44,8 @@ struct TileArgs {   // must match TileArgs in spicey_native.cu (shared with tile
   const double4* el_rec;   // [n_ac_elem] {bits of (i1, i2), ya, yb, yg}; index Nvar = the ground node
   const double* ind_L;
   long long* fb_list; int* fb_count;
+  const long long* plist; const int* pcount;   // optional: solve the launch-local points plist[0 .. *pcount) only
+  unsigned long long* fb_total;
   int n_ind, n_ent, nn, nV, n_elem, n_ac_elem, off_v, off_v_end, off_i;
 };
 
@@ -73,16 +75,22 @@ extern "C" __global__ void __launch_bounds__(WL_THREADS, WL_MINB) spicey_warp_lu
 
   // CTA-uniform trip count (the warps of a CTA meet at barriers inside): warps past the end solve the last point again
   // and store nothing
-  for (long long cta_base = (long long)blockIdx.x * WL_WARPS; cta_base < a.p_count; cta_base += n_warps) {
+  const long long work = a.plist ? (long long)*a.pcount : a.p_count;
+  if (a.plist && a.fb_total && blockIdx.x == 0 && threadIdx.x == 0 && work > 0) {
+    atomicAdd(a.fb_total, (unsigned long long)work);
+    atomicAdd(a.fb_total + 1, (unsigned long long)work);
+  }
+  for (long long cta_base = (long long)blockIdx.x * WL_WARPS; cta_base < work; cta_base += n_warps) {
     const long long q0 = cta_base + wib;
-    bool valid = q0 < a.p_count;
-    const long long q = valid ? q0 : a.p_count - 1;
+    bool valid = q0 < work;
+    const long long qi = valid ? q0 : work - 1;
+    const long long q = a.plist ? a.plist[qi] : qi;
     const double w = (2 * WL_PI) * a.freqs[a.p_begin + q];
     const double iw = 1.0 / w;
     if (a.n_ind > 0) {   // inductor guards of simulateAC.ts:47-51: the one-thread-per-row kernel decides
       int bad = 0;
-      for (int qi = lane; qi < a.n_ind; qi += 32) {
-        const double d = w * a.ind_L[qi];
+      for (int li = lane; li < a.n_ind; li += 32) {
+        const double d = w * a.ind_L[li];
         bad |= (int)(fabs(d) < WL_EPS) | (int)(d * d < WL_EPS);
       }
       if (__any_sync(WL_FULL, bad)) {

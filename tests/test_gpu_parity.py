@@ -1267,3 +1267,40 @@ def test_tran_host_call_pipelines_instance_chunks(monkeypatch):
     vr, ir, _, st, _ = co.tran_solve(ck, one["dt"], one["steps"], n_inst=n, overrides=ov, nthreads=8)
     assert st.max() == 0 and many["status"].max() == 0
     assert np.max(np.abs(many["v"] - np.transpose(vr, (1, 2, 0)))) <= TRAN_TOL * np.max(np.abs(vr))
+
+
+def test_ac_program_tiers_hand_over_when_the_pilot_order_does_not_hold():
+    """A random RLC network swept over five decades: the pivot order of the pilot point holds for almost no other point, so
+    nearly every system of the first launch comes back on the fallback list — solved there by the register kernels (the
+    one-warp-per-system LU in list mode), exact statuses and results — and the handle then sends later launches of this
+    topology to the dense tier directly (one check per cached program)."""
+    import spicey_b200 as sp
+    rng = np.random.default_rng(14060)
+    text = random_rlc_netlist(rng, 14, 60, n_v=2).replace(".ac dec 7 10 1meg", ".ac dec 1640 10 1meg")
+    ck = parse_netlist(text)
+    freqs = np.array(sp.analysis.ac_frequencies(ck))
+    assert freqs.shape[0] >= 8192
+    pick = np.arange(0, freqs.shape[0], 61)
+    xr, ier, st = co.ac_solve(ck, freqs[pick], nthreads=8)
+    scale, iscale = np.max(np.abs(xr), axis=1, keepdims=True), np.max(np.abs(ier), axis=1, keepdims=True)
+    e = native.Engine()
+    try:
+        for call, flags in enumerate((SM, SM, 0)):
+            out = sp.simulate_ac_batch(ck, freqs, engine=e, flags=flags)
+            stt = e.stats()
+            if call == 0:
+                assert stt["tier"] in (native.TIER_SPARSE, native.TIER_SPARSE_JIT), stt
+                assert stt["fallback_solves"] * 4 >= freqs.shape[0], stt
+            else:
+                assert stt["tier"] == native.TIER_TILE and stt["fallback_solves"] == 0, (call, stt)
+            assert out["status"].max() == 0 and st.max() == 0
+            assert np.max(np.abs(out["x"][0][pick] - xr) / scale) <= AC_TOL, call
+            assert np.max(np.abs(out["ielem"][0][pick] - ier) / iscale) <= AC_TOL, call
+        # a topology whose pilot order does hold keeps its program tier on the same handle (cfg 2's ladder)
+        ckl = parse_netlist(w.rc_ladder(64))
+        fl = np.array(sp.analysis.ac_frequencies(ckl))[::97]
+        for _ in range(3):
+            sp.simulate_ac_batch(ckl, fl, engine=e, flags=SM)
+            assert e.stats()["tier"] == native.TIER_SPARSE and e.stats()["fallback_solves"] == 0, e.stats()
+    finally:
+        e.close()

@@ -1,7 +1,7 @@
 #!/usr/bin/env python3
 """GPU: time one AC workload under several flag sets (kernel tiers) and check each against the strict row kernel.
    usage: tier_sweep.py "SPARSE|NO_JIT" "SPARSE|JIT" "SPARSE|BAND" "DENSE" ...   (names of native.FLAG_*, SERIES_MAJOR is added)
-   SWEEP_WL=ladder<n> | mesh<side> | dense<n> (default ladder400), SWEEP_P points (default 200000), SWEEP_NO_IELEM=1"""
+   SWEEP_WL=ladder<n> | mesh<side> | dense<n> | rlc<nodes>x<elements> (default ladder400), SWEEP_P points (default 200000), SWEEP_NO_IELEM=1"""
 import os
 import sys
 
@@ -20,6 +20,20 @@ def main():
         text = workloads.rc_ladder(int(wl[6:]))
     elif wl.startswith("mesh"):
         text = workloads.rc_mesh(int(wl[4:]))
+    elif wl.startswith("rlc"):   # rlc<nodes>x<extra elements>: a seeded random RLC network (resistor tree + random R / C / L)
+        n_nodes, n_elem = (int(v) for v in wl[3:].split("x"))
+        rng = np.random.default_rng(n_nodes * 1000 + n_elem)
+        nodes = ["0"] + ["n%d" % i for i in range(1, n_nodes + 1)]
+        lines = ["* random RLC", "v1 n1 0 dc 1 ac 1 0", "v2 n2 0 dc 1 ac 0.5 45"]
+        for i in range(1, n_nodes + 1):
+            lines.append("r%d n%d %s %g" % (i, i, nodes[rng.integers(0, i)], rng.uniform(10, 1e4)))
+        for k in range(n_elem):
+            a, b = rng.choice(len(nodes), 2, replace=False)
+            kind = "rcl"[rng.integers(0, 3)]
+            val = {"r": rng.uniform(10, 1e4), "c": rng.uniform(1e-9, 1e-6), "l": rng.uniform(1e-4, 1e-2)}[kind]
+            lines.append("%s%d %s %s %g" % (kind, 100 + k, nodes[a], nodes[b], val))
+        lines.append(".ac dec 40000 10 1meg")
+        text = "\n".join(lines) + "\n"
     else:
         text = workloads.rc_dense(int(wl[5:]))
     ck = parsing.parse_netlist(text)
