@@ -1304,3 +1304,65 @@ def test_ac_program_tiers_hand_over_when_the_pilot_order_does_not_hold():
             assert e.stats()["tier"] == native.TIER_SPARSE and e.stats()["fallback_solves"] == 0, e.stats()
     finally:
         e.close()
+
+
+def _rc_system_matrices(table):
+    """A(w) = A0 + j w A1 and b of an R / C / V circuit, stamped as simulateAC.ts:24-60 does (rows of node ids n - 1,
+    V branch rows nn + k, b[branch] = the source phasor) — independent of the oracle and of the library's own plan."""
+    n, nn = table.nvar, table.n_nodes
+    A0, A1, b = np.zeros((n, n)), np.zeros((n, n)), np.zeros(n, dtype=np.complex128)
+    kv = 0
+    for e in range(table.n_ac_elem):
+        ty, n1, n2, v = int(table.type[e]), int(table.n1[e]) - 1, int(table.n2[e]) - 1, table.values[table.value_idx[e]:]
+        if ty == native.ELEM_V:
+            j = nn + kv
+            kv += 1
+            if n1 >= 0:
+                A0[n1, j] += 1; A0[j, n1] += 1
+            if n2 >= 0:
+                A0[n2, j] -= 1; A0[j, n2] -= 1
+            b[j] += v[1] * np.exp(1j * np.pi * v[2] / 180)
+            continue
+        M, y = (A0, 1 / v[0]) if ty == native.ELEM_R else (A1, v[0])
+        assert ty in (native.ELEM_R, native.ELEM_C)
+        if n1 >= 0:
+            M[n1, n1] += y
+        if n2 >= 0:
+            M[n2, n2] += y
+        if n1 >= 0 and n2 >= 0:
+            M[n1, n2] -= y; M[n2, n1] -= y
+    return A0, A1, b
+
+
+def test_full_size_properties_dense64(eng):
+    """The dense workload (complete RC graph, Nvar 65) at the bench's size, 200,000 points through the register-tile tier:
+    every status 0, and EVERY point's solution satisfies its own system — the residual |A(w) x - b| against
+    |A| |x| + |b|, row by row, with A(w) built here from the element table in batches on the GPU — plus KCL at the source
+    node and a 1/997 subsample against the oracle."""
+    import torch
+    import spicey_b200 as sp
+    ck = parse_netlist(w.rc_dense(64))
+    table = sp.packing.pack_circuit(ck)
+    freqs = np.array(sp.analysis.ac_frequencies(ck))
+    freqs = np.ascontiguousarray(freqs[:: freqs.shape[0] // 200000][:200000])
+    out = sp.simulate_ac_batch(ck, freqs, engine=eng, want_currents=False)
+    assert eng.stats()["tier"] == native.TIER_TILE and out["status"].max() == 0
+    x = out["x"][0]
+    A0, A1, b = _rc_system_matrices(table)
+    dev = torch.device("cuda", 0)
+    tA0, tA1 = torch.from_numpy(A0).to(dev).to(torch.complex128), torch.from_numpy(A1).to(dev).to(torch.complex128)
+    tb = torch.from_numpy(b).to(dev)
+    worst = 0.0
+    for c0 in range(0, freqs.shape[0], 20000):
+        wv = torch.from_numpy(2 * np.pi * freqs[c0:c0 + 20000]).to(dev).to(torch.complex128)
+        A = tA0[None] + 1j * wv[:, None, None] * tA1[None]
+        tx = torch.from_numpy(np.ascontiguousarray(x[c0:c0 + 20000])).to(dev)
+        res = torch.abs(torch.einsum("pij,pj->pi", A, tx) - tb[None])
+        den = torch.einsum("pij,pj->pi", torch.abs(A), torch.abs(tx)) + torch.abs(tb)[None]
+        worst = max(worst, float(torch.max(res / den)))
+        del A, res, den
+    assert worst <= 1e-13, worst
+    assert np.max(np.abs(x[:, 0] - 1.0)) <= 1e-15            # the driven node carries the source phasor
+    sub = slice(0, None, 997)
+    xr, _, st = co.ac_solve(ck, freqs[sub], nthreads=8)
+    assert st.max() == 0 and rel_err(x[sub], xr) <= AC_TOL
