@@ -1649,7 +1649,9 @@ int32_t spicey_ac_solve(spicey_handle* h, const spicey_elem_table* table, const 
   // Chunk size: ~96 MiB of results per chunk so that copies overlap the next chunk's kernel.
   // ... but never fewer points than fill the GPU (one thread per point in the sparse tier), within 4 GiB per buffer.
   const size_t prow = xrow + (ielem ? irow : 0) + 4;
-  long long chunk = std::max<long long>(1024, (long long)((96ull << 20) / prow));
+  size_t chunk_bytes = 96ull << 20;
+  if (const char* e = getenv("SPICEY_AC_CHUNK_BYTES")) chunk_bytes = (size_t)std::max(1ll << 20, atoll(e));   // experiments
+  long long chunk = std::max<long long>(1024, (long long)(chunk_bytes / prow));
   chunk = std::max<long long>(chunk, std::min<long long>((long long)h->devs[0].sm_count * 1024, (long long)((4ull << 30) / prow)));
   int64_t launches = 0, h2d = 0, d2h = 0;
   int tier = 0;
