@@ -258,6 +258,17 @@ int32_t spicey_tran_solve_waves(spicey_handle* h, const spicey_elem_table* table
                                 const double* state0, double* v, double* ielem, double* state_out,
                                 int32_t* iters, int32_t* status, uint32_t flags);
 
+/* spicey_tran_solve / spicey_tran_solve_waves (waves NULL: vsrc_mask as in spicey_tran_solve; else the descriptors)
+ * returning only the node voltages a caller will keep: simulateTRAN filters result.nodeVoltages by the `.PRINT TRAN`
+ * probes (lib/analysis/simulateTRAN.ts:240-249), so the others need not cross the bus.  node_sel[n_sel]: node ids
+ * (1 .. n_nodes) in the order wanted; v: [steps+1][n_sel][n_inst] (v may be NULL when n_sel == 0).  ielem, state_out,
+ * iters, status as in spicey_tran_solve (element currents are not filtered by the reference; pass ielem = NULL to leave
+ * them on the device too). */
+int32_t spicey_tran_solve_probes(spicey_handle* h, const spicey_elem_table* table, const spicey_sweep* sweep,
+                                 double dt, int64_t steps, const spicey_waves* waves, const double* vsrc, const int32_t* vsrc_mask,
+                                 const double* state0, const int32_t* node_sel, int32_t n_sel, double* v, double* ielem,
+                                 double* state_out, int32_t* iters, int32_t* status, uint32_t flags);
+
 int32_t spicey_tran_solve_waves_device(spicey_handle* h, int32_t dev_index, const spicey_elem_table* table,
                                        const spicey_sweep* sweep, double dt, int64_t steps,
                                        const spicey_waves* waves /* host */, const double* d_vsrc,

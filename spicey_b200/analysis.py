@@ -227,15 +227,18 @@ def simulateTRAN(ckt: ParsedCircuit, engine: Optional[native.Engine] = None, fla
     dt, steps = compute_effective_time_step(ckt.analyses.tran.dt, ckt.analyses.tran.tstop)
     table = pack_circuit(ckt)
     vsrc, mask = sample_sources(ckt, dt, steps)
-    res = eng.tran_solve(table, dt, steps, vsrc=vsrc, vsrc_mask=mask, state0=initial_state(ckt, table), flags=flags)
+    names = ckt.nodes.rev[1:]
+    sel = None
+    if len(ckt.probes.tran) > 0:  # :240-249 keeps the probed node voltages only (elementCurrents are not filtered):
+        upper = [p.upper() for p in ckt.probes.tran]   # the others stay on the device (spicey_tran_solve_probes)
+        sel = [i + 1 for i, k in enumerate(names) if k.upper() in upper]
+        names = [names[i - 1] for i in sel]
+    res = eng.tran_solve(table, dt, steps, vsrc=vsrc, vsrc_mask=mask, state0=initial_state(ckt, table), flags=flags, node_sel=sel)
     _raise_first_failure(res["status"], table, ckt, _TRAN_ERRORS)
     write_back_state(ckt, res["state"][:, 0])
     times = [k * dt for k in range(steps + 1)]  # t = step*dt, never accumulated (:147)
-    volt = _series_by_name(ckt.nodes.rev[1:], res["v"][:, :, 0])
+    volt = _series_by_name(names, res["v"][:, :, 0])
     cur = _series_by_name(table.names, res["ielem"][:, :, 0])
-    if len(ckt.probes.tran) > 0:  # :240-249 (elementCurrents are not filtered)
-        upper = [p.upper() for p in ckt.probes.tran]
-        volt = {k: v for k, v in volt.items() if k.upper() in upper}
     return {"times": times, "nodeVoltages": volt, "elementCurrents": cur}
 
 

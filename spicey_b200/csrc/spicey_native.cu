@@ -1809,9 +1809,10 @@ static int32_t tran_solve_device_impl(spicey_handle* h, int32_t dev_index, const
 static int32_t tran_solve_impl(spicey_handle* h, const spicey_elem_table* table, const spicey_sweep* sweep, double dt,
                           int64_t steps, const double* vsrc, const int32_t* vsrc_mask, const spicey_waves* wv, const double* state0,
                           double* v, double* ielem, double* state_out, int32_t* iters, int32_t* status,
-                          uint32_t flags) {
+                          uint32_t flags, const int32_t* node_sel = nullptr, int32_t n_sel = -1) {
   if (!h) return fail(SPICEY_ERR_INVALID, "handle is NULL");
-  if (steps < 1 || !v || !status) return fail(SPICEY_ERR_INVALID, "NULL buffer or steps < 1");
+  if (steps < 1 || !status || (!v && n_sel != 0)) return fail(SPICEY_ERR_INVALID, "NULL buffer or steps < 1");
+  if (n_sel > 0 && !node_sel) return fail(SPICEY_ERR_INVALID, "node_sel is NULL");
   const double t0 = now_ms();
   int rc = cached_plan(h, table, sweep);
   if (rc) return rc;
@@ -1822,6 +1823,8 @@ static int32_t tran_solve_impl(spicey_handle* h, const spicey_elem_table* table,
   const int n_var = sweep ? sweep->n_var : 0;
   const long long S1 = steps + 1;
   const int D = (int)h->devs.size();
+  for (int k = 0; k < n_sel; ++k)
+    if (node_sel[k] < 1 || node_sel[k] > hp.nn) return fail(SPICEY_ERR_INVALID, "node_sel entry is not a node id 1..n_nodes");
   WaveList waves;
   if ((rc = build_waves(hp, wv, vsrc_mask, vsrc != nullptr, waves))) return rc;
   bool any_wave = false;   // any pre-sampled row to upload
@@ -1903,9 +1906,18 @@ static int32_t tran_solve_impl(spicey_handle* h, const spicey_elem_table* table,
       CUDA_TRY(cudaStreamWaitEvent(ctx.copy, ke, 0));
       // [rows][n] device slabs -> [rows][n_inst] host arrays at column offset c0
       const size_t dp_ = sizeof(double) * n_inst, sp_ = sizeof(double) * n;
-      CUDA_TRY(cudaMemcpy2DAsync((char*)v + sizeof(double) * c0, dp_, a.v, sp_, sp_, S1 * hp.nn,
-                                 cudaMemcpyDeviceToHost, ctx.copy));
-      d2h += (int64_t)(sp_ * S1 * hp.nn);
+      if (n_sel < 0) {
+        CUDA_TRY(cudaMemcpy2DAsync((char*)v + sizeof(double) * c0, dp_, a.v, sp_, sp_, S1 * hp.nn,
+                                   cudaMemcpyDeviceToHost, ctx.copy));
+        d2h += (int64_t)(sp_ * S1 * hp.nn);
+      } else {
+        // probes only (simulateTRAN.ts:240-249 keeps the probed node voltages): one strided copy per selected node,
+        // device rows [step][node] of n instances -> host [step][k] of n_inst
+        for (int k = 0; k < n_sel; ++k)
+          CUDA_TRY(cudaMemcpy2DAsync((char*)v + sizeof(double) * ((size_t)k * n_inst + c0), dp_ * n_sel,
+                                     a.v + (size_t)(node_sel[k] - 1) * n, sp_ * hp.nn, sp_, S1, cudaMemcpyDeviceToHost, ctx.copy));
+        d2h += (int64_t)(sp_ * S1 * n_sel);
+      }
       if (ielem && hp.n_elem > 0) {
         CUDA_TRY(cudaMemcpy2DAsync((char*)ielem + sizeof(double) * c0, dp_, a.ielem, sp_, sp_, S1 * hp.n_elem,
                                    cudaMemcpyDeviceToHost, ctx.copy));
@@ -1964,6 +1976,15 @@ int32_t spicey_tran_solve(spicey_handle* h, const spicey_elem_table* table, cons
                           double* v, double* ielem, double* state_out, int32_t* iters, int32_t* status,
                           uint32_t flags) {
   return tran_solve_impl(h, table, sweep, dt, steps, vsrc, vsrc_mask, nullptr, state0, v, ielem, state_out, iters, status, flags);
+}
+
+int32_t spicey_tran_solve_probes(spicey_handle* h, const spicey_elem_table* table, const spicey_sweep* sweep,
+                                 double dt, int64_t steps, const spicey_waves* waves, const double* vsrc, const int32_t* vsrc_mask,
+                                 const double* state0, const int32_t* node_sel, int32_t n_sel, double* v, double* ielem,
+                                 double* state_out, int32_t* iters, int32_t* status, uint32_t flags) {
+  if (n_sel < 0) return fail(SPICEY_ERR_INVALID, "n_sel < 0");
+  return tran_solve_impl(h, table, sweep, dt, steps, vsrc, waves ? nullptr : vsrc_mask, waves, state0, v, ielem, state_out, iters,
+                         status, flags, node_sel, n_sel);
 }
 
 int32_t spicey_tran_solve_waves(spicey_handle* h, const spicey_elem_table* table, const spicey_sweep* sweep, double dt,

@@ -31,7 +31,7 @@ EXPORTS = [
     "spicey_debug_sparse_source", "spicey_series_ld", "spicey_debug_tran_source", "spicey_debug_warp_stats",
     "spicey_tran_solve_waves", "spicey_tran_solve_waves_device", "spicey_debug_tran_source_waves",
     "spicey_debug_band_stats", "spicey_debug_band_source", "spicey_debug_tile_source",
-    "spicey_debug_warp_lu_source",
+    "spicey_debug_warp_lu_source", "spicey_tran_solve_probes",
 ]
 WAVE_DC, WAVE_TABLE, WAVE_PULSE, WAVE_PWL = 0, 1, 2, 3
 
@@ -110,6 +110,9 @@ def load_library(path: Optional[str] = None):
     wv = C.POINTER(WavesStruct)
     lib.spicey_tran_solve_waves.restype = C.c_int32
     lib.spicey_tran_solve_waves.argtypes = [vp, tb, sw, C.c_double, C.c_int64, wv, vp, vp, vp, vp, vp, vp, vp, C.c_uint32]
+    lib.spicey_tran_solve_probes.restype = C.c_int32
+    lib.spicey_tran_solve_probes.argtypes = [vp, tb, sw, C.c_double, C.c_int64, wv, vp, vp, vp, vp, C.c_int32, vp, vp, vp, vp, vp,
+                                             C.c_uint32]
     lib.spicey_tran_solve_waves_device.restype = C.c_int32
     lib.spicey_tran_solve_waves_device.argtypes = [vp, C.c_int32, tb, sw, C.c_double, C.c_int64, wv, vp, vp, vp, vp,
                                                    vp, vp, vp, C.c_uint32, vp]
@@ -373,9 +376,11 @@ class Engine:
 
     def tran_solve(self, table: ElemTable, dt: float, steps: int, vsrc=None, vsrc_mask=None,
                    sweep: Optional[Sweep] = None, state0=None, want_currents=True, want_iters=False, flags=0,
-                   out=None, waves: Optional[Waves] = None):
+                   out=None, waves: Optional[Waves] = None, node_sel=None):
         """Returns dict(v[S1,nn,n_inst], ielem[S1,n_elem,n_inst]|None, state[n_state,n_inst], iters, status).
-        waves: per-source descriptors (PULSE / PWL evaluated on the device); vsrc_mask is then ignored."""
+        waves: per-source descriptors (PULSE / PWL evaluated on the device); vsrc_mask is then ignored.
+        node_sel: node ids (1-based) whose voltages are wanted, e.g. the .PRINT TRAN probes — v is then [S1,len(node_sel),n_inst]
+        and only those rows cross the bus (spicey_tran_solve_probes)."""
         n_inst = sweep.n_inst if sweep else 1
         S1 = steps + 1
         nV = table.n_vsrc
@@ -386,8 +391,9 @@ class Engine:
             mask[:nV] = np.asarray(vsrc_mask, dtype=np.int32)
         if state0 is not None:
             state0 = np.ascontiguousarray(state0, dtype=np.float64).reshape(table.n_state, n_inst)
+        sel = None if node_sel is None else np.ascontiguousarray(node_sel, dtype=np.int32)
         if out is None:
-            v = np.empty((S1, table.n_nodes, n_inst), dtype=np.float64)
+            v = np.empty((S1, table.n_nodes if sel is None else len(sel), n_inst), dtype=np.float64)
             ie = np.empty((S1, table.n_elem, n_inst), dtype=np.float64) if want_currents else None
         else:
             v, ie = out
@@ -396,7 +402,13 @@ class Engine:
         status = np.empty(n_inst, dtype=np.int32)
         ts = table.struct()
         ss = sweep.struct() if sweep else None
-        if waves is not None:
+        if sel is not None:
+            ws = waves.struct() if waves is not None else None
+            _check(self.lib, self.lib.spicey_tran_solve_probes(
+                self._h, C.byref(ts), C.byref(ss) if ss else None, float(dt), int(steps), C.byref(ws) if ws else None,
+                _ptr(vsrc), _ptr(mask), _ptr(state0), _ptr(sel), int(len(sel)), _ptr(v) if len(sel) else None, _ptr(ie),
+                _ptr(state), _ptr(iters), _ptr(status), flags))
+        elif waves is not None:
             ws = waves.struct()
             _check(self.lib, self.lib.spicey_tran_solve_waves(
                 self._h, C.byref(ts), C.byref(ss) if ss else None, float(dt), int(steps), C.byref(ws), _ptr(vsrc),

@@ -1366,3 +1366,55 @@ def test_full_size_properties_dense64(eng):
     sub = slice(0, None, 997)
     xr, _, st = co.ac_solve(ck, freqs[sub], nthreads=8)
     assert st.max() == 0 and rel_err(x[sub], xr) <= AC_TOL
+
+
+def test_tran_probes_select_what_crosses_the_bus(eng, golden, monkeypatch):
+    """spicey_tran_solve_probes: simulateTRAN keeps the `.PRINT TRAN` node voltages only (simulateTRAN.ts:240-249), so only
+    those rows are copied to the host — same keys and bit-identical waveforms as the full call, fewer bytes; any order and
+    repetition of node ids, batches in several pipeline chunks, and an empty selection."""
+    import spicey_b200 as sp
+    for name in ("switch_vt_vh", "boost_converter_probe", "two_probes"):
+        g = golden(name)
+        ck = parse_netlist(g["netlist"])
+        assert len(ck.probes.tran) > 0
+        got = sp.simulateTRAN(ck, engine=eng)
+        d2h_sel = eng.stats()["d2h_bytes"]
+        ref = o.simulate_tran(parse_netlist(g["netlist"]))
+        assert list(got["nodeVoltages"].keys()) == list(ref["nodeVoltages"].keys())
+        ck2 = parse_netlist(g["netlist"])
+        ck2.probes.tran.clear()
+        full = sp.simulateTRAN(ck2, engine=eng)
+        if name == "two_probes":   # (probes both of its nodes)
+            assert eng.stats()["d2h_bytes"] == d2h_sel and len(full["nodeVoltages"]) == len(got["nodeVoltages"]) == 2
+        else:
+            assert eng.stats()["d2h_bytes"] > d2h_sel and len(full["nodeVoltages"]) > len(got["nodeVoltages"])
+        for k, series in got["nodeVoltages"].items():
+            assert np.array_equal(series, full["nodeVoltages"][k]), (name, k)
+            want = np.asarray(ref["nodeVoltages"][k])
+            assert np.max(np.abs(series - want)) <= TRAN_TOL * max(1.0, np.max(np.abs(want))), (name, k)
+        for k, series in got["elementCurrents"].items():
+            assert np.array_equal(series, full["elementCurrents"][k]), (name, k)
+    # batch, ragged chunks, repeated / reordered ids
+    n = 150
+    ov = {k: v[:n] for k, v in w.rectifier_overrides(100000).items()}
+    ck = parse_netlist(w.RECTIFIER)
+    table = sp.packing.pack_circuit(ck)
+    dt, steps = compute_effective_time_step(ck.analyses.tran.dt, ck.analyses.tran.tstop)
+    vsrc, mask = sp.packing.sample_sources(ck, dt, steps)
+    sweep = sp.packing.make_sweep(table, n, ov)
+    st0 = sp.packing.initial_state(ck, table, n)
+    full = eng.tran_solve(table, dt, steps, vsrc=vsrc, vsrc_mask=mask, sweep=sweep, state0=st0)
+    monkeypatch.setenv("SPICEY_TRAN_CHUNK_BYTES", str(64 * 3001 * 8 * 6))
+    e2 = native.Engine()
+    try:
+        for sel in ([2], [2, 1, 2], []):
+            part = e2.tran_solve(table, dt, steps, vsrc=vsrc, vsrc_mask=mask, sweep=sweep, state0=st0, node_sel=sel)
+            assert part["v"].shape == (steps + 1, len(sel), n)
+            for k, node in enumerate(sel):
+                assert np.array_equal(part["v"][:, k, :], full["v"][:, node - 1, :]), (sel, k)
+            assert np.array_equal(part["ielem"], full["ielem"]) and np.array_equal(part["state"], full["state"])
+            assert np.array_equal(part["status"], full["status"])
+        with pytest.raises(native.NativeError):
+            e2.tran_solve(table, dt, steps, vsrc=vsrc, vsrc_mask=mask, sweep=sweep, state0=st0, node_sel=[3])
+    finally:
+        e2.close()

@@ -32,27 +32,31 @@ function simulateTRAN(ckt: ParsedCircuit) {
     ...ckt.C.map((c) => c.vPrev), ...ckt.L.map((l) => l.iPrev),
     ...S.map((s) => (s.isOn ? 1 : 0)), ...D.map((d) => d.vdPrev),
   ])
-  const { v, ielem, stateOut, status } = tranSolve(table, dt, steps, vsrc, mask, state0)
+  // `.PRINT TRAN` probes (lib/analysis/simulateTRAN.ts:240-249 keeps those node voltages only): the others stay on the GPU
+  const names = ckt.nodes.rev.slice(1)
+  let sel: number[] | undefined
+  if (ckt.probes.tran.length > 0) {
+    const upper = ckt.probes.tran.map((p) => p.toUpperCase())
+    sel = names.flatMap((n, i) => (upper.includes(n.toUpperCase()) ? [i + 1] : []))
+  }
+  const { v, ielem, stateOut, status, nOut } = tranSolve(
+    table, dt, steps, vsrc, mask, state0, sel ? Int32Array.from(sel) : undefined,
+  )
   if (status[0] !== STATUS.OK) throw new Error("Singular matrix (real)")
   let si = 0
   for (const c of ckt.C) c.vPrev = stateOut[si++]!
   for (const l of ckt.L) l.iPrev = stateOut[si++]!
   for (const s of S) s.isOn = stateOut[si++]! !== 0
   for (const d of D) d.vdPrev = stateOut[si++]!
-  const nn = table.nNodes, ne = table.type.length
+  const ne = table.type.length
   const nodeVoltages: Record<string, number[]> = {}
-  ckt.nodes.rev.forEach((name, id) => {
-    if (id !== 0) nodeVoltages[name] = Array.from({ length: S1 }, (_, k) => v[k * nn + id - 1]!)
+  const outIds = sel ?? names.map((_, i) => i + 1)
+  outIds.forEach((id, col) => {
+    nodeVoltages[names[id - 1]!] = Array.from({ length: S1 }, (_, k) => v[k * nOut + col]!)
   })
   const elementCurrents: Record<string, number[]> = {}
   for (let k = 0; k < S1; k++)
     table.names.forEach((name, e) => (elementCurrents[name] ||= []).push(ielem[k * ne + e]!))
-  if (ckt.probes.tran.length > 0) {
-    const upper = ckt.probes.tran.map((p) => p.toUpperCase())
-    const probed: Record<string, number[]> = {}
-    for (const n in nodeVoltages) if (upper.includes(n.toUpperCase())) probed[n] = nodeVoltages[n]!
-    return { times, nodeVoltages: probed, elementCurrents }
-  }
   return { times, nodeVoltages, elementCurrents }
 }
 

@@ -23,6 +23,11 @@ const { symbols: C } = dlopen(LIB_PATH, {
     args: [p, p, p, f64, i64, p, p, p, p, p, p, p, p, u32],
     returns: i32,
   },
+  // (h, table, sweep, dt, steps, waves, vsrc, vsrc_mask, state0, node_sel, n_sel, v, ielem, state_out, iters, status, flags)
+  spicey_tran_solve_probes: {
+    args: [p, p, p, f64, i64, p, p, p, p, p, i32, p, p, p, p, p, u32],
+    returns: i32,
+  },
   // (h, table, sweep, dt, steps, waves, vsrc, state0, v, ielem, state_out, iters, status, flags)
   spicey_tran_solve_waves: {
     args: [p, p, p, f64, i64, p, p, p, p, p, p, p, p, u32],
@@ -133,13 +138,27 @@ export function tranSolve(
   vsrc: Float64Array,
   vsrcMask: Int32Array,
   state0: Float64Array,
+  /** node ids (1-based) whose voltages are wanted — the `.PRINT TRAN` probes: only those rows cross the bus, v is [S1][nodeSel.length] */
+  nodeSel?: Int32Array,
 ) {
   const S1 = steps + 1
-  const v = new Float64Array(S1 * t.nNodes)
+  const nOut = nodeSel ? nodeSel.length : t.nNodes
+  const v = new Float64Array(Math.max(1, S1 * nOut))
   const ielem = new Float64Array(S1 * t.type.length)
   const stateOut = new Float64Array(Math.max(1, t.nState))
   const status = new Int32Array(1)
   const ts = tableStruct(t)
+  if (nodeSel) {
+    check(
+      C.spicey_tran_solve_probes(
+        getHandle(), ptr(ts), null, dt, BigInt(steps), null,
+        vsrc.length ? ptr(vsrc) : null, ptr(vsrcMask),
+        state0.length ? ptr(state0) : null, nodeSel.length ? ptr(nodeSel) : null, nodeSel.length,
+        nodeSel.length ? ptr(v) : null, t.type.length ? ptr(ielem) : null, ptr(stateOut), null, ptr(status), 0,
+      ),
+    )
+    return { v, ielem, stateOut, status, nOut }
+  }
   check(
     C.spicey_tran_solve(
       getHandle(), ptr(ts), null, dt, BigInt(steps),
@@ -148,7 +167,7 @@ export function tranSolve(
       t.type.length ? ptr(ielem) : null, ptr(stateOut), null, ptr(status), 0,
     ),
   )
-  return { v, ielem, stateOut, status }
+  return { v, ielem, stateOut, status, nOut }
 }
 
 /** AC batch: point p = inst * F + k; series-major slabs x[Nvar][P], ielem[nAc][P]. */
