@@ -474,6 +474,7 @@ int prepare_sparse(DeviceCtx& ctx, const HostPlan& hp, double pilot_f, bool eage
 int launch_ac_dense(DeviceCtx& ctx, const HostPlan& hp, const DevPlan& dp, const AcArgs& args, uint32_t flags,
                     cudaStream_t stream, int* tier_out, int64_t* launches);
 
+constexpr long long kTileMinPoints = 4096;    // below this the ~2 s compile of a new (Nvar, shape) dense kernel does not pay off (unless forced)
 constexpr long long kSparseMinPoints = 2048;  // batches from which the sparse program path pays for its host-side analysis
 constexpr size_t kJitMaxOps = 3000;          // larger programs stay on the interpreter (compile time: cfg2's 831 micro-ops take 4 s)
 constexpr int kJitSpareValues = 64;          // cross-phase values the registers can hold beside the shared-memory slots
@@ -815,8 +816,12 @@ int launch_ac_sparse(DeviceCtx& ctx, const HostPlan& hp, const DevPlan& dp, cons
     ctx.sp_jit_fit_key = ctx.sp_key;
     ctx.sp_jit_fits = count_cross_phase_values(ctx.sp) <= (ctx.sp_eager ? ctx.sp_jit_slots_eager : ctx.sp_jit_slots) + kJitSpareValues;
   }
+  // Circuits with inductors change their pivot order along a sweep more often than not (see launch_ac): their first
+  // >= 4,096 points run interpreted, and a kernel is compiled for the topology only once the pilot order has been seen to hold.
+  const bool order_known = ctx.sp.ind_L.empty() || ctx.sp_adapt == 1 || (flags & (SPICEY_FLAG_BAND | SPICEY_FLAG_WARP)) ||
+                           args.p_count < kTileMinPoints;
   const bool want_jit = !(flags & (SPICEY_FLAG_NO_JIT | SPICEY_FLAG_BAND)) && ctx.sp.code.size() <= kJitMaxOps && ctx.sp_jit_fits &&
-                        (args.p_count >= kJitMinPoints || (flags & SPICEY_FLAG_JIT));
+                        order_known && (args.p_count >= kJitMinPoints || (flags & SPICEY_FLAG_JIT));
   DeviceCtx::JitVariant* jv = (want_jit && args.series_ld < (1ll << 32)) ? ensure_jit(ctx, hp, args.ielem != nullptr) : nullptr;
   if (jv) {
     JitArgs j;
@@ -842,7 +847,7 @@ int launch_ac_sparse(DeviceCtx& ctx, const HostPlan& hp, const DevPlan& dp, cons
   }
   // Banded + bordered circuits the thread-per-system compiled kernel does not take (meshes, long ladders): a few
   // lanes per system, register-blocked (band_plan.h / band_kernel.cuh).  Compiled once per band shape and machine.
-  if (!ctx.sp_eager && !(flags & (SPICEY_FLAG_NO_BAND | SPICEY_FLAG_NO_JIT)) && args.series_ld < (1ll << 31) &&
+  if (!ctx.sp_eager && !(flags & (SPICEY_FLAG_NO_BAND | SPICEY_FLAG_NO_JIT)) && args.series_ld < (1ll << 31) && order_known &&
       ((flags & SPICEY_FLAG_BAND) || args.p_count >= kJitMinPoints || (flags & SPICEY_FLAG_JIT))) {
     rc = prepare_band(ctx, hp, stream, (flags & SPICEY_FLAG_BAND) != 0);
     if (rc) return rc;
@@ -948,7 +953,6 @@ struct TileArgs {   // must match tile_kernel.cuh
   int n_ind, n_ent, nn, nV, n_elem, n_ac_elem, off_v, off_v_end, off_i;
 };
 
-constexpr long long kTileMinPoints = 4096;   // below this the ~2 s compile of a new (Nvar, shape) does not pay off (unless forced)
 
 bool tile_shape_for(const DeviceCtx& ctx, const HostPlan& hp, TileShape& sh) {
   const int n_src = hp.nV + hp.nI;
