@@ -1082,25 +1082,29 @@ int warp_lu_sync() {
   if (const char* e = getenv("SPICEY_WARP_LU_SYNC")) return std::max(0, std::min(32, atoi(e)));   // experiments
   return 4;
 }
-size_t warp_lu_smem_bytes(int n) { return sizeof(double2) * (size_t)kWarpLuWarps * (2 * (n + 3) + n + 1); }
-std::string warp_lu_source(int n, int variant) {
-  char head[256];
-  snprintf(head, sizeof head, "#define WL_N %d\n#define WL_WARPS %d\n#define WL_MINB %d\n#define WL_IELEM %d\n#define WL_RC %d\n#define WL_SYNC %d\n",
-           n, kWarpLuWarps, warp_lu_minb(n), variant & 1, (variant >> 2) & 1, warp_lu_sync());
+// per warp: two step records, x; per-instance stamping adds the element admittances, source phasors and the stamped image
+size_t warp_lu_smem_bytes(int n, bool cst, int n_elem, int n_src) {
+  const size_t per_warp = 2 * (size_t)(n + 3) + n + 1 + (cst ? 0 : (size_t)n_elem + std::max(1, n_src) + (size_t)(n + 1) * 32);
+  return sizeof(double2) * (size_t)kWarpLuWarps * per_warp;
+}
+std::string warp_lu_source(int n, int variant, int minb) {
+  char head[320];
+  snprintf(head, sizeof head, "#define WL_N %d\n#define WL_WARPS %d\n#define WL_MINB %d\n#define WL_IELEM %d\n#define WL_CONST %d\n#define WL_RC %d\n#define WL_SYNC %d\n",
+           n, kWarpLuWarps, minb, variant & 1, (variant >> 1) & 1, (variant >> 2) & 1, warp_lu_sync());
   return std::string(head) + kWarpLuKernelSource;
 }
 
-DeviceCtx::TileJit* ensure_warp_lu_jit(DeviceCtx& ctx, int n, int variant) {
+DeviceCtx::TileJit* ensure_warp_lu_jit(DeviceCtx& ctx, int n, int variant, int minb) {
   DeviceCtx::TileJit& jv = ctx.tile_jit[variant & 15];
-  const int shape[5] = {n, kWarpLuWarps, warp_lu_minb(n), variant, warp_lu_sync()};
+  const int shape[5] = {n, kWarpLuWarps, minb, variant, warp_lu_sync()};
   uint64_t key = fnv1a(1469598103934665603ull, shape, sizeof shape);
   if (!key) key = 1;
   if (jv.key == key) return jv.failed ? nullptr : &jv;
   jv.key = key;
   jv.failed = true;
   if (jv.lib) { cudaLibraryUnload(jv.lib); jv.lib = nullptr; jv.kernel = nullptr; }
-  if (!load_jit_kernel(warp_lu_source(n, variant), "spicey_warp_lu_jit", &jv.lib, &jv.kernel, ctx.tl_note)) return nullptr;
-  jv.n = n; jv.tr = 32; jv.tc = 1; jv.warps = kWarpLuWarps; jv.minb = warp_lu_minb(n);
+  if (!load_jit_kernel(warp_lu_source(n, variant, minb), "spicey_warp_lu_jit", &jv.lib, &jv.kernel, ctx.tl_note)) return nullptr;
+  jv.n = n; jv.tr = 32; jv.tc = 1; jv.warps = kWarpLuWarps; jv.minb = minb;
   jv.failed = false;
   ctx.tl_note = "ok";
   return &jv;
@@ -1133,13 +1137,15 @@ int launch_ac_tile(DeviceCtx& ctx, const HostPlan& hp, const DevPlan& dp, const 
   int rc = prepare_tile(ctx, hp, sh, stream);
   if (rc) return rc;
   const bool cst = ctx.tl_dev.has_const && dp.n_inst == 1 && !(flags & SPICEY_FLAG_TILE_GENERIC);
-  // Nvar <= 32 on a plain sweep: one warp per system, the row of a lane in registers (unless a thread grid is forced)
-  bool warp_lu = cst && hp.nvar <= 32 && !getenv("SPICEY_TILE_SHAPE");
+  // Nvar <= 32: one warp per system, the row of a lane in registers (unless a thread grid is forced)
+  const size_t wl_smem = warp_lu_smem_bytes(hp.nvar, cst, hp.n_elem, hp.nV + hp.nI);
+  bool warp_lu = hp.nvar <= 32 && !getenv("SPICEY_TILE_SHAPE") && wl_smem + 1024 <= ctx.smem_optin;
   if (const char* e = getenv("SPICEY_WARP_LU")) warp_lu = warp_lu && atoi(e) != 0;   // experiments
+  const int wl_minb = warp_lu ? std::max(1, std::min<int>(warp_lu_minb(hp.nvar), (int)(ctx.smem_optin / (wl_smem + 1024)))) : 0;
   const int variant = (args.ielem ? 1 : 0) | (cst ? 2 : 0) | (cst && ctx.tl_dev.rc_only ? 4 : 0) | (warp_lu ? 8 : 0);
-  DeviceCtx::TileJit* jv = warp_lu ? ensure_warp_lu_jit(ctx, hp.nvar, variant) : ensure_tile_jit(ctx, sh, variant);
+  DeviceCtx::TileJit* jv = warp_lu ? ensure_warp_lu_jit(ctx, hp.nvar, variant, wl_minb) : ensure_tile_jit(ctx, sh, variant);
   if (!jv) return SPICEY_SUCCESS;
-  const size_t smem = warp_lu ? warp_lu_smem_bytes(hp.nvar)
+  const size_t smem = warp_lu ? wl_smem
                               : tile_smem_bytes(hp.nvar, cst ? 0 : hp.n_elem, cst ? 0 : hp.nV + hp.nI, jv->tr, jv->tc, cst);
   CUDA_TRY(cudaFuncSetAttribute((const void*)jv->kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   unsigned grid = (unsigned)std::min<long long>(warp_lu ? (args.p_count + kWarpLuWarps - 1) / kWarpLuWarps : args.p_count,
@@ -2134,8 +2140,9 @@ int64_t spicey_debug_tile_source(int32_t nvar, int32_t n_elem, int32_t n_src, in
 
 int64_t spicey_debug_warp_lu_source(int32_t nvar, int32_t variant, int32_t* shape_out, char* buf, int64_t cap) {
   if (nvar < 1 || nvar > 32) return -1;
-  if (shape_out) { shape_out[0] = kWarpLuWarps; shape_out[1] = warp_lu_minb(nvar); shape_out[2] = (int32_t)warp_lu_smem_bytes(nvar); }
-  const std::string src = warp_lu_source(nvar, variant);
+  const bool cst = (variant >> 1) & 1;
+  if (shape_out) { shape_out[0] = kWarpLuWarps; shape_out[1] = warp_lu_minb(nvar); shape_out[2] = (int32_t)warp_lu_smem_bytes(nvar, cst, 64, 2); }
+  const std::string src = warp_lu_source(nvar, variant, warp_lu_minb(nvar));
   if (buf && cap > 0) {
     const size_t n = std::min<size_t>(src.size(), (size_t)cap - 1);
     memcpy(buf, src.data(), n);

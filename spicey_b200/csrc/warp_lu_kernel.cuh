@@ -34,6 +34,9 @@ typedef double2 wcplx;
 #ifndef WL_SYNC
 #define WL_SYNC 4
 #endif
+#ifndef WL_CONST
+#define WL_CONST 1                     /* 1: entries from per-topology constants (plain sweep); 0: per-instance values, stamped from the element table */
+#endif
 
 struct TileArgs {   // must match TileArgs in spicey_native.cu (shared with tile_kernel.cuh)
   const double* freqs; long long n_freq, p_begin, p_count;
@@ -55,6 +58,41 @@ __device__ __forceinline__ wcplx wl_mul(wcplx a, wcplx b) {
 __device__ __forceinline__ wcplx wl_submul(wcplx a, wcplx f, wcplx p) {
   return make_double2(fma(-f.x, p.x, fma(f.y, p.y, a.x)), fma(-f.x, p.y, fma(-f.y, p.x, a.y)));
 }
+#if !WL_CONST
+__device__ __forceinline__ double wl_value(const TileArgs& a, int slot, long long inst) {
+  const int v = __ldg(a.var_of_slot + slot);
+  return v < 0 ? __ldg(a.values + slot) : __ldg(a.var_values + (long long)v * a.n_inst + inst);
+}
+// Element admittance at frequency f (simulateAC.ts:36-52) and source phasor (:54-57); returns the status.
+__device__ __forceinline__ int wl_element(const TileArgs& a, int type, int vidx, long long inst, double f, wcplx& Y, wcplx& J) {
+  const double twoPi = 2 * WL_PI;
+  Y = make_double2(0.0, 0.0);
+  J = make_double2(0.0, 0.0);
+  if (type == 0) {          // R
+    const double R = wl_value(a, vidx, inst);
+    if (R <= 0) return 3;   // :37
+    Y.x = 1 / R;
+  } else if (type == 1) {   // C: twoPi * f * c.C  :43
+    Y.y = __dmul_rn(__dmul_rn(twoPi, f), wl_value(a, vidx, inst));
+  } else if (type == 2) {   // L
+    const double d = __dmul_rn(__dmul_rn(twoPi, f), wl_value(a, vidx, inst));
+    if (fabs(d) < WL_EPS) return 0;     // denom.abs() < EPS -> Y = 0  :49
+    const double dd = __dmul_rn(d, d);
+    if (dd < WL_EPS) return 2;          // Complex.div guard (Complex.ts:41-42)
+    Y.x = 0.0 / dd;
+    Y.y = (0.0 - d) / dd;
+  } else if (type == 3 || type == 6) {  // V, I: phasor fromPolar(acMag, acPhaseDeg)  Complex.ts:16-19
+    const double mag = wl_value(a, vidx + 1, inst), deg = wl_value(a, vidx + 2, inst);
+    const double ph = (deg * WL_PI) / 180;
+    double sn, cs;
+    sincos(ph, &sn, &cs);
+    J.x = mag * cs;
+    J.y = mag * sn;
+  }
+  return 0;
+}
+#endif
+
 __device__ __forceinline__ double wl_rcp(double a) {   // MUFU seed + two Newton steps (<= 1 ulp), no slow path
   double y, e;
   asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(a));
@@ -68,8 +106,18 @@ extern __shared__ __align__(16) unsigned char wl_smem[];
 extern "C" __global__ void __launch_bounds__(WL_THREADS, WL_MINB) spicey_warp_lu_jit(const TileArgs a) {
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   // per warp: two step records | x (Nvar + 1 entries, the last one the ground node's zero)
+  //           [| element admittances | source phasors | the stamped image [column][lane = row]: per-instance values only]
+#if WL_CONST
   wcplx* rec = (wcplx*)wl_smem + (size_t)wib * (2 * WL_REC + WL_NC);
   wcplx* xs = rec + 2 * WL_REC;
+#else
+  const int n_src = a.nV + (a.n_elem - a.off_i);
+  wcplx* rec = (wcplx*)wl_smem + (size_t)wib * (2 * WL_REC + WL_NC + a.n_elem + (n_src > 0 ? n_src : 1) + WL_NC * 32);
+  wcplx* xs = rec + 2 * WL_REC;
+  wcplx* Yv = xs + WL_NC;
+  wcplx* Jv = Yv + a.n_elem;
+  wcplx* img = Jv + (n_src > 0 ? n_src : 1);
+#endif
   const long long n_warps = (long long)gridDim.x * WL_WARPS;
   const bool row = lane < WL_N;
 
@@ -85,12 +133,22 @@ extern "C" __global__ void __launch_bounds__(WL_THREADS, WL_MINB) spicey_warp_lu
     bool valid = q0 < work;
     const long long qi = valid ? q0 : work - 1;
     const long long q = a.plist ? a.plist[qi] : qi;
+#if WL_CONST
     const double w = (2 * WL_PI) * a.freqs[a.p_begin + q];
     const double iw = 1.0 / w;
-    if (a.n_ind > 0) {   // inductor guards of simulateAC.ts:47-51: the one-thread-per-row kernel decides
+#else
+    const long long p_abs = a.p_begin + q;
+    const long long inst = p_abs / a.n_freq;
+    const double fq = a.freqs[p_abs - inst * a.n_freq];
+#endif
+    if (WL_CONST && a.n_ind > 0) {   // inductor guards of simulateAC.ts:47-51: the one-thread-per-row kernel decides
       int bad = 0;
       for (int li = lane; li < a.n_ind; li += 32) {
+#if WL_CONST
         const double d = w * a.ind_L[li];
+#else
+        const double d = 1.0;
+#endif
         bad |= (int)(fabs(d) < WL_EPS) | (int)(d * d < WL_EPS);
       }
       if (__any_sync(WL_FULL, bad)) {
@@ -100,6 +158,8 @@ extern "C" __global__ void __launch_bounds__(WL_THREADS, WL_MINB) spicey_warp_lu
     }
     // ---- my row, straight from the constants of the topology (simulateAC.ts:24-60) ----
     wcplx A[WL_NC];
+    int st = 0;
+#if WL_CONST
 #pragma unroll
     for (int j = 0; j < WL_NC; ++j) {
       const size_t o = (size_t)j * 32 + lane;
@@ -111,9 +171,47 @@ extern "C" __global__ void __launch_bounds__(WL_THREADS, WL_MINB) spicey_warp_lu
       A[j] = make_double2(c0.x, fma(w, c1.x, -c1.y * iw) + c0.y);
 #endif
     }
+#else
+    // element admittances of this instance, then gather stamping with one lane per matrix entry (the contributions of
+    // an entry summed in the reference's stamping order), through the warp's image in shared memory
+    __syncwarp();   // the previous point's readers of Yv / xs are done
+    {
+      int st_el = 0;
+      for (int e = lane; e < a.n_elem; e += 32) {
+        const int2 mt = __ldg(a.meta + e);
+        wcplx Y, J;
+        const int s1 = wl_element(a, mt.x, mt.y, inst, fq, Y, J);
+        Yv[e] = Y;
+        if (mt.x == 3) Jv[e - a.off_v] = J;
+        else if (mt.x == 6) Jv[a.nV + (e - a.off_i)] = J;
+        st_el = s1 > st_el ? s1 : st_el;
+      }
+      st = __reduce_max_sync(WL_FULL, st_el);   // R <= 0 (3) outranks the inductor's divide guard (2)
+#pragma unroll
+      for (int j = 0; j < WL_NC; ++j) img[j * 32 + lane] = make_double2(0.0, 0.0);
+      __syncwarp();
+      for (int en = lane; en < a.n_ent; en += 32) {
+        const int rc = __ldg(a.ent_rc + en);
+        const int c_end = __ldg(a.ent_ptr + en + 1);
+        wcplx acc = make_double2(0.0, 0.0);
+        for (int c = __ldg(a.ent_ptr + en); c < c_end; ++c) {
+          const int wd = __ldg(a.contrib + c);
+          const int src = (wd >> 1) & 3, idx = wd >> 3;
+          wcplx v;
+          if (src == 0) v = Yv[idx];
+          else if (src == 1) v = Jv[idx < a.off_v_end ? idx - a.off_v : a.nV + (idx - a.off_i)];
+          else v = make_double2(1.0, 0.0);
+          if (wd & 1) { acc.x -= v.x; acc.y -= v.y; } else { acc.x += v.x; acc.y += v.y; }
+        }
+        img[(rc >> 16) * 32 + (rc & 0xffff)] = acc;
+      }
+      __syncwarp();
+#pragma unroll
+      for (int j = 0; j < WL_NC; ++j) A[j] = img[j * 32 + lane];
+    }
+#endif
     bool done = !row;
     int pos = lane;
-    int st = 0;
     wcplx rdiag = make_double2(0.0, 0.0);
 
     // ---- elimination (solveComplex.ts:15-53), fully unrolled ----
@@ -200,11 +298,23 @@ extern "C" __global__ void __launch_bounds__(WL_THREADS, WL_MINB) spicey_warp_lu
       if (a.ielem) {
         wcplx* io = sld ? a.ielem + q : a.ielem + (size_t)q * a.n_ac_elem;
         for (int e = lane; e < a.n_ac_elem; e += 32) {
+#if WL_CONST
           const double2 lo2 = __ldg((const double2*)(a.el_rec + e)), hi2 = __ldg((const double2*)(a.el_rec + e) + 1);
           const long long ij = __double_as_longlong(lo2.x);
           const wcplx v1 = xs[(int)(ij & 0xffffffffll)], v2 = xs[(int)(ij >> 32)];
           const wcplx Y = make_double2(lo2.y, fma(w, hi2.x, -hi2.y * iw));
           io[e * xst] = st == 0 ? wl_mul(Y, make_double2(v1.x - v2.x, v1.y - v2.y)) : nanv;
+#else
+          wcplx cur;
+          if (e >= a.off_v) {
+            cur = xs[a.nn + (e - a.off_v)];
+          } else {
+            const int4 en = __ldg(a.ends + e);
+            const wcplx v1 = xs[en.x == 0 ? WL_N : en.x - 1], v2 = xs[en.y == 0 ? WL_N : en.y - 1];
+            cur = wl_mul(Yv[e], make_double2(v1.x - v2.x, v1.y - v2.y));
+          }
+          io[e * xst] = st == 0 ? cur : nanv;
+#endif
         }
       }
 #endif

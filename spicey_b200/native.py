@@ -193,11 +193,11 @@ def tile_kernel_source(nvar: int, n_elem: int = 0, n_src: int = 1, tr: int = 0, 
     return buf.value.decode(), dict(zip(keys, list(shp)))
 
 
-def warp_lu_kernel_source(nvar: int, with_ielem=True, rc_only=False):
+def warp_lu_kernel_source(nvar: int, with_ielem=True, rc_only=False, const_tables=True):
     """(CUDA source, shape dict) of the one-warp-per-system dense LU (tier 9, Nvar <= 32); None above 32.  Host-only tooling."""
     lib = load_library()
     shp = (C.c_int32 * 3)()
-    args = (nvar, (1 if with_ielem else 0) | 2 | (4 if rc_only else 0), shp)
+    args = (nvar, (1 if with_ielem else 0) | (2 if const_tables else 0) | (4 if rc_only else 0), shp)
     need = lib.spicey_debug_warp_lu_source(*args, None, 0)
     if need < 0:
         return None

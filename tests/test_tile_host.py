@@ -54,14 +54,15 @@ def test_tile_kernel_compiles_within_its_register_budget(tmp_path, nvar, tr, tc,
     assert int(m.group(1)) * threads * sh["ctas_per_sm"] <= 65536, (m.group(1), sh)
 
 
-@pytest.mark.parametrize("nvar,rc_only", [(32, True), (17, False), (3, True)])
-def test_warp_lu_kernel_compiles_within_its_register_budget(tmp_path, nvar, rc_only):
+@pytest.mark.parametrize("nvar,rc_only,const_tables", [(32, True, True), (17, False, True), (3, True, True), (32, False, False), (9, False, False)])
+def test_warp_lu_kernel_compiles_within_its_register_budget(tmp_path, nvar, rc_only, const_tables):
     """The one-warp-per-system dense LU (Nvar <= 32): a lane's row in registers at the occupancy the host asks for."""
     nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
     if not os.path.exists(nvcc):
         pytest.skip("nvcc not found")
     assert native.warp_lu_kernel_source(33) is None
-    src, sh = native.warp_lu_kernel_source(nvar, rc_only=rc_only)
+    src, sh = native.warp_lu_kernel_source(nvar, rc_only=rc_only, const_tables=const_tables)
+    assert "#define WL_CONST %d\n" % const_tables in src
     assert "#define WL_N %d\n" % nvar in src and "spicey_warp_lu_jit" in src and "__reduce_max_sync" in src
     cu = tmp_path / "wlu.cu"
     cu.write_text(src)
