@@ -96,6 +96,10 @@ __device__ __forceinline__ double tl_rcp(double a) {   // MUFU seed + two Newton
 __device__ __forceinline__ void tl_sts(tcplx* p, tcplx v) {
   asm volatile("st.shared.v2.f64 [%0], {%1, %2};" ::"r"((unsigned)__cvta_generic_to_shared(p)), "d"(v.x), "d"(v.y));
 }
+template <int OFF>   // ... with a compile-time byte offset folded into the instruction
+__device__ __forceinline__ void tl_sts_at(unsigned base, tcplx v) {
+  asm volatile("st.shared.v2.f64 [%0 + %3], {%1, %2};" ::"r"(base), "d"(v.x), "d"(v.y), "n"(OFF));
+}
 __device__ __forceinline__ void tl_sts1(void* p, int a) {
   asm volatile("st.shared.b32 [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(p)), "r"(a));
 }
@@ -149,22 +153,31 @@ struct TileCtx {   // what the step functions need besides the tile
 // as `v > vmax` never holds for it in JavaScript), redux.sync.max over the high words of the IEEE bit patterns and, when a
 // single lane holds that maximum (the usual case), one shuffle of its row index; ties go through the low words and the
 // lowest row index.
+template <int KR, int M>
+__device__ __forceinline__ void tl_search_rows(const TileCtx& t, int k, const tcplx (&col)[TL_MR], bool owner, unsigned cb,
+                                               double& bm, int& bi, bool& nanp) {
+  if (M >= TL_MR) return;
+  constexpr int MM = M < TL_MR ? M : TL_MR - 1;
+  const int i = MM * TL_TR + t.tr;
+  if (owner) tl_sts_at<MM * TL_TR * 16>(cb, col[MM]);
+  const tcplx v = col[MM];
+  const double mt = fma(v.x, v.x, v.y * v.y);
+  const bool in = owner && i >= k && i < TL_N;
+  if (in && mt > bm) { bm = mt; bi = i; }          // ascending i, strict >: the first maximum (a NaN never passes)
+  nanp = nanp || (in && i == k && mt != mt);       // ... except in place: JS keeps a NaN vmax (v > NaN never holds)
+  tl_search_rows<KR, (M < TL_MR ? M + 1 : M)>(t, k, col, owner, cb, bm, bi, nanp);
+}
+
 template <int KR>
 __device__ __forceinline__ void tl_search(const TileCtx& t, int k, const tcplx (&col)[TL_MR], bool owner) {
   const int par = k & 1;
+  const unsigned cb = (unsigned)__cvta_generic_to_shared(t.Cb + par * (TL_NP + 1) + t.tr);
   double bm = -1.0;
   int bi = 0x7fffffff;
-#pragma unroll
-  for (int m = KR; m < TL_MR; ++m) {
-    const int i = m * TL_TR + t.tr;
-    if (owner) tl_sts(t.Cb + par * (TL_NP + 1) + i, col[m]);
-    const tcplx v = col[m];
-    const double mt = fma(v.x, v.x, v.y * v.y);
-    const bool in = owner && i >= k && i < TL_N;
-    const bool take = in && ((i == k) ? !(mt <= bm) : (mt > bm));
-    if (take) { bm = mt; bi = i; }
-  }
-  const unsigned long long key = bi == 0x7fffffff ? 0ull : (unsigned long long)__double_as_longlong(bm);
+  bool nanp = false;
+  tl_search_rows<KR, KR>(t, k, col, owner, cb, bm, bi, nanp);
+  unsigned long long key = bi == 0x7fffffff ? 0ull : (unsigned long long)__double_as_longlong(bm);
+  if (nanp) { key = ~0ull; bi = k; }
   const unsigned hi = (unsigned)(key >> 32), lo = (unsigned)key;
   const unsigned mh = __reduce_max_sync(TL_FULL, hi);
   const unsigned tie = __ballot_sync(TL_FULL, hi == mh);
@@ -186,15 +199,12 @@ template <int KR, int KC>
 __device__ __forceinline__ void tl_update(const TileCtx& t, int k, int p, bool own, tcplx (&A)[TL_MR][TL_MC], const tcplx (&F)[TL_MR]) {
   const int trk = k - KR * TL_TR;
   const bool patch = p != k && t.tr == trk;      // position k takes the pivot row (F of row k is 0)
-  if (own) {
-    constexpr int KC1 = KC + 1 < TL_MC ? KC + 1 : KC;
-    const bool nxt = k + 1 >= (KC + 1) * TL_TC;           // column k + 1 opens local column KC + 1
-    const int c1 = nxt ? KC + 1 : KC;
-    const tcplx pv1 = t.Pb[c1 * TL_TC + t.tc];
+  if (own) {   // (column k + 1 is local column KC of its thread column: the first column of a block is searched at the block's start)
+    const tcplx pv1 = t.Pb[KC * TL_TC + t.tc];
     tcplx col1[TL_MR];
 #pragma unroll
-    for (int m = KR; m < TL_MR; ++m) col1[m] = tl_submul(nxt ? A[m][KC1] : A[m][KC], F[m], pv1);
-    tl_search<KR>(t, k + 1, col1, t.act && t.tc == k + 1 - c1 * TL_TC);
+    for (int m = KR; m < TL_MR; ++m) col1[m] = tl_submul(A[m][KC], F[m], pv1);
+    tl_search<KR>(t, k + 1, col1, t.act && t.tc == k + 1 - KC * TL_TC);
   }
 #pragma unroll
   for (int c = KC; c < TL_MC; ++c) {
@@ -244,6 +254,14 @@ __device__ __forceinline__ void tl_segment(const TileCtx& t, tcplx (&A)[TL_MR][T
   if (k0 >= k1) return;
   const int tr = t.tr, tc = t.tc, warp = t.warp;
   tcplx *Cb = t.Cb, *Pb = t.Pb, *Kb = t.Kb, *Rd = t.Rd;
+  if (k0 == KC * TL_TC && status == 0) {   // column k0 opens local column KC: nobody searched it during step k0 - 1
+    if (warp == 0) {
+      tcplx col0[TL_MR];
+#pragma unroll
+      for (int m = KR; m < TL_MR; ++m) col0[m] = A[m][KC];
+      tl_search<KR>(t, k0, col0, t.act && tc == 0);
+    }
+  }
 #pragma unroll 1
   for (int k = k0; k < k1; ++k) {
     if (status != 0) break;
@@ -285,9 +303,10 @@ __device__ __forceinline__ void tl_segment(const TileCtx& t, tcplx (&A)[TL_MR][T
       F[m] = fm;
     }
     if (p != k) tl_row_in<KR, KC, KR>(A, mp, tr == trp, Kb, tc);
-    // column k + 1 belongs to thread column (k + 1) mod TC: (k + 1) - KC TC, or 0 when it opens local column KC + 1
-    const int tck1 = (k + 1 >= (KC + 1) * TL_TC) ? 0 : k + 1 - KC * TL_TC;
-    tl_update<KR, KC>(t, k, p, k + 1 < TL_N && warp == tck1 / TL_TPW, A, F);
+    // column k + 1 belongs to thread column (k + 1) - KC TC while it is local column KC; the warp that owns it searches it
+    // during this step (the first column of the next block is searched at that block's start: it sits in other registers)
+    const int tck1 = k + 1 - KC * TL_TC;
+    tl_update<KR, KC>(t, k, p, k + 1 < TL_N && tck1 < TL_TC && warp == tck1 / TL_TPW, A, F);
   }
 }
 
@@ -432,12 +451,6 @@ extern "C" __global__ void __launch_bounds__(TL_THREADS, TL_MINB) spicey_tile_ji
 
     if (status == 0) {
       // ---- elimination (solveComplex.ts:15-53) ----
-      if (warp == 0) {   // search of step 0 (every later search is done during the step before it)
-        tcplx col0[TL_MR];
-#pragma unroll
-        for (int m = 0; m < TL_MR; ++m) col0[m] = A[m][0];
-        tl_search<0>(t, 0, col0, t.act && tc == 0);
-      }
       TlSeg<0, 0>::run(t, A, status);
     }
 
