@@ -327,7 +327,8 @@ int32_t spicey_debug_warp_stats(const spicey_elem_table* table, double pilot_f, 
 int32_t spicey_debug_band_stats(const spicey_elem_table* table, double pilot_f, int32_t* out);
 
 /* Tooling (no device needed): the CUDA source NVRTC compiles for one band shape; returns the size needed.
- * abmask: bits 0-15 active border columns of band rows, bit 16: (alpha, beta)-only tables (RC circuits). */
+ * abmask: bits 0-15 active border columns of band rows, bit 16: (alpha, beta)-only tables (RC circuits),
+ * bits 17-18: how the pivot rows reach the workspace (0 plain stores, 1 paired 32-byte stores, 2 TMA tensor store). */
 int64_t spicey_debug_band_source(int32_t L, int32_t RPL, int32_t NB, uint32_t abmask, int32_t with_ielem, int32_t warps,
                                  int32_t minb, char* buf, int64_t cap);
 

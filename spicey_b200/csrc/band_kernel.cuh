@@ -17,6 +17,14 @@
 //   BAND_WARPS    warps per CTA,  BAND_MINB  CTAs per SM (launch bounds)
 //   BAND_RC       1: tables hold (alpha, beta) only (no inductors, real source phasors)
 //   BAND_SYNC     n > 0: the warps of a CTA meet at a barrier n times per W steps (instruction-cache locality)
+//   BAND_UMODE    how the pivot rows (U) leave for the workspace:
+//                 0  one STG.128 per entry from the lane that owns the column: a warp's 32 lanes write 32 different
+//                    128-byte lines per instruction (the workspace is column-major for the back-substitution)
+//                 2  (W >= 4) the pivot record itself is the source of a TMA tensor store (cp.async.bulk.tensor.3d, one
+//                    instruction per warp and step, issued by lane 0): the record of a warp's systems is laid out
+//                    [column][system] in shared memory, the tensor map (second kernel parameter) describes the
+//                    workspace as (row slot, system, column), box = one row slot x the warp's systems x W columns.
+//                    No load / store unit cycle is spent on U.
 //
 // Mapping.  One group of L lanes owns one system.  Pivot step k (column k, pivot row k of the pilot's order) touches
 // the W rows k+1 .. k+W: row i lives in lane i mod L, row slot (i / L) mod RPL, as W band entries (column c in
@@ -49,9 +57,21 @@
 #ifndef BAND_SYNC
 #define BAND_SYNC 1
 #endif
+#ifndef BAND_UMODE
+#define BAND_UMODE 0
+#endif
+#define BAND_TMA (BAND_UMODE == 2)
 #define BW (BAND_L * BAND_RPL)
 #define BNB BAND_NB
 #define BPS (BW + BNB + 2)          /* pivot record: W band entries | NB border columns | rhs | diagonal */
+#define BPX (BNB + 2)               /* the part of it that stays per system under BAND_TMA */
+#define BPBUF (BAND_TMA ? 4 : 2)    /* pivot records alive: the tensor store reads a record up to 2 steps later */
+#if BAND_UMODE != 0 && BAND_UMODE != 2
+#error "BAND_UMODE is 0 or 2"
+#endif
+#if BAND_TMA && BW < 4
+#error "BAND_UMODE 2 needs W >= 4 (the record buffer of step k is k mod 4 = s mod 4)"
+#endif
 // per-step record of the stamp tables (entries): new column [W] | column k+1 [W] | entering row: entry (k+W, k),
 // border columns + rhs [NB+1] | border rows' new column [NB]; padded to a multiple of 8 entries
 #define BST_NC 0
@@ -81,7 +101,17 @@ struct BandArgs {   // must match BandArgs in spicey_native.cu
   const double* ind_L;
   int n, nb, n_out, n_ac_elem, n_ind;           // n = nb + NB unknowns incl. padding (nb: a multiple of W), n_out: the circuit's own
   int o_init, o_initb, o_brd0, o_bb0, o_step;   // table offsets (entries); o_step: record of step 0
+  unsigned long long* prof;                     // BAND_PROF: cycles of [stamping | elimination | back-substitution | results], summed over warps
 };
+#ifndef BAND_PROF
+#define BAND_PROF 0
+#endif
+
+#if BAND_PROF
+#define BAND_TICK(i) { const long long t_ = clock64(); if (lane == 0) atomicAdd(a.prof + (i), (unsigned long long)(t_ - tick)); tick = t_; }
+#else
+#define BAND_TICK(i)
+#endif
 
 typedef double2 bcplx;
 
@@ -139,9 +169,14 @@ __device__ __forceinline__ void band_stage(double2* dst, const double2* src, int
   asm volatile("cp.async.commit_group;" ::: "memory");
 }
 
-extern __shared__ double2 band_sm[];
+extern __shared__ __align__(128) double2 band_sm[];
 
+#if BAND_TMA
+struct __align__(64) BandTmap { unsigned long long opaque[16]; };   // a CUtensorMap (cuTensorMapEncodeTiled, spicey_native.cu)
+extern "C" __global__ void __launch_bounds__(BAND_WARPS * 32, BAND_MINB) spicey_band_jit(BandArgs a, const __grid_constant__ BandTmap tm) {
+#else
 extern "C" __global__ void __launch_bounds__(BAND_WARPS * 32, BAND_MINB) spicey_band_jit(BandArgs a) {
+#endif
   const unsigned FULL = 0xffffffffu;
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   // The groups of a warp are interleaved: lane = l * (32 / L) + g.  The owners of one row in the 32 / L systems of a
@@ -150,14 +185,34 @@ extern "C" __global__ void __launch_bounds__(BAND_WARPS * 32, BAND_MINB) spicey_
   const int g = lane % BGPW;                  // group (system) within the warp
   const int l = lane / BGPW;                  // lane within the group
   const int n = a.n, nb = a.nb;
-  // shared memory: per warp a ring of BRING step records; per group x in elimination order | two pivot records
-  double2* ring = band_sm + (size_t)wib * (BRING * BST_STRIDE * BREC);
+  // shared memory: [BAND_TMA: per warp BPBUF pivot records [column][system], the TMA sources, 128-byte aligned |]
+  // per warp a ring of BRING step records; per group x in elimination order | the pivot records
+#if BAND_TMA
+  double2* PRw = band_sm + (size_t)wib * (BPBUF * BW * BGPW);   // W BGPW 16 = 512 RPL bytes per record
+  double2* PR = PRw + g;
+  double2* band_sm1 = band_sm + (size_t)BAND_WARPS * (BPBUF * BW * BGPW);
+  const int grp0 = (blockIdx.x * BAND_WARPS + wib) * BGPW;      // first system of this warp: the box's system coordinate
+#else
+  double2* band_sm1 = band_sm;
+#endif
+  double2* ring = band_sm1 + (size_t)wib * (BRING * BST_STRIDE * BREC);
   // x[n] is a zero (the ground node of the element records).  The stride is odd (in 16-byte units): the systems of a
   // warp read and write the same offsets of their areas in one instruction, and an odd stride puts up to eight of
   // them on eight different 16-byte bank groups (an even stride of 296 units made every access a 4-way conflict)
-  const int sys_stride = (n + 1 + 2 * BPS) | 1;
-  double2* xs = band_sm + (size_t)BAND_WARPS * (BRING * BST_STRIDE * BREC) + (size_t)(wib * BGPW + g) * sys_stride;
+  const int sys_stride = (n + 1 + (BAND_TMA ? 2 * BPX : BPBUF * BPS)) | 1;
+  double2* xs = band_sm1 + (size_t)BAND_WARPS * (BRING * BST_STRIDE * BREC) + (size_t)(wib * BGPW + g) * sys_stride;
   double2* Pb = xs + n + 1;
+  // The pivot record of the step at unroll position s_ (s_ = k mod W; W is a multiple of BPBUF, so the buffer index is
+  // a constant of the unrolled code): P_BAND(s_, t) = the entry in column slot t, P_EXT(s_, j) = border column j |
+  // rhs (j = NB) | diagonal (j = NB + 1).  Under BAND_TMA the band part is stored by column, (t - s_ - 1) mod W =
+  // the column's distance from k + 1, which is the order the tensor store wants and still a constant.
+#if BAND_TMA
+#define P_BAND(s_, t) PR[((((s_) & (BPBUF - 1)) * BW) + (((t) - (s_) - 1) & (BW - 1))) * BGPW]
+#define P_EXT(s_, j) Pb[((s_) & 1) * BPX + (j)]
+#else
+#define P_BAND(s_, t) Pb[((s_) & (BPBUF - 1)) * BPS + (t)]
+#define P_EXT(s_, j) Pb[((s_) & (BPBUF - 1)) * BPS + BW + (j)]
+#endif
   const long long n_groups = (long long)gridDim.x * BAND_WARPS * BGPW;
   const long long grp = ((long long)blockIdx.x * BAND_WARPS + wib) * BGPW + g;
   double2* Gu = a.G + grp * a.g_stride;                 // [(nb + W) columns][W]
@@ -168,7 +223,13 @@ extern "C" __global__ void __launch_bounds__(BAND_WARPS * 32, BAND_MINB) spicey_
   // Rows above the matrix (the first W unknowns have fewer than W rows above them): their U entries are read as
   // zeros by the back-substitution and never written by anybody, so one fill per launch is enough.
   for (int q = l; q < BW * BW; q += BAND_L) Gu[q] = make_double2(0.0, 0.0);
-  for (int q = l; q < 2 * BPS; q += BAND_L) Pb[q] = make_double2(0.0, 0.0);
+#if BAND_TMA
+  for (int q = l; q < 2 * BPX; q += BAND_L) Pb[q] = make_double2(0.0, 0.0);
+  for (int q = lane; q < BPBUF * BW * BGPW; q += 32) PRw[q] = make_double2(0.0, 0.0);
+  asm volatile("fence.proxy.async;" ::: "memory");   // the fill above precedes the tensor stores to the same lines
+#else
+  for (int q = l; q < BPBUF * BPS; q += BAND_L) Pb[q] = make_double2(0.0, 0.0);
+#endif
   if (l == 0) xs[n] = make_double2(0.0, 0.0);
   __syncwarp();
 
@@ -180,6 +241,9 @@ extern "C" __global__ void __launch_bounds__(BAND_WARPS * 32, BAND_MINB) spicey_
     const long long p = valid ? base + g : a.p_count - 1;
     const double w = B_TWO_PI * a.freqs[p];
     const double iw = 1.0 / w;
+#if BAND_PROF
+    long long tick = clock64();
+#endif
 #define REC(idx) band_rec(tab, (idx), w, iw)
     const double2* steps = tab + (size_t)a.o_step * BREC;
     __syncwarp();   // the previous system is done with the ring
@@ -215,18 +279,21 @@ extern "C" __global__ void __launch_bounds__(BAND_WARPS * 32, BAND_MINB) spicey_
       for (int j = 0; j <= BNB; ++j) BB[b][j] = REC(a.o_bb0 + b * (BNB + 1) + j);
     }
     __syncwarp();   // the previous system's readers of the pivot records and of xs are done
+#if BAND_TMA
+    asm volatile("fence.proxy.async;" ::: "memory");   // the previous system's reads of the workspace precede this one's tensor stores
+#endif
     if (l == 0) {   // row 0 is the first pivot row
-      double2* P0 = Pb;
-      P0[BW + BNB + 1] = A[0][0];
+      P_EXT(0, BNB + 1) = A[0][0];
 #pragma unroll
-      for (int t = 1; t < BW; ++t) P0[t] = A[0][t];
-      P0[0] = REC(a.o_step + BST_NC + 0);          // a[0][W]: column W enters with step 0
+      for (int t = 1; t < BW; ++t) P_BAND(0, t) = A[0][t];
+      P_BAND(0, 0) = REC(a.o_step + BST_NC + 0);          // a[0][W]: column W enters with step 0
 #pragma unroll
       for (int j = 0; j <= BNB; ++j)
-        if (j == BNB || ((BAND_ABMASK >> j) & 1)) P0[BW + j] = AB[0][j];
+        if (j == BNB || ((BAND_ABMASK >> j) & 1)) P_EXT(0, j) = AB[0][j];
     }
     __syncwarp();
 
+    BAND_TICK(0)
     // ---- elimination of the band columns ----
     for (int kb = 0; kb < nb; kb += BW) {
 #pragma unroll
@@ -244,17 +311,29 @@ extern "C" __global__ void __launch_bounds__(BAND_WARPS * 32, BAND_MINB) spicey_
         if (k < nb) {
           const int pl = s % BAND_L, rs = s / BAND_L;              // owner lane / row slot of rows = s (mod W)
           const int s1 = (s + 1) % BW, pl1 = s1 % BAND_L, rs1 = s1 / BAND_L;
-          const double2* Pc = Pb + (s & 1) * BPS;                  // W is even: the parity of k is the parity of s
-          double2* Pn = Pb + ((s + 1) & 1) * BPS;
           // records k and k + 1 have landed (all but the newest cp.async group), record k + 2 leaves now; the barrier
           // also publishes the pivot record written at the end of the previous step
           band_stage(ring + ((k + 2) & (BRING - 1)) * (BST_STRIDE * BREC), steps + (size_t)(k + 2) * (BST_STRIDE * BREC), lane);
           asm volatile("cp.async.wait_group 1;" ::: "memory");
+#if BAND_TMA
+          // the owners' stores of record k become visible to the async proxy; the tensor store of record k - 3 has read
+          // its buffer, which record k + 1 takes at the end of this step
+          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+          if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 2;" ::: "memory");
+#endif
           __syncwarp();
+#if BAND_TMA
+          if (lane == 0) {   // U row k: columns k + 1 .. k + W of row slot s, for the BGPW systems of this warp
+            const unsigned src = (unsigned)__cvta_generic_to_shared(PRw + (s & (BPBUF - 1)) * (BW * BGPW));
+            asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.tile.bulk_group [%0, {%1, %2, %3}], [%4];"
+                         ::"l"((unsigned long long)&tm), "r"(2 * s), "r"(grp0), "r"(k + 1), "r"(src) : "memory");
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+          }
+#endif
           const double2* rk = ring + (k & (BRING - 1)) * (BST_STRIDE * BREC);
           const double2* rk1 = ring + ((k + 1) & (BRING - 1)) * (BST_STRIDE * BREC);
 #define RECS(off) band_rec_sm(rk, (off), w, iw)
-          const bcplx dg = Pc[BW + BNB + 1];
+          const bcplx dg = P_EXT(s, BNB + 1);
           const uint2 fl = *(const uint2*)(rk + BST_FLAGS * BREC);
           const double mp = band_mag(dg);
           bad |= (unsigned)!(mp >= B_EPS);            // singular / Complex.div guard / NaN
@@ -305,14 +384,14 @@ extern "C" __global__ void __launch_bounds__(BAND_WARPS * 32, BAND_MINB) spicey_
           // the update: a_ij -= f_i * u_kj
 #pragma unroll
           for (int t = 0; t < BW; ++t) {
-            const bcplx pt = Pc[t];
+            const bcplx pt = P_BAND(s, t);
 #pragma unroll
             for (int q = 0; q < BAND_RPL; ++q) A[q][t] = band_submul(A[q][t], F[q], pt);
           }
 #pragma unroll
           for (int j = 0; j <= BNB; ++j)
             if (j == BNB || ((BAND_ABMASK >> j) & 1)) {
-              const bcplx pt = Pc[BW + j];
+              const bcplx pt = P_EXT(s, j);
 #pragma unroll
               for (int q = 0; q < BAND_RPL; ++q) AB[q][j] = band_submul(AB[q][j], F[q], pt);
 #pragma unroll
@@ -323,29 +402,37 @@ extern "C" __global__ void __launch_bounds__(BAND_WARPS * 32, BAND_MINB) spicey_
 #pragma unroll
           for (int q = 0; q < BAND_RPL; ++q) {
             const int slot = l + BAND_L * q;
-            const bcplx pt = Pc[slot];
+#if BNB > 0 || BAND_UMODE != 2
+            const bcplx pt = P_BAND(s, slot);
+#endif
 #pragma unroll
             for (int b = 0; b < BNB; ++b) BR[b][q] = band_submul(BR[b][q], FB[b], pt);
+#if BAND_UMODE == 0
             const int c = k + 1 + ((slot - s - 1) & (BW - 1));
             __stcg(Gu + (size_t)c * BW + s, pt);
+#endif
           }
           if (l == pl) __stcg(Gr + k, r);
           // row k + 1 is final: its owner publishes it as the next pivot record
           if (l == pl1) {
-            Pn[BW + BNB + 1] = A[rs1][s1];
+            P_EXT(s + 1, BNB + 1) = A[rs1][s1];
 #pragma unroll
             for (int t = 0; t < BW; ++t)
-              if (t != s1) Pn[t] = A[rs1][t];
-            Pn[s1] = band_rec_sm(rk1, BST_NC + s1, w, iw);    // a[k+1][k+1+W]
+              if (t != s1) P_BAND(s + 1, t) = A[rs1][t];
+            P_BAND(s + 1, s1) = band_rec_sm(rk1, BST_NC + s1, w, iw);    // a[k+1][k+1+W]
 #pragma unroll
             for (int j = 0; j <= BNB; ++j)
-              if (j == BNB || ((BAND_ABMASK >> j) & 1)) Pn[BW + j] = AB[rs1][j];
+              if (j == BNB || ((BAND_ABMASK >> j) & 1)) P_EXT(s + 1, j) = AB[rs1][j];
           }
 #undef RECS
         }
       }
     }
     asm volatile("cp.async.wait_group 0;" ::: "memory");
+    BAND_TICK(1)
+#if BAND_TMA
+    if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // every U row is in the workspace
+#endif
 
     // ---- the border block: NB x NB, replicated; same verification ----
     bcplx RB[BNB > 0 ? BNB : 1];
@@ -375,7 +462,10 @@ extern "C" __global__ void __launch_bounds__(BAND_WARPS * 32, BAND_MINB) spicey_
       XB[b] = band_mul(acc, RB[b]);
       if (l == 0) xs[nb + b] = XB[b];
     }
-    __syncwarp();   // the workspace written by other lanes of the group is visible
+    __syncwarp();   // the workspace written by other lanes of the group (BAND_TMA: by lane 0's tensor stores) is visible
+#if BAND_TMA
+    asm volatile("fence.proxy.async;" ::: "memory");
+#endif
 
     // ---- back-substitution, column oriented: x_j by its owner, then every row of column j takes its term ----
     // row i: lane i mod L, slot (i / L) mod RPL, accumulator = b_i - sum over the border columns - sum_j u_ij x_j
@@ -451,6 +541,7 @@ extern "C" __global__ void __launch_bounds__(BAND_WARPS * 32, BAND_MINB) spicey_
 #undef BAND_BSTEP
     }
     __syncwarp();
+    BAND_TICK(2)
 
     // ---- status, results (simulateAC.ts:85-126) ----
     const unsigned vote = __ballot_sync(FULL, bad != 0u);
@@ -499,6 +590,7 @@ extern "C" __global__ void __launch_bounds__(BAND_WARPS * 32, BAND_MINB) spicey_
       }
 #endif
     }
+    BAND_TICK(3)
 #undef REC
   }
 }

@@ -8,6 +8,8 @@
 // entry point fails with SPICEY_ERR_NO_DEVICE.
 #include "../../include/spicey_native.h"
 
+#include <cuda.h>   // CUtensorMap types only: cuTensorMapEncodeTiled is reached through cudaGetDriverEntryPoint (no libcuda link)
+
 #include <algorithm>
 #include <chrono>
 #include <cstdio>
@@ -129,8 +131,10 @@ struct DeviceCtx {
     uint64_t key = 0;
     bool failed = false;
     int warps = 0, minb = 0;
+    int umode = 0;            // BAND_UMODE of band_kernel.cuh: how U leaves for the workspace (2 = TMA tensor store)
     size_t smem_bytes = 0;
   } band_jit[2];              // [0] without, [1] with element currents
+  bool band_tma_refused = false;   // cuTensorMapEncodeTiled unavailable or refused the workspace: BAND_UMODE 2 -> 0
   // dense register-tile tier (tile_kernel.cuh): per-entry gather lists of the last topology and the compiled kernels
   Buffer tl_blob;
   uint64_t tl_key = 0;        // plan key the entry lists were uploaded for (0 = none)
@@ -638,12 +642,14 @@ struct BandArgs {   // must match band_kernel.cuh
   const double* ind_L;
   int n, nb, n_out, n_ac_elem, n_ind;
   int o_init, o_initb, o_brd0, o_bb0, o_step;
+  unsigned long long* prof;
 };
 
 // Half-bandwidth from which the banded tier beats the interpreted thread-per-system program (measured, tools/tier_sweep.py,
 // 200,000 points: mesh4 (W 4) 567 against 440 M solves/s, mesh6 138 / 97, mesh8 87 / 25, mesh16 11.9 / 1.45; but mesh3 (W 3)
 // 735 / 1,124 and the 400-node ladder (W 1) 14 / 38: a step of the band kernel costs ~150 instructions whatever the width)
 constexpr int kBandMinBandwidth = 4;
+constexpr int kBandUModeDefault = 2;   // band_kernel.cuh BAND_UMODE: the pivot rows leave through the TMA unit
 
 void band_input(const HostPlan& hp, const SparseProgram& sp, double pilot_f, BandInput& in) {
   in.n = hp.nvar; in.nn = hp.nn; in.nV = hp.nV;
@@ -718,34 +724,65 @@ int band_sync_default() {
   return 1;
 }
 
-std::string band_source(const BandPlan& bp, bool with_ielem, int warps, int minb) {
+// How the pivot rows (U) reach the workspace (BAND_UMODE of band_kernel.cuh).  The column-major workspace makes the plain
+// store (0) touch 32 lines per instruction; the tensor store (2) takes the pivot record from shared memory through the
+// TMA unit instead; 1 pairs two steps into one 32-byte store per lane.
+typedef CUresult (*TensorMapEncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                           const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                           CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+TensorMapEncodeTiledFn tensor_map_encoder() {
+  static TensorMapEncodeTiledFn fn = [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q = cudaDriverEntryPointSymbolNotFound;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess) {
+      cudaGetLastError();
+      p = nullptr;
+    }
+    return (TensorMapEncodeTiledFn)p;
+  }();
+  return fn;
+}
+
+int band_umode(const DeviceCtx& ctx, const BandPlan& bp) {
+  int m = kBandUModeDefault;
+  if (const char* e = getenv("SPICEY_BAND_UMODE")) m = atoi(e) == 2 ? 2 : 0;   // experiments
+  if (bp.W < 4) m = 0;
+  if (m == 2 && (ctx.band_tma_refused || !tensor_map_encoder())) m = 0;
+  return m;
+}
+
+std::string band_source(const BandPlan& bp, bool with_ielem, int warps, int minb, int umode) {
   char head[512];
   snprintf(head, sizeof head,
            "#define BAND_L %d\n#define BAND_RPL %d\n#define BAND_NB %d\n#define BAND_ABMASK %uu\n#define BAND_IELEM %d\n"
-           "#define BAND_WARPS %d\n#define BAND_MINB %d\n#define BAND_RC %d\n#define BAND_SYNC %d\n",
-           bp.L, bp.RPL, bp.NB, bp.abmask, with_ielem ? 1 : 0, warps, minb, bp.rc_only ? 1 : 0, band_sync_default());
+           "#define BAND_WARPS %d\n#define BAND_MINB %d\n#define BAND_RC %d\n#define BAND_SYNC %d\n#define BAND_UMODE %d\n#define BAND_PROF %d\n",
+           bp.L, bp.RPL, bp.NB, bp.abmask, with_ielem ? 1 : 0, warps, minb, bp.rc_only ? 1 : 0, band_sync_default(), umode,
+           getenv("SPICEY_BAND_PROF") ? 1 : 0);
   return std::string(head) + kBandKernelSource;
 }
 
-// Shared memory of one CTA: per warp the ring of staged step records, per system the solution vector and two pivot records.
-size_t band_smem_bytes(const BandPlan& bp, int warps) {
+// Shared memory of one CTA: per warp the ring of staged step records, per system the solution vector and the pivot
+// records (umode 2: their band part per warp, [4][W][systems of the warp], in front: the tensor store's source).
+size_t band_smem_bytes(const BandPlan& bp, int warps, int umode) {
   const size_t ring = (size_t)4 * bp.step_stride * (bp.rc_only ? 1 : 2);   // BRING step records per warp
-  const size_t sys = ((size_t)bp.n + 1 + 2 * (size_t)(bp.W + bp.NB + 2)) | 1;   // odd: see band_kernel.cuh
-  return sizeof(double2) * (size_t)warps * (ring + (32 / bp.L) * sys);
+  const size_t recs = umode == 2 ? 2 * (size_t)(bp.NB + 2) : (umode ? 4 : 2) * (size_t)(bp.W + bp.NB + 2);
+  const size_t sys = ((size_t)bp.n + 1 + recs) | 1;   // odd: see band_kernel.cuh
+  const size_t tma = umode == 2 ? (size_t)4 * bp.W * (32 / bp.L) : 0;
+  return sizeof(double2) * (size_t)warps * (tma + ring + (32 / bp.L) * sys);
 }
 
 // Launch shape: as many warps per SM as shared memory and the register file (255 per thread) allow.
-bool band_launch_shape(const DeviceCtx& ctx, const BandPlan& bp, int& warps, int& minb) {
+bool band_launch_shape(const DeviceCtx& ctx, const BandPlan& bp, int umode, int& warps, int& minb) {
   if (const char* e = getenv("SPICEY_BAND_CFG")) {   // experiments: warps per CTA, CTAs per SM
     int a = 0, b = 0;
-    if (sscanf(e, "%d,%d", &a, &b) == 2 && a >= 1 && a <= 16 && b >= 1 && b <= 8 && band_smem_bytes(bp, a) * b + 1024 * b <= ctx.smem_optin + 1024) {
+    if (sscanf(e, "%d,%d", &a, &b) == 2 && a >= 1 && a <= 16 && b >= 1 && b <= 8 && band_smem_bytes(bp, a, umode) * b + 1024 * b <= ctx.smem_optin + 1024) {
       warps = a; minb = b;
       return true;
     }
   }
   const int shapes[][2] = {{4, 2}, {2, 2}, {2, 1}, {1, 1}};
   for (const auto& sh : shapes)
-    if ((band_smem_bytes(bp, sh[0]) + 1024) * sh[1] <= ctx.smem_optin) { warps = sh[0]; minb = sh[1]; return true; }
+    if ((band_smem_bytes(bp, sh[0], umode) + 1024) * sh[1] <= ctx.smem_optin) { warps = sh[0]; minb = sh[1]; return true; }
   return false;
 }
 
@@ -753,17 +790,18 @@ DeviceCtx::BandJit* ensure_band_jit(DeviceCtx& ctx, bool with_ielem) {
   DeviceCtx::BandJit& jv = ctx.band_jit[with_ielem ? 1 : 0];
   const BandPlan& bp = ctx.bp;
   int warps = 0, minb = 0;
-  if (!band_launch_shape(ctx, bp, warps, minb)) return nullptr;
-  const int shape[9] = {bp.L, bp.RPL, bp.NB, (int)bp.abmask, warps, minb, with_ielem ? 1 : 0, bp.rc_only ? 1 : 0, band_sync_default()};
+  const int umode = band_umode(ctx, bp);
+  if (!band_launch_shape(ctx, bp, umode, warps, minb)) return nullptr;
+  const int shape[10] = {bp.L, bp.RPL, bp.NB, (int)bp.abmask, warps, minb, with_ielem ? 1 : 0, bp.rc_only ? 1 : 0, band_sync_default(), umode};
   uint64_t key = fnv1a(1469598103934665603ull, shape, sizeof shape);
   if (!key) key = 1;
   if (jv.key == key) return jv.failed ? nullptr : &jv;
   jv.key = key;
   jv.failed = true;
   if (jv.lib) { cudaLibraryUnload(jv.lib); jv.lib = nullptr; jv.kernel = nullptr; }
-  const std::string src = band_source(bp, with_ielem, warps, minb);
+  const std::string src = band_source(bp, with_ielem, warps, minb, umode);
   if (!load_jit_kernel(src, "spicey_band_jit", &jv.lib, &jv.kernel, ctx.sp_jit_note)) return nullptr;
-  jv.warps = warps; jv.minb = minb;
+  jv.warps = warps; jv.minb = minb; jv.umode = umode;
   jv.failed = false;
   return &jv;
 }
@@ -772,7 +810,7 @@ int launch_ac_band(DeviceCtx& ctx, const HostPlan& hp, const AcArgs& args, Devic
                    long long* fb_list, int* fb_count, int64_t* launches) {
   const BandPlan& bp = ctx.bp;
   const int gpb = jv->warps * (32 / bp.L);   // systems per CTA
-  const size_t smem = band_smem_bytes(bp, jv->warps);
+  const size_t smem = band_smem_bytes(bp, jv->warps, jv->umode);
   unsigned grid = (unsigned)std::min<long long>((args.p_count + gpb - 1) / gpb, (long long)ctx.sm_count * jv->minb);
   if (const char* e = getenv("SPICEY_BAND_GRID")) grid = std::min<unsigned>(grid, (unsigned)std::max(1, atoi(e)));   // experiments
   int rc = ctx.bp_work.ensure(sizeof(double2) * (size_t)bp.g_stride * grid * gpb);
@@ -790,7 +828,45 @@ int launch_ac_band(DeviceCtx& ctx, const HostPlan& hp, const AcArgs& args, Devic
   a.ind_L = sa.ind_L;
   a.n = bp.n; a.nb = bp.nb; a.n_out = hp.nvar; a.n_ac_elem = hp.n_ac_elem; a.n_ind = sa.n_ind;
   a.o_init = bp.o_init; a.o_initb = bp.o_initb; a.o_brd0 = bp.o_brd0; a.o_bb0 = bp.o_bb0; a.o_step = bp.o_step;
-  void* kargs[] = {&a};
+  alignas(64) CUtensorMap tm;
+  memset(&tm, 0, sizeof tm);
+  if (jv->umode == 2) {
+    // The U part of every system's workspace as one tensor of doubles: (2 W: row slot x re / im | systems | nb + W columns);
+    // a box is one row slot of the W columns k + 1 .. k + W for the systems of one warp, [column][system] in shared memory.
+    const cuuint64_t dims[3] = {(cuuint64_t)2 * bp.W, (cuuint64_t)grid * gpb, (cuuint64_t)(bp.nb + bp.W)};
+    const cuuint64_t strides[2] = {(cuuint64_t)bp.g_stride * sizeof(double2), (cuuint64_t)bp.W * sizeof(double2)};
+    const cuuint32_t box[3] = {2, (cuuint32_t)(32 / bp.L), (cuuint32_t)bp.W};
+    const cuuint32_t estr[3] = {1, 1, 1};
+    TensorMapEncodeTiledFn enc = tensor_map_encoder();
+    const CUresult er = enc ? enc(&tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, ctx.bp_work.p, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                                  CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE)
+                            : CUDA_ERROR_NOT_SUPPORTED;
+    if (er != CUDA_SUCCESS) {   // this driver will not describe the workspace: compile and run the plain-store kernel instead
+      ctx.band_tma_refused = true;
+      ctx.sp_jit_note = "cuTensorMapEncodeTiled refused the band workspace (CUresult " + std::to_string((int)er) + "): plain U stores";
+      DeviceCtx::BandJit* alt = ensure_band_jit(ctx, args.ielem != nullptr);
+      if (!alt || alt->umode == 2) return fail(SPICEY_ERR_CUDA, "the band kernel could not be rebuilt without the tensor store");
+      return launch_ac_band(ctx, hp, args, alt, stream, fb_list, fb_count, launches);
+    }
+  }
+  void* kargs[] = {&a, &tm};   // the plain-store kernels take the first parameter only
+  if (getenv("SPICEY_BAND_PROF")) {   // experiments: cycles per phase, summed over the warps, printed per launch (synchronous)
+    unsigned long long* d = nullptr;
+    unsigned long long h[4] = {0, 0, 0, 0};
+    CUDA_TRY(cudaMalloc(&d, sizeof h));
+    CUDA_TRY(cudaMemsetAsync(d, 0, sizeof h, stream));
+    a.prof = d;
+    CUDA_TRY(cudaLaunchKernel((const void*)jv->kernel, dim3(grid), dim3(jv->warps * 32), kargs, smem, stream));
+    CUDA_TRY(cudaMemcpyAsync(h, d, sizeof h, cudaMemcpyDeviceToHost, stream));
+    CUDA_TRY(cudaStreamSynchronize(stream));
+    cudaFree(d);
+    const double tot = (double)(h[0] + h[1] + h[2] + h[3]) + 1e-9;
+    fprintf(stderr, "[band prof] warps %u  cycles/warp: stamp %.0f (%.1f%%)  elim %.0f (%.1f%%)  backsub %.0f (%.1f%%)  results %.0f (%.1f%%)\n",
+            grid * jv->warps, h[0] / (double)(grid * jv->warps), 100 * h[0] / tot, h[1] / (double)(grid * jv->warps), 100 * h[1] / tot,
+            h[2] / (double)(grid * jv->warps), 100 * h[2] / tot, h[3] / (double)(grid * jv->warps), 100 * h[3] / tot);
+    if (launches) ++*launches;
+    return SPICEY_SUCCESS;
+  }
   CUDA_TRY(cudaLaunchKernel((const void*)jv->kernel, dim3(grid), dim3(jv->warps * 32), kargs, smem, stream));
   if (launches) ++*launches;
   return SPICEY_SUCCESS;
@@ -2109,7 +2185,7 @@ int64_t spicey_debug_band_source(int32_t L, int32_t RPL, int32_t NB, uint32_t ab
                                  int32_t minb, char* buf, int64_t cap) {
   BandPlan bp;
   bp.L = L; bp.RPL = RPL; bp.NB = NB; bp.abmask = abmask & 0xffffu; bp.rc_only = (abmask >> 16) & 1u;
-  const std::string src = band_source(bp, with_ielem != 0, warps, minb);
+  const std::string src = band_source(bp, with_ielem != 0, warps, minb, (int)((abmask >> 17) & 3u));
   if (buf && cap > 0) {
     const size_t n = std::min<size_t>(src.size(), (size_t)cap - 1);
     memcpy(buf, src.data(), n);

@@ -1,7 +1,7 @@
 #!/usr/bin/env python3
 """GPU: time the banded + bordered tier (tier 8) on the cfg4 mesh (or SWEEP_WL=mesh<side> / ladder<n>) for several
 band shapes and launch shapes, and check each against the strict dense pivoting kernel on a subsample.
-   usage: band_sweep.py "8,2:4,2" "16,1:4,4" ...    each argument = SPICEY_BAND_SHAPE:SPICEY_BAND_CFG[:SPICEY_BAND_SYNC] (L,RPL:warps,minb[:0|1])
+   usage: band_sweep.py "8,2:4,2" "16,1:4,4" ...    each argument = SPICEY_BAND_SHAPE:SPICEY_BAND_CFG[:SPICEY_BAND_SYNC[:SPICEY_BAND_UMODE]] (L,RPL:warps,minb[:n[:0|1|2]])
    SWEEP_P points (default 400000), SWEEP_NO_IELEM=1 without element currents, SWEEP_PM=1 point-major results"""
 import os
 import sys
@@ -41,6 +41,11 @@ def main():
     for arg in sys.argv[1:] or ["8,2:4,2"]:
         shape, _, cfg = arg.partition(":")
         cfg, _, sync = cfg.partition(":")
+        sync, _, umode = sync.partition(":")
+        if umode:
+            os.environ["SPICEY_BAND_UMODE"] = umode
+        else:
+            os.environ.pop("SPICEY_BAND_UMODE", None)
         if sync:
             os.environ["SPICEY_BAND_SYNC"] = sync
         else:
