@@ -136,6 +136,13 @@ __device__ __forceinline__ void band_zero_if(bool p, double& x) {
   asm("{\n\t.reg .pred q;\n\tsetp.ne.s32 q, %1, 0;\n\t@q mov.f64 %0, 0d0000000000000000;\n\t}" : "+d"(x) : "r"((int)p));
 }
 
+// an L2 load the compiler must leave where it is written (the software pipeline of the back-substitution)
+__device__ __forceinline__ bcplx band_ldcg_now(const double2* ptr) {
+  bcplx v;
+  asm volatile("ld.global.cg.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "l"(ptr) : "memory");
+  return v;
+}
+
 // stamped value of a table entry at angular frequency w (simulateAC.ts:36-57)
 // BAND_RC: every entry of the circuit is (alpha, w beta) — no inductors, real source phasors — and the tables hold
 // one double2 (alpha, beta) per entry
@@ -490,9 +497,11 @@ extern "C" __global__ void __launch_bounds__(BAND_WARPS * 32, BAND_MINB) spicey_
       constexpr int BH = BW / 2;
       bcplx Ua[BH][BAND_RPL], Ub[BH][BAND_RPL];
       bcplx RJ[BAND_RPL], ENT[BAND_RPL], RJn[BAND_RPL], ENTn[BAND_RPL];
+      // (volatile: the compiler otherwise sinks a half block's loads to their first use — the r3c capture has a
+      //  ~2,900-cycle stall per block on a DFMA thirty instructions behind its LDG — which undoes the pipeline)
 #define BAND_LOAD_U(U, j0)                                                                                   \
       _Pragma("unroll") for (int s_ = 0; s_ < BH; ++s_)                                                      \
-        _Pragma("unroll") for (int q = 0; q < BAND_RPL; ++q) U[s_][q] = __ldcg(Gu + (size_t)((j0) + s_) * BW + l + BAND_L * q);
+        _Pragma("unroll") for (int q = 0; q < BAND_RPL; ++q) U[s_][q] = band_ldcg_now(Gu + (size_t)((j0) + s_) * BW + l + BAND_L * q);
 #define BAND_LOAD_RE(R, E, jb_)                                                                              \
       _Pragma("unroll") for (int q = 0; q < BAND_RPL; ++q) {                                                 \
         const int j = (jb_) + l + BAND_L * q;                                                                \
@@ -525,6 +534,7 @@ extern "C" __global__ void __launch_bounds__(BAND_WARPS * 32, BAND_MINB) spicey_
             if (ln + l < (BW * BW * 16 + 127) / 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(nx + (ln + l) * 128));
         }
         BAND_LOAD_U(Ub, jb)
+        __syncwarp();   // ptxas does not move the loads below a warp barrier (it sank them into the second half block)
 #pragma unroll
         for (int s = BW - 1; s >= BH; --s) BAND_BSTEP(s, Ua[s - BH])
         if (jb >= BW) {

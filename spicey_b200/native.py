@@ -167,10 +167,12 @@ def band_plan_stats(table: "ElemTable", pilot_f: float = 1000.0) -> dict:
 
 
 def band_kernel_source(lanes=8, rows_per_lane=2, border_rows=1, border_col_mask=0, with_ielem=True, warps=4,
-                       min_blocks=2) -> str:
-    """CUDA source NVRTC compiles for one band shape (tier 8).  Host-only tooling."""
+                       min_blocks=2, rc_only=False, umode=0) -> str:
+    """CUDA source NVRTC compiles for one band shape (tier 8); umode 2: the pivot rows leave through TMA tensor
+    stores, 0: plain stores.  Host-only tooling."""
     lib = load_library()
-    args = (lanes, rows_per_lane, border_rows, border_col_mask, int(with_ielem), warps, min_blocks)
+    mask = (border_col_mask & 0xFFFF) | (int(bool(rc_only)) << 16) | ((umode & 3) << 17)
+    args = (lanes, rows_per_lane, border_rows, mask, int(with_ielem), warps, min_blocks)
     need = lib.spicey_debug_band_source(*args, None, 0)
     buf = C.create_string_buffer(need)
     lib.spicey_debug_band_source(*args, buf, need)

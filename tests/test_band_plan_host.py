@@ -38,3 +38,34 @@ def test_band_schedule_matches_dense_pivoted_elimination(checker, kind, seed, si
     args = [checker, str(kind), str(seed), str(size), str(nv)] + ([str(L), str(RPL)] if L else [])
     out = subprocess.run(args, capture_output=True, text=True)
     assert out.returncode == 0 and out.stdout.startswith("OK"), out.stdout + out.stderr
+
+
+@pytest.mark.parametrize("lanes,rpl,nb,warps,minb,rc_only,umode", [(8, 2, 1, 4, 2, True, 2), (8, 2, 1, 4, 2, True, 0), (16, 1, 2, 4, 2, False, 2),
+                                                                    (4, 1, 1, 4, 2, True, 2), (2, 1, 1, 4, 2, True, 0)])
+def test_band_kernel_compiles_for_both_store_modes(tmp_path, lanes, rpl, nb, warps, minb, rc_only, umode):
+    """The kernel text the library hands to NVRTC for a band shape, compiled here with nvcc for sm_100a: within the register
+    file at the launch shape, and with BAND_UMODE 2 the pivot rows leave through the TMA unit (UTMASTG, one per unrolled
+    step) instead of per-lane global stores."""
+    import re
+    import shutil
+    from spicey_b200 import native
+    nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    cuobjdump = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+    if not os.path.exists(nvcc) or not os.path.exists(cuobjdump):
+        pytest.skip("nvcc / cuobjdump not found")
+    src = native.band_kernel_source(lanes, rpl, nb, 0, True, warps, minb, rc_only=rc_only, umode=umode)
+    assert "#define BAND_L %d\n#define BAND_RPL %d\n#define BAND_NB %d\n" % (lanes, rpl, nb) in src and "#define BAND_UMODE %d\n" % umode in src
+    cu = tmp_path / "band.cu"
+    cu.write_text(src)
+    res = subprocess.run([nvcc, "-cubin", "-gencode", "arch=compute_100a,code=sm_100a", "-std=c++17", "-Xptxas", "-v",
+                          "-o", str(tmp_path / "band.cubin"), str(cu)], capture_output=True, text=True)
+    assert res.returncode == 0, res.stderr[-2000:]
+    regs = int(re.search(r"Used (\d+) registers", res.stderr).group(1))
+    assert regs * warps * 32 * minb <= 65536, (regs, warps, minb)
+    assert max(int(v) for v in re.findall(r"(\d+) bytes spill stores", res.stderr)) <= 64, res.stderr
+    sass = subprocess.run([cuobjdump, "-sass", str(tmp_path / "band.cubin")], capture_output=True, text=True).stdout
+    n_tma = len(re.findall(r"UTMASTG", sass))
+    W = lanes * rpl
+    assert n_tma == (W if umode == 2 else 0), (n_tma, W)
+    if umode == 2:
+        assert "cp.async.bulk.tensor.3d.global.shared::cta" in src and "FENCE.VIEW.ASYNC" in sass

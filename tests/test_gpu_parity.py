@@ -871,6 +871,31 @@ def test_ac_band_tier_forced_shapes_mesh16(shape, monkeypatch):
         e.close()
 
 
+@pytest.mark.parametrize("name,text", [("mesh16", w.rc_mesh(16)), ("mesh5", w.rc_mesh(5, ppd=50))])
+def test_ac_band_tier_tensor_store_equals_plain_stores(name, text, monkeypatch):
+    """The banded tier writes its pivot rows to the workspace through TMA tensor stores by default (BAND_UMODE 2,
+    band_kernel.cuh); SPICEY_BAND_UMODE=0 compiles the per-lane store form.  Same arithmetic, same order: every node
+    voltage, element current and status bit-identical, no fallback in either."""
+    import spicey_b200 as sp
+    ck = parse_netlist(text)
+    freqs = np.array(sp.analysis.ac_frequencies(ck))
+    freqs = np.ascontiguousarray(freqs[:: max(1, freqs.shape[0] // 3001)])
+    res = {}
+    for umode in ("2", "0"):
+        monkeypatch.setenv("SPICEY_BAND_UMODE", umode)
+        e = native.Engine()
+        try:
+            out = sp.simulate_ac_batch(ck, freqs, engine=e, flags=BAND)
+            stt = e.stats()
+            assert stt["tier"] == native.TIER_BAND and stt["fallback_solves"] == 0, stt
+            res[umode] = out
+        finally:
+            e.close()
+    assert res["2"]["status"].max() == 0
+    for key in ("x", "ielem", "status"):
+        assert np.array_equal(res["2"][key], res["0"][key]), (name, key)
+
+
 def test_ac_band_tier_pivot_changes_fall_back(eng):
     """An RLC ladder with two sources swept over seven decades: the pivot order of the pilot point does not hold
     everywhere, those points go to the dense kernel; statuses and values equal the oracle's either way."""
