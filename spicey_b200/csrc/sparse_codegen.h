@@ -64,11 +64,17 @@ struct CodegenOptions {
   int stagger_ns = 0;     // > 0: CTAs start in four phases this many ns apart, so that the SMs are not all storing at once
   int prefetch_steps = 8; // per-instance stamping: element values are loaded this many pivots / rows ahead of their use
   int antiphase_ns = 0;     // min_blocks >= 2: start delay of the k-th wave of CTAs (k * antiphase_ns)
+  int reg_values = -1;      // >= 0: cross-phase values that may stay in registers beside the shared-memory slots; the
+                            // longest-lived of the rest go to a [slot][thread] column of global memory (JitArgs.work)
+  int gmem_ahead = 6;       // back-substitution rows between the load of a global-column value and its use
+  bool l2_policy = true;    // global column: L2 evict_last, result stores: evict_first (the column of the resident grid is
+                            // rewritten by every point and fits L2 for mid-size programs; the results only pass through)
 };
 
 struct CodegenStats {
   int n_saved = 0;        // values crossing from the elimination into the back-substitution
   int smem_slots = 0;     // of those, placed in shared memory
+  int gmem_slots = 0;     // ... and in the global column (double2 per thread each)
   size_t smem_bytes = 0;  // dynamic shared memory per CTA
   int n_classes = 0;      // distinct stamped values
 };
@@ -100,6 +106,7 @@ struct JitArgs {
   double2* x; double2* ielem; int* status; long long series_ld;
   long long* fb_list; int* fb_count; int n; int n_ac_elem;
   const double* var_values; long long n_inst; long long n_freq; long long p_begin;   // per-instance stamping
+  double2* work;   // [gmem slot][gridDim.x * BLOCK]: the factor values that fit neither registers nor shared memory
 };
 #define EPS 1e-15
 #define THR 1e-30
@@ -119,6 +126,11 @@ extern __shared__ double2 sm[];
 // local memory) across the whole elimination, which is exactly what the placement is meant to avoid.
 #define SMST(off, v) asm volatile("st.shared.v2.f64 [%0+" #off "], {%1, %2};" :: "r"(sbase), "d"((v).x), "d"((v).y) : "memory")
 #define SMLD(v, off) asm volatile("ld.shared.v2.f64 {%0, %1}, [%2+" #off "];" : "=d"((v).x), "=d"((v).y) : "r"(sbase) : "memory")
+// Global column of the factor values (programs past a thread's registers + shared memory) with an L2 evict_last policy,
+// result stores with evict_first: the column is rewritten by every point and should stay in L2, the results only pass.
+#define GST(p, v) asm volatile("st.global.L2::cache_hint.v2.f64 [%0], {%1, %2}, %3;" :: "l"(p), "d"((v).x), "d"((v).y), "l"(pol_keep) : "memory")
+#define GLD(v, p) asm volatile("ld.global.cg.L2::cache_hint.v2.f64 {%0, %1}, [%2], %3;" : "=d"((v).x), "=d"((v).y) : "l"(p), "l"(pol_keep) : "memory")
+#define RST(p, re, im) asm volatile("st.global.L2::cache_hint.v2.f64 [%0], {%1, %2}, %3;" :: "l"(p), "d"((double)(re)), "d"((double)(im)), "l"(pol_stream) : "memory")
 )SRC";
 }
 
@@ -233,8 +245,12 @@ inline std::string generate_sparse_kernel_source(const CodegenInput& in, const C
   }
   // ---- shared-memory placement of the cross-phase values: the longest-lived go to shared memory, registers
   //      keep what the back-substitution consumes first ----
-  std::vector<int> slot_of(sp.n_virtual, -1);
-  int ns = 0;
+  // Larger programs (a 400-node ladder hands 1,600 values to its back-substitution) would leave the rest to the register
+  // allocator, i.e. to kilobytes of local-memory spills: with opt.reg_values >= 0 the longest-lived values beyond
+  // registers + shared memory go to a per-thread column of GLOBAL memory instead ([slot][thread]: one coalesced 512-byte
+  // store per warp when the value is produced, one such load a few rows before the back-substitution needs it).
+  std::vector<int> slot_of(sp.n_virtual, -1), gslot_of(sp.n_virtual, -1);
+  int ns = 0, ng = 0;
   {
     std::vector<std::pair<int, int>> saved;  // (-lifetime, v)
     for (int v = 0; v < sp.n_virtual; ++v)
@@ -242,11 +258,19 @@ inline std::string generate_sparse_kernel_source(const CodegenInput& in, const C
     std::sort(saved.begin(), saved.end());
     st.n_saved = (int)saved.size();
     ns = std::min<int>(std::max(0, opt.smem_slots), (int)saved.size());
-    for (int i = 0; i < ns; ++i) slot_of[saved[i].second] = i;
+    if (opt.reg_values >= 0) ng = std::max(0, (int)saved.size() - ns - opt.reg_values);
+    for (int i = 0; i < ng; ++i) gslot_of[saved[i].second] = i;
+    for (int i = 0; i < ns; ++i) slot_of[saved[ng + i].second] = i;
     st.smem_slots = ns;
+    st.gmem_slots = ng;
     st.smem_bytes = (size_t)ns * opt.block * 16;
   }
   auto soff = [&](int slot) { return std::to_string((long long)slot * opt.block * 16); };
+  auto gst = [&](int v, const std::string& name) -> std::string {   // store of a value that lives in the global column
+    if (gslot_of[v] < 0) return std::string();
+    if (opt.l2_policy) return "    GST(gwp + " + std::to_string(gslot_of[v]) + " * gT, " + name + ");\n";
+    return "    __stcg(gwp + " + std::to_string(gslot_of[v]) + " * gT, " + name + ");\n";
+  };
 
   std::string s;
   s.reserve(1 << 20);
@@ -369,6 +393,12 @@ inline std::string generate_sparse_kernel_source(const CodegenInput& in, const C
   s += "  const unsigned ld = a.series_ld ? (unsigned)a.series_ld : 1u;\n";
   s += "  const unsigned sbase = (unsigned)__cvta_generic_to_shared(sm) + threadIdx.x * 16u;\n";
   s += "  const long long stride = (long long)gridDim.x * BLOCK, plast = a.p_count - 1;\n";
+  if (ng > 0) s += "  const size_t gT = (size_t)stride;\n  double2* const gw = a.work + (size_t)blockIdx.x * BLOCK + threadIdx.x;\n";
+  const bool hinted = ng > 0 && opt.l2_policy;
+  if (hinted)
+    s += "  unsigned long long pol_keep, pol_stream;\n"
+         "  asm(\"createpolicy.fractional.L2::evict_last.b64 %0, 1.0;\" : \"=l\"(pol_keep));\n"
+         "  asm(\"createpolicy.fractional.L2::evict_first.b64 %0, 1.0;\" : \"=l\"(pol_stream));\n";
   if (!in.eager) s += "  double fnext = a.freqs[min((long long)blockIdx.x * BLOCK + threadIdx.x, plast)];\n";
   // block-uniform trip count: lanes past the end solve the last point again and store nothing
   s += "  for (long long base = (long long)blockIdx.x * BLOCK; base < a.p_count; base += stride) {\n";
@@ -388,6 +418,9 @@ inline std::string generate_sparse_kernel_source(const CodegenInput& in, const C
   // and store it to the last point's rows: a benign duplicate write instead of a predicate, which keeps every result
   // store unconditional and the back-substitution one basic block (no BSSY / BRA / BSYNC around each row's stores).
   s += "    const long long pc = min(p, plast);\n";
+  // (two opaque copies of the column's base, one per phase: the compiler otherwise keeps every slot's 64-bit address in a
+  //  register from the store in the elimination to the load in the back-substitution — hundreds of them, all spilled)
+  if (ng > 0) s += "    double2 *gwp = gw, *gwq = gw; asm volatile(\"\" : \"+l\"(gwp), \"+l\"(gwq));\n";
   s += "    char* const xb = (char*)(a.series_ld ? a.x + pc : a.x + pc * a.n);\n";
   if (opt.with_ielem) s += "    char* const ib = (char*)(a.series_ld ? a.ielem + pc : a.ielem + pc * a.n_ac_elem);\n";
   s += "    bool ok = true, bad = false;\n    double mp, m, inv;\n    double2 r, fm;\n";
@@ -433,7 +466,8 @@ inline std::string generate_sparse_kernel_source(const CodegenInput& in, const C
   std::vector<Out> pending;
   auto flush_outputs = [&]() {
     for (const Out& o : pending)
-      s += std::string("    *(double2*)(") + (o.cur ? "ib" : "xb") + " + " + off(o.k) + ") = D2(" + o.re + ", " + o.im + ");\n";
+      if (hinted) s += std::string("    RST(") + (o.cur ? "ib" : "xb") + " + " + off(o.k) + ", " + o.re + ", " + o.im + ");\n";
+      else s += std::string("    *(double2*)(") + (o.cur ? "ib" : "xb") + " + " + off(o.k) + ") = D2(" + o.re + ", " + o.im + ");\n";
     pending.clear();
   };
 
@@ -490,10 +524,27 @@ inline std::string generate_sparse_kernel_source(const CodegenInput& in, const C
     }
   };
 
+  // global-column values: loaded opt.gmem_ahead back-substitution rows before the row that reads them
+  std::vector<char> g_loaded(sp.n_virtual, 0);
+  auto gload_ahead = [&](int t) {
+    if (ng == 0) return;
+    int rows = 0;
+    for (int q = t; q < n_ir; ++q) {
+      if (q > t && ir[q].kind == SOP_BSUB && ++rows > opt.gmem_ahead) break;
+      for (int o : ir[q].reads)
+        if (o >= 0 && gslot_of[o] >= 0 && !g_loaded[o]) {
+          g_loaded[o] = 1;
+          if (opt.l2_policy) s += "    double2 g" + std::to_string(o) + "; GLD(g" + std::to_string(o) + ", gwq + " + std::to_string(gslot_of[o]) + " * gT);\n";
+          else s += "    const double2 g" + std::to_string(o) + " = __ldcg(gwq + " + std::to_string(gslot_of[o]) + " * gT);\n";
+        }
+    }
+  };
+
   int n_piv = 0, n_bs = 0;
   for (int t = 0; t < n_ir; ++t) {
     const IrOp& op = ir[t];
     if (t == B) phase = 'b';
+    if (op.kind == SOP_BSUB) gload_ahead(t);
     if (op.kind == SOP_PIVOT || op.kind == SOP_BSUB) prefetch_from(t);
     if (t == B) {
       // Every pivot has been verified.  A system whose pivot order differs from the pilot's, or that trips a
@@ -518,6 +569,7 @@ inline std::string generate_sparse_kernel_source(const CodegenInput& in, const C
            (ap.im0 ? std::string("0.0") : "-" + ap.im + " * inv") + ");\n";
       s += "    r = " + v + ";\n";
       if (slot_of[op.def] >= 0) s += "    SMST(" + soff(slot_of[op.def]) + ", " + v + ");\n";
+      s += gst(op.def, v);
     } else if (op.kind == SOP_ELIM) {
       std::string re, im;
       Opnd rr; rr.re = "r.x"; rr.im = "r.y";
@@ -531,6 +583,7 @@ inline std::string generate_sparse_kernel_source(const CodegenInput& in, const C
         submul(a, "fm", pq, re, im);
         s += "    const double2 " + v + " = D2(" + re + ", " + im + ");\n";
         if (slot_of[u.dst_new] >= 0) s += "    SMST(" + soff(slot_of[u.dst_new]) + ", " + v + ");\n";
+        s += gst(u.dst_new, v);
       }
     } else {
       if (opt.sync_every > 0 && n_bs % opt.sync_every == 0) s += "    __syncthreads();\n";
@@ -549,6 +602,7 @@ inline std::string generate_sparse_kernel_source(const CodegenInput& in, const C
         }
       auto bop = [&](int o) -> Opnd {
         if (o >= 0 && local.count(o)) { Opnd r2; r2.re = local[o] + ".x"; r2.im = local[o] + ".y"; return r2; }
+        if (o >= 0 && gslot_of[o] >= 0) { Opnd r2; r2.re = "g" + std::to_string(o) + ".x"; r2.im = "g" + std::to_string(o) + ".y"; return r2; }
         return opnd(o);
       };
       Opnd acc = bop(op.reads[0]);

@@ -88,7 +88,9 @@ struct DeviceCtx {
     bool failed = false;
     size_t smem_bytes = 0;
     int block = 0, min_blocks = 1;
+    int gmem_slots = 0;   // double2 per thread of the global column (JitArgs.work)
   } sp_jit[2];
+  Buffer sp_jit_work;
   // Launch shape of the compiled kernel, measured on cfg2 (tools/jit_sweep.py): one CTA of 6 warps per SM with
   // 255 registers per thread and 75 shared-memory slots per thread for the factor values (0.76 ms per 1e6
   // points); 5 warps x 90 slots: 0.81 ms, 4 x 113: 1.03 ms, 8 x 55 (spills): 1.0 ms.  A __syncthreads every
@@ -111,6 +113,7 @@ struct DeviceCtx {
   double sp_jit_compile_ms = 0;
   uint64_t sp_jit_fit_key = 0;   // sparse program the fit check below was made for
   bool sp_jit_fits = false;
+  bool sp_jit_column = false;   // the compiled kernel of this topology needs its global column
   std::string sp_jit_note;
   // warp-cooperative form of the sparse program (warp_program.h): large programs, one warp per system
   WarpProgram wp;
@@ -317,6 +320,7 @@ struct JitArgs {   // must match sparse_jit_prelude()
   double2* x; double2* ielem; int* status; long long series_ld;
   long long* fb_list; int* fb_count; int n; int n_ac_elem;
   const double* var_values; long long n_inst; long long n_freq; long long p_begin;   // per-instance stamping
+  double2* work;   // global column of the factor values beyond registers + shared memory (CodegenStats.gmem_slots)
 };
 
 // Host half of the sparse path: per-entry constants, pilot matrix and the program itself (no device needed).
@@ -482,6 +486,8 @@ constexpr long long kTileMinPoints = 4096;    // below this the ~2 s compile of 
 constexpr long long kSparseMinPoints = 2048;  // batches from which the sparse program path pays for its host-side analysis
 constexpr size_t kJitMaxOps = 3000;          // larger programs stay on the interpreter (compile time: cfg2's 831 micro-ops take 4 s)
 constexpr int kJitSpareValues = 64;          // cross-phase values the registers can hold beside the shared-memory slots
+constexpr int kJitRegValuesWithColumn = 40;  // ... when the global column is in use (its loads in flight need registers too)
+constexpr int kJitMaxGlobalValues = 2048;    // ... and beside the kernel's [slot][thread] column of global memory (32 KB per thread)
 constexpr long long kJitMinPoints = 200000;  // below this the ~4 s compile does not pay off (unless forced)
 
 void jit_source(const SparseProgram& sp, const HostPlan& hp, const CodegenOptions& opt, bool eager, std::string& src,
@@ -546,6 +552,13 @@ DeviceCtx::JitVariant* ensure_jit(DeviceCtx& ctx, const HostPlan& hp, bool with_
   if (const char* e = getenv("SPICEY_JIT_ANTIPHASE")) opt.antiphase_ns = atoi(e);   // experiments
   opt.smem_slots = std::min<int>(ctx.sp_eager ? ctx.sp_jit_slots_eager : ctx.sp_jit_slots,
                                  (int)((size_t)(227 * 1024 / opt.min_blocks - 1024) / ((size_t)opt.block * 16)));
+  // What exceeds registers + shared memory lives in the kernel's global column.  Programs that fit without it (cfg 2: 129
+  // values = 75 slots + 54 registers) are generated exactly as before; the others keep fewer values in registers, because
+  // the loads of the column run a few rows ahead of their use and need registers of their own.
+  opt.reg_values = count_cross_phase_values(ctx.sp) <= opt.smem_slots + kJitSpareValues ? kJitSpareValues : kJitRegValuesWithColumn;
+  if (const char* e = getenv("SPICEY_JIT_REGVALUES")) opt.reg_values = std::max(0, atoi(e));   // experiments
+  if (const char* e = getenv("SPICEY_JIT_GAHEAD")) opt.gmem_ahead = std::max(1, atoi(e));
+  if (const char* e = getenv("SPICEY_JIT_L2POLICY")) opt.l2_policy = atoi(e) != 0;
   std::string src;
   CodegenStats st;
   jit_source(ctx.sp, hp, opt, ctx.sp_eager, src, st);
@@ -556,6 +569,7 @@ DeviceCtx::JitVariant* ensure_jit(DeviceCtx& ctx, const HostPlan& hp, bool with_
     return nullptr;
   }
   jv.smem_bytes = st.smem_bytes;
+  jv.gmem_slots = st.gmem_slots;
   jv.block = opt.block;
   jv.min_blocks = opt.min_blocks;
   jv.failed = false;
@@ -886,18 +900,29 @@ int launch_ac_sparse(DeviceCtx& ctx, const HostPlan& hp, const DevPlan& dp, cons
   long long* fb_list = (long long*)((char*)ctx.sp_fb.p + 64);
   CUDA_TRY(cudaMemsetAsync(fb_count, 0, sizeof(int), stream));
   ctx.sp_launched += args.p_count;
-  // the factorisation of one system must fit one thread's registers + shared memory (cfg2: 129 values), or the
-  // compiled kernel spills kilobytes per thread and takes minutes to compile (a 400-node ladder: 801 values)
+  // The factorisation of one system fits one thread's registers + shared memory (cfg2: 129 values), or what exceeds
+  // them goes to the compiled kernel's global column (sparse_codegen.h: mid-size ladders, trees, sparse networks;
+  // bounded, so that the column of the resident grid stays a few hundred MB).  kJitMaxOps bounds the compile time.
   if (ctx.sp_jit_fit_key != ctx.sp_key) {
     ctx.sp_jit_fit_key = ctx.sp_key;
-    ctx.sp_jit_fits = count_cross_phase_values(ctx.sp) <= (ctx.sp_eager ? ctx.sp_jit_slots_eager : ctx.sp_jit_slots) + kJitSpareValues;
+    const int on_chip = (ctx.sp_eager ? ctx.sp_jit_slots_eager : ctx.sp_jit_slots) + kJitSpareValues;
+    const int crossing = count_cross_phase_values(ctx.sp);
+    ctx.sp_jit_fits = crossing <= on_chip + kJitMaxGlobalValues;
+    ctx.sp_jit_column = crossing > on_chip;
   }
   // Circuits with inductors change their pivot order along a sweep more often than not (see launch_ac): their first
   // >= 4,096 points run interpreted, and a kernel is compiled for the topology only once the pilot order has been seen to hold.
   const bool order_known = ctx.sp.ind_L.empty() || ctx.sp_adapt == 1 || (flags & (SPICEY_FLAG_BAND | SPICEY_FLAG_WARP)) ||
                            args.p_count < kTileMinPoints;
-  const bool want_jit = !(flags & (SPICEY_FLAG_NO_JIT | SPICEY_FLAG_BAND)) && ctx.sp.code.size() <= kJitMaxOps && ctx.sp_jit_fits &&
-                        order_known && (args.p_count >= kJitMinPoints || (flags & SPICEY_FLAG_JIT));
+  bool want_jit = !(flags & (SPICEY_FLAG_NO_JIT | SPICEY_FLAG_BAND)) && ctx.sp.code.size() <= kJitMaxOps && ctx.sp_jit_fits &&
+                  order_known && (args.p_count >= kJitMinPoints || (flags & SPICEY_FLAG_JIT));
+  // A program that needs the global column and is banded enough for the register-blocked banded tier (meshes from
+  // half-bandwidth 4: measured faster there than one thread per system) is left to that tier, as before the column existed.
+  if (want_jit && ctx.sp_jit_column && !ctx.sp_eager && !(flags & SPICEY_FLAG_NO_BAND) && args.series_ld < (1ll << 31)) {
+    rc = prepare_band(ctx, hp, stream, false);
+    if (rc) return rc;
+    if (ctx.bp_valid) want_jit = false;
+  }
   DeviceCtx::JitVariant* jv = (want_jit && args.series_ld < (1ll << 32)) ? ensure_jit(ctx, hp, args.ielem != nullptr) : nullptr;
   if (jv) {
     JitArgs j;
@@ -909,6 +934,12 @@ int launch_ac_sparse(DeviceCtx& ctx, const HostPlan& hp, const DevPlan& dp, cons
     const long long resident = (long long)ctx.sm_count * jv->min_blocks;
     unsigned jgrid = (unsigned)std::min<long long>((args.p_count + jblock - 1) / jblock, resident);
     if (const char* e = getenv("SPICEY_JIT_GRID")) jgrid = std::min<unsigned>(jgrid, (unsigned)std::max(1, atoi(e)));   // experiments: fewer SMs
+    if (jv->gmem_slots > 0) {
+      if ((rc = ctx.sp_jit_work.ensure(sizeof(double2) * (size_t)jv->gmem_slots * jgrid * jblock))) return rc;
+      j.work = (double2*)ctx.sp_jit_work.p;
+    } else {
+      j.work = nullptr;
+    }
     void* kargs[] = {&j};
     CUDA_TRY(cudaLaunchKernel((const void*)jv->kernel, dim3(jgrid), dim3(jblock), kargs, jv->smem_bytes, stream));
     if (launches) ++*launches;
@@ -1627,7 +1658,7 @@ void spicey_destroy(spicey_handle* h) {
     cudaDeviceSynchronize();
     Buffer* bufs[] = {&c.plan, &c.scratch, &c.in0, &c.in1, &c.in2, &c.out_x[0], &c.out_x[1], &c.out_i[0],
                       &c.out_i[1], &c.out_s[0], &c.out_s[1], &c.aux0, &c.aux1, &c.sp_blob, &c.sp_work, &c.sp_fb,
-                      &c.wp_blob, &c.wp_work, &c.bp_blob, &c.bp_work, &c.tl_blob, &c.tr_iters[0], &c.tr_iters[1], &c.tr_state[0], &c.tr_state[1], &c.sp_cnt, &c.tl_fb};
+                      &c.wp_blob, &c.wp_work, &c.sp_jit_work, &c.bp_blob, &c.bp_work, &c.tl_blob, &c.tr_iters[0], &c.tr_iters[1], &c.tr_state[0], &c.tr_state[1], &c.sp_cnt, &c.tl_fb};
     for (Buffer* b : bufs) b->release();
     for (auto& jv : c.sp_jit) if (jv.lib) cudaLibraryUnload(jv.lib);
     for (auto& jv : c.tr_jit) if (jv.lib) cudaLibraryUnload(jv.lib);
@@ -2103,13 +2134,17 @@ int64_t spicey_debug_sparse_source(const spicey_elem_table* table, const spicey_
   CodegenOptions opt;
   opt.block = block; opt.min_blocks = min_blocks; opt.smem_slots = smem_slots; opt.with_ielem = (with_ielem & 1) != 0;
   opt.sync_every = (with_ielem >> 16) & 0xff;
+  if ((with_ielem >> 1) & 1) opt.reg_values = (with_ielem >> 24) & 0x7f;   // bit 1: global column beyond that many register values
+  if (const char* e = getenv("SPICEY_JIT_GAHEAD")) opt.gmem_ahead = std::max(1, atoi(e));
+  if (const char* e = getenv("SPICEY_JIT_L2POLICY")) opt.l2_policy = atoi(e) != 0;
   if (const char* e = getenv("SPICEY_JIT_ANTIPHASE")) opt.antiphase_ns = atoi(e);
   std::string src;
   CodegenStats st;
   jit_source(sp, hp, opt, eager, src, st);
   if (stats_out) {
     stats_out[0] = st.n_saved; stats_out[1] = st.smem_slots; stats_out[2] = st.n_classes; stats_out[3] = (int32_t)sp.code.size();
-    stats_out[4] = (int32_t)sp.n_fma; stats_out[5] = (int32_t)sp.n_div; stats_out[6] = sp.n_virtual; stats_out[7] = sp.n_slots;
+    stats_out[4] = (int32_t)sp.n_fma; stats_out[5] = (int32_t)sp.n_div; stats_out[6] = sp.n_virtual;
+    stats_out[7] = (with_ielem >> 1) & 1 ? st.gmem_slots : sp.n_slots;
   }
   if (buf && cap > 0) {
     const size_t n = std::min<size_t>(src.size(), (size_t)cap - 1);

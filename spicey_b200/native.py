@@ -226,21 +226,27 @@ def tran_kernel_source(table: "ElemTable", sweep: Optional["Sweep"] = None, with
 
 
 def sparse_kernel_source(table: "ElemTable", pilot_f: float, block=192, min_blocks=1, smem_slots=75, with_ielem=True,
-                         sync=4, sweep: Optional["Sweep"] = None):
+                         sync=4, sweep: Optional["Sweep"] = None, reg_values: Optional[int] = None):
     """CUDA source of the compiled straight-line sparse kernel (tier 5) for a circuit, plus the generator's
-    statistics.  Host-only tooling: lets the generated code be inspected / compiled offline with nvcc."""
+    statistics.  Host-only tooling: lets the generated code be inspected / compiled offline with nvcc.
+    reg_values (0..127): cross-phase values beyond shared memory + that many registers go to the kernel's global
+    column, as the library does (64); None: the round-1 generator (everything else is left to the registers); the last
+    statistic is then the interpreter's slot count instead of the global column's."""
     lib = load_library()
     st = (C.c_int32 * 8)()
     ts = table.struct()
     ss = sweep.struct() if sweep else None
     sp_ = C.byref(ss) if ss else None
     mode = int(with_ielem) | (sync << 16)
+    if reg_values is not None:
+        mode |= 2 | ((int(reg_values) & 0x7f) << 24)
     need = lib.spicey_debug_sparse_source(C.byref(ts), sp_, pilot_f, block, min_blocks, smem_slots, mode, None, 0, st)
     if need < 0:
         raise NativeError(-1, (lib.spicey_last_error() or b"").decode())
     buf = C.create_string_buffer(need)
     lib.spicey_debug_sparse_source(C.byref(ts), sp_, pilot_f, block, min_blocks, smem_slots, mode, buf, need, st)
-    keys = ("saved_values", "smem_slots", "classes", "micro_ops", "cfma", "reciprocals", "virtual_values", "interp_slots")
+    keys = ("saved_values", "smem_slots", "classes", "micro_ops", "cfma", "reciprocals", "virtual_values",
+            "interp_slots" if reg_values is None else "gmem_slots")
     return buf.value.decode(), dict(zip(keys, list(st)))
 
 

@@ -1006,10 +1006,37 @@ def test_simulate_ac_lazy_currents_match_the_oracle(eng):
     assert sp.formatAcResult(got) == sp.formatAcResult(eager)
 
 
+@pytest.mark.parametrize("n", [100, 150])
+def test_mid_size_ladder_compiled_with_its_global_column(eng, n):
+    """Ladders past cfg 2's size (Nvar 101 / 151: 201 / 301 values cross from the elimination into the
+    back-substitution, 75 fit shared memory and 40 registers) still take the compiled straight-line tier: the
+    longest-lived values go to the kernel's [slot][thread] column of global memory (sparse_codegen.h, JitArgs.work).
+    Values within 1e-9 of the oracle, both result layouts, with and without element currents; the interpreted
+    program of the same topology agrees with it to rounding."""
+    import spicey_b200 as sp
+    ck = parse_netlist(w.rc_ladder(n, ppd=400))
+    freqs = np.array(sp.analysis.ac_frequencies(ck))
+    sub = slice(0, None, 37)
+    xr, ier, st = co.ac_solve(ck, freqs[sub], nthreads=8)
+    assert st.max() == 0
+    for flags in (native.FLAG_SPARSE | native.FLAG_JIT, native.FLAG_SPARSE | native.FLAG_JIT | SM):
+        out = sp.simulate_ac_batch(ck, freqs, engine=eng, flags=flags)
+        stt = eng.stats()
+        assert stt["tier"] == native.TIER_SPARSE_JIT and stt["fallback_solves"] == 0, stt
+        assert out["status"].max() == 0
+        assert rel_err(out["x"][0][sub], xr) <= AC_TOL, rel_err(out["x"][0][sub], xr)
+        assert rel_err(out["ielem"][0][sub], ier) <= AC_TOL
+        out2 = sp.simulate_ac_batch(ck, freqs, engine=eng, flags=flags, want_currents=False)
+        assert eng.stats()["tier"] == native.TIER_SPARSE_JIT and np.array_equal(out2["x"], out["x"])
+    interp = sp.simulate_ac_batch(ck, freqs, engine=eng, flags=native.FLAG_SPARSE | native.FLAG_NO_JIT)
+    assert eng.stats()["tier"] == native.TIER_SPARSE
+    assert rel_err(out["x"][0], interp["x"][0]) <= 1e-12
+
+
 def test_long_ladder_default_policy(eng):
     """A 400-node ladder (Nvar = 401, 3,200 points): chain-like, so the warp tier declines (2-3 updates per row
-    would idle the lanes), and 801 values cross into the back-substitution, far more than a thread's registers
-    and shared memory hold, so the straight-line compiled tier declines.  The banded tier could take it with two
+    would idle the lanes), and its program of 5,199 micro-ops is past what the straight-line compiled tier takes
+    (kJitMaxOps: such a kernel compiles for more than a minute), so that tier declines.  The banded tier could take it with two
     lanes per system (half-bandwidth 1) but loses to the interpreted thread-per-system program below half-bandwidth 4
     (measured: 14 against 38 M solves/s), so the default stays with the program whatever is asked for, and the banded
     tier runs only when forced."""
