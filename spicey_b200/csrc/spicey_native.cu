@@ -487,6 +487,8 @@ constexpr long long kSparseMinPoints = 2048;  // batches from which the sparse p
 constexpr size_t kJitMaxOps = 3000;          // larger programs stay on the interpreter (compile time: cfg2's 831 micro-ops take 4 s)
 constexpr int kJitSpareValues = 64;          // cross-phase values the registers can hold beside the shared-memory slots
 constexpr int kJitRegValuesWithColumn = 40;  // ... when the global column is in use (its loads in flight need registers too)
+constexpr int kJitRegValuesWide = 8;         // ... in the 16-warps-per-SM shape of large column programs (128 registers per thread)
+constexpr size_t kJitWideOps = 1600;         // program size from which a column program takes that shape
 constexpr int kJitMaxGlobalValues = 2048;    // ... and beside the kernel's [slot][thread] column of global memory (32 KB per thread)
 constexpr long long kJitMinPoints = 200000;  // below this the ~4 s compile does not pay off (unless forced)
 
@@ -545,17 +547,25 @@ DeviceCtx::JitVariant* ensure_jit(DeviceCtx& ctx, const HostPlan& hp, bool with_
   CodegenOptions opt;
   opt.block = ctx.sp_eager ? ctx.sp_jit_block_eager : ctx.sp_jit_block; opt.with_ielem = with_ielem;
   opt.min_blocks = ctx.sp_eager ? ctx.sp_jit_minb_eager : ctx.sp_jit_minb;
+  int slots_cfg = ctx.sp_eager ? ctx.sp_jit_slots_eager : ctx.sp_jit_slots;
+  const int crossing = count_cross_phase_values(ctx.sp);
+  const bool with_column = crossing > slots_cfg + kJitSpareValues;
+  // Large programs that use the global column anyway run from L2 (their code is several times the instruction cache)
+  // and are bound by latency, not by HBM: 16 warps per SM with few values on chip beat 6 warps with many (measured,
+  // profiles/r3k_ladder_probe.txt: 150 / 200-node ladders 230 -> 339 / 163 -> 250 M solves/s; the 100-node ladder,
+  // which is bound by HBM, loses 25 % that way and keeps the cfg-2 shape)
+  const bool wide = with_column && !ctx.sp_eager && ctx.sp.code.size() >= kJitWideOps && !getenv("SPICEY_JIT_CFG");
+  if (wide) { opt.block = 128; opt.min_blocks = 4; slots_cfg = 27; }
   opt.prefetch_steps = ctx.sp_jit_prefetch; opt.stagger_ns = ctx.sp_eager ? ctx.sp_jit_stagger_eager : ctx.sp_jit_stagger;
   opt.sync_every = ctx.sp_jit_sync;
   if (!ctx.sp_eager && opt.min_blocks >= 2)
     opt.antiphase_ns = (int)std::min(200000.0, ctx.sp_jit_antiphase_ns_per_op * (double)ctx.sp.code.size() * 2.0 / opt.min_blocks);
   if (const char* e = getenv("SPICEY_JIT_ANTIPHASE")) opt.antiphase_ns = atoi(e);   // experiments
-  opt.smem_slots = std::min<int>(ctx.sp_eager ? ctx.sp_jit_slots_eager : ctx.sp_jit_slots,
-                                 (int)((size_t)(227 * 1024 / opt.min_blocks - 1024) / ((size_t)opt.block * 16)));
+  opt.smem_slots = std::min<int>(slots_cfg, (int)((size_t)(227 * 1024 / opt.min_blocks - 1024) / ((size_t)opt.block * 16)));
   // What exceeds registers + shared memory lives in the kernel's global column.  Programs that fit without it (cfg 2: 129
   // values = 75 slots + 54 registers) are generated exactly as before; the others keep fewer values in registers, because
   // the loads of the column run a few rows ahead of their use and need registers of their own.
-  opt.reg_values = count_cross_phase_values(ctx.sp) <= opt.smem_slots + kJitSpareValues ? kJitSpareValues : kJitRegValuesWithColumn;
+  opt.reg_values = !with_column ? kJitSpareValues : wide ? kJitRegValuesWide : kJitRegValuesWithColumn;
   if (const char* e = getenv("SPICEY_JIT_REGVALUES")) opt.reg_values = std::max(0, atoi(e));   // experiments
   if (const char* e = getenv("SPICEY_JIT_GAHEAD")) opt.gmem_ahead = std::max(1, atoi(e));
   if (const char* e = getenv("SPICEY_JIT_L2POLICY")) opt.l2_policy = atoi(e) != 0;
