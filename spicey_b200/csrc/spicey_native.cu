@@ -107,9 +107,12 @@ struct DeviceCtx {
   // per-instance (eager) stamping keeps element values in flight: fewer threads, more shared memory each.  cfg2mc:
   // 2 CTAs x 64 threads x 112 slots 1.18 ms, 1 x 128 x 113 1.28 ms, 2 x 96 x 75 1.57, 1 x 160 x 90 1.50 (a start delay
   // between the two CTAs changes nothing here: the kernel is bound by its arithmetic, not by the store port);
-  // prefetch 8 pivots ahead (4: +5 %, 2: +12 %)
+  // prefetch 8 pivots ahead (4: +5 %, 2: +12 %).  Since the global column exists (sparse_codegen.h) the values that do not
+  // fit beside the element values in flight go there instead of asking for more shared memory per thread: 6 warps per SM
+  // (2 x 96 x 75 slots + 40 register values + 14 in the column) 0.98 ms against 1.17 ms for the 4 warps of 2 x 64 x 112
+  // (profiles/r3s_cfg2mc_shapes.txt; 3 x 64 x 75: the same, 4 x 64 x 56: 1.00, 6 x 32 x 75: 1.14)
   int sp_jit_minb_eager = 2, sp_jit_stagger_eager = 0;
-  int sp_jit_block_eager = 64, sp_jit_slots_eager = 112, sp_jit_prefetch = 8;
+  int sp_jit_block_eager = 96, sp_jit_slots_eager = 75, sp_jit_prefetch = 8;
   double sp_jit_compile_ms = 0;
   uint64_t sp_jit_fit_key = 0;   // sparse program the fit check below was made for
   bool sp_jit_fits = false;
@@ -549,7 +552,8 @@ DeviceCtx::JitVariant* ensure_jit(DeviceCtx& ctx, const HostPlan& hp, bool with_
   opt.min_blocks = ctx.sp_eager ? ctx.sp_jit_minb_eager : ctx.sp_jit_minb;
   int slots_cfg = ctx.sp_eager ? ctx.sp_jit_slots_eager : ctx.sp_jit_slots;
   const int crossing = count_cross_phase_values(ctx.sp);
-  const bool with_column = crossing > slots_cfg + kJitSpareValues;
+  // (per-instance stamping keeps element values in flight: 40 register values at most, the rest in the column)
+  const bool with_column = crossing > slots_cfg + (ctx.sp_eager ? kJitRegValuesWithColumn : kJitSpareValues);
   // Large programs that use the global column anyway run from L2 (their code is several times the instruction cache)
   // and are bound by latency, not by HBM: 16 warps per SM with few values on chip beat 6 warps with many (measured,
   // profiles/r3k_ladder_probe.txt: 150 / 200-node ladders 230 -> 339 / 163 -> 250 M solves/s; the 100-node ladder,
