@@ -326,6 +326,12 @@ int32_t spicey_debug_warp_stats(const spicey_elem_table* table, double pilot_f, 
  * mask, workspace values per system.  SPICEY_ERR_UNSUPPORTED when the circuit does not qualify. */
 int32_t spicey_debug_band_stats(const spicey_elem_table* table, double pilot_f, int32_t* out);
 
+/* Tooling (no device needed): how far the solution in the banded plan's elimination order is from the solution in the
+ * netlist order (the reference's), per entry, both by the reference's algorithm on the host at frequency f:
+ * max |x_plan - x_netlist| / max(|x_netlist|, 1e-12 max|x_netlist|); 0 when the plan keeps the netlist order, negative
+ * when there is no plan.  A renumbered plan above 5e-10 at the pilot or either end of the sweep is not used by default. */
+double spicey_debug_band_order_deviation(const spicey_elem_table* table, double pilot_f, double f);
+
 /* Tooling (no device needed): the CUDA source NVRTC compiles for one band shape; returns the size needed.
  * abmask: bits 0-15 active border columns of band rows, bit 16: (alpha, beta)-only tables (RC circuits),
  * bits 17-18: how the pivot rows reach the workspace (0 plain stores, 1 paired 32-byte stores, 2 TMA tensor store). */

@@ -160,6 +160,45 @@ inline void run_pilot(int n, std::vector<std::complex<double>>& M, Pilot& P) {
   P.ok = true;
 }
 
+// The reference's whole solve (solveComplex.ts:15-72: elimination as run_pilot, back-substitution :55-72) of the dense
+// augmented matrix M[n][n+1]; false when a pivot trips one of its guards.
+inline bool solve_like_reference(int n, std::vector<std::complex<double>>& M, std::vector<std::complex<double>>& x) {
+  typedef std::complex<double> cd;
+  const double EPS = 1e-15;
+  const int ld = n + 1;
+  for (int k = 0; k < n; ++k) {
+    int imax = k;
+    double vmax = std::hypot(M[(size_t)k * ld + k].real(), M[(size_t)k * ld + k].imag());
+    for (int i = k + 1; i < n; ++i) {
+      const cd& z = M[(size_t)i * ld + k];
+      const double v = std::hypot(z.real(), z.imag());
+      if (v > vmax) { vmax = v; imax = i; }
+    }
+    if (vmax < EPS) return false;
+    if (imax != k) for (int j = 0; j <= n; ++j) std::swap(M[(size_t)k * ld + j], M[(size_t)imax * ld + j]);
+    const cd pivot = M[(size_t)k * ld + k];
+    if (std::norm(pivot) < EPS) return false;
+    for (int i = k + 1; i < n; ++i) {
+      const cd z = M[(size_t)i * ld + k];
+      if (z.real() == 0.0 && z.imag() == 0.0) continue;
+      const cd f = z / pivot;
+      if (std::abs(f) < EPS) continue;
+      for (int j = k; j <= n; ++j) {
+        const cd u = M[(size_t)k * ld + j];
+        if (u.real() != 0.0 || u.imag() != 0.0) M[(size_t)i * ld + j] -= f * u;
+      }
+    }
+  }
+  x.assign(n, cd(0, 0));
+  for (int i = n - 1; i >= 0; --i) {
+    cd acc = M[(size_t)i * ld + n];
+    for (int j = i + 1; j < n; ++j) acc -= M[(size_t)i * ld + j] * x[j];
+    if (std::norm(M[(size_t)i * ld + i]) < EPS) return false;
+    x[i] = acc / M[(size_t)i * ld + i];
+  }
+  return true;
+}
+
 }  // namespace band_detail
 
 // (L, RPL) for a measured half-bandwidth: W = L * RPL is a power of two >= max(2, bandwidth).
@@ -369,6 +408,39 @@ inline void build_band_plan(const BandInput& in, BandPlan& bp, int force_L = 0, 
     build_band_plan_for_order(in, rcm, bp, force_L, force_RPL);
     if (bp.ok) bp.renumbered = true;
   }
+}
+
+// What a renumbering costs in per-entry agreement with the reference.  A symmetric renumbering changes the elimination
+// order, not the exact solution; in floating point both orders are backward stable, i.e. equally good relative to the
+// LARGEST unknown, but the small unknowns of a strongly attenuating network (a node voltage 1e-6 of the source's) keep
+// their relative accuracy only along some orders.  The parity bar is per entry against the reference's order (1e-9), so
+// a plan that renumbers is checked before it is used: the reference's algorithm on the host in both orders at angular
+// frequency w, returns max_i |x_plan[i] - x_netlist[i]| / max(|x_netlist[i]|, 1e-12 max|x_netlist|), or a negative value
+// when either solve trips a guard.  (cfg 4's mesh: a few 1e-11; a random RC tree of 100 nodes with chords: 1e-6.)
+inline double band_order_deviation(const BandInput& in, const BandPlan& bp, double w) {
+  typedef std::complex<double> cd;
+  const int n = in.n, ld = n + 1;
+  if (!bp.ok || (int)bp.newvar.size() < n) return -1.0;
+  // compact permutation: rank of every original variable in the plan's (padded) elimination order
+  std::vector<int> by_new(n), rank(n);
+  for (int v = 0; v < n; ++v) by_new[v] = v;
+  std::sort(by_new.begin(), by_new.end(), [&](int a, int b) { return bp.newvar[a] < bp.newvar[b]; });
+  for (int i = 0; i < n; ++i) rank[by_new[i]] = i;
+  std::vector<cd> A((size_t)n * ld, cd(0, 0)), B((size_t)n * ld, cd(0, 0));
+  for (int r = 0; r < n; ++r)
+    for (int en = (*in.row_ptr)[r]; en < (*in.row_ptr)[r + 1]; ++en) {
+      const int c = (*in.ent_col)[en];
+      const cd v((*in.ent_alpha)[en] + (*in.ent_jre)[en], w * (*in.ent_beta)[en] - (*in.ent_gamma)[en] / w + (*in.ent_jim)[en]);
+      A[(size_t)r * ld + c] += v;
+      B[(size_t)rank[r] * ld + (c < n ? rank[c] : n)] += v;
+    }
+  std::vector<cd> xa, xb;
+  if (!band_detail::solve_like_reference(n, A, xa) || !band_detail::solve_like_reference(n, B, xb)) return -1.0;
+  double big = 0.0;
+  for (int i = 0; i < n; ++i) big = std::max(big, std::abs(xa[i]));
+  double dev = 0.0;
+  for (int i = 0; i < n; ++i) dev = std::max(dev, std::abs(xb[rank[i]] - xa[i]) / std::max(std::abs(xa[i]), 1e-12 * big));
+  return dev;
 }
 
 }  // namespace spicey

@@ -130,6 +130,7 @@ struct DeviceCtx {
   uint64_t bp_key = 0;        // sparse-program key the band plan was built for (0 = none)
   bool bp_valid = false;
   Buffer bp_blob, bp_work;
+  double bp_order_dev = 0;   // band_order_deviation of the last renumbered plan
   struct BandDev { const void *tab, *flags, *newvar, *el_rec; } bp_dev = {nullptr, nullptr, nullptr, nullptr};
   struct BandJit {
     cudaLibrary_t lib = nullptr;
@@ -160,6 +161,7 @@ struct DeviceCtx {
                               // bit 3 the one-warp-per-system kernel (Nvar <= 32)
   std::string tl_note;
   double sp_pilot_f = 0;      // frequency of the pilot point the cached programs were built from
+  double sp_f_lo = 0, sp_f_hi = 0;   // first / last frequency of the call that built them (0: unknown)
   uint64_t plan_up_key = 0;   // plan currently resident in `plan` (its device pointers are in plan_dp)
   DevPlan plan_dp;
   JitVariant tr_jit[2];   // compiled transient kernel of the last topology: [0] without, [1] with element currents
@@ -677,6 +679,7 @@ struct BandArgs {   // must match band_kernel.cuh
 // 200,000 points: mesh4 (W 4) 567 against 440 M solves/s, mesh6 138 / 97, mesh8 87 / 25, mesh16 11.9 / 1.45; but mesh3 (W 3)
 // 735 / 1,124 and the 400-node ladder (W 1) 14 / 38: a step of the band kernel costs ~150 instructions whatever the width)
 constexpr int kBandMinBandwidth = 4;
+constexpr double kBandOrderTol = 5e-10;   // per-entry agreement of a renumbered plan with the netlist order (parity bar: 1e-9)
 constexpr int kBandUModeDefault = 2;   // band_kernel.cuh BAND_UMODE: the pivot rows leave through the TMA unit
 
 void band_input(const HostPlan& hp, const SparseProgram& sp, double pilot_f, BandInput& in) {
@@ -708,6 +711,21 @@ int prepare_band(DeviceCtx& ctx, const HostPlan& hp, cudaStream_t stream, bool f
   build_band_plan(in, ctx.bp, fl, fr);
   BandPlan& bp = ctx.bp;
   if (!bp.ok || (bp.bandwidth < kBandMinBandwidth && !force)) return SPICEY_SUCCESS;
+  // A renumbered plan eliminates in another order than the reference: before it becomes the default for a topology,
+  // the reference's algorithm is run on the host in both orders at the pilot frequency and at both ends of the sweep
+  // (band_plan.h: band_order_deviation); a plan whose solution differs per entry by more than kBandOrderTol — strongly
+  // attenuating networks whose small node voltages keep their relative accuracy only in the netlist order — is declined
+  // (SPICEY_FLAG_BAND still forces it).  cfg 4's mesh: a few 1e-11.
+  if (bp.renumbered && !force) {
+    double worst = 0.0;
+    for (double f : {ctx.sp_pilot_f, ctx.sp_f_lo, ctx.sp_f_hi}) {
+      if (!(f > 0.0)) continue;
+      const double d = band_order_deviation(in, bp, (2 * kPi) * f);
+      worst = std::max(worst, d < 0.0 ? 1.0 : d);
+    }
+    ctx.bp_order_dev = worst;
+    if (worst > kBandOrderTol) return SPICEY_SUCCESS;
+  }
   // element records of the unpack phase: current = Y (x[i1] - x[i2]) in elimination-order indices, index n = the
   // zero slot (ground; bp.n counts the padding rows of the band); a V element's current is its branch unknown:
   // (branch, zero slot, Y = 1)
@@ -1367,7 +1385,8 @@ int launch_ac_dense(DeviceCtx& ctx, const HostPlan& hp, const DevPlan& dp, const
 
 // Dispatcher: sparse program path for a large single-instance sweep, dense pivoting kernel otherwise.
 int launch_ac(DeviceCtx& ctx, const HostPlan& hp, const DevPlan& dp, const AcArgs& args, uint32_t flags,
-              cudaStream_t stream, int* tier_out, int64_t* launches, double pilot_f, bool pilot_known) {
+              cudaStream_t stream, int* tier_out, int64_t* launches, double pilot_f, bool pilot_known, double f_lo = 0.0,
+              double f_hi = 0.0) {
   const bool want_sparse = !(flags & (SPICEY_FLAG_STRICT | SPICEY_FLAG_FORCE_GMEM | SPICEY_FLAG_DENSE)) &&
                            (args.p_count >= kSparseMinPoints || (flags & SPICEY_FLAG_SPARSE));
   if (want_sparse) {
@@ -1377,13 +1396,16 @@ int launch_ac(DeviceCtx& ctx, const HostPlan& hp, const DevPlan& dp, const AcArg
     if (eager && hp.nI > 0) return launch_ac_dense(ctx, hp, dp, args, flags, stream, tier_out, launches);
     const uint64_t key = plan_key(hp) ^ (eager ? 0x9e3779b97f4a7c15ull : 0ull);
     if (ctx.sp_key != key) {
-      if (!pilot_known) {  // device-resident frequencies: fetch one representative value
-        const long long mid = eager ? args.n_freq / 2 : args.p_begin + args.p_count / 2;
-        CUDA_TRY(cudaMemcpyAsync(&pilot_f, args.freqs + mid, sizeof(double), cudaMemcpyDeviceToHost, stream));
+      if (!pilot_known) {  // device-resident frequencies: fetch a representative value and both ends
+        const long long first = eager ? 0 : args.p_begin, count = eager ? args.n_freq : args.p_count;
+        CUDA_TRY(cudaMemcpyAsync(&pilot_f, args.freqs + first + count / 2, sizeof(double), cudaMemcpyDeviceToHost, stream));
+        CUDA_TRY(cudaMemcpyAsync(&f_lo, args.freqs + first, sizeof(double), cudaMemcpyDeviceToHost, stream));
+        CUDA_TRY(cudaMemcpyAsync(&f_hi, args.freqs + first + count - 1, sizeof(double), cudaMemcpyDeviceToHost, stream));
         CUDA_TRY(cudaStreamSynchronize(stream));
       }
       int rc = prepare_sparse(ctx, hp, pilot_f, eager, stream);
       if (rc) return rc;
+      ctx.sp_f_lo = f_lo; ctx.sp_f_hi = f_hi;
     }
     // Once per cached program: how did the pilot order hold up so far?  When a quarter of the points launched through
     // it came back on the fallback list, the program tiers only add their own pass in front of the dense solve: later
@@ -1836,7 +1858,7 @@ int32_t spicey_ac_solve(spicey_handle* h, const spicey_elem_table* table, const 
       a.status = (int*)ctx.out_s[b].p; a.scratch = nullptr; a.plist = nullptr; a.pcount = nullptr; a.fb_total = nullptr;
       a.series_ld = series ? cld : 0;
       CUDA_TRY(cudaEventRecord(ks, ctx.compute));
-      rc = launch_ac(ctx, hp, dp, a, flags, ctx.compute, &tier, &launches, freqs[n_freq / 2], true);
+      rc = launch_ac(ctx, hp, dp, a, flags, ctx.compute, &tier, &launches, freqs[n_freq / 2], true, freqs[0], freqs[n_freq - 1]);
       if (rc) return rc;
       CUDA_TRY(cudaEventRecord(ke, ctx.compute));
       CUDA_TRY(cudaStreamWaitEvent(ctx.copy, ke, 0));
@@ -2209,6 +2231,20 @@ int32_t spicey_debug_warp_stats(const spicey_elem_table* table, double pilot_f, 
   out[0] = wp.n; out[1] = wp.n_pool; out[2] = wp.n_gslots; out[3] = wp.max_elim;
   out[4] = (int32_t)wp.n_upd_total; out[5] = (int32_t)chunks; out[6] = (int32_t)wp.colent.size(); out[7] = sp.n_slots;
   return SPICEY_SUCCESS;
+}
+
+double spicey_debug_band_order_deviation(const spicey_elem_table* table, double pilot_f, double f) {
+  HostPlan hp;
+  if (build_plan(table, nullptr, hp) != SPICEY_SUCCESS) return -1.0;
+  SparseProgram sp;
+  build_sparse_host(hp, pilot_f, false, sp);
+  if (!sp.ok) return -1.0;
+  BandInput in;
+  band_input(hp, sp, pilot_f, in);
+  BandPlan bp;
+  build_band_plan(in, bp);
+  if (!bp.ok) return -1.0;
+  return bp.renumbered ? band_order_deviation(in, bp, (2 * kPi) * f) : 0.0;
 }
 
 int32_t spicey_debug_band_stats(const spicey_elem_table* table, double pilot_f, int32_t* out) {

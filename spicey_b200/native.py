@@ -30,7 +30,7 @@ EXPORTS = [
     "spicey_ac_solve_device", "spicey_tran_solve", "spicey_tran_solve_device", "spicey_measure_fp64_peak",
     "spicey_debug_sparse_source", "spicey_series_ld", "spicey_debug_tran_source", "spicey_debug_warp_stats",
     "spicey_tran_solve_waves", "spicey_tran_solve_waves_device", "spicey_debug_tran_source_waves",
-    "spicey_debug_band_stats", "spicey_debug_band_source", "spicey_debug_tile_source",
+    "spicey_debug_band_stats", "spicey_debug_band_source", "spicey_debug_tile_source", "spicey_debug_band_order_deviation",
     "spicey_debug_warp_lu_source", "spicey_tran_solve_probes",
 ]
 WAVE_DC, WAVE_TABLE, WAVE_PULSE, WAVE_PWL = 0, 1, 2, 3
@@ -164,6 +164,16 @@ def band_plan_stats(table: "ElemTable", pilot_f: float = 1000.0) -> dict:
     keys = ("window", "lanes", "rows_per_lane", "bandwidth", "renumbered", "border_rows", "border_col_mask",
             "workspace_values")
     return dict(zip(keys, list(st)))
+
+
+def band_order_deviation(table: "ElemTable", pilot_f: float, f: float) -> float:
+    """Per-entry distance between the solutions in the banded plan's order and in the netlist order at frequency f
+    (host only; band_plan.h: band_order_deviation)."""
+    lib = load_library()
+    lib.spicey_debug_band_order_deviation.restype = C.c_double
+    lib.spicey_debug_band_order_deviation.argtypes = [C.POINTER(type(table.struct())), C.c_double, C.c_double]
+    ts = table.struct()
+    return float(lib.spicey_debug_band_order_deviation(C.byref(ts), pilot_f, f))
 
 
 def band_kernel_source(lanes=8, rows_per_lane=2, border_rows=1, border_col_mask=0, with_ielem=True, warps=4,

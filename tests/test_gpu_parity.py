@@ -896,6 +896,31 @@ def test_ac_band_tier_tensor_store_equals_plain_stores(name, text, monkeypatch):
         assert np.array_equal(res["2"][key], res["0"][key]), (name, key)
 
 
+def test_attenuating_network_keeps_the_netlist_order(eng):
+    """A random RC tree with chords (60 nodes; at 100 kHz its far nodes sit 1e-12 below the source) qualifies for the
+    banded tier only after a renumbering, and in that order its small unknowns lose per-entry agreement with the
+    reference (1e-8; 3e-13 relative to the largest unknown).  The host checks a renumbered plan against the netlist order
+    before using it (band_plan.h: band_order_deviation) and leaves this circuit to a tier that eliminates in the
+    reference's order: EVERY entry within 1e-9 of the oracle.  SPICEY_FLAG_BAND still forces the banded tier, whose
+    result is then as good as backward stability makes it."""
+    import spicey_b200 as sp
+    from test_band_plan_host import _rc_tree
+    text = _rc_tree(60, ppd=600)
+    ck = parse_netlist(text)
+    freqs = np.array(sp.analysis.ac_frequencies(ck))
+    xr, ier, st = co.ac_solve(ck, freqs, nthreads=8)
+    assert st.max() == 0
+    out = sp.simulate_ac_batch(ck, freqs, engine=eng, flags=native.FLAG_SPARSE | native.FLAG_JIT)
+    stt = eng.stats()
+    assert stt["tier"] != native.TIER_BAND, stt
+    assert out["status"].max() == 0
+    assert np.max(np.abs(out["x"][0] - xr) / np.abs(xr)) <= AC_TOL
+    assert np.max(np.abs(out["ielem"][0] - ier) / np.maximum(np.abs(ier), 1e-300)) <= AC_TOL
+    forced = sp.simulate_ac_batch(ck, freqs, engine=eng, flags=BAND)
+    assert eng.stats()["tier"] == native.TIER_BAND and forced["status"].max() == 0
+    assert np.max(np.abs(forced["x"][0] - xr) / np.max(np.abs(xr), axis=1, keepdims=True)) <= 1e-11
+
+
 def test_ac_band_tier_pivot_changes_fall_back(eng):
     """An RLC ladder with two sources swept over seven decades: the pivot order of the pilot point does not hold
     everywhere, those points go to the dense kernel; statuses and values equal the oracle's either way."""

@@ -1,7 +1,8 @@
 #!/usr/bin/env python3
-"""GPU: RC ladders past cfg 2's size through the compiled straight-line tier (tier 5, with its global column) against the
-interpreted program (tier 4) of the same topology: M solves/s and the error against the strict dense kernel on a subsample.
-   usage: ladder_probe.py 100 150 200 ...     LADDER_P points (default 1,000,000)"""
+"""GPU: RC ladders past cfg 2's size (and random sparse RC networks: a resistor tree + N/4 chords, every node with a
+capacitor) through the compiled straight-line tier (tier 5, with its global column) against the interpreted program
+(tier 4) of the same topology: M solves/s and the error against the strict dense kernel on a subsample.
+   usage: ladder_probe.py 100 150 tree80 tree120 ...     LADDER_P points (default 1,000,000)"""
 import os
 import sys
 import time
@@ -19,8 +20,23 @@ def main():
     P = int(os.environ.get("LADDER_P", "1000000"))
     dev = torch.device("cuda", 0)
     stream = torch.cuda.current_stream()
-    for n in [int(a) for a in sys.argv[1:]] or [100, 150, 200]:
-        ck = parsing.parse_netlist(workloads.rc_ladder(n, ppd=max(1, P // 5)))
+    for arg in sys.argv[1:] or ["100", "150", "200"]:
+        if arg.startswith("tree"):
+            n = int(arg[4:])
+            rng = np.random.default_rng(n)
+            lines = ["* random sparse RC network", "v1 n1 0 dc 1 ac 1"]
+            for i in range(2, n + 1):
+                lines.append("r%d n%d n%d %g" % (i, i, rng.integers(1, i), rng.uniform(100, 1e4)))
+            for i in range(1, n + 1):
+                lines.append("c%d n%d 0 %g" % (i, i, rng.uniform(1e-9, 1e-7)))
+            for k in range(n // 4):
+                a, b = rng.choice(np.arange(1, n + 1), 2, replace=False)
+                lines.append("r%d n%d n%d %g" % (1000 + k, a, b, rng.uniform(100, 1e4)))
+            lines += [".ac dec %d 1 100k" % max(1, P // 5), ".end"]
+            ck = parsing.parse_netlist("\n".join(lines) + "\n")
+        else:
+            n = int(arg)
+            ck = parsing.parse_netlist(workloads.rc_ladder(n, ppd=max(1, P // 5)))
         freqs = np.ascontiguousarray(np.array(sp.analysis.ac_frequencies(ck), dtype=np.float64)[:P])
         table = packing.pack_circuit(ck)
         p = freqs.shape[0]
@@ -58,8 +74,8 @@ def main():
             err = max(float(np.max(np.abs(x - x0.reshape(len(sub), -1)) / np.maximum(np.abs(x0.reshape(len(sub), -1)), 1e-300))),
                       float(np.max(np.abs(ie - i0.reshape(len(sub), -1)) / np.maximum(np.abs(i0.reshape(len(sub), -1)), 1e-300))))
             bytes_per = 8 + 16 * (table.nvar + table.n_ac_elem)
-            print("ladder%-4d %-12s tier=%d fb=%d  first call %.1f s  ms min = %.3f  %.1f M solves/s  %.0f GB/s of results  relerr=%.2e" % (
-                n, name, st["tier"], st["fallback_solves"], first, min(ts), p / min(ts) / 1e3, p / min(ts) / 1e3 * bytes_per / 1e3, err), flush=True)
+            print("%-10s %-12s tier=%d fb=%d  first call %.1f s  ms min = %.3f  %.1f M solves/s  %.0f GB/s of results  relerr=%.2e" % (
+                arg if arg.startswith("tree") else "ladder" + arg, name, st["tier"], st["fallback_solves"], first, min(ts), p / min(ts) / 1e3, p / min(ts) / 1e3 * bytes_per / 1e3, err), flush=True)
             eng.close()
 
 
