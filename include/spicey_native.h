@@ -289,7 +289,8 @@ enum {
   SPICEY_FLAG_WARP = 512u,         /* AC: use the warp-per-system sparse tier even for small programs (testing) */
   SPICEY_FLAG_NO_WARP = 1024u,     /* AC: never use the warp-per-system sparse tier */
   SPICEY_FLAG_NO_JIT = 256u,       /* never compile: interpreted sparse program (AC), generic kernels (TRAN) */
-  SPICEY_FLAG_BAND = 2048u,        /* AC: use the banded + bordered tier even for small batches / small programs (testing) */
+  SPICEY_FLAG_BAND = 2048u,        /* AC: use the banded + bordered tier even for small batches / small programs, and even when
+                                      its renumbered order fails the per-entry check against the netlist order (testing) */
   SPICEY_FLAG_NO_BAND = 4096u,     /* AC: never use the banded + bordered tier */
   SPICEY_FLAG_TILE = 8192u,        /* AC: use the dense register-tile tier even for small batches / sparse circuits (testing) */
   SPICEY_FLAG_NO_TILE = 16384u,    /* AC: never use the dense register-tile tier */
