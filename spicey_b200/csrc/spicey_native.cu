@@ -721,7 +721,7 @@ int prepare_band(DeviceCtx& ctx, const HostPlan& hp, cudaStream_t stream, bool f
     for (double f : {ctx.sp_pilot_f, ctx.sp_f_lo, ctx.sp_f_hi}) {
       if (!(f > 0.0)) continue;
       const double d = band_order_deviation(in, bp, (2 * kPi) * f);
-      worst = std::max(worst, d < 0.0 ? 1.0 : d);
+      worst = std::max(worst, (d < 0.0 || d != d) ? 1.0 : d);   // a guard tripped / NaN: no evidence, no renumbering
     }
     ctx.bp_order_dev = worst;
     if (worst > kBandOrderTol) return SPICEY_SUCCESS;
